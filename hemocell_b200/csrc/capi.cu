@@ -1,0 +1,681 @@
+// C ABI of libhemocell_gpu.so (include/hemocell_gpu.h): context lifetime, up/downloads,
+// the iterate() scheduler (reference core/hemoCell.cpp:299-376) and per-operator entry points.
+#include "ctx.cuh"
+#include <nccl.h>
+#include <algorithm>
+#include <cstring>
+#include <cstdio>
+
+hcg_status lat_pad3(hcg_ctx* c, const double* src_dev, double* dst);
+hcg_status lat_unpad(hcg_ctx* c, const double* src, double* dst_dev, int ncomp);
+
+static thread_local std::string g_create_error;
+
+hcg_status hcg_fail(hcg_ctx* c, hcg_status code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+namespace {
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1)/t); }
+
+__global__ void k_aos_to_soa(const double* __restrict__ in, double* x, double* y, double* z, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  x[i] = in[3*i]; y[i] = in[3*i+1]; z[i] = in[3*i+2];
+}
+__global__ void k_soa_to_aos(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                             double* out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[3*i] = x[i]; out[3*i+1] = y[i]; out[3*i+2] = z[i];
+}
+__global__ void k_add_force(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ f,
+                            double* fx, double* fy, double* fz, int64_t np) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = idx[i];
+  if (p < 0 || p >= np) return;
+  atomicAdd(fx + p, f[3*i]); atomicAdd(fy + p, f[3*i+1]); atomicAdd(fz + p, f[3*i+2]);
+}
+__global__ void k_pad_flags(const uint8_t* __restrict__ src, uint8_t* dst, int64_t Nl, int64_t P) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < Nl) dst[i + P] = src[i];
+}
+__global__ void k_count_alive(const uint8_t* __restrict__ alive, const int32_t* __restrict__ ctype,
+                              const int* __restrict__ typeV, int64_t n, unsigned long long* out) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n || !alive[i]) return;
+  atomicAdd(out, 1ULL); atomicAdd(out + 1, (unsigned long long)typeV[ctype[i]]);
+}
+
+hcg_status ensure_staging(hcg_ctx* c, size_t bytes) {
+  if (c->staging_bytes >= bytes) return HCG_OK;
+  if (c->staging) cudaFree(c->staging);
+  c->staging = nullptr; c->staging_bytes = 0;
+  CUDA_TRY(c, cudaMalloc(&c->staging, bytes));
+  c->staging_bytes = bytes;
+  return HCG_OK;
+}
+
+template <class T> hcg_status upload_table(hcg_ctx* c, CellTypeHost& th, T** dst, const T* src, size_t n) {
+  const size_t bytes = sizeof(T)*(n > 0 ? n : 1);
+  CUDA_TRY(c, cudaMalloc(dst, bytes));
+  th.allocs.push_back(*dst);
+  if (n > 0) CUDA_TRY(c, cudaMemcpy(*dst, src, sizeof(T)*n, cudaMemcpyHostToDevice));
+  return HCG_OK;
+}
+
+hcg_status exchange_flags(hcg_ctx* c) {
+  const int R = c->dom.n_ranks, r = c->dom.rank; const bool px = c->dom.periodic[0];
+  const int64_t P = c->P;
+  // default: ghost planes are non-fluid (outside a non-periodic domain)
+  CUDA_TRY(c, cudaMemsetAsync(c->flags, HCG_BOUNCEBACK, P, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->flags + (int64_t)(c->nxl+1)*P, HCG_BOUNCEBACK, P, c->stream));
+  if (R == 1) {
+    if (px) {
+      CUDA_TRY(c, cudaMemcpyAsync(c->flags, c->flags + (int64_t)c->nxl*P, P, cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_TRY(c, cudaMemcpyAsync(c->flags + (int64_t)(c->nxl+1)*P, c->flags + P, P, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return HCG_OK;
+  }
+  if (!c->nccl) return HCG_OK;     // done again from hcg_comm_init
+  ncclComm_t comm = (ncclComm_t)c->nccl;
+  const int left = (r == 0) ? (px ? R - 1 : -1) : r - 1;
+  const int right = (r == R - 1) ? (px ? 0 : -1) : r + 1;
+  ncclGroupStart();
+  if (left >= 0) ncclSend(c->flags + P, P, ncclUint8, left, comm, c->stream);
+  if (right >= 0) ncclSend(c->flags + (int64_t)c->nxl*P, P, ncclUint8, right, comm, c->stream);
+  if (right >= 0) ncclRecv(c->flags + (int64_t)(c->nxl+1)*P, P, ncclUint8, right, comm, c->stream);
+  if (left >= 0) ncclRecv(c->flags, P, ncclUint8, left, comm, c->stream);
+  ncclResult_t rc = ncclGroupEnd();
+  if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("flag exchange: ") + ncclGetErrorString(rc));
+  return HCG_OK;
+}
+
+struct OpTimer {
+  hcg_ctx* c; const char* name; bool on;
+  OpTimer(hcg_ctx* c_, const char* n) : c(c_), name(n), on(c_->timers_on) { if (on) cudaEventRecord(c->ev_a, c->stream); }
+  ~OpTimer() {
+    if (!on) return;
+    cudaEventRecord(c->ev_b, c->stream); cudaEventSynchronize(c->ev_b);
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+    auto it = c->timer_idx.find(name);
+    int k;
+    if (it == c->timer_idx.end()) { k = (int)c->timers.size(); c->timers.push_back({name, 0.0, 0}); c->timer_idx[name] = k; }
+    else k = it->second;
+    c->timers[k].ms += ms; c->timers[k].calls++;
+  }
+};
+
+hcg_status do_mechanics(hcg_ctx* c, bool forced, bool components) {
+  OpTimer t(c, "applyConstitutiveModel");
+  for (size_t k = 0; k < c->types.size(); k++) {
+    if (forced || c->iter % c->types[k].timescale == 0) {      // hemoCellParticleField.cpp:655
+      hcg_status s = mech_apply(c, (int)k, components); if (s) return s;
+    }
+  }
+  return HCG_OK;
+}
+
+// one HemoCell::iterate() (core/hemoCell.cpp:299-376)
+hcg_status step(hcg_ctx* c) {
+  hcg_status s;
+  const bool have_p = c->np > 0;
+  if (have_p && c->rep_on && c->iter % c->ts_rep == 0) { OpTimer t(c, "applyRepulsionForce"); if ((s = rep_apply(c))) return s; }
+  if (have_p && c->wall_on && c->iter % c->ts_wall == 0) { OpTimer t(c, "applyBoundaryRepulsionForce"); if ((s = rep_wall_apply(c))) return s; }
+  if (have_p) { OpTimer t(c, "spreadParticleForce"); if ((s = ibm_spread(c))) return s; }
+  const bool interp = have_p && (c->iter % c->ts_vel == 0);
+  { OpTimer t(c, "collideAndStream"); if ((s = lat_collide_stream(c, !interp))) return s; }
+  if (interp) {
+    { OpTimer t(c, "interpolateFluidVelocity"); if ((s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate(c))) return s; }
+    { OpTimer t(c, "advanceParticles"); if ((s = ibm_advance(c))) return s; }
+  } else if (have_p) {
+    OpTimer t(c, "advanceParticles"); if ((s = ibm_advance(c))) return s;
+  }
+  if (have_p && (s = do_mechanics(c, false, false))) return s;
+  c->iter++;
+  return HCG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hcg_last_error(const hcg_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+const char* hcg_version(void) { return "hemocell_b200 0.1 (sm_100a)"; }
+
+hcg_status hcg_create(const hcg_domain* d, hcg_ctx** out) {
+  if (!d || !out) return hcg_fail(nullptr, HCG_ERR_ARG, "null argument");
+  if (d->nx < 1 || d->ny < 3 || d->nz < 3) return hcg_fail(nullptr, HCG_ERR_ARG, "lattice too small");
+  if (d->n_ranks < 1 || d->rank < 0 || d->rank >= d->n_ranks || d->nx % d->n_ranks)
+    return hcg_fail(nullptr, HCG_ERR_ARG, "bad rank/n_ranks (nx must be divisible by n_ranks)");
+  if (!(d->tau > 0.5)) return hcg_fail(nullptr, HCG_ERR_ARG, "tau must be > 0.5");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return hcg_fail(nullptr, HCG_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (d->device < 0 || d->device >= ndev) return hcg_fail(nullptr, HCG_ERR_ARG, "bad device ordinal");
+  hcg_ctx* c = new hcg_ctx();
+  c->dom = *d;
+  c->nxl = d->nx / d->n_ranks; c->x0 = c->nxl * d->rank;
+  if (d->n_ranks > 1 && c->nxl < 3) { delete c; return hcg_fail(nullptr, HCG_ERR_ARG, "slab thinner than 3 planes"); }
+  c->P = (int64_t)d->ny * d->nz; c->S = (int64_t)(c->nxl + 2) * c->P; c->Nl = (int64_t)c->nxl * c->P;
+  c->omega = 1.0 / d->tau;
+  memset(c->bc_vel, 0, sizeof(c->bc_vel)); memset(c->body, 0, sizeof(c->body));
+  c->f_limit = 1e300;
+  c->cur = 0; c->u_valid = false; c->has_velbc = false; c->rho = nullptr;
+  c->np = c->ncells = c->cap_p = c->cap_c = 0;
+  for (int k = 0; k < 3; k++) c->pos[k] = c->vel[k] = c->frc[k] = c->frep[k] = nullptr;
+  memset(c->comp, 0, sizeof(c->comp)); c->comp_alloc = false;
+  c->p_cell = nullptr; c->cell_alive = nullptr; c->cell_type = nullptr; c->cell_base = nullptr;
+  c->rep_on = c->wall_on = false; c->rep_k = c->rep_cut = c->wall_k = c->wall_cut = 0.0;
+  c->ts_vel = c->ts_rep = c->ts_wall = 1;
+  c->bin_count = c->bin_start = c->bin_items = nullptr; c->wall_nodes = nullptr; c->n_wall = 0; c->wall_built = false;
+  c->scan_tmp = nullptr; c->scan_tmp_bytes = 0;
+  c->iter = 0; c->nccl = nullptr; c->timers_on = false; c->launches = 0;
+  c->staging = nullptr; c->staging_bytes = 0;
+  c->halo_send[0] = c->halo_send[1] = c->halo_recv[0] = c->halo_recv[1] = nullptr;
+  *out = c;
+  CUDA_TRY(c, cudaSetDevice(d->device));
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream_halo, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaEventCreate(&c->ev_a)); CUDA_TRY(c, cudaEventCreate(&c->ev_b));
+  CUDA_TRY(c, cudaMalloc(&c->g[0], sizeof(double)*19*c->S));
+  CUDA_TRY(c, cudaMalloc(&c->g[1], sizeof(double)*19*c->S));
+  CUDA_TRY(c, cudaMalloc(&c->F, sizeof(double)*3*c->S));
+  CUDA_TRY(c, cudaMalloc(&c->U, sizeof(double)*3*c->S));
+  CUDA_TRY(c, cudaMalloc(&c->flags, c->S));
+  CUDA_TRY(c, cudaMalloc(&c->d_bc, sizeof(double)*18));
+  CUDA_TRY(c, cudaMemsetAsync(c->d_bc, 0, sizeof(double)*18, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->g[0], 0, sizeof(double)*19*c->S, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->g[1], 0, sizeof(double)*19*c->S, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->F, 0, sizeof(double)*3*c->S, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->U, 0, sizeof(double)*3*c->S, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->flags, HCG_FLUID, c->S, c->stream));
+  hcg_status s = exchange_flags(c); if (s) return s;
+  const double u0[3] = {0, 0, 0};
+  if (d->n_ranks == 1) { s = lat_init_equilibrium(c, 1.0, u0); if (s) return s; }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+void hcg_destroy(hcg_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->dom.device);
+  cudaDeviceSynchronize();
+  if (c->nccl) ncclCommDestroy((ncclComm_t)c->nccl);
+  cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); cudaFree(c->flags); cudaFree(c->d_bc);
+  if (c->rho) cudaFree(c->rho);
+  for (int k = 0; k < 3; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->frc[k]); cudaFree(c->frep[k]); }
+  for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) if (c->comp[k][d]) cudaFree(c->comp[k][d]);
+  cudaFree(c->p_cell); cudaFree(c->cell_alive); cudaFree(c->cell_type); cudaFree(c->cell_base);
+  cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->bin_items); cudaFree(c->wall_nodes); cudaFree(c->scan_tmp);
+  cudaFree(c->staging);
+  for (auto& t : c->types) for (void* p : t.allocs) cudaFree(p);
+  cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
+  cudaStreamDestroy(c->stream); cudaStreamDestroy(c->stream_halo);
+  delete c;
+}
+
+hcg_status hcg_comm_unique_id(void* out128) {
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return hcg_fail(nullptr, HCG_ERR_NCCL, "ncclGetUniqueId failed");
+  static_assert(sizeof(ncclUniqueId) == 128, "unique id size");
+  memcpy(out128, &id, 128);
+  return HCG_OK;
+}
+
+hcg_status hcg_comm_init(hcg_ctx* c, const void* id128) {
+  if (!c || !id128) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (c->dom.n_ranks == 1) return HCG_OK;
+  ncclUniqueId id; memcpy(&id, id128, 128);
+  ncclComm_t comm;
+  ncclResult_t rc = ncclCommInitRank(&comm, c->dom.n_ranks, id, c->dom.rank);
+  if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(rc));
+  c->nccl = comm;
+  hcg_status s = exchange_flags(c); if (s) return s;
+  const double u0[3] = {0, 0, 0};
+  s = lat_init_equilibrium(c, 1.0, u0); if (s) return s;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_lattice_set_flags(hcg_ctx* c, const uint8_t* flags) {
+  if (!c || !flags) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  bool vel = false;
+  for (int64_t i = 0; i < c->Nl; i++) {
+    if (flags[i] > HCG_VEL_ZP) return hcg_fail(c, HCG_ERR_ARG, "unknown node flag");
+    vel = vel || flags[i] >= HCG_VEL_XN;
+  }
+  c->has_velbc = vel;
+  hcg_status s = ensure_staging(c, c->Nl); if (s) return s;
+  CUDA_TRY(c, cudaMemcpyAsync(c->staging, flags, c->Nl, cudaMemcpyHostToDevice, c->stream));
+  k_pad_flags<<<nblk(c->Nl, 256), 256, 0, c->stream>>>((const uint8_t*)c->staging, c->flags, c->Nl, c->P);
+  KERNEL_CHECK(c);
+  s = exchange_flags(c); if (s) return s;
+  c->wall_built = false;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_lattice_set_bc_velocity(hcg_ctx* c, int32_t o, const double u[3]) {
+  if (!c || !u || o < 0 || o > 5) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  for (int k = 0; k < 3; k++) c->bc_vel[o][k] = u[k];
+  CUDA_TRY(c, cudaMemcpy(c->d_bc, c->bc_vel, sizeof(c->bc_vel), cudaMemcpyHostToDevice));
+  return HCG_OK;
+}
+
+hcg_status hcg_lattice_init_equilibrium(hcg_ctx* c, double rho, const double u[3]) {
+  if (!c || !u) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  hcg_status s = lat_init_equilibrium(c, rho, u); if (s) return s;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_lattice_set_body_force(hcg_ctx* c, const double f[3]) {
+  if (!c || !f) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  for (int k = 0; k < 3; k++) c->body[k] = f[k];
+  hcg_status s = lat_reset_force(c); if (s) return s;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_lattice_upload(hcg_ctx* c, int32_t field, const double* in) {
+  if (!c || !in) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  hcg_status s;
+  if (field == HCG_LAT_POP) {
+    if ((s = ensure_staging(c, sizeof(double)*19*c->Nl))) return s;
+    CUDA_TRY(c, cudaMemcpyAsync(c->staging, in, sizeof(double)*19*c->Nl, cudaMemcpyHostToDevice, c->stream));
+    if ((s = lat_pop_from_reference(c, c->staging))) return s;
+  } else if (field == HCG_LAT_FORCE) {
+    if ((s = ensure_staging(c, sizeof(double)*3*c->Nl))) return s;
+    CUDA_TRY(c, cudaMemcpyAsync(c->staging, in, sizeof(double)*3*c->Nl, cudaMemcpyHostToDevice, c->stream));
+    if ((s = lat_pad3(c, c->staging, c->F))) return s;
+  } else return hcg_fail(c, HCG_ERR_ARG, "lattice_upload: field must be POP or FORCE");
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_lattice_download(hcg_ctx* c, int32_t field, double* out) {
+  if (!c || !out) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  hcg_status s;
+  if (field == HCG_LAT_POP) {
+    if ((s = ensure_staging(c, sizeof(double)*19*c->Nl))) return s;
+    if ((s = lat_pop_to_reference(c, c->staging))) return s;
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*19*c->Nl, cudaMemcpyDeviceToHost, c->stream));
+  } else if (field == HCG_LAT_FORCE) {
+    if ((s = ensure_staging(c, sizeof(double)*3*c->Nl))) return s;
+    if ((s = lat_unpad(c, c->F, c->staging, 3))) return s;
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*3*c->Nl, cudaMemcpyDeviceToHost, c->stream));
+  } else if (field == HCG_LAT_VELOCITY || field == HCG_LAT_DENSITY) {
+    // Cell::computeVelocity / computeDensity of the current populations and node force
+    if ((s = lat_moments(c, false, true))) return s;
+    if ((s = ensure_staging(c, sizeof(double)*3*c->Nl))) return s;
+    if (field == HCG_LAT_VELOCITY) {
+      if ((s = lat_unpad(c, c->U, c->staging, 3))) return s;
+      CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*3*c->Nl, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+      if ((s = lat_unpad(c, c->rho, c->staging, 1))) return s;
+      CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*c->Nl, cudaMemcpyDeviceToHost, c->stream));
+    }
+  } else return hcg_fail(c, HCG_ERR_ARG, "lattice_download: unknown field");
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_celltype_add(hcg_ctx* c, const hcg_celltype* t, int32_t* ctype_out) {
+  if (!c || !t) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (c->types.size() >= HCG_MAX_TYPES) return hcg_fail(c, HCG_ERR_CAPACITY, "too many cell types");
+  if (t->model != HCG_MODEL_RBC_HIGHORDER && t->model != HCG_MODEL_PLT_SIMPLE) return hcg_fail(c, HCG_ERR_ARG, "unknown model");
+  const int V = t->n_vertices, T = t->n_triangles, E = t->n_edges, I = t->n_inner_edges;
+  if (V < 4 || T < 4 || E < 6 || I < 0) return hcg_fail(c, HCG_ERR_ARG, "degenerate mesh");
+  // ---- per-vertex gather tables
+  std::vector<int> vt(6*(size_t)V, -1), ve(6*(size_t)V, -1), vb(7*(size_t)V, -1), vpe(12*(size_t)V, -1), vin(4*(size_t)V, -1);
+  std::vector<int> nvt(V, 0), nve(V, 0), nvpe(V, 0), nvin(V, 0);
+  for (int k = 0; k < T; k++) for (int m = 0; m < 3; m++) {
+    const int v = t->triangles[3*k+m];
+    if (v < 0 || v >= V) return hcg_fail(c, HCG_ERR_ARG, "triangle index out of range");
+    if (nvt[v] >= 6) return hcg_fail(c, HCG_ERR_ARG, "vertex with more than 6 triangles");
+    vt[6*v + nvt[v]++] = k;
+  }
+  for (int e = 0; e < E; e++) for (int m = 0; m < 2; m++) {
+    const int v = t->edges[2*e+m];
+    if (v < 0 || v >= V) return hcg_fail(c, HCG_ERR_ARG, "edge index out of range");
+    if (nve[v] >= 6) return hcg_fail(c, HCG_ERR_ARG, "vertex with more than 6 edges");
+    ve[6*v + nve[v]++] = 2*e + m;
+  }
+  for (int v = 0; v < V; v++) {
+    const int nn = t->vertex_n_vertexes[v];
+    if (nn < 3 || nn > 6) return hcg_fail(c, HCG_ERR_ARG, "vertex ring size must be 3..6");
+    std::vector<int> s(t->vertex_vertexes + 6*v, t->vertex_vertexes + 6*v + nn);
+    s.push_back(v);
+    std::sort(s.begin(), s.end());
+    for (size_t k = 0; k < s.size(); k++) vb[7*v + k] = s[k];
+  }
+  if (t->model == HCG_MODEL_PLT_SIMPLE) {
+    for (int e = 0; e < E; e++) {
+      const int role_v[4] = {t->edges[2*e], t->edges[2*e+1], t->edge_bending_outer_points[2*e], t->edge_bending_outer_points[2*e+1]};
+      for (int r = 0; r < 4; r++) {
+        const int v = role_v[r];
+        if (v < 0 || v >= V) return hcg_fail(c, HCG_ERR_ARG, "bending point out of range");
+        if (nvpe[v] >= 12) return hcg_fail(c, HCG_ERR_ARG, "vertex touches more than 12 bending edges");
+        vpe[12*v + nvpe[v]++] = 4*e + r;
+      }
+    }
+    for (int e = 0; e < I; e++) for (int m = 0; m < 2; m++) {
+      const int v = t->inner_edges[2*e+m];
+      if (v < 0 || v >= V) return hcg_fail(c, HCG_ERR_ARG, "inner edge index out of range");
+      if (nvin[v] >= 4) return hcg_fail(c, HCG_ERR_ARG, "vertex with more than 4 inner edges");
+      vin[4*v + nvin[v]++] = 2*e + m;
+    }
+  }
+  CellTypeHost th;
+  CellTypeDev& d = th.d;
+  memset(&d, 0, sizeof(d));
+  d.model = t->model; d.V = V; d.T = T; d.E = E; d.I = I;
+  hcg_status s;
+#define UP(dst, src, n) if ((s = upload_table(c, th, &d.dst, src, (size_t)(n)))) return s
+  UP(tri, t->triangles, 3*T); UP(edge, t->edges, 2*E); UP(inner, t->inner_edges, 2*I);
+  UP(ring, t->vertex_vertexes, 6*V); UP(nring, t->vertex_n_vertexes, V);
+  UP(bend_tri, t->edge_bending_triangles, 2*E); UP(bend_outer, t->edge_bending_outer_points, 2*E);
+  UP(edge_len_eq, t->edge_length_eq, E); UP(edge_ang_eq, t->edge_angle_eq, E);
+  UP(tri_area_eq, t->triangle_area_eq, T); UP(patch_eq, t->patch_dist_eq, V); UP(inner_len_eq, t->inner_edge_length_eq, I);
+  UP(vt, vt.data(), vt.size()); UP(ve, ve.data(), ve.size()); UP(vb, vb.data(), vb.size());
+  UP(vpe, vpe.data(), vpe.size()); UP(vin, vin.data(), vin.size());
+#undef UP
+  d.volume_eq = t->volume_eq; d.area_mean_eq = t->area_mean_eq; d.edge_mean_eq = t->edge_mean_eq;
+  d.k_volume = t->k_volume; d.k_area = t->k_area; d.k_link = t->k_link; d.k_bend = t->k_bend; d.eta_m = t->eta_m;
+  th.first_cell = c->ncells; th.first_particle = c->np;
+  c->types.push_back(th);
+  if (ctype_out) *ctype_out = (int32_t)c->types.size() - 1;
+  return HCG_OK;
+}
+
+hcg_status hcg_celltype_set_stiffness(hcg_ctx* c, int32_t ctype, double kv, double ka, double kl, double kb, double eta) {
+  if (!c || ctype < 0 || ctype >= (int)c->types.size()) return HCG_ERR_ARG;
+  CellTypeDev& d = c->types[ctype].d;
+  d.k_volume = kv; d.k_area = ka; d.k_link = kl; d.k_bend = kb; d.eta_m = eta;
+  return HCG_OK;
+}
+
+hcg_status hcg_cells_add(hcg_ctx* c, int32_t ctype, int64_t n_cells, const int64_t* cell_id, const double* pos) {
+  if (!c || ctype < 0 || ctype >= (int)c->types.size() || n_cells < 0) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  for (size_t k = ctype + 1; k < c->types.size(); k++)
+    if (c->types[k].n_cells > 0) return hcg_fail(c, HCG_ERR_STATE, "cells must be added in cell-type order");
+  CellTypeHost& th = c->types[ctype];
+  if (th.n_cells > 0) return hcg_fail(c, HCG_ERR_STATE, "cells of a type must be added in one call");
+  if (n_cells == 0) return HCG_OK;
+  if (!cell_id || !pos) return HCG_ERR_ARG;
+  const int V = th.d.V;
+  const int64_t add_p = n_cells*V, new_p = c->np + add_p, new_c = c->ncells + n_cells;
+  if (new_p > 2000000000LL) return hcg_fail(c, HCG_ERR_CAPACITY, "more than 2e9 particles on one GPU");
+  // grow SoA arrays
+  auto grow = [&](double** arr) -> cudaError_t {
+    double* n; cudaError_t e = cudaMalloc(&n, sizeof(double)*new_p); if (e) return e;
+    e = cudaMemsetAsync(n, 0, sizeof(double)*new_p, c->stream); if (e) return e;
+    if (*arr && c->np) { e = cudaMemcpyAsync(n, *arr, sizeof(double)*c->np, cudaMemcpyDeviceToDevice, c->stream); if (e) return e; }
+    e = cudaStreamSynchronize(c->stream); if (e) return e;
+    if (*arr) cudaFree(*arr);
+    *arr = n; return cudaSuccess;
+  };
+  for (int k = 0; k < 3; k++) { CUDA_TRY(c, grow(&c->pos[k])); CUDA_TRY(c, grow(&c->vel[k])); CUDA_TRY(c, grow(&c->frc[k])); CUDA_TRY(c, grow(&c->frep[k])); }
+  if (c->comp_alloc) { for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) { cudaFree(c->comp[k][d]); c->comp[k][d] = nullptr; } c->comp_alloc = false; }
+  th.first_cell = c->ncells; th.first_particle = c->np; th.n_cells = n_cells;
+  for (size_t k = ctype + 1; k < c->types.size(); k++) { c->types[k].first_cell = new_c; c->types[k].first_particle = new_p; }
+  // host-side cell tables
+  std::vector<int32_t> pc(add_p);
+  for (int64_t i = 0; i < n_cells; i++) {
+    c->h_cell_id.push_back(cell_id[i]); c->h_cell_type.push_back(ctype); c->h_cell_base.push_back(c->np + i*V);
+    for (int v = 0; v < V; v++) pc[i*V + v] = (int32_t)(c->ncells + i);
+  }
+  // device cell tables (rebuilt)
+  cudaFree(c->cell_alive); cudaFree(c->cell_type); cudaFree(c->cell_base);
+  int32_t* npc;
+  CUDA_TRY(c, cudaMalloc(&npc, sizeof(int32_t)*new_p));
+  if (c->p_cell && c->np) CUDA_TRY(c, cudaMemcpy(npc, c->p_cell, sizeof(int32_t)*c->np, cudaMemcpyDeviceToDevice));
+  CUDA_TRY(c, cudaMemcpy(npc + c->np, pc.data(), sizeof(int32_t)*add_p, cudaMemcpyHostToDevice));
+  cudaFree(c->p_cell); c->p_cell = npc;
+  CUDA_TRY(c, cudaMalloc(&c->cell_alive, new_c));
+  CUDA_TRY(c, cudaMemset(c->cell_alive, 1, new_c));
+  CUDA_TRY(c, cudaMalloc(&c->cell_type, sizeof(int32_t)*new_c));
+  CUDA_TRY(c, cudaMalloc(&c->cell_base, sizeof(int64_t)*new_c));
+  CUDA_TRY(c, cudaMemcpy(c->cell_type, c->h_cell_type.data(), sizeof(int32_t)*new_c, cudaMemcpyHostToDevice));
+  CUDA_TRY(c, cudaMemcpy(c->cell_base, c->h_cell_base.data(), sizeof(int64_t)*new_c, cudaMemcpyHostToDevice));
+  // positions
+  hcg_status s = ensure_staging(c, sizeof(double)*3*add_p); if (s) return s;
+  CUDA_TRY(c, cudaMemcpyAsync(c->staging, pos, sizeof(double)*3*add_p, cudaMemcpyHostToDevice, c->stream));
+  k_aos_to_soa<<<nblk(add_p, 256), 256, 0, c->stream>>>(c->staging, c->pos[0] + c->np, c->pos[1] + c->np, c->pos[2] + c->np, add_p);
+  KERNEL_CHECK(c);
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->np = new_p; c->ncells = new_c; c->cap_p = new_p; c->cap_c = new_c;
+  if (c->bin_items) { cudaFree(c->bin_items); cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->scan_tmp);
+                      c->bin_items = c->bin_count = c->bin_start = nullptr; c->scan_tmp = nullptr; }
+  return HCG_OK;
+}
+
+hcg_status hcg_cells_capacity(hcg_ctx* c, int64_t* n_cells, int64_t* n_particles) {
+  if (!c) return HCG_ERR_ARG;
+  if (n_cells) *n_cells = c->ncells;
+  if (n_particles) *n_particles = c->np;
+  return HCG_OK;
+}
+
+hcg_status hcg_cells_count(hcg_ctx* c, int64_t* n_cells_alive, int64_t* n_particles_alive) {
+  if (!c) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  unsigned long long h[2] = {0, 0};
+  if (c->ncells > 0) {
+    std::vector<int> hv; for (auto& t : c->types) hv.push_back(t.d.V);
+    int* dv; unsigned long long* dout;
+    CUDA_TRY(c, cudaMalloc(&dv, sizeof(int)*hv.size())); CUDA_TRY(c, cudaMalloc(&dout, sizeof(h)));
+    CUDA_TRY(c, cudaMemcpyAsync(dv, hv.data(), sizeof(int)*hv.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(dout, 0, sizeof(h), c->stream));
+    k_count_alive<<<nblk(c->ncells, 256), 256, 0, c->stream>>>(c->cell_alive, c->cell_type, dv, c->ncells, dout);
+    KERNEL_CHECK(c);
+    CUDA_TRY(c, cudaMemcpyAsync(h, dout, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dv); cudaFree(dout);
+  }
+  if (n_cells_alive) *n_cells_alive = (int64_t)h[0];
+  if (n_particles_alive) *n_particles_alive = (int64_t)h[1];
+  return HCG_OK;
+}
+
+static hcg_status field_arrays(hcg_ctx* c, int32_t field, double** a) {
+  switch (field) {
+    case HCG_P_POS: a[0] = c->pos[0]; a[1] = c->pos[1]; a[2] = c->pos[2]; return HCG_OK;
+    case HCG_P_VEL: a[0] = c->vel[0]; a[1] = c->vel[1]; a[2] = c->vel[2]; return HCG_OK;
+    case HCG_P_FORCE: a[0] = c->frc[0]; a[1] = c->frc[1]; a[2] = c->frc[2]; return HCG_OK;
+    case HCG_P_FREP: a[0] = c->frep[0]; a[1] = c->frep[1]; a[2] = c->frep[2]; return HCG_OK;
+    default:
+      if (field >= HCG_P_F_AREA && field <= HCG_P_F_INNER) {
+        if (!c->comp_alloc) return hcg_fail(c, HCG_ERR_STATE, "component forces not computed: call hcg_op_mechanics(ctx, forced, 1) first");
+        for (int d = 0; d < 3; d++) a[d] = c->comp[field - HCG_P_F_AREA][d];
+        return HCG_OK;
+      }
+  }
+  return hcg_fail(c, HCG_ERR_ARG, "unknown particle field");
+}
+
+hcg_status hcg_cells_upload(hcg_ctx* c, int32_t field, const double* in) {
+  if (!c || !in) return HCG_ERR_ARG;
+  if (field > HCG_P_FREP) return hcg_fail(c, HCG_ERR_ARG, "cells_upload: field must be POS, VEL, FORCE or FREP");
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (c->np == 0) return HCG_OK;
+  double* a[3]; hcg_status s = field_arrays(c, field, a); if (s) return s;
+  if ((s = ensure_staging(c, sizeof(double)*3*c->np))) return s;
+  CUDA_TRY(c, cudaMemcpyAsync(c->staging, in, sizeof(double)*3*c->np, cudaMemcpyHostToDevice, c->stream));
+  k_aos_to_soa<<<nblk(c->np, 256), 256, 0, c->stream>>>(c->staging, a[0], a[1], a[2], c->np);
+  KERNEL_CHECK(c);
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_cells_download(hcg_ctx* c, int32_t field, double* out) {
+  if (!c || !out) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (c->np == 0) return HCG_OK;
+  double* a[3]; hcg_status s = field_arrays(c, field, a); if (s) return s;
+  if ((s = ensure_staging(c, sizeof(double)*3*c->np))) return s;
+  k_soa_to_aos<<<nblk(c->np, 256), 256, 0, c->stream>>>(a[0], a[1], a[2], c->staging, c->np);
+  KERNEL_CHECK(c);
+  CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*3*c->np, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_cells_info(hcg_ctx* c, int64_t* cell_id_out, int32_t* ctype_out, uint8_t* alive_out) {
+  if (!c) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (cell_id_out) std::copy(c->h_cell_id.begin(), c->h_cell_id.end(), cell_id_out);
+  if (ctype_out) std::copy(c->h_cell_type.begin(), c->h_cell_type.end(), ctype_out);
+  if (alive_out && c->ncells) {
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemcpy(alive_out, c->cell_alive, c->ncells, cudaMemcpyDeviceToHost));
+  }
+  return HCG_OK;
+}
+
+hcg_status hcg_cells_add_force(hcg_ctx* c, int64_t n, const int64_t* idx, const double* f) {
+  if (!c || n < 0 || (n > 0 && (!idx || !f))) return HCG_ERR_ARG;
+  if (n == 0) return HCG_OK;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  hcg_status s = ensure_staging(c, (sizeof(int64_t) + 3*sizeof(double))*n); if (s) return s;
+  int64_t* di = (int64_t*)c->staging; double* df = (double*)(di + n);
+  CUDA_TRY(c, cudaMemcpyAsync(di, idx, sizeof(int64_t)*n, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(df, f, sizeof(double)*3*n, cudaMemcpyHostToDevice, c->stream));
+  k_add_force<<<nblk(n, 128), 128, 0, c->stream>>>(n, di, df, c->frc[0], c->frc[1], c->frc[2], c->np);
+  KERNEL_CHECK(c);
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // host buffers are caller-owned
+  return HCG_OK;
+}
+
+hcg_status hcg_set_force_limit(hcg_ctx* c, double f) { if (!c || !(f > 0)) return HCG_ERR_ARG; c->f_limit = f; return HCG_OK; }
+hcg_status hcg_set_timescales(hcg_ctx* c, int32_t v, int32_t r, int32_t w) {
+  if (!c || v < 1 || r < 1 || w < 1) return HCG_ERR_ARG;
+  c->ts_vel = v; c->ts_rep = r; c->ts_wall = w; return HCG_OK;
+}
+hcg_status hcg_set_material_timescale(hcg_ctx* c, int32_t ctype, int32_t every) {
+  if (!c || ctype < 0 || ctype >= (int)c->types.size() || every < 1) return HCG_ERR_ARG;
+  c->types[ctype].timescale = every; return HCG_OK;
+}
+hcg_status hcg_set_repulsion(hcg_ctx* c, int32_t on, double k, double cut) {
+  if (!c || (on && !(cut > 0))) return HCG_ERR_ARG;
+  c->rep_on = on != 0; c->rep_k = k; c->rep_cut = cut; return HCG_OK;
+}
+hcg_status hcg_set_wall_repulsion(hcg_ctx* c, int32_t on, double k, double cut) {
+  if (!c || (on && !(cut > 0))) return HCG_ERR_ARG;
+  c->wall_on = on != 0; c->wall_k = k; c->wall_cut = cut; return HCG_OK;
+}
+hcg_status hcg_set_iteration(hcg_ctx* c, int64_t it) { if (!c || it < 0) return HCG_ERR_ARG; c->iter = it; return HCG_OK; }
+hcg_status hcg_get_iteration(hcg_ctx* c, int64_t* it) { if (!c || !it) return HCG_ERR_ARG; *it = c->iter; return HCG_OK; }
+
+hcg_status hcg_iterate(hcg_ctx* c, int64_t n) {
+  if (!c || n < 0) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  // sanityCheck (core/hemoCell.cpp:600-627): material / repulsion cadences are multiples of the velocity cadence
+  for (auto& t : c->types) if (t.timescale % c->ts_vel) return hcg_fail(c, HCG_ERR_STATE, "material timescale must be a multiple of the velocity timescale");
+  if (c->rep_on && c->ts_rep % c->ts_vel) return hcg_fail(c, HCG_ERR_STATE, "repulsion timescale must be a multiple of the velocity timescale");
+  for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) return s; }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_iterate_timed(hcg_ctx* c, int64_t n, double* ms_out) {
+  if (!c || n < 0 || !ms_out) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  const bool t_on = c->timers_on; c->timers_on = false;
+  cudaEvent_t a, b;
+  CUDA_TRY(c, cudaEventCreate(&a)); CUDA_TRY(c, cudaEventCreate(&b));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  CUDA_TRY(c, cudaEventRecord(a, c->stream));
+  for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) { c->timers_on = t_on; return s; } }
+  CUDA_TRY(c, cudaEventRecord(b, c->stream));
+  CUDA_TRY(c, cudaEventSynchronize(b));
+  float ms = 0; CUDA_TRY(c, cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  *ms_out = ms; c->timers_on = t_on;
+  return HCG_OK;
+}
+
+hcg_status hcg_fluid_warmup(hcg_ctx* c, int64_t n) {
+  if (!c || n < 0) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  // case files call lattice->collideAndStream() directly: the node force is NOT reset
+  for (int64_t i = 0; i < n; i++) { hcg_status s = lat_collide_stream(c, false); if (s) return s; }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+#define OP_PROLOGUE if (!c) return HCG_ERR_ARG; CUDA_TRY(c, cudaSetDevice(c->dom.device)); hcg_status s
+#define OP_EPILOGUE CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return HCG_OK
+hcg_status hcg_op_repulsion(hcg_ctx* c) { OP_PROLOGUE; if ((s = rep_apply(c))) return s; OP_EPILOGUE; }
+hcg_status hcg_op_wall_repulsion(hcg_ctx* c) { OP_PROLOGUE; if ((s = rep_wall_apply(c))) return s; OP_EPILOGUE; }
+hcg_status hcg_op_spread(hcg_ctx* c) { OP_PROLOGUE; if ((s = ibm_spread(c))) return s; OP_EPILOGUE; }
+hcg_status hcg_op_collide_stream(hcg_ctx* c) { OP_PROLOGUE; if ((s = lat_collide_stream(c, false))) return s; OP_EPILOGUE; }
+hcg_status hcg_op_interpolate(hcg_ctx* c) {
+  OP_PROLOGUE; if ((s = lat_moments(c, false, false))) return s; if ((s = ibm_interpolate(c))) return s; OP_EPILOGUE;
+}
+hcg_status hcg_op_sync(hcg_ctx* c) { OP_PROLOGUE; s = HCG_OK; (void)s; OP_EPILOGUE; }
+hcg_status hcg_op_advance(hcg_ctx* c) { OP_PROLOGUE; if ((s = ibm_advance(c))) return s; OP_EPILOGUE; }
+hcg_status hcg_op_mechanics(hcg_ctx* c, int32_t forced, int32_t components) {
+  OP_PROLOGUE; if ((s = do_mechanics(c, forced != 0, components != 0))) return s; OP_EPILOGUE;
+}
+hcg_status hcg_op_zero_force(hcg_ctx* c) { OP_PROLOGUE; if ((s = lat_reset_force(c))) return s; OP_EPILOGUE; }
+
+hcg_status hcg_cells_bbox(hcg_ctx* c, double* bbox) {
+  if (!c || !bbox) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (c->ncells == 0) return HCG_OK;
+  hcg_status s = ensure_staging(c, sizeof(double)*6*c->ncells); if (s) return s;
+  if ((s = mech_bbox(c, c->staging))) return s;
+  CUDA_TRY(c, cudaMemcpy(bbox, c->staging, sizeof(double)*6*c->ncells, cudaMemcpyDeviceToHost));
+  return HCG_OK;
+}
+
+hcg_status hcg_cells_volume_area(hcg_ctx* c, double* volume, double* area) {
+  if (!c || !volume || !area) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (c->ncells == 0) return HCG_OK;
+  hcg_status s = ensure_staging(c, sizeof(double)*2*c->ncells); if (s) return s;
+  if ((s = mech_volume_area(c, c->staging, c->staging + c->ncells))) return s;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  CUDA_TRY(c, cudaMemcpy(volume, c->staging, sizeof(double)*c->ncells, cudaMemcpyDeviceToHost));
+  CUDA_TRY(c, cudaMemcpy(area, c->staging + c->ncells, sizeof(double)*c->ncells, cudaMemcpyDeviceToHost));
+  return HCG_OK;
+}
+
+hcg_status hcg_fluid_velocity_stats(hcg_ctx* c, double* vmin, double* vmax, double* vmean) {
+  if (!c || !vmin || !vmax || !vmean) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  hcg_status s = lat_moments(c, false, false); if (s) return s;
+  return lat_velocity_stats(c, vmin, vmax, vmean);
+}
+
+hcg_status hcg_timers_enable(hcg_ctx* c, int32_t on) { if (!c) return HCG_ERR_ARG; c->timers_on = on != 0; return HCG_OK; }
+hcg_status hcg_timers_reset(hcg_ctx* c) { if (!c) return HCG_ERR_ARG; c->timers.clear(); c->timer_idx.clear(); return HCG_OK; }
+hcg_status hcg_timers(hcg_ctx* c, hcg_timer* out, int32_t* n) {
+  if (!c || !n) return HCG_ERR_ARG;
+  const int have = (int)c->timers.size();
+  if (out) for (int k = 0; k < have && k < *n; k++) {
+    memset(out[k].name, 0, sizeof(out[k].name));
+    strncpy(out[k].name, c->timers[k].name.c_str(), sizeof(out[k].name) - 1);
+    out[k].ms_total = c->timers[k].ms; out[k].calls = c->timers[k].calls;
+  }
+  *n = have;
+  return HCG_OK;
+}
+hcg_status hcg_launch_count(hcg_ctx* c, int64_t* n) { if (!c || !n) return HCG_ERR_ARG; *n = c->launches; return HCG_OK; }
+hcg_status hcg_synchronize(hcg_ctx* c) { if (!c) return HCG_ERR_ARG; CUDA_TRY(c, cudaSetDevice(c->dom.device)); CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return HCG_OK; }
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// Internal definitions shared by the CUDA translation units of libhemocell_gpu.so.
+// Device memory layout:
+//   lattice: slab of nxl planes + 1 ghost plane on each x side; plane = ny*nz nodes;
+//            local node index  n = z + nz*(y + ny*lx), lx = x - x0 + 1 in [0, nxl+1]
+//   populations g[q*S + n], S = (nxl+2)*ny*nz: the PRE-STREAMED (post-collision) value that
+//            will arrive at node n + c_q; the reference's post-stream state is S_q(n) = g_q(n - c_q)
+//   node force F[d*S + n], velocity U[d*S + n], flags[n]
+//   particles: SoA by component, p = cell_base + vertexId
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/hemocell_gpu.h"
+
+#define HCG_MAX_TYPES 8
+#define HCG_MAX_RING 6
+
+struct CellTypeDev {
+  int model, V, T, E, I;
+  int *tri, *edge, *inner, *ring, *nring, *bend_tri, *bend_outer;
+  double *edge_len_eq, *edge_ang_eq, *tri_area_eq, *patch_eq, *inner_len_eq;
+  // per-vertex gather tables (built on the host in hcg_celltype_add)
+  int *vt;    // [V][6]  incident triangles, ascending, -1 padded
+  int *ve;    // [V][6]  incident edges, ascending: 2*e + (v == edge[e][1]), -1 padded
+  int *vb;    // [V][7]  ring(v) U {v}, ascending, -1 padded  (RBC bending contributions)
+  int *vpe;   // [V][12] PLT: edges touching v as end or outer point: 4*e + role, ascending
+  int *vin;   // [V][4]  PLT inner edges: 2*e + side
+  double volume_eq, area_mean_eq, edge_mean_eq;
+  double k_volume, k_area, k_link, k_bend, eta_m;
+};
+
+struct CellTypeHost {
+  CellTypeDev d;
+  int64_t n_cells = 0, first_cell = 0, first_particle = 0;
+  int timescale = 1;
+  std::vector<void*> allocs;
+};
+
+struct TimerSlot { std::string name; double ms = 0; int64_t calls = 0; };
+
+struct hcg_ctx {
+  hcg_domain dom;
+  int nxl, x0;                 // slab
+  int64_t P, S, Nl;            // plane size, padded slab size, real nodes
+  double omega;
+  double bc_vel[6][3]; double* d_bc;
+  double body[3];
+  double f_limit;
+  // lattice
+  double *g[2]; int cur;       // double-buffered pre-streamed populations
+  double *F, *U, *rho;         // node force, interpolation velocity (+ density scratch)
+  uint8_t* flags;
+  bool u_valid, has_velbc;
+  // particles
+  int64_t np, ncells, cap_p, cap_c;
+  double *pos[3], *vel[3], *frc[3], *frep[3];
+  double *comp[6][3];          // optional per-component force arrays
+  bool comp_alloc;
+  int32_t* p_cell;             // particle -> cell slot
+  uint8_t* cell_alive;         // per cell
+  int32_t* cell_type;          // per cell (device)
+  int64_t* cell_base;          // per cell (device) first particle
+  std::vector<int64_t> h_cell_id; std::vector<int32_t> h_cell_type; std::vector<int64_t> h_cell_base;
+  std::vector<CellTypeHost> types;
+  // repulsion
+  bool rep_on, wall_on; double rep_k, rep_cut, wall_k, wall_cut;
+  int ts_vel, ts_rep, ts_wall;
+  int *bin_count, *bin_start, *bin_items; int64_t* wall_nodes; int64_t n_wall; bool wall_built;
+  void* scan_tmp; size_t scan_tmp_bytes;
+  int64_t iter;
+  // execution
+  cudaStream_t stream, stream_halo;
+  cudaEvent_t ev_a, ev_b;
+  void* nccl;                  // ncclComm_t
+  double* halo_send[2]; double* halo_recv[2];
+  bool timers_on; std::vector<TimerSlot> timers; std::map<std::string,int> timer_idx;
+  int64_t launches;
+  std::string err;
+  double* staging; size_t staging_bytes;   // device scratch for AoS<->SoA transposes
+};
+
+hcg_status hcg_fail(hcg_ctx* c, hcg_status code, const std::string& msg);
+#define CUDA_TRY(c, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+  return hcg_fail((c), HCG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+#define KERNEL_CHECK(c) do { (c)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
+  return hcg_fail((c), HCG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); } while (0)
+
+// lattice.cu
+hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force);
+hcg_status lat_moments(hcg_ctx* c, bool reset_force, bool want_rho);
+hcg_status lat_reset_force(hcg_ctx* c);
+hcg_status lat_init_equilibrium(hcg_ctx* c, double rho, const double u[3]);
+hcg_status lat_halo_exchange_pop(hcg_ctx* c);
+hcg_status lat_halo_exchange_u(hcg_ctx* c);
+hcg_status lat_pop_to_reference(hcg_ctx* c, double* dst_dev);      // S_q(n) = g_q(n - c_q), compact slab
+hcg_status lat_pop_from_reference(hcg_ctx* c, const double* src_dev);
+hcg_status lat_velocity_stats(hcg_ctx* c, double* vmin, double* vmax, double* vmean);
+// ibm.cu
+hcg_status ibm_spread(hcg_ctx* c);
+hcg_status ibm_interpolate(hcg_ctx* c);
+hcg_status ibm_advance(hcg_ctx* c);
+hcg_status ibm_interpolate_advance(hcg_ctx* c);
+// mechanics.cu
+hcg_status mech_apply(hcg_ctx* c, int ctype, bool components);
+hcg_status mech_bbox(hcg_ctx* c, double* out_dev);
+hcg_status mech_volume_area(hcg_ctx* c, double* vol_dev, double* area_dev);
+// repulsion.cu
+hcg_status rep_apply(hcg_ctx* c);
+hcg_status rep_wall_apply(hcg_ctx* c);
+
+// D3Q19, Palabos order; opposite(i) = i + 9
+__device__ __constant__ static const int d_cx[19] = {0,-1,0,0,-1,-1,-1,-1,0,0, 1,0,0,1,1,1,1,0,0};
+__device__ __constant__ static const int d_cy[19] = {0,0,-1,0,-1,1,0,0,-1,-1, 0,1,0,1,-1,0,0,1,1};
+__device__ __constant__ static const int d_cz[19] = {0,0,0,-1,0,0,-1,1,-1,1, 0,0,1,0,0,1,-1,1,-1};

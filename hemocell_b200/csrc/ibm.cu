@@ -1,0 +1,189 @@
+// K2 / K4b: immersed-boundary spread + interpolate (phi2 kernel) and particle advance.
+// Replaces HemoCellParticleField::spreadParticleForce / interpolateFluidVelocity /
+// advanceParticles (reference core/hemoCellParticleField.cpp:841-863, 819-839, 566-588) and
+// interpolationCoefficientsPhi2 (core/immersedBoundaryMethod.h:62-138).
+#include "ctx.cuh"
+
+namespace {
+
+struct IbmArgs {
+  int nx, ny, nz, px, py, pz;
+  int nxl, x0, nranks;
+  int64_t P, S, np;
+  double f_limit;
+};
+
+// global (unwrapped) node x -> local plane index incl. ghosts; false if not held by this rank
+// or outside a non-periodic domain
+__device__ __forceinline__ bool local_x(int gx, const IbmArgs& a, int& lx, bool& outside) {
+  outside = false;
+  if (gx < 0 || gx >= a.nx) {
+    if (!a.px) { outside = true; return false; }
+    gx %= a.nx; if (gx < 0) gx += a.nx;
+  }
+  int rel = gx - a.x0; if (rel < 0) rel += a.nx;
+  if (rel < a.nxl) { lx = rel + 1; return true; }
+  if (a.nranks > 1) {
+    if (rel == a.nx - 1) { lx = 0; return true; }
+    if (rel == a.nxl) { lx = a.nxl + 1; return true; }
+  }
+  return false;
+}
+__device__ __forceinline__ bool wrap_yz(int& v, int n, int periodic) {
+  if (v >= 0 && v < n) return true;
+  if (!periodic) return false;
+  v %= n; if (v < 0) v += n;
+  return true;
+}
+__device__ __forceinline__ double phi2(double x) { x = 1.0 - fabs(x); return x > 0.0 ? x : 0.0; }
+
+// Kernel of one particle: up to 8 (node, weight) pairs in the reference's x-outer/z-inner
+// order, zero weights and boundary nodes skipped, normalised.  Returns the count, or -1 when a
+// candidate node is not addressable from this rank (particle irrelevant here).
+__device__ __forceinline__ int ibm_kernel(const IbmArgs& a, const uint8_t* __restrict__ flags,
+                                          double px, double py, double pz, int64_t node[8], double w[8]) {
+  const int bx = (int)floor(px), by = (int)floor(py), bz = (int)floor(pz);
+  int n = 0; double total = 0.0;
+#pragma unroll
+  for (int dx = 0; dx < 2; dx++) {
+    const double wx = phi2(px - (double)(bx + dx));
+    if (wx == 0.0) continue;
+    int lx; bool out;
+    if (!local_x(bx + dx, a, lx, out)) { if (out) continue; return -1; }
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++) {
+      const double wy = phi2(py - (double)(by + dy));
+      int y = by + dy;
+      if (wy == 0.0 || !wrap_yz(y, a.ny, a.py)) continue;
+#pragma unroll
+      for (int dz = 0; dz < 2; dz++) {
+        const double wz = phi2(pz - (double)(bz + dz));
+        int z = bz + dz;
+        if (wz == 0.0 || !wrap_yz(z, a.nz, a.pz)) continue;
+        const double weight = wx*wy*wz;
+        if (weight == 0.0) continue;
+        const int64_t id = (int64_t)z + (int64_t)a.nz*((int64_t)y + (int64_t)a.ny*lx);
+        if (flags[id] != HCG_FLUID) continue;
+        total += weight;
+        node[n] = id; w[n] = weight; n++;
+      }
+    }
+  }
+  const double coeff = 1.0/total;
+  for (int k = 0; k < n; k++) w[k] *= coeff;
+  return n;
+}
+
+__global__ void __launch_bounds__(256)
+k_spread(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __restrict__ p_cell,
+         const uint8_t* __restrict__ alive,
+         const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+         double* fx, double* fy, double* fz,
+         const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+         double* __restrict__ F) {
+  const int64_t p = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= a.np) return;
+  if (!alive[p_cell[p]]) return;
+  double f0 = fx[p], f1 = fy[p], f2 = fz[p];
+  // force cap, permanent (hemoCellParticleField.cpp:848-852)
+  const double mag = sqrt(f0*f0 + f1*f1 + f2*f2);
+  if (mag > a.f_limit) {
+    const double s = a.f_limit/mag;
+    f0 *= s; f1 *= s; f2 *= s;
+    fx[p] = f0; fy[p] = f1; fz[p] = f2;
+  }
+  int64_t node[8]; double w[8];
+  const int n = ibm_kernel(a, flags, x[p], y[p], z[p], node, w);
+  const double t0 = rx[p] + f0, t1 = ry[p] + f1, t2 = rz[p] + f2;
+  const int64_t lo = a.P, hi = (int64_t)(a.nxl + 1)*a.P;      // real planes only
+  for (int k = 0; k < n; k++) {
+    if (node[k] < lo || node[k] >= hi) continue;
+    atomicAdd(F + node[k], t0*w[k]);
+    atomicAdd(F + a.S + node[k], t1*w[k]);
+    atomicAdd(F + 2*a.S + node[k], t2*w[k]);
+  }
+}
+
+template <bool ADVANCE, bool INTERP>
+__global__ void __launch_bounds__(256)
+k_interp_advance(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __restrict__ p_cell,
+                 uint8_t* alive, double* x, double* y, double* z,
+                 double* vx, double* vy, double* vz, const double* __restrict__ U) {
+  const int64_t p = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= a.np) return;
+  const int cell = p_cell[p];
+  if (!alive[cell]) return;
+  double px = x[p], py = y[p], pz = z[p];
+  double v0, v1, v2;
+  if (INTERP) {
+    int64_t node[8]; double w[8];
+    const int n = ibm_kernel(a, flags, px, py, pz, node, w);
+    v0 = v1 = v2 = 0.0;
+    for (int k = 0; k < n; k++) {
+      v0 += __ldg(U + node[k])*w[k];
+      v1 += __ldg(U + a.S + node[k])*w[k];
+      v2 += __ldg(U + 2*a.S + node[k])*w[k];
+    }
+    if (n >= 0) { vx[p] = v0; vy[p] = v1; vz[p] = v2; }
+    else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
+  } else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
+  if (ADVANCE) {
+    px += v0; py += v1; pz += v2;
+    x[p] = px; y[p] = py; z[p] = pz;
+    // particle on a boundary node => its cell is deleted (hemoCellParticleField.cpp:572-584, 512-553)
+    int lx; bool out;
+    int yy = (int)floor(py + 0.5), zz = (int)floor(pz + 0.5);
+    if (local_x((int)floor(px + 0.5), a, lx, out) && wrap_yz(yy, a.ny, a.py) && wrap_yz(zz, a.nz, a.pz)) {
+      if (flags[(int64_t)zz + (int64_t)a.nz*((int64_t)yy + (int64_t)a.ny*lx)] != HCG_FLUID) alive[cell] = 0;
+    }
+  }
+}
+
+IbmArgs make_args(const hcg_ctx* c) {
+  IbmArgs a;
+  a.nx = c->dom.nx; a.ny = c->dom.ny; a.nz = c->dom.nz;
+  a.px = c->dom.periodic[0]; a.py = c->dom.periodic[1]; a.pz = c->dom.periodic[2];
+  a.nxl = c->nxl; a.x0 = c->x0; a.nranks = c->dom.n_ranks;
+  a.P = c->P; a.S = c->S; a.np = c->np; a.f_limit = c->f_limit;
+  return a;
+}
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1)/t); }
+
+}  // namespace
+
+hcg_status ibm_spread(hcg_ctx* c) {
+  if (c->np == 0) return HCG_OK;
+  IbmArgs a = make_args(c);
+  k_spread<<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->frc[0], c->frc[1], c->frc[2],
+      c->frep[0], c->frep[1], c->frep[2], c->F);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+
+hcg_status ibm_interpolate(hcg_ctx* c) {
+  if (c->np == 0) return HCG_OK;
+  IbmArgs a = make_args(c);
+  k_interp_advance<false, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+
+hcg_status ibm_advance(hcg_ctx* c) {
+  if (c->np == 0) return HCG_OK;
+  IbmArgs a = make_args(c);
+  k_interp_advance<true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+
+hcg_status ibm_interpolate_advance(hcg_ctx* c) {
+  if (c->np == 0) return HCG_OK;
+  IbmArgs a = make_args(c);
+  k_interp_advance<true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}

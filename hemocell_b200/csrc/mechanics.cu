@@ -1,0 +1,351 @@
+// K3: membrane constitutive forces, one CTA per cell, positions staged in shared memory,
+// per-vertex GATHER over precomputed adjacency so that every vertex accumulates its terms in
+// exactly the order the reference's sequential loops produce them (no atomics, deterministic).
+// Replaces RbcHighOrderModel::ParticleMechanics (reference mechanics/rbcHighOrderModel.cpp:38-207)
+// and PltSimpleModel::ParticleMechanics (mechanics/pltSimpleModel.cpp:44-208) behind
+// HemoCellParticleField::applyConstitutiveModel (core/hemoCellParticleField.cpp:633-675).
+#include "ctx.cuh"
+#include <cfloat>
+
+namespace {
+
+struct MechArgs {
+  CellTypeDev t;
+  int64_t first_cell, first_particle;
+  const uint8_t* alive;
+  const double *x, *y, *z, *vx, *vy, *vz;
+  double *fx, *fy, *fz;
+  double* comp[6][3];
+};
+
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 sub(V3 a, V3 b) { return {a.x-b.x, a.y-b.y, a.z-b.z}; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return {a.y*b.z - a.z*b.y, a.z*b.x - a.x*b.z, a.x*b.y - a.y*b.x}; }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x*b.x + a.y*b.y + a.z*b.z; }
+__device__ __forceinline__ double norm(V3 a) { return sqrt(a.x*a.x + a.y*a.y + a.z*a.z); }
+__device__ __forceinline__ V3 ldv(const double* X, int V, int i) { return {X[i], X[V+i], X[2*V+i]}; }
+// helper/array.h:271-285
+__device__ __forceinline__ void tri_area_normal(V3 v0, V3 v1, V3 v2, double& area, V3& n) {
+  n = cross(sub(v1, v0), sub(v2, v0));
+  const double nn = norm(n);
+  if (nn != 0.0) { area = 0.5*nn; n.x /= nn; n.y /= nn; n.z /= nn; }
+  else { area = 0.0; n = {0.0, 0.0, 0.0}; }
+}
+
+// MODEL 0 = RbcHighOrderModel, 1 = PltSimpleModel; VISC: membrane viscosity term evaluated
+template <int MODEL, bool VISC, bool COMP>
+__global__ void __launch_bounds__(256)
+k_mechanics(MechArgs a) {
+  extern __shared__ double sm[];
+  const CellTypeDev& t = a.t;
+  const int V = t.V, T = t.T;
+  const int64_t cell = a.first_cell + blockIdx.x;
+  if (!a.alive[cell]) return;
+  const int64_t base = a.first_particle + (int64_t)blockIdx.x*V;
+  double* X = sm;                    // [3V]
+  double* VEL = X + 3*V;             // [3V] if VISC
+  double* TA = VEL + (VISC ? 3*V : 0);   // [T]
+  double* TN = TA + T;               // [3T]
+  double* VT = TN + 3*T;             // [T]
+  double* BF = VT + T;               // [3V] (RBC)
+  __shared__ double s_volume;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (int i = tid; i < V; i += nt) {
+    X[i] = a.x[base+i]; X[V+i] = a.y[base+i]; X[2*V+i] = a.z[base+i];
+    if (VISC) { VEL[i] = a.vx[base+i]; VEL[V+i] = a.vy[base+i]; VEL[2*V+i] = a.vz[base+i]; }
+  }
+  __syncthreads();
+
+  // ---- per triangle: signed-volume term (bit-exact, no contraction), area, unit normal
+  for (int k = tid; k < T; k += nt) {
+    const int i0 = t.tri[3*k], i1 = t.tri[3*k+1], i2 = t.tri[3*k+2];
+    const V3 v0 = ldv(X, V, i0), v1 = ldv(X, V, i1), v2 = ldv(X, V, i2);
+    const double v210 = __dmul_rn(__dmul_rn(v2.x, v1.y), v0.z);
+    const double v120 = __dmul_rn(__dmul_rn(v1.x, v2.y), v0.z);
+    const double v201 = __dmul_rn(__dmul_rn(v2.x, v0.y), v1.z);
+    const double v021 = __dmul_rn(__dmul_rn(v0.x, v2.y), v1.z);
+    const double v102 = __dmul_rn(__dmul_rn(v1.x, v0.y), v2.z);
+    const double v012 = __dmul_rn(__dmul_rn(v0.x, v1.y), v2.z);
+    VT[k] = __dadd_rn(__dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(-v210, v120), v201), v021), v102), v012);
+    double area; V3 n;
+    tri_area_normal(v0, v1, v2, area, n);
+    TA[k] = area; TN[3*k] = n.x; TN[3*k+1] = n.y; TN[3*k+2] = n.z;
+  }
+  // ---- RBC: bending force of every vertex's own patch (rbcHighOrderModel.cpp:127-158)
+  if (MODEL == 0) {
+    for (int i = tid; i < V; i += nt) {
+      const int nn = t.nring[i];
+      const int* ring = t.ring + 6*i;
+      const V3 xi = ldv(X, V, i);
+      V3 sum = {0.0, 0.0, 0.0};
+      for (int j = 0; j < nn; j++) { const V3 r = ldv(X, V, ring[j]); sum.x += r.x; sum.y += r.y; sum.z += r.z; }
+      const V3 mid = {sum.x/nn, sum.y/nn, sum.z/nn};
+      const V3 dev = sub(mid, xi);
+      V3 pn = {0.0, 0.0, 0.0};
+      V3 prev = sub(ldv(X, V, ring[0]), xi);
+      const V3 first = prev;
+      for (int j = 0; j < nn; j++) {
+        const V3 nxt = (j + 1 < nn) ? sub(ldv(X, V, ring[j+1]), xi) : first;
+        V3 tn = cross(prev, nxt);
+        const double l = norm(tn);
+        pn.x += tn.x/l; pn.y += tn.y/l; pn.z += tn.z/l;
+        prev = nxt;
+      }
+      const double l = norm(pn);
+      pn.x /= l; pn.y /= l; pn.z /= l;
+      const double ndev = dot(pn, dev);
+      const double dDev = (ndev - t.patch_eq[i]) / t.edge_mean_eq;
+      const double s = t.k_bend * (dDev + dDev/fabs(0.0555 - dDev*dDev));
+      BF[i] = s*pn.x; BF[V+i] = s*pn.y; BF[2*V+i] = s*pn.z;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {   // sequential sum in triangle order == the reference's rounding
+    double vol = 0.0;
+    for (int k = 0; k < T; k++) vol = __dadd_rn(vol, VT[k]);
+    s_volume = __dmul_rn(vol, 1.0/6.0);
+  }
+  __syncthreads();
+  const double volume_frac = (s_volume - t.volume_eq)/t.volume_eq;
+  const double volume_force = -t.k_volume * volume_frac/fabs(0.01 - volume_frac*volume_frac);
+
+  // ---- per vertex gather
+  for (int v = tid; v < V; v += nt) {
+    const V3 xv = ldv(X, V, v);
+    double F0 = 0.0, F1 = 0.0, F2 = 0.0;
+    double c0, c1, c2;
+    // area force (rbcHighOrderModel.cpp:72-92)
+    c0 = c1 = c2 = 0.0;
+    for (int k = 0; k < 6; k++) {
+      const int tr = t.vt[6*v + k]; if (tr < 0) break;
+      const int i0 = t.tri[3*tr], i1 = t.tri[3*tr+1], i2 = t.tri[3*tr+2];
+      const V3 v0 = ldv(X, V, i0), v1 = ldv(X, V, i1), v2 = ldv(X, V, i2);
+      const double aeq = t.tri_area_eq[tr];
+      const double areaRatio = (TA[tr] - aeq)/aeq;
+      const double afm = t.k_area * (areaRatio + areaRatio/fabs(0.09 - areaRatio*areaRatio));
+      const double cx = (v0.x+v1.x+v2.x)/3.0, cy = (v0.y+v1.y+v2.y)/3.0, cz = (v0.z+v1.z+v2.z)/3.0;
+      const double a0 = afm*(cx - xv.x), a1 = afm*(cy - xv.y), a2 = afm*(cz - xv.z);
+      F0 += a0; F1 += a1; F2 += a2;
+      if (COMP) { c0 += a0; c1 += a1; c2 += a2; }
+    }
+    if (COMP) { a.comp[0][0][base+v] = c0; a.comp[0][1][base+v] = c1; a.comp[0][2][base+v] = c2; c0 = c1 = c2 = 0.0; }
+    // volume force (rbcHighOrderModel.cpp:100-113)
+    for (int k = 0; k < 6; k++) {
+      const int tr = t.vt[6*v + k]; if (tr < 0) break;
+      const double s = TA[tr]/t.area_mean_eq;
+      const double a0 = (volume_force*TN[3*tr])*s, a1 = (volume_force*TN[3*tr+1])*s, a2 = (volume_force*TN[3*tr+2])*s;
+      F0 += a0; F1 += a1; F2 += a2;
+      if (COMP) { c0 += a0; c1 += a1; c2 += a2; }
+    }
+    if (COMP) { a.comp[1][0][base+v] = c0; a.comp[1][1][base+v] = c1; a.comp[1][2][base+v] = c2; c0 = c1 = c2 = 0.0; }
+    if (MODEL == 0) {
+      // bending: own patch force + reaction -F_i/n_i of every neighbour patch, by ascending i
+      for (int k = 0; k < 7; k++) {
+        const int i = t.vb[7*v + k]; if (i < 0) break;
+        double a0, a1, a2;
+        if (i == v) { a0 = BF[i]; a1 = BF[V+i]; a2 = BF[2*V+i]; }
+        else { const int nn = t.nring[i]; a0 = -BF[i]/nn; a1 = -BF[V+i]/nn; a2 = -BF[2*V+i]/nn; }
+        F0 += a0; F1 += a1; F2 += a2;
+        if (COMP) { c0 += a0; c1 += a1; c2 += a2; }
+      }
+      if (COMP) { a.comp[2][0][base+v] = c0; a.comp[2][1][base+v] = c1; a.comp[2][2][base+v] = c2; }
+      // links (+ membrane viscosity) (rbcHighOrderModel.cpp:169-201)
+      double l0 = 0, l1 = 0, l2 = 0, s0 = 0, s1 = 0, s2 = 0;
+      for (int k = 0; k < 6; k++) {
+        const int code = t.ve[6*v + k]; if (code < 0) break;
+        const int e = code >> 1; const double sg = (code & 1) ? -1.0 : 1.0;
+        const int ia = t.edge[2*e], ib = t.edge[2*e+1];
+        const V3 ev = sub(ldv(X, V, ib), ldv(X, V, ia));
+        const double len = norm(ev);
+        const V3 uv = {ev.x/len, ev.y/len, ev.z/len};
+        const double leq = t.edge_len_eq[e];
+        const double frac = (len - leq)/leq;
+        const double fs = t.k_link * (frac + frac/fabs(9.0 - frac*frac));
+        const double a0 = uv.x*fs, a1 = uv.y*fs, a2 = uv.z*fs;
+        F0 += sg*a0; F1 += sg*a1; F2 += sg*a2;
+        if (COMP) { l0 += sg*a0; l1 += sg*a1; l2 += sg*a2; }
+        if (VISC) {
+          const V3 rv = sub(ldv(VEL, V, ib), ldv(VEL, V, ia));
+          const double pr = dot(rv, uv);
+          double g0 = t.eta_m*(pr*uv.x), g1 = t.eta_m*(pr*uv.y), g2 = t.eta_m*(pr*uv.z);
+          const double mag = sqrt(g0*g0 + g1*g1 + g2*g2);
+          if (mag > 12.5) { const double s = 12.5/mag; g0 *= s; g1 *= s; g2 *= s; }
+          F0 += sg*g0; F1 += sg*g1; F2 += sg*g2;
+          if (COMP) { s0 += sg*g0; s1 += sg*g1; s2 += sg*g2; }
+        }
+      }
+      if (COMP) {
+        a.comp[3][0][base+v] = l0; a.comp[3][1][base+v] = l1; a.comp[3][2][base+v] = l2;
+        a.comp[4][0][base+v] = s0; a.comp[4][1][base+v] = s1; a.comp[4][2][base+v] = s2;
+        a.comp[5][0][base+v] = 0.0; a.comp[5][1][base+v] = 0.0; a.comp[5][2][base+v] = 0.0;
+      }
+    } else {
+      // PLT: per edge link, viscosity, dihedral bending (pltSimpleModel.cpp:119-185)
+      double l0 = 0, l1 = 0, l2 = 0, s0 = 0, s1 = 0, s2 = 0, b0 = 0, b1 = 0, b2 = 0;
+      for (int k = 0; k < 12; k++) {
+        const int code = t.vpe[12*v + k]; if (code < 0) break;
+        const int e = code >> 2, role = code & 3;
+        const int ia = t.edge[2*e], ib = t.edge[2*e+1];
+        const V3 ev = sub(ldv(X, V, ib), ldv(X, V, ia));
+        const double len = sqrt(ev.x*ev.x + ev.y*ev.y + ev.z*ev.z);
+        const V3 uv = {ev.x/len, ev.y/len, ev.z/len};
+        if (role < 2) {
+          const double sg = role ? -1.0 : 1.0;
+          const double leq = t.edge_len_eq[e];
+          const double frac = (len - leq)/leq;
+          const double fs = t.k_link * (frac + frac/fabs(9.0 - frac*frac));
+          const double a0 = uv.x*fs, a1 = uv.y*fs, a2 = uv.z*fs;
+          F0 += sg*a0; F1 += sg*a1; F2 += sg*a2;
+          if (COMP) { l0 += sg*a0; l1 += sg*a1; l2 += sg*a2; }
+          const V3 rv = sub(ldv(VEL, V, ib), ldv(VEL, V, ia));
+          const double pr = dot(rv, uv);
+          double g0 = t.eta_m*(pr*uv.x), g1 = t.eta_m*(pr*uv.y), g2 = t.eta_m*(pr*uv.z);
+          const double mag = sqrt(g0*g0 + g1*g1 + g2*g2);
+          if (mag > 12.5) { const double s = 12.5/mag; g0 *= s; g1 *= s; g2 *= s; }
+          F0 += sg*g0; F1 += sg*g1; F2 += sg*g2;
+          if (COMP) { s0 += sg*g0; s1 += sg*g1; s2 += sg*g2; }
+        }
+        const int t0 = t.bend_tri[2*e], t1 = t.bend_tri[2*e+1];
+        const V3 n1 = {TN[3*t0], TN[3*t0+1], TN[3*t0+2]}, n2 = {TN[3*t1], TN[3*t1+1], TN[3*t1+2]};
+        const double angle = atan2(dot(cross(n1, n2), uv), dot(n1, n2));
+        const double af = angle - t.edge_ang_eq[e];
+        const double fm = t.k_bend * (af + af/fabs(2.467 - af*af));
+        const double sb = (role < 2) ? 1.0 : -1.0;
+        const double a0 = fm*(n1.x+n2.x)*0.5, a1 = fm*(n1.y+n2.y)*0.5, a2 = fm*(n1.z+n2.z)*0.5;
+        F0 += sb*a0; F1 += sb*a1; F2 += sb*a2;
+        if (COMP) { b0 += sb*a0; b1 += sb*a1; b2 += sb*a2; }
+      }
+      // inner links, linear (pltSimpleModel.cpp:188-205)
+      double n0 = 0, n1_ = 0, n2_ = 0;
+      for (int k = 0; k < 4; k++) {
+        const int code = t.vin[4*v + k]; if (code < 0) break;
+        const int e = code >> 1; const double sg = (code & 1) ? -1.0 : 1.0;
+        const int ia = t.inner[2*e], ib = t.inner[2*e+1];
+        const V3 ev = sub(ldv(X, V, ib), ldv(X, V, ia));
+        const double len = sqrt(ev.x*ev.x + ev.y*ev.y + ev.z*ev.z);
+        const double leq = t.inner_len_eq[e];
+        const double frac = (len - leq)/leq;
+        const double fs = t.k_link*5.0*frac;
+        const double a0 = (ev.x/len)*fs, a1 = (ev.y/len)*fs, a2 = (ev.z/len)*fs;
+        F0 += sg*a0; F1 += sg*a1; F2 += sg*a2;
+        if (COMP) { n0 += sg*a0; n1_ += sg*a1; n2_ += sg*a2; }
+      }
+      if (COMP) {
+        a.comp[2][0][base+v] = b0; a.comp[2][1][base+v] = b1; a.comp[2][2][base+v] = b2;
+        a.comp[3][0][base+v] = l0; a.comp[3][1][base+v] = l1; a.comp[3][2][base+v] = l2;
+        a.comp[4][0][base+v] = s0; a.comp[4][1][base+v] = s1; a.comp[4][2][base+v] = s2;
+        a.comp[5][0][base+v] = n0; a.comp[5][1][base+v] = n1_; a.comp[5][2][base+v] = n2_;
+      }
+    }
+    a.fx[base+v] = F0; a.fy[base+v] = F1; a.fz[base+v] = F2;
+  }
+}
+
+// per cell: bounding box (helper/cellInfo.cpp:170-200) ; one warp per cell
+__global__ void k_bbox(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                       const int64_t* __restrict__ cell_base, const int32_t* __restrict__ cell_type,
+                       const int* __restrict__ typeV, int64_t ncells, double* out) {
+  const int64_t cell = (int64_t)blockIdx.x*(blockDim.x/32) + threadIdx.x/32;
+  if (cell >= ncells) return;
+  const int lane = threadIdx.x & 31;
+  const int V = typeV[cell_type[cell]]; const int64_t b = cell_base[cell];
+  double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (int i = lane; i < V; i += 32) {
+    const double p[3] = {x[b+i], y[b+i], z[b+i]};
+    for (int d = 0; d < 3; d++) { mn[d] = fmin(mn[d], p[d]); mx[d] = fmax(mx[d], p[d]); }
+  }
+  for (int s = 16; s > 0; s >>= 1)
+    for (int d = 0; d < 3; d++) {
+      mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], s));
+      mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], s));
+    }
+  if (lane == 0) for (int d = 0; d < 3; d++) { out[6*cell + 2*d] = mn[d]; out[6*cell + 2*d + 1] = mx[d]; }
+}
+
+// per cell: volume and surface area (helper/cellInfo.cpp:39-101); one warp per cell, type given
+__global__ void k_volume_area(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                              int64_t first_cell, int64_t first_particle, int64_t ncells, int V, int T,
+                              const int* __restrict__ tri, double* vol, double* area) {
+  const int64_t c = (int64_t)blockIdx.x*(blockDim.x/32) + threadIdx.x/32;
+  if (c >= ncells) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t b = first_particle + c*V;
+  double v = 0.0, ar = 0.0;
+  for (int k = lane; k < T; k += 32) {
+    const int i0 = tri[3*k], i1 = tri[3*k+1], i2 = tri[3*k+2];
+    const V3 v0 = {x[b+i0], y[b+i0], z[b+i0]}, v1 = {x[b+i1], y[b+i1], z[b+i1]}, v2 = {x[b+i2], y[b+i2], z[b+i2]};
+    // translation-safe: relative to the first vertex of the cell
+    const V3 o = {x[b], y[b], z[b]};
+    v += dot(sub(v0, o), cross(sub(v1, o), sub(v2, o)));
+    ar += 0.5*norm(cross(sub(v1, v0), sub(v2, v0)));
+  }
+  for (int s = 16; s > 0; s >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, s); ar += __shfl_xor_sync(0xffffffffu, ar, s); }
+  if (lane == 0) { vol[first_cell + c] = v/6.0; area[first_cell + c] = ar; }
+}
+
+template <int MODEL, bool VISC>
+hcg_status launch(hcg_ctx* c, const MechArgs& a, int64_t ncells, size_t smem, int threads, bool comp) {
+  if (comp) {
+    CUDA_TRY(c, cudaFuncSetAttribute(k_mechanics<MODEL, VISC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_mechanics<MODEL, VISC, true><<<(unsigned)ncells, threads, smem, c->stream>>>(a);
+  } else {
+    CUDA_TRY(c, cudaFuncSetAttribute(k_mechanics<MODEL, VISC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_mechanics<MODEL, VISC, false><<<(unsigned)ncells, threads, smem, c->stream>>>(a);
+  }
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+
+}  // namespace
+
+hcg_status mech_apply(hcg_ctx* c, int ctype, bool components) {
+  CellTypeHost& th = c->types[ctype];
+  if (th.n_cells == 0) return HCG_OK;
+  if (components && !c->comp_alloc) {
+    for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) {
+      CUDA_TRY(c, cudaMalloc(&c->comp[k][d], sizeof(double)*c->cap_p));
+      CUDA_TRY(c, cudaMemsetAsync(c->comp[k][d], 0, sizeof(double)*c->cap_p, c->stream));
+    }
+    c->comp_alloc = true;
+  }
+  MechArgs a;
+  a.t = th.d; a.first_cell = th.first_cell; a.first_particle = th.first_particle;
+  a.alive = c->cell_alive;
+  a.x = c->pos[0]; a.y = c->pos[1]; a.z = c->pos[2];
+  a.vx = c->vel[0]; a.vy = c->vel[1]; a.vz = c->vel[2];
+  a.fx = c->frc[0]; a.fy = c->frc[1]; a.fz = c->frc[2];
+  for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) a.comp[k][d] = components ? c->comp[k][d] : nullptr;
+  const int V = th.d.V, T = th.d.T;
+  const bool plt = th.d.model == HCG_MODEL_PLT_SIMPLE;
+  const bool visc = plt || th.d.eta_m != 0.0;
+  const size_t smem = sizeof(double)*((size_t)3*V + (visc ? 3*V : 0) + 5*(size_t)T + (plt ? 0 : 3*V));
+  const int threads = V >= 256 ? 256 : (V >= 128 ? 128 : 64);
+  if (plt) return launch<1, true>(c, a, th.n_cells, smem, threads, components);
+  if (visc) return launch<0, true>(c, a, th.n_cells, smem, threads, components);
+  return launch<0, false>(c, a, th.n_cells, smem, threads, components);
+}
+
+hcg_status mech_bbox(hcg_ctx* c, double* out_dev) {
+  if (c->ncells == 0) return HCG_OK;
+  std::vector<int> hv; for (auto& t : c->types) hv.push_back(t.d.V);
+  int* dv;
+  CUDA_TRY(c, cudaMalloc(&dv, sizeof(int)*hv.size()));
+  CUDA_TRY(c, cudaMemcpyAsync(dv, hv.data(), sizeof(int)*hv.size(), cudaMemcpyHostToDevice, c->stream));
+  k_bbox<<<(unsigned)((c->ncells + 7)/8), 256, 0, c->stream>>>(c->pos[0], c->pos[1], c->pos[2], c->cell_base,
+                                                               c->cell_type, dv, c->ncells, out_dev);
+  KERNEL_CHECK(c);
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaFree(dv);
+  return HCG_OK;
+}
+
+hcg_status mech_volume_area(hcg_ctx* c, double* vol_dev, double* area_dev) {
+  for (auto& th : c->types) {
+    if (th.n_cells == 0) continue;
+    k_volume_area<<<(unsigned)((th.n_cells + 7)/8), 256, 0, c->stream>>>(c->pos[0], c->pos[1], c->pos[2],
+        th.first_cell, th.first_particle, th.n_cells, th.d.V, th.d.T, th.d.tri, vol_dev, area_dev);
+    KERNEL_CHECK(c);
+  }
+  return HCG_OK;
+}

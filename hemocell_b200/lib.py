@@ -1,0 +1,300 @@
+"""ctypes binding of libhemocell_gpu.so (include/hemocell_gpu.h) -- the harness side of the C ABI.
+
+This is what the pytest / bench harness uses to drive the product; it contains no compute and
+no fallback: if the CUDA library is missing, import fails loudly.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhemocell_gpu.so")
+
+c_dp = C.POINTER(C.c_double)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+
+FLUID, BOUNCEBACK, VEL_XN, VEL_XP, VEL_YN, VEL_YP, VEL_ZN, VEL_ZP = range(8)
+MODEL_RBC, MODEL_PLT = 0, 1
+LAT_POP, LAT_FORCE, LAT_VELOCITY, LAT_DENSITY = range(4)
+P_POS, P_VEL, P_FORCE, P_FREP, P_F_AREA, P_F_VOLUME, P_F_BEND, P_F_LINK, P_F_VISC, P_F_INNER = range(10)
+
+
+class HcgDomain(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("periodic", C.c_int32 * 3),
+                ("tau", C.c_double), ("device", C.c_int32), ("rank", C.c_int32), ("n_ranks", C.c_int32)]
+
+
+class HcgCellType(C.Structure):
+    _fields_ = [("model", C.c_int32), ("n_vertices", C.c_int32), ("n_triangles", C.c_int32),
+                ("n_edges", C.c_int32), ("n_inner_edges", C.c_int32),
+                ("triangles", c_i32p), ("edges", c_i32p), ("inner_edges", c_i32p),
+                ("vertex_vertexes", c_i32p), ("vertex_n_vertexes", c_i32p),
+                ("edge_bending_triangles", c_i32p), ("edge_bending_outer_points", c_i32p),
+                ("edge_length_eq", c_dp), ("edge_angle_eq", c_dp), ("triangle_area_eq", c_dp),
+                ("patch_dist_eq", c_dp), ("inner_edge_length_eq", c_dp),
+                ("volume_eq", C.c_double), ("area_mean_eq", C.c_double), ("edge_mean_eq", C.c_double),
+                ("k_volume", C.c_double), ("k_area", C.c_double), ("k_link", C.c_double),
+                ("k_bend", C.c_double), ("eta_m", C.c_double)]
+
+
+class HcgTimer(C.Structure):
+    _fields_ = [("name", C.c_char * 40), ("ms_total", C.c_double), ("calls", C.c_int64)]
+
+
+# every symbol include/hemocell_gpu.h declares (tests check that the .so exports all of them)
+SYMBOLS = """hcg_last_error hcg_version hcg_create hcg_destroy hcg_comm_unique_id hcg_comm_init
+hcg_lattice_set_flags hcg_lattice_set_bc_velocity hcg_lattice_init_equilibrium hcg_lattice_set_body_force
+hcg_lattice_upload hcg_lattice_download hcg_celltype_add hcg_cells_add hcg_cells_count hcg_cells_capacity
+hcg_cells_upload hcg_cells_download hcg_cells_info hcg_cells_add_force hcg_celltype_set_stiffness
+hcg_set_force_limit hcg_set_timescales hcg_set_material_timescale hcg_set_repulsion hcg_set_wall_repulsion
+hcg_set_iteration hcg_get_iteration hcg_iterate hcg_fluid_warmup hcg_op_repulsion hcg_op_wall_repulsion
+hcg_op_spread hcg_op_collide_stream hcg_op_interpolate hcg_op_sync hcg_op_advance hcg_op_mechanics
+hcg_op_zero_force hcg_cells_bbox hcg_cells_volume_area hcg_fluid_velocity_stats hcg_timers_enable
+hcg_timers hcg_timers_reset hcg_launch_count hcg_synchronize hcg_iterate_timed""".split()
+
+_lib = None
+
+
+def load():
+    """dlopen the CUDA library; raises if it was not built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _lib.hcg_last_error.restype = C.c_char_p
+        _lib.hcg_last_error.argtypes = [C.c_void_p]
+        _lib.hcg_version.restype = C.c_char_p
+    return _lib
+
+
+class HcgError(RuntimeError):
+    pass
+
+
+def _p(a, t=c_dp):
+    return a.ctypes.data_as(t)
+
+
+class Context:
+    """One hcg_ctx (one GPU).  Thin: every method is one C-ABI call."""
+
+    def __init__(self, nx, ny, nz, periodic, tau, device=0, rank=0, n_ranks=1):
+        self.L = load()
+        d = HcgDomain()
+        d.nx, d.ny, d.nz = nx, ny, nz
+        for k in range(3):
+            d.periodic[k] = int(bool(periodic[k]))
+        d.tau, d.device, d.rank, d.n_ranks = tau, device, rank, n_ranks
+        self.dom = d
+        self.h = C.c_void_p()
+        st = self.L.hcg_create(C.byref(d), C.byref(self.h))
+        if st != 0:
+            msg = self.L.hcg_last_error(self.h if self.h else None)
+            raise HcgError(f"hcg_create failed ({st}): {msg.decode() if msg else ''}")
+        self.nxl = nx // n_ranks
+        self.Nl = self.nxl * ny * nz
+        self._keep = []
+
+    def _ck(self, st):
+        if st != 0:
+            raise HcgError(f"status {st}: {self.L.hcg_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.L.hcg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- multi-GPU
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        st = load().hcg_comm_unique_id(buf)
+        if st != 0:
+            raise HcgError("hcg_comm_unique_id failed")
+        return bytes(buf)
+
+    def comm_init(self, id128):
+        buf = (C.c_uint8 * 128).from_buffer_copy(id128)
+        self._ck(self.L.hcg_comm_init(self.h, buf))
+
+    # ---- lattice
+    def set_flags(self, flags):
+        f = np.ascontiguousarray(flags, dtype=np.uint8).reshape(-1)
+        assert f.size == self.Nl
+        self._ck(self.L.hcg_lattice_set_flags(self.h, _p(f, c_u8p)))
+
+    def set_bc_velocity(self, orientation, u):
+        self._ck(self.L.hcg_lattice_set_bc_velocity(self.h, C.c_int32(orientation), (C.c_double * 3)(*u)))
+
+    def init_equilibrium(self, rho=1.0, u=(0.0, 0.0, 0.0)):
+        self._ck(self.L.hcg_lattice_init_equilibrium(self.h, C.c_double(rho), (C.c_double * 3)(*u)))
+
+    def set_body_force(self, f):
+        self._ck(self.L.hcg_lattice_set_body_force(self.h, (C.c_double * 3)(*f)))
+
+    def lattice_upload(self, field, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        assert a.size == {LAT_POP: 19, LAT_FORCE: 3}[field] * self.Nl
+        self._ck(self.L.hcg_lattice_upload(self.h, C.c_int32(field), _p(a)))
+
+    def lattice_download(self, field):
+        n = {LAT_POP: 19, LAT_FORCE: 3, LAT_VELOCITY: 3, LAT_DENSITY: 1}[field] * self.Nl
+        out = np.empty(n)
+        self._ck(self.L.hcg_lattice_download(self.h, C.c_int32(field), _p(out)))
+        return out
+
+    # ---- cells
+    def add_celltype(self, model, tables, k):
+        """tables: dict with the CommonCellConstants member names; k: dict of k_* and eta_m"""
+        a = dict(
+            triangles=np.ascontiguousarray(tables['triangle_list'], dtype=np.int32),
+            edges=np.ascontiguousarray(tables['edge_list'], dtype=np.int32),
+            inner=np.ascontiguousarray(tables['inner_edge_list'], dtype=np.int32).reshape(-1, 2),
+            vv=np.ascontiguousarray(tables['vertex_vertexes'], dtype=np.int32),
+            nvv=np.ascontiguousarray(tables['vertex_n_vertexes'], dtype=np.int32),
+            bt=np.ascontiguousarray(tables['edge_bending_triangles_list'], dtype=np.int32),
+            bo=np.ascontiguousarray(tables['edge_bending_triangles_outer_points'], dtype=np.int32),
+            el=np.ascontiguousarray(tables['edge_length_eq_list'], dtype=np.float64),
+            ea=np.ascontiguousarray(tables['edge_angle_eq_list'], dtype=np.float64),
+            ta=np.ascontiguousarray(tables['triangle_area_eq_list'], dtype=np.float64),
+            pd=np.ascontiguousarray(tables['surface_patch_center_dist_eq_list'], dtype=np.float64),
+            il=np.ascontiguousarray(tables['inner_edge_length_eq_list'], dtype=np.float64))
+        t = HcgCellType()
+        t.model = model
+        t.n_vertices = a['nvv'].shape[0]
+        t.n_triangles = a['triangles'].shape[0]
+        t.n_edges = a['edges'].shape[0]
+        t.n_inner_edges = a['inner'].shape[0]
+        t.triangles, t.edges, t.inner_edges = _p(a['triangles'], c_i32p), _p(a['edges'], c_i32p), _p(a['inner'], c_i32p)
+        t.vertex_vertexes, t.vertex_n_vertexes = _p(a['vv'], c_i32p), _p(a['nvv'], c_i32p)
+        t.edge_bending_triangles, t.edge_bending_outer_points = _p(a['bt'], c_i32p), _p(a['bo'], c_i32p)
+        t.edge_length_eq, t.edge_angle_eq, t.triangle_area_eq = _p(a['el']), _p(a['ea']), _p(a['ta'])
+        t.patch_dist_eq, t.inner_edge_length_eq = _p(a['pd']), _p(a['il'])
+        t.volume_eq, t.area_mean_eq, t.edge_mean_eq = tables['volume_eq'], tables['area_mean_eq'], tables['edge_mean_eq']
+        t.k_volume, t.k_area, t.k_link, t.k_bend, t.eta_m = k['k_volume'], k['k_area'], k['k_link'], k['k_bend'], k['eta_m']
+        out = C.c_int32(-1)
+        self._ck(self.L.hcg_celltype_add(self.h, C.byref(t), C.byref(out)))
+        return out.value
+
+    def add_cells(self, ctype, positions, cell_ids):
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        ids = np.ascontiguousarray(cell_ids, dtype=np.int64)
+        self._ck(self.L.hcg_cells_add(self.h, C.c_int32(ctype), C.c_int64(ids.shape[0]), _p(ids, c_i64p), _p(pos)))
+
+    def capacity(self):
+        nc, npt = C.c_int64(), C.c_int64()
+        self._ck(self.L.hcg_cells_capacity(self.h, C.byref(nc), C.byref(npt)))
+        return nc.value, npt.value
+
+    def count(self):
+        nc, npt = C.c_int64(), C.c_int64()
+        self._ck(self.L.hcg_cells_count(self.h, C.byref(nc), C.byref(npt)))
+        return nc.value, npt.value
+
+    def cells_upload(self, field, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        assert a.size == 3 * self.capacity()[1]
+        self._ck(self.L.hcg_cells_upload(self.h, C.c_int32(field), _p(a)))
+
+    def cells_download(self, field):
+        out = np.empty((self.capacity()[1], 3))
+        self._ck(self.L.hcg_cells_download(self.h, C.c_int32(field), _p(out)))
+        return out
+
+    def cells_info(self):
+        nc = self.capacity()[0]
+        ids, ct, alive = np.empty(nc, dtype=np.int64), np.empty(nc, dtype=np.int32), np.empty(nc, dtype=np.uint8)
+        self._ck(self.L.hcg_cells_info(self.h, _p(ids, c_i64p), _p(ct, c_i32p), _p(alive, c_u8p)))
+        return ids, ct, alive
+
+    def add_force(self, index, f):
+        idx = np.ascontiguousarray(index, dtype=np.int64)
+        ff = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        self._ck(self.L.hcg_cells_add_force(self.h, C.c_int64(idx.shape[0]), _p(idx, c_i64p), _p(ff)))
+
+    # ---- knobs
+    def set_force_limit(self, f):
+        self._ck(self.L.hcg_set_force_limit(self.h, C.c_double(f)))
+
+    def set_timescales(self, velocity=1, repulsion=1, wall=1):
+        self._ck(self.L.hcg_set_timescales(self.h, C.c_int32(velocity), C.c_int32(repulsion), C.c_int32(wall)))
+
+    def set_material_timescale(self, ctype, every):
+        self._ck(self.L.hcg_set_material_timescale(self.h, C.c_int32(ctype), C.c_int32(every)))
+
+    def set_repulsion(self, on, k, cutoff):
+        self._ck(self.L.hcg_set_repulsion(self.h, C.c_int32(int(on)), C.c_double(k), C.c_double(cutoff)))
+
+    def set_wall_repulsion(self, on, k, cutoff):
+        self._ck(self.L.hcg_set_wall_repulsion(self.h, C.c_int32(int(on)), C.c_double(k), C.c_double(cutoff)))
+
+    def set_iteration(self, it):
+        self._ck(self.L.hcg_set_iteration(self.h, C.c_int64(it)))
+
+    @property
+    def iteration(self):
+        it = C.c_int64()
+        self._ck(self.L.hcg_get_iteration(self.h, C.byref(it)))
+        return it.value
+
+    # ---- run
+    def iterate(self, n=1):
+        self._ck(self.L.hcg_iterate(self.h, C.c_int64(n)))
+
+    def iterate_timed(self, n):
+        ms = C.c_double()
+        self._ck(self.L.hcg_iterate_timed(self.h, C.c_int64(n), C.byref(ms)))
+        return ms.value
+
+    def fluid_warmup(self, n):
+        self._ck(self.L.hcg_fluid_warmup(self.h, C.c_int64(n)))
+
+    def op(self, name, *args):
+        fn = getattr(self.L, "hcg_op_" + name)
+        self._ck(fn(self.h, *[C.c_int32(int(a)) for a in args]))
+
+    # ---- observables / timing
+    def bbox(self):
+        out = np.empty((self.capacity()[0], 6))
+        self._ck(self.L.hcg_cells_bbox(self.h, _p(out)))
+        return out
+
+    def volume_area(self):
+        nc = self.capacity()[0]
+        v, a = np.empty(nc), np.empty(nc)
+        self._ck(self.L.hcg_cells_volume_area(self.h, _p(v), _p(a)))
+        return v, a
+
+    def velocity_stats(self):
+        a, b, m = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.L.hcg_fluid_velocity_stats(self.h, C.byref(a), C.byref(b), C.byref(m)))
+        return a.value, b.value, m.value
+
+    def timers_enable(self, on=True):
+        self._ck(self.L.hcg_timers_enable(self.h, C.c_int32(int(on))))
+
+    def timers(self):
+        n = C.c_int32(64)
+        arr = (HcgTimer * 64)()
+        self._ck(self.L.hcg_timers(self.h, arr, C.byref(n)))
+        return {arr[k].name.decode(): (arr[k].ms_total, arr[k].calls) for k in range(min(n.value, 64))}
+
+    def timers_reset(self):
+        self._ck(self.L.hcg_timers_reset(self.h))
+
+    def launch_count(self):
+        n = C.c_int64()
+        self._ck(self.L.hcg_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def synchronize(self):
+        self._ck(self.L.hcg_synchronize(self.h))

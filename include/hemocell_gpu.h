@@ -1,0 +1,186 @@
+/*
+ * hemocell_gpu.h -- C ABI of the B200-native HemoCell hot path (libhemocell_gpu.so).
+ *
+ * The reference (UvaCsl/HemoCell) has no FFI boundary: its per-timestep path is reached
+ * through C++ classes.  Every entry point below names the reference interface it replaces
+ * (paths relative to the reference tree).  Host arrays are caller-owned, plain pointers and
+ * sizes; no pointer handed out by the library outlives hcg_destroy(); uploads/downloads are
+ * synchronous with respect to the context's streams.  Nothing here throws or exit()s: every
+ * call returns an hcg_status and hcg_last_error() holds the message.
+ *
+ * Conventions
+ *   node index    idx = z + nz*(y + ny*x)  (patch/palabos.patch:245), x,y,z GLOBAL coordinates
+ *   populations   pop[q*N + idx], q = 0..18 in Palabos D3Q19 order, stored as f_q - t_q,
+ *                 POST-STREAM (what Palabos holds between collideAndStream() calls)
+ *   node vectors  a[d*N + idx], d = 0..2
+ *   flags         uint8: HCG_FLUID, HCG_BOUNCEBACK, HCG_VEL_* (velocity plane, OUTWARD normal)
+ *   particles     AoS xyz, cells contiguous, vertices in vertexId order, cell types in the
+ *                 order they were added:  a[3*(base(cell) + vertexId) + d]
+ *   multi-GPU     one context per rank/GPU; the lattice is cut into n_ranks slabs along x.
+ *                 Lattice up/downloads take/return the rank's own slab (nx_local*ny*nz nodes,
+ *                 same index formula with x local); particle calls are per rank.
+ */
+#ifndef HEMOCELL_GPU_H
+#define HEMOCELL_GPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hcg_ctx hcg_ctx;
+typedef int32_t hcg_status;               /* 0 = ok, < 0 = error */
+#define HCG_OK 0
+#define HCG_ERR_ARG (-1)
+#define HCG_ERR_CUDA (-2)
+#define HCG_ERR_STATE (-3)
+#define HCG_ERR_NCCL (-4)
+#define HCG_ERR_CAPACITY (-5)
+
+enum { HCG_FLUID = 0, HCG_BOUNCEBACK = 1, HCG_VEL_XN = 2, HCG_VEL_XP = 3, HCG_VEL_YN = 4,
+       HCG_VEL_YP = 5, HCG_VEL_ZN = 6, HCG_VEL_ZP = 7 };
+enum { HCG_MODEL_RBC_HIGHORDER = 0, HCG_MODEL_PLT_SIMPLE = 1 };
+/* lattice fields */
+enum { HCG_LAT_POP = 0, HCG_LAT_FORCE = 1, HCG_LAT_VELOCITY = 2, HCG_LAT_DENSITY = 3 };
+/* particle fields */
+enum { HCG_P_POS = 0, HCG_P_VEL = 1, HCG_P_FORCE = 2, HCG_P_FREP = 3, HCG_P_F_AREA = 4,
+       HCG_P_F_VOLUME = 5, HCG_P_F_BEND = 6, HCG_P_F_LINK = 7, HCG_P_F_VISC = 8, HCG_P_F_INNER = 9 };
+
+/* MultiBlockLattice3D ctor + periodicity().toggle + GuoExternalForceBGKdynamics(1/tau)
+ * (cases/performance_testing/performance_testing.cpp:55-67) */
+typedef struct {
+  int32_t nx, ny, nz;          /* global lattice */
+  int32_t periodic[3];
+  double tau;
+  int32_t device;              /* CUDA device ordinal of this context */
+  int32_t rank, n_ranks;       /* slab decomposition along x; nx % n_ranks == 0 */
+} hcg_domain;
+
+/* CommonCellConstants (mechanics/commonCellConstants.h:39-86) + the k_* of the model
+ * (mechanics/rbcHighOrderModel.h:34-51, mechanics/cellMechanics.h:50-78) */
+typedef struct {
+  int32_t model;               /* HCG_MODEL_* */
+  int32_t n_vertices, n_triangles, n_edges, n_inner_edges;
+  const int32_t* triangles;                   /* [T][3] triangle_list */
+  const int32_t* edges;                       /* [E][2] edge_list */
+  const int32_t* inner_edges;                 /* [I][2] inner_edge_list */
+  const int32_t* vertex_vertexes;             /* [V][6] ring ordered, -1 padded */
+  const int32_t* vertex_n_vertexes;           /* [V] */
+  const int32_t* edge_bending_triangles;      /* [E][2] */
+  const int32_t* edge_bending_outer_points;   /* [E][2] */
+  const double* edge_length_eq;               /* [E] */
+  const double* edge_angle_eq;                /* [E] */
+  const double* triangle_area_eq;             /* [T] */
+  const double* patch_dist_eq;                /* [V] surface_patch_center_dist_eq_list */
+  const double* inner_edge_length_eq;         /* [I] */
+  double volume_eq, area_mean_eq, edge_mean_eq;
+  double k_volume, k_area, k_link, k_bend, eta_m;
+} hcg_celltype;
+
+typedef struct {               /* helper/profiler.h:47-76 key names, CUDA-event times */
+  char name[40];
+  double ms_total;
+  int64_t calls;
+} hcg_timer;
+
+const char* hcg_last_error(const hcg_ctx*);   /* ctx may be NULL: error of a failed hcg_create */
+const char* hcg_version(void);
+
+/* ---- lifetime: HemoCell ctor/dtor + initializeLattice (core/hemoCell.cpp:69-127, 438-583) */
+hcg_status hcg_create(const hcg_domain* d, hcg_ctx** out);
+void       hcg_destroy(hcg_ctx*);
+
+/* ---- multi-GPU plumbing (replaces plb::plbInit/MPI_Init + ParallelBlockCommunicator3D).
+ * The caller distributes the 128-byte NCCL unique id of rank 0 (e.g. torch.distributed
+ * broadcast); one context per process/GPU. */
+hcg_status hcg_comm_unique_id(void* out128);
+hcg_status hcg_comm_init(hcg_ctx*, const void* id128);
+
+/* ---- lattice set-up */
+/* defineDynamics(lattice, domain, new BounceBack) / setVelocityConditionOnBlockBoundaries
+ * (examples/cube/cube.cpp:74-88, helper/hemocellInit.hh:64-73): flags of this rank's slab */
+hcg_status hcg_lattice_set_flags(hcg_ctx*, const uint8_t* flags);
+/* setBoundaryVelocity(lattice, plane, u) (helper/hemocellInit.hh:75-77): one wall velocity per
+ * velocity-plane orientation, index = flag - HCG_VEL_XN */
+hcg_status hcg_lattice_set_bc_velocity(hcg_ctx*, int32_t orientation, const double u[3]);
+/* HemoCell::latticeEquilibrium -> initializeAtEquilibrium (core/hemoCell.cpp:129-133) */
+hcg_status hcg_lattice_init_equilibrium(hcg_ctx*, double rho, const double u[3]);
+/* the setExternalVector(lattice, bbox, forceBeginsAt, f) every case file re-applies after
+ * iterate() (examples/pipeflow/pipeflow.cpp:144-146): the value the node force is reset to */
+hcg_status hcg_lattice_set_body_force(hcg_ctx*, const double f[3]);
+hcg_status hcg_lattice_upload(hcg_ctx*, int32_t field /*POP|FORCE*/, const double* in);
+hcg_status hcg_lattice_download(hcg_ctx*, int32_t field /*POP|FORCE|VELOCITY|DENSITY*/, double* out);
+
+/* ---- cell types and cells */
+/* HemoCell::addCellType<Model>(name, constructType) (hemocell.h:122-128) */
+hcg_status hcg_celltype_add(hcg_ctx*, const hcg_celltype* t, int32_t* ctype_out);
+/* HemoCell::loadParticles (core/hemoCell.cpp:191-197) after placement: all cells of one type,
+ * call once per type in type order.  pos: [n_cells][V][3]. */
+hcg_status hcg_cells_add(hcg_ctx*, int32_t ctype, int64_t n_cells, const int64_t* cell_id, const double* pos);
+hcg_status hcg_cells_count(hcg_ctx*, int64_t* n_cells_alive, int64_t* n_particles_alive);
+/* whole-array particle access in storage order incl. deleted cells (alive_out marks them);
+ * needed by per-operator parity tests and checkpoint restore.  n = hcg_cells_capacity */
+hcg_status hcg_cells_capacity(hcg_ctx*, int64_t* n_cells, int64_t* n_particles);
+hcg_status hcg_cells_upload(hcg_ctx*, int32_t field /*POS|VEL|FORCE|FREP*/, const double* in);
+hcg_status hcg_cells_download(hcg_ctx*, int32_t field, double* out);
+hcg_status hcg_cells_info(hcg_ctx*, int64_t* cell_id_out, int32_t* ctype_out, uint8_t* alive_out);
+/* HemoCellStretch::applyForce (helper/hemoCellStretch.cpp:63-78, 102-110): force[lsp] += f */
+hcg_status hcg_cells_add_force(hcg_ctx*, int64_t n, const int64_t* particle_index, const double* f /*[n][3]*/);
+/* stiffness update without re-uploading topology (CellMechanics k_* members) */
+hcg_status hcg_celltype_set_stiffness(hcg_ctx*, int32_t ctype, double k_volume, double k_area,
+                                      double k_link, double k_bend, double eta_m);
+
+/* ---- knobs */
+/* Parameters::f_limit (mechanics/constantConversion.cpp:55-57) */
+hcg_status hcg_set_force_limit(hcg_ctx*, double f_limit_lbm);
+/* setParticleVelocityUpdateTimeScaleSeparation / setRepulsionTimeScaleSeperation /
+ * enableBoundaryParticles step / setMaterialTimeScaleSeparation (hemocell.h:158-176) */
+hcg_status hcg_set_timescales(hcg_ctx*, int32_t velocity, int32_t repulsion, int32_t wall_repulsion);
+hcg_status hcg_set_material_timescale(hcg_ctx*, int32_t ctype, int32_t every);
+/* HemoCell::setRepulsion(k, cutoff) (core/hemoCell.cpp:420-426); cutoff in lattice units;
+ * enabled != 0 switches the operator on inside hcg_iterate */
+hcg_status hcg_set_repulsion(hcg_ctx*, int32_t enabled, double k, double cutoff_lu);
+/* HemoCell::enableBoundaryParticles (core/hemoCell.cpp:428-436) */
+hcg_status hcg_set_wall_repulsion(hcg_ctx*, int32_t enabled, double k, double cutoff_lu);
+/* store the interpolation velocity field u = j/rho + F/2 explicitly (1) or gather it from the
+ * populations inside the interpolation kernel (0) */
+hcg_status hcg_set_iteration(hcg_ctx*, int64_t iter);
+hcg_status hcg_get_iteration(hcg_ctx*, int64_t* iter);
+
+/* ---- run: HemoCell::iterate() x n (core/hemoCell.cpp:299-376), incl. the case file's
+ * lattice->collideAndStream() warm-up loop when fluid_only != 0 */
+hcg_status hcg_iterate(hcg_ctx*, int64_t n_steps);
+hcg_status hcg_fluid_warmup(hcg_ctx*, int64_t n_steps);
+
+/* ---- per-operator entry points (single-step parity; same order as iterate()) */
+hcg_status hcg_op_repulsion(hcg_ctx*);       /* HemoCellFields::applyRepulsionForce          */
+hcg_status hcg_op_wall_repulsion(hcg_ctx*);  /* HemoCellFields::applyBoundaryRepulsionForce  */
+hcg_status hcg_op_spread(hcg_ctx*);          /* HemoCellFields::spreadParticleForce          */
+hcg_status hcg_op_collide_stream(hcg_ctx*);  /* lattice->collideAndStream()                  */
+hcg_status hcg_op_interpolate(hcg_ctx*);     /* HemoCellFields::interpolateFluidVelocity     */
+hcg_status hcg_op_sync(hcg_ctx*);            /* HemoCellFields::syncEnvelopes (multi-GPU)    */
+hcg_status hcg_op_advance(hcg_ctx*);         /* HemoCellFields::advanceParticles             */
+hcg_status hcg_op_mechanics(hcg_ctx*, int32_t forced, int32_t components); /* applyConstitutiveModel */
+hcg_status hcg_op_zero_force(hcg_ctx*);      /* setExternalVector(lattice, bbox, 0 | body)   */
+
+/* ---- observables (helper/cellInfo.cpp, helper/fluidInfo.cpp): per cell in storage order */
+hcg_status hcg_cells_bbox(hcg_ctx*, double* bbox /*[n_cells][6] xmin xmax ymin ymax zmin zmax*/);
+hcg_status hcg_cells_volume_area(hcg_ctx*, double* volume, double* area);
+hcg_status hcg_fluid_velocity_stats(hcg_ctx*, double* vmin, double* vmax, double* vmean);
+
+/* ---- timing (helper/profiler.cpp): CUDA-event totals under the reference's key names */
+hcg_status hcg_timers_enable(hcg_ctx*, int32_t on);
+hcg_status hcg_timers(hcg_ctx*, hcg_timer* out, int32_t* n_inout);
+hcg_status hcg_timers_reset(hcg_ctx*);
+/* number of kernels launched by this context so far */
+hcg_status hcg_launch_count(hcg_ctx*, int64_t* n);
+hcg_status hcg_synchronize(hcg_ctx*);
+
+/* ---- device-resident benchmark support: step with CUDA events bracketing n_steps,
+ * returns elapsed milliseconds on the context's stream */
+hcg_status hcg_iterate_timed(hcg_ctx*, int64_t n_steps, double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
