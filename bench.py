@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the HemoCell per-timestep IB-LBM hot path on B200.
+
+Metric (BASELINE.json): MLUPS (D3Q19 fp64, with RBCs) and cell-steps/s.
+Workload at N GPUs: the cases/performance_testing weak-scaling unit, 256^3 lattice nodes per
+GPU (domain 256*N x 256 x 256, slabs along x), fully periodic, tau = 1, body force (f,f,f),
+RBCs seeded to ~33 % hematocrit per unit (synthetic, seeded lattice packing), material update
+every 20 steps, velocity interpolation every `--cadence` steps (1 = configs/, 5 = configs_timestep_5/).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU oracle on the host cores
+
+One JSON line on stdout (rank 0).  A "step" is one HemoCell::iterate().
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MLUPS (D3Q19 fp64, with RBCs)"
+UNIT_N = 256                       # lattice nodes per edge of one weak-scaling unit
+DX = 0.5e-6
+B_LU = 304.0                       # algorithmic bytes per lattice update (19 reads + 19 writes, fp64)
+
+
+# ----------------------------------------------------------------------------- workload
+def synthetic_rows(unit_n=UNIT_N, seed=1234):
+    """Seeded hematocrit packing of one unit: RBC discs on a 15 x 15 x 38 lattice (x, y, z spacing
+    17.07 x 17.07 x 6.74 lu, disc axis along z), jittered by +-0.25 lu.  8550 cells * 81.1 um^3 /
+    (128 um)^3 = 33 % hematocrit.  Rows are .pos records: centre in um, angles in degrees."""
+    s = unit_n / 256.0
+    nxy, nz = max(1, int(round(15 * s))), max(1, int(round(38 * s)))
+    rng = np.random.default_rng(seed)
+    ix, iy, iz = np.meshgrid(np.arange(nxy), np.arange(nxy), np.arange(nz), indexing="ij")
+    ctr = np.stack([(ix + 0.5) * unit_n / nxy, (iy + 0.5) * unit_n / nxy, (iz + 0.5) * unit_n / nz], -1).reshape(-1, 3)
+    ctr = ctr + rng.uniform(-0.25, 0.25, ctr.shape)
+    rows = np.zeros((ctr.shape[0], 6))
+    rows[:, 0:3] = ctr * (DX / 1e-6)          # lattice units -> um
+    rows[:, 3] = 90.0                          # disc axis y -> z, as examples/oneCellShear/RBC.pos
+    return rows
+
+
+def body_force(nu_lbm, n):
+    """performance_testing.cpp:74-78: 8 nu (u_max/2) / R^2 with u_max = Re nu / (2 R), Re 0.5, R = n/2"""
+    u_max = 0.5 * nu_lbm / n           # lbm_pipe_parameters(cfg, nx): pipe_radius = nx
+    r = n / 2.0
+    f = 8 * nu_lbm * (u_max * 0.5) / r / r
+    return (f, f, f)
+
+
+# ----------------------------------------------------------------------------- helpers
+def pinned_empty(n_doubles):
+    """page-locked host buffer through cudart (the C ABI takes plain host pointers)"""
+    rt = C.CDLL("libcudart.so.12")
+    ptr = C.c_void_p()
+    rc = rt.cudaHostAlloc(C.byref(ptr), C.c_size_t(8 * n_doubles), C.c_uint(0))
+    if rc != 0:
+        raise RuntimeError(f"cudaHostAlloc failed: {rc}")
+    buf = (C.c_double * n_doubles).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=np.float64)
+    _PINNED.append((rt, ptr, buf))
+    return arr
+
+
+_PINNED = []
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, ln in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("dram_bytes_per_launch_256cubed")
+    return None
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_cuda(args):
+    rank, world = args.rank, args.world
+    from hemocell_b200 import lib as H
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(args.local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", args.local_rank))
+    par = H.parameters(DX, -1.0)
+    ct = H.HostCellType(H.MODEL_RBC, H.RBC_FROM_SPHERE, par, H.RBC_MATERIAL)
+    rows = synthetic_rows()
+    nx = UNIT_N * world
+    # every unit gets the same packing, shifted along x (examples/cube/preprocess/analysis.py:cell_positions)
+    unit_cells, unit_ids = ct.place(rows, DX, (UNIT_N, UNIT_N, UNIT_N))
+    n_unit = len(unit_ids)
+    ctx = H.Context(nx, UNIT_N, UNIT_N, (1, 1, 1), par["tau"], device=args.local_rank, rank=rank, n_ranks=world)
+    if world > 1:
+        import torch
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idbuf.copy_(torch.frombuffer(bytearray(H.Context.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        ctx.comm_init(bytes(idbuf.cpu().numpy().tobytes()))
+    ctx.set_flags(np.zeros(ctx.Nl, dtype=np.uint8))
+    ctx.set_body_force(body_force(par["nu_lbm"], UNIT_N))
+    ctx.set_force_limit(par["f_limit"])
+    t = ct.add_to(ctx)
+    cells, ids = ctx.select_local_cells(unit_cells, unit_ids, UNIT_N, world) if world > 1 else (unit_cells, unit_ids)
+    pos_host = pinned_empty(cells.size)
+    pos_host[:] = cells.reshape(-1)
+    ctx.add_cells(t, pos_host.reshape(cells.shape), ids)
+    ctx.set_timescales(args.cadence, 1, 1)
+    ctx.set_material_timescale(t, 20)
+    n_cells_global = n_unit * world
+    nodes = nx * UNIT_N * UNIT_N
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        import torch
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- device-resident leg: W warm-up steps, then exactly K timed steps
+    ctx.iterate(args.warmup)
+    launches0 = ctx.launch_count()
+    ctx.timers_enable(True); ctx.timers_reset()
+    sampler = ClockSampler(args.local_rank) if rank == 0 else None
+    barrier()
+    t0 = time.time()
+    ms = ctx.iterate_timed(args.steps)            # CUDA events on the launching stream
+    barrier()
+    t1 = time.time()
+    ms = max_over_ranks(ms)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    launches = ctx.launch_count() - launches0
+    timers = ctx.timers()
+    ctx.timers_enable(False)
+    alive_cells = ctx.count()[0]
+
+    # ---- end-to-end leg through the C ABI with HOST buffers (pinned): state upload, K x
+    # (body force H2D + iterate(1) + cell-count D2H), final read-back of positions and forces
+    npart = ctx.capacity()[1]
+    out_pos = pinned_empty(3 * npart); out_frc = pinned_empty(3 * npart)
+    ctx.set_iteration(0)
+    barrier()
+    te0 = time.time()
+    ctx.cells_upload(H.P_POS, pos_host)
+    bf = body_force(par["nu_lbm"], UNIT_N)
+    for _ in range(args.steps):
+        ctx.set_body_force(bf)                    # setExternalVector after every iterate (performance_testing.cpp:132-135)
+        ctx.iterate(1)
+        ctx.count()
+    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), out_pos.ctypes.data_as(H.c_dp))
+    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_FORCE), out_frc.ctypes.data_as(H.c_dp))
+    barrier()
+    e2e_ms = max_over_ranks((time.time() - te0) * 1e3)
+    h2d = (8 * 3 * npart) / args.steps + 24
+    d2h = (2 * 8 * 3 * npart) / args.steps + 16
+
+    if rank != 0:
+        ctx.close()
+        return None
+    k1_ms, k1_calls = timers.get("kernel:k_collide_stream", (0.0, 0))
+    peak, peak_src = measured_peak()
+    nodes_local = UNIT_N ** 3
+    k1_avg_ms = k1_ms / max(k1_calls, 1)
+    achieved = B_LU * nodes_local / (k1_avg_ms * 1e-3) / 1e9 if k1_calls else None
+    line = {
+        "metric": METRIC, "value": nodes * args.steps / (ms * 1e-3) / 1e6, "unit": "MLUPS",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "cell_steps_per_s": (alive_cells if world == 1 else n_cells_global) * args.steps / (ms * 1e-3),
+        "config": {"workload": f"cases/performance_testing unit: {nx}x{UNIT_N}x{UNIT_N} D3Q19 fp64, fully periodic, tau=1, "
+                               f"body force, {n_cells_global} RBC (642 LSP each, ~33% hematocrit), material every 20, "
+                               f"velocity every {args.cadence}",
+                   "lattice": [nx, UNIT_N, UNIT_N], "cells": n_cells_global, "lsp": n_cells_global * ct.V,
+                   "velocity_cadence": args.cadence, "material_cadence": 20, "decomposition": f"{world} x-slabs",
+                   "l2": "inputs (5.1 GB of populations per GPU) are far larger than the 126 MB L2; no flush needed"},
+        "roofline": {"bound": "hbm", "kernel": "k_collide_stream", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(),
+                     "peak_source": peak_src, "bytes_per_lu": B_LU, "launch_ms": k1_avg_ms, "launches_timed": k1_calls},
+        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()},
+        "e2e": {"value": nodes * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "MLUPS",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    ctx.close()
+    return line
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def run_cpu(steps, warmup, cadence, budget_s=150.0):
+    """The reference cannot be built (Palabos/MPI/HDF5 absent): time the CPU oracle (a port) with
+    OpenMP on the host cores, on a bounded sub-box of the same workload (same packing density)."""
+    import oracle as O
+    from oracle import mesh as M
+    cores = os.cpu_count() or 1
+    O.set_parallel(1)
+    par = M.Parameters(DX, -1.0)
+    ct = O.rbc_celltype(par)
+
+    def make(n):
+        rows = synthetic_rows(n)
+        cells, ids = M.place_cells(ct.verts, rows, DX, (n, n, n))
+        dom = O.make_domain(n, n, n, (1, 1, 1), par.tau)
+        sim = O.OracleSim(dom, np.zeros(n ** 3, dtype=np.uint8), par.f_limit, body_force(par.nu_lbm, UNIT_N))
+        sim.vel_timescale = cadence
+        sim.add_celltype(ct, 20)
+        sim.add_cells(0, cells, ids)
+        return sim, len(ids)
+
+    # pick the sample so that (steps + warmup) iterations fit the budget
+    sim, ncell = make(64)
+    t = time.time(); sim.iterate(); sim.iterate(); per64 = (time.time() - t) / 2
+    n = 64
+    for cand in (128, 96):
+        if per64 * (cand / 64.0) ** 3 * (steps + warmup) <= budget_s:
+            n = cand
+            break
+    if n != 64:
+        sim, ncell = make(n)
+    for _ in range(warmup):
+        sim.iterate()
+    t0 = time.time()
+    for _ in range(steps):
+        sim.iterate()
+    dt = time.time() - t0
+    return {"value": n ** 3 * steps / dt / 1e6, "unit": "MLUPS", "cores": cores, "kind": "port",
+            "sample": f"{n}^3 periodic sub-box of the same workload, {ncell} RBC, {steps} iterate() steps, "
+                      f"OpenMP on {cores} threads, CPU oracle (restatement, not the reference build)",
+            "ms_per_step": dt / steps * 1e3, "cell_steps_per_s": ncell * steps / dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--cadence", type=int, default=1, help="velocity interpolation every n steps (stepParticleEvery)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.rank = int(os.environ.get("RANK", "0"))
+    args.world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.rank != 0:
+            return
+        cb = run_cpu(args.steps, args.warmup, args.cadence)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "MLUPS", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "cases/performance_testing unit (bounded CPU sample, see cpu_baseline.sample)",
+                           "velocity_cadence": args.cadence, "material_cadence": 20},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    line = run_cuda(args)
+    if args.rank != 0:
+        return
+    if args.world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = run_cpu(6, 1, args.cadence, budget_s=30.0)
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

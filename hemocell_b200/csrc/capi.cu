@@ -94,21 +94,6 @@ hcg_status exchange_flags(hcg_ctx* c) {
   return HCG_OK;
 }
 
-struct OpTimer {
-  hcg_ctx* c; const char* name; bool on;
-  OpTimer(hcg_ctx* c_, const char* n) : c(c_), name(n), on(c_->timers_on) { if (on) cudaEventRecord(c->ev_a, c->stream); }
-  ~OpTimer() {
-    if (!on) return;
-    cudaEventRecord(c->ev_b, c->stream); cudaEventSynchronize(c->ev_b);
-    float ms = 0; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
-    auto it = c->timer_idx.find(name);
-    int k;
-    if (it == c->timer_idx.end()) { k = (int)c->timers.size(); c->timers.push_back({name, 0.0, 0}); c->timer_idx[name] = k; }
-    else k = it->second;
-    c->timers[k].ms += ms; c->timers[k].calls++;
-  }
-};
-
 hcg_status do_mechanics(hcg_ctx* c, bool forced, bool components) {
   OpTimer t(c, "applyConstitutiveModel");
   for (size_t k = 0; k < c->types.size(); k++) {
@@ -213,6 +198,8 @@ void hcg_destroy(hcg_ctx* c) {
   cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->bin_items); cudaFree(c->wall_nodes); cudaFree(c->scan_tmp);
   cudaFree(c->staging);
   for (auto& t : c->types) for (void* p : t.allocs) cudaFree(p);
+  for (auto& p : c->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
   cudaStreamDestroy(c->stream); cudaStreamDestroy(c->stream_halo);
   delete c;
@@ -594,17 +581,16 @@ hcg_status hcg_iterate(hcg_ctx* c, int64_t n) {
 hcg_status hcg_iterate_timed(hcg_ctx* c, int64_t n, double* ms_out) {
   if (!c || n < 0 || !ms_out) return HCG_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
-  const bool t_on = c->timers_on; c->timers_on = false;
   cudaEvent_t a, b;
   CUDA_TRY(c, cudaEventCreate(&a)); CUDA_TRY(c, cudaEventCreate(&b));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   CUDA_TRY(c, cudaEventRecord(a, c->stream));
-  for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) { c->timers_on = t_on; return s; } }
+  for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) return s; }
   CUDA_TRY(c, cudaEventRecord(b, c->stream));
   CUDA_TRY(c, cudaEventSynchronize(b));
   float ms = 0; CUDA_TRY(c, cudaEventElapsedTime(&ms, a, b));
   cudaEventDestroy(a); cudaEventDestroy(b);
-  *ms_out = ms; c->timers_on = t_on;
+  *ms_out = ms;
   return HCG_OK;
 }
 
@@ -663,9 +649,10 @@ hcg_status hcg_fluid_velocity_stats(hcg_ctx* c, double* vmin, double* vmax, doub
 }
 
 hcg_status hcg_timers_enable(hcg_ctx* c, int32_t on) { if (!c) return HCG_ERR_ARG; c->timers_on = on != 0; return HCG_OK; }
-hcg_status hcg_timers_reset(hcg_ctx* c) { if (!c) return HCG_ERR_ARG; c->timers.clear(); c->timer_idx.clear(); return HCG_OK; }
+hcg_status hcg_timers_reset(hcg_ctx* c) { if (!c) return HCG_ERR_ARG; resolve_timers(c); c->timers.clear(); c->timer_idx.clear(); return HCG_OK; }
 hcg_status hcg_timers(hcg_ctx* c, hcg_timer* out, int32_t* n) {
   if (!c || !n) return HCG_ERR_ARG;
+  resolve_timers(c);
   const int have = (int)c->timers.size();
   if (out) for (int k = 0; k < have && k < *n; k++) {
     memset(out[k].name, 0, sizeof(out[k].name));

@@ -39,6 +39,7 @@ struct CellTypeHost {
 };
 
 struct TimerSlot { std::string name; double ms = 0; int64_t calls = 0; };
+struct TimerPending { int slot; cudaEvent_t a, b; };
 
 struct hcg_ctx {
   hcg_domain dom;
@@ -76,6 +77,7 @@ struct hcg_ctx {
   void* nccl;                  // ncclComm_t
   double* halo_send[2]; double* halo_recv[2];
   bool timers_on; std::vector<TimerSlot> timers; std::map<std::string,int> timer_idx;
+  std::vector<cudaEvent_t> ev_pool; std::vector<TimerPending> ev_pending;
   int64_t launches;
   std::string err;
   double* staging; size_t staging_bytes;   // device scratch for AoS<->SoA transposes
@@ -86,6 +88,32 @@ hcg_status hcg_fail(hcg_ctx* c, hcg_status code, const std::string& msg);
   return hcg_fail((c), HCG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
 #define KERNEL_CHECK(c) do { (c)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
   return hcg_fail((c), HCG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); } while (0)
+
+// CUDA-event timers under the reference's Profiler key names (helper/profiler.cpp).  Events are
+// recorded on the launching stream without any host synchronisation; they are resolved in
+// resolve_timers() (hcg_timers), so enabling them does not serialise the step.
+struct OpTimer {
+  hcg_ctx* c; int slot; cudaEvent_t a, b; bool on;
+  OpTimer(hcg_ctx* c_, const char* name) : c(c_), slot(-1), on(c_->timers_on) {
+    if (!on) return;
+    auto it = c->timer_idx.find(name);
+    if (it == c->timer_idx.end()) { slot = (int)c->timers.size(); c->timers.push_back({name, 0.0, 0}); c->timer_idx[name] = slot; }
+    else slot = it->second;
+    if (c->ev_pool.size() < 2) { cudaEvent_t e; cudaEventCreate(&e); c->ev_pool.push_back(e); cudaEventCreate(&e); c->ev_pool.push_back(e); }
+    a = c->ev_pool.back(); c->ev_pool.pop_back(); b = c->ev_pool.back(); c->ev_pool.pop_back();
+    cudaEventRecord(a, c->stream);
+  }
+  ~OpTimer() { if (!on) return; cudaEventRecord(b, c->stream); c->ev_pending.push_back({slot, a, b}); }
+};
+inline void resolve_timers(hcg_ctx* c) {
+  cudaStreamSynchronize(c->stream);
+  for (auto& p : c->ev_pending) {
+    float ms = 0; cudaEventElapsedTime(&ms, p.a, p.b);
+    c->timers[p.slot].ms += ms; c->timers[p.slot].calls++;
+    c->ev_pool.push_back(p.a); c->ev_pool.push_back(p.b);
+  }
+  c->ev_pending.clear();
+}
 
 // lattice.cu
 hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force);

@@ -337,12 +337,15 @@ hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
   const int64_t n = (int64_t)c->nxl*c->P;
   double* gin = c->g[c->cur]; double* gout = c->g[1 - c->cur];
   const unsigned nb = nblk(n, 256);
+  {
+  OpTimer tk(c, "kernel:k_collide_stream");
   if (c->has_velbc) {
     if (reset_force) k_collide_stream<true, true><<<nb, 256, 0, c->stream>>>(gin, gout, c->F, c->flags, a);
     else k_collide_stream<false, true><<<nb, 256, 0, c->stream>>>(gin, gout, c->F, c->flags, a);
   } else {
     if (reset_force) k_collide_stream<true, false><<<nb, 256, 0, c->stream>>>(gin, gout, c->F, c->flags, a);
     else k_collide_stream<false, false><<<nb, 256, 0, c->stream>>>(gin, gout, c->F, c->flags, a);
+  }
   }
   KERNEL_CHECK(c);
   c->cur = 1 - c->cur;
@@ -355,12 +358,15 @@ hcg_status lat_moments(hcg_ctx* c, bool reset_force, bool want_rho) {
   const int64_t n = (int64_t)c->nxl*c->P;
   const unsigned nb = nblk(n, 256);
   if (want_rho && !c->rho) CUDA_TRY(c, cudaMalloc(&c->rho, sizeof(double)*c->S));
+  {
+  OpTimer tk(c, "kernel:k_moments");
   if (reset_force) {
     if (want_rho) k_moments<true, true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->rho, c->flags, a);
     else k_moments<true, false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->rho, c->flags, a);
   } else {
     if (want_rho) k_moments<false, true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->rho, c->flags, a);
     else k_moments<false, false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->rho, c->flags, a);
+  }
   }
   KERNEL_CHECK(c);
   c->u_valid = true;

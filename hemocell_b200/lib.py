@@ -298,3 +298,110 @@ class Context:
 
     def synchronize(self):
         self._ck(self.L.hcg_synchronize(self.h))
+
+
+# ------------------------------------------------------------------ host-side set-up (C++ in the same .so)
+HOST_SYMBOLS = """hch_parameters hch_celltype_build hch_celltype_view hch_celltype_vertices hch_celltype_scalar
+hch_celltype_free hch_read_pos hch_place_cells hch_last_error""".split()
+
+RBC_MATERIAL = dict(kBend=80.0, kVolume=20.0, kArea=5.0, kLink=15.0, eta_m=0.0, minNumTriangles=600,
+                    radius=3.91e-6, aspectRatio=0.3)
+PLT_MATERIAL = dict(kBend=250.0, kVolume=100.0, kArea=8.0, kLink=25.0, eta_m=0.0, minNumTriangles=66,
+                    radius=1.25e-6, aspectRatio=0.434782608696)
+PLT_INNER_EDGES = [(60, 65), (62, 64), (37, 42), (54, 56), (34, 40), (25, 46), (50, 59), (29, 47), (61, 63),
+                   (26, 45), (33, 43), (27, 35), (32, 39), (49, 51), (0, 4), (48, 52), (6, 10), (53, 55),
+                   (19, 21), (57, 58), (15, 13)]
+RBC_FROM_SPHERE, ELLIPSOID_FROM_SPHERE = 1, 6
+
+
+def parameters(dx, dt, nu_p=1.1e-6, rho_p=1025.0, kBT_p=4.100531391e-21):
+    """hemo::Parameters::lbm_base_parameters -> dict(tau, nu_lbm, dt, dm, df, f_limit, kBT_lbm)"""
+    out = (C.c_double * 7)()
+    fn = load().hch_parameters
+    fn.restype = None
+    fn(C.c_double(dx), C.c_double(dt), C.c_double(nu_p), C.c_double(rho_p), C.c_double(kBT_p), out)
+    d = dict(zip(["tau", "nu_lbm", "dt", "dm", "df", "f_limit", "kBT_lbm"], list(out)))
+    d.update(dx=dx, nu_p=nu_p, rho_p=rho_p, kBT_p=kBT_p)
+    return d
+
+
+class HostCellType:
+    """hemo::CellTypeTables built by the product's C++ host code"""
+
+    def __init__(self, model, construct_type, par, material, inner_edges=()):
+        L = load()
+        L.hch_celltype_build.restype = C.c_void_p
+        L.hch_celltype_view.restype = C.POINTER(HcgCellType)
+        L.hch_celltype_view.argtypes = [C.c_void_p]
+        L.hch_celltype_vertices.argtypes = [C.c_void_p, c_dp]
+        L.hch_celltype_scalar.restype = C.c_double
+        L.hch_celltype_scalar.argtypes = [C.c_void_p, C.c_int32]
+        L.hch_celltype_free.argtypes = [C.c_void_p]
+        L.hch_last_error.restype = C.c_char_p
+        ie = np.ascontiguousarray(np.array(inner_edges, dtype=np.int32).reshape(-1, 2))
+        m = material
+        self.h = L.hch_celltype_build(
+            C.c_int32(model), C.c_int32(construct_type), C.c_double(par["dx"]), C.c_double(par["dt"]),
+            C.c_double(par["nu_p"]), C.c_double(par["rho_p"]), C.c_double(par["kBT_p"]),
+            C.c_double(m["kBend"]), C.c_double(m["kVolume"]), C.c_double(m["kArea"]), C.c_double(m["kLink"]),
+            C.c_double(m["eta_m"]), C.c_double(m["radius"]), C.c_double(m["aspectRatio"]),
+            C.c_int32(m["minNumTriangles"]), _p(ie, c_i32p), C.c_int32(ie.shape[0]))
+        if not self.h:
+            raise HcgError("hch_celltype_build: " + L.hch_last_error().decode())
+        self.L = L
+        self.model = model
+        self.view = L.hch_celltype_view(self.h)
+        self.V = self.view.contents.n_vertices
+        self.verts = np.empty((self.V, 3))
+        L.hch_celltype_vertices(self.h, _p(self.verts))
+
+    def table(self, name, shape, dtype):
+        ptr = getattr(self.view.contents, name)
+        n = int(np.prod(shape))
+        if n == 0:
+            return np.zeros(shape, dtype=dtype)
+        return np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape).astype(dtype, copy=True)
+
+    def scalar(self, which):
+        return self.L.hch_celltype_scalar(self.h, which)
+
+    def add_to(self, ctx):
+        out = C.c_int32(-1)
+        ctx._ck(ctx.L.hcg_celltype_add(ctx.h, self.view, C.byref(out)))
+        return out.value
+
+    def place(self, rows, dx, dims, flags=None, min_dist_um=0.0, cell_id0=0):
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 6)
+        n = rows.shape[0]
+        out = np.empty((n, self.V, 3))
+        ids = np.empty(n, dtype=np.int64)
+        fl = None
+        if flags is not None:
+            fl = np.ascontiguousarray(flags, dtype=np.uint8).reshape(-1)
+        fn = self.L.hch_place_cells
+        fn.restype = C.c_int64
+        k = fn(C.c_void_p(self.h), _p(rows), C.c_int64(n), C.c_double(dx), C.c_int32(dims[0]), C.c_int32(dims[1]),
+               C.c_int32(dims[2]), _p(fl, c_u8p) if fl is not None else None, C.c_double(min_dist_um),
+               C.c_int64(cell_id0), _p(out), _p(ids, c_i64p))
+        if k < 0:
+            raise HcgError("hch_place_cells: " + self.L.hch_last_error().decode())
+        return np.ascontiguousarray(out[:k]), ids[:k].copy()
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.hch_celltype_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def read_pos(path):
+    fn = load().hch_read_pos
+    fn.restype = C.c_int64
+    n = fn(path.encode(), None, C.c_int64(0))
+    if n < 0:
+        raise HcgError("hch_read_pos: cannot read " + path)
+    rows = np.empty((n, 6))
+    fn(path.encode(), _p(rows), C.c_int64(n))
+    return rows

@@ -1,0 +1,49 @@
+/*
+ * hemocell_host.h -- C view of the C++ host-side set-up code (hemocell_b200/host/), exported
+ * by the same libhemocell_gpu.so.  Lets a non-C++ harness (ctypes) run the product's own mesh
+ * generation, CommonCellConstants construction, unit conversion and .pos placement instead of
+ * re-implementing them.  Reference interfaces replaced (paths in the reference tree):
+ *   hch_parameters       hemo::Parameters::lbm_base_parameters   mechanics/constantConversion.cpp:36-59
+ *   hch_celltype_build   HemoCellField ctor + CommonCellConstants + calculate_k*
+ *                        core/hemoCellField.cpp:38-118, mechanics/commonCellConstants.cpp:70-409,
+ *                        mechanics/cellMechanics.h:50-78
+ *   hch_read_pos / hch_place_cells   readPositionsBloodCellField3D + loadParticles
+ *                        io/readPositionsBloodCells.cpp:120-361, core/hemoCell.cpp:191-197
+ */
+#ifndef HEMOCELL_HOST_H
+#define HEMOCELL_HOST_H
+#include <stdint.h>
+#include "hemocell_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hch_celltype hch_celltype;
+
+/* out[7] = tau, nu_lbm, dt, dm, df, f_limit, kBT_lbm */
+void hch_parameters(double dx, double dt, double nu_p, double rho_p, double kBT_p, double* out7);
+
+/* construct_type: 1 = RBC_FROM_SPHERE, 6 = ELLIPSOID_FROM_SPHERE; returns NULL on error */
+hch_celltype* hch_celltype_build(int32_t model, int32_t construct_type,
+                                 double dx, double dt, double nu_p, double rho_p, double kBT_p,
+                                 double kBend, double kVolume, double kArea, double kLink, double eta_m,
+                                 double radius_m, double aspect_ratio, int32_t min_num_triangles,
+                                 const int32_t* inner_edges /*[n][2]*/, int32_t n_inner_edges);
+const hcg_celltype* hch_celltype_view(const hch_celltype*);
+int32_t hch_celltype_vertices(const hch_celltype*, double* out /*[V][3] lattice units*/);
+double hch_celltype_scalar(const hch_celltype*, int32_t which /*0 volume_eq,1 surface,2 angle_mean_eq*/);
+void hch_celltype_free(hch_celltype*);
+
+/* returns the number of rows in the file (rows6 may be NULL to query), -1 on error */
+int64_t hch_read_pos(const char* path, double* rows6, int64_t capacity_rows);
+/* returns the number of surviving cells; out_pos capacity n_rows*V*3, out_ids capacity n_rows */
+int64_t hch_place_cells(const hch_celltype*, const double* rows6, int64_t n_rows, double dx,
+                        int32_t nx, int32_t ny, int32_t nz, const uint8_t* flags /*may be NULL*/,
+                        double min_dist_from_solid_um, int64_t cell_id0, double* out_pos, int64_t* out_ids);
+const char* hch_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

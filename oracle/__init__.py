@@ -59,6 +59,11 @@ def lib():
     return _LIB
 
 
+def set_parallel(on):
+    """OpenMP on the oracle loops (bench.py cpu_baseline only; tests keep the serial order)"""
+    lib().ora_set_parallel(C.c_int(int(on)))
+
+
 def _p(a, t=c_dp):
     return a.ctypes.data_as(t)
 

@@ -13,6 +13,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* OpenMP is used only by bench.py's cpu_baseline / --impl reference legs (ora_set_parallel(1));
+ * the parity tests run the loops serially, in the reference's order. */
+static int ora_parallel = 0;
+void ora_set_parallel(int on) { ora_parallel = on; }
+
 /* D3Q19 of Palabos descriptors::D3Q19Descriptor (opposite = i+9,
  * patch/palabos.patch:492-497) */
 static const int C[19][3] = {
@@ -133,6 +138,7 @@ static void regularized_velocity_complete(double f[19], int o, const double uw[3
 void ora_collide_and_stream(const ora_domain* d, const uint8_t* flags, double* pop,
                             const double* force, double* scratch) {
   int64_t N = nnodes(d);
+  #pragma omp parallel for schedule(static) if(ora_parallel)
   for (int64_t n = 0; n < N; n++) {
     double f[19], F[3];
     for (int i = 0; i < 19; i++) f[i] = pop[i*N + n];
@@ -147,6 +153,7 @@ void ora_collide_and_stream(const ora_domain* d, const uint8_t* flags, double* p
     for (int i = 0; i < 19; i++) pop[i*N + n] = f[i];
   }
   memset(scratch, 0, sizeof(double)*19*N);
+  #pragma omp parallel for schedule(static) if(ora_parallel)
   for (int x = 0; x < d->nx; x++) for (int y = 0; y < d->ny; y++) for (int z = 0; z < d->nz; z++) {
     int64_t n = nidx(d, x, y, z);
     for (int i = 0; i < 19; i++) {
@@ -166,6 +173,7 @@ void ora_collide_and_stream(const ora_domain* d, const uint8_t* flags, double* p
 void ora_moments(const ora_domain* d, const uint8_t* flags, const double* pop,
                  const double* force, double* rho_out, double* vel) {
   int64_t N = nnodes(d);
+  #pragma omp parallel for schedule(static) if(ora_parallel)
   for (int64_t n = 0; n < N; n++) {
     double rhoBar = 0.0, j[3] = {0,0,0};
     for (int i = 0; i < 19; i++) {
@@ -219,6 +227,7 @@ int ora_ibm_kernel(const ora_domain* d, const uint8_t* flags, const double p[3],
 void ora_spread(const ora_domain* d, const uint8_t* flags, int64_t np, const double* pos,
                 double* pforce, const double* frep, double f_limit, double* node_force) {
   int64_t N = nnodes(d);
+  #pragma omp parallel for schedule(static) if(ora_parallel)
   for (int64_t p = 0; p < np; p++) {
     int64_t node[8]; double w[8];
     int n = ora_ibm_kernel(d, flags, pos + 3*p, node, w);
@@ -226,8 +235,11 @@ void ora_spread(const ora_domain* d, const uint8_t* flags, int64_t np, const dou
     double mag = sqrt(f[0]*f[0] + f[1]*f[1] + f[2]*f[2]);
     if (mag > f_limit) { double s = f_limit/mag; f[0] *= s; f[1] *= s; f[2] *= s; }
     for (int k = 0; k < n; k++)
-      for (int c = 0; c < 3; c++)
-        node_force[c*N + node[k]] += (frep[3*p + c] + f[c]) * w[k];
+      for (int c = 0; c < 3; c++) {
+        const double add = (frep[3*p + c] + f[c]) * w[k];
+        #pragma omp atomic
+        node_force[c*N + node[k]] += add;
+      }
   }
 }
 
@@ -236,6 +248,7 @@ void ora_spread(const ora_domain* d, const uint8_t* flags, int64_t np, const dou
 void ora_interpolate(const ora_domain* d, const uint8_t* flags, int64_t np, const double* pos,
                      const double* pop, const double* node_force, double* vel) {
   int64_t N = nnodes(d);
+  #pragma omp parallel for schedule(static) if(ora_parallel)
   for (int64_t p = 0; p < np; p++) {
     int64_t node[8]; double w[8];
     int n = ora_ibm_kernel(d, flags, pos + 3*p, node, w);
@@ -261,6 +274,7 @@ void ora_interpolate(const ora_domain* d, const uint8_t* flags, int64_t np, cons
 int64_t ora_advance(const ora_domain* d, const uint8_t* flags, int64_t np, double* pos,
                     const double* vel, uint8_t* hit) {
   int64_t nhit = 0;
+  #pragma omp parallel for schedule(static) reduction(+:nhit) if(ora_parallel)
   for (int64_t p = 0; p < np; p++) {
     for (int c = 0; c < 3; c++) pos[3*p + c] += vel[3*p + c];
     int q[3] = {(int)floor(pos[3*p] + 0.5), (int)floor(pos[3*p+1] + 0.5), (int)floor(pos[3*p+2] + 0.5)};
@@ -426,6 +440,7 @@ static void mech_one_cell(const ora_celltype* t, const double* x, const double* 
 void ora_mechanics(const ora_celltype* t, int64_t n_cells, const double* pos, const double* vel,
                    double* force, double* const* comp) {
   const int64_t V = t->n_vertices;
+  #pragma omp parallel for schedule(dynamic, 8) if(ora_parallel)
   for (int64_t c = 0; c < n_cells; c++) {
     int64_t o = 3*V*c;
     mech_one_cell(t, pos + o, vel + o, force + o,

@@ -63,6 +63,9 @@ typedef struct {
   double k_volume, k_area, k_link, k_bend, eta_m;
 } ora_celltype;
 
+/* OpenMP on/off (off by default; on only for the timed cpu_baseline legs of bench.py) */
+void ora_set_parallel(int on);
+
 /* ---- lattice (Palabos v2.3.0 behaviour restated) ---- */
 void ora_init_equilibrium(const ora_domain* d, double rho, const double u[3], double* pop);
 void ora_collide_and_stream(const ora_domain* d, const uint8_t* flags, double* pop,

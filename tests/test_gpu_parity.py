@@ -38,7 +38,7 @@ def test_collide_stream_parity(periodic, flagkind, tau):
     fl = fl.reshape(-1)
     dom = O.make_domain(nx, ny, nz, periodic, tau, bc)
     rng = np.random.default_rng(7)
-    pop = U.smooth_state(dom, 11)
+    pop = U.mask_inflow(dom, U.smooth_state(dom, 11))
     force = np.ascontiguousarray(1e-5 * rng.standard_normal(3 * nx * ny * nz))
     ctx = U.gpu_context(dom, fl, bc)
     ctx.lattice_upload(H.LAT_POP, pop)
@@ -99,7 +99,7 @@ def test_spread_interpolate_advance_parity():
     pos = np.ascontiguousarray(cells.reshape(-1, 3))
     pforce = np.ascontiguousarray(rng.standard_normal(pos.shape) * par.f_limit * 0.5)   # some exceed the cap
     frep = np.ascontiguousarray(rng.standard_normal(pos.shape) * par.f_limit * 0.01)
-    pop = U.smooth_state(dom, 21)
+    pop = U.mask_inflow(dom, U.smooth_state(dom, 21))
     ctx = U.gpu_context(dom, fl, bc)
     ctx.set_force_limit(par.f_limit)
     t = U.gpu_add_type(ctx, ct)
@@ -202,7 +202,7 @@ def test_repulsion_parity():
     dom = O.make_domain(nx, ny, nz, (1, 0, 1), par.tau)
     ct = O.rbc_celltype(par)
     # three cells in near contact; one wraps across periodic x, one hugs the y = 0 wall
-    centers = [(10.0, 14.0, 16.0), (10.5, 16.3, 16.2), (46.0, 9.2, 15.0)]
+    centers = [(10.0, 14.0, 16.0), (10.5, 16.3, 16.2), (46.0, 2.0, 15.0)]
     cells = U.deformed_cells(ct, centers, 4, amp=0.0, stretch=(1, 1, 1))
     pos = np.ascontiguousarray(cells.reshape(-1, 3))
     cell_of = np.repeat(np.arange(3), ct.V)

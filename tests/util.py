@@ -50,6 +50,23 @@ def smooth_state(dom, seed, amp_u=0.03, amp_rho=1e-3):
     return np.ascontiguousarray(pop.reshape(-1))
 
 
+def mask_inflow(dom, pop):
+    """zero the populations that would have streamed in through a non-periodic face: by
+    definition (include/hemocell_gpu.h) what enters there is the rest equilibrium, stored 0"""
+    C = [(0,0,0),(-1,0,0),(0,-1,0),(0,0,-1),(-1,-1,0),(-1,1,0),(-1,0,-1),(-1,0,1),(0,-1,-1),(0,-1,1),
+         (1,0,0),(0,1,0),(0,0,1),(1,1,0),(1,-1,0),(1,0,1),(1,0,-1),(0,1,1),(0,1,-1)]
+    n = (dom.nx, dom.ny, dom.nz)
+    p = pop.reshape(19, dom.nx, dom.ny, dom.nz)
+    for q, c in enumerate(C):
+        for ax in range(3):
+            if dom.periodic[ax] or c[ax] == 0:
+                continue
+            sl = [slice(None)] * 3
+            sl[ax] = 0 if c[ax] > 0 else n[ax] - 1
+            p[(q,) + tuple(sl)] = 0.0
+    return pop
+
+
 def couette_flags(nx, ny, nz):
     fl = np.zeros((nx, ny, nz), dtype=np.uint8)
     fl[:, :, 0] = 6
