@@ -7,7 +7,7 @@
 #include <cstdio>
 
 hcg_status lat_pad3(hcg_ctx* c, const double* src_dev, double* dst);
-hcg_status lat_unpad(hcg_ctx* c, const double* src, double* dst_dev, int ncomp);
+hcg_status lat_unpad(hcg_ctx* c, const double* src, double* dst_dev, int first, int ncomp);
 
 static thread_local std::string g_create_error;
 
@@ -114,8 +114,8 @@ hcg_status step(hcg_ctx* c) {
   const bool interp = have_p && (c->iter % c->ts_vel == 0);
   { OpTimer t(c, "collideAndStream"); if ((s = lat_collide_stream(c, !interp))) return s; }
   if (interp) {
-    { OpTimer t(c, "interpolateFluidVelocity"); if ((s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate(c))) return s; }
-    { OpTimer t(c, "advanceParticles"); if ((s = ibm_advance(c))) return s; }
+    // interpolation and advance share one pass over the particles (advance uses the velocity just interpolated)
+    { OpTimer t(c, "interpolateFluidVelocity"); if ((s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate_advance(c))) return s; }
   } else if (have_p) {
     OpTimer t(c, "advanceParticles"); if ((s = ibm_advance(c))) return s;
   }
@@ -168,15 +168,15 @@ hcg_status hcg_create(const hcg_domain* d, hcg_ctx** out) {
   CUDA_TRY(c, cudaEventCreate(&c->ev_a)); CUDA_TRY(c, cudaEventCreate(&c->ev_b));
   CUDA_TRY(c, cudaMalloc(&c->g[0], sizeof(double)*19*c->S));
   CUDA_TRY(c, cudaMalloc(&c->g[1], sizeof(double)*19*c->S));
-  CUDA_TRY(c, cudaMalloc(&c->F, sizeof(double)*3*c->S));
-  CUDA_TRY(c, cudaMalloc(&c->U, sizeof(double)*3*c->S));
+  CUDA_TRY(c, cudaMalloc(&c->F, sizeof(double)*4*c->S));
+  CUDA_TRY(c, cudaMalloc(&c->U, sizeof(double)*4*c->S));
   CUDA_TRY(c, cudaMalloc(&c->flags, c->S));
   CUDA_TRY(c, cudaMalloc(&c->d_bc, sizeof(double)*18));
   CUDA_TRY(c, cudaMemsetAsync(c->d_bc, 0, sizeof(double)*18, c->stream));
   CUDA_TRY(c, cudaMemsetAsync(c->g[0], 0, sizeof(double)*19*c->S, c->stream));
   CUDA_TRY(c, cudaMemsetAsync(c->g[1], 0, sizeof(double)*19*c->S, c->stream));
-  CUDA_TRY(c, cudaMemsetAsync(c->F, 0, sizeof(double)*3*c->S, c->stream));
-  CUDA_TRY(c, cudaMemsetAsync(c->U, 0, sizeof(double)*3*c->S, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->F, 0, sizeof(double)*4*c->S, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->U, 0, sizeof(double)*4*c->S, c->stream));
   CUDA_TRY(c, cudaMemsetAsync(c->flags, HCG_FLUID, c->S, c->stream));
   hcg_status s = exchange_flags(c); if (s) return s;
   const double u0[3] = {0, 0, 0};
@@ -300,17 +300,17 @@ hcg_status hcg_lattice_download(hcg_ctx* c, int32_t field, double* out) {
     CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*19*c->Nl, cudaMemcpyDeviceToHost, c->stream));
   } else if (field == HCG_LAT_FORCE) {
     if ((s = ensure_staging(c, sizeof(double)*3*c->Nl))) return s;
-    if ((s = lat_unpad(c, c->F, c->staging, 3))) return s;
+    if ((s = lat_unpad(c, c->F, c->staging, 0, 3))) return s;
     CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*3*c->Nl, cudaMemcpyDeviceToHost, c->stream));
   } else if (field == HCG_LAT_VELOCITY || field == HCG_LAT_DENSITY) {
     // Cell::computeVelocity / computeDensity of the current populations and node force
     if ((s = lat_moments(c, false, true))) return s;
     if ((s = ensure_staging(c, sizeof(double)*3*c->Nl))) return s;
     if (field == HCG_LAT_VELOCITY) {
-      if ((s = lat_unpad(c, c->U, c->staging, 3))) return s;
+      if ((s = lat_unpad(c, c->U, c->staging, 0, 3))) return s;
       CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*3*c->Nl, cudaMemcpyDeviceToHost, c->stream));
     } else {
-      if ((s = lat_unpad(c, c->rho, c->staging, 1))) return s;
+      if ((s = lat_unpad(c, c->U, c->staging, 3, 1))) return s;
       CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*c->Nl, cudaMemcpyDeviceToHost, c->stream));
     }
   } else return hcg_fail(c, HCG_ERR_ARG, "lattice_download: unknown field");

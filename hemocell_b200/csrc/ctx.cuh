@@ -4,7 +4,7 @@
 //            local node index  n = z + nz*(y + ny*lx), lx = x - x0 + 1 in [0, nxl+1]
 //   populations g[q*S + n], S = (nxl+2)*ny*nz: the PRE-STREAMED (post-collision) value that
 //            will arrive at node n + c_q; the reference's post-stream state is S_q(n) = g_q(n - c_q)
-//   node force F[d*S + n], velocity U[d*S + n], flags[n]
+//   node force F[4*n + d], velocity U[4*n + d] (AoS, one 32-byte sector per node; U slot 3 = density), flags[n]
 //   particles: SoA by component, p = cell_base + vertexId
 #pragma once
 #include <cuda_runtime.h>

@@ -98,9 +98,10 @@ k_spread(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __restrict
   const int64_t lo = a.P, hi = (int64_t)(a.nxl + 1)*a.P;      // real planes only
   for (int k = 0; k < n; k++) {
     if (node[k] < lo || node[k] >= hi) continue;
-    atomicAdd(F + node[k], t0*w[k]);
-    atomicAdd(F + a.S + node[k], t1*w[k]);
-    atomicAdd(F + 2*a.S + node[k], t2*w[k]);
+    double* Fn = F + 4*node[k];            // node vectors are AoS [n][4]: one 32-byte sector per node
+    atomicAdd(Fn, t0*w[k]);
+    atomicAdd(Fn + 1, t1*w[k]);
+    atomicAdd(Fn + 2, t2*w[k]);
   }
 }
 
@@ -120,9 +121,11 @@ k_interp_advance(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __
     const int n = ibm_kernel(a, flags, px, py, pz, node, w);
     v0 = v1 = v2 = 0.0;
     for (int k = 0; k < n; k++) {
-      v0 += __ldg(U + node[k])*w[k];
-      v1 += __ldg(U + a.S + node[k])*w[k];
-      v2 += __ldg(U + 2*a.S + node[k])*w[k];
+      const double2 ua = __ldg(reinterpret_cast<const double2*>(U + 4*node[k]));
+      const double ub = __ldg(U + 4*node[k] + 2);
+      v0 += ua.x*w[k];
+      v1 += ua.y*w[k];
+      v2 += ub*w[k];
     }
     if (n >= 0) { vx[p] = v0; vy[p] = v1; vz[p] = v2; }
     else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }

@@ -5,6 +5,7 @@
 #include "ctx.cuh"
 #include <nccl.h>
 #include <cfloat>
+#include <cstdlib>
 
 namespace {
 
@@ -130,8 +131,8 @@ __device__ __forceinline__ void regularized_complete(double f[19], int o, const 
 
 // One thread per real node.  RESET: write the body force back after reading F (steps without
 // velocity interpolation).
-template <bool RESET, bool VELBC>
-__global__ void __launch_bounds__(256)
+template <bool RESET, bool VELBC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, double* __restrict__ F,
                  const uint8_t* __restrict__ flags, LatArgs a) {
   const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
@@ -146,11 +147,12 @@ k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, doub
 #pragma unroll
     for (int q = 1; q <= 9; q++) { const double t = f[q]; f[q] = f[q+9]; f[q+9] = t; }
   } else {
-    double Fn[3] = {F[n], F[a.S + n], F[2*a.S + n]};
+    const double2 fa = *reinterpret_cast<const double2*>(F + 4*n);
+    double Fn[3] = {fa.x, fa.y, F[4*n + 2]};
     if (VELBC && fl >= HCG_VEL_XN) { const double uw[3] = {a.bc[3*(fl-2)], a.bc[3*(fl-2)+1], a.bc[3*(fl-2)+2]}; regularized_complete(f, fl - 2, uw); }
     guo_collide(f, Fn, a.omega);
   }
-  if (RESET) { F[n] = a.body[0]; F[a.S + n] = a.body[1]; F[2*a.S + n] = a.body[2]; }
+  if (RESET) { double2* Fw = reinterpret_cast<double2*>(F + 4*n); Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0); }
 #pragma unroll
   for (int q = 0; q < 19; q++) gout[(int64_t)q*a.S + n] = f[q];
 }
@@ -158,10 +160,10 @@ k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, doub
 // Moments pass: velocity the IBM interpolation sees, u = j/rho + F/2 of the POST-stream
 // populations with the spread force still on the node (Cell::computeVelocity through
 // core/hemoCellParticleField.cpp:833).  BounceBack: 0; velocity plane: wall velocity.
-template <bool RESET, bool RHO>
+template <bool RESET>
 __global__ void __launch_bounds__(256)
 k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restrict__ U,
-          double* __restrict__ rho_out, const uint8_t* __restrict__ flags, LatArgs a) {
+          const uint8_t* __restrict__ flags, LatArgs a) {
   const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= (int64_t)a.nxl*a.P) return;
   const int64_t n = i + a.P;
@@ -175,18 +177,20 @@ k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restri
   double u0, u1, u2, rho = 1.0 + rhoBar;
   if (fl == HCG_FLUID) {
     const double invRho = 1.0/rho;
-    u0 = j[0]*invRho + 0.5*F[n]; u1 = j[1]*invRho + 0.5*F[a.S + n]; u2 = j[2]*invRho + 0.5*F[2*a.S + n];
+    const double2 fa = *reinterpret_cast<const double2*>(F + 4*n);
+    u0 = j[0]*invRho + 0.5*fa.x; u1 = j[1]*invRho + 0.5*fa.y; u2 = j[2]*invRho + 0.5*F[4*n + 2];
   } else if (fl == HCG_BOUNCEBACK) { u0 = u1 = u2 = 0.0; rho = 1.0; }
   else { u0 = a.bc[3*(fl-2)]; u1 = a.bc[3*(fl-2)+1]; u2 = a.bc[3*(fl-2)+2]; }
-  U[n] = u0; U[a.S + n] = u1; U[2*a.S + n] = u2;
-  if (RHO) rho_out[n] = rho;
-  if (RESET) { F[n] = a.body[0]; F[a.S + n] = a.body[1]; F[2*a.S + n] = a.body[2]; }
+  double2* Uw = reinterpret_cast<double2*>(U + 4*n);
+  Uw[0] = make_double2(u0, u1); Uw[1] = make_double2(u2, rho);      // slot 3 carries the density
+  if (RESET) { double2* Fw = reinterpret_cast<double2*>(F + 4*n); Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0); }
 }
 
-__global__ void k_fill3(double* F, int64_t S, int64_t total, double b0, double b1, double b2) {
+__global__ void k_fill4(double* F, int64_t total, double b0, double b1, double b2) {
   const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= total) return;
-  F[i] = b0; F[S + i] = b1; F[2*S + i] = b2;
+  double2* Fw = reinterpret_cast<double2*>(F + 4*i);
+  Fw[0] = make_double2(b0, b1); Fw[1] = make_double2(b2, 0.0);
 }
 
 __global__ void k_fill_pop(double* g, int64_t S, int64_t lo, int64_t hi, const double* vals19) {
@@ -197,7 +201,7 @@ __global__ void k_fill_pop(double* g, int64_t S, int64_t lo, int64_t hi, const d
 }
 
 // periodic self-exchange (n_ranks == 1): left ghost <- last real plane, right ghost <- first
-__global__ void k_halo_self(double* buf, int64_t S, int64_t P, int nxl, const int* qL, int nL, const int* qR, int nR) {
+__global__ void k_halo_self(double* buf, int64_t S, int64_t P /* elements per plane */, int nxl, const int* qL, int nL, const int* qR, int nR) {
   const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= P) return;
   const int k = blockIdx.y;
@@ -236,6 +240,18 @@ __global__ void k_from_reference(const double* __restrict__ s, double* __restric
     g[(int64_t)q*a.S + n] = ok ? s[(int64_t)q*a.S + src] : 0.0;
   }
 }
+// compact SoA [3][Nl] (C ABI) <-> padded AoS [n][4] (device node vectors)
+__global__ void k_pad4(const double* __restrict__ src, double* __restrict__ dst, int64_t Nl, int64_t P) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= Nl) return;
+  double* d = dst + 4*(P + i);
+  d[0] = src[i]; d[1] = src[Nl + i]; d[2] = src[2*Nl + i]; d[3] = 0.0;
+}
+__global__ void k_unpad4(const double* __restrict__ src, double* __restrict__ dst, int64_t Nl, int64_t P, int first, int ncomp) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= Nl) return;
+  for (int q = 0; q < ncomp; q++) dst[(int64_t)q*Nl + i] = src[4*(P + i) + first + q];
+}
 __global__ void k_pad(const double* __restrict__ src, double* __restrict__ dst, int64_t Nl, int64_t S, int64_t P, int ncomp) {
   const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= Nl) return;
@@ -255,7 +271,7 @@ __global__ void k_vel_stats(const double* __restrict__ U, const uint8_t* __restr
   for (int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x; i < Nl; i += (int64_t)gridDim.x*blockDim.x) {
     const int64_t n = i + P;
     if (flags[n] != HCG_FLUID) continue;
-    const double u = sqrt(U[n]*U[n] + U[S+n]*U[S+n] + U[2*S+n]*U[2*S+n]);
+    const double u = sqrt(U[4*n]*U[4*n] + U[4*n+1]*U[4*n+1] + U[4*n+2]*U[4*n+2]);
     mn = fmin(mn, u); mx = fmax(mx, u); sm += u; ct += 1.0;
   }
   const int t = threadIdx.x;
@@ -286,13 +302,13 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1)/t); }
 int* d_qsets = nullptr;   // {10,13,14,15,16, 1,4,5,6,7, 0,1,2}
 const int h_qsets[13] = {10,13,14,15,16, 1,4,5,6,7, 0,1,2};
 
-hcg_status exchange(hcg_ctx* c, double* buf, const int* hL, const int* dL, int nL, const int* hR, const int* dR, int nR) {
+hcg_status exchange(hcg_ctx* c, double* buf, int64_t P /* elements per plane */, const int* hL, const int* dL, int nL, const int* hR, const int* dR, int nR) {
   const bool px = c->dom.periodic[0];
   const int R = c->dom.n_ranks, r = c->dom.rank;
   if (R == 1) {
     if (!px) return HCG_OK;
-    dim3 grid(nblk(c->P, 256), nL + nR);
-    k_halo_self<<<grid, 256, 0, c->stream>>>(buf, c->S, c->P, c->nxl, dL, nL, dR, nR);
+    dim3 grid(nblk(P, 256), nL + nR);
+    k_halo_self<<<grid, 256, 0, c->stream>>>(buf, c->S, P, c->nxl, dL, nL, dR, nR);
     KERNEL_CHECK(c);
     return HCG_OK;
   }
@@ -300,7 +316,7 @@ hcg_status exchange(hcg_ctx* c, double* buf, const int* hL, const int* dL, int n
   ncclComm_t comm = (ncclComm_t)c->nccl;
   const int left = (r == 0) ? (px ? R - 1 : -1) : r - 1;
   const int right = (r == R - 1) ? (px ? 0 : -1) : r + 1;
-  const int64_t P = c->P, S = c->S;
+  const int64_t S = c->S;
   ncclGroupStart();
   // my first real plane -> left neighbour's RIGHT ghost (sets R); my last -> right neighbour's LEFT ghost (sets L)
   if (left >= 0) for (int k = 0; k < nR; k++) ncclSend(buf + (int64_t)hR[k]*S + P, P, ncclDouble, left, comm, c->stream);
@@ -325,11 +341,12 @@ hcg_status ensure_qsets(hcg_ctx* c) {
 hcg_status lat_halo_exchange_pop(hcg_ctx* c) {
   hcg_status s = ensure_qsets(c); if (s) return s;
   // pull kernel: left ghost read by c_x = +1 populations, right ghost by c_x = -1
-  return exchange(c, c->g[c->cur], h_qsets, d_qsets, 5, h_qsets + 5, d_qsets + 5, 5);
+  return exchange(c, c->g[c->cur], c->P, h_qsets, d_qsets, 5, h_qsets + 5, d_qsets + 5, 5);
 }
 hcg_status lat_halo_exchange_u(hcg_ctx* c) {
   hcg_status s = ensure_qsets(c); if (s) return s;
-  return exchange(c, c->U, h_qsets + 10, d_qsets + 10, 3, h_qsets + 10, d_qsets + 10, 3);
+  // node vectors are AoS [n][4]: one contiguous block of 4*P doubles per plane ("population" 0)
+  return exchange(c, c->U, 4*c->P, h_qsets + 10, d_qsets + 10, 1, h_qsets + 10, d_qsets + 10, 1);
 }
 
 hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
@@ -339,13 +356,12 @@ hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
   const unsigned nb = nblk(n, 256);
   {
   OpTimer tk(c, "kernel:k_collide_stream");
-  if (c->has_velbc) {
-    if (reset_force) k_collide_stream<true, true><<<nb, 256, 0, c->stream>>>(gin, gout, c->F, c->flags, a);
-    else k_collide_stream<false, true><<<nb, 256, 0, c->stream>>>(gin, gout, c->F, c->flags, a);
-  } else {
-    if (reset_force) k_collide_stream<true, false><<<nb, 256, 0, c->stream>>>(gin, gout, c->F, c->flags, a);
-    else k_collide_stream<false, false><<<nb, 256, 0, c->stream>>>(gin, gout, c->F, c->flags, a);
-  }
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("HCG_K1_MINB"); variant = e ? atoi(e) : 2; }
+#define K1_LAUNCH(R, V, M) k_collide_stream<R, V, M><<<nb, 256, 0, c->stream>>>(gin, gout, c->F, c->flags, a)
+#define K1_PICK(M) do { if (c->has_velbc) { if (reset_force) K1_LAUNCH(true, true, M); else K1_LAUNCH(false, true, M); } \
+                        else { if (reset_force) K1_LAUNCH(true, false, M); else K1_LAUNCH(false, false, M); } } while (0)
+  if (variant == 4) K1_PICK(4); else if (variant == 3) K1_PICK(3); else if (variant == 2) K1_PICK(2); else K1_PICK(1);
   }
   KERNEL_CHECK(c);
   c->cur = 1 - c->cur;
@@ -354,19 +370,14 @@ hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
 }
 
 hcg_status lat_moments(hcg_ctx* c, bool reset_force, bool want_rho) {
+  (void)want_rho;   // the density always rides in slot 3 of the node velocity
   LatArgs a = make_args(c);
   const int64_t n = (int64_t)c->nxl*c->P;
   const unsigned nb = nblk(n, 256);
-  if (want_rho && !c->rho) CUDA_TRY(c, cudaMalloc(&c->rho, sizeof(double)*c->S));
   {
   OpTimer tk(c, "kernel:k_moments");
-  if (reset_force) {
-    if (want_rho) k_moments<true, true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->rho, c->flags, a);
-    else k_moments<true, false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->rho, c->flags, a);
-  } else {
-    if (want_rho) k_moments<false, true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->rho, c->flags, a);
-    else k_moments<false, false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->rho, c->flags, a);
-  }
+  if (reset_force) k_moments<true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a);
+  else k_moments<false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a);
   }
   KERNEL_CHECK(c);
   c->u_valid = true;
@@ -374,7 +385,7 @@ hcg_status lat_moments(hcg_ctx* c, bool reset_force, bool want_rho) {
 }
 
 hcg_status lat_reset_force(hcg_ctx* c) {
-  k_fill3<<<nblk(c->S, 256), 256, 0, c->stream>>>(c->F, c->S, c->S, c->body[0], c->body[1], c->body[2]);
+  k_fill4<<<nblk(c->S, 256), 256, 0, c->stream>>>(c->F, c->S, c->body[0], c->body[1], c->body[2]);
   KERNEL_CHECK(c);
   return HCG_OK;
 }
@@ -419,7 +430,7 @@ hcg_status lat_pop_from_reference(hcg_ctx* c, const double* src_dev) {
   KERNEL_CHECK(c);
   hcg_status st = ensure_qsets(c); if (st) return st;
   // g_q(n) = S_q(n + c_q): c_x = -1 populations read the LEFT ghost, c_x = +1 the RIGHT ghost
-  st = exchange(c, s, h_qsets + 5, d_qsets + 5, 5, h_qsets, d_qsets, 5); if (st) return st;
+  st = exchange(c, s, c->P, h_qsets + 5, d_qsets + 5, 5, h_qsets, d_qsets, 5); if (st) return st;
   CUDA_TRY(c, cudaMemsetAsync(c->g[c->cur], 0, sizeof(double)*19*c->S, c->stream));
   k_from_reference<<<nblk((int64_t)c->nxl*c->P, 256), 256, 0, c->stream>>>(s, c->g[c->cur], a);
   KERNEL_CHECK(c);
@@ -442,10 +453,10 @@ hcg_status lat_velocity_stats(hcg_ctx* c, double* vmin, double* vmax, double* vm
 
 // utilities used by capi.cu
 hcg_status lat_pad3(hcg_ctx* c, const double* src_dev, double* dst) {
-  k_pad<<<nblk(c->Nl, 256), 256, 0, c->stream>>>(src_dev, dst, c->Nl, c->S, c->P, 3);
+  k_pad4<<<nblk(c->Nl, 256), 256, 0, c->stream>>>(src_dev, dst, c->Nl, c->P);
   KERNEL_CHECK(c); return HCG_OK;
 }
-hcg_status lat_unpad(hcg_ctx* c, const double* src, double* dst_dev, int ncomp) {
-  k_unpad<<<nblk(c->Nl, 256), 256, 0, c->stream>>>(src, dst_dev, c->Nl, c->S, c->P, ncomp);
+hcg_status lat_unpad(hcg_ctx* c, const double* src, double* dst_dev, int first, int ncomp) {
+  k_unpad4<<<nblk(c->Nl, 256), 256, 0, c->stream>>>(src, dst_dev, c->Nl, c->P, first, ncomp);
   KERNEL_CHECK(c); return HCG_OK;
 }

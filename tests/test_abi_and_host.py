@@ -1,0 +1,108 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol the headers
+declare; the product's C++ host set-up code agrees with the numpy oracle; creating a context
+without a GPU fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import mesh as M
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header, prefix):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(" + prefix + r"_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from hemocell_b200 import lib as H
+    L = H.load()
+    dev = _declared("hemocell_gpu.h", "hcg")
+    host = _declared("hemocell_host.h", "hch")
+    assert len(dev) >= 45 and len(host) >= 9
+    for name in dev + host:
+        assert hasattr(L, name), f"{name} declared in include/ but not exported"
+    assert sorted(H.SYMBOLS) == dev
+    assert sorted(H.HOST_SYMBOLS) == host
+    assert b"sm_100a" in L.hcg_version()
+
+
+def test_no_cpu_fallback():
+    from hemocell_b200 import lib as H
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(H.HcgError, match="no CUDA device"):
+        H.Context(8, 8, 8, (1, 1, 1), 1.0)
+
+
+def test_argument_validation():
+    from hemocell_b200 import lib as H
+    L = H.load()
+    d = H.HcgDomain(); d.nx, d.ny, d.nz = 10, 10, 10; d.tau = 0.4; d.n_ranks = 1
+    h = C.c_void_p()
+    assert L.hcg_create(C.byref(d), C.byref(h)) == -1            # tau <= 0.5
+    d.tau = 1.0; d.n_ranks = 3
+    assert L.hcg_create(C.byref(d), C.byref(h)) == -1            # nx not divisible by n_ranks
+    assert b"divisible" in L.hcg_last_error(None)
+
+
+@pytest.mark.parametrize("kind", ["rbc", "plt"])
+def test_host_cpp_matches_numpy_oracle(kind):
+    from hemocell_b200 import lib as H
+    par_o = M.Parameters(0.5e-6, 1e-7)
+    par = H.parameters(0.5e-6, 1e-7)
+    for k in ("tau", "nu_lbm", "df", "f_limit", "kBT_lbm"):
+        assert par[k] == getattr(par_o, k)
+    if kind == "rbc":
+        h = H.HostCellType(H.MODEL_RBC, H.RBC_FROM_SPHERE, par, H.RBC_MATERIAL)
+        ct = O.rbc_celltype(par_o)
+    else:
+        h = H.HostCellType(H.MODEL_PLT, H.ELLIPSOID_FROM_SPHERE, par, H.PLT_MATERIAL, H.PLT_INNER_EDGES)
+        ct = O.plt_celltype(par_o)
+    v = h.view.contents
+    V, T, E, I = v.n_vertices, v.n_triangles, v.n_edges, v.n_inner_edges
+    assert (V, T, E, I) == (ct.V, ct.cc["triangle_list"].shape[0], ct.cc["edge_list"].shape[0], ct.cc["inner_edge_list"].shape[0])
+    np.testing.assert_allclose(h.verts, ct.verts, rtol=0, atol=1e-13)
+    for name, shape, key in [("triangles", (T, 3), "triangle_list"), ("edges", (E, 2), "edge_list"),
+                             ("vertex_vertexes", (V, 6), "vertex_vertexes"), ("vertex_n_vertexes", (V,), "vertex_n_vertexes"),
+                             ("edge_bending_triangles", (E, 2), "edge_bending_triangles_list"),
+                             ("edge_bending_outer_points", (E, 2), "edge_bending_triangles_outer_points")]:
+        assert np.array_equal(h.table(name, shape, np.int32), ct.cc[key]), name
+    for name, shape, key in [("edge_length_eq", (E,), "edge_length_eq_list"), ("edge_angle_eq", (E,), "edge_angle_eq_list"),
+                             ("triangle_area_eq", (T,), "triangle_area_eq_list"),
+                             ("patch_dist_eq", (V,), "surface_patch_center_dist_eq_list"),
+                             ("inner_edge_length_eq", (I,), "inner_edge_length_eq_list")]:
+        np.testing.assert_allclose(h.table(name, shape, np.float64), ct.cc[key], rtol=1e-12, atol=1e-14, err_msg=name)
+    np.testing.assert_allclose([v.volume_eq, v.area_mean_eq, v.edge_mean_eq], [ct.cc[k] for k in ("volume_eq", "area_mean_eq", "edge_mean_eq")], rtol=1e-13)
+    np.testing.assert_allclose([v.k_volume, v.k_area, v.k_link, v.k_bend, v.eta_m],
+                               [ct.k[k] for k in ("k_volume", "k_area", "k_link", "k_bend", "eta_m")], rtol=1e-15)
+
+
+def test_host_placement_matches_oracle(tmp_path):
+    from hemocell_b200 import lib as H
+    par = H.parameters(0.5e-6, 1e-7)
+    h = H.HostCellType(H.MODEL_RBC, H.RBC_FROM_SPHERE, par, H.RBC_MATERIAL)
+    ct = O.rbc_celltype(M.Parameters(0.5e-6, 1e-7))
+    rng = np.random.default_rng(2)
+    rows = np.concatenate([rng.uniform(0, 32, (40, 3)), rng.uniform(-180, 180, (40, 3))], axis=1)
+    dims = (64, 48, 40)
+    fl = np.zeros(dims, dtype=np.uint8); fl[:, 0, :] = 1; fl[:, -1, :] = 1; fl[:, :, 0] = 6; fl[:, :, -1] = 7
+    p = tmp_path / "RBC.pos"
+    p.write_text("40\n" + "\n".join(" ".join(repr(float(x)) for x in r) for r in rows) + "\n")
+    rows_rd = H.read_pos(str(p))
+    assert np.array_equal(rows_rd, rows)
+    for md in (0.0, 1.0):
+        pos_h, ids_h = h.place(rows_rd, 0.5e-6, dims, fl, md, cell_id0=7)
+        pos_o, ids_o = M.place_cells(ct.verts, rows, 0.5e-6, dims, fl.reshape(-1), md, cell_id0=7)
+        assert ids_h.tolist() == ids_o.tolist() and len(ids_h) > 0
+        np.testing.assert_allclose(pos_h, pos_o, rtol=0, atol=1e-12)

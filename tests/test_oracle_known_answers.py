@@ -1,0 +1,213 @@
+"""CPU tests that pin the oracle: known answers from the reference's own tests / CI scripts and
+size-independent physical invariants.  (No GPU; the whole file runs in well under a minute.)"""
+import json
+import os
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import mesh as M
+import util as U
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PAR = M.Parameters(dx=0.5e-6, dt=1e-7)
+
+
+def test_mesh_counts_and_known_volume_area():
+    rbc = O.rbc_celltype(PAR)
+    assert rbc.V == 642 and rbc.cc["triangle_list"].shape[0] == 1280 and rbc.cc["edge_list"].shape[0] == 1920
+    assert np.bincount(rbc.cc["vertex_n_vertexes"]).tolist()[5:] == [12, 630]
+    plt = O.plt_celltype(PAR)
+    assert plt.V == 66 and plt.cc["triangle_list"].shape[0] == 128 and plt.cc["edge_list"].shape[0] == 192
+    assert np.bincount(plt.cc["vertex_n_vertexes"]).tolist()[4:] == [6, 0, 60]
+    # scripts/ci/stretchCell_sanity.sh:15-34: the stretched cell keeps 81.12 <= V <= 81.19 um^3 while
+    # 100 % <= V/V_eq <= 100.1 %  =>  81.04 <= V_eq <= 81.19; surface of the stretched cell >= 129.34
+    v_um3 = rbc.cc["volume_eq"] * 0.5 ** 3
+    a_um2 = rbc.cc["triangle_area_eq_list"].sum() * 0.5 ** 2
+    assert 81.04 <= v_um3 <= 81.19, v_um3
+    assert 128.5 <= a_um2 <= 133.04, a_um2
+    # bounding box: diameter 2 x 3.91 um (RBC.xml radius), thickness ~2.3 um
+    ext = (rbc.verts.max(0) - rbc.verts.min(0)) * 0.5
+    assert abs(ext[0] - 7.82) < 0.01 and abs(ext[2] - 7.82) < 0.01 and 2.2 < ext[1] < 2.4
+
+
+def test_plt_inner_edges_are_mirror_pairs():
+    """examples/pipeflow/PLT.xml hard-codes 21 vertex-id pairs; under the restated Palabos numbering
+    every pair is an exact point- or mirror-image, which pins constructSphere + numbering + rotate"""
+    plt = O.plt_celltype(PAR)
+    v = plt.verts - 0.5 * (plt.verts.min(0) + plt.verts.max(0))
+    for a, b in M.PLT_INNER_EDGES:
+        mirror = np.abs(np.abs(v[a]) - np.abs(v[b])).max()
+        assert mirror < 1e-6, (a, b, v[a], v[b])
+        assert np.linalg.norm(v[a] - v[b]) > 1.5          # across the platelet, not neighbours
+
+
+@pytest.mark.parametrize("kind", ["rbc", "plt"])
+def test_membrane_forces_vanish_at_rest_and_balance_when_deformed(kind):
+    ct = O.rbc_celltype(PAR) if kind == "rbc" else O.plt_celltype(PAR)
+    rest = np.ascontiguousarray(ct.verts + np.array([40.0, 50.0, 60.0]))
+    f = np.zeros_like(rest)
+    O.mechanics(ct, rest, np.zeros_like(rest), f)
+    scale = ct.k["k_link"]
+    assert np.abs(f).max() < 1e-6 * scale                     # equilibrium shape carries no force
+    cells = U.deformed_cells(ct, [(40.0, 50.0, 60.0)], 5, amp=0.02)
+    pos = np.ascontiguousarray(cells.reshape(-1, 3))
+    f = np.zeros_like(pos)
+    comp = O.mechanics(ct, pos, np.zeros_like(pos), f, components=True)
+    fmax = np.abs(f).max()
+    assert fmax > 1e-3 * scale
+    # internal forces: zero net force; link / bending pairs also carry zero net torque
+    for k, name in enumerate(["area", "volume", "bending", "link", "visc", "inner"]):
+        assert np.abs(comp[k].sum(0)).max() < 1e-9 * max(np.abs(comp[k]).max(), 1e-30) * len(pos) + 1e-12 * fmax, name
+    assert np.abs(f.sum(0)).max() < 1e-9 * fmax
+    tq = np.cross(pos - pos.mean(0), comp[3]).sum(0)
+    assert np.abs(tq).max() < 1e-8 * fmax * 10
+    np.testing.assert_allclose(sum(comp), f, rtol=0, atol=1e-12 * fmax)
+
+
+def test_plt_bending_is_restoring():
+    """the getAdjacentTriangleIds order is not in the reference tree; the chosen order must make the
+    dihedral force of pltSimpleModel.cpp:156-182 push a sharpened ridge back"""
+    plt = O.plt_celltype(PAR)
+    pos = np.ascontiguousarray(plt.verts.copy())
+    e = 10
+    a, b = plt.cc["edge_list"][e]
+    n, _ = M.tri_normals_areas(pos, plt.cc["triangle_list"])
+    t0, t1 = plt.cc["edge_bending_triangles_list"][e]
+    navg = n[t0] + n[t1]; navg /= np.linalg.norm(navg)
+    pos[a] += 0.05 * navg; pos[b] += 0.05 * navg                # push the edge outward: sharper ridge
+    f = np.zeros_like(pos)
+    comp = O.mechanics(plt, pos, np.zeros_like(pos), f, components=True)
+    assert np.dot(comp[2][a], navg) < 0 and np.dot(comp[2][b], navg) < 0
+
+
+def test_spread_conserves_momentum_and_interpolation_reproduces_uniform_flow():
+    nx, ny, nz = 24, 20, 18
+    dom = O.make_domain(nx, ny, nz, (1, 1, 1), 1.0)
+    fl = np.zeros(nx * ny * nz, dtype=np.uint8)
+    rng = np.random.default_rng(0)
+    pos = np.ascontiguousarray(rng.uniform(-3, 30, (500, 3)))           # also outside: periodic wrap
+    pf = np.ascontiguousarray(rng.standard_normal((500, 3)) * 1e-3)
+    fr = np.ascontiguousarray(rng.standard_normal((500, 3)) * 1e-4)
+    F = np.zeros(3 * nx * ny * nz)
+    O.spread(dom, fl, pos, pf, fr, 1e9, F)
+    np.testing.assert_allclose(F.reshape(3, -1).sum(1), (pf + fr).sum(0), rtol=1e-11)
+    u0 = (0.01, -0.02, 0.005)
+    pop = O.init_equilibrium(dom, 1.0, u0)
+    v = O.interpolate(dom, fl, pos, pop, np.zeros_like(F))
+    np.testing.assert_allclose(v, np.tile(u0, (500, 1)), rtol=1e-12, atol=1e-16)
+    # the force cap mutates the particle force in place (hemoCellParticleField.cpp:848-852)
+    pf2 = pf.copy()
+    O.spread(dom, fl, pos, pf2, fr, 1e-3, np.zeros_like(F))
+    assert np.linalg.norm(pf2, axis=1).max() <= 1e-3 * (1 + 1e-12)
+
+
+def test_ibm_kernel_skips_boundary_nodes_and_renormalises():
+    import ctypes as C
+    nx = ny = nz = 8
+    dom = O.make_domain(nx, ny, nz, (0, 0, 0), 1.0)
+    fl = np.zeros((nx, ny, nz), dtype=np.uint8); fl[:, :, 0] = 1
+    fl = fl.reshape(-1)
+    node = (C.c_int64 * 8)(); w = (C.c_double * 8)()
+    n = O.lib().ora_ibm_kernel(C.byref(dom), fl.ctypes.data_as(O.c_u8p), (C.c_double * 3)(3.3, 4.6, 0.4), node, w)
+    assert n == 4 and abs(sum(w[:n]) - 1.0) < 1e-15                     # the 4 nodes at z = 0 are bounce-back
+    assert all(node[k] % nz == 1 for k in range(n))
+    n = O.lib().ora_ibm_kernel(C.byref(dom), fl.ctypes.data_as(O.c_u8p), (C.c_double * 3)(3.0, 4.0, 2.0), node, w)
+    assert n == 1 and w[0] == 1.0                                       # on a node: single entry
+
+
+def test_poiseuille_body_force_profile():
+    """channel between bounce-back planes, x/y periodic: steady u(z) = g/(2 nu) (z-z0)(z1-z) with the
+    full-way walls half a node outside the last fluid nodes"""
+    nx, ny, nz = 4, 4, 19
+    tau = 1.0; nu = (tau - 0.5) / 3; g = 1e-6
+    dom = O.make_domain(nx, ny, nz, (1, 1, 0), tau)
+    fl = np.zeros((nx, ny, nz), dtype=np.uint8); fl[:, :, 0] = 1; fl[:, :, -1] = 1
+    fl = fl.reshape(-1)
+    N = nx * ny * nz
+    F = np.zeros(3 * N); F[:N] = g
+    pop = O.init_equilibrium(dom)
+    sc = np.empty_like(pop)
+    for _ in range(4000):
+        O.collide_and_stream(dom, fl, pop, F, sc)
+    _, vel = O.moments(dom, fl, pop, F)
+    ux = vel[:N].reshape(nx, ny, nz)[1, 1, 1:-1]
+    z = np.arange(1, nz - 1)
+    ana = g / (2 * nu) * (z - 0.5) * (nz - 1.5 - z)
+    assert np.abs(ux - ana).max() / ana.max() < 0.01
+
+
+def test_couette_regularized_velocity_planes():
+    nx, ny, nz = 4, 4, 17
+    tau = 1.16; uw = 0.02
+    bc = np.zeros((6, 3)); bc[4] = (uw, 0, 0); bc[5] = (-uw, 0, 0)
+    dom = O.make_domain(nx, ny, nz, (1, 1, 0), tau, bc)
+    fl = U.couette_flags(nx, ny, nz).reshape(-1)
+    N = nx * ny * nz
+    F = np.zeros(3 * N)
+    pop = O.init_equilibrium(dom); sc = np.empty_like(pop)
+    for _ in range(6000):
+        O.collide_and_stream(dom, fl, pop, F, sc)
+    rho, vel = O.moments(dom, fl, pop, F)
+    ux = vel[:N].reshape(nx, ny, nz)[2, 2, :]
+    ana = uw * (1 - 2 * np.arange(nz) / (nz - 1))
+    assert np.abs(ux - ana).max() < 2e-4 * uw * 50
+    assert abs(rho.mean() - 1.0) < 1e-3
+
+
+def test_repulsion_quirks():
+    """pairs in neighbouring bins get +-R once; pairs sharing a node get it twice (Appendix D.1);
+    pairs two bins apart are never visited even inside the cutoff"""
+    dom = O.make_domain(16, 16, 16, (1, 1, 1), 1.0)
+    k, cut = 2.0, 1.4
+    def pair(p, q):
+        pos = np.array([p, q], dtype=np.float64)
+        return O.repulsion(dom, pos, np.array([0, 1]), k, cut)
+    f = pair((5.1, 5.0, 5.0), (5.3, 5.0, 5.0))            # same bin
+    d = 0.2
+    assert abs(f[0, 0] + 2 * k * cut / d) < 1e-12 and abs(f[1, 0] - 2 * k * cut / d) < 1e-12
+    f = pair((5.4, 5.0, 5.0), (5.6, 5.0, 5.0))            # neighbouring bins
+    assert abs(f[0, 0] + k * cut / d) < 1e-9 and abs(f[1, 0] - k * cut / d) < 1e-9
+    f = pair((5.45, 5.0, 5.0), (6.55, 5.0, 5.0))          # bins 5 and 7: d = 1.1 < cutoff, not visited
+    assert np.all(f == 0)
+    f = pair((15.4, 5.0, 5.0), (-0.4, 5.0, 5.0))          # bins 15 and 0: neighbours across the periodic face, d = 0.2
+    assert abs(f[0, 0] + k * cut / d) < 1e-9 and abs(f[1, 0] - k * cut / d) < 1e-9
+    same_cell = O.repulsion(dom, np.array([[5.1, 5, 5], [5.3, 5, 5]], dtype=np.float64), np.array([3, 3]), k, cut)
+    assert np.all(same_cell == 0)
+
+
+def test_placement_rules():
+    ct = O.rbc_celltype(PAR)
+    dims = (64, 40, 40)
+    fl = np.zeros(dims, dtype=np.uint8); fl[:, 0, :] = 1; fl[:, -1, :] = 1
+    rows = np.array([[16.0, 10.0, 10.0, 0, 0, 0],        # inside
+                     [1.0, 10.0, 10.0, 0, 0, 0],         # pokes through x = 0: incomplete after loadParticles
+                     [16.0, 1.2, 10.0, 0, 0, 0],         # touches the y wall
+                     [20.0, 10.0, 10.0, 90, 45, 10]])
+    pos, ids = M.place_cells(ct.verts, rows, 0.5e-6, dims, fl.reshape(-1))
+    assert ids.tolist() == [0, 3]
+    assert pos.shape == (2, 642, 3)
+    ctr = 0.5 * (pos[0].min(0) + pos[0].max(0))
+    np.testing.assert_allclose(ctr, [32.0, 20.0, 20.0], atol=1e-9)     # .pos holds the bbox centre
+
+
+def test_stretch_cell_golden_against_reference_bounds():
+    """tests/validation/stretch_cell/test_stretch_cell.cpp:158-162 with the oracle; the 10 000-iteration
+    runs are stored in tests/golden/stretch_oracle.json (tools/gen_stretch_golden.py); here the bounds
+    are asserted on the stored values and the first 200 iterations are re-run live"""
+    path = os.path.join(HERE, "golden", "stretch_oracle.json")
+    g = json.load(open(path))
+    for run in g["runs"]:
+        b = g["bounds_um"][str(run["force_pN"])]
+        last = run["trace"][str(run["iterations"])]
+        assert run["iterations"] == 10000
+        assert b["transverse"][0] <= last["transverse_um"] <= b["transverse"][1], run
+        assert b["axial"][0] <= last["axial_um"] <= b["axial"][1], run
+        assert 0.98 < last["volume_ratio"] <= 1.02
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen", os.path.join(os.path.dirname(HERE), "tools", "gen_stretch_golden.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    live = gen.run(75, 200)
+    ref = [r for r in g["runs"] if r["force_pN"] == 75][0]["trace"]["200"]
+    assert abs(live["trace"]["200"]["axial_um"] - ref["axial_um"]) < 1e-9
+    assert abs(live["trace"]["200"]["transverse_um"] - ref["transverse_um"]) < 1e-9
