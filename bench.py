@@ -158,7 +158,14 @@ def run_cuda(args):
     ctx.set_body_force(body_force(par["nu_lbm"], UNIT_N))
     ctx.set_force_limit(par["f_limit"])
     t = ct.add_to(ctx)
-    cells, ids = ctx.select_local_cells(unit_cells, unit_ids, UNIT_N, world) if world > 1 else (unit_cells, unit_ids)
+    if world > 1:
+        # own unit plus the neighbouring units; the library keeps the cells within its hold region
+        ctx.set_exchange(4.0, 20, 0.3)
+        units = sorted({(rank - 1) % world, rank, (rank + 1) % world})
+        cells = np.concatenate([unit_cells + np.array([u * UNIT_N, 0.0, 0.0]) for u in units])
+        ids = np.concatenate([unit_ids + u * len(rows) for u in units])
+    else:
+        cells, ids = unit_cells, unit_ids
     pos_host = pinned_empty(cells.size)
     pos_host[:] = cells.reshape(-1)
     ctx.add_cells(t, pos_host.reshape(cells.shape), ids)
@@ -201,10 +208,12 @@ def run_cuda(args):
     # (body force H2D + iterate(1) + cell-count D2H), final read-back of positions and forces
     npart = ctx.capacity()[1]
     out_pos = pinned_empty(3 * npart); out_frc = pinned_empty(3 * npart)
+    state_host = pinned_empty(3 * npart)          # the particle state as the host holds it (pinned)
+    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), state_host.ctypes.data_as(H.c_dp))
     ctx.set_iteration(0)
     barrier()
     te0 = time.time()
-    ctx.cells_upload(H.P_POS, pos_host)
+    ctx.cells_upload(H.P_POS, state_host)
     bf = body_force(par["nu_lbm"], UNIT_N)
     for _ in range(args.steps):
         ctx.set_body_force(bf)                    # setExternalVector after every iterate (performance_testing.cpp:132-135)

@@ -43,10 +43,19 @@ __global__ void k_pad_flags(const uint8_t* __restrict__ src, uint8_t* dst, int64
   const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (i < Nl) dst[i + P] = src[i];
 }
+// multi-GPU: a cell is counted by the rank that owns its vertex 0 (replicas are not counted twice)
 __global__ void k_count_alive(const uint8_t* __restrict__ alive, const int32_t* __restrict__ ctype,
-                              const int* __restrict__ typeV, int64_t n, unsigned long long* out) {
+                              const int* __restrict__ typeV, int64_t n, unsigned long long* out,
+                              const int64_t* __restrict__ cell_base, const double* __restrict__ x,
+                              int nranks, int nx, int px, int x0, int nxl) {
   const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= n || !alive[i]) return;
+  if (nranks > 1) {
+    int gx = (int)floor(x[cell_base[i]] + 0.5);
+    if (px) { gx %= nx; if (gx < 0) gx += nx; }
+    int rel = gx - x0; if (px && rel < 0) rel += nx;
+    if (rel < 0 || rel >= nxl) return;
+  }
   atomicAdd(out, 1ULL); atomicAdd(out + 1, (unsigned long long)typeV[ctype[i]]);
 }
 
@@ -115,12 +124,21 @@ hcg_status step(hcg_ctx* c) {
   { OpTimer t(c, "collideAndStream"); if ((s = lat_collide_stream(c, !interp))) return s; }
   if (interp) {
     // interpolation and advance share one pass over the particles (advance uses the velocity just interpolated)
-    { OpTimer t(c, "interpolateFluidVelocity"); if ((s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate_advance(c))) return s; }
+    if (c->dom.n_ranks == 1) {
+      OpTimer t(c, "interpolateFluidVelocity"); if ((s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate_advance(c))) return s;
+    } else {
+      { OpTimer t(c, "interpolateFluidVelocity"); if ((s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate(c))) return s; }
+      { OpTimer t(c, "syncEnvelopes"); if ((s = multi_velocity_sync(c))) return s; }
+      { OpTimer t(c, "advanceParticles"); if ((s = ibm_advance(c))) return s; }
+    }
   } else if (have_p) {
     OpTimer t(c, "advanceParticles"); if ((s = ibm_advance(c))) return s;
   }
   if (have_p && (s = do_mechanics(c, false, false))) return s;
   c->iter++;
+  if (c->dom.n_ranks > 1 && c->iter % c->multi.sync_every == 0) {
+    OpTimer t(c, "syncEnvelopes"); if ((s = multi_rebalance(c, false))) return s;
+  }
   return HCG_OK;
 }
 
@@ -401,10 +419,32 @@ hcg_status hcg_cells_add(hcg_ctx* c, int32_t ctype, int64_t n_cells, const int64
     if (c->types[k].n_cells > 0) return hcg_fail(c, HCG_ERR_STATE, "cells must be added in cell-type order");
   CellTypeHost& th = c->types[ctype];
   if (th.n_cells > 0) return hcg_fail(c, HCG_ERR_STATE, "cells of a type must be added in one call");
-  if (n_cells == 0) return HCG_OK;
-  if (!cell_id || !pos) return HCG_ERR_ARG;
+  if (n_cells > 0 && (!cell_id || !pos)) return HCG_ERR_ARG;
   const int V = th.d.V;
-  const int64_t add_p = n_cells*V, new_p = c->np + add_p, new_c = c->ncells + n_cells;
+  // multi-GPU: keep the cells whose x-extent intersects this rank's hold region (the caller may
+  // pass any superset, e.g. the global list) and reserve spare slots for later arrivals
+  std::vector<int64_t> keep_id; std::vector<double> keep_pos;
+  int64_t n_slots = n_cells;
+  if (c->dom.n_ranks > 1) {
+    std::vector<double> lo(n_cells), hi(n_cells);
+    for (int64_t i = 0; i < n_cells; i++) {
+      double a = pos[3*i*V], b = a;
+      for (int v = 1; v < V; v++) { const double x = pos[3*(i*V + v)]; a = x < a ? x : a; b = x > b ? x : b; }
+      lo[i] = a; hi[i] = b;
+    }
+    std::vector<uint8_t> held(n_cells), sl(n_cells), sr(n_cells);
+    hch_slab_membership(n_cells, lo.data(), hi.data(), c->dom.nx, c->dom.periodic[0], c->nxl, c->dom.rank,
+                        c->dom.n_ranks, c->multi.margin, held.data(), sl.data(), sr.data());
+    for (int64_t i = 0; i < n_cells; i++) if (held[i]) {
+      keep_id.push_back(cell_id[i]);
+      keep_pos.insert(keep_pos.end(), pos + 3*i*V, pos + 3*(i + 1)*V);
+    }
+    n_cells = (int64_t)keep_id.size();
+    cell_id = keep_id.data(); pos = keep_pos.data();
+    n_slots = n_cells + (int64_t)(c->multi.slack*n_cells) + 64;
+  }
+  if (n_slots == 0) return HCG_OK;
+  const int64_t add_p = n_slots*V, new_p = c->np + add_p, new_c = c->ncells + n_slots;
   if (new_p > 2000000000LL) return hcg_fail(c, HCG_ERR_CAPACITY, "more than 2e9 particles on one GPU");
   // grow SoA arrays
   auto grow = [&](double** arr) -> cudaError_t {
@@ -417,15 +457,22 @@ hcg_status hcg_cells_add(hcg_ctx* c, int32_t ctype, int64_t n_cells, const int64
   };
   for (int k = 0; k < 3; k++) { CUDA_TRY(c, grow(&c->pos[k])); CUDA_TRY(c, grow(&c->vel[k])); CUDA_TRY(c, grow(&c->frc[k])); CUDA_TRY(c, grow(&c->frep[k])); }
   if (c->comp_alloc) { for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) { cudaFree(c->comp[k][d]); c->comp[k][d] = nullptr; } c->comp_alloc = false; }
-  th.first_cell = c->ncells; th.first_particle = c->np; th.n_cells = n_cells;
+  th.first_cell = c->ncells; th.first_particle = c->np; th.n_cells = n_cells; th.cap_cells = n_slots;
   for (size_t k = ctype + 1; k < c->types.size(); k++) { c->types[k].first_cell = new_c; c->types[k].first_particle = new_p; }
-  // host-side cell tables
+  // host-side cell tables (slots beyond n_cells are spare: id -1, not alive)
   std::vector<int32_t> pc(add_p);
-  for (int64_t i = 0; i < n_cells; i++) {
-    c->h_cell_id.push_back(cell_id[i]); c->h_cell_type.push_back(ctype); c->h_cell_base.push_back(c->np + i*V);
+  std::vector<uint8_t> alive_new(n_slots, 0);
+  c->multi.free_slots.resize(c->types.size());
+  for (int64_t i = 0; i < n_slots; i++) {
+    c->h_cell_id.push_back(i < n_cells ? cell_id[i] : -1); c->h_cell_type.push_back(ctype); c->h_cell_base.push_back(c->np + i*V);
+    c->multi.h_held.push_back(i < n_cells); c->multi.h_shared[0].push_back(0); c->multi.h_shared[1].push_back(0);
+    alive_new[i] = i < n_cells;
     for (int v = 0; v < V; v++) pc[i*V + v] = (int32_t)(c->ncells + i);
   }
   // device cell tables (rebuilt)
+  std::vector<uint8_t> alive_all(new_c, 0);
+  if (c->ncells) CUDA_TRY(c, cudaMemcpy(alive_all.data(), c->cell_alive, c->ncells, cudaMemcpyDeviceToHost));
+  std::copy(alive_new.begin(), alive_new.end(), alive_all.begin() + c->ncells);
   cudaFree(c->cell_alive); cudaFree(c->cell_type); cudaFree(c->cell_base);
   int32_t* npc;
   CUDA_TRY(c, cudaMalloc(&npc, sizeof(int32_t)*new_p));
@@ -433,18 +480,23 @@ hcg_status hcg_cells_add(hcg_ctx* c, int32_t ctype, int64_t n_cells, const int64
   CUDA_TRY(c, cudaMemcpy(npc + c->np, pc.data(), sizeof(int32_t)*add_p, cudaMemcpyHostToDevice));
   cudaFree(c->p_cell); c->p_cell = npc;
   CUDA_TRY(c, cudaMalloc(&c->cell_alive, new_c));
-  CUDA_TRY(c, cudaMemset(c->cell_alive, 1, new_c));
+  CUDA_TRY(c, cudaMemcpy(c->cell_alive, alive_all.data(), new_c, cudaMemcpyHostToDevice));
   CUDA_TRY(c, cudaMalloc(&c->cell_type, sizeof(int32_t)*new_c));
   CUDA_TRY(c, cudaMalloc(&c->cell_base, sizeof(int64_t)*new_c));
   CUDA_TRY(c, cudaMemcpy(c->cell_type, c->h_cell_type.data(), sizeof(int32_t)*new_c, cudaMemcpyHostToDevice));
   CUDA_TRY(c, cudaMemcpy(c->cell_base, c->h_cell_base.data(), sizeof(int64_t)*new_c, cudaMemcpyHostToDevice));
   // positions
-  hcg_status s = ensure_staging(c, sizeof(double)*3*add_p); if (s) return s;
-  CUDA_TRY(c, cudaMemcpyAsync(c->staging, pos, sizeof(double)*3*add_p, cudaMemcpyHostToDevice, c->stream));
-  k_aos_to_soa<<<nblk(add_p, 256), 256, 0, c->stream>>>(c->staging, c->pos[0] + c->np, c->pos[1] + c->np, c->pos[2] + c->np, add_p);
-  KERNEL_CHECK(c);
+  const int64_t live_p = n_cells*V;
+  hcg_status s = ensure_staging(c, sizeof(double)*3*(live_p + 1)); if (s) return s;
+  if (live_p) {
+    CUDA_TRY(c, cudaMemcpyAsync(c->staging, pos, sizeof(double)*3*live_p, cudaMemcpyHostToDevice, c->stream));
+    k_aos_to_soa<<<nblk(live_p, 256), 256, 0, c->stream>>>(c->staging, c->pos[0] + c->np, c->pos[1] + c->np, c->pos[2] + c->np, live_p);
+    KERNEL_CHECK(c);
+  }
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->np = new_p; c->ncells = new_c; c->cap_p = new_p; c->cap_c = new_c;
+  if (c->multi.d_arr) { cudaFree(c->multi.d_arr); c->multi.d_arr = nullptr; }     // array pointers changed
+  if (c->dom.n_ranks > 1 && (s = multi_rebalance(c, true))) return s;            // builds the shared lists
   if (c->bin_items) { cudaFree(c->bin_items); cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->scan_tmp);
                       c->bin_items = c->bin_count = c->bin_start = nullptr; c->scan_tmp = nullptr; }
   return HCG_OK;
@@ -467,7 +519,8 @@ hcg_status hcg_cells_count(hcg_ctx* c, int64_t* n_cells_alive, int64_t* n_partic
     CUDA_TRY(c, cudaMalloc(&dv, sizeof(int)*hv.size())); CUDA_TRY(c, cudaMalloc(&dout, sizeof(h)));
     CUDA_TRY(c, cudaMemcpyAsync(dv, hv.data(), sizeof(int)*hv.size(), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(dout, 0, sizeof(h), c->stream));
-    k_count_alive<<<nblk(c->ncells, 256), 256, 0, c->stream>>>(c->cell_alive, c->cell_type, dv, c->ncells, dout);
+    k_count_alive<<<nblk(c->ncells, 256), 256, 0, c->stream>>>(c->cell_alive, c->cell_type, dv, c->ncells, dout,
+        c->cell_base, c->pos[0], c->dom.n_ranks, c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
     KERNEL_CHECK(c);
     CUDA_TRY(c, cudaMemcpyAsync(h, dout, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -563,6 +616,21 @@ hcg_status hcg_set_repulsion(hcg_ctx* c, int32_t on, double k, double cut) {
 hcg_status hcg_set_wall_repulsion(hcg_ctx* c, int32_t on, double k, double cut) {
   if (!c || (on && !(cut > 0))) return HCG_ERR_ARG;
   c->wall_on = on != 0; c->wall_k = k; c->wall_cut = cut; return HCG_OK;
+}
+hcg_status hcg_set_exchange(hcg_ctx* c, double margin_lu, int32_t sync_every, double slack) {
+  if (!c || !(margin_lu >= 2.0) || sync_every < 1 || slack < 0) return hcg_fail(c, HCG_ERR_ARG, "exchange: margin >= 2 lu, sync_every >= 1, slack >= 0");
+  if (c->ncells > 0) return hcg_fail(c, HCG_ERR_STATE, "hcg_set_exchange must precede hcg_cells_add");
+  if (c->dom.n_ranks > 1 && 2*margin_lu + 20 > c->nxl) return hcg_fail(c, HCG_ERR_ARG, "slab too thin for this margin");
+  c->multi.margin = margin_lu; c->multi.sync_every = sync_every; c->multi.slack = slack;
+  return HCG_OK;
+}
+hcg_status hcg_exchange_stats(hcg_ctx* c, int64_t* shared_left, int64_t* shared_right, int64_t* migrated_in, int64_t* migrated_out) {
+  if (!c) return HCG_ERR_ARG;
+  if (shared_left) *shared_left = c->multi.face[0].n;
+  if (shared_right) *shared_right = c->multi.face[1].n;
+  if (migrated_in) *migrated_in = c->multi.migrated_in;
+  if (migrated_out) *migrated_out = c->multi.migrated_out;
+  return HCG_OK;
 }
 hcg_status hcg_set_iteration(hcg_ctx* c, int64_t it) { if (!c || it < 0) return HCG_ERR_ARG; c->iter = it; return HCG_OK; }
 hcg_status hcg_get_iteration(hcg_ctx* c, int64_t* it) { if (!c || !it) return HCG_ERR_ARG; *it = c->iter; return HCG_OK; }

@@ -13,6 +13,7 @@
 #include <vector>
 #include <map>
 #include "../../include/hemocell_gpu.h"
+#include "../../include/hemocell_host.h"
 
 #define HCG_MAX_TYPES 8
 #define HCG_MAX_RING 6
@@ -33,9 +34,25 @@ struct CellTypeDev {
 
 struct CellTypeHost {
   CellTypeDev d;
-  int64_t n_cells = 0, first_cell = 0, first_particle = 0;
+  int64_t n_cells = 0, first_cell = 0, first_particle = 0;   // n_cells = slots in use (high-water mark)
+  int64_t cap_cells = 0;                                      // slots reserved (multi-GPU arrivals)
   int timescale = 1;
   std::vector<void*> allocs;
+};
+
+// multi-GPU particle exchange state (csrc/multi.cu)
+struct MultiFace { int32_t* d_cells = nullptr; int64_t* d_off = nullptr; int n = 0, cap = 0; int64_t total = 0; };
+struct MultiState {
+  double margin = 4.0;            // hold region = slab +- margin lattice units
+  int sync_every = 20;            // membership re-evaluation cadence
+  double slack = 0.3;             // spare cell slots per type for arrivals
+  MultiFace face[2];              // cells shared through the left / right face, sorted by global id
+  std::vector<uint8_t> h_held, h_shared[2];
+  std::vector<std::vector<int32_t>> free_slots;
+  double* sync_buf = nullptr; size_t sync_cap = 0;
+  double* mig_buf = nullptr; size_t mig_cap = 0;
+  int64_t* d_cnt = nullptr; double** d_arr = nullptr;
+  int64_t migrated_in = 0, migrated_out = 0;
 };
 
 struct TimerSlot { std::string name; double ms = 0; int64_t calls = 0; };
@@ -75,6 +92,7 @@ struct hcg_ctx {
   cudaStream_t stream, stream_halo;
   cudaEvent_t ev_a, ev_b;
   void* nccl;                  // ncclComm_t
+  MultiState multi;
   double* halo_send[2]; double* halo_recv[2];
   bool timers_on; std::vector<TimerSlot> timers; std::map<std::string,int> timer_idx;
   std::vector<cudaEvent_t> ev_pool; std::vector<TimerPending> ev_pending;
@@ -134,6 +152,9 @@ hcg_status ibm_interpolate_advance(hcg_ctx* c);
 hcg_status mech_apply(hcg_ctx* c, int ctype, bool components);
 hcg_status mech_bbox(hcg_ctx* c, double* out_dev);
 hcg_status mech_volume_area(hcg_ctx* c, double* vol_dev, double* area_dev);
+// multi.cu
+hcg_status multi_velocity_sync(hcg_ctx* c);
+hcg_status multi_rebalance(hcg_ctx* c, bool initial);
 // repulsion.cu
 hcg_status rep_apply(hcg_ctx* c);
 hcg_status rep_wall_apply(hcg_ctx* c);

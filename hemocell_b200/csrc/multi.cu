@@ -1,0 +1,323 @@
+// Multi-GPU particle handling for the x-slab decomposition (one context per rank/GPU).
+// Replaces HemoCellFields::syncEnvelopes + HemoCellParticleDataTransfer (reference
+// core/hemoCellFields.cpp:377-499, core/hemoCellParticleDataTransfer.cpp:33-466) and the
+// deleteNonLocalParticles / deleteIncompleteCells bookkeeping (hemoCellFields.cpp:676-688).
+//
+// Scheme ("replicated whole cells", the reference's own strategy):
+//  * a rank HOLDS every cell whose x-extent intersects [x0 - M, x0 + nxl + M); cells near a slab
+//    face are therefore held by both neighbours, as complete bit-identical copies;
+//  * every holder spreads onto its own real nodes and computes the membrane forces of the whole
+//    cell redundantly from identical inputs -> no force halo is ever communicated;
+//  * on velocity-interpolation steps each vertex velocity is authoritative on the rank that OWNS
+//    the vertex (x in [x0 - 0.5, x0 + nxl - 0.5)); the two holders of a shared cell swap their
+//    velocity arrays (NCCL send/recv) and keep the neighbour's value for vertices they do not own;
+//    the cells' alive flags are AND-ed in the same message;
+//  * every `sync_every` steps membership is re-evaluated from the cells' bounding boxes: cells that
+//    entered a neighbour's hold region are shipped whole (pos, vel, force, frep), cells that left
+//    the own region are dropped.  M = 2 (kernel support) + drift allowance.
+#include "ctx.cuh"
+#include <nccl.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1)/t); }
+
+// does [lo, hi] (unwrapped) intersect [a, b) on a circle of length nx (or on the line)?
+inline bool band_hit(double lo, double hi, double a, double b, int nx, bool periodic) {
+  for (int k = periodic ? -1 : 0; k <= (periodic ? 1 : 0); k++) {
+    const double l = lo + (double)k*nx, h = hi + (double)k*nx;
+    if (l < b && h >= a) return true;
+  }
+  return false;
+}
+
+__global__ void k_pack_sync(const int32_t* __restrict__ cells, const int64_t* __restrict__ off, int n, int64_t total,
+                            const int64_t* __restrict__ cell_base, const uint8_t* __restrict__ alive,
+                            const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
+                            double* buf) {
+  // buf = [n alive flags][3 * total velocities]
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int c = cells[i];
+  const int64_t b = cell_base[c], o = off[i];
+  const int V = (int)(off[i+1] - o);
+  if (threadIdx.x == 0) buf[i] = alive[c] ? 1.0 : 0.0;
+  double* v = buf + n + 3*o;
+  for (int k = threadIdx.x; k < V; k += blockDim.x) { v[3*k] = vx[b+k]; v[3*k+1] = vy[b+k]; v[3*k+2] = vz[b+k]; }
+}
+
+__global__ void k_unpack_sync(const int32_t* __restrict__ cells, const int64_t* __restrict__ off, int n,
+                              const int64_t* __restrict__ cell_base, uint8_t* alive,
+                              const double* __restrict__ x, double* vx, double* vy, double* vz,
+                              const double* __restrict__ buf, int nx, int px, int x0, int nxl) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int c = cells[i];
+  const int64_t b = cell_base[c], o = off[i];
+  const int V = (int)(off[i+1] - o);
+  if (threadIdx.x == 0 && buf[i] == 0.0) alive[c] = 0;
+  const double* v = buf + n + 3*o;
+  for (int k = threadIdx.x; k < V; k += blockDim.x) {
+    // owner test on the pre-advance position: nearest node inside my slab
+    int gx = (int)floor(x[b+k] + 0.5);
+    if (px) { gx %= nx; if (gx < 0) gx += nx; }
+    int rel = gx - x0; if (px && rel < 0) rel += nx;
+    const bool mine = rel >= 0 && rel < nxl;
+    if (!mine) { vx[b+k] = v[3*k]; vy[b+k] = v[3*k+1]; vz[b+k] = v[3*k+2]; }
+  }
+}
+
+// whole-cell migration payload: per cell 12*V doubles (pos, vel, force, frep as xyz triples)
+__global__ void k_pack_cells(const int32_t* __restrict__ cells, const int64_t* __restrict__ off, int n,
+                             const int64_t* __restrict__ cell_base,
+                             const double* const* __restrict__ arr /* 12 SoA arrays */, double* buf) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int64_t b = cell_base[cells[i]], o = off[i];
+  const int V = (int)(off[i+1] - o);
+  double* out = buf + 12*o;
+  for (int k = threadIdx.x; k < 12*V; k += blockDim.x) { const int a = k / V, v = k - a*V; out[k] = arr[a][b+v]; }
+}
+__global__ void k_unpack_cells(const int32_t* __restrict__ cells, const int64_t* __restrict__ off, int n,
+                               const int64_t* __restrict__ cell_base, double* const* __restrict__ arr,
+                               const double* __restrict__ buf, uint8_t* alive) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int c = cells[i];
+  const int64_t b = cell_base[c], o = off[i];
+  const int V = (int)(off[i+1] - o);
+  const double* in = buf + 12*o;
+  for (int k = threadIdx.x; k < 12*V; k += blockDim.x) { const int a = k / V, v = k - a*V; arr[a][b+v] = in[k]; }
+  if (threadIdx.x == 0) alive[c] = 1;
+}
+
+hcg_status nccl_fail(hcg_ctx* c, const char* what, ncclResult_t rc) {
+  return hcg_fail(c, HCG_ERR_NCCL, std::string(what) + ": " + ncclGetErrorString(rc));
+}
+
+// grouped neighbour exchange of raw bytes; order keeps the 2-rank periodic case matched
+hcg_status neighbour_exchange(hcg_ctx* c, const void* sendL, size_t nsL, const void* sendR, size_t nsR,
+                              void* recvR, size_t nrR, void* recvL, size_t nrL) {
+  ncclComm_t comm = (ncclComm_t)c->nccl;
+  const int R = c->dom.n_ranks, r = c->dom.rank; const bool px = c->dom.periodic[0];
+  const int left = (r == 0) ? (px ? R - 1 : -1) : r - 1;
+  const int right = (r == R - 1) ? (px ? 0 : -1) : r + 1;
+  ncclGroupStart();
+  if (left >= 0 && nsL) ncclSend(sendL, nsL, ncclUint8, left, comm, c->stream);
+  if (right >= 0 && nsR) ncclSend(sendR, nsR, ncclUint8, right, comm, c->stream);
+  if (right >= 0 && nrR) ncclRecv(recvR, nrR, ncclUint8, right, comm, c->stream);
+  if (left >= 0 && nrL) ncclRecv(recvL, nrL, ncclUint8, left, comm, c->stream);
+  ncclResult_t rc = ncclGroupEnd();
+  if (rc != ncclSuccess) return nccl_fail(c, "neighbour exchange", rc);
+  return HCG_OK;
+}
+
+hcg_status ensure_buf(hcg_ctx* c, double** p, size_t* cap, size_t doubles) {
+  if (*cap >= doubles) return HCG_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  const size_t want = doubles + doubles/4 + 1024;
+  CUDA_TRY(c, cudaMalloc(p, sizeof(double)*want));
+  *cap = want;
+  return HCG_OK;
+}
+
+// upload a face's shared list (cells sorted by global id) and its particle offsets
+hcg_status upload_list(hcg_ctx* c, MultiFace& f, const std::vector<int32_t>& cells) {
+  f.n = (int)cells.size();
+  std::vector<int64_t> off(f.n + 1, 0);
+  for (int i = 0; i < f.n; i++) off[i+1] = off[i] + c->types[c->h_cell_type[cells[i]]].d.V;
+  f.total = off[f.n];
+  if (f.cap < f.n + 1) {
+    if (f.d_cells) { cudaFree(f.d_cells); cudaFree(f.d_off); }
+    f.cap = f.n + 1 + f.n/2 + 64;
+    CUDA_TRY(c, cudaMalloc(&f.d_cells, sizeof(int32_t)*f.cap));
+    CUDA_TRY(c, cudaMalloc(&f.d_off, sizeof(int64_t)*f.cap));
+  }
+  if (f.n) CUDA_TRY(c, cudaMemcpyAsync(f.d_cells, cells.data(), sizeof(int32_t)*f.n, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(f.d_off, off.data(), sizeof(int64_t)*(f.n + 1), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));     // host vectors go out of scope
+  return HCG_OK;
+}
+
+}  // namespace
+
+// pure host logic, exported for CPU tests (include/hemocell_host.h)
+extern "C" void hch_slab_membership(int64_t n, const double* xlo, const double* xhi, int32_t nx, int32_t periodic_x,
+                                    int32_t nxl, int32_t rank, int32_t n_ranks, double margin,
+                                    uint8_t* held, uint8_t* share_left, uint8_t* share_right) {
+  const double x0 = (double)nxl*rank, x1 = x0 + nxl;
+  const bool px = periodic_x != 0;
+  const bool has_left = n_ranks > 1 && (rank > 0 || px), has_right = n_ranks > 1 && (rank < n_ranks - 1 || px);
+  for (int64_t i = 0; i < n; i++) {
+    const bool h = n_ranks == 1 ? true : band_hit(xlo[i], xhi[i], x0 - margin, x1 + margin, nx, px);
+    held[i] = h;
+    share_left[i] = h && has_left && band_hit(xlo[i], xhi[i], x0 - margin, x0 + margin, nx, px);
+    share_right[i] = h && has_right && band_hit(xlo[i], xhi[i], x1 - margin, x1 + margin, nx, px);
+  }
+}
+
+// velocity + alive-flag swap of the shared cells (every interpolation step)
+hcg_status multi_velocity_sync(hcg_ctx* c) {
+  if (c->dom.n_ranks == 1) return HCG_OK;
+  MultiState& m = c->multi;
+  hcg_status s;
+  size_t ns[2], off_send[2], off_recv[2];
+  size_t tot = 0;
+  for (int f = 0; f < 2; f++) { ns[f] = (size_t)m.face[f].n + 3*(size_t)m.face[f].total; off_send[f] = tot; tot += ns[f]; }
+  for (int f = 0; f < 2; f++) { off_recv[f] = tot; tot += ns[f]; }      // both sides hold the same lists
+  if ((s = ensure_buf(c, &m.sync_buf, &m.sync_cap, tot))) return s;
+  for (int f = 0; f < 2; f++) {
+    if (!m.face[f].n) continue;
+    k_pack_sync<<<m.face[f].n, 128, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n, m.face[f].total,
+        c->cell_base, c->cell_alive, c->vel[0], c->vel[1], c->vel[2], m.sync_buf + off_send[f]);
+    KERNEL_CHECK(c);
+  }
+  if ((s = neighbour_exchange(c, m.sync_buf + off_send[0], 8*ns[0], m.sync_buf + off_send[1], 8*ns[1],
+                              m.sync_buf + off_recv[1], 8*ns[1], m.sync_buf + off_recv[0], 8*ns[0]))) return s;
+  for (int f = 0; f < 2; f++) {
+    if (!m.face[f].n) continue;
+    k_unpack_sync<<<m.face[f].n, 128, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n,
+        c->cell_base, c->cell_alive, c->pos[0], c->vel[0], c->vel[1], c->vel[2], m.sync_buf + off_recv[f],
+        c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
+    KERNEL_CHECK(c);
+  }
+  return HCG_OK;
+}
+
+// membership re-evaluation + whole-cell migration (host coordinated; every sync_every steps)
+hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
+  if (c->dom.n_ranks == 1) return HCG_OK;
+  MultiState& m = c->multi;
+  hcg_status s;
+  const int64_t nc = c->ncells;
+  const int nx = c->dom.nx; const bool px = c->dom.periodic[0];
+  // 0. agree on the alive flags first (a boundary hit is seen only by the rank that holds the node)
+  if (!initial && (s = multi_velocity_sync(c))) return s;
+  // 1. bounding boxes and alive flags of every slot
+  std::vector<double> bbox(6*(size_t)std::max<int64_t>(nc, 1));
+  std::vector<uint8_t> alive(std::max<int64_t>(nc, 1));
+  if (nc) {
+    double* d_bbox;
+    CUDA_TRY(c, cudaMalloc(&d_bbox, sizeof(double)*6*nc));
+    if ((s = mech_bbox(c, d_bbox))) return s;
+    CUDA_TRY(c, cudaMemcpy(bbox.data(), d_bbox, sizeof(double)*6*nc, cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemcpy(alive.data(), c->cell_alive, nc, cudaMemcpyDeviceToHost));
+    cudaFree(d_bbox);
+  }
+  std::vector<double> lo(nc), hi(nc);
+  for (int64_t i = 0; i < nc; i++) { lo[i] = bbox[6*i]; hi[i] = bbox[6*i+1]; }
+  std::vector<uint8_t> held(nc), shl(nc), shr(nc);
+  hch_slab_membership(nc, lo.data(), hi.data(), nx, px, c->nxl, c->dom.rank, c->dom.n_ranks, m.margin,
+                      held.data(), shl.data(), shr.data());
+  // 2. drops and departures
+  std::vector<int32_t> send[2];
+  bool alive_dirty = false;
+  for (int64_t i = 0; i < nc; i++) {
+    if (!m.h_held[i]) continue;
+    if (!held[i] || !alive[i]) {          // left my hold region, or deleted on every holder: forget it
+      m.h_held[i] = 0; m.h_shared[0][i] = m.h_shared[1][i] = 0;
+      if (alive[i]) { alive[i] = 0; alive_dirty = true; }
+      c->h_cell_id[i] = -1;
+      m.free_slots[c->h_cell_type[i]].push_back((int32_t)i);
+      continue;
+    }
+    const uint8_t sh[2] = {shl[i], shr[i]};
+    for (int f = 0; f < 2; f++) {
+      if (sh[f] && !m.h_shared[f][i] && alive[i] && !initial) send[f].push_back((int32_t)i);
+      m.h_shared[f][i] = sh[f];
+    }
+  }
+  // 3. exchange counts, then meta (id, type) and payload
+  int64_t h_cnt[4] = {(int64_t)send[0].size(), (int64_t)send[1].size(), 0, 0};
+  if (!m.d_cnt) CUDA_TRY(c, cudaMalloc(&m.d_cnt, sizeof(int64_t)*4));
+  CUDA_TRY(c, cudaMemcpyAsync(m.d_cnt, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, c->stream));
+  if ((s = neighbour_exchange(c, m.d_cnt, 8, m.d_cnt + 1, 8, m.d_cnt + 3, 8, m.d_cnt + 2, 8))) return s;
+  CUDA_TRY(c, cudaMemcpyAsync(h_cnt, m.d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const int64_t n_recv[2] = {h_cnt[2], h_cnt[3]};      // from left, from right
+  const int R = c->dom.n_ranks, r = c->dom.rank;
+  const bool has[2] = {r > 0 || px, r < R - 1 || px};
+  // meta
+  std::vector<int64_t> meta_send[2], meta_recv[2];
+  int64_t *d_ms[2] = {nullptr, nullptr}, *d_mr[2] = {nullptr, nullptr};
+  for (int f = 0; f < 2; f++) {
+    for (int32_t sl : send[f]) { meta_send[f].push_back(c->h_cell_id[sl]); meta_send[f].push_back(c->h_cell_type[sl]); }
+    if (!meta_send[f].empty()) {
+      CUDA_TRY(c, cudaMalloc(&d_ms[f], sizeof(int64_t)*meta_send[f].size()));
+      CUDA_TRY(c, cudaMemcpyAsync(d_ms[f], meta_send[f].data(), sizeof(int64_t)*meta_send[f].size(), cudaMemcpyHostToDevice, c->stream));
+    }
+    meta_recv[f].resize(2*(size_t)(has[f] ? n_recv[f] : 0));
+    if (!meta_recv[f].empty()) CUDA_TRY(c, cudaMalloc(&d_mr[f], sizeof(int64_t)*meta_recv[f].size()));
+  }
+  if ((s = neighbour_exchange(c, d_ms[0], 8*meta_send[0].size(), d_ms[1], 8*meta_send[1].size(),
+                              d_mr[1], 8*meta_recv[1].size(), d_mr[0], 8*meta_recv[0].size()))) return s;
+  for (int f = 0; f < 2; f++)
+    if (!meta_recv[f].empty()) CUDA_TRY(c, cudaMemcpyAsync(meta_recv[f].data(), d_mr[f], 8*meta_recv[f].size(), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  // payload
+  MultiFace tmp_send[2], tmp_recv[2];
+  std::vector<int32_t> arrive[2];
+  for (int f = 0; f < 2; f++) {
+    for (size_t k = 0; k < meta_recv[f].size()/2; k++) {
+      const int t = (int)meta_recv[f][2*k+1];
+      if (t < 0 || t >= (int)c->types.size()) return hcg_fail(c, HCG_ERR_STATE, "migration: unknown cell type received");
+      int32_t slot;
+      if (!m.free_slots[t].empty()) { slot = m.free_slots[t].back(); m.free_slots[t].pop_back(); }
+      else {
+        CellTypeHost& th = c->types[t];
+        if (th.n_cells >= th.cap_cells) return hcg_fail(c, HCG_ERR_CAPACITY, "migration: no free cell slot (raise the slack)");
+        slot = (int32_t)(th.first_cell + th.n_cells++);
+      }
+      c->h_cell_id[slot] = meta_recv[f][2*k];
+      m.h_held[slot] = 1; m.h_shared[0][slot] = m.h_shared[1][slot] = 0;
+      m.h_shared[f][slot] = 1;            // shared with the rank it came from, through that face
+      arrive[f].push_back(slot);
+    }
+    if ((s = upload_list(c, tmp_send[f], send[f]))) return s;
+    if ((s = upload_list(c, tmp_recv[f], arrive[f]))) return s;
+  }
+  size_t need = 0, o_s[2], o_r[2];
+  for (int f = 0; f < 2; f++) { o_s[f] = need; need += 12*(size_t)tmp_send[f].total; }
+  for (int f = 0; f < 2; f++) { o_r[f] = need; need += 12*(size_t)tmp_recv[f].total; }
+  if ((s = ensure_buf(c, &m.mig_buf, &m.mig_cap, need))) return s;
+  if (!m.d_arr) {
+    double* h_arr[12];
+    for (int k = 0; k < 3; k++) { h_arr[k] = c->pos[k]; h_arr[3+k] = c->vel[k]; h_arr[6+k] = c->frc[k]; h_arr[9+k] = c->frep[k]; }
+    CUDA_TRY(c, cudaMalloc(&m.d_arr, sizeof(h_arr)));
+    CUDA_TRY(c, cudaMemcpy(m.d_arr, h_arr, sizeof(h_arr), cudaMemcpyHostToDevice));
+  }
+  for (int f = 0; f < 2; f++) if (tmp_send[f].n) {
+    k_pack_cells<<<tmp_send[f].n, 256, 0, c->stream>>>(tmp_send[f].d_cells, tmp_send[f].d_off, tmp_send[f].n, c->cell_base,
+                                                        (const double* const*)m.d_arr, m.mig_buf + o_s[f]);
+    KERNEL_CHECK(c);
+  }
+  if ((s = neighbour_exchange(c, m.mig_buf + o_s[0], 8*12*(size_t)tmp_send[0].total, m.mig_buf + o_s[1], 8*12*(size_t)tmp_send[1].total,
+                              m.mig_buf + o_r[1], 8*12*(size_t)tmp_recv[1].total, m.mig_buf + o_r[0], 8*12*(size_t)tmp_recv[0].total))) return s;
+  if (alive_dirty) CUDA_TRY(c, cudaMemcpyAsync(c->cell_alive, alive.data(), nc, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int f = 0; f < 2; f++) if (tmp_recv[f].n) {
+    k_unpack_cells<<<tmp_recv[f].n, 256, 0, c->stream>>>(tmp_recv[f].d_cells, tmp_recv[f].d_off, tmp_recv[f].n, c->cell_base,
+                                                          m.d_arr, m.mig_buf + o_r[f], c->cell_alive);
+    KERNEL_CHECK(c);
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int f = 0; f < 2; f++) {
+    cudaFree(d_ms[f]); cudaFree(d_mr[f]);
+    cudaFree(tmp_send[f].d_cells); cudaFree(tmp_send[f].d_off); cudaFree(tmp_recv[f].d_cells); cudaFree(tmp_recv[f].d_off);
+  }
+  m.migrated_in += (int64_t)arrive[0].size() + (int64_t)arrive[1].size();
+  m.migrated_out += (int64_t)send[0].size() + (int64_t)send[1].size();
+  // 4. shared lists, sorted by global cell id so that both holders pack in the same order
+  for (int f = 0; f < 2; f++) {
+    std::vector<int32_t> list;
+    for (int64_t i = 0; i < nc; i++)
+      if (m.h_held[i] && m.h_shared[f][i] && c->h_cell_id[i] >= 0) list.push_back((int32_t)i);
+    std::sort(list.begin(), list.end(), [&](int32_t a, int32_t b) { return c->h_cell_id[a] < c->h_cell_id[b]; });
+    if ((s = upload_list(c, m.face[f], list))) return s;
+  }
+  return HCG_OK;
+}

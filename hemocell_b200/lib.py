@@ -49,7 +49,7 @@ hcg_lattice_set_flags hcg_lattice_set_bc_velocity hcg_lattice_init_equilibrium h
 hcg_lattice_upload hcg_lattice_download hcg_celltype_add hcg_cells_add hcg_cells_count hcg_cells_capacity
 hcg_cells_upload hcg_cells_download hcg_cells_info hcg_cells_add_force hcg_celltype_set_stiffness
 hcg_set_force_limit hcg_set_timescales hcg_set_material_timescale hcg_set_repulsion hcg_set_wall_repulsion
-hcg_set_iteration hcg_get_iteration hcg_iterate hcg_fluid_warmup hcg_op_repulsion hcg_op_wall_repulsion
+hcg_set_exchange hcg_exchange_stats hcg_set_iteration hcg_get_iteration hcg_iterate hcg_fluid_warmup hcg_op_repulsion hcg_op_wall_repulsion
 hcg_op_spread hcg_op_collide_stream hcg_op_interpolate hcg_op_sync hcg_op_advance hcg_op_mechanics
 hcg_op_zero_force hcg_cells_bbox hcg_cells_volume_area hcg_fluid_velocity_stats hcg_timers_enable
 hcg_timers hcg_timers_reset hcg_launch_count hcg_synchronize hcg_iterate_timed""".split()
@@ -237,6 +237,14 @@ class Context:
     def set_wall_repulsion(self, on, k, cutoff):
         self._ck(self.L.hcg_set_wall_repulsion(self.h, C.c_int32(int(on)), C.c_double(k), C.c_double(cutoff)))
 
+    def set_exchange(self, margin=4.0, sync_every=20, slack=0.3):
+        self._ck(self.L.hcg_set_exchange(self.h, C.c_double(margin), C.c_int32(sync_every), C.c_double(slack)))
+
+    def exchange_stats(self):
+        v = [C.c_int64() for _ in range(4)]
+        self._ck(self.L.hcg_exchange_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(["shared_left", "shared_right", "migrated_in", "migrated_out"], [x.value for x in v]))
+
     def set_iteration(self, it):
         self._ck(self.L.hcg_set_iteration(self.h, C.c_int64(it)))
 
@@ -302,7 +310,7 @@ class Context:
 
 # ------------------------------------------------------------------ host-side set-up (C++ in the same .so)
 HOST_SYMBOLS = """hch_parameters hch_celltype_build hch_celltype_view hch_celltype_vertices hch_celltype_scalar
-hch_celltype_free hch_read_pos hch_place_cells hch_last_error""".split()
+hch_celltype_free hch_read_pos hch_place_cells hch_slab_membership hch_last_error""".split()
 
 RBC_MATERIAL = dict(kBend=80.0, kVolume=20.0, kArea=5.0, kLink=15.0, eta_m=0.0, minNumTriangles=600,
                     radius=3.91e-6, aspectRatio=0.3)
@@ -394,6 +402,18 @@ class HostCellType:
                 self.h = None
         except Exception:
             pass
+
+
+def slab_membership(xlo, xhi, nx, periodic_x, nxl, rank, n_ranks, margin):
+    """hch_slab_membership -> (held, share_left, share_right) boolean arrays"""
+    xlo = np.ascontiguousarray(xlo, dtype=np.float64); xhi = np.ascontiguousarray(xhi, dtype=np.float64)
+    n = xlo.shape[0]
+    out = [np.zeros(n, dtype=np.uint8) for _ in range(3)]
+    fn = load().hch_slab_membership
+    fn.restype = None
+    fn(C.c_int64(n), _p(xlo), _p(xhi), C.c_int32(nx), C.c_int32(int(periodic_x)), C.c_int32(nxl), C.c_int32(rank),
+       C.c_int32(n_ranks), C.c_double(margin), *[_p(o, c_u8p) for o in out])
+    return [o.astype(bool) for o in out]
 
 
 def read_pos(path):

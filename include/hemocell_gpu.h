@@ -142,8 +142,13 @@ hcg_status hcg_set_material_timescale(hcg_ctx*, int32_t ctype, int32_t every);
 hcg_status hcg_set_repulsion(hcg_ctx*, int32_t enabled, double k, double cutoff_lu);
 /* HemoCell::enableBoundaryParticles (core/hemoCell.cpp:428-436) */
 hcg_status hcg_set_wall_repulsion(hcg_ctx*, int32_t enabled, double k, double cutoff_lu);
-/* store the interpolation velocity field u = j/rho + F/2 explicitly (1) or gather it from the
- * populations inside the interpolation kernel (0) */
+/* multi-GPU particle exchange (replaces particleEnvelope of config.xml and the comm. structure of
+ * HemoCellFields::calculateCommunicationStructure, core/hemoCellFields.cpp:363-372): a rank holds
+ * every cell within `margin_lu` of its slab, membership is re-evaluated every `sync_every` steps,
+ * `slack` = fraction of spare cell slots for arrivals.  Must precede hcg_cells_add. */
+hcg_status hcg_set_exchange(hcg_ctx*, double margin_lu, int32_t sync_every, double slack);
+hcg_status hcg_exchange_stats(hcg_ctx*, int64_t* shared_left, int64_t* shared_right,
+                              int64_t* migrated_in, int64_t* migrated_out);
 hcg_status hcg_set_iteration(hcg_ctx*, int64_t iter);
 hcg_status hcg_get_iteration(hcg_ctx*, int64_t* iter);
 

@@ -41,6 +41,12 @@ int64_t hch_read_pos(const char* path, double* rows6, int64_t capacity_rows);
 int64_t hch_place_cells(const hch_celltype*, const double* rows6, int64_t n_rows, double dx,
                         int32_t nx, int32_t ny, int32_t nz, const uint8_t* flags /*may be NULL*/,
                         double min_dist_from_solid_um, int64_t cell_id0, double* out_pos, int64_t* out_ids);
+/* slab membership of cells for the multi-GPU exchange (pure host logic of csrc/multi.cu; replaces the
+ * envelope tests of HemoCellParticleField::isContainedABS, core/hemoCellParticleField.h:93-103):
+ * from the cells' x-extents decide which this rank holds and which it shares through each face */
+void hch_slab_membership(int64_t n, const double* xlo, const double* xhi, int32_t nx, int32_t periodic_x,
+                         int32_t nxl, int32_t rank, int32_t n_ranks, double margin,
+                         uint8_t* held, uint8_t* share_left, uint8_t* share_right);
 const char* hch_last_error(void);
 
 #ifdef __cplusplus

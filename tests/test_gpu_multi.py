@@ -1,0 +1,131 @@
+"""Multi-GPU parity (needs >= 2 GPUs in one box; skipped otherwise): the x-slab decomposition with
+NCCL halo exchange + whole-cell replication/migration must reproduce the single-GPU run of the
+same global problem.  One context per GPU, driven from one thread each (NCCL needs concurrency)."""
+import ctypes as C
+import threading
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import mesh as M
+import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    try:
+        rt = C.CDLL("libcudart.so.12")
+        n = C.c_int(0)
+        return n.value if rt.cudaGetDeviceCount(C.byref(n)) == 0 and n.value >= 0 and not None else 0
+    except OSError:
+        return 0
+
+
+def _device_count():
+    rt = C.CDLL("libcudart.so.12")
+    n = C.c_int(0)
+    return n.value if rt.cudaGetDeviceCount(C.byref(n)) == 0 else 0
+
+
+def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, cadence, sync_every, f_limit):
+    from hemocell_b200 import lib as H
+    nx, ny, nz = dims
+    nxl = nx // R
+    uid = H.Context.unique_id()
+    out, err = [None] * R, [None] * R
+    fl3 = fl.reshape(nx, ny, nz)
+
+    def work(r):
+        try:
+            ctx = H.Context(nx, ny, nz, periodic, tau, device=r, rank=r, n_ranks=R)
+            ctx.comm_init(uid)
+            ctx.set_flags(np.ascontiguousarray(fl3[r * nxl:(r + 1) * nxl]))
+            for o in range(6):
+                ctx.set_bc_velocity(o, bc[o])
+            ctx.set_body_force(body)
+            ctx.init_equilibrium(1.0, u0)
+            ctx.set_force_limit(f_limit)
+            ctx.set_exchange(4.0, sync_every, 0.5)
+            t = ctx.add_celltype(ct.model, ct.cc, ct.k)
+            ctx.add_cells(t, cells, ids)                  # global list: the library keeps what it holds
+            ctx.set_timescales(cadence, 1, 1)
+            ctx.set_material_timescale(t, cadence)
+            ctx.iterate(steps)
+            cid, _, alive = ctx.cells_info()
+            out[r] = dict(pop=ctx.lattice_download(H.LAT_POP), pos=ctx.cells_download(H.P_POS),
+                          vel=ctx.cells_download(H.P_VEL), frc=ctx.cells_download(H.P_FORCE),
+                          ids=cid, alive=alive, count=ctx.count(), stats=ctx.exchange_stats())
+            ctx.close()
+        except Exception as e:          # noqa: BLE001
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(R)]
+    [t.start() for t in th]
+    [t.join(timeout=600) for t in th]
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+@pytest.mark.parametrize("cadence", [1, 5])
+def test_two_gpu_matches_single_gpu(cadence):
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from hemocell_b200 import lib as H
+    R = 2
+    dims = (96, 32, 28)
+    nx, ny, nz = dims
+    periodic = (1, 1, 0)
+    par = M.Parameters(dx=0.5e-6, dt=0.5e-7)
+    bc = np.zeros((6, 3)); bc[4] = (0.06, 0, 0); bc[5] = (0.02, 0, 0)
+    fl = U.couette_flags(nx, ny, nz).reshape(-1)
+    body = (1e-6, 0.0, 0.0)
+    u0 = (0.04, 0.0, 0.0)
+    ct = O.rbc_celltype(par)
+    # cells near both slab faces (x = 48 and the periodic x = 0/96) and in the bulk
+    centers = [(41.0, 16.0, 14.0), (49.5, 12.0, 9.0), (88.5, 17.0, 15.0), (3.0, 14.0, 18.0), (24.0, 16.0, 13.0), (70.0, 15.0, 8.5)]
+    cells = U.deformed_cells(ct, centers, 6, amp=0.0, stretch=(1.04, 0.98, 0.98))
+    ids = np.arange(len(centers)) + 100
+    steps, sync_every = 120, 5
+    # single-GPU reference run
+    ctx = H.Context(nx, ny, nz, periodic, par.tau, device=0)
+    ctx.set_flags(fl)
+    for o in range(6):
+        ctx.set_bc_velocity(o, bc[o])
+    ctx.set_body_force(body); ctx.init_equilibrium(1.0, u0); ctx.set_force_limit(par.f_limit)
+    t = ctx.add_celltype(ct.model, ct.cc, ct.k)
+    ctx.add_cells(t, cells, ids)
+    ctx.set_timescales(cadence, 1, 1); ctx.set_material_timescale(t, cadence)
+    ctx.iterate(steps)
+    ref_pop = ctx.lattice_download(H.LAT_POP).reshape(19, nx, ny, nz)
+    ref_pos = ctx.cells_download(H.P_POS).reshape(len(centers), ct.V, 3)
+    ref_vel = ctx.cells_download(H.P_VEL).reshape(len(centers), ct.V, 3)
+    ref_frc = ctx.cells_download(H.P_FORCE).reshape(len(centers), ct.V, 3)
+    assert ctx.count()[0] == len(centers)
+    ctx.close()
+    # the cells moved ~5 lu downstream: some crossed a slab face
+    assert (ref_pos[:, :, 0].mean(1) - cells[:, :, 0].mean(1)).min() > 3.0
+
+    out = _run_multi(R, dims, periodic, par.tau, fl, bc, body, ct, cells, ids, u0, steps, cadence, sync_every, par.f_limit)
+    nxl = nx // R
+    for r in range(R):
+        got = out[r]["pop"].reshape(19, nxl, ny, nz)
+        U.assert_close(got, ref_pop[:, r * nxl:(r + 1) * nxl], f"populations of rank {r}", rtol=1e-9, floor=1e-11)
+    assert sum(o["count"][0] for o in out) == len(centers)          # every cell counted exactly once
+    seen = set()
+    for r in range(R):
+        o = out[r]
+        pos = o["pos"].reshape(-1, ct.V, 3); vel = o["vel"].reshape(-1, ct.V, 3); frc = o["frc"].reshape(-1, ct.V, 3)
+        for slot, (cid, al) in enumerate(zip(o["ids"], o["alive"])):
+            if cid < 0 or not al:
+                continue
+            k = int(cid) - 100
+            seen.add(k)
+            U.assert_close(pos[slot], ref_pos[k], f"rank {r} cell {cid} positions", rtol=1e-11, floor=1e-12)
+            U.assert_close(vel[slot], ref_vel[k], f"rank {r} cell {cid} velocities", rtol=1e-7, floor=1e-9)
+            U.assert_close(frc[slot], ref_frc[k], f"rank {r} cell {cid} forces", rtol=1e-6, floor=1e-8)
+    assert seen == set(range(len(centers)))
+    assert sum(o["stats"]["migrated_in"] for o in out) > 0            # whole-cell migration was exercised
+    assert all(o["stats"]["shared_left"] + o["stats"]["shared_right"] > 0 for o in out)
