@@ -85,7 +85,7 @@ def test_two_gpu_matches_single_gpu(cadence):
     u0 = (0.04, 0.0, 0.0)
     ct = O.rbc_celltype(par)
     # cells near both slab faces (x = 48 and the periodic x = 0/96) and in the bulk
-    centers = [(41.0, 16.0, 14.0), (49.5, 12.0, 9.0), (88.5, 17.0, 15.0), (3.0, 14.0, 18.0), (24.0, 16.0, 13.0), (70.0, 15.0, 8.5)]
+    centers = [(41.0, 16.0, 14.0), (58.0, 12.0, 9.0), (88.5, 17.0, 15.0), (3.0, 14.0, 18.0), (34.0, 24.0, 14.0), (70.0, 15.0, 8.5)]
     cells = U.deformed_cells(ct, centers, 6, amp=0.0, stretch=(1.04, 0.98, 0.98))
     ids = np.arange(len(centers)) + 100
     steps, sync_every = 120, 5
@@ -128,4 +128,6 @@ def test_two_gpu_matches_single_gpu(cadence):
             U.assert_close(frc[slot], ref_frc[k], f"rank {r} cell {cid} forces", rtol=1e-6, floor=1e-8)
     assert seen == set(range(len(centers)))
     assert sum(o["stats"]["migrated_in"] for o in out) > 0            # whole-cell migration was exercised
+    assert sum(o["stats"]["migrated_in"] for o in out) == sum(o["stats"]["migrated_out"] for o in out)
+    assert any(int((o["ids"] < 0).sum()) > 0 for o in out)                 # ... and so was dropping
     assert all(o["stats"]["shared_left"] + o["stats"]["shared_right"] > 0 for o in out)
