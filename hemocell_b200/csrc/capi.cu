@@ -113,13 +113,25 @@ hcg_status do_mechanics(hcg_ctx* c, bool forced, bool components) {
   return HCG_OK;
 }
 
+// spreadParticleForce: node-sorted pair path when every cell type supports it, else plain atomics
+hcg_status do_spread(hcg_ctx* c) {
+  bool sorted = c->spread_mode == 1;
+  for (auto& t : c->types) if (t.n_cells > 0 && !spread_sorted_supported(t)) sorted = false;
+  if (!sorted) return ibm_spread(c);
+  if (!c->perm_valid || c->iter % c->perm_every == 0) {
+    hcg_status s = spread_sorted_rebuild(c); if (s) return s;
+    c->perm_valid = true;
+  }
+  return spread_sorted(c);
+}
+
 // one HemoCell::iterate() (core/hemoCell.cpp:299-376)
 hcg_status step(hcg_ctx* c) {
   hcg_status s;
   const bool have_p = c->np > 0;
   if (have_p && c->rep_on && c->iter % c->ts_rep == 0) { OpTimer t(c, "applyRepulsionForce"); if ((s = rep_apply(c))) return s; }
   if (have_p && c->wall_on && c->iter % c->ts_wall == 0) { OpTimer t(c, "applyBoundaryRepulsionForce"); if ((s = rep_wall_apply(c))) return s; }
-  if (have_p) { OpTimer t(c, "spreadParticleForce"); if ((s = ibm_spread(c))) return s; }
+  if (have_p) { OpTimer t(c, "spreadParticleForce"); if ((s = do_spread(c))) return s; }
   const bool interp = have_p && (c->iter % c->ts_vel == 0);
   { OpTimer t(c, "collideAndStream"); if ((s = lat_collide_stream(c, !interp))) return s; }
   if (interp) {
@@ -167,7 +179,7 @@ hcg_status hcg_create(const hcg_domain* d, hcg_ctx** out) {
   c->omega = 1.0 / d->tau;
   memset(c->bc_vel, 0, sizeof(c->bc_vel)); memset(c->body, 0, sizeof(c->body));
   c->f_limit = 1e300;
-  c->cur = 0; c->u_valid = false; c->has_velbc = false; c->rho = nullptr;
+  c->cur = 0; c->u_valid = false; c->has_velbc = false; c->has_nonfluid = d->n_ranks > 1; c->rho = nullptr;
   c->np = c->ncells = c->cap_p = c->cap_c = 0;
   for (int k = 0; k < 3; k++) c->pos[k] = c->vel[k] = c->frc[k] = c->frep[k] = nullptr;
   memset(c->comp, 0, sizeof(c->comp)); c->comp_alloc = false;
@@ -176,7 +188,7 @@ hcg_status hcg_create(const hcg_domain* d, hcg_ctx** out) {
   c->ts_vel = c->ts_rep = c->ts_wall = 1;
   c->bin_count = c->bin_start = c->bin_items = nullptr; c->wall_nodes = nullptr; c->n_wall = 0; c->wall_built = false;
   c->scan_tmp = nullptr; c->scan_tmp_bytes = 0;
-  c->iter = 0; c->nccl = nullptr; c->timers_on = false; c->launches = 0;
+  c->iter = 0; c->spread_mode = 1; c->perm_valid = false; c->perm_every = 20; c->nccl = nullptr; c->timers_on = false; c->launches = 0;
   c->staging = nullptr; c->staging_bytes = 0;
   c->halo_send[0] = c->halo_send[1] = c->halo_recv[0] = c->halo_recv[1] = nullptr;
   *out = c;
@@ -215,7 +227,7 @@ void hcg_destroy(hcg_ctx* c) {
   cudaFree(c->p_cell); cudaFree(c->cell_alive); cudaFree(c->cell_type); cudaFree(c->cell_base);
   cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->bin_items); cudaFree(c->wall_nodes); cudaFree(c->scan_tmp);
   cudaFree(c->staging);
-  for (auto& t : c->types) for (void* p : t.allocs) cudaFree(p);
+  for (auto& t : c->types) { for (void* p : t.allocs) cudaFree(p); if (t.perm) cudaFree(t.perm); }
   for (auto& p : c->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
@@ -256,6 +268,9 @@ hcg_status hcg_lattice_set_flags(hcg_ctx* c, const uint8_t* flags) {
     vel = vel || flags[i] >= HCG_VEL_XN;
   }
   c->has_velbc = vel;
+  bool nonfluid = c->dom.n_ranks > 1;           // ghost planes carry the neighbour's flags
+  for (int64_t i = 0; i < c->Nl && !nonfluid; i++) nonfluid = flags[i] != HCG_FLUID;
+  c->has_nonfluid = nonfluid;
   hcg_status s = ensure_staging(c, c->Nl); if (s) return s;
   CUDA_TRY(c, cudaMemcpyAsync(c->staging, flags, c->Nl, cudaMemcpyHostToDevice, c->stream));
   k_pad_flags<<<nblk(c->Nl, 256), 256, 0, c->stream>>>((const uint8_t*)c->staging, c->flags, c->Nl, c->P);
@@ -496,6 +511,7 @@ hcg_status hcg_cells_add(hcg_ctx* c, int32_t ctype, int64_t n_cells, const int64
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->np = new_p; c->ncells = new_c; c->cap_p = new_p; c->cap_c = new_c;
   if (c->multi.d_arr) { cudaFree(c->multi.d_arr); c->multi.d_arr = nullptr; }     // array pointers changed
+  c->perm_valid = false;
   if (c->dom.n_ranks > 1 && (s = multi_rebalance(c, true))) return s;            // builds the shared lists
   if (c->bin_items) { cudaFree(c->bin_items); cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->scan_tmp);
                       c->bin_items = c->bin_count = c->bin_start = nullptr; c->scan_tmp = nullptr; }
@@ -617,6 +633,11 @@ hcg_status hcg_set_wall_repulsion(hcg_ctx* c, int32_t on, double k, double cut) 
   if (!c || (on && !(cut > 0))) return HCG_ERR_ARG;
   c->wall_on = on != 0; c->wall_k = k; c->wall_cut = cut; return HCG_OK;
 }
+hcg_status hcg_set_spread_mode(hcg_ctx* c, int32_t mode, int32_t resort_every) {
+  if (!c || mode < 0 || mode > 1 || resort_every < 1) return HCG_ERR_ARG;
+  c->spread_mode = mode; c->perm_every = resort_every; c->perm_valid = false;
+  return HCG_OK;
+}
 hcg_status hcg_set_exchange(hcg_ctx* c, double margin_lu, int32_t sync_every, double slack) {
   if (!c || !(margin_lu >= 2.0) || sync_every < 1 || slack < 0) return hcg_fail(c, HCG_ERR_ARG, "exchange: margin >= 2 lu, sync_every >= 1, slack >= 0");
   if (c->ncells > 0) return hcg_fail(c, HCG_ERR_STATE, "hcg_set_exchange must precede hcg_cells_add");
@@ -675,7 +696,7 @@ hcg_status hcg_fluid_warmup(hcg_ctx* c, int64_t n) {
 #define OP_EPILOGUE CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return HCG_OK
 hcg_status hcg_op_repulsion(hcg_ctx* c) { OP_PROLOGUE; if ((s = rep_apply(c))) return s; OP_EPILOGUE; }
 hcg_status hcg_op_wall_repulsion(hcg_ctx* c) { OP_PROLOGUE; if ((s = rep_wall_apply(c))) return s; OP_EPILOGUE; }
-hcg_status hcg_op_spread(hcg_ctx* c) { OP_PROLOGUE; if ((s = ibm_spread(c))) return s; OP_EPILOGUE; }
+hcg_status hcg_op_spread(hcg_ctx* c) { OP_PROLOGUE; if ((s = do_spread(c))) return s; OP_EPILOGUE; }
 hcg_status hcg_op_collide_stream(hcg_ctx* c) { OP_PROLOGUE; if ((s = lat_collide_stream(c, false))) return s; OP_EPILOGUE; }
 hcg_status hcg_op_interpolate(hcg_ctx* c) {
   OP_PROLOGUE; if ((s = lat_moments(c, false, false))) return s; if ((s = ibm_interpolate(c))) return s; OP_EPILOGUE;

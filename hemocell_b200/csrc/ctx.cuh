@@ -36,6 +36,7 @@ struct CellTypeHost {
   CellTypeDev d;
   int64_t n_cells = 0, first_cell = 0, first_particle = 0;   // n_cells = slots in use (high-water mark)
   int64_t cap_cells = 0;                                      // slots reserved (multi-GPU arrivals)
+  uint16_t* perm = nullptr;                                   // node-sorted (vertex, corner) pairs per cell (spread_sorted.cu)
   int timescale = 1;
   std::vector<void*> allocs;
 };
@@ -70,7 +71,7 @@ struct hcg_ctx {
   double *g[2]; int cur;       // double-buffered pre-streamed populations
   double *F, *U, *rho;         // node force, interpolation velocity (+ density scratch)
   uint8_t* flags;
-  bool u_valid, has_velbc;
+  bool u_valid, has_velbc, has_nonfluid;
   // particles
   int64_t np, ncells, cap_p, cap_c;
   double *pos[3], *vel[3], *frc[3], *frep[3];
@@ -88,6 +89,7 @@ struct hcg_ctx {
   int *bin_count, *bin_start, *bin_items; int64_t* wall_nodes; int64_t n_wall; bool wall_built;
   void* scan_tmp; size_t scan_tmp_bytes;
   int64_t iter;
+  int spread_mode; bool perm_valid; int perm_every;   // 1 = node-sorted pairs + warp reduction, 0 = plain atomics
   // execution
   cudaStream_t stream, stream_halo;
   cudaEvent_t ev_a, ev_b;
@@ -152,6 +154,10 @@ hcg_status ibm_interpolate_advance(hcg_ctx* c);
 hcg_status mech_apply(hcg_ctx* c, int ctype, bool components);
 hcg_status mech_bbox(hcg_ctx* c, double* out_dev);
 hcg_status mech_volume_area(hcg_ctx* c, double* vol_dev, double* area_dev);
+// spread_sorted.cu
+bool spread_sorted_supported(const CellTypeHost& th);
+hcg_status spread_sorted_rebuild(hcg_ctx* c);
+hcg_status spread_sorted(hcg_ctx* c);
 // multi.cu
 hcg_status multi_velocity_sync(hcg_ctx* c);
 hcg_status multi_rebalance(hcg_ctx* c, bool initial);

@@ -1,0 +1,262 @@
+// K2 (fast path): IBM force spreading with per-cell node-sorted (vertex, corner) pairs and a
+// warp-level segmented reduction in front of the fp64 global RED.
+//
+// The plain kernel (k_spread, ibm.cu) issues 8 nodes x 3 components = 24 fp64 atomics per LSP and is
+// bound by the L2 atomic rate (~165 G RED/s measured on B200).  Membrane vertices sit ~1 lu apart, so
+// within one cell every lattice node is hit by ~3-4 (vertex, corner) pairs.  Here one CTA handles one
+// cell: the 8*V pairs are visited in an order sorted by target node (the permutation is rebuilt every
+// few steps by k_pair_sort and only needs to be *a* permutation for correctness - a stale order just
+// merges less), runs of equal node are summed with shuffles, and only the run tails touch global
+// memory.  Same arithmetic per pair as HemoCellParticleField::spreadParticleForce
+// (reference core/hemoCellParticleField.cpp:841-863): force cap, phi2 weights in the reference's
+// accumulation order for the normalisation, (frep + f) * w.
+#include "ctx.cuh"
+#include <cub/block/block_radix_sort.cuh>
+#include <climits>
+
+namespace {
+
+struct SpArgs {
+  int nx, ny, nz, px, py, pz;
+  int nxl, x0, nranks;
+  int64_t P;
+  double f_limit;
+  int V;
+  int64_t first_cell, first_particle;
+};
+
+__device__ __forceinline__ bool sp_local_x(int gx, const SpArgs& a, int& lx, bool& outside) {
+  outside = false;
+  if (gx < 0 || gx >= a.nx) {
+    if (!a.px) { outside = true; return false; }
+    gx %= a.nx; if (gx < 0) gx += a.nx;
+  }
+  int rel = gx - a.x0; if (rel < 0) rel += a.nx;
+  if (rel < a.nxl) { lx = rel + 1; return true; }
+  if (a.nranks > 1) {
+    if (rel == a.nx - 1) { lx = 0; return true; }
+    if (rel == a.nxl) { lx = a.nxl + 1; return true; }
+  }
+  return false;
+}
+__device__ __forceinline__ bool sp_wrap(int& v, int n, int periodic) {
+  if (v >= 0 && v < n) return true;
+  if (!periodic) return false;
+  v %= n; if (v < 0) v += n;
+  return true;
+}
+__device__ __forceinline__ double sp_phi2(double x) { x = 1.0 - fabs(x); return x > 0.0 ? x : 0.0; }
+
+// node (local index incl. ghosts) and raw weight of one corner; false if the corner carries nothing
+__device__ __forceinline__ bool corner_node(const SpArgs& a, const uint8_t* __restrict__ flags, double px, double py,
+                                            double pz, int corner, int& node, double& weight, bool& unaddressable) {
+  unaddressable = false;
+  const int dx = corner >> 2, dy = (corner >> 1) & 1, dz = corner & 1;
+  const int bx = (int)floor(px) + dx, by = (int)floor(py) + dy, bz = (int)floor(pz) + dz;
+  const double wx = sp_phi2(px - (double)bx), wy = sp_phi2(py - (double)by), wz = sp_phi2(pz - (double)bz);
+  weight = wx*wy*wz;
+  if (wx == 0.0) return false;
+  int lx; bool out;
+  if (!sp_local_x(bx, a, lx, out)) { if (!out) unaddressable = true; return false; }
+  int y = by, z = bz;
+  if (wy == 0.0 || !sp_wrap(y, a.ny, a.py)) return false;
+  if (wz == 0.0 || !sp_wrap(z, a.nz, a.pz)) return false;
+  if (weight == 0.0) return false;
+  node = z + a.nz*(y + a.ny*lx);
+  return flags[node] == HCG_FLUID;
+}
+
+// ---------------------------------------------------------------- permutation rebuild
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+k_pair_sort(SpArgs a, const uint8_t* __restrict__ alive, const double* __restrict__ x, const double* __restrict__ y,
+            const double* __restrict__ z, uint16_t* __restrict__ perm) {
+  typedef cub::BlockRadixSort<uint32_t, THREADS, ITEMS, uint16_t> Sort;
+  __shared__ typename Sort::TempStorage tmp;
+  __shared__ int s_min[3];
+  const int64_t cell = a.first_cell + blockIdx.x;
+  if (!alive[cell]) return;
+  const int64_t base = a.first_particle + (int64_t)blockIdx.x*a.V;
+  const int npair = 8*a.V;
+  if (threadIdx.x < 3) s_min[threadIdx.x] = INT_MAX;
+  __syncthreads();
+  int mn[3] = {INT_MAX, INT_MAX, INT_MAX};
+  for (int v = threadIdx.x; v < a.V; v += THREADS) {
+    mn[0] = min(mn[0], (int)floor(x[base+v])); mn[1] = min(mn[1], (int)floor(y[base+v])); mn[2] = min(mn[2], (int)floor(z[base+v]));
+  }
+  for (int d = 0; d < 3; d++) atomicMin(&s_min[d], mn[d]);
+  __syncthreads();
+  uint32_t keys[ITEMS]; uint16_t vals[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    const int e = threadIdx.x*ITEMS + i;
+    if (e < npair) {
+      const int v = e >> 3, c = e & 7;
+      int rx = (int)floor(x[base+v]) + (c >> 2) - s_min[0];
+      int ry = (int)floor(y[base+v]) + ((c >> 1) & 1) - s_min[1];
+      int rz = (int)floor(z[base+v]) + (c & 1) - s_min[2];
+      rx = min(rx, 63); ry = min(ry, 63); rz = min(rz, 63);
+      keys[i] = ((uint32_t)rx << 12) | ((uint32_t)ry << 6) | (uint32_t)rz;
+      vals[i] = (uint16_t)e;
+    } else { keys[i] = 0xFFFFFFFFu; vals[i] = 0xFFFF; }
+  }
+  Sort(tmp).Sort(keys, vals, 0, 19);
+  uint16_t* out = perm + (int64_t)blockIdx.x*npair;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    const int e = threadIdx.x*ITEMS + i;
+    if (e < npair) out[e] = vals[i];          // padding keys sort to the end
+  }
+}
+
+__global__ void k_perm_identity(uint16_t* perm, int npair, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < total) perm[i] = (uint16_t)(i % npair);
+}
+
+// ---------------------------------------------------------------- spread
+// One CTA per cell.  Phase 1 (thread = vertex): force cap, the 8 kernel nodes and their NORMALISED
+// weights -> shared memory (key = -1 for corners outside the kernel or on a ghost plane).
+// Phase 2 (thread = chunk of 8 consecutive node-sorted pairs): walk the chunk sequentially, merge
+// runs of equal node in registers, one fp64 RED triple per run.
+template <int THREADS, bool CHECK_FLAGS>
+__global__ void __launch_bounds__(THREADS)
+k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ alive,
+                const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                double* fx, double* fy, double* fz,
+                const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                const uint16_t* __restrict__ perm, double* __restrict__ F) {
+  extern __shared__ double sm[];
+  const int V = a.V;
+  const int64_t cell = a.first_cell + blockIdx.x;
+  if (!alive[cell]) return;
+  const int64_t base = a.first_particle + (int64_t)blockIdx.x*V;
+  double* W = sm;                      // [8][V] normalised weights
+  double* t0 = W + 8*V; double* t1 = t0 + V; double* t2 = t1 + V;
+  int* K = reinterpret_cast<int*>(t2 + V);   // [8][V] node index, -1 = nothing to add
+
+  for (int v = threadIdx.x; v < V; v += THREADS) {
+    const int64_t p = base + v;
+    const double px = x[p], py = y[p], pz = z[p];
+    double f0 = fx[p], f1 = fy[p], f2 = fz[p];
+    const double mag = sqrt(f0*f0 + f1*f1 + f2*f2);
+    if (mag > a.f_limit) {                      // permanent cap (hemoCellParticleField.cpp:848-852)
+      const double s = a.f_limit/mag;
+      f0 *= s; f1 *= s; f2 *= s;
+      fx[p] = f0; fy[p] = f1; fz[p] = f2;
+    }
+    bool skip = false;
+    const int bx = (int)floor(px), by = (int)floor(py), bz = (int)floor(pz);
+    double ax[2], ay[2], az[2]; int jx[2], jy[2], jz[2]; bool realx[2];
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+      ax[d] = sp_phi2(px - (double)(bx + d)); jx[d] = 0; realx[d] = false;
+      if (ax[d] != 0.0) {
+        int lx; bool out;
+        if (sp_local_x(bx + d, a, lx, out)) { jx[d] = lx*a.ny*a.nz; realx[d] = lx >= 1 && lx <= a.nxl; }
+        else { ax[d] = 0.0; if (!out) skip = true; }
+      }
+      ay[d] = sp_phi2(py - (double)(by + d)); int yy = by + d;
+      if (ay[d] != 0.0 && !sp_wrap(yy, a.ny, a.py)) ay[d] = 0.0;
+      jy[d] = yy*a.nz;
+      az[d] = sp_phi2(pz - (double)(bz + d)); int zz = bz + d;
+      if (az[d] != 0.0 && !sp_wrap(zz, a.nz, a.pz)) az[d] = 0.0;
+      jz[d] = zz;
+    }
+    double w[8]; int key[8];
+    double total = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {               // corner order == the reference's x-outer / z-inner order
+      const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
+      w[c] = ax[dx]*ay[dy]*az[dz];
+      const int node = jx[dx] + jy[dy] + jz[dz];
+      key[c] = -1;
+      if (w[c] == 0.0) continue;
+      if (CHECK_FLAGS && flags[node] != HCG_FLUID) { w[c] = 0.0; continue; }
+      total += w[c];
+      if (realx[dx]) key[c] = node;             // ghost planes count in the normalisation only
+    }
+    const double coeff = 1.0/total;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      W[c*V + v] = w[c]*coeff;
+      K[c*V + v] = skip ? -1 : key[c];           // multi-GPU: a candidate node is not addressable here
+    }
+    t0[v] = rx[p] + f0; t1[v] = ry[p] + f1; t2[v] = rz[p] + f2;
+  }
+  __syncthreads();
+
+  const uint4* pp = reinterpret_cast<const uint4*>(perm + (int64_t)blockIdx.x*8*V);
+  for (int j = threadIdx.x; j < V; j += THREADS) {
+    const uint4 q = __ldg(pp + j);              // 8 consecutive sorted pairs
+    const unsigned e8[4] = {q.x, q.y, q.z, q.w};
+    int cur = -1; double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const unsigned e = (e8[k >> 1] >> ((k & 1)*16)) & 0xFFFFu;
+      const int v = e >> 3, c = e & 7;
+      const int key = K[c*V + v];
+      if (key < 0) continue;
+      const double w = W[c*V + v];
+      const double v0 = t0[v]*w, v1 = t1[v]*w, v2 = t2[v]*w;
+      if (key != cur) {
+        if (cur >= 0) { double* Fn = F + 4*(int64_t)cur; atomicAdd(Fn, a0); atomicAdd(Fn + 1, a1); atomicAdd(Fn + 2, a2); }
+        cur = key; a0 = v0; a1 = v1; a2 = v2;
+      } else { a0 += v0; a1 += v1; a2 += v2; }
+    }
+    if (cur >= 0) { double* Fn = F + 4*(int64_t)cur; atomicAdd(Fn, a0); atomicAdd(Fn + 1, a1); atomicAdd(Fn + 2, a2); }
+  }
+}
+
+SpArgs make_args(const hcg_ctx* c, const CellTypeHost& th) {
+  SpArgs a;
+  a.nx = c->dom.nx; a.ny = c->dom.ny; a.nz = c->dom.nz;
+  a.px = c->dom.periodic[0]; a.py = c->dom.periodic[1]; a.pz = c->dom.periodic[2];
+  a.nxl = c->nxl; a.x0 = c->x0; a.nranks = c->dom.n_ranks;
+  a.P = c->P; a.f_limit = c->f_limit; a.V = th.d.V;
+  a.first_cell = th.first_cell; a.first_particle = th.first_particle;
+  return a;
+}
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1)/t); }
+
+}  // namespace
+
+// supported when 8*V pairs fit the compiled sort shapes (RBC 642 -> 256 x 21; PLT 66 -> 64 x 9)
+bool spread_sorted_supported(const CellTypeHost& th) { return 8*th.d.V <= 256*21; }
+
+hcg_status spread_sorted_rebuild(hcg_ctx* c) {
+  for (auto& th : c->types) {
+    if (th.n_cells == 0 || !spread_sorted_supported(th)) continue;
+    const int npair = 8*th.d.V;
+    if (!th.perm) {
+      const int64_t total = (int64_t)th.cap_cells*npair;
+      CUDA_TRY(c, cudaMalloc(&th.perm, sizeof(uint16_t)*total));
+      k_perm_identity<<<nblk(total, 256), 256, 0, c->stream>>>(th.perm, npair, total);
+      KERNEL_CHECK(c);
+    }
+    SpArgs a = make_args(c, th);
+    if (npair <= 64*9) k_pair_sort<64, 9><<<(unsigned)th.n_cells, 64, 0, c->stream>>>(a, c->cell_alive, c->pos[0], c->pos[1], c->pos[2], th.perm);
+    else k_pair_sort<256, 21><<<(unsigned)th.n_cells, 256, 0, c->stream>>>(a, c->cell_alive, c->pos[0], c->pos[1], c->pos[2], th.perm);
+    KERNEL_CHECK(c);
+  }
+  return HCG_OK;
+}
+
+hcg_status spread_sorted(hcg_ctx* c) {
+  for (auto& th : c->types) {
+    if (th.n_cells == 0) continue;
+    SpArgs a = make_args(c, th);
+    const int V = th.d.V;
+    const size_t smem = sizeof(double)*11*V + sizeof(int)*8*V + 16;
+    const bool chk = c->has_nonfluid;
+#define SP_LAUNCH(T, C) do { \
+      CUDA_TRY(c, cudaFuncSetAttribute(k_spread_sorted<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_spread_sorted<T, C><<<(unsigned)th.n_cells, T, smem, c->stream>>>(a, c->flags, c->cell_alive, c->pos[0], c->pos[1], c->pos[2], \
+          c->frc[0], c->frc[1], c->frc[2], c->frep[0], c->frep[1], c->frep[2], th.perm, c->F); } while (0)
+    if (V >= 256) { if (chk) SP_LAUNCH(256, true); else SP_LAUNCH(256, false); }
+    else { if (chk) SP_LAUNCH(64, true); else SP_LAUNCH(64, false); }
+#undef SP_LAUNCH
+    KERNEL_CHECK(c);
+  }
+  return HCG_OK;
+}

@@ -142,6 +142,9 @@ hcg_status hcg_set_material_timescale(hcg_ctx*, int32_t ctype, int32_t every);
 hcg_status hcg_set_repulsion(hcg_ctx*, int32_t enabled, double k, double cutoff_lu);
 /* HemoCell::enableBoundaryParticles (core/hemoCell.cpp:428-436) */
 hcg_status hcg_set_wall_repulsion(hcg_ctx*, int32_t enabled, double k, double cutoff_lu);
+/* spreading strategy: 1 (default) = per-cell node-sorted (vertex, corner) pairs + warp-level reduction in
+ * front of the fp64 atomics, permutation rebuilt every `resort_every` steps; 0 = one atomic per pair */
+hcg_status hcg_set_spread_mode(hcg_ctx*, int32_t mode, int32_t resort_every);
 /* multi-GPU particle exchange (replaces particleEnvelope of config.xml and the comm. structure of
  * HemoCellFields::calculateCommunicationStructure, core/hemoCellFields.cpp:363-372): a rank holds
  * every cell within `margin_lu` of its slab, membership is re-evaluated every `sync_every` steps,

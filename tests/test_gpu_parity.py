@@ -91,7 +91,8 @@ def _one_rbc_setup(periodic=(1, 1, 0), n_cells=2, seed=3):
     return par, dom, fl, bc, ct, cells
 
 
-def test_spread_interpolate_advance_parity():
+@pytest.mark.parametrize("spread_mode", [1, 0])     # 1 = node-sorted pairs + warp reduction, 0 = plain atomics
+def test_spread_interpolate_advance_parity(spread_mode):
     H = _lib()
     par, dom, fl, bc, ct, cells = _one_rbc_setup()
     N = dom.nx * dom.ny * dom.nz
@@ -102,6 +103,7 @@ def test_spread_interpolate_advance_parity():
     pop = U.mask_inflow(dom, U.smooth_state(dom, 21))
     ctx = U.gpu_context(dom, fl, bc)
     ctx.set_force_limit(par.f_limit)
+    ctx.set_spread_mode(spread_mode, 20)
     t = U.gpu_add_type(ctx, ct)
     ctx.add_cells(t, cells, np.arange(cells.shape[0]))
     ctx.cells_upload(H.P_FORCE, pforce); ctx.cells_upload(H.P_FREP, frep)
