@@ -133,13 +133,15 @@ hcg_status step(hcg_ctx* c) {
   if (have_p && c->wall_on && c->iter % c->ts_wall == 0) { OpTimer t(c, "applyBoundaryRepulsionForce"); if ((s = rep_wall_apply(c))) return s; }
   if (have_p) { OpTimer t(c, "spreadParticleForce"); if ((s = do_spread(c))) return s; }
   const bool interp = have_p && (c->iter % c->ts_vel == 0);
-  { OpTimer t(c, "collideAndStream"); if ((s = lat_collide_stream(c, !interp))) return s; }
+  bool fused = false;
+  if (interp) { OpTimer t(c, "collideAndStream+moments"); if ((s = lat_collide_moments_overlapped(c, &fused))) return s; }
+  if (!fused) { OpTimer t(c, "collideAndStream"); if ((s = lat_collide_stream(c, !interp))) return s; }
   if (interp) {
     // interpolation and advance share one pass over the particles (advance uses the velocity just interpolated)
     if (c->dom.n_ranks == 1) {
-      OpTimer t(c, "interpolateFluidVelocity"); if ((s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate_advance(c))) return s;
+      OpTimer t(c, "interpolateFluidVelocity"); if (!fused && (s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate_advance(c))) return s;
     } else {
-      { OpTimer t(c, "interpolateFluidVelocity"); if ((s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate(c))) return s; }
+      { OpTimer t(c, "interpolateFluidVelocity"); if (!fused && (s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate(c))) return s; }
       { OpTimer t(c, "syncEnvelopes"); if ((s = multi_velocity_sync(c))) return s; }
       { OpTimer t(c, "advanceParticles"); if ((s = ibm_advance(c))) return s; }
     }
@@ -222,6 +224,7 @@ void hcg_destroy(hcg_ctx* c) {
   if (c->nccl) ncclCommDestroy((ncclComm_t)c->nccl);
   cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); cudaFree(c->flags); cudaFree(c->d_bc);
   if (c->rho) cudaFree(c->rho);
+  if (c->fused_done) cudaFree(c->fused_done);
   for (int k = 0; k < 3; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->frc[k]); cudaFree(c->frep[k]); }
   for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) if (c->comp[k][d]) cudaFree(c->comp[k][d]);
   cudaFree(c->p_cell); cudaFree(c->cell_alive); cudaFree(c->cell_type); cudaFree(c->cell_base);

@@ -99,6 +99,9 @@ struct hcg_ctx {
   bool timers_on; std::vector<TimerSlot> timers; std::map<std::string,int> timer_idx;
   std::vector<cudaEvent_t> ev_pool; std::vector<TimerPending> ev_pending;
   int64_t launches;
+  int sm_count = 0, smem_optin = 0;
+  int* fused_done = nullptr;   // per-plane completion counters (collision kernel -> overlapped moments kernel)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   double* staging; size_t staging_bytes;   // device scratch for AoS<->SoA transposes
 };
@@ -137,7 +140,9 @@ inline void resolve_timers(hcg_ctx* c) {
 
 // lattice.cu
 hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force);
+hcg_status lat_collide_rows(hcg_ctx* c, bool reset_force, int row0, int row1, cudaStream_t st, int* done);
 hcg_status lat_moments(hcg_ctx* c, bool reset_force, bool want_rho);
+hcg_status lat_collide_moments_overlapped(hcg_ctx* c, bool* done_out);
 hcg_status lat_reset_force(hcg_ctx* c);
 hcg_status lat_init_equilibrium(hcg_ctx* c, double rho, const double u[3]);
 hcg_status lat_halo_exchange_pop(hcg_ctx* c);

@@ -6,6 +6,7 @@
 #include <nccl.h>
 #include <cfloat>
 #include <cstdlib>
+#include <cstdio>
 
 namespace {
 
@@ -134,9 +135,10 @@ __device__ __forceinline__ void regularized_complete(double f[19], int o, const 
 template <bool RESET, bool VELBC, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, double* __restrict__ F,
-                 const uint8_t* __restrict__ flags, LatArgs a) {
-  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
-  if (i >= (int64_t)a.nxl*a.P) return;
+                 const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count) {
+  const int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int64_t i = first + k;
   const int64_t n = i + a.P;
   const int rem = (int)(i % a.P);
   const int y = rem / a.nz, z = rem - y*a.nz;
@@ -163,9 +165,10 @@ k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, doub
 template <bool RESET>
 __global__ void __launch_bounds__(256)
 k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restrict__ U,
-          const uint8_t* __restrict__ flags, LatArgs a) {
-  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
-  if (i >= (int64_t)a.nxl*a.P) return;
+          const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count) {
+  const int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int64_t i = first + k;
   const int64_t n = i + a.P;
   const int rem = (int)(i % a.P);
   const int y = rem / a.nz, z = rem - y*a.nz;
@@ -184,6 +187,326 @@ k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restri
   double2* Uw = reinterpret_cast<double2*>(U + 4*n);
   Uw[0] = make_double2(u0, u1); Uw[1] = make_double2(u2, rho);      // slot 3 carries the density
   if (RESET) { double2* Fw = reinterpret_cast<double2*>(F + 4*n); Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-pipelined lattice kernels (EXPERIMENTAL, opt-in with HCG_K1_ROWS=1; nz even, a few rows must fit shared memory).
+// Measured on B200 (256^3): 1.05 ms vs 0.945 ms for the plain one-thread-per-node kernel, so the plain kernel is the default.
+//
+// One task = one z-row (fixed lx, y; nz nodes).  Every source row g_q(lx - c_x, y - c_y, :) is nz
+// contiguous doubles, so a task is 19 bulk-async copies (cp.async.bulk, the 1-D TMA path) plus the
+// node-force row, landing in a ring of shared-memory stages and signalled through one mbarrier per
+// stage.  A persistent CTA walks a contiguous range of rows: thread 0 keeps `stages - 1` rows in
+// flight, all threads read the populations of "their" node out of shared memory (the z shift of the
+// pull becomes a shared-memory index, wrap included), collide in registers and store coalesced.
+// The loads of a row are in flight while the previous rows are being collided, independent of the
+// register-limited occupancy that bounds the plain one-thread-per-node kernel.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  long long t_start = 0;
+  for (unsigned spin = 0; !ok; spin++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (!ok && (spin & 255u) == 255u) {       // a byte-count mismatch must not hang the device: trap after ~2 s
+      const long long now = clock64();
+      if (t_start == 0) t_start = now; else if (now - t_start > 4000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Guo-forced BGK collision, opposite pairs sharing their symmetric part (same algebra as guo_collide,
+// re-associated: differences are a few ulp of the intermediate terms).
+__device__ __forceinline__ void guo_collide_pairs(double f[19], const double F[3], double omega) {
+  constexpr int CX[19] = {0,-1,0,0,-1,-1,-1,-1,0,0, 1,0,0,1,1,1,1,0,0};
+  constexpr int CY[19] = {0,0,-1,0,-1,1,0,0,-1,-1, 0,1,0,1,-1,0,0,1,1};
+  constexpr int CZ[19] = {0,0,0,-1,0,0,-1,1,-1,1, 0,0,1,0,0,1,-1,1,-1};
+  constexpr double T0 = 1.0/3.0, T1 = 1.0/18.0, T2 = 1.0/36.0;
+  double rhoBar, j[3];
+  moments19(f, rhoBar, j);
+  const double rho = 1.0 + rhoBar, invRho = 1.0/rho;
+  const double ux = j[0]*invRho + 0.5*F[0], uy = j[1]*invRho + 0.5*F[1], uz = j[2]*invRho + 0.5*F[2];
+  const double om1 = 1.0 - omega, fpre = 1.0 - 0.5*omega;
+  const double uSqr = ux*ux + uy*uy + uz*uz;
+  const double uF = ux*F[0] + uy*F[1] + uz*F[2];
+  // feq = t (rhoBar + 3 rho cu + 4.5 rho cu^2 - 1.5 rho u^2);  Guo = t fpre (3 cF - 3 uF + 9 cu cF)
+  const double base = omega*(rhoBar - 1.5*rho*uSqr) - 3.0*fpre*uF;     // symmetric, c-independent
+  const double a2 = 4.5*omega*rho, a1 = 3.0*omega*rho, g2 = 9.0*fpre, g1 = 3.0*fpre;
+  f[0] = om1*f[0] + T0*base;
+#pragma unroll
+  for (int q = 1; q <= 9; q++) {
+    const double t = (q <= 3) ? T1 : T2;
+    const double cu = CX[q]*ux + CY[q]*uy + CZ[q]*uz;
+    const double cF = CX[q]*F[0] + CY[q]*F[1] + CZ[q]*F[2];
+    const double sym = t*(base + cu*(a2*cu + g2*cF));
+    const double asym = t*(a1*cu + g1*cF);
+    f[q] = om1*f[q] + (sym + asym);
+    f[q+9] = om1*f[q+9] + (sym - asym);
+  }
+}
+
+// Warp-specialised: warp 0 is the producer (its lanes issue the 19 population rows + the force row of
+// every row of a stage), the other warps are consumers.  full[s]: bytes landed; empty[s]: every consumer
+// warp has pulled its nodes of stage s into registers (arrives BEFORE colliding, so the refill overlaps
+// the arithmetic).  No CTA-wide barrier inside the loop.
+template <int NT /*32 producer + consumer threads*/, int MODE /*0 = collide + stream, 1 = moments*/, bool RESET, bool VELBC>
+__global__ void __launch_bounds__(NT)
+k_rows(const double* __restrict__ gin, double* __restrict__ gout, double* __restrict__ F, double* __restrict__ U,
+       const uint8_t* __restrict__ flags, LatArgs a, int row0, int row1, int stages, int R, int interleave, int* done) {
+  constexpr int CY[19] = {0,0,-1,0,-1,1,0,0,-1,-1, 0,1,0,1,-1,0,0,1,1};
+  constexpr int CZ[19] = {0,0,0,-1,0,0,-1,1,-1,1, 0,0,1,0,0,1,-1,1,-1};
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int nz = a.nz, ny = a.ny;
+  const bool fsm = false;                                     // (flag row in the stage measured slower than a direct load: off)
+  const int row_doubles = 23*nz + (fsm ? nz/8 : 0);           // 19 population rows + the [nz][4] force row (+ nz flag bytes)
+  const size_t stage_doubles = (size_t)R*row_doubles;
+  double* sbase = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sbase + (size_t)stages*stage_doubles);
+  uint64_t* empty = full + stages;
+  const int ncons = (int)blockDim.x - 32, nwarp_cons = ncons >> 5;
+
+  // contiguous range of row groups (R rows each) for this CTA
+  const int ngroups = (row1 - row0 + R - 1)/R;
+  // interleave: CTA b takes groups b, b + G, b + 2G, ... (all SMs stream through one window of the
+  // lattice: DRAM-page / TLB locality); else one contiguous range per CTA
+  const int per = (ngroups + (int)gridDim.x - 1)/(int)gridDim.x;
+  const int g0 = (interleave & 1) ? (int)blockIdx.x : (int)blockIdx.x*per;
+  const int gstep = (interleave & 1) ? (int)gridDim.x : 1;
+  const int ng = (interleave & 1) ? (ngroups - g0 + gstep - 1)/gstep : min(g0 + per, ngroups) - g0;
+  if (ng <= 0) return;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; s++) { mbar_init(full + s, 1); mbar_init(empty + s, (uint32_t)nwarp_cons); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (threadIdx.x < 32) {
+    // ------------------------------------------------------------------ producer warp
+    const int lane = threadIdx.x;                             // lane q < 19: population q; lane 19: node force
+    int cx = 0, cy = 0;
+    if (lane < 19) { cx = d_cx[lane]; cy = d_cy[lane]; }
+    for (int it = 0; it < ng; it++) {
+      const int s = it % stages;
+      if (it >= stages) mbar_wait(empty + s, (uint32_t)(((it / stages) - 1) & 1));
+      const int r_first = row0 + (g0 + it*gstep)*R;
+      const int nr = min(R, row1 - r_first);
+      double* st = sbase + (size_t)s*stage_doubles;
+      if (lane == 0) {
+        int bytes = 0;
+        for (int r = 0; r < nr; r++) {
+          const int task = r_first + r, y = task % ny;
+          int nvalid = 19;
+          if (!a.py) { if (y == 0) nvalid -= 5; if (y == ny - 1) nvalid -= 5; }   // 5 populations per c_y sign
+          bytes += nvalid*nz*8 + nz*32 + (fsm ? nz : 0);
+        }
+        mbar_expect_tx(full + s, (uint32_t)bytes);
+      }
+      __syncwarp();
+      if (lane < 20 || (lane == 20 && fsm)) {
+        for (int r = 0; r < nr; r++) {
+          const int task = r_first + r;
+          const int lx = task / ny + 1, y = task - (lx - 1)*ny;
+          double* dst = st + (size_t)r*row_doubles + (size_t)lane*nz;
+          if (lane < 19) {
+            int sy = y - cy; bool ok = true;
+            if (sy < 0) { ok = a.py; sy += ny; } else if (sy >= ny) { ok = a.py; sy -= ny; }
+            if (ok) bulk_g2s(dst, gin + (int64_t)lane*a.S + ((int64_t)(lx - cx)*ny + sy)*nz, (uint32_t)(nz*8), full + s);
+          } else if (lane == 19) {
+            bulk_g2s(dst, F + 4*((int64_t)lx*ny + y)*nz, (uint32_t)(nz*32), full + s);
+          } else {
+            bulk_g2s(st + (size_t)r*row_doubles + (size_t)23*nz, flags + ((int64_t)lx*ny + y)*nz, (uint32_t)nz, full + s);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer warps
+  const int lane = (int)threadIdx.x & 31;
+  const int wbase = (int)threadIdx.x - 32 - lane;             // warp-uniform index of the warp's first node
+  // `done` (optional): per-plane count of finished (row group, consumer warp) pairs, read by the moments
+  // kernel running concurrently two planes behind (lat_collide_moments_overlapped).  A group is published
+  // one task late, when its stores have long drained, so the fence costs next to nothing.
+  int pending = -1;
+  for (int it = 0; it < ng; it++) {
+    const int s = it % stages;
+    const int r_first = row0 + (g0 + it*gstep)*R;
+    const int nr = min(R, row1 - r_first);
+    const int nnode = nr*nz;
+    const double* st = sbase + (size_t)s*stage_doubles;
+    // flags of this thread's first node: issued before the wait so that the latency overlaps it
+    uint8_t fl0 = 0;
+    if (!fsm && wbase + lane < nnode) {
+      const int k = wbase + lane, r = k / nz, z = k - r*nz, task = r_first + r;
+      const int lx = task / ny + 1, y = task - (lx - 1)*ny;
+      fl0 = flags[((int64_t)lx*ny + y)*nz + z];
+    }
+    mbar_wait(full + s, (uint32_t)((it / stages) & 1));
+    if (wbase >= nnode) {                                     // nothing to do in this stage: still owes its arrival
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(empty + s)) : "memory");
+      continue;
+    }
+    for (int kb = wbase; kb < nnode; kb += ncons) {           // kb is warp-uniform
+      const int k = kb + lane;
+      const bool act = k < nnode;
+      double f[19]; double2 fa = make_double2(0.0, 0.0); double fb = 0.0; int64_t n = 0; uint8_t fls = 0;
+      if (act) {
+        const int r = k / nz, z = k - r*nz, task = r_first + r;
+        const int lx = task / ny + 1, y = task - (lx - 1)*ny;
+        n = ((int64_t)lx*ny + y)*nz + z;
+        const bool vyp = a.py || (y + 1 < ny), vym = a.py || (y > 0);
+        const double* sr = st + (size_t)r*row_doubles;
+        int zm = z - 1, zp = z + 1; bool vzm = true, vzp = true;   // source z for c_z = +1 / -1
+        if (zm < 0) { zm = nz - 1; vzm = a.pz; }
+        if (zp >= nz) { zp = 0; vzp = a.pz; }
+#pragma unroll
+        for (int q = 0; q < 19; q++) {
+          bool ok = true; int zz = z;
+          if (CY[q] == 1) ok = vym; else if (CY[q] == -1) ok = vyp;
+          if (CZ[q] == 1) { zz = zm; ok = ok && vzm; } else if (CZ[q] == -1) { zz = zp; ok = ok && vzp; }
+          f[q] = ok ? sr[q*nz + zz] : 0.0;
+        }
+        fa = *reinterpret_cast<const double2*>(sr + 19*nz + 4*z);
+        fb = sr[19*nz + 4*z + 2];
+        if (fsm) fls = reinterpret_cast<const uint8_t*>(sr + 23*nz)[z];
+      }
+      if (kb + ncons >= nnode) {                              // the warp has pulled its last nodes of stage s
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(empty + s)) : "memory");
+      }
+      if (MODE == 0 && kb == wbase && pending >= 0) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(done + pending, 1);
+        pending = -1;
+      }
+      if (!act) continue;
+      const uint8_t fl = fsm ? fls : ((kb == wbase) ? fl0 : flags[n]);
+      if (MODE == 0) {
+        if (fl == HCG_BOUNCEBACK) {
+#pragma unroll
+          for (int q = 1; q <= 9; q++) { const double t = f[q]; f[q] = f[q+9]; f[q+9] = t; }
+        } else {
+          const double Fn[3] = {fa.x, fa.y, fb};
+          if (VELBC && fl >= HCG_VEL_XN) { const double uw[3] = {a.bc[3*(fl-2)], a.bc[3*(fl-2)+1], a.bc[3*(fl-2)+2]}; regularized_complete(f, fl - 2, uw); }
+          guo_collide_pairs(f, Fn, a.omega);
+        }
+#pragma unroll
+        if (interleave & 2) { for (int q = 0; q < 19; q++) gout[(int64_t)q*a.S + n] = f[q]; }
+        else { for (int q = 0; q < 19; q++) __stcs(gout + (int64_t)q*a.S + n, f[q]); }
+      } else {
+        double rhoBar, j[3];
+        moments19(f, rhoBar, j);
+        double u0, u1, u2, rho = 1.0 + rhoBar;
+        if (fl == HCG_FLUID) {
+          const double invRho = 1.0/rho;
+          u0 = j[0]*invRho + 0.5*fa.x; u1 = j[1]*invRho + 0.5*fa.y; u2 = j[2]*invRho + 0.5*fb;
+        } else if (fl == HCG_BOUNCEBACK) { u0 = u1 = u2 = 0.0; rho = 1.0; }
+        else { u0 = a.bc[3*(fl-2)]; u1 = a.bc[3*(fl-2)+1]; u2 = a.bc[3*(fl-2)+2]; }
+        double2* Uw = reinterpret_cast<double2*>(U + 4*n);
+        Uw[0] = make_double2(u0, u1); Uw[1] = make_double2(u2, rho);
+      }
+      if (RESET) { double2* Fw = reinterpret_cast<double2*>(F + 4*n); Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0); }
+    }
+    if (MODE == 0 && done) pending = r_first / ny + 1;        // plane of this group (groups never straddle planes here)
+  }
+  if (MODE == 0 && pending >= 0) { __threadfence(); __syncwarp(); if (lane == 0) atomicAdd(done + pending, 1); }
+}
+
+// Moments pass that runs CONCURRENTLY with the collision kernel of the same step (second stream), a few
+// planes behind it: the populations it pulls were written moments ago and are still in the 126 MB L2,
+// so the pass costs its U/F traffic instead of a second 152 B/node sweep over HBM.  CTA j handles 256
+// consecutive nodes starting at plane `first_plane` (the ring-closing planes come last); thread 0 spins
+// on the plane counters published by k_rows until the three source planes are complete.
+__global__ void __launch_bounds__(256)
+k_moments_wait(const double* __restrict__ g, double* __restrict__ F, double* __restrict__ U,
+               const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count, int64_t rot,
+               const int* done, int expected, int wrapx) {
+  int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  const int64_t kfirst = (int64_t)blockIdx.x*blockDim.x;
+  // rotate so that the planes whose sources close the periodic ring are handled last
+  auto rotate = [&](int64_t v) { v += rot; if (v >= count) v -= count; return v; };
+  if (threadIdx.x == 0) {
+    const int64_t klast = min(kfirst + (int64_t)blockDim.x, count) - 1;
+    const int p0 = (int)((first + rotate(kfirst)) / a.P) + 1, p1 = (int)((first + rotate(klast)) / a.P) + 1;
+    long long t_start = 0;
+    for (int pp = 0; pp < 2; pp++) {
+      const int p = pp ? p1 : p0;
+      if (pp && p1 == p0) break;
+      int need[3] = {p - 1, p, p + 1};
+      if (need[0] == 0) need[0] = wrapx ? a.nxl : -1;
+      if (need[2] == a.nxl + 1) need[2] = wrapx ? 1 : -1;
+      for (int m = 0; m < 3; m++) {
+        if (need[m] < 0) continue;
+        unsigned spin = 0;
+        while (ld_acquire_gpu(done + need[m]) < expected) {
+          if ((++spin & 1023u) == 0) {
+            const long long now = clock64();
+            if (t_start == 0) t_start = now; else if (now - t_start > 4000000000LL) __trap();
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (k >= count) return;
+  const int64_t i = first + rotate(k);
+  const int64_t n = i + a.P;
+  const int rem = (int)(i % a.P);
+  const int y = rem / a.nz, z = rem - y*a.nz;
+  double f[19];
+  // the ring-closing planes read the wrapped plane directly: the ghost planes are filled only after this step
+  if (wrapx && (n < 2*a.P || n >= (int64_t)a.nxl*a.P)) {
+    constexpr int CX[19] = {0,-1,0,0,-1,-1,-1,-1,0,0, 1,0,0,1,1,1,1,0,0};
+    constexpr int CY[19] = {0,0,-1,0,-1,1,0,0,-1,-1, 0,1,0,1,-1,0,0,1,1};
+    constexpr int CZ[19] = {0,0,0,-1,0,0,-1,1,-1,1, 0,0,1,0,0,1,-1,1,-1};
+    const int lx = (int)(n / a.P);
+#pragma unroll
+    for (int q = 0; q < 19; q++) {
+      int sx = lx - CX[q], sy = y - CY[q], sz = z - CZ[q]; bool ok = true;
+      if (sx == 0) sx = a.nxl; else if (sx == a.nxl + 1) sx = 1;
+      if (sy < 0) { sy += a.ny; ok = ok && a.py; } else if (sy >= a.ny) { sy -= a.ny; ok = ok && a.py; }
+      if (sz < 0) { sz += a.nz; ok = ok && a.pz; } else if (sz >= a.nz) { sz -= a.nz; ok = ok && a.pz; }
+      f[q] = ok ? __ldcg(g + (int64_t)q*a.S + ((int64_t)sx*a.ny + sy)*a.nz + sz) : 0.0;
+    }
+  } else pull19(g, a, n, y, z, f);
+  double rhoBar, j[3];
+  moments19(f, rhoBar, j);
+  const uint8_t fl = flags[n];
+  double u0, u1, u2, rho = 1.0 + rhoBar;
+  if (fl == HCG_FLUID) {
+    const double invRho = 1.0/rho;
+    const double2 fa = *reinterpret_cast<const double2*>(F + 4*n);
+    u0 = j[0]*invRho + 0.5*fa.x; u1 = j[1]*invRho + 0.5*fa.y; u2 = j[2]*invRho + 0.5*F[4*n + 2];
+  } else if (fl == HCG_BOUNCEBACK) { u0 = u1 = u2 = 0.0; rho = 1.0; }
+  else { u0 = a.bc[3*(fl-2)]; u1 = a.bc[3*(fl-2)+1]; u2 = a.bc[3*(fl-2)+2]; }
+  double2* Uw = reinterpret_cast<double2*>(U + 4*n);
+  __stcs(Uw, make_double2(u0, u1)); __stcs(Uw + 1, make_double2(u2, rho));
+  double2* Fw = reinterpret_cast<double2*>(F + 4*n);              // force reset rides along
+  __stcs(Fw, make_double2(a.body[0], a.body[1])); __stcs(Fw + 1, make_double2(a.body[2], 0.0));
 }
 
 __global__ void k_fill4(double* F, int64_t total, double b0, double b1, double b2) {
@@ -349,38 +672,156 @@ hcg_status lat_halo_exchange_u(hcg_ctx* c) {
   return exchange(c, c->U, 4*c->P, h_qsets + 10, d_qsets + 10, 1, h_qsets + 10, d_qsets + 10, 1);
 }
 
-hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
-  LatArgs a = make_args(c);
-  const int64_t n = (int64_t)c->nxl*c->P;
-  double* gin = c->g[c->cur]; double* gout = c->g[1 - c->cur];
-  const unsigned nb = nblk(n, 256);
-  {
-  OpTimer tk(c, "kernel:k_collide_stream");
-  static int variant = -1;
-  if (variant < 0) { const char* e = getenv("HCG_K1_MINB"); variant = e ? atoi(e) : 2; }
-#define K1_LAUNCH(R, V, M) k_collide_stream<R, V, M><<<nb, 256, 0, c->stream>>>(gin, gout, c->F, c->flags, a)
-#define K1_PICK(M) do { if (c->has_velbc) { if (reset_force) K1_LAUNCH(true, true, M); else K1_LAUNCH(false, true, M); } \
-                        else { if (reset_force) K1_LAUNCH(true, false, M); else K1_LAUNCH(false, false, M); } } while (0)
-  if (variant == 4) K1_PICK(4); else if (variant == 3) K1_PICK(3); else if (variant == 2) K1_PICK(2); else K1_PICK(1);
+// row-pipelined path: eligibility and launch shape
+namespace {
+struct RowCfg { bool ok; int stages, grid, R, nt, interleave; size_t smem; };
+RowCfg row_config(hcg_ctx* c, int nrows) {
+  static int env_mode = -2, env_stages = 0, env_ctas = 0, env_nt = 0, env_il = 1;
+  if (env_mode == -2) {
+    const char* e = getenv("HCG_K1_ROWS"); env_mode = e ? atoi(e) : 0;      // opt-in: measured slower than k_collide_stream
+    e = getenv("HCG_K1_STAGES"); env_stages = e ? atoi(e) : 0;
+    e = getenv("HCG_K1_CTAS"); env_ctas = e ? atoi(e) : 0;
+    e = getenv("HCG_K1_NT"); env_nt = e ? atoi(e) : 0;
+    e = getenv("HCG_K1_INTERLEAVE"); env_il = e ? atoi(e) : 1;
+  }
+  RowCfg r; r.ok = false; r.stages = 0; r.grid = 0; r.smem = 0; r.R = 1; r.nt = 288;
+  const int nz = c->dom.nz;
+  if (env_mode <= 0 || (nz & 1) || nz < 16) return r;
+  if (c->sm_count <= 0) {
+    int dev = c->dom.device, v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); c->sm_count = v > 0 ? v : 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); c->smem_optin = v > 0 ? v : 0;
+  }
+  r.nt = (env_nt == 544) ? 544 : 288;
+  const int ncons = r.nt - 32;
+  r.R = (ncons + nz - 1)/nz;                                  // rows per stage: one node per consumer thread
+  if (r.R < 1) r.R = 1;
+  const size_t stage = (size_t)r.R*23*nz*sizeof(double);
+  int ctas = env_ctas > 0 ? env_ctas : 2;
+  int stages = env_stages > 0 ? env_stages : 2;
+  // shrink to what one SM holds (228 KB per SM, 1 KB reserved per CTA)
+  while (ctas > 1 && ctas*(stages*stage + 128 + 1024) > (size_t)228*1024) ctas--;
+  while (stages > 2 && stages*stage + 128 > (size_t)c->smem_optin) stages--;
+  if (stages*stage + 128 > (size_t)c->smem_optin) return r;
+  r.ok = true; r.stages = stages; r.smem = stages*stage + 128; r.interleave = env_il;
+  const int ngroups = (nrows + r.R - 1)/r.R;
+  r.grid = c->sm_count*ctas; if (r.grid > ngroups) r.grid = ngroups;
+  return r;
+}
+template <int MODE, bool RESET, bool VELBC>
+hcg_status launch_rows(hcg_ctx* c, const RowCfg& rc, const double* gin, double* gout, const LatArgs& a, int row0, int row1, cudaStream_t st, int* done = nullptr) {
+  if (rc.nt == 544) {
+    CUDA_TRY(c, cudaFuncSetAttribute(k_rows<544, MODE, RESET, VELBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rc.smem));
+    k_rows<544, MODE, RESET, VELBC><<<rc.grid, 544, rc.smem, st>>>(gin, gout, c->F, c->U, c->flags, a, row0, row1, rc.stages, rc.R, rc.interleave, done);
+  } else {
+    CUDA_TRY(c, cudaFuncSetAttribute(k_rows<288, MODE, RESET, VELBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rc.smem));
+    k_rows<288, MODE, RESET, VELBC><<<rc.grid, 288, rc.smem, st>>>(gin, gout, c->F, c->U, c->flags, a, row0, row1, rc.stages, rc.R, rc.interleave, done);
   }
   KERNEL_CHECK(c);
+  return HCG_OK;
+}
+}  // namespace
+
+// collide + stream of the rows [row0, row1) of the slab (row = (lx - 1)*ny + y) on stream `st`
+hcg_status lat_collide_rows(hcg_ctx* c, bool reset_force, int row0, int row1, cudaStream_t st, int* done) {
+  if (row1 <= row0) return HCG_OK;
+  LatArgs a = make_args(c);
+  double* gin = c->g[c->cur]; double* gout = c->g[1 - c->cur];
+  const RowCfg rc = row_config(c, row1 - row0);
+  if (rc.ok) {
+    if (c->has_velbc) return reset_force ? launch_rows<0, true, true>(c, rc, gin, gout, a, row0, row1, st, done)
+                                         : launch_rows<0, false, true>(c, rc, gin, gout, a, row0, row1, st, done);
+    return reset_force ? launch_rows<0, true, false>(c, rc, gin, gout, a, row0, row1, st, done)
+                       : launch_rows<0, false, false>(c, rc, gin, gout, a, row0, row1, st, done);
+  }
+  if (done) return hcg_fail(c, HCG_ERR_STATE, "plane counters need the row-pipelined kernel");
+  const int64_t first = (int64_t)row0*a.nz, n = (int64_t)(row1 - row0)*a.nz;
+  const unsigned nb = nblk(n, 256);
+#define K1_LAUNCH(R, V) k_collide_stream<R, V, 2><<<nb, 256, 0, st>>>(gin, gout, c->F, c->flags, a, first, n)
+  if (c->has_velbc) { if (reset_force) K1_LAUNCH(true, true); else K1_LAUNCH(false, true); }
+  else { if (reset_force) K1_LAUNCH(true, false); else K1_LAUNCH(false, false); }
+#undef K1_LAUNCH
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+
+hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
+  {
+    OpTimer tk(c, "kernel:k_collide_stream");
+    hcg_status s = lat_collide_rows(c, reset_force, 0, c->nxl*c->dom.ny, c->stream, nullptr); if (s) return s;
+  }
   c->cur = 1 - c->cur;
   c->u_valid = false;
   return lat_halo_exchange_pop(c);
 }
 
+// moments of the rows [row0, row1): plain one-thread-per-node kernel (read-dominated, no register
+// pressure: it out-runs the row-pipelined variant)
+static hcg_status moments_rows(hcg_ctx* c, bool reset_force, int row0, int row1) {
+  if (row1 <= row0) return HCG_OK;
+  LatArgs a = make_args(c);
+  const int64_t first = (int64_t)row0*a.nz, n = (int64_t)(row1 - row0)*a.nz;
+  const unsigned nb = nblk(n, 256);
+  if (reset_force) k_moments<true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n);
+  else k_moments<false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+
 hcg_status lat_moments(hcg_ctx* c, bool reset_force, bool want_rho) {
   (void)want_rho;   // the density always rides in slot 3 of the node velocity
-  LatArgs a = make_args(c);
-  const int64_t n = (int64_t)c->nxl*c->P;
-  const unsigned nb = nblk(n, 256);
   {
-  OpTimer tk(c, "kernel:k_moments");
-  if (reset_force) k_moments<true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a);
-  else k_moments<false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a);
+    OpTimer tk(c, "kernel:k_moments");
+    hcg_status s = moments_rows(c, reset_force, 0, c->nxl*c->dom.ny); if (s) return s;
   }
-  KERNEL_CHECK(c);
   c->u_valid = true;
+  return lat_halo_exchange_u(c);
+}
+
+// collideAndStream + the interpolation-step moments pass (with the force reset), overlapped: the collision
+// kernel (row-pipelined, publishes per-plane completion counters) on the main stream, the moments kernel on
+// the second stream trailing it through L2.  Returns *done_out = false when the shape is not eligible
+// (the caller then runs the two passes back to back).
+hcg_status lat_collide_moments_overlapped(hcg_ctx* c, bool* done_out) {
+  *done_out = false;
+  static int env_on = -1;
+  if (env_on < 0) { const char* e = getenv("HCG_OVERLAP"); env_on = e ? atoi(e) : 0; }   // opt-in (needs HCG_K1_ROWS=1): measured slower, DESIGN.md §4
+  const int ny = c->dom.ny, nxl = c->nxl;
+  RowCfg rc = row_config(c, nxl*ny);
+  if (!env_on || !rc.ok || !rc.interleave || ny % rc.R || nxl < 4) return HCG_OK;
+  const int R = c->dom.n_ranks;
+  const int wrapx = (R == 1 && c->dom.periodic[0]) ? 1 : 0;
+  if (!c->fused_done) CUDA_TRY(c, cudaMalloc(&c->fused_done, sizeof(int)*(nxl + 2)));
+  if (!c->ev_fork) { CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)); CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)); }
+  CUDA_TRY(c, cudaMemsetAsync(c->fused_done, 0, sizeof(int)*(nxl + 2), c->stream));
+  CUDA_TRY(c, cudaEventRecord(c->ev_fork, c->stream));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->stream_halo, c->ev_fork, 0));
+  hcg_status s;
+  {
+    OpTimer tk(c, "kernel:k_collide_stream");
+    if ((s = lat_collide_rows(c, false, 0, nxl*ny, c->stream, c->fused_done))) return s;
+  }
+  c->cur = 1 - c->cur;
+  {
+    // planes m_lo..m_hi; multi-GPU: the face planes need the neighbour's halo and follow after the exchange
+    const int m_lo = R > 1 ? 2 : 1, m_hi = R > 1 ? nxl - 1 : nxl;
+    LatArgs a = make_args(c);
+    const int64_t first = (int64_t)(m_lo - 1)*c->P, count = (int64_t)(m_hi - m_lo + 1)*c->P;
+    const int64_t rot = (wrapx && count > c->P) ? c->P : 0;   // start at plane 2: plane 1 (needs plane nxl) comes last
+    const int expected = (ny/rc.R)*((rc.nt - 32)/32);
+    k_moments_wait<<<nblk(count, 256), 256, 0, c->stream_halo>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, count, rot,
+                                                                 c->fused_done, expected, wrapx);
+    KERNEL_CHECK(c);
+  }
+  CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream_halo));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  if ((s = lat_halo_exchange_pop(c))) return s;
+  if (R > 1) {                                                // face planes: their ghost neighbours have just arrived
+    if ((s = moments_rows(c, true, 0, ny))) return s;
+    if ((s = moments_rows(c, true, (nxl - 1)*ny, nxl*ny))) return s;
+  }
+  c->u_valid = true;
+  *done_out = true;
   return lat_halo_exchange_u(c);
 }
 

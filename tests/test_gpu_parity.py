@@ -17,15 +17,17 @@ def _lib():
 
 
 # --------------------------------------------------------------------------- lattice
+# several shapes (the opt-in row-pipelined kernel, HCG_K1_ROWS=1, is eligible for nz = 32 / 64)
+@pytest.mark.parametrize("shape", [(24, 20, 16), (12, 14, 32), (7, 9, 64)])
 @pytest.mark.parametrize("periodic,flagkind,tau", [
     ((1, 1, 1), "bb_slab", 1.16), ((1, 1, 1), "none", 1.0), ((1, 1, 0), "couette", 1.16),
     ((0, 0, 0), "box", 0.86), ((1, 0, 0), "channel_bb", 1.82)])
-def test_collide_stream_parity(periodic, flagkind, tau):
+def test_collide_stream_parity(periodic, flagkind, tau, shape):
     H = _lib()
-    nx, ny, nz = 24, 20, 16
+    nx, ny, nz = shape
     bc = np.zeros((6, 3))
     if flagkind == "bb_slab":
-        fl = np.zeros((nx, ny, nz), dtype=np.uint8); fl[5:9, 3:11, 2:7] = 1; fl[:, 0, :] = 1
+        fl = np.zeros((nx, ny, nz), dtype=np.uint8); fl[nx//4:nx//4+3, 3:ny//2+1, 2:7] = 1; fl[:, 0, :] = 1
     elif flagkind == "none":
         fl = np.zeros((nx, ny, nz), dtype=np.uint8)
     elif flagkind == "couette":
@@ -229,12 +231,14 @@ def test_repulsion_parity():
 
 
 # --------------------------------------------------------------------------- iterate
+# nz = 32 is also eligible for the opt-in overlapped collide+moments path (HCG_K1_ROWS=1 HCG_OVERLAP=1)
+@pytest.mark.parametrize("nz", [24, 32])
 @pytest.mark.parametrize("cadence", [(1, 1), (5, 10)])
-def test_iterate_parity(cadence):
+def test_iterate_parity(cadence, nz):
     """full HemoCell::iterate() for 20 steps: shear flow, one RBC + one PLT, body force"""
     H = _lib()
     vel_ts, mat_ts = cadence
-    nx, ny, nz = 40, 32, 24
+    nx, ny = 40, 32
     par = M.Parameters(dx=0.5e-6, dt=0.5e-7)
     bc = np.zeros((6, 3)); bc[4] = (0.02, 0, 0); bc[5] = (-0.02, 0, 0)
     fl = U.couette_flags(nx, ny, nz).reshape(-1)
@@ -264,3 +268,17 @@ def test_iterate_parity(cadence):
         U.assert_close(ctx.lattice_download(H.LAT_POP), sim.pop, f"populations @ {sim.iter}", rtol=1e-10, floor=1e-12)
         U.assert_close(ctx.lattice_download(H.LAT_FORCE), sim.force, f"node force reset @ {sim.iter}", rtol=0, floor=0)
     ctx.close()
+
+
+# --------------------------------------------------------------------------- experimental lattice paths
+def test_experimental_row_pipeline_matches_default():
+    """the opt-in bulk-async row kernel + overlapped moments pass give the default path's results"""
+    import subprocess, sys, os
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fused_repro.py")
+    base = dict(os.environ)
+    r0 = subprocess.run([sys.executable, script, "24", "24", "64", "6"], env=dict(base, HCG_FUSED="0", HCG_K1_ROWS="0", HCG_OVERLAP="0"),
+                        capture_output=True, text=True, timeout=300)
+    assert r0.returncode == 0, r0.stdout + r0.stderr
+    r1 = subprocess.run([sys.executable, script, "24", "24", "64", "6"], env=dict(base, HCG_FUSED="1", HCG_K1_ROWS="1", HCG_OVERLAP="1"),
+                        capture_output=True, text=True, timeout=300)
+    assert r1.returncode == 0 and "fused == separate" in r1.stdout, r1.stdout + r1.stderr
