@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 
 hcg_status lat_pad3(hcg_ctx* c, const double* src_dev, double* dst);
 hcg_status lat_unpad(hcg_ctx* c, const double* src, double* dst_dev, int first, int ncomp);
@@ -103,6 +104,22 @@ hcg_status exchange_flags(hcg_ctx* c) {
   return HCG_OK;
 }
 
+// has_nonfluid = the IBM kernels must look at node flags: real nodes or ghost planes (neighbour's face /
+// outside of a non-periodic domain) hold something that is not plain fluid
+hcg_status refresh_nonfluid(hcg_ctx* c) {
+  std::vector<uint8_t> gh(2*(size_t)c->P);
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  CUDA_TRY(c, cudaMemcpy(gh.data(), c->flags, c->P, cudaMemcpyDeviceToHost));
+  CUDA_TRY(c, cudaMemcpy(gh.data() + c->P, c->flags + (int64_t)(c->nxl+1)*c->P, c->P, cudaMemcpyDeviceToHost));
+  bool nf = c->real_nonfluid;
+  // ghost planes beyond a non-periodic end of the domain are never addressed by the IBM kernels
+  const bool useL = c->dom.periodic[0] || c->dom.rank > 0, useR = c->dom.periodic[0] || c->dom.rank < c->dom.n_ranks - 1;
+  for (int64_t i = 0; i < c->P && !nf && useL; i++) nf = gh[i] != HCG_FLUID;
+  for (int64_t i = 0; i < c->P && !nf && useR; i++) nf = gh[c->P + i] != HCG_FLUID;
+  c->has_nonfluid = nf;
+  return HCG_OK;
+}
+
 hcg_status do_mechanics(hcg_ctx* c, bool forced, bool components) {
   OpTimer t(c, "applyConstitutiveModel");
   for (size_t k = 0; k < c->types.size(); k++) {
@@ -128,7 +145,8 @@ hcg_status do_spread(hcg_ctx* c) {
 // one HemoCell::iterate() (core/hemoCell.cpp:299-376)
 hcg_status step(hcg_ctx* c) {
   hcg_status s;
-  const bool have_p = c->np > 0;
+  // multi-GPU: every rank runs the same operator sequence (the exchanges are collective), cells or not
+  const bool have_p = c->np > 0 || (c->dom.n_ranks > 1 && !c->types.empty());
   if (have_p && c->rep_on && c->iter % c->ts_rep == 0) { OpTimer t(c, "applyRepulsionForce"); if ((s = rep_apply(c))) return s; }
   if (have_p && c->wall_on && c->iter % c->ts_wall == 0) { OpTimer t(c, "applyBoundaryRepulsionForce"); if ((s = rep_wall_apply(c))) return s; }
   if (have_p) { OpTimer t(c, "spreadParticleForce"); if ((s = do_spread(c))) return s; }
@@ -141,9 +159,10 @@ hcg_status step(hcg_ctx* c) {
     if (c->dom.n_ranks == 1) {
       OpTimer t(c, "interpolateFluidVelocity"); if (!fused && (s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate_advance(c))) return s;
     } else {
-      { OpTimer t(c, "interpolateFluidVelocity"); if (!fused && (s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate(c))) return s; }
+      // cells no neighbour holds move in the interpolation pass; the shared ones after the velocity sync
+      { OpTimer t(c, "interpolateFluidVelocity"); if (!fused && (s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate_advance_unshared(c))) return s; }
       { OpTimer t(c, "syncEnvelopes"); if ((s = multi_velocity_sync(c))) return s; }
-      { OpTimer t(c, "advanceParticles"); if ((s = ibm_advance(c))) return s; }
+      { OpTimer t(c, "advanceParticles"); if ((s = ibm_advance_shared(c))) return s; }
     }
   } else if (have_p) {
     OpTimer t(c, "advanceParticles"); if ((s = ibm_advance(c))) return s;
@@ -221,12 +240,14 @@ void hcg_destroy(hcg_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->dom.device);
   cudaDeviceSynchronize();
+  peer_destroy(c);
   if (c->nccl) ncclCommDestroy((ncclComm_t)c->nccl);
   cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); cudaFree(c->flags); cudaFree(c->d_bc);
   if (c->rho) cudaFree(c->rho);
   if (c->fused_done) cudaFree(c->fused_done);
   for (int k = 0; k < 3; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->frc[k]); cudaFree(c->frep[k]); }
   for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) if (c->comp[k][d]) cudaFree(c->comp[k][d]);
+  if (c->multi.d_cell_shared) cudaFree(c->multi.d_cell_shared);
   cudaFree(c->p_cell); cudaFree(c->cell_alive); cudaFree(c->cell_type); cudaFree(c->cell_base);
   cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->bin_items); cudaFree(c->wall_nodes); cudaFree(c->scan_tmp);
   cudaFree(c->staging);
@@ -255,7 +276,10 @@ hcg_status hcg_comm_init(hcg_ctx* c, const void* id128) {
   ncclResult_t rc = ncclCommInitRank(&comm, c->dom.n_ranks, id, c->dom.rank);
   if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(rc));
   c->nccl = comm;
-  hcg_status s = exchange_flags(c); if (s) return s;
+  if (const char* e = getenv("HCG_TRANSPORT")) c->peer.transport = (strcmp(e, "nccl") == 0) ? 0 : 1;
+  hcg_status s = peer_setup(c); if (s) return s;
+  s = exchange_flags(c); if (s) return s;
+  if ((s = refresh_nonfluid(c))) return s;
   const double u0[3] = {0, 0, 0};
   s = lat_init_equilibrium(c, 1.0, u0); if (s) return s;
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -271,17 +295,16 @@ hcg_status hcg_lattice_set_flags(hcg_ctx* c, const uint8_t* flags) {
     vel = vel || flags[i] >= HCG_VEL_XN;
   }
   c->has_velbc = vel;
-  bool nonfluid = c->dom.n_ranks > 1;           // ghost planes carry the neighbour's flags
+  bool nonfluid = false;
   for (int64_t i = 0; i < c->Nl && !nonfluid; i++) nonfluid = flags[i] != HCG_FLUID;
-  c->has_nonfluid = nonfluid;
+  c->real_nonfluid = nonfluid; c->has_nonfluid = true;
   hcg_status s = ensure_staging(c, c->Nl); if (s) return s;
   CUDA_TRY(c, cudaMemcpyAsync(c->staging, flags, c->Nl, cudaMemcpyHostToDevice, c->stream));
   k_pad_flags<<<nblk(c->Nl, 256), 256, 0, c->stream>>>((const uint8_t*)c->staging, c->flags, c->Nl, c->P);
   KERNEL_CHECK(c);
   s = exchange_flags(c); if (s) return s;
   c->wall_built = false;
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  return HCG_OK;
+  return refresh_nonfluid(c);                   // (collective for n_ranks > 1: every rank sets its flags)
 }
 
 hcg_status hcg_lattice_set_bc_velocity(hcg_ctx* c, int32_t o, const double u[3]) {
@@ -646,6 +669,12 @@ hcg_status hcg_set_exchange(hcg_ctx* c, double margin_lu, int32_t sync_every, do
   if (c->ncells > 0) return hcg_fail(c, HCG_ERR_STATE, "hcg_set_exchange must precede hcg_cells_add");
   if (c->dom.n_ranks > 1 && 2*margin_lu + 20 > c->nxl) return hcg_fail(c, HCG_ERR_ARG, "slab too thin for this margin");
   c->multi.margin = margin_lu; c->multi.sync_every = sync_every; c->multi.slack = slack;
+  return HCG_OK;
+}
+hcg_status hcg_set_transport(hcg_ctx* c, int32_t transport) {
+  if (!c || transport < 0 || transport > 1) return HCG_ERR_ARG;
+  if (c->nccl) return hcg_fail(c, HCG_ERR_STATE, "hcg_set_transport must precede hcg_comm_init");
+  c->peer.transport = transport;
   return HCG_OK;
 }
 hcg_status hcg_exchange_stats(hcg_ctx* c, int64_t* shared_left, int64_t* shared_right, int64_t* migrated_in, int64_t* migrated_out) {

@@ -48,12 +48,36 @@ struct MultiState {
   int sync_every = 20;            // membership re-evaluation cadence
   double slack = 0.3;             // spare cell slots per type for arrivals
   MultiFace face[2];              // cells shared through the left / right face, sorted by global id
+  MultiFace all;                  // union of the two lists (each shared cell once)
+  uint8_t* d_cell_shared = nullptr; int64_t cell_shared_cap = 0;   // per cell slot: 1 = on a shared list
   std::vector<uint8_t> h_held, h_shared[2];
   std::vector<std::vector<int32_t>> free_slots;
   double* sync_buf = nullptr; size_t sync_cap = 0;
   double* mig_buf = nullptr; size_t mig_cap = 0;
   int64_t* d_cnt = nullptr; double** d_arr = nullptr;
   int64_t migrated_in = 0, migrated_out = 0;
+};
+
+// NVLink peer-memory transport (csrc/peer.cu): the slab neighbours' lattice buffers, flag words and
+// velocity-sync receive buffers mapped into this context (CUDA IPC across processes, direct peer
+// access inside one process), so that halo planes and shared-cell velocities are STORED into the
+// neighbour by the producing kernel and a one-CTA flag kernel replaces the NCCL send/recv pair.
+#define HCG_PEER_NPTR 6            // g[0], g[1], U, flag words, sync_recv[left face], sync_recv[right face]
+struct PeerLink {
+  int rank = -1;                   // neighbour rank, -1 = none (non-periodic end)
+  void* ptr[HCG_PEER_NPTR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+struct PeerMap { unsigned char handle[64]; void* base; };
+struct PeerState {
+  int transport = 1;               // 1 = peer memory (default), 0 = NCCL send/recv
+  bool ready = false;
+  PeerLink link[2];                // left, right
+  unsigned long long* flags = nullptr;   // my flag words: [0] written by the left neighbour, [1] by the right
+  unsigned long long epoch = 0, sync_count = 0;
+  double* sync_recv[2] = {nullptr, nullptr}; size_t sync_recv_cap[2] = {0, 0};
+  std::vector<PeerMap> maps;       // IPC handles opened by this context
+  std::vector<void*> retired;      // outgrown receive buffers: a neighbour may still map them, freed at destroy
+  void* d_blob = nullptr;
 };
 
 struct TimerSlot { std::string name; double ms = 0; int64_t calls = 0; };
@@ -72,6 +96,7 @@ struct hcg_ctx {
   double *F, *U, *rho;         // node force, interpolation velocity (+ density scratch)
   uint8_t* flags;
   bool u_valid, has_velbc, has_nonfluid;
+  bool real_nonfluid = false;  // any non-fluid flag on this rank's real nodes (has_nonfluid also covers the ghost planes)
   // particles
   int64_t np, ncells, cap_p, cap_c;
   double *pos[3], *vel[3], *frc[3], *frep[3];
@@ -95,6 +120,7 @@ struct hcg_ctx {
   cudaEvent_t ev_a, ev_b;
   void* nccl;                  // ncclComm_t
   MultiState multi;
+  PeerState peer;
   double* halo_send[2]; double* halo_recv[2];
   bool timers_on; std::vector<TimerSlot> timers; std::map<std::string,int> timer_idx;
   std::vector<cudaEvent_t> ev_pool; std::vector<TimerPending> ev_pending;
@@ -155,6 +181,8 @@ hcg_status ibm_spread(hcg_ctx* c);
 hcg_status ibm_interpolate(hcg_ctx* c);
 hcg_status ibm_advance(hcg_ctx* c);
 hcg_status ibm_interpolate_advance(hcg_ctx* c);
+hcg_status ibm_interpolate_advance_unshared(hcg_ctx* c);   // multi-GPU: interpolate all, advance the cells no neighbour holds
+hcg_status ibm_advance_shared(hcg_ctx* c);                 // ... and the shared ones after the velocity sync
 // mechanics.cu
 hcg_status mech_apply(hcg_ctx* c, int ctype, bool components);
 hcg_status mech_bbox(hcg_ctx* c, double* out_dev);
@@ -166,6 +194,14 @@ hcg_status spread_sorted(hcg_ctx* c);
 // multi.cu
 hcg_status multi_velocity_sync(hcg_ctx* c);
 hcg_status multi_rebalance(hcg_ctx* c, bool initial);
+hcg_status multi_neighbour_exchange(hcg_ctx* c, const void* sendL, size_t nsL, const void* sendR, size_t nsR,
+                                    void* recvR, size_t nrR, void* recvL, size_t nrL);
+// peer.cu
+inline bool peer_on(const hcg_ctx* c) { return c->dom.n_ranks > 1 && c->peer.transport == 1 && c->peer.ready; }
+hcg_status peer_setup(hcg_ctx* c);                        // collective over slab neighbours (NCCL must be up)
+hcg_status peer_barrier(hcg_ctx* c);                      // publish "everything before this is stored", wait for both neighbours
+hcg_status peer_reserve_sync(hcg_ctx* c, size_t doubles_left, size_t doubles_right, bool* changed);
+void peer_destroy(hcg_ctx* c);
 // repulsion.cu
 hcg_status rep_apply(hcg_ctx* c);
 hcg_status rep_wall_apply(hcg_ctx* c);

@@ -105,11 +105,19 @@ k_spread(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __restrict
   }
 }
 
+// hold_back (multi-GPU): cells flagged there wait for the neighbour's velocities before they move
+// advance of the cells on a list (one CTA per cell): the shared cells after the velocity sync
+__global__ void __launch_bounds__(256)
+k_advance_list(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __restrict__ cells, const int64_t* __restrict__ off,
+               int n, const int64_t* __restrict__ cell_base, uint8_t* alive, double* x, double* y, double* z,
+               const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz);
+
 template <bool ADVANCE, bool INTERP>
 __global__ void __launch_bounds__(256)
 k_interp_advance(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __restrict__ p_cell,
                  uint8_t* alive, double* x, double* y, double* z,
-                 double* vx, double* vy, double* vz, const double* __restrict__ U) {
+                 double* vx, double* vy, double* vz, const double* __restrict__ U,
+                 const uint8_t* __restrict__ hold_back) {
   const int64_t p = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (p >= a.np) return;
   const int cell = p_cell[p];
@@ -130,10 +138,32 @@ k_interp_advance(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __
     if (n >= 0) { vx[p] = v0; vy[p] = v1; vz[p] = v2; }
     else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
   } else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
-  if (ADVANCE) {
+  if (ADVANCE && !(hold_back && hold_back[cell])) {
     px += v0; py += v1; pz += v2;
     x[p] = px; y[p] = py; z[p] = pz;
     // particle on a boundary node => its cell is deleted (hemoCellParticleField.cpp:572-584, 512-553)
+    int lx; bool out;
+    int yy = (int)floor(py + 0.5), zz = (int)floor(pz + 0.5);
+    if (local_x((int)floor(px + 0.5), a, lx, out) && wrap_yz(yy, a.ny, a.py) && wrap_yz(zz, a.nz, a.pz)) {
+      if (flags[(int64_t)zz + (int64_t)a.nz*((int64_t)yy + (int64_t)a.ny*lx)] != HCG_FLUID) alive[cell] = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_advance_list(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __restrict__ cells, const int64_t* __restrict__ off,
+               int n, const int64_t* __restrict__ cell_base, uint8_t* alive, double* x, double* y, double* z,
+               const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int cell = cells[i];
+  if (!alive[cell]) return;
+  const int64_t b = cell_base[cell];
+  const int V = (int)(off[i+1] - off[i]);
+  for (int k = threadIdx.x; k < V; k += blockDim.x) {
+    const int64_t p = b + k;
+    const double px = x[p] + vx[p], py = y[p] + vy[p], pz = z[p] + vz[p];
+    x[p] = px; y[p] = py; z[p] = pz;
     int lx; bool out;
     int yy = (int)floor(py + 0.5), zz = (int)floor(pz + 0.5);
     if (local_x((int)floor(px + 0.5), a, lx, out) && wrap_yz(yy, a.ny, a.py) && wrap_yz(zz, a.nz, a.pz)) {
@@ -168,7 +198,7 @@ hcg_status ibm_interpolate(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   IbmArgs a = make_args(c);
   k_interp_advance<false, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U);
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
   KERNEL_CHECK(c);
   return HCG_OK;
 }
@@ -177,7 +207,7 @@ hcg_status ibm_advance(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   IbmArgs a = make_args(c);
   k_interp_advance<true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U);
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
   KERNEL_CHECK(c);
   return HCG_OK;
 }
@@ -186,7 +216,27 @@ hcg_status ibm_interpolate_advance(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   IbmArgs a = make_args(c);
   k_interp_advance<true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U);
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+
+hcg_status ibm_interpolate_advance_unshared(hcg_ctx* c) {
+  if (c->np == 0) return HCG_OK;
+  if (!c->multi.d_cell_shared) return hcg_fail(c, HCG_ERR_STATE, "shared-cell flags missing (multi_rebalance has not run)");
+  IbmArgs a = make_args(c);
+  k_interp_advance<true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+
+hcg_status ibm_advance_shared(hcg_ctx* c) {
+  const MultiFace& f = c->multi.all;
+  if (c->np == 0 || f.n == 0) return HCG_OK;
+  IbmArgs a = make_args(c);
+  k_advance_list<<<f.n, 256, 0, c->stream>>>(a, c->flags, f.d_cells, f.d_off, f.n, c->cell_base, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2]);
   KERNEL_CHECK(c);
   return HCG_OK;
 }

@@ -132,10 +132,14 @@ __device__ __forceinline__ void regularized_complete(double f[19], int o, const 
 
 // One thread per real node.  RESET: write the body force back after reading F (steps without
 // velocity interpolation).
-template <bool RESET, bool VELBC, int MINB>
+// PEER (multi-GPU, csrc/peer.cu): the face planes additionally store their 5 outgoing populations
+// into the slab neighbour's ghost plane over NVLink (peerL / peerR = the neighbours' output buffers),
+// which replaces the separate halo exchange.
+template <bool RESET, bool VELBC, int MINB, bool PEER>
 __global__ void __launch_bounds__(256, MINB)
 k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, double* __restrict__ F,
-                 const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count) {
+                 const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count,
+                 double* __restrict__ peerL, double* __restrict__ peerR) {
   const int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (k >= count) return;
   const int64_t i = first + k;
@@ -157,15 +161,27 @@ k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, doub
   if (RESET) { double2* Fw = reinterpret_cast<double2*>(F + 4*n); Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0); }
 #pragma unroll
   for (int q = 0; q < 19; q++) gout[(int64_t)q*a.S + n] = f[q];
+  if (PEER) {
+    // my first real plane -> left neighbour's RIGHT ghost (c_x = -1 set); my last -> right neighbour's LEFT ghost (c_x = +1 set)
+    if (i < a.P && peerL) {
+      const int64_t off = (int64_t)(a.nxl + 1)*a.P + rem;
+      peerL[1*a.S + off] = f[1]; peerL[4*a.S + off] = f[4]; peerL[5*a.S + off] = f[5]; peerL[6*a.S + off] = f[6]; peerL[7*a.S + off] = f[7];
+    }
+    if (i >= (int64_t)(a.nxl - 1)*a.P && peerR) {
+      const int64_t off = rem;
+      peerR[10*a.S + off] = f[10]; peerR[13*a.S + off] = f[13]; peerR[14*a.S + off] = f[14]; peerR[15*a.S + off] = f[15]; peerR[16*a.S + off] = f[16];
+    }
+  }
 }
 
 // Moments pass: velocity the IBM interpolation sees, u = j/rho + F/2 of the POST-stream
 // populations with the spread force still on the node (Cell::computeVelocity through
 // core/hemoCellParticleField.cpp:833).  BounceBack: 0; velocity plane: wall velocity.
-template <bool RESET>
+template <bool RESET, bool PEER>
 __global__ void __launch_bounds__(256)
 k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restrict__ U,
-          const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count) {
+          const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count,
+          double* __restrict__ peerL, double* __restrict__ peerR) {
   const int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (k >= count) return;
   const int64_t i = first + k;
@@ -186,6 +202,10 @@ k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restri
   else { u0 = a.bc[3*(fl-2)]; u1 = a.bc[3*(fl-2)+1]; u2 = a.bc[3*(fl-2)+2]; }
   double2* Uw = reinterpret_cast<double2*>(U + 4*n);
   Uw[0] = make_double2(u0, u1); Uw[1] = make_double2(u2, rho);      // slot 3 carries the density
+  if (PEER) {                                                        // node velocity of the face planes -> neighbours' ghost planes
+    if (i < a.P && peerL) { double2* Pw = reinterpret_cast<double2*>(peerL + 4*((int64_t)(a.nxl + 1)*a.P + rem)); Pw[0] = make_double2(u0, u1); Pw[1] = make_double2(u2, rho); }
+    if (i >= (int64_t)(a.nxl - 1)*a.P && peerR) { double2* Pw = reinterpret_cast<double2*>(peerR + 4*(int64_t)rem); Pw[0] = make_double2(u0, u1); Pw[1] = make_double2(u2, rho); }
+  }
   if (RESET) { double2* Fw = reinterpret_cast<double2*>(F + 4*n); Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0); }
 }
 
@@ -686,7 +706,7 @@ RowCfg row_config(hcg_ctx* c, int nrows) {
   }
   RowCfg r; r.ok = false; r.stages = 0; r.grid = 0; r.smem = 0; r.R = 1; r.nt = 288;
   const int nz = c->dom.nz;
-  if (env_mode <= 0 || (nz & 1) || nz < 16) return r;
+  if (env_mode <= 0 || (nz & 1) || nz < 16 || peer_on(c)) return r;   // (the row kernel has no peer-store variant)
   if (c->sm_count <= 0) {
     int dev = c->dom.device, v = 0;
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); c->sm_count = v > 0 ? v : 148;
@@ -737,10 +757,19 @@ hcg_status lat_collide_rows(hcg_ctx* c, bool reset_force, int row0, int row1, cu
   if (done) return hcg_fail(c, HCG_ERR_STATE, "plane counters need the row-pipelined kernel");
   const int64_t first = (int64_t)row0*a.nz, n = (int64_t)(row1 - row0)*a.nz;
   const unsigned nb = nblk(n, 256);
-#define K1_LAUNCH(R, V) k_collide_stream<R, V, 2><<<nb, 256, 0, st>>>(gin, gout, c->F, c->flags, a, first, n)
-  if (c->has_velbc) { if (reset_force) K1_LAUNCH(true, true); else K1_LAUNCH(false, true); }
-  else { if (reset_force) K1_LAUNCH(true, false); else K1_LAUNCH(false, false); }
+  if (peer_on(c)) {
+    double* pL = c->peer.link[0].rank >= 0 ? (double*)c->peer.link[0].ptr[1 - c->cur] : nullptr;
+    double* pR = c->peer.link[1].rank >= 0 ? (double*)c->peer.link[1].ptr[1 - c->cur] : nullptr;
+#define K1_LAUNCH(R, V) k_collide_stream<R, V, 2, true><<<nb, 256, 0, st>>>(gin, gout, c->F, c->flags, a, first, n, pL, pR)
+    if (c->has_velbc) { if (reset_force) K1_LAUNCH(true, true); else K1_LAUNCH(false, true); }
+    else { if (reset_force) K1_LAUNCH(true, false); else K1_LAUNCH(false, false); }
 #undef K1_LAUNCH
+  } else {
+#define K1_LAUNCH(R, V) k_collide_stream<R, V, 2, false><<<nb, 256, 0, st>>>(gin, gout, c->F, c->flags, a, first, n, nullptr, nullptr)
+    if (c->has_velbc) { if (reset_force) K1_LAUNCH(true, true); else K1_LAUNCH(false, true); }
+    else { if (reset_force) K1_LAUNCH(true, false); else K1_LAUNCH(false, false); }
+#undef K1_LAUNCH
+  }
   KERNEL_CHECK(c);
   return HCG_OK;
 }
@@ -752,6 +781,7 @@ hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
   }
   c->cur = 1 - c->cur;
   c->u_valid = false;
+  if (peer_on(c)) return peer_barrier(c);          // the face planes were stored into the neighbours by the kernel itself
   return lat_halo_exchange_pop(c);
 }
 
@@ -762,8 +792,15 @@ static hcg_status moments_rows(hcg_ctx* c, bool reset_force, int row0, int row1)
   LatArgs a = make_args(c);
   const int64_t first = (int64_t)row0*a.nz, n = (int64_t)(row1 - row0)*a.nz;
   const unsigned nb = nblk(n, 256);
-  if (reset_force) k_moments<true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n);
-  else k_moments<false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n);
+  if (peer_on(c)) {
+    double* pL = c->peer.link[0].rank >= 0 ? (double*)c->peer.link[0].ptr[2] : nullptr;
+    double* pR = c->peer.link[1].rank >= 0 ? (double*)c->peer.link[1].ptr[2] : nullptr;
+    if (reset_force) k_moments<true, true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, pL, pR);
+    else k_moments<false, true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, pL, pR);
+  } else {
+    if (reset_force) k_moments<true, false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, nullptr, nullptr);
+    else k_moments<false, false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, nullptr, nullptr);
+  }
   KERNEL_CHECK(c);
   return HCG_OK;
 }
@@ -775,6 +812,7 @@ hcg_status lat_moments(hcg_ctx* c, bool reset_force, bool want_rho) {
     hcg_status s = moments_rows(c, reset_force, 0, c->nxl*c->dom.ny); if (s) return s;
   }
   c->u_valid = true;
+  if (peer_on(c)) return peer_barrier(c);
   return lat_halo_exchange_u(c);
 }
 

@@ -34,39 +34,52 @@ inline bool band_hit(double lo, double hi, double a, double b, int nx, bool peri
   return false;
 }
 
-__global__ void k_pack_sync(const int32_t* __restrict__ cells, const int64_t* __restrict__ off, int n, int64_t total,
-                            const int64_t* __restrict__ cell_base, const uint8_t* __restrict__ alive,
-                            const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
-                            double* buf) {
-  // buf = [n alive flags][3 * total velocities]
+// owner test shared by both holders of a cell (pre-advance position, identical bits on both sides):
+// the vertex' nearest node lies inside the slab [x0, x0 + nxl)
+__device__ __forceinline__ bool owns_vertex(double x, int nx, int px, int x0, int nxl) {
+  int gx = (int)floor(x + 0.5);
+  if (px) { gx %= nx; if (gx < 0) gx += nx; }
+  int rel = gx - x0; if (px && rel < 0) rel += nx;
+  return rel >= 0 && rel < nxl;
+}
+
+// message = [n alive flags][vx of all shared vertices][vy ...][vz ...]; only the entries of vertices this
+// rank OWNS are written (the receiver reads exactly those: the vertices it does not own), which halves the
+// NVLink traffic; component blocks keep the stores coalesced.
+__global__ void __launch_bounds__(256)
+k_pack_sync(const int32_t* __restrict__ cells, const int64_t* __restrict__ off, int n, int64_t total,
+            const int64_t* __restrict__ cell_base, const uint8_t* __restrict__ alive,
+            const double* __restrict__ x,
+            const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
+            double* buf, int nx, int px, int x0, int nxl) {
   const int i = blockIdx.x;
   if (i >= n) return;
   const int c = cells[i];
   const int64_t b = cell_base[c], o = off[i];
   const int V = (int)(off[i+1] - o);
   if (threadIdx.x == 0) buf[i] = alive[c] ? 1.0 : 0.0;
-  double* v = buf + n + 3*o;
-  for (int k = threadIdx.x; k < V; k += blockDim.x) { v[3*k] = vx[b+k]; v[3*k+1] = vy[b+k]; v[3*k+2] = vz[b+k]; }
+  double* v = buf + n + o;
+  for (int k = threadIdx.x; k < V; k += blockDim.x) {
+    if (!owns_vertex(x[b+k], nx, px, x0, nxl)) continue;
+    v[k] = vx[b+k]; v[total + k] = vy[b+k]; v[2*total + k] = vz[b+k];
+  }
 }
 
-__global__ void k_unpack_sync(const int32_t* __restrict__ cells, const int64_t* __restrict__ off, int n,
-                              const int64_t* __restrict__ cell_base, uint8_t* alive,
-                              const double* __restrict__ x, double* vx, double* vy, double* vz,
-                              const double* __restrict__ buf, int nx, int px, int x0, int nxl) {
+__global__ void __launch_bounds__(256)
+k_unpack_sync(const int32_t* __restrict__ cells, const int64_t* __restrict__ off, int n, int64_t total,
+              const int64_t* __restrict__ cell_base, uint8_t* alive,
+              const double* __restrict__ x, double* vx, double* vy, double* vz,
+              const double* __restrict__ buf, int nx, int px, int x0, int nxl) {
   const int i = blockIdx.x;
   if (i >= n) return;
   const int c = cells[i];
   const int64_t b = cell_base[c], o = off[i];
   const int V = (int)(off[i+1] - o);
   if (threadIdx.x == 0 && buf[i] == 0.0) alive[c] = 0;
-  const double* v = buf + n + 3*o;
+  const double* v = buf + n + o;
   for (int k = threadIdx.x; k < V; k += blockDim.x) {
-    // owner test on the pre-advance position: nearest node inside my slab
-    int gx = (int)floor(x[b+k] + 0.5);
-    if (px) { gx %= nx; if (gx < 0) gx += nx; }
-    int rel = gx - x0; if (px && rel < 0) rel += nx;
-    const bool mine = rel >= 0 && rel < nxl;
-    if (!mine) { vx[b+k] = v[3*k]; vy[b+k] = v[3*k+1]; vz[b+k] = v[3*k+2]; }
+    if (owns_vertex(x[b+k], nx, px, x0, nxl)) continue;      // authoritative here
+    vx[b+k] = v[k]; vy[b+k] = v[total + k]; vz[b+k] = v[2*total + k];
   }
 }
 
@@ -145,6 +158,11 @@ hcg_status upload_list(hcg_ctx* c, MultiFace& f, const std::vector<int32_t>& cel
 
 }  // namespace
 
+hcg_status multi_neighbour_exchange(hcg_ctx* c, const void* sendL, size_t nsL, const void* sendR, size_t nsR,
+                                    void* recvR, size_t nrR, void* recvL, size_t nrL) {
+  return neighbour_exchange(c, sendL, nsL, sendR, nsR, recvR, nrR, recvL, nrL);
+}
+
 // pure host logic, exported for CPU tests (include/hemocell_host.h)
 extern "C" void hch_slab_membership(int64_t n, const double* xlo, const double* xhi, int32_t nx, int32_t periodic_x,
                                     int32_t nxl, int32_t rank, int32_t n_ranks, double margin,
@@ -167,20 +185,49 @@ hcg_status multi_velocity_sync(hcg_ctx* c) {
   hcg_status s;
   size_t ns[2], off_send[2], off_recv[2];
   size_t tot = 0;
+  if (peer_on(c)) {
+    // peer-memory path: the pack kernel stores straight into the neighbour's receive buffer of the facing
+    // face (left neighbour: its right-face buffer, ptr[5]; right neighbour: its left-face buffer, ptr[4])
+    // Receive buffers are double-buffered by sync parity: the neighbour's unpack of sync k may still be
+    // running when I pack sync k+1 (no barrier in between), but never when I pack sync k+2.
+    const size_t half = (size_t)(c->peer.sync_count++ & 1ULL);
+    for (int f = 0; f < 2; f++) {
+      if (!m.face[f].n || c->peer.link[f].rank < 0) continue;
+      double* dst = (double*)c->peer.link[f].ptr[4 + (1 - f)];
+      if (!dst) return hcg_fail(c, HCG_ERR_STATE, "peer transport: neighbour receive buffer not mapped");
+      dst += half*((size_t)m.face[f].n + 3*(size_t)m.face[f].total);
+      k_pack_sync<<<m.face[f].n, 256, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n, m.face[f].total,
+          c->cell_base, c->cell_alive, c->pos[0], c->vel[0], c->vel[1], c->vel[2], dst,
+          c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
+      KERNEL_CHECK(c);
+    }
+    if ((s = peer_barrier(c))) return s;
+    for (int f = 0; f < 2; f++) {
+      if (!m.face[f].n || c->peer.link[f].rank < 0) continue;
+      k_unpack_sync<<<m.face[f].n, 256, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n, m.face[f].total,
+          c->cell_base, c->cell_alive, c->pos[0], c->vel[0], c->vel[1], c->vel[2],
+          c->peer.sync_recv[f] + half*((size_t)m.face[f].n + 3*(size_t)m.face[f].total),
+          c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
+      KERNEL_CHECK(c);
+    }
+    // the neighbour may overwrite my receive buffer only after it has seen my NEXT barrier, which follows these kernels
+    return HCG_OK;
+  }
   for (int f = 0; f < 2; f++) { ns[f] = (size_t)m.face[f].n + 3*(size_t)m.face[f].total; off_send[f] = tot; tot += ns[f]; }
   for (int f = 0; f < 2; f++) { off_recv[f] = tot; tot += ns[f]; }      // both sides hold the same lists
   if ((s = ensure_buf(c, &m.sync_buf, &m.sync_cap, tot))) return s;
   for (int f = 0; f < 2; f++) {
     if (!m.face[f].n) continue;
-    k_pack_sync<<<m.face[f].n, 128, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n, m.face[f].total,
-        c->cell_base, c->cell_alive, c->vel[0], c->vel[1], c->vel[2], m.sync_buf + off_send[f]);
+    k_pack_sync<<<m.face[f].n, 256, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n, m.face[f].total,
+        c->cell_base, c->cell_alive, c->pos[0], c->vel[0], c->vel[1], c->vel[2], m.sync_buf + off_send[f],
+        c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
     KERNEL_CHECK(c);
   }
   if ((s = neighbour_exchange(c, m.sync_buf + off_send[0], 8*ns[0], m.sync_buf + off_send[1], 8*ns[1],
                               m.sync_buf + off_recv[1], 8*ns[1], m.sync_buf + off_recv[0], 8*ns[0]))) return s;
   for (int f = 0; f < 2; f++) {
     if (!m.face[f].n) continue;
-    k_unpack_sync<<<m.face[f].n, 128, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n,
+    k_unpack_sync<<<m.face[f].n, 256, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n, m.face[f].total,
         c->cell_base, c->cell_alive, c->pos[0], c->vel[0], c->vel[1], c->vel[2], m.sync_buf + off_recv[f],
         c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
     KERNEL_CHECK(c);
@@ -318,6 +365,26 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
       if (m.h_held[i] && m.h_shared[f][i] && c->h_cell_id[i] >= 0) list.push_back((int32_t)i);
     std::sort(list.begin(), list.end(), [&](int32_t a, int32_t b) { return c->h_cell_id[a] < c->h_cell_id[b]; });
     if ((s = upload_list(c, m.face[f], list))) return s;
+  }
+  // union list + per-slot flag: the step advances unshared cells in the interpolation pass and the
+  // shared ones after the velocity sync
+  {
+    std::vector<int32_t> list;
+    std::vector<uint8_t> flag((size_t)std::max<int64_t>(nc, 1), 0);
+    for (int64_t i = 0; i < nc; i++)
+      if (m.h_held[i] && (m.h_shared[0][i] || m.h_shared[1][i]) && c->h_cell_id[i] >= 0) { list.push_back((int32_t)i); flag[i] = 1; }
+    if ((s = upload_list(c, m.all, list))) return s;
+    if (m.cell_shared_cap < nc || !m.d_cell_shared) {
+      if (m.d_cell_shared) cudaFree(m.d_cell_shared);
+      CUDA_TRY(c, cudaMalloc(&m.d_cell_shared, (size_t)std::max<int64_t>(nc, 1)));
+      m.cell_shared_cap = nc;
+    }
+    CUDA_TRY(c, cudaMemcpy(m.d_cell_shared, flag.data(), (size_t)std::max<int64_t>(nc, 1), cudaMemcpyHostToDevice));
+  }
+  // peer transport: receive buffers sized for the new lists, mappings re-published (collective, cheap)
+  if (c->peer.transport == 1) {
+    if ((s = peer_reserve_sync(c, 2*((size_t)m.face[0].n + 3*(size_t)m.face[0].total), 2*((size_t)m.face[1].n + 3*(size_t)m.face[1].total), nullptr))) return s;
+    if ((s = peer_setup(c))) return s;
   }
   return HCG_OK;
 }

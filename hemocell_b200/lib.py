@@ -49,7 +49,7 @@ hcg_lattice_set_flags hcg_lattice_set_bc_velocity hcg_lattice_init_equilibrium h
 hcg_lattice_upload hcg_lattice_download hcg_celltype_add hcg_cells_add hcg_cells_count hcg_cells_capacity
 hcg_cells_upload hcg_cells_download hcg_cells_info hcg_cells_add_force hcg_celltype_set_stiffness
 hcg_set_force_limit hcg_set_timescales hcg_set_material_timescale hcg_set_repulsion hcg_set_wall_repulsion
-hcg_set_spread_mode hcg_set_exchange hcg_exchange_stats hcg_set_iteration hcg_get_iteration hcg_iterate hcg_fluid_warmup hcg_op_repulsion hcg_op_wall_repulsion
+hcg_set_spread_mode hcg_set_exchange hcg_set_transport hcg_exchange_stats hcg_set_iteration hcg_get_iteration hcg_iterate hcg_fluid_warmup hcg_op_repulsion hcg_op_wall_repulsion
 hcg_op_spread hcg_op_collide_stream hcg_op_interpolate hcg_op_sync hcg_op_advance hcg_op_mechanics
 hcg_op_zero_force hcg_cells_bbox hcg_cells_volume_area hcg_fluid_velocity_stats hcg_timers_enable
 hcg_timers hcg_timers_reset hcg_launch_count hcg_synchronize hcg_iterate_timed""".split()
@@ -242,6 +242,10 @@ class Context:
 
     def set_exchange(self, margin=4.0, sync_every=20, slack=0.3):
         self._ck(self.L.hcg_set_exchange(self.h, C.c_double(margin), C.c_int32(sync_every), C.c_double(slack)))
+
+    def set_transport(self, transport):
+        """1 = NVLink peer memory (default), 0 = NCCL send/recv; before comm_init"""
+        self._ck(self.L.hcg_set_transport(self.h, C.c_int32(transport)))
 
     def exchange_stats(self):
         v = [C.c_int64() for _ in range(4)]

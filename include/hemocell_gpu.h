@@ -150,6 +150,13 @@ hcg_status hcg_set_spread_mode(hcg_ctx*, int32_t mode, int32_t resort_every);
  * every cell within `margin_lu` of its slab, membership is re-evaluated every `sync_every` steps,
  * `slack` = fraction of spare cell slots for arrivals.  Must precede hcg_cells_add. */
 hcg_status hcg_set_exchange(hcg_ctx*, double margin_lu, int32_t sync_every, double slack);
+/* multi-GPU transport of the per-step exchanges (lattice ghost planes, node velocity ghosts, shared-cell
+ * velocity sync; replaces the MPI messages of Palabos' block communicator and of
+ * HemoCellParticleDataTransfer::send/receive, core/hemoCellParticleDataTransfer.cpp:67-180):
+ * 1 (default) = NVLink peer memory: the producing kernels store into the neighbour's buffers, a flag
+ * kernel synchronises (needs P2P access between neighbouring GPUs of one box); 0 = NCCL send/recv.
+ * Must precede hcg_comm_init.  Environment HCG_TRANSPORT=nccl|peer overrides. */
+hcg_status hcg_set_transport(hcg_ctx*, int32_t transport);
 hcg_status hcg_exchange_stats(hcg_ctx*, int64_t* shared_left, int64_t* shared_right,
                               int64_t* migrated_in, int64_t* migrated_out);
 hcg_status hcg_set_iteration(hcg_ctx*, int64_t iter);

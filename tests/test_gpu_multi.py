@@ -28,7 +28,7 @@ def _device_count():
     return n.value if rt.cudaGetDeviceCount(C.byref(n)) == 0 else 0
 
 
-def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, cadence, sync_every, f_limit):
+def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, cadence, sync_every, f_limit, transport=1):
     from hemocell_b200 import lib as H
     nx, ny, nz = dims
     nxl = nx // R
@@ -39,6 +39,7 @@ def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, 
     def work(r):
         try:
             ctx = H.Context(nx, ny, nz, periodic, tau, device=r, rank=r, n_ranks=R)
+            ctx.set_transport(transport)
             ctx.comm_init(uid)
             ctx.set_flags(np.ascontiguousarray(fl3[r * nxl:(r + 1) * nxl]))
             for o in range(6):
@@ -69,8 +70,10 @@ def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, 
     return out
 
 
+# transport 1 = NVLink peer memory (kernels store into the neighbour, flag barrier), 0 = NCCL send/recv
+@pytest.mark.parametrize("transport", [1, 0])
 @pytest.mark.parametrize("cadence", [1, 5])
-def test_two_gpu_matches_single_gpu(cadence):
+def test_two_gpu_matches_single_gpu(cadence, transport):
     if _device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from hemocell_b200 import lib as H
@@ -108,7 +111,7 @@ def test_two_gpu_matches_single_gpu(cadence):
     # the cells moved ~5 lu downstream: some crossed a slab face
     assert (ref_pos[:, :, 0].mean(1) - cells[:, :, 0].mean(1)).min() > 3.0
 
-    out = _run_multi(R, dims, periodic, par.tau, fl, bc, body, ct, cells, ids, u0, steps, cadence, sync_every, par.f_limit)
+    out = _run_multi(R, dims, periodic, par.tau, fl, bc, body, ct, cells, ids, u0, steps, cadence, sync_every, par.f_limit, transport)
     nxl = nx // R
     for r in range(R):
         got = out[r]["pop"].reshape(19, nxl, ny, nz)
@@ -131,3 +134,59 @@ def test_two_gpu_matches_single_gpu(cadence):
     assert sum(o["stats"]["migrated_in"] for o in out) == sum(o["stats"]["migrated_out"] for o in out)
     assert any(int((o["ids"] < 0).sum()) > 0 for o in out)                 # ... and so was dropping
     assert all(o["stats"]["shared_left"] + o["stats"]["shared_right"] > 0 for o in out)
+
+
+def test_two_processes_peer_ipc(tmp_path):
+    """one process per GPU (bench.py topology): the peer transport maps the neighbour through CUDA IPC"""
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os, subprocess, sys
+    from hemocell_b200 import lib as H
+    R = 2
+    nx, ny, nz = 96, 32, 32
+    periodic = (1, 1, 0)
+    par = M.Parameters(dx=0.5e-6, dt=0.5e-7)
+    bc = np.zeros((6, 3)); bc[4] = (0.06, 0, 0); bc[5] = (0.02, 0, 0)
+    fl = U.couette_flags(nx, ny, nz).reshape(-1)
+    body = (1e-6, 0.0, 0.0); u0 = (0.04, 0.0, 0.0)
+    ct = O.rbc_celltype(par)
+    centers = [(41.0, 16.0, 14.0), (88.5, 17.0, 15.0), (3.0, 14.0, 18.0), (70.0, 15.0, 8.5)]
+    cells = U.deformed_cells(ct, centers, 6, amp=0.0, stretch=(1.04, 0.98, 0.98))
+    ids = np.arange(len(centers)) + 100
+    steps, sync_every, cadence = 60, 5, 1
+    ctx = H.Context(nx, ny, nz, periodic, par.tau, device=0)
+    ctx.set_flags(fl)
+    for o in range(6):
+        ctx.set_bc_velocity(o, bc[o])
+    ctx.set_body_force(body); ctx.init_equilibrium(1.0, u0); ctx.set_force_limit(par.f_limit)
+    t = ctx.add_celltype(ct.model, ct.cc, ct.k)
+    ctx.add_cells(t, cells, ids)
+    ctx.set_timescales(cadence, 1, 1); ctx.set_material_timescale(t, cadence)
+    ctx.iterate(steps)
+    ref_pop = ctx.lattice_download(H.LAT_POP).reshape(19, nx, ny, nz)
+    ref_pos = ctx.cells_download(H.P_POS).reshape(len(centers), ct.V, 3)
+    ctx.close()
+    np.savez(tmp_path / "problem.npz", dims=[nx, ny, nz], periodic=periodic, flags=fl, bc=bc, body=body, u0=u0,
+             cells=cells, ids=ids, steps=steps, sync_every=sync_every, cadence=cadence)
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi_proc_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), str(R), str(tmp_path), "1"], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(R)]
+    logs = []
+    for p in procs:
+        try:
+            logs.append(p.communicate(timeout=420)[0])
+        except subprocess.TimeoutExpired:
+            p.kill(); logs.append("TIMEOUT " + p.communicate()[0])
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    nxl = nx // R
+    seen = set()
+    for r in range(R):
+        o = np.load(tmp_path / f"out_{r}.npz")
+        U.assert_close(o["pop"].reshape(19, nxl, ny, nz), ref_pop[:, r * nxl:(r + 1) * nxl], f"populations of rank {r}", rtol=1e-9, floor=1e-11)
+        pos = o["pos"].reshape(-1, ct.V, 3)
+        for slot, (cid, al) in enumerate(zip(o["ids"], o["alive"])):
+            if cid < 0 or not al:
+                continue
+            seen.add(int(cid) - 100)
+            U.assert_close(pos[slot], ref_pos[int(cid) - 100], f"rank {r} cell {cid} positions", rtol=1e-11, floor=1e-12)
+    assert seen == set(range(len(centers)))
