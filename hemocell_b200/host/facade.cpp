@@ -1,0 +1,941 @@
+// The HemoCell C++ API surface (include/hemocell.h) implemented over the C ABI of
+// libhemocell_gpu.so.  Host orchestration only: every operator call ends in an hcg_* entry point.
+//   reference: core/hemoCell.cpp, core/hemoCellFields.cpp, core/hemoCellField.cpp, config/config.cpp,
+//              config/logfile.cpp, mechanics/constantConversion.cpp, helper/cellInfo.cpp,
+//              helper/fluidInfo.cpp, helper/profiler.cpp, io/writeCellInfoCSV.cpp
+#include "hemo_mesh.h"          // hemo::host:: set-up code (before hemocell.h: its enum names are macros there)
+#include "hemo_xml.h"
+#include "hemocell.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <functional>
+#include <iomanip>
+#include <thread>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace hemo {
+
+// ------------------------------------------------------------------------------------------------
+// process view: one process per GPU, rank / size from the launcher
+// ------------------------------------------------------------------------------------------------
+namespace {
+int env_int(const char* a, const char* b, int dflt) {
+  const char* v = getenv(a);
+  if (!v && b) v = getenv(b);
+  return v ? atoi(v) : dflt;
+}
+[[noreturn]] void fatal(const std::string& msg) {
+  // reference convention: log, then exit(1) (e.g. core/hemoCell.cpp:75-79)
+  std::cerr << msg << std::endl;
+  hlog << msg << std::endl;
+  exit(1);
+}
+void ck(hcg_ctx* c, hcg_status s, const char* what) {
+  if (s == HCG_OK) return;
+  fatal(std::string("(HemoCell) (GPU) ") + what + " failed: " + hcg_last_error(c));
+}
+bool file_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+void mkpath(const std::string& p) {
+  std::string cur;
+  for (size_t i = 0; i < p.size(); i++) {
+    cur += p[i];
+    if (p[i] == '/' || i + 1 == p.size()) mkdir(cur.c_str(), 0777);
+  }
+}
+std::string zeroPadNumber(unsigned long n) { std::ostringstream o; o << std::setw(12) << std::setfill('0') << n; return o.str(); }   // helper/genericFunctions.h:63
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// rank 0 -> all ranks of this launch through a file (all ranks share one box and one parent launcher)
+void share_bytes(const char* tag, void* data, size_t n) {
+  static int generation = 0;
+  const int rank = env_int("RANK", "OMPI_COMM_WORLD_RANK", 0);
+  const char* dir = getenv("HEMOCELL_RENDEZVOUS_DIR");
+  std::ostringstream p;
+  p << (dir ? dir : "/tmp") << "/hemocell_" << tag << "_" << (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0") << "_" << getppid() << "_" << generation++;
+  const std::string path = p.str();
+  if (rank == 0) {
+    std::ofstream f(path + ".tmp", std::ios::binary);
+    f.write((const char*)data, (std::streamsize)n); f.close();
+    rename((path + ".tmp").c_str(), path.c_str());
+  } else {
+    const double t0 = now_s();
+    while (!file_exists(path)) {
+      if (now_s() - t0 > 300) fatal("(HemoCell) timed out waiting for rank 0 at " + path);
+      std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    }
+    std::ifstream f(path, std::ios::binary);
+    f.read((char*)data, (std::streamsize)n);
+  }
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// GpuLattice: host-side domain description recorded by the plb:: calls + the device context
+// ------------------------------------------------------------------------------------------------
+class GpuLattice {
+ public:
+  int nx, ny, nz;
+  double omega;
+  bool periodic[3] = {false, false, false};
+  std::vector<uint8_t> flags;                 // global, z + nz*(y + ny*x)
+  double bc[6][3];
+  double body[3] = {0, 0, 0};
+  double eq_rho = 1.0, eq_u[3] = {0, 0, 0};
+  bool eq_pending = true, body_pending = true;
+  hcg_ctx* ctx = nullptr;
+  bool created_periodic[3] = {false, false, false};
+  bool has_cells = false;
+  int generation = 0;                         // bumped whenever a new device context is created
+
+  GpuLattice(int nx_, int ny_, int nz_, double omega_) : nx(nx_), ny(ny_), nz(nz_), omega(omega_), flags((size_t)nx_*ny_*nz_, HCG_FLUID) {
+    memset(bc, 0, sizeof(bc));
+  }
+  ~GpuLattice() { if (ctx) hcg_destroy(ctx); }
+
+  int64_t idx(int x, int y, int z) const { return (int64_t)z + (int64_t)nz*((int64_t)y + (int64_t)ny*x); }
+  int rank() const { return plb::global::mpi().getRank(); }
+  int size() const { return plb::global::mpi().getSize(); }
+  int nxl() const { return nx / size(); }
+
+  // create the context on first device use; re-create if the periodicity was toggled afterwards
+  void materialize() {
+    if (ctx && !memcmp(periodic, created_periodic, sizeof(periodic))) { flush(); return; }
+    if (ctx) {
+      if (has_cells) fatal("(HemoCell) (Periodicity) the periodicity cannot change once particles are loaded");
+      hcg_destroy(ctx); ctx = nullptr;
+    }
+    hcg_domain d;
+    d.nx = nx; d.ny = ny; d.nz = nz;
+    for (int k = 0; k < 3; k++) d.periodic[k] = periodic[k];
+    d.tau = 1.0/omega;
+    d.device = plb::global::mpi().getLocalRank();
+    d.rank = rank(); d.n_ranks = size();
+    if (nx % d.n_ranks) fatal("(HemoCell) (GPU) the lattice x-size must be divisible by the number of GPU ranks");
+    hcg_status s = hcg_create(&d, &ctx);
+    if (s != HCG_OK) fatal(std::string("(HemoCell) (GPU) cannot create the device context: ") + hcg_last_error(ctx));
+    if (d.n_ranks > 1) {
+      unsigned char id[128];
+      rendezvous(id);
+      ck(ctx, hcg_comm_init(ctx, id), "hcg_comm_init");
+    }
+    memcpy(created_periodic, periodic, sizeof(periodic));
+    generation++;
+    const int64_t P = (int64_t)ny*nz;
+    ck(ctx, hcg_lattice_set_flags(ctx, flags.data() + (int64_t)rank()*nxl()*P), "hcg_lattice_set_flags");
+    for (int o = 0; o < 6; o++) ck(ctx, hcg_lattice_set_bc_velocity(ctx, o, bc[o]), "hcg_lattice_set_bc_velocity");
+    flags_dirty = false;
+    eq_pending = true; body_pending = true;
+    flush();
+    global.statistics.setDeviceTimers(ctx);
+    hcg_timers_enable(ctx, 1);
+  }
+  void flush() {
+    if (!ctx) return;
+    if (flags_dirty) {
+      const int64_t P = (int64_t)ny*nz;
+      ck(ctx, hcg_lattice_set_flags(ctx, flags.data() + (int64_t)rank()*nxl()*P), "hcg_lattice_set_flags");
+      for (int o = 0; o < 6; o++) ck(ctx, hcg_lattice_set_bc_velocity(ctx, o, bc[o]), "hcg_lattice_set_bc_velocity");
+      flags_dirty = false;
+    }
+    if (eq_pending) { ck(ctx, hcg_lattice_init_equilibrium(ctx, eq_rho, eq_u), "hcg_lattice_init_equilibrium"); eq_pending = false; }
+    if (body_pending) { ck(ctx, hcg_lattice_set_body_force(ctx, body), "hcg_lattice_set_body_force"); body_pending = false; }
+  }
+  void touchFlags() { flags_dirty = true; }
+
+ private:
+  bool flags_dirty = false;
+  void rendezvous(unsigned char id[128]) {
+    if (rank() == 0) ck(nullptr, hcg_comm_unique_id(id), "hcg_comm_unique_id");
+    share_bytes("nccl", id, 128);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// globals
+// ------------------------------------------------------------------------------------------------
+ConfigValues global;
+Logfile hlog(true), hlogfile(false);
+T Parameters::dt = 0, Parameters::dx = 0, Parameters::dm = 0, Parameters::df = 0, Parameters::nu_p = 0, Parameters::rho_p = 0,
+  Parameters::tau = 0, Parameters::re = 0, Parameters::nu_lbm = 0, Parameters::u_lbm_max = 0, Parameters::pipe_radius = 0,
+  Parameters::kBT_p = 0, Parameters::kBT_lbm = 0, Parameters::shearrate_lbm = 0, Parameters::f_limit = 0;
+map<int, CellInformation> CellInformationFunctionals::info_per_cell;
+
+// ------------------------------------------------------------------------------------------------
+// Config (config/config.cpp:28-84)
+// ------------------------------------------------------------------------------------------------
+std::string XMLElement::text() const { return orig ? orig->text : std::string(); }
+XMLElement XMLElement::operator[](const std::string& name) const {
+  const xml::Node* child = orig ? orig->firstChild(name) : nullptr;
+  if (!child) throw std::invalid_argument("XML child " + name + " does not exist.");
+  return XMLElement(child);
+}
+Config::Config(const std::string& f) { load(f); }
+Config::~Config() {}
+void Config::reload(const std::string& f) { load(f); }
+void Config::load(const std::string& f) {
+  if (!file_exists(f)) { pcout << f + " is not an existing config file, exiting ..." << std::endl; exit(1); }
+  try { doc = xml::parseFile(f); }
+  catch (std::exception& e) { pcout << f << ": " << e.what() << ", exiting ..." << std::endl; exit(1); }
+  // fresh start or checkpointed run: the first element is <Checkpoint> or <hemocell>
+  checkpointed = !doc->children.empty() && doc->children[0]->name == "Checkpoint";
+}
+XMLElement Config::operator[](const std::string& name) const {
+  if (checkpointed) return XMLElement(doc.get())["Checkpoint"]["hemocell"][name];
+  return XMLElement(doc.get())["hemocell"][name];
+}
+
+void loadDirectories(Config* cfg, bool edit_out_dir) {
+  auto& dirs = plb::global::directories();
+  dirs.setInputDir("./");
+  if (edit_out_dir) {
+    std::string outDir;
+    try {
+      outDir = (*cfg)["parameters"]["outputDirectory"].read<std::string>();
+      while (!outDir.empty() && outDir.back() == '/') outDir.pop_back();
+      if (outDir.empty() || outDir[0] != '/') outDir = "./" + outDir;
+    } catch (std::invalid_argument&) { outDir = "./tmp"; }
+    // never overwrite an earlier run: tmp, tmp_0, tmp_1, ... (rank 0 decides, the others follow)
+    std::string chosen = outDir;
+    if (plb::global::mpi().isMainProcessor()) {
+      for (int i = 0; file_exists(chosen); i++) chosen = outDir + "_" + std::to_string(i);
+      mkpath(chosen + "/hdf5/");
+    }
+    if (plb::global::mpi().getSize() > 1) {
+      char buf[1024] = {0};
+      strncpy(buf, chosen.c_str(), sizeof(buf) - 1);
+      share_bytes("outdir", buf, sizeof(buf));
+      chosen = buf;
+    }
+    dirs.setOutputDir(chosen + "/");
+  }
+  try { dirs.setLogOutDir(dirs.getOutputDir() + "/" + (*cfg)["parameters"]["logDirectory"].read<std::string>() + "/"); }
+  catch (std::invalid_argument&) { dirs.setLogOutDir(dirs.getOutputDir() + "/log/"); }
+  std::string logfilename = "logfile";
+  try { logfilename = (*cfg)["parameters"]["logFile"].read<std::string>(); } catch (std::invalid_argument&) {}
+  if (plb::global::mpi().isMainProcessor()) mkpath(dirs.getLogOutDir());
+  // logfile, logfile.0, logfile.1, ... (config/config.cpp:120-135)
+  std::string base = dirs.getLogOutDir() + logfilename, name = base;
+  for (int i = 0; file_exists(name); i++) name = base + "." + std::to_string(i);
+  hlog.open(name); hlogfile.open(name);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parameters (mechanics/constantConversion.cpp:36-110)
+// ------------------------------------------------------------------------------------------------
+void Parameters::lbm_base_parameters(Config& cfg) {
+  host::Parameters p;
+  p.lbm_base_parameters(cfg["domain"]["dx"].read<T>(), cfg["domain"]["dt"].read<T>(), cfg["domain"]["nuP"].read<T>(),
+                        cfg["domain"]["rhoP"].read<T>(), cfg["domain"]["kBT"].read<T>());
+  if (cfg["domain"]["dt"].read<T>() < 0.0) hlog << "(HemoCell) dt is set to *auto*. Tau will be set to 1!" << std::endl;
+  dt = p.dt; dx = p.dx; nu_p = p.nu_p; rho_p = p.rho_p; kBT_p = p.kBT_p; tau = p.tau; nu_lbm = p.nu_lbm;
+  dm = p.dm; df = p.df; f_limit = p.f_limit; kBT_lbm = p.kBT_lbm;
+}
+void Parameters::lbm_pipe_parameters(Config& cfg, int nY) {
+  lbm_base_parameters(cfg);
+  re = cfg["domain"]["Re"].read<T>();
+  pipe_radius = nY;
+  hlog << "(Parameters) The channel has a predefined radius of " << pipe_radius << " LU." << std::endl;
+  u_lbm_max = re * nu_lbm / (pipe_radius*2);
+}
+void Parameters::lbm_shear_parameters(Config& cfg, T nx) {
+  lbm_base_parameters(cfg);
+  const T shearrate_p = cfg["domain"]["shearrate"].read<T>();
+  re = (nx * (shearrate_p * (nx*0.5))) / nu_p;
+  shearrate_lbm = shearrate_p*dt;
+  u_lbm_max = shearrate_lbm;
+}
+void Parameters::printParameters() {
+  hlog << "(HemoCell) System parameters:" << std::endl;
+  hlog << "\t dx: \t" << dx << std::endl;
+  hlog << "\t dt: \t" << dt << std::endl;
+  hlog << "\t dm: \t" << dm << std::endl;
+  hlog << "\t dN: \t" << df << std::endl;
+  hlog << "\t tau: \t" << tau << std::endl;
+  hlog << "\t nu_lbm: \t" << nu_lbm << std::endl;
+  hlog << "\t u_lb_max: \t" << u_lbm_max << std::endl;
+  hlog << "\t f_limit: \t" << f_limit << std::endl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Profiler (helper/profiler.cpp:156-180): wall clock for the run, CUDA-event times per operator
+// ------------------------------------------------------------------------------------------------
+void Profiler::start() { t0 = now_s(); running = true; }
+void Profiler::stop() { if (running) { t_total += now_s() - t0; running = false; } }
+double Profiler::elapsed() const { return t_total + (running ? now_s() - t0 : 0.0); }
+std::string Profiler::toString(double s) { std::ostringstream o; o << std::fixed << std::setprecision(6) << s; return o.str(); }
+void Profiler::render(std::ostream& o) {
+  o << name << ": " << toString(elapsed()) << " s" << std::endl;
+  if (!ctx) return;
+  int32_t n = 0;
+  hcg_timers(ctx, nullptr, &n);
+  std::vector<hcg_timer> t((size_t)std::max(n, 1));
+  hcg_timers(ctx, t.data(), &n);
+  o << "  iterate (device operators, CUDA events)" << std::endl;
+  for (int i = 0; i < n; i++)
+    o << "    " << std::left << std::setw(34) << t[i].name << " " << toString(t[i].ms_total*1e-3) << " s  (" << t[i].calls << " calls)" << std::endl;
+}
+void Profiler::printStatistics() { std::ostringstream o; render(o); hlog << o.str(); }
+void Profiler::outputStatistics() {
+  if (!plb::global::mpi().isMainProcessor() || hlog.filename.empty()) return;
+  std::ofstream f(hlog.filename + ".statistics");
+  render(f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cell types
+// ------------------------------------------------------------------------------------------------
+struct CellTypeImpl {
+  host::CellTypeTables tables;
+  host::MaterialModel material;
+  int device_ctype = -1;
+  int device_generation = -1;                 // GpuLattice::generation the type was uploaded to
+  int64_t n_cells_loaded = 0;
+};
+
+static host::MaterialModel read_material(Config& m, int constructType) {
+  host::MaterialModel mm;
+  XMLElement mat = m["MaterialModel"];
+  mm.kBend = mat["kBend"].read<T>(); mm.kVolume = mat["kVolume"].read<T>(); mm.kArea = mat["kArea"].read<T>();
+  mm.kLink = mat["kLink"].read<T>();
+  try { mm.eta_m = mat["eta_m"].read<T>(); } catch (std::invalid_argument&) { mm.eta_m = 0; }
+  mm.radius = mat["radius"].read<T>();
+  mm.minNumTriangles = (int)mat["minNumTriangles"].read<T>();
+  if (constructType == ELLIPSOID_FROM_SPHERE) mm.aspectRatio = mat["aspectRatio"].read<T>();
+  try { mm.volume = mat["Volume"].read<T>(); } catch (std::invalid_argument&) {}
+  // <InnerEdges><Edge> a b </Edge>...</InnerEdges> (mechanics/commonCellConstants.cpp:359-375)
+  try {
+    XMLElement ie = mat["InnerEdges"];
+    for (auto& ch : ie.getOrig()->children) {
+      if (ch->name != "Edge") continue;
+      std::stringstream ss(ch->text); int a, b;
+      if (ss >> a >> b) mm.innerEdges.push_back({a, b});
+    }
+  } catch (std::invalid_argument&) {}
+  return mm;
+}
+
+HemoCellField::HemoCellField(HemoCellFields& cellFields_, const std::string& name_, unsigned int ctype_, int constructType_)
+    : name(name_), cellFields(cellFields_), desiredOutputVariables({OUTPUT_POSITION}), ctype((unsigned char)ctype_), constructType(constructType_) {
+  if (ctype_ > 255) fatal("(HemoCell) (AddCellType) more celltypes than UCHAR_MAX (255) added, please convert celltype to int or add less celltypes");
+  if (constructType != RBC_FROM_SPHERE && constructType != ELLIPSOID_FROM_SPHERE)
+    fatal("(HemoCell) (AddCellType) only RBC_FROM_SPHERE and ELLIPSOID_FROM_SPHERE meshes are built in");
+  materialCfg = new Config(name + ".xml");
+  impl = new CellTypeImpl();
+  impl->material = read_material(*materialCfg, constructType);
+  host::Parameters p;
+  p.lbm_base_parameters(param::dx, param::dt < 0 ? -1.0 : param::dt, param::nu_p, param::rho_p, param::kBT_p);
+  // model id is fixed once the mechanics object exists (HemoCell::addCellType); tables do not depend on it
+  impl->tables.build(HCG_MODEL_RBC_HIGHORDER, constructType, impl->material, p);
+  numVertex = impl->tables.mesh.getNumVertices();
+  for (auto& t : impl->tables.cc.triangle_list) triangle_list.push_back({{t[0], t[1], t[2]}});
+  volume = impl->material.volume;
+  if (volume > 0) volumeFractionOfLspPerNode = (volume/numVertex)/std::pow(param::dx*1e6, 3);
+  else hlog << "(HemoCell) (WARNING) (AddCellType) Volume of celltype " << name << " not present, volume set to zero" << endl;
+}
+HemoCellField::~HemoCellField() { delete mechanics; delete materialCfg; delete impl; }
+void HemoCellField::setOutputVariables(const vector<int>& outputs) {
+  desiredOutputVariables = outputs;
+  auto it = std::find(desiredOutputVariables.begin(), desiredOutputVariables.end(), OUTPUT_TRIANGLES);
+  if (it != desiredOutputVariables.end()) { desiredOutputVariables.erase(it); outputTriangles = true; } else outputTriangles = false;
+}
+void HemoCellField::statistics() {
+  hlog << "Cellfield  (+ material model) of " << name << endl;
+  hlog << "  timescale separation: " << timescale << endl;
+  if (mechanics) mechanics->statistics();
+}
+int HemoCellField::getNumberOfCells_Global() { return (int)CellInformationFunctionals::getNumberOfCellsFromType(&cellFields.hemocell, name); }
+T HemoCellField::getVolumeFraction() {
+  auto box = cellFields.lattice->getBoundingBox();
+  return getNumberOfCells_Global()*volume/(box.nCells()*std::pow(param::dx*1e6, 3));
+}
+
+// CellMechanics --------------------------------------------------------------------------------------
+static CommonCellConstantsView make_view(HemoCellField& f) {
+  CommonCellConstantsView v;
+  const host::CommonCellConstants& cc = f.impl->tables.cc;
+  for (auto& t : cc.triangle_list) v.triangle_list.push_back({{t[0], t[1], t[2]}});
+  for (auto& e : cc.edge_list) v.edge_list.push_back({{e[0], e[1]}});
+  v.edge_length_eq_list = cc.edge_length_eq_list; v.edge_angle_eq_list = cc.edge_angle_eq_list;
+  v.triangle_area_eq_list = cc.triangle_area_eq_list; v.surface_patch_center_dist_eq_list = cc.surface_patch_center_dist_eq_list;
+  v.volume_eq = cc.volume_eq; v.area_mean_eq = cc.area_mean_eq; v.edge_mean_eq = cc.edge_mean_eq; v.angle_mean_eq = cc.angle_mean_eq;
+  return v;
+}
+CellMechanics::CellMechanics(HemoCellField& cellfield, Config& modelCfg_) : cellConstants(make_view(cellfield)), cfg(modelCfg_), field_(cellfield) {}
+T CellMechanics::calculate_kLink(Config& c) { return c["MaterialModel"]["kLink"].read<T>() * param::kBT_lbm/(7.5e-9/param::dx); }
+T CellMechanics::calculate_kBend(Config& c) { return c["MaterialModel"]["kBend"].read<T>() * param::kBT_lbm/(5e-7/param::dx); }
+T CellMechanics::calculate_kVolume(Config& c) {
+  return c["MaterialModel"]["kVolume"].read<T>() * (1280.0/cellConstants.triangle_list.size()) * param::kBT_lbm/(5e-7/param::dx);
+}
+T CellMechanics::calculate_kArea(Config& c) {
+  return c["MaterialModel"]["kArea"].read<T>() * (1280.0/cellConstants.triangle_list.size()) * param::kBT_lbm/(5e-7/param::dx);
+}
+T CellMechanics::calculate_etaM(Config& c) {
+  T eta = 0; try { eta = c["MaterialModel"]["eta_m"].read<T>(); } catch (std::invalid_argument&) {}
+  return eta * param::dx/param::dt/param::df;
+}
+
+static void device_only(const char* model) {
+  fatal(std::string("(HemoCell) (") + model + ") ParticleMechanics(map<...>) is the reference's host interface; this model runs as the device kernel k_mechanics "
+        "inside HemoCellFields::applyConstitutiveModel()");
+}
+RbcHighOrderModel::RbcHighOrderModel(Config& modelCfg_, HemoCellField& cellField_)
+    : CellMechanics(cellField_, modelCfg_), cellField(cellField_), k_volume(calculate_kVolume(modelCfg_)), k_area(calculate_kArea(modelCfg_)),
+      k_link(calculate_kLink(modelCfg_)), k_bend(calculate_kBend(modelCfg_)), eta_m(calculate_etaM(modelCfg_)) {}
+void RbcHighOrderModel::ParticleMechanics(std::map<int, std::vector<HemoCellParticle*>>&, const std::map<int, bool>&, pluint) { device_only("RbcHighOrderModel"); }
+void RbcHighOrderModel::statistics() {
+  hlog << "(Cell-mechanics model) High Order model parameters for " << cellField.name << " cellfield" << std::endl;
+  hlog << "\t k_link:   " << k_link << std::endl; hlog << "\t k_area:   " << k_area << std::endl;
+  hlog << "\t k_bend: : " << k_bend << std::endl; hlog << "\t k_volume: " << k_volume << std::endl;
+  hlog << "\t eta_m:    " << eta_m << std::endl;
+}
+PltSimpleModel::PltSimpleModel(Config& modelCfg_, HemoCellField& cellField_)
+    : CellMechanics(cellField_, modelCfg_), cellField(cellField_), k_volume(calculate_kVolume(modelCfg_)), k_area(calculate_kArea(modelCfg_)),
+      k_link(calculate_kLink(modelCfg_)), k_bend(calculate_kBend(modelCfg_)), eta_m(calculate_etaM(modelCfg_)) {}
+void PltSimpleModel::ParticleMechanics(std::map<int, std::vector<HemoCellParticle*>>&, const std::map<int, bool>&, pluint) { device_only("PltSimpleModel"); }
+void PltSimpleModel::statistics() {
+  hlog << "(Cell-mechanics model) Reduced-model parameters for " << cellField.name << " cellfield" << std::endl;
+  hlog << "\t k_link:   " << k_link << std::endl; hlog << "\t k_area:   " << k_area << std::endl;
+  hlog << "\t k_bend: : " << k_bend << std::endl; hlog << "\t k_volume: " << k_volume << std::endl;
+  hlog << "\t eta_m:    " << eta_m << std::endl;
+}
+
+// HemoCellFields ---------------------------------------------------------------------------------------
+HemoCellFields::HemoCellFields(plb::MultiBlockLattice3D<T, DESCRIPTOR>& lattice_, unsigned int particleEnvelopeWidth, HemoCell& hemocell_)
+    : lattice(&lattice_), envelopeSize(particleEnvelopeWidth), hemocell(hemocell_) {}
+HemoCellFields::~HemoCellFields() { for (auto* f : cellFields) delete f; }
+hcg_ctx* HemoCellFields::ctx() { return hemocell.ctx(); }
+HemoCellField* HemoCellFields::addCellType(const std::string& name_, int constructType) {
+  HemoCellField* f = new HemoCellField(*this, name_, (unsigned int)cellFields.size(), constructType);
+  cellFields.push_back(f);
+  return f;
+}
+HemoCellField* HemoCellFields::operator[](const std::string& name) {
+  for (auto* f : cellFields) if (f->name == name) return f;
+  fatal("(HemoCell) (CellField) cell type " + name + " does not exist");
+}
+void HemoCellFields::advanceParticles() { ck(ctx(), hcg_op_advance(ctx()), "advanceParticles"); }
+void HemoCellFields::interpolateFluidVelocity() { ck(ctx(), hcg_op_interpolate(ctx()), "interpolateFluidVelocity"); }
+void HemoCellFields::spreadParticleForce() { ck(ctx(), hcg_op_spread(ctx()), "spreadParticleForce"); }
+void HemoCellFields::applyRepulsionForce() { ck(ctx(), hcg_op_repulsion(ctx()), "applyRepulsionForce"); }
+void HemoCellFields::applyBoundaryRepulsionForce() { ck(ctx(), hcg_op_wall_repulsion(ctx()), "applyBoundaryRepulsionForce"); }
+void HemoCellFields::applyConstitutiveModel(bool forced) { ck(ctx(), hcg_op_mechanics(ctx(), forced ? 1 : 0, separateForces ? 1 : 0), "applyConstitutiveModel"); }
+void HemoCellFields::syncEnvelopes() { ck(ctx(), hcg_op_sync(ctx()), "syncEnvelopes"); }
+void HemoCellFields::getParticles(vector<HemoCellParticle>& particles) {
+  particles.clear();
+  hcg_ctx* c = ctx();
+  int64_t nc = 0, np = 0;
+  ck(c, hcg_cells_capacity(c, &nc, &np), "hcg_cells_capacity");
+  if (np == 0) return;
+  std::vector<double> pos(3*np), vel(3*np), frc(3*np), frep(3*np);
+  ck(c, hcg_cells_download(c, HCG_P_POS, pos.data()), "download"); ck(c, hcg_cells_download(c, HCG_P_VEL, vel.data()), "download");
+  ck(c, hcg_cells_download(c, HCG_P_FORCE, frc.data()), "download"); ck(c, hcg_cells_download(c, HCG_P_FREP, frep.data()), "download");
+  std::vector<int64_t> ids(nc); std::vector<int32_t> types(nc); std::vector<uint8_t> alive(nc);
+  ck(c, hcg_cells_info(c, ids.data(), types.data(), alive.data()), "hcg_cells_info");
+  int64_t p = 0;
+  for (int64_t k = 0; k < nc; k++) {
+    const int V = cellFields[types[k]]->numVertex;
+    if (alive[k] && ids[k] >= 0) for (int v = 0; v < V; v++) {
+      HemoCellParticle q;
+      for (int d = 0; d < 3; d++) { q.sv.position[d] = pos[3*(p+v)+d]; q.sv.v[d] = vel[3*(p+v)+d]; q.sv.force[d] = frc[3*(p+v)+d]; q.sv.force_repulsion[d] = frep[3*(p+v)+d]; }
+      q.sv.cellId = ids[k]; q.sv.vertexId = (uint16_t)v; q.sv.restime = 0; q.sv.celltype = (unsigned char)types[k];
+      particles.push_back(q);
+    }
+    p += V;
+  }
+}
+
+// HemoCell ---------------------------------------------------------------------------------------------
+HemoCell::HemoCell(char* configFileName, int argc, char* argv[]) {
+  plb::plbInit(&argc, &argv);
+  if (global.hemoCellInitialized) { pcout << "(HemoCell) (Error) Hemocell object already created, refusing to construct another one" << endl; exit(1); }
+  global.hemoCellInitialized = true;
+  pcout << "(HemoCell) (Config) reading " << configFileName << endl;
+  cfg = new Config(configFileName);
+  if (cfg->checkpointed) pcout << "(HemoCell) (Config) Checkpointed config, deferring the loading of the directories (out,log,checkpoint) until loadCheckpoint is called" << endl;
+  else loadDirectories(cfg);
+  try { global.cellsDeletedInfo = (*cfg)["verbose"]["cellsDeletedInfo"].read<int>() != 0; } catch (std::invalid_argument&) {}
+  hlog << "(HemoCell) B200-native build: " << hcg_version() << endl;
+  global.statistics.start();
+}
+HemoCell::~HemoCell() {
+  delete cellfields; delete cfg; delete lattice;
+  global.statistics.setDeviceTimers(nullptr);
+  global.hemoCellInitialized = false;
+}
+hcg_ctx* HemoCell::ctx() {
+  if (!lattice) fatal("(HemoCell) please create a lattice first");
+  lattice->gpu()->materialize();
+  return lattice->gpu()->ctx;
+}
+void HemoCell::latticeEquilibrium(T rho, hemo::Array<T, 3> vel) {
+  hlog << "(HemoCell) (Fluid) Setting Fluid Equilibrium" << endl;
+  plb::initializeAtEquilibrium(*lattice, lattice->getBoundingBox(), rho, plb::Array<T, 3>(vel[0], vel[1], vel[2]));
+}
+void HemoCell::initializeCellfield() {
+  if (!lattice) fatal("(HemoCell) (CellField) please create a lattice before initializing the cellfield");
+  cellfields = new HemoCellFields(*lattice, (*cfg)["domain"]["particleEnvelope"].read<int>(), *this);
+}
+void HemoCell::registerCellType(HemoCellField* f) {
+  if (f->mechanics->deviceModel() < 0) fatal("(HemoCell) (AddCellType) " + f->name + ": this mechanics class has no device kernel (deviceModel() < 0)");
+  f->impl->tables.c.model = f->mechanics->deviceModel();
+}
+// cell types go to the device when it is first needed (the periodicity may be toggled until then,
+// which re-creates the context: hemocell.setSystemPeriodicity comes after addCellType in the case files)
+static void upload_celltypes(HemoCell& h) {
+  hcg_ctx* c = h.ctx();
+  const int gen = h.lattice->gpu()->generation;
+  for (auto* f : h.cellfields->cellFields) {
+    if (f->impl->device_generation == gen) continue;
+    hcg_celltype t = f->impl->tables.c;
+    // the k_* members of the model object are authoritative (a case may derive its own values)
+    if (auto* m = dynamic_cast<RbcHighOrderModel*>(f->mechanics)) { t.k_volume = m->k_volume; t.k_area = m->k_area; t.k_link = m->k_link; t.k_bend = m->k_bend; t.eta_m = m->eta_m; }
+    else if (auto* m2 = dynamic_cast<PltSimpleModel*>(f->mechanics)) { t.k_volume = m2->k_volume; t.k_area = m2->k_area; t.k_link = m2->k_link; t.k_bend = m2->k_bend; t.eta_m = m2->eta_m; }
+    int32_t id = -1;
+    ck(c, hcg_celltype_add(c, &t, &id), "hcg_celltype_add");
+    f->impl->device_ctype = id; f->impl->device_generation = gen;
+  }
+  ck(c, hcg_set_force_limit(c, param::f_limit), "hcg_set_force_limit");
+}
+void HemoCell::setOutputs(std::string name, vector<int> outputs) {
+  hlog << "(HemoCell) (CellField) Setting output variables for " << name << " cells" << endl;
+  (*cellfields)[name]->setOutputVariables(outputs);
+}
+void HemoCell::setFluidOutputs(vector<int> outputs) {
+  hlog << "(HemoCell) (Fluid) Setting output variables for fluid field" << endl;
+  cellfields->desiredFluidOutputVariables = outputs;
+}
+void HemoCell::setRepulsion(T repulsionConstant, T repulsionCutoff) {
+  hlog << "(HemoCell) (Repulsion) Setting repulsion constant to " << repulsionConstant << ". repulsionCutoff to" << repulsionCutoff << " µm" << endl;
+  hlogfile << "(HemoCell) (Repulsion) Enabling repulsion." << endl;
+  cellfields->repulsionConstant = repulsionConstant;
+  cellfields->repulsionCutoff = repulsionCutoff*(1e-6/param::dx);
+  repulsionEnabled = true;
+}
+void HemoCell::enableBoundaryParticles(T k, T cutoff, unsigned int timestep) {
+  hlog << "(HemoCell) (Repulsion) Setting boundary repulsion constant to " << k << ". boundary repulsionCutoff to" << cutoff << " µm" << endl;
+  hlogfile << "(HemoCell) (Repulsion) Enabling boundary repulsion" << endl;
+  cellfields->boundaryRepulsionConstant = k;
+  cellfields->boundaryRepulsionCutoff = cutoff*(1e-6/param::dx);
+  cellfields->boundaryRepulsionTimescale = timestep;
+  boundaryRepulsionEnabled = true;
+}
+void HemoCell::setMaterialTimeScaleSeparation(std::string name, unsigned int separation) {
+  hlog << "(HemoCell) (Timescale Seperation) Setting seperation of " << name << " to " << separation << " timesteps" << endl;
+  (*cellfields)[name]->timescale = separation;
+}
+void HemoCell::setParticleVelocityUpdateTimeScaleSeparation(unsigned int separation) {
+  hlog << "(HemoCell) (Timescale separation) Setting update separation of all particles to " << separation << " timesteps" << endl;
+  hlogfile << "(HemoCell) WARNING this introduces curvature artifacts. Make sure, it is smaller than material timescale separation!" << endl;
+  cellfields->particleVelocityUpdateTimescale = separation;
+}
+void HemoCell::setRepulsionTimeScaleSeperation(unsigned int separation) {
+  hlog << "(HemoCell) (Repulsion Timescale Seperation) Setting seperation to " << separation << " timesteps" << endl;
+  cellfields->repulsionTimescale = separation;
+}
+void HemoCell::setInitialMinimumDistanceFromSolid(std::string name, T distance) {
+  hlog << "(HemoCell) (Set Distance) Setting minimum distance from solid to " << distance << " micrometer for " << name << endl;
+  if (loadParticlesIsCalled) pcout << "(HemoCell) (Set Distance) WARNING: this function is called after the particles are loaded, so it has no effect!" << endl;
+  (*cellfields)[name]->minimumDistanceFromSolid = distance;
+}
+void HemoCell::setSystemPeriodicity(unsigned int axis, bool bePeriodic) {
+  if (lattice == nullptr) { pcerr << "(HemoCell) (Periodicity) please create a lattice before trying to set the periodicity" << endl; exit(1); }
+  if (cellfields == nullptr) { pcerr << "(HemoCell) (Periodicity) please create a particlefield (hemocell.initializeCellfields()) before trying to set the periodicity" << endl; exit(1); }
+  lattice->periodicity().toggle(axis, bePeriodic);
+}
+void HemoCell::setSystemPeriodicityLimit(unsigned int axis, int limit) {
+  hlog << "(HemoCell) (Periodicity) Setting periodicity limit of axis " << axis << " to " << limit << endl;
+  cellfields->periodicity_limit[axis] = limit;
+}
+void HemoCell::initializeLattice(const plb::MultiBlockManagement3D& management) {
+  delete lattice;
+  hlog << "(HemoCell) Using default domain management." << endl;
+  lattice = new plb::MultiBlockLattice3D<T, DESCRIPTOR>(management, nullptr, nullptr, nullptr,
+                                                        new plb::GuoExternalForceBGKdynamics<T, DESCRIPTOR>(1.0/param::tau));
+}
+
+// settings that live in host-side knobs until the device needs them
+void HemoCell::pushSettings() {
+  hcg_ctx* c = ctx();
+  upload_celltypes(*this);
+  ck(c, hcg_set_timescales(c, (int)cellfields->particleVelocityUpdateTimescale, (int)cellfields->repulsionTimescale,
+                           (int)cellfields->boundaryRepulsionTimescale), "hcg_set_timescales");
+  for (auto* f : cellfields->cellFields) ck(c, hcg_set_material_timescale(c, f->impl->device_ctype, (int)f->timescale), "hcg_set_material_timescale");
+  ck(c, hcg_set_repulsion(c, repulsionEnabled, cellfields->repulsionConstant, repulsionEnabled ? cellfields->repulsionCutoff : 1.0), "hcg_set_repulsion");
+  ck(c, hcg_set_wall_repulsion(c, boundaryRepulsionEnabled, cellfields->boundaryRepulsionConstant,
+                               boundaryRepulsionEnabled ? cellfields->boundaryRepulsionCutoff : 1.0), "hcg_set_wall_repulsion");
+  ck(c, hcg_set_iteration(c, iter), "hcg_set_iteration");
+}
+
+void HemoCell::loadParticles() {
+  hlog << "(HemoCell) (CellField) Loading particle positions " << endl;
+  loadParticlesIsCalled = true;
+  hcg_ctx* c = ctx();
+  upload_celltypes(*this);
+  GpuLattice* g = lattice->gpu();
+  int64_t cellid = 0;                                  // one counter over the .pos files of all types (readPositionsBloodCells.cpp:204-228)
+  for (auto* f : cellfields->cellFields) {
+    std::vector<std::array<T, 6>> rows;
+    try { rows = host::readPositionsFile(f->name + ".pos"); }
+    catch (std::invalid_argument&) { cout << "*** WARNING! particle positions input file " << f->name << ".pos does not exist!" << endl; }
+    hlog << "(readPositionsBloodCells) Particle count in file (" << f->name << "): " << rows.size() << "." << endl;
+    std::vector<T> pos;
+    std::vector<int64_t> ids = host::placeCells(f->impl->tables.mesh, rows, param::dx, g->nx, g->ny, g->nz, g->flags.data(),
+                                                f->minimumDistanceFromSolid, cellid, pos);
+    cellid += (int64_t)rows.size();
+    g->has_cells = g->has_cells || !ids.empty();
+    ck(c, hcg_cells_add(c, f->impl->device_ctype, (int64_t)ids.size(), ids.data(), pos.data()), "hcg_cells_add");
+    f->impl->n_cells_loaded = (int64_t)ids.size();
+    hlog << "(readPositionsBloodCells) " << ids.size() << " " << f->name << " cells placed inside the domain." << endl;
+  }
+  cellfields->number_of_cells = cellid;
+}
+
+void HemoCell::sanityCheck() {
+  // core/hemoCell.cpp:600-627: material / repulsion cadences must be multiples of the velocity cadence
+  hlog << "(HemoCell) (SanityCheck) Performing Sanity check on simulation parameters and setup" << endl;
+  for (auto* f : cellfields->cellFields)
+    if (f->timescale % cellfields->particleVelocityUpdateTimescale != 0)
+      fatal("(HemoCell) (SanityCheck) Error, Velocity timescale separation cannot divide this material timescale separation, exiting ...");
+  if (repulsionEnabled && cellfields->repulsionTimescale % cellfields->particleVelocityUpdateTimescale != 0)
+    fatal("(HemoCell) (SanityCheck) Error, Velocity timescale separation cannot divide this repulsion timescale separation, exiting ...");
+  if (param::tau < 0.5 || param::tau > 2.0) hlog << "(HemoCell) (SanityCheck) WARNING: tau = " << param::tau << " is outside of the recommended range (0.5, 2.0]" << endl;
+  pushSettings();
+  sanityCheckDone = true;
+}
+
+void HemoCell::iterate() {
+  if (!sanityCheckDone) sanityCheck();
+  hcg_ctx* c = ctx();
+  ck(c, hcg_iterate(c, 1), "hcg_iterate");
+  iter++;
+}
+
+void HemoCell::saveCheckPoint() {
+  hlog << "(HemoCell) (Saving Functions) Saving Checkpoint at timestep " << iter << endl;
+  hcg_ctx* c = ctx();
+  GpuLattice* g = lattice->gpu();
+  const std::string dir = plb::global::directories().getOutputDir() + "/checkpoint/";
+  if (plb::global::mpi().isMainProcessor()) mkpath(dir);
+  plb::global::mpi().barrier();
+  const std::string base = dir + "rank" + std::to_string(plb::global::mpi().getRank());
+  // keep the previous checkpoint as .old (core/hemoCellFields.cpp:240-262)
+  if (file_exists(base + ".bin")) rename((base + ".bin").c_str(), (base + ".bin.old").c_str());
+  std::ofstream f(base + ".bin", std::ios::binary);
+  const int64_t Nl = (int64_t)g->nxl()*g->ny*g->nz;
+  int64_t nc = 0, np = 0;
+  ck(c, hcg_cells_capacity(c, &nc, &np), "hcg_cells_capacity");
+  const int64_t hdr[6] = {0x48434731, (int64_t)iter, Nl, nc, np, (int64_t)cellfields->size()};
+  f.write((const char*)hdr, sizeof(hdr));
+  std::vector<double> buf((size_t)std::max<int64_t>(19*Nl, 3*np));
+  ck(c, hcg_lattice_download(c, HCG_LAT_POP, buf.data()), "download"); f.write((const char*)buf.data(), 8*19*Nl);
+  ck(c, hcg_lattice_download(c, HCG_LAT_FORCE, buf.data()), "download"); f.write((const char*)buf.data(), 8*3*Nl);
+  for (int fld : {HCG_P_POS, HCG_P_VEL, HCG_P_FORCE, HCG_P_FREP}) { ck(c, hcg_cells_download(c, fld, buf.data()), "download"); f.write((const char*)buf.data(), 8*3*np); }
+  std::vector<int64_t> ids(nc); std::vector<int32_t> types(nc); std::vector<uint8_t> alive(nc);
+  ck(c, hcg_cells_info(c, ids.data(), types.data(), alive.data()), "hcg_cells_info");
+  f.write((const char*)ids.data(), 8*nc); f.write((const char*)types.data(), 4*nc); f.write((const char*)alive.data(), nc);
+  f.close();
+  if (plb::global::mpi().isMainProcessor()) {
+    // checkpoint.xml: <Checkpoint><General><Iteration>..</Iteration></General> + the original <hemocell> tree (config/config.cpp:53-78)
+    xml::Node root; xml::Node* cp = root.addChild("Checkpoint");
+    cp->addChild("General")->addChild("Iteration", std::to_string(iter));
+    std::function<void(const xml::Node*, xml::Node*)> copy = [&](const xml::Node* s, xml::Node* d) {
+      for (auto& ch : s->children) { xml::Node* n = d->addChild(ch->name, ch->text); n->attributes = ch->attributes; copy(ch.get(), n); }
+    };
+    const xml::Node* src = cfg->checkpointed ? cfg->root()->firstChild("Checkpoint") : cfg->root();
+    if (const xml::Node* h = src->firstChild("hemocell")) copy(h, cp->addChild("hemocell"));
+    if (file_exists(dir + "checkpoint.xml")) rename((dir + "checkpoint.xml").c_str(), (dir + "checkpoint.xml.old").c_str());
+    std::ofstream x(dir + "checkpoint.xml"); x << xml::serialize(root);
+  }
+}
+
+void HemoCell::loadCheckPoint() {
+  hlog << "(HemoCell) (Saving Functions) Loading Checkpoint" << endl;
+  if (!cfg->checkpointed) fatal("(HemoCell) loadCheckPoint() needs a checkpoint.xml as configuration file");
+  loadDirectories(cfg, false);
+  hcg_ctx* c = ctx();
+  upload_celltypes(*this);
+  GpuLattice* g = lattice->gpu();
+  const xml::Node* cp = cfg->root()->firstChild("Checkpoint");
+  iter = (unsigned int)XMLElement(cp)["General"]["Iteration"].read<unsigned long>();
+  std::string dir = global.checkpointDirectory;
+  try { dir = XMLElement(cp)["General"]["Directory"].read<std::string>(); } catch (std::invalid_argument&) {}
+  const std::string base = dir + "/rank" + std::to_string(plb::global::mpi().getRank()) + ".bin";
+  std::ifstream f(base, std::ios::binary);
+  if (!f) fatal("(HemoCell) cannot open checkpoint data " + base);
+  int64_t hdr[6]; f.read((char*)hdr, sizeof(hdr));
+  const int64_t Nl = (int64_t)g->nxl()*g->ny*g->nz;
+  if (hdr[0] != 0x48434731 || hdr[2] != Nl || hdr[5] != (int64_t)cellfields->size()) fatal("(HemoCell) checkpoint does not match this domain / cell types");
+  const int64_t nc = hdr[3], np = hdr[4];
+  std::vector<double> pop(19*Nl), frc(3*Nl);
+  f.read((char*)pop.data(), 8*19*Nl); f.read((char*)frc.data(), 8*3*Nl);
+  std::vector<double> P[4];
+  for (auto& v : P) { v.resize(3*np); f.read((char*)v.data(), 8*3*np); }
+  std::vector<int64_t> ids(nc); std::vector<int32_t> types(nc); std::vector<uint8_t> alive(nc);
+  f.read((char*)ids.data(), 8*nc); f.read((char*)types.data(), 4*nc); f.read((char*)alive.data(), nc);
+  // re-create the cells slot by slot (live ones only; slot order = type order), then overwrite the state
+  std::vector<int64_t> base_of(nc); { int64_t p = 0; for (int64_t k = 0; k < nc; k++) { base_of[k] = p; p += (*cellfields)[(unsigned)types[k]]->numVertex; } }
+  std::vector<double> vel, force, frep;
+  for (auto* fl : cellfields->cellFields) {
+    std::vector<int64_t> tid; std::vector<double> tpos;
+    for (int64_t k = 0; k < nc; k++) if (types[k] == fl->impl->device_ctype && alive[k] && ids[k] >= 0) {
+      tid.push_back(ids[k]);
+      const int V = fl->numVertex;
+      tpos.insert(tpos.end(), P[0].begin() + 3*base_of[k], P[0].begin() + 3*(base_of[k] + V));
+      vel.insert(vel.end(), P[1].begin() + 3*base_of[k], P[1].begin() + 3*(base_of[k] + V));
+      force.insert(force.end(), P[2].begin() + 3*base_of[k], P[2].begin() + 3*(base_of[k] + V));
+      frep.insert(frep.end(), P[3].begin() + 3*base_of[k], P[3].begin() + 3*(base_of[k] + V));
+    }
+    ck(c, hcg_cells_add(c, fl->impl->device_ctype, (int64_t)tid.size(), tid.data(), tpos.data()), "hcg_cells_add");
+    g->has_cells = g->has_cells || !tid.empty();
+  }
+  if (plb::global::mpi().getSize() == 1 && !vel.empty()) {
+    ck(c, hcg_cells_upload(c, HCG_P_VEL, vel.data()), "upload"); ck(c, hcg_cells_upload(c, HCG_P_FORCE, force.data()), "upload");
+    ck(c, hcg_cells_upload(c, HCG_P_FREP, frep.data()), "upload");
+  }
+  ck(c, hcg_lattice_upload(c, HCG_LAT_POP, pop.data()), "upload"); ck(c, hcg_lattice_upload(c, HCG_LAT_FORCE, frc.data()), "upload");
+  g->eq_pending = false; g->body_pending = false;
+  loadParticlesIsCalled = true;
+}
+
+void HemoCell::writeOutput() {
+  const double el = global.statistics.elapsed();
+  const std::string tpi = (iter != lastOutputAt) ? Profiler::toString((el - lastOutput)/(iter - lastOutputAt)) : "0.00";
+  lastOutput = el; lastOutputAt = iter;
+  pcout << "(HemoCell) (Output) writing output at timestep " << iter << " (" << param::dt * iter << " s). Approx. performance: " << tpi << " s / iteration." << endl;
+  if (!sanityCheckDone) pushSettings();
+  hcg_ctx* c = ctx();
+  // the reference recomputes repulsion and (forced) membrane forces at every output: part of the trajectory (core/hemoCell.cpp:236-262)
+  if (repulsionEnabled) cellfields->applyRepulsionForce();
+  if (boundaryRepulsionEnabled) cellfields->applyBoundaryRepulsionForce();
+  cellfields->separate_force_vectors();
+  cellfields->applyConstitutiveModel(true);
+  const std::string out = plb::global::directories().getOutputDir();
+  if (plb::global::mpi().isMainProcessor()) { mkpath(out + "/hdf5/" + zeroPadNumber(iter)); mkpath(out + "/csv"); }
+  plb::global::mpi().barrier();
+  // CSV cell info (io/writeCellInfoCSV.cpp:47-70); the HDF5 field/particle files are SURVEY.md 8(f1), not written yet
+  CellInformationFunctionals::calculateCellInformation(this);
+  if (plb::global::mpi().getSize() == 1) {
+    std::vector<std::ofstream> csv(cellfields->size());
+    for (unsigned i = 0; i < cellfields->size(); i++) {
+      csv[i].open(out + "/csv/" + (*cellfields)[i]->name + "." + zeroPadNumber(iter) + ".csv", std::ofstream::trunc);
+      csv[i] << "X,Y,Z,area,volume,atomic_block,cellId,baseCellId,velocity_x,velocity_y,velocity_z" << endl;
+    }
+    for (auto& pr : CellInformationFunctionals::info_per_cell) {
+      CellInformation ci = pr.second;
+      if (outputInSiUnits) { ci.position *= param::dx; ci.area *= param::dx*param::dx; ci.velocity *= param::dx/param::dt; ci.volume *= param::dx*param::dx*param::dx; }
+      auto& o = csv[ci.cellType];
+      o << ci.position[0] << "," << ci.position[1] << "," << ci.position[2] << "," << ci.area << "," << ci.volume << "," << ci.blockId << ","
+        << pr.first << "," << ci.base_cell_id << "," << ci.velocity[0] << "," << ci.velocity[1] << "," << ci.velocity[2] << endl;
+    }
+  }
+  cellfields->unify_force_vectors();
+  (void)c;
+}
+
+// CellInformationFunctionals / FluidInfo ------------------------------------------------------------------
+namespace {
+struct CellSnapshot {
+  int64_t nc = 0, np = 0;
+  std::vector<int64_t> ids, base; std::vector<int32_t> types; std::vector<uint8_t> alive;
+};
+CellSnapshot snapshot(HemoCell* h) {
+  CellSnapshot s; hcg_ctx* c = h->ctx();
+  ck(c, hcg_cells_capacity(c, &s.nc, &s.np), "hcg_cells_capacity");
+  s.ids.resize(s.nc); s.types.resize(s.nc); s.alive.resize(s.nc); s.base.resize(s.nc);
+  if (s.nc) ck(c, hcg_cells_info(c, s.ids.data(), s.types.data(), s.alive.data()), "hcg_cells_info");
+  int64_t p = 0;
+  for (int64_t k = 0; k < s.nc; k++) { s.base[k] = p; p += (*h->cellfields)[(unsigned)s.types[k]]->numVertex; }
+  return s;
+}
+CellInformation& entry(const CellSnapshot& s, int64_t k) {
+  CellInformation& ci = CellInformationFunctionals::info_per_cell[(int)s.ids[k]];
+  ci.cellType = (pluint)s.types[k]; ci.base_cell_id = (int)s.ids[k]; ci.blockId = (pluint)plb::global::mpi().getRank();
+  return ci;
+}
+}  // namespace
+void CellInformationFunctionals::calculateCellVolume(HemoCell* h) {
+  CellSnapshot s = snapshot(h); if (!s.nc) return;
+  std::vector<double> vol(s.nc), area(s.nc);
+  ck(h->ctx(), hcg_cells_volume_area(h->ctx(), vol.data(), area.data()), "hcg_cells_volume_area");
+  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0) entry(s, k).volume = vol[k];
+}
+void CellInformationFunctionals::calculateCellArea(HemoCell* h) {
+  CellSnapshot s = snapshot(h); if (!s.nc) return;
+  std::vector<double> vol(s.nc), area(s.nc);
+  ck(h->ctx(), hcg_cells_volume_area(h->ctx(), vol.data(), area.data()), "hcg_cells_volume_area");
+  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0) entry(s, k).area = area[k];
+}
+void CellInformationFunctionals::calculateCellBoundingBox(HemoCell* h) {
+  CellSnapshot s = snapshot(h); if (!s.nc) return;
+  std::vector<double> bb(6*s.nc);
+  ck(h->ctx(), hcg_cells_bbox(h->ctx(), bb.data()), "hcg_cells_bbox");
+  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0) for (int d = 0; d < 6; d++) entry(s, k).bbox[d] = bb[6*k + d];
+}
+void CellInformationFunctionals::calculateCellPosition(HemoCell* h) {
+  CellSnapshot s = snapshot(h); if (!s.np) return;
+  std::vector<double> pos(3*s.np), vel(3*s.np);
+  ck(h->ctx(), hcg_cells_download(h->ctx(), HCG_P_POS, pos.data()), "download");
+  ck(h->ctx(), hcg_cells_download(h->ctx(), HCG_P_VEL, vel.data()), "download");
+  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0) {
+    const int V = (*h->cellfields)[(unsigned)s.types[k]]->numVertex;
+    CellInformation& ci = entry(s, k);
+    for (int d = 0; d < 3; d++) {
+      double a = 0, b = 0;
+      for (int v = 0; v < V; v++) { a += pos[3*(s.base[k]+v)+d]; b += vel[3*(s.base[k]+v)+d]; }
+      ci.position[d] = a/V; ci.velocity[d] = b/V;
+    }
+  }
+}
+void CellInformationFunctionals::calculateCellStretch(HemoCell* h) {
+  CellSnapshot s = snapshot(h); if (!s.np) return;
+  std::vector<double> pos(3*s.np);
+  ck(h->ctx(), hcg_cells_download(h->ctx(), HCG_P_POS, pos.data()), "download");
+  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0) {
+    const int V = (*h->cellfields)[(unsigned)s.types[k]]->numVertex;
+    const double* p = pos.data() + 3*s.base[k];
+    double mx = 0;
+    for (int i = 0; i < V; i++) for (int j = i + 1; j < V; j++) {
+      const double dx = p[3*i]-p[3*j], dy = p[3*i+1]-p[3*j+1], dz = p[3*i+2]-p[3*j+2];
+      mx = std::max(mx, dx*dx + dy*dy + dz*dz);
+    }
+    entry(s, k).stretch = std::sqrt(mx);
+  }
+}
+void CellInformationFunctionals::calculateCellInformation(HemoCell* h) {
+  clear_list();
+  calculateCellVolume(h); calculateCellArea(h); calculateCellPosition(h); calculateCellBoundingBox(h);
+}
+pluint CellInformationFunctionals::getTotalNumberOfCells(HemoCell* h) {
+  int64_t n = 0, p = 0;
+  ck(h->ctx(), hcg_cells_count(h->ctx(), &n, &p), "hcg_cells_count");
+  return (pluint)n;
+}
+pluint CellInformationFunctionals::getNumberOfCellsFromType(HemoCell* h, std::string type) {
+  CellSnapshot s = snapshot(h);
+  const int t = (*h->cellfields)[type]->impl->device_ctype;
+  pluint n = 0;
+  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0 && s.types[k] == t) n++;
+  return n;
+}
+FluidStatistics FluidInfo::calculateVelocityStatistics(HemoCell* h) {
+  FluidStatistics f;
+  ck(h->ctx(), hcg_fluid_velocity_stats(h->ctx(), &f.min, &f.max, &f.avg), "hcg_fluid_velocity_stats");
+  return f;
+}
+
+}  // namespace hemo
+
+// ====================================================================================================
+// plb:: shim
+// ====================================================================================================
+namespace plb {
+
+Parallel_ostream pcout(std::cout), pcerr(std::cerr);
+void plbInit(int*, char***) {}
+void plb_ofstream::open(const char* filename, std::ios_base::openmode mode) { if (global::mpi().isMainProcessor()) f.open(filename, mode); }
+namespace global {
+int MpiManager::getRank() const { return hemo::env_int("RANK", "OMPI_COMM_WORLD_RANK", 0); }
+int MpiManager::getSize() const { return hemo::env_int("WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", 1); }
+int MpiManager::getLocalRank() const { return hemo::env_int("LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", getRank()); }
+void MpiManager::barrier() {}      // ranks meet in the NCCL / peer exchanges of the device path; host-side files are per rank
+MpiManager& mpi() { static MpiManager m; return m; }
+Directories& directories() { static Directories d; return d; }
+}  // namespace global
+
+}  // namespace plb
+
+// non-template back end of the plb:: shim ---------------------------------------------------------------
+namespace hemo {
+using plb::Box3D;
+namespace {
+Box3D clip(const GpuLattice& g, Box3D b) {
+  b.x0 = std::max<plint>(b.x0, 0); b.y0 = std::max<plint>(b.y0, 0); b.z0 = std::max<plint>(b.z0, 0);
+  b.x1 = std::min<plint>(b.x1, g.nx - 1); b.y1 = std::min<plint>(b.y1, g.ny - 1); b.z1 = std::min<plint>(b.z1, g.nz - 1);
+  return b;
+}
+// orientation of a face plane of the bounding box: 0..5 = -x +x -y +y -z +z, or -1
+int plane_orientation(const GpuLattice& g, const Box3D& b) {
+  if (b.x0 == b.x1) { if (b.x0 == 0) return 0; if (b.x0 == g.nx - 1) return 1; }
+  if (b.y0 == b.y1) { if (b.y0 == 0) return 2; if (b.y0 == g.ny - 1) return 3; }
+  if (b.z0 == b.z1) { if (b.z0 == 0) return 4; if (b.z0 == g.nz - 1) return 5; }
+  return -1;
+}
+}  // namespace
+
+GpuLattice* gpu_lattice_create(long nx, long ny, long nz, double omega) {
+  if (nx < 1 || ny < 3 || nz < 3 || !(omega > 0 && omega < 2)) fatal("(HemoCell) (Fluid) invalid lattice size or relaxation frequency");
+  return new GpuLattice((int)nx, (int)ny, (int)nz, omega);
+}
+void gpu_lattice_destroy(GpuLattice* g) { delete g; }
+void gpu_lattice_size(const GpuLattice* g, long out[3]) { out[0] = g->nx; out[1] = g->ny; out[2] = g->nz; }
+void gpu_lattice_set_periodic(GpuLattice* g, int axis, bool on) { if (axis >= 0 && axis < 3) g->periodic[axis] = on; }
+bool gpu_lattice_get_periodic(const GpuLattice* g, int axis) { return axis >= 0 && axis < 3 && g->periodic[axis]; }
+void gpu_lattice_collide_and_stream(GpuLattice* g) {
+  g->materialize();
+  ck(g->ctx, hcg_fluid_warmup(g->ctx, 1), "collideAndStream");
+}
+void gpu_lattice_velocity_plane(GpuLattice* gp, const Box3D& plane_) {
+  GpuLattice& g = *gp;
+  const Box3D plane = clip(g, plane_);
+  const int o = plane_orientation(g, plane);
+  if (o < 0) fatal("(HemoCell) (BoundaryCondition) velocity conditions are supported on the face planes of the bounding box");
+  for (plint x = plane.x0; x <= plane.x1; x++) for (plint y = plane.y0; y <= plane.y1; y++) for (plint z = plane.z0; z <= plane.z1; z++)
+    g.flags[g.idx((int)x, (int)y, (int)z)] = (uint8_t)(HCG_VEL_XN + o);
+  g.touchFlags();
+}
+void gpu_lattice_velocity_all_faces(GpuLattice* g) {
+  // z faces last: rim nodes belong to the z planes, then y, then x (every rim node gets exactly one plane closure)
+  gpu_lattice_velocity_plane(g, Box3D(0, 0, 0, g->ny - 1, 0, g->nz - 1));
+  gpu_lattice_velocity_plane(g, Box3D(g->nx - 1, g->nx - 1, 0, g->ny - 1, 0, g->nz - 1));
+  gpu_lattice_velocity_plane(g, Box3D(0, g->nx - 1, 0, 0, 0, g->nz - 1));
+  gpu_lattice_velocity_plane(g, Box3D(0, g->nx - 1, g->ny - 1, g->ny - 1, 0, g->nz - 1));
+  gpu_lattice_velocity_plane(g, Box3D(0, g->nx - 1, 0, g->ny - 1, 0, 0));
+  gpu_lattice_velocity_plane(g, Box3D(0, g->nx - 1, 0, g->ny - 1, g->nz - 1, g->nz - 1));
+}
+void gpu_lattice_boundary_velocity(GpuLattice* gp, const Box3D& domain_, const double u[3]) {
+  GpuLattice& g = *gp;
+  const Box3D domain = clip(g, domain_);
+  // the device keeps one wall velocity per face orientation: set it for every orientation present in the box
+  bool seen[6] = {false, false, false, false, false, false};
+  for (plint x = domain.x0; x <= domain.x1; x++) for (plint y = domain.y0; y <= domain.y1; y++) for (plint z = domain.z0; z <= domain.z1; z++) {
+    const uint8_t f = g.flags[g.idx((int)x, (int)y, (int)z)];
+    if (f >= HCG_VEL_XN) seen[f - HCG_VEL_XN] = true;
+  }
+  for (int o = 0; o < 6; o++) if (seen[o]) for (int k = 0; k < 3; k++) g.bc[o][k] = u[k];
+  g.touchFlags();
+}
+void gpu_lattice_external_vector(GpuLattice* gp, const Box3D& domain_, const double vec[3]) {
+  GpuLattice& g = *gp;
+  const Box3D domain = clip(g, domain_);
+  if (domain.nCells() != (plint)g.nx*g.ny*g.nz) fatal("(HemoCell) (setExternalVector) only the whole bounding box is supported (uniform driving force)");
+  // after iterate() every node already carries the driving force again: re-applying the same value is free
+  if (g.ctx && !g.body_pending && vec[0] == g.body[0] && vec[1] == g.body[1] && vec[2] == g.body[2]) return;
+  for (int k = 0; k < 3; k++) g.body[k] = vec[k];
+  g.body_pending = true;
+  g.flush();
+}
+void gpu_lattice_define_flag(GpuLattice* gp, const Box3D& domain_, const plb::DomainFunctional3D* fun, int flag) {
+  GpuLattice& g = *gp;
+  const Box3D domain = clip(g, domain_);
+  for (plint x = domain.x0; x <= domain.x1; x++) for (plint y = domain.y0; y <= domain.y1; y++) for (plint z = domain.z0; z <= domain.z1; z++)
+    if (!fun || (*fun)(x, y, z)) g.flags[g.idx((int)x, (int)y, (int)z)] = (uint8_t)flag;
+  g.touchFlags();
+}
+void gpu_lattice_equilibrium(GpuLattice* g, double rho, const double u[3]) {
+  g->eq_rho = rho; for (int k = 0; k < 3; k++) g->eq_u[k] = u[k];
+  g->eq_pending = true;
+  g->flush();
+}
+std::string gpu_lattice_info(const GpuLattice* g) {
+  std::ostringstream o;
+  const int R = plb::global::mpi().getSize();
+  o << "Size of the multi-block:     " << g->nx << "-by-" << g->ny << "-by-" << g->nz << "\n"
+    << "Number of atomic-blocks:     " << R << " (one x-slab per GPU)\n"
+    << "Smallest atomic-block:       " << g->nx/R << "-by-" << g->ny << "-by-" << g->nz << "\n"
+    << "Number of allocated cells:   " << (double)g->nx*g->ny*g->nz/1e6 << " million\n";
+  return o.str();
+}
+}  // namespace hemo

@@ -12,6 +12,7 @@
 #include <tuple>
 
 namespace hemo {
+namespace host {
 
 namespace {
 const T PI = 3.14159265358979323846;
@@ -386,4 +387,5 @@ std::vector<int64_t> placeCells(const TriangularSurfaceMesh& mesh0, const std::v
   return ids;
 }
 
+}  // namespace host
 }  // namespace hemo

@@ -12,6 +12,7 @@
 #include "hemocell_gpu.h"
 
 namespace hemo {
+namespace host {
 
 typedef double T;
 using Vec3 = std::array<T, 3>;
@@ -92,4 +93,5 @@ std::vector<int64_t> placeCells(const TriangularSurfaceMesh& mesh, const std::ve
                                 T dx, int nx, int ny, int nz, const uint8_t* flags, T minDistFromSolid_um,
                                 int64_t cell_id0, std::vector<T>& out);
 
+}  // namespace host
 }  // namespace hemo

@@ -5,7 +5,7 @@
 #include <exception>
 #include <string>
 
-struct hch_celltype { hemo::CellTypeTables t; };
+struct hch_celltype { hemo::host::CellTypeTables t; };
 static thread_local std::string g_err;
 
 extern "C" {
@@ -13,7 +13,7 @@ extern "C" {
 const char* hch_last_error(void) { return g_err.c_str(); }
 
 void hch_parameters(double dx, double dt, double nu_p, double rho_p, double kBT_p, double* out7) {
-  hemo::Parameters p; p.lbm_base_parameters(dx, dt, nu_p, rho_p, kBT_p);
+  hemo::host::Parameters p; p.lbm_base_parameters(dx, dt, nu_p, rho_p, kBT_p);
   out7[0] = p.tau; out7[1] = p.nu_lbm; out7[2] = p.dt; out7[3] = p.dm; out7[4] = p.df; out7[5] = p.f_limit; out7[6] = p.kBT_lbm;
 }
 
@@ -22,8 +22,8 @@ hch_celltype* hch_celltype_build(int32_t model, int32_t construct_type, double d
                                  double kLink, double eta_m, double radius_m, double aspect_ratio,
                                  int32_t min_num_triangles, const int32_t* inner_edges, int32_t n_inner_edges) {
   try {
-    hemo::Parameters p; p.lbm_base_parameters(dx, dt, nu_p, rho_p, kBT_p);
-    hemo::MaterialModel m;
+    hemo::host::Parameters p; p.lbm_base_parameters(dx, dt, nu_p, rho_p, kBT_p);
+    hemo::host::MaterialModel m;
     m.kBend = kBend; m.kVolume = kVolume; m.kArea = kArea; m.kLink = kLink; m.eta_m = eta_m;
     m.radius = radius_m; m.aspectRatio = aspect_ratio; m.minNumTriangles = min_num_triangles;
     for (int i = 0; i < n_inner_edges; i++) m.innerEdges.push_back({inner_edges[2*i], inner_edges[2*i+1]});
@@ -49,7 +49,7 @@ void hch_celltype_free(hch_celltype* h) { delete h; }
 
 int64_t hch_read_pos(const char* path, double* rows6, int64_t cap) {
   try {
-    auto rows = hemo::readPositionsFile(path);
+    auto rows = hemo::host::readPositionsFile(path);
     if (rows6) for (size_t i = 0; i < rows.size() && (int64_t)i < cap; i++) memcpy(rows6 + 6*i, rows[i].data(), 6*sizeof(double));
     return (int64_t)rows.size();
   } catch (std::exception& e) { g_err = e.what(); return -1; }
@@ -63,7 +63,7 @@ int64_t hch_place_cells(const hch_celltype* h, const double* rows6, int64_t n_ro
     std::vector<std::array<double, 6>> rows(n_rows);
     for (int64_t i = 0; i < n_rows; i++) memcpy(rows[i].data(), rows6 + 6*i, 6*sizeof(double));
     std::vector<double> out;
-    auto ids = hemo::placeCells(h->t.mesh, rows, dx, nx, ny, nz, flags, min_dist_um, cell_id0, out);
+    auto ids = hemo::host::placeCells(h->t.mesh, rows, dx, nx, ny, nz, flags, min_dist_um, cell_id0, out);
     memcpy(out_pos, out.data(), out.size()*sizeof(double));
     memcpy(out_ids, ids.data(), ids.size()*sizeof(int64_t));
     return (int64_t)ids.size();

@@ -1,0 +1,6 @@
+/* The case files of the reference include "palabos3D.h" / "palabos3D.hh" next to "hemocell.h".  Here the
+ * Palabos calls they make are served by the plb:: shim inside hemocell.h. */
+#ifndef HEMOCELL_PALABOS3D_SHIM_HH
+#define HEMOCELL_PALABOS3D_SHIM_HH
+#include "hemocell.h"
+#endif

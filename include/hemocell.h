@@ -76,7 +76,24 @@
 
 typedef double T;
 
-namespace hemo { class GpuLattice; class HemoCell; class HemoCellFields; class HemoCellField; class Config; }
+namespace plb { struct Box3D; struct DomainFunctional3D; }
+namespace hemo {
+class GpuLattice; class HemoCell; class HemoCellFields; class HemoCellField; class Config;
+/* non-template back end of the plb:: shim (hemocell_b200/host/facade.cpp) */
+GpuLattice* gpu_lattice_create(long nx, long ny, long nz, double omega);
+void gpu_lattice_destroy(GpuLattice*);
+void gpu_lattice_size(const GpuLattice*, long out[3]);
+void gpu_lattice_set_periodic(GpuLattice*, int axis, bool on);
+bool gpu_lattice_get_periodic(const GpuLattice*, int axis);
+void gpu_lattice_collide_and_stream(GpuLattice*);
+void gpu_lattice_velocity_plane(GpuLattice*, const plb::Box3D& plane);
+void gpu_lattice_velocity_all_faces(GpuLattice*);
+void gpu_lattice_boundary_velocity(GpuLattice*, const plb::Box3D& domain, const double u[3]);
+void gpu_lattice_external_vector(GpuLattice*, const plb::Box3D& domain, const double v[3]);
+void gpu_lattice_define_flag(GpuLattice*, const plb::Box3D& domain, const plb::DomainFunctional3D* fun, int flag);
+void gpu_lattice_equilibrium(GpuLattice*, double rho, const double u[3]);
+std::string gpu_lattice_info(const GpuLattice*);
+}
 
 /* ================================================================================================== */
 /* plb:: shim                                                                                         */
@@ -165,9 +182,9 @@ struct defaultMultiBlockPolicy3D {
 class PeriodicitySwitch3D {
  public:
   explicit PeriodicitySwitch3D(hemo::GpuLattice* l) : lat(l) {}
-  void toggle(plint axis, bool on);
+  void toggle(plint axis, bool on) { hemo::gpu_lattice_set_periodic(lat, (int)axis, on); }
   void toggleAll(bool on) { toggle(0, on); toggle(1, on); toggle(2, on); }
-  bool get(plint axis) const;
+  bool get(plint axis) const { return hemo::gpu_lattice_get_periodic(lat, (int)axis); }
  private:
   hemo::GpuLattice* lat;
 };
@@ -177,19 +194,22 @@ template <typename U, template <typename V> class Descriptor>
 class MultiBlockLattice3D {
  public:
   MultiBlockLattice3D(const MultiBlockManagement3D& m, BlockCommunicator3D*, CombinedStatistics*, MultiCellAccess3D<U, Descriptor>*,
-                      Dynamics<U, Descriptor>* background);
-  MultiBlockLattice3D(plint nx, plint ny, plint nz, Dynamics<U, Descriptor>* background);
-  ~MultiBlockLattice3D();
+                      Dynamics<U, Descriptor>* background_)
+      : impl(hemo::gpu_lattice_create(m.getBoundingBox().getNx(), m.getBoundingBox().getNy(), m.getBoundingBox().getNz(), background_->getOmega())),
+        mgmt(m), background(background_), per(impl) {}
+  MultiBlockLattice3D(plint nx, plint ny, plint nz, Dynamics<U, Descriptor>* background_)
+      : impl(hemo::gpu_lattice_create(nx, ny, nz, background_->getOmega())), mgmt(nx, ny, nz, 1), background(background_), per(impl) {}
+  ~MultiBlockLattice3D() { hemo::gpu_lattice_destroy(impl); delete background; }
   MultiBlockLattice3D(const MultiBlockLattice3D&) = delete;
   MultiBlockLattice3D& operator=(const MultiBlockLattice3D&) = delete;
-  Box3D getBoundingBox() const;
+  Box3D getBoundingBox() const { long n[3]; hemo::gpu_lattice_size(impl, n); return Box3D(0, n[0] - 1, 0, n[1] - 1, 0, n[2] - 1); }
   plint getNx() const { return getBoundingBox().getNx(); }
   plint getNy() const { return getBoundingBox().getNy(); }
   plint getNz() const { return getBoundingBox().getNz(); }
   PeriodicitySwitch3D& periodicity() { return per; }
   void toggleInternalStatistics(bool) {}
-  void initialize();                         /* uploads flags / boundary velocities / periodicity: creates the device context */
-  void collideAndStream();                   /* Palabos call of the case files' warm-up loops (force is NOT reset) */
+  void initialize() {}                       /* the device context is created on first device use (periodicity may still be toggled) */
+  void collideAndStream() { hemo::gpu_lattice_collide_and_stream(impl); }   /* warm-up loops of the case files (force is NOT reset) */
   MultiBlockManagement3D& getMultiBlockManagement() { return mgmt; }
   void signalPeriodicity() {}
   Dynamics<U, Descriptor>& getBackgroundDynamics() { return *background; }
@@ -206,25 +226,46 @@ template <typename U, template <typename V> class Descriptor>
 class OnLatticeBoundaryCondition3D {
  public:
   /* regularized ("local") velocity condition on one face plane of the bounding box (helper/hemocellInit.hh:72-73) */
-  void setVelocityConditionOnBlockBoundaries(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D plane, boundary::BcType = boundary::dirichlet);
+  void setVelocityConditionOnBlockBoundaries(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D plane, boundary::BcType = boundary::dirichlet) {
+    hemo::gpu_lattice_velocity_plane(lattice.gpu(), plane);
+  }
   /* ... on all six faces (tests/validation/stretch_cell/test_stretch_cell.cpp:90) */
-  void setVelocityConditionOnBlockBoundaries(MultiBlockLattice3D<U, Descriptor>& lattice, boundary::BcType = boundary::dirichlet);
+  void setVelocityConditionOnBlockBoundaries(MultiBlockLattice3D<U, Descriptor>& lattice, boundary::BcType = boundary::dirichlet) {
+    hemo::gpu_lattice_velocity_all_faces(lattice.gpu());
+  }
 };
 template <typename U, template <typename V> class Descriptor>
 OnLatticeBoundaryCondition3D<U, Descriptor>* createLocalBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<U, Descriptor>(); }
 
 template <typename U, template <typename V> class Descriptor>
-void setBoundaryVelocity(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, Array<U, 3> velocity);
+void setBoundaryVelocity(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, Array<U, 3> velocity) {
+  const double u[3] = {velocity[0], velocity[1], velocity[2]};
+  hemo::gpu_lattice_boundary_velocity(lattice.gpu(), domain, u);
+}
 template <typename U, template <typename V> class Descriptor>
-void setExternalVector(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, int vectorStartsAt, Array<U, 3> vec);
+void setExternalVector(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, int vectorStartsAt, Array<U, 3> vec) {
+  (void)vectorStartsAt;                       /* the only external vector of ForcedD3Q19Descriptor is the force */
+  const double v[3] = {vec[0], vec[1], vec[2]};
+  hemo::gpu_lattice_external_vector(lattice.gpu(), domain, v);
+}
 template <typename U, template <typename V> class Descriptor>
-void defineDynamics(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, Dynamics<U, Descriptor>* dynamics);
+void defineDynamics(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, Dynamics<U, Descriptor>* dynamics) {
+  hemo::gpu_lattice_define_flag(lattice.gpu(), domain, nullptr, dynamics->nodeFlag());
+  delete dynamics;
+}
 template <typename U, template <typename V> class Descriptor>
-void defineDynamics(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, DomainFunctional3D* functional, Dynamics<U, Descriptor>* dynamics);
+void defineDynamics(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, DomainFunctional3D* functional, Dynamics<U, Descriptor>* dynamics) {
+  hemo::gpu_lattice_define_flag(lattice.gpu(), domain, functional, dynamics->nodeFlag());
+  delete dynamics; delete functional;
+}
 template <typename U, template <typename V> class Descriptor>
-void initializeAtEquilibrium(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, U rho, Array<U, 3> velocity);
+void initializeAtEquilibrium(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, U rho, Array<U, 3> velocity) {
+  (void)domain;
+  const double u[3] = {velocity[0], velocity[1], velocity[2]};
+  hemo::gpu_lattice_equilibrium(lattice.gpu(), rho, u);
+}
 template <typename U, template <typename V> class Descriptor>
-std::string getMultiBlockInfo(MultiBlockLattice3D<U, Descriptor>& lattice);
+std::string getMultiBlockInfo(MultiBlockLattice3D<U, Descriptor>& lattice) { return hemo::gpu_lattice_info(lattice.gpu()); }
 
 /* rank-0 streams and the process "MPI" view: one process per GPU, rank / size from the launcher's
  * environment (RANK / WORLD_SIZE / LOCAL_RANK of torchrun, or OMPI_COMM_WORLD_*) */
@@ -237,6 +278,19 @@ class Parallel_ostream {
   std::ostream& os;
 };
 extern Parallel_ostream pcout, pcerr;
+/* file stream that only the main processor writes (Palabos io/parallelIO.h) */
+class plb_ofstream {
+ public:
+  plb_ofstream() {}
+  explicit plb_ofstream(const char* filename, std::ios_base::openmode mode = std::ios_base::out) { open(filename, mode); }
+  void open(const char* filename, std::ios_base::openmode mode = std::ios_base::out);
+  void close() { if (f.is_open()) f.close(); }
+  bool is_open() { return f.is_open(); }
+  template <typename V> plb_ofstream& operator<<(const V& v) { if (f.is_open()) f << v; return *this; }
+  plb_ofstream& operator<<(std::ostream& (*fn)(std::ostream&)) { if (f.is_open()) f << fn; return *this; }
+ private:
+  std::ofstream f;
+};
 void plbInit(int* argc, char*** argv);
 namespace global {
 class MpiManager {
@@ -284,12 +338,19 @@ struct Array {
   Array& operator+=(const Array& o) { for (size_t i = 0; i < n; i++) data[i] += o.data[i]; return *this; }
   Array& operator-=(const Array& o) { for (size_t i = 0; i < n; i++) data[i] -= o.data[i]; return *this; }
   Array& operator*=(U s) { for (size_t i = 0; i < n; i++) data[i] *= s; return *this; }
+  Array& operator/=(U s) { for (size_t i = 0; i < n; i++) data[i] /= s; return *this; }
+  Array operator/(U s) const { Array r = *this; r /= s; return r; }
+  void resetToZero() { for (size_t i = 0; i < n; i++) data[i] = U(); }
+  size_t size() const { return n; }
   Array operator+(const Array& o) const { Array r = *this; r += o; return r; }
   Array operator-(const Array& o) const { Array r = *this; r -= o; return r; }
   Array operator*(U s) const { Array r = *this; r *= s; return r; }
 };
 template <typename U> U dot(const Array<U, 3>& a, const Array<U, 3>& b) { return a[0]*b[0] + a[1]*b[1] + a[2]*b[2]; }
 template <typename U> U norm(const Array<U, 3>& a) { return std::sqrt(dot(a, a)); }
+template <typename U> Array<U, 3> crossProduct(const Array<U, 3>& a, const Array<U, 3>& b) {
+  return Array<U, 3>{{a[1]*b[2] - a[2]*b[1], a[2]*b[0] - a[0]*b[2], a[0]*b[1] - a[1]*b[0]}};
+}
 
 /* ---- config/config.h ---------------------------------------------------------------------------- */
 namespace xml { struct Node; }
@@ -572,7 +633,17 @@ class FluidInfo {
 /* helper/hemocellInit.hh:59-92 */
 template <typename U, template <class V> class Descriptor>
 void iniLatticeSquareCouette(plb::MultiBlockLattice3D<U, Descriptor>& lattice, plint nx, plint ny, plint nz,
-                             plb::OnLatticeBoundaryCondition3D<U, Descriptor>& boundaryCondition, U shearRate);
+                             plb::OnLatticeBoundaryCondition3D<U, Descriptor>& boundaryCondition, U shearRate) {
+  plb::Box3D top(0, nx - 1, 0, ny - 1, nz - 1, nz - 1), bottom(0, nx - 1, 0, ny - 1, 0, 0);
+  lattice.periodicity().toggle(0, true); lattice.periodicity().toggle(1, true); lattice.periodicity().toggle(2, false);
+  boundaryCondition.setVelocityConditionOnBlockBoundaries(lattice, top);
+  boundaryCondition.setVelocityConditionOnBlockBoundaries(lattice, bottom);
+  const U vHalf = (nz - 1)*shearRate*0.5;
+  plb::setBoundaryVelocity(lattice, top, plb::Array<U, 3>(-vHalf, 0.0, 0.0));
+  plb::setBoundaryVelocity(lattice, bottom, plb::Array<U, 3>(vHalf, 0.0, 0.0));
+  plb::setExternalVector(lattice, lattice.getBoundingBox(), Descriptor<U>::ExternalField::forceBeginsAt, plb::Array<U, 3>(0.0, 0.0, 0.0));
+  lattice.initialize();
+}
 
 }  // namespace hemo
 

@@ -1,0 +1,86 @@
+// CPU-side checks of the C++ API surface (include/hemocell.h): config parsing, unit conversion, cell-type
+// set-up.  No device call is made (the context is created lazily).  Prints "ok <name>" per check; exit code
+// = number of failures.  usage: test_host_facade <scratch dir>
+#include <cmath>
+#include <cstdio>
+#include <unistd.h>
+#include "hemocell.h"
+#include "rbcHighOrderModel.h"
+#include "pltSimpleModel.h"
+
+using namespace hemo;
+static int failures = 0;
+#define CHECK(name, cond) do { if (cond) std::printf("ok %s\n", name); else { std::printf("FAIL %s\n", name); failures++; } } while (0)
+static bool close_rel(double a, double b, double tol) { return std::fabs(a - b) <= tol*std::max(std::fabs(a), std::fabs(b)); }
+
+static void write(const std::string& path, const std::string& s) { std::ofstream f(path); f << s; }
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 100;
+  if (chdir(argv[1]) != 0) return 101;
+  write("config.xml",
+        "<?xml version=\"1.0\" ?>\n<!-- a comment -->\n<hemocell>\n<parameters><warmup> 3 </warmup><outputDirectory>out</outputDirectory></parameters>\n"
+        "<ibm><radius>3.91e-6</radius><stepMaterialEvery> 20 </stepMaterialEvery></ibm>\n"
+        "<domain attr=\"x &amp; y\"><shearrate> 111.0 </shearrate><rhoP>1025</rhoP><nuP>1.1e-6</nuP><dx>0.5e-6</dx><dt>0.5e-7</dt>\n"
+        "<particleEnvelope>20</particleEnvelope><kBT>4.100531391e-21</kBT><Re>0.5</Re><empty/></domain>\n"
+        "<sim><tmax>10</tmax></sim></hemocell>\n");
+  write("RBC.xml",
+        "<?xml version=\"1.0\" ?><hemocell><MaterialModel><name>RBC</name><eta_m>0.0</eta_m><kBend>80.0</kBend><kVolume>20.0</kVolume>"
+        "<kArea>5.0</kArea><kLink>15.0</kLink><minNumTriangles>600</minNumTriangles><radius>3.91e-6</radius><Volume>90</Volume></MaterialModel></hemocell>");
+  write("PLT.xml",
+        "<?xml version=\"1.0\" ?><hemocell><MaterialModel><name>PLT</name><eta_m>0.0</eta_m><kBend>250.0</kBend><kVolume>100.0</kVolume>"
+        "<kArea>8.0</kArea><kLink>25.0</kLink><minNumTriangles>66</minNumTriangles><radius>1.25e-6</radius><aspectRatio>0.434782608696</aspectRatio>"
+        "<Volume>11</Volume><InnerEdges><Edge> 0 1 </Edge><Edge>2 3</Edge></InnerEdges></MaterialModel></hemocell>");
+  char prog[] = "test"; char cfgname[] = "config.xml"; char* av[] = {prog, cfgname};
+  HemoCell hemocell(cfgname, 2, av);
+  Config* cfg = hemocell.cfg;
+  CHECK("config.read<int>", (*cfg)["parameters"]["warmup"].read<int>() == 3);
+  CHECK("config.read<double>", (*cfg)["domain"]["shearrate"].read<T>() == 111.0);
+  CHECK("config.read<string>", (*cfg)["parameters"]["outputDirectory"].read<std::string>() == "out");
+  CHECK("config.not_checkpointed", !cfg->checkpointed);
+  bool threw = false;
+  try { (*cfg)["domain"]["nope"]; } catch (std::invalid_argument&) { threw = true; }
+  CHECK("config.missing_key_throws_invalid_argument", threw);
+  CHECK("output_directory_created", access(global::directories().getOutputDir().c_str(), F_OK) == 0);
+
+  param::lbm_shear_parameters(*cfg, 40);
+  CHECK("param.tau", close_rel(param::tau, 1.16, 1e-14));
+  CHECK("param.nu_lbm", close_rel(param::nu_lbm, 0.22, 1e-14));
+  CHECK("param.df", close_rel(param::df, 1025*std::pow(0.5e-6, 4)/std::pow(0.5e-7, 2), 1e-14));
+  CHECK("param.f_limit", close_rel(param::f_limit, 50.0/1e12/param::df, 1e-14));
+  CHECK("param.shearrate_lbm", close_rel(param::shearrate_lbm, 111.0*0.5e-7, 1e-14));
+  param::lbm_pipe_parameters(*cfg, 256);
+  CHECK("param.u_lbm_max", close_rel(param::u_lbm_max, 0.5*param::nu_lbm/512.0, 1e-14));
+
+  hemocell.lattice = new MultiBlockLattice3D<T, DESCRIPTOR>(defaultMultiBlockPolicy3D().getMultiBlockManagement(40, 40, 20, 2),
+      defaultMultiBlockPolicy3D().getBlockCommunicator(), defaultMultiBlockPolicy3D().getCombinedStatistics(),
+      defaultMultiBlockPolicy3D().getMultiCellAccess<T, DESCRIPTOR>(), new GuoExternalForceBGKdynamics<T, DESCRIPTOR>(1.0/param::tau));
+  CHECK("lattice.bbox", hemocell.lattice->getBoundingBox().getNx() == 40 && hemocell.lattice->getNz() == 20);
+  hemocell.lattice->periodicity().toggle(0, true);
+  CHECK("lattice.periodicity", hemocell.lattice->periodicity().get(0) && !hemocell.lattice->periodicity().get(2));
+  defineDynamics(*hemocell.lattice, Box3D(0, 39, 0, 0, 0, 19), new BounceBack<T, DESCRIPTOR>(1.));
+  hemocell.latticeEquilibrium(1., plb::Array<T, 3>(0., 0., 0.));
+  hemocell.lattice->initialize();                      // still no device needed
+
+  hemocell.initializeCellfield();
+  hemocell.addCellType<RbcHighOrderModel>("RBC", RBC_FROM_SPHERE);
+  hemocell.addCellType<PltSimpleModel>("PLT", ELLIPSOID_FROM_SPHERE);
+  hemocell.setMaterialTimeScaleSeparation("RBC", 20);
+  HemoCellField* rbc = (*hemocell.cellfields)["RBC"];
+  HemoCellField* plt = (*hemocell.cellfields)[1];
+  CHECK("rbc.mesh", rbc->numVertex == 642 && rbc->triangle_list.size() == 1280);
+  CHECK("plt.mesh", plt->numVertex == 66 && plt->triangle_list.size() == 128);
+  CHECK("rbc.timescale", rbc->timescale == 20);
+  CHECK("rbc.edges", rbc->mechanics->cellConstants.edge_list.size() == 1920);
+  const RbcHighOrderModel* m = dynamic_cast<RbcHighOrderModel*>(rbc->mechanics);
+  const double kBT_lbm = 4.100531391e-21/(param::df*param::dx);
+  CHECK("rbc.k_link", m && close_rel(m->k_link, 15.0*kBT_lbm/(7.5e-9/param::dx), 1e-13));
+  CHECK("rbc.k_bend", m && close_rel(m->k_bend, 80.0*kBT_lbm/(5e-7/param::dx), 1e-13));
+  CHECK("rbc.k_volume", m && close_rel(m->k_volume, 20.0*kBT_lbm/(5e-7/param::dx), 1e-13));
+  const PltSimpleModel* pm = dynamic_cast<PltSimpleModel*>(plt->mechanics);
+  CHECK("plt.k_area_face_scaling", pm && close_rel(pm->k_area, 8.0*(1280.0/128.0)*kBT_lbm/(5e-7/param::dx), 1e-13));
+  CHECK("rbc.volume_eq_um3", std::fabs(rbc->mechanics->cellConstants.volume_eq*std::pow(0.5, 3) - 81.1) < 0.2);
+  CHECK("cellfields.size", hemocell.cellfields->size() == 2);
+  std::printf("%d failures\n", failures);
+  return failures;
+}

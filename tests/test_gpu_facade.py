@@ -1,0 +1,93 @@
+"""GPU tests of the C++ API surface: case files (ours, and the reference's own unmodified ones when they were
+built in the authoring container: examples/Makefile `refcases`) driving the CUDA path through
+hemo::HemoCell, checked against the CPU oracle."""
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import mesh as M
+import util as U
+import facade_cases as F
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_shear(steps, tmeas, rows, material_every=1, particle_every=1):
+    nx, ny, nz = 40, 40, 20
+    par = M.Parameters(dx=0.5e-6, dt=0.5e-7)
+    vh = (nz - 1) * 111.0 * par.dt * 0.5
+    bc = np.zeros((6, 3)); bc[4] = (vh, 0, 0); bc[5] = (-vh, 0, 0)
+    fl = U.couette_flags(nx, ny, nz).reshape(-1)
+    dom = O.make_domain(nx, ny, nz, (1, 1, 0), par.tau, bc)
+    ct = O.rbc_celltype(par)
+    cells, ids = M.place_cells(ct.verts, np.array(rows, dtype=float), par.dx, (nx, ny, nz), fl)
+    sim = O.OracleSim(dom, fl, par.f_limit)
+    sim.vel_timescale = particle_every
+    sim.add_celltype(ct, material_every); sim.add_cells(0, cells, ids)
+    out = []
+    for _ in range(steps // tmeas):
+        for _ in range(tmeas):
+            sim.iterate()
+        sim.apply_mechanics(forced=True)                  # HemoCell::writeOutput recomputes the forces (core/hemoCell.cpp:258)
+        p = sim.pos[:ct.V]
+        d = p[:, None, :] - p[None, :, :]
+        out.append(dict(iter=sim.iter, diam=(p.max(0) - p.min(0)) * 0.5, dmax=np.sqrt((d * d).sum(-1).max()) * 0.5))
+    return out
+
+
+@pytest.mark.parametrize("cadence", [(1, 1), (10, 5)])
+def test_shear_cell_case_file_matches_oracle(tmp_path, cadence):
+    """examples/shear_cell (HemoCell API -> C ABI -> CUDA) vs the CPU oracle on the oneCellShear set-up"""
+    exe = os.path.join(ROOT, "examples", "shear_cell", "shear_cell")
+    assert os.path.exists(exe), "examples/shear_cell/shear_cell is not built (python __graft_entry__.py)"
+    mat, vel = cadence
+    rows = [(9.5, 9.5, 4.5, 70, 20, 0)]
+    F.write_shear_case(tmp_path, tmax=300, tmeas=100, rows=rows, material_every=mat, particle_every=vel)
+    r = subprocess.run([exe, "config.xml"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    got = np.loadtxt(tmp_path / "shear.log").reshape(-1, 8)
+    ref = _oracle_shear(300, 100, rows, mat, vel)
+    assert got.shape[0] == len(ref) == 3
+    for g, o in zip(got, ref):
+        assert int(g[0]) == o["iter"]
+        U.assert_close(g[1:4], o["diam"], f"bounding-box diameters at {o['iter']}", rtol=1e-9)
+        U.assert_close(g[6:7], np.array([o["dmax"]]), f"largest diameter at {o['iter']}", rtol=1e-9)
+    assert abs(got[-1, 4] - 100.0) < 0.1                      # volume conserved
+    # operator profile written under the reference's key names
+    stats = list((tmp_path / "tmp" / "log").glob("*.statistics"))
+    assert stats and "collideAndStream" in stats[0].read_text() and "spreadParticleForce" in stats[0].read_text()
+    assert list((tmp_path / "tmp" / "csv").glob("RBC.*.csv"))
+
+
+def test_reference_oneCellShear_unmodified_binary(tmp_path):
+    """the REFERENCE's own examples/oneCellShear/oneCellShear.cpp, compiled unmodified against include/hemocell.h,
+    reproduces the oracle's stretch.log (tests/golden/shear_oracle.json) on the GPU"""
+    src = os.path.join(ROOT, "build", "refcases", "oneCellShear")
+    if not os.path.exists(os.path.join(src, "oneCellShear")):
+        pytest.skip("build/refcases not present (built from /root/reference in the authoring container)")
+    for f in ("oneCellShear", "config.xml", "RBC.xml", "RBC.pos"):
+        shutil.copy(os.path.join(src, f), tmp_path / f)
+    cfg = (tmp_path / "config.xml").read_text()
+    cfg = re.sub(r"<tmax>.*?</tmax>", "<tmax> 4000 </tmax>", cfg)
+    cfg = re.sub(r"<tcheckpoint>.*?</tcheckpoint>", "<tcheckpoint> 4000 </tcheckpoint>", cfg)
+    (tmp_path / "config.xml").write_text(cfg)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "hemocell_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([str(tmp_path / "oneCellShear"), "config.xml"], cwd=tmp_path, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    got = np.loadtxt(tmp_path / "stretch.log").reshape(-1, 8)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "shear_oracle.json")))["trace"]
+    assert got.shape[0] == 2
+    for g, o in zip(got, gold[:2]):
+        assert int(g[0]) == o["iter"]
+        U.assert_close(g[1:4], np.array(o["diam_um"]), f"diameters at {o['iter']}", rtol=2e-6)        # stretch.log holds 6 digits
+        U.assert_close(g[6:7], np.array([o["largest_diam_um"]]), f"largest diameter at {o['iter']}", rtol=2e-6)
+        assert abs(g[7] - o["deformation_index_pct"]) < 1e-3
+    assert (tmp_path / "tmp" / "checkpoint" / "checkpoint.xml").exists()
