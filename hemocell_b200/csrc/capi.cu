@@ -17,6 +17,34 @@ hcg_status hcg_fail(hcg_ctx* c, hcg_status code, const std::string& msg) {
   return code;
 }
 
+// one byte per node (flags, wall mask): my face planes -> the neighbours' ghost planes; ghosts beyond a
+// non-periodic end of the domain keep `ghost_default`
+hcg_status lat_exchange_byte_planes(hcg_ctx* c, uint8_t* buf, int ghost_default) {
+  const int R = c->dom.n_ranks, r = c->dom.rank; const bool px = c->dom.periodic[0];
+  const int64_t P = c->P;
+  CUDA_TRY(c, cudaMemsetAsync(buf, ghost_default, P, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(buf + (int64_t)(c->nxl+1)*P, ghost_default, P, c->stream));
+  if (R == 1) {
+    if (px) {
+      CUDA_TRY(c, cudaMemcpyAsync(buf, buf + (int64_t)c->nxl*P, P, cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_TRY(c, cudaMemcpyAsync(buf + (int64_t)(c->nxl+1)*P, buf + P, P, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return HCG_OK;
+  }
+  if (!c->nccl) return HCG_OK;     // done again from hcg_comm_init
+  ncclComm_t comm = (ncclComm_t)c->nccl;
+  const int left = (r == 0) ? (px ? R - 1 : -1) : r - 1;
+  const int right = (r == R - 1) ? (px ? 0 : -1) : r + 1;
+  ncclGroupStart();
+  if (left >= 0) ncclSend(buf + P, P, ncclUint8, left, comm, c->stream);
+  if (right >= 0) ncclSend(buf + (int64_t)c->nxl*P, P, ncclUint8, right, comm, c->stream);
+  if (right >= 0) ncclRecv(buf + (int64_t)(c->nxl+1)*P, P, ncclUint8, right, comm, c->stream);
+  if (left >= 0) ncclRecv(buf, P, ncclUint8, left, comm, c->stream);
+  ncclResult_t rc = ncclGroupEnd();
+  if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("byte-plane exchange: ") + ncclGetErrorString(rc));
+  return HCG_OK;
+}
+
 namespace {
 
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1)/t); }
@@ -77,32 +105,7 @@ template <class T> hcg_status upload_table(hcg_ctx* c, CellTypeHost& th, T** dst
   return HCG_OK;
 }
 
-hcg_status exchange_flags(hcg_ctx* c) {
-  const int R = c->dom.n_ranks, r = c->dom.rank; const bool px = c->dom.periodic[0];
-  const int64_t P = c->P;
-  // default: ghost planes are non-fluid (outside a non-periodic domain)
-  CUDA_TRY(c, cudaMemsetAsync(c->flags, HCG_BOUNCEBACK, P, c->stream));
-  CUDA_TRY(c, cudaMemsetAsync(c->flags + (int64_t)(c->nxl+1)*P, HCG_BOUNCEBACK, P, c->stream));
-  if (R == 1) {
-    if (px) {
-      CUDA_TRY(c, cudaMemcpyAsync(c->flags, c->flags + (int64_t)c->nxl*P, P, cudaMemcpyDeviceToDevice, c->stream));
-      CUDA_TRY(c, cudaMemcpyAsync(c->flags + (int64_t)(c->nxl+1)*P, c->flags + P, P, cudaMemcpyDeviceToDevice, c->stream));
-    }
-    return HCG_OK;
-  }
-  if (!c->nccl) return HCG_OK;     // done again from hcg_comm_init
-  ncclComm_t comm = (ncclComm_t)c->nccl;
-  const int left = (r == 0) ? (px ? R - 1 : -1) : r - 1;
-  const int right = (r == R - 1) ? (px ? 0 : -1) : r + 1;
-  ncclGroupStart();
-  if (left >= 0) ncclSend(c->flags + P, P, ncclUint8, left, comm, c->stream);
-  if (right >= 0) ncclSend(c->flags + (int64_t)c->nxl*P, P, ncclUint8, right, comm, c->stream);
-  if (right >= 0) ncclRecv(c->flags + (int64_t)(c->nxl+1)*P, P, ncclUint8, right, comm, c->stream);
-  if (left >= 0) ncclRecv(c->flags, P, ncclUint8, left, comm, c->stream);
-  ncclResult_t rc = ncclGroupEnd();
-  if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("flag exchange: ") + ncclGetErrorString(rc));
-  return HCG_OK;
-}
+hcg_status exchange_flags(hcg_ctx* c) { return lat_exchange_byte_planes(c, c->flags, HCG_BOUNCEBACK); }
 
 // has_nonfluid = the IBM kernels must look at node flags: real nodes or ghost planes (neighbour's face /
 // outside of a non-periodic domain) hold something that is not plain fluid
@@ -248,6 +251,7 @@ void hcg_destroy(hcg_ctx* c) {
   for (int k = 0; k < 3; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->frc[k]); cudaFree(c->frep[k]); }
   for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) if (c->comp[k][d]) cudaFree(c->comp[k][d]);
   if (c->multi.d_cell_shared) cudaFree(c->multi.d_cell_shared);
+  if (c->cell_gid) cudaFree(c->cell_gid);
   cudaFree(c->p_cell); cudaFree(c->cell_alive); cudaFree(c->cell_type); cudaFree(c->cell_base);
   cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->bin_items); cudaFree(c->wall_nodes); cudaFree(c->scan_tmp);
   cudaFree(c->staging);
@@ -537,7 +541,7 @@ hcg_status hcg_cells_add(hcg_ctx* c, int32_t ctype, int64_t n_cells, const int64
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->np = new_p; c->ncells = new_c; c->cap_p = new_p; c->cap_c = new_c;
   if (c->multi.d_arr) { cudaFree(c->multi.d_arr); c->multi.d_arr = nullptr; }     // array pointers changed
-  c->perm_valid = false;
+  c->perm_valid = false; c->cell_gid_dirty = true;
   if (c->dom.n_ranks > 1 && (s = multi_rebalance(c, true))) return s;            // builds the shared lists
   if (c->bin_items) { cudaFree(c->bin_items); cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->scan_tmp);
                       c->bin_items = c->bin_count = c->bin_start = nullptr; c->scan_tmp = nullptr; }

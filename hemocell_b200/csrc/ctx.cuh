@@ -106,6 +106,7 @@ struct hcg_ctx {
   uint8_t* cell_alive;         // per cell
   int32_t* cell_type;          // per cell (device)
   int64_t* cell_base;          // per cell (device) first particle
+  int64_t* cell_gid = nullptr; bool cell_gid_dirty = true; int64_t cell_gid_cap = 0;   // per cell (device) global id, on demand
   std::vector<int64_t> h_cell_id; std::vector<int32_t> h_cell_type; std::vector<int64_t> h_cell_base;
   std::vector<CellTypeHost> types;
   // repulsion
@@ -173,6 +174,7 @@ hcg_status lat_reset_force(hcg_ctx* c);
 hcg_status lat_init_equilibrium(hcg_ctx* c, double rho, const double u[3]);
 hcg_status lat_halo_exchange_pop(hcg_ctx* c);
 hcg_status lat_halo_exchange_u(hcg_ctx* c);
+hcg_status lat_exchange_byte_planes(hcg_ctx* c, uint8_t* buf, int ghost_default);   // per-node byte field: face planes -> neighbours' ghosts
 hcg_status lat_pop_to_reference(hcg_ctx* c, double* dst_dev);      // S_q(n) = g_q(n - c_q), compact slab
 hcg_status lat_pop_from_reference(hcg_ctx* c, const double* src_dev);
 hcg_status lat_velocity_stats(hcg_ctx* c, double* vmin, double* vmax, double* vmean);
@@ -192,7 +194,9 @@ bool spread_sorted_supported(const CellTypeHost& th);
 hcg_status spread_sorted_rebuild(hcg_ctx* c);
 hcg_status spread_sorted(hcg_ctx* c);
 // multi.cu
-hcg_status multi_velocity_sync(hcg_ctx* c);
+hcg_status multi_velocity_sync(hcg_ctx* c);                // = multi_field_sync(c, 0)
+hcg_status multi_field_sync(hcg_ctx* c, int field);        // 0 = velocity + alive flags, 1 = repulsion force
+hcg_status multi_upload_cell_gid(hcg_ctx* c);
 hcg_status multi_rebalance(hcg_ctx* c, bool initial);
 hcg_status multi_neighbour_exchange(hcg_ctx* c, const void* sendL, size_t nsL, const void* sendR, size_t nsR,
                                     void* recvR, size_t nrR, void* recvL, size_t nrL);

@@ -178,10 +178,28 @@ extern "C" void hch_slab_membership(int64_t n, const double* xlo, const double* 
   }
 }
 
-// velocity + alive-flag swap of the shared cells (every interpolation step)
-hcg_status multi_velocity_sync(hcg_ctx* c) {
+hcg_status multi_upload_cell_gid(hcg_ctx* c) {
+  if (!c->cell_gid_dirty && c->cell_gid) return HCG_OK;
+  const int64_t nc = c->ncells;
+  if (c->cell_gid_cap < nc || !c->cell_gid) {
+    if (c->cell_gid) cudaFree(c->cell_gid);
+    CUDA_TRY(c, cudaMalloc(&c->cell_gid, sizeof(int64_t)*(size_t)std::max<int64_t>(nc, 1)));
+    c->cell_gid_cap = nc;
+  }
+  if (nc) CUDA_TRY(c, cudaMemcpy(c->cell_gid, c->h_cell_id.data(), sizeof(int64_t)*nc, cudaMemcpyHostToDevice));
+  c->cell_gid_dirty = false;
+  return HCG_OK;
+}
+
+hcg_status multi_velocity_sync(hcg_ctx* c) { return multi_field_sync(c, 0); }
+
+// per-vertex swap of a particle field of the shared cells: the rank that OWNS a vertex is authoritative.
+// field 0: velocity (every interpolation step; the alive flags are AND-ed in the same message);
+// field 1: repulsion force (after applyRepulsionForce / applyBoundaryRepulsionForce)
+hcg_status multi_field_sync(hcg_ctx* c, int field) {
   if (c->dom.n_ranks == 1) return HCG_OK;
   MultiState& m = c->multi;
+  double* const* arr = field == 0 ? c->vel : c->frep;
   hcg_status s;
   size_t ns[2], off_send[2], off_recv[2];
   size_t tot = 0;
@@ -197,7 +215,7 @@ hcg_status multi_velocity_sync(hcg_ctx* c) {
       if (!dst) return hcg_fail(c, HCG_ERR_STATE, "peer transport: neighbour receive buffer not mapped");
       dst += half*((size_t)m.face[f].n + 3*(size_t)m.face[f].total);
       k_pack_sync<<<m.face[f].n, 256, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n, m.face[f].total,
-          c->cell_base, c->cell_alive, c->pos[0], c->vel[0], c->vel[1], c->vel[2], dst,
+          c->cell_base, c->cell_alive, c->pos[0], arr[0], arr[1], arr[2], dst,
           c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
       KERNEL_CHECK(c);
     }
@@ -205,7 +223,7 @@ hcg_status multi_velocity_sync(hcg_ctx* c) {
     for (int f = 0; f < 2; f++) {
       if (!m.face[f].n || c->peer.link[f].rank < 0) continue;
       k_unpack_sync<<<m.face[f].n, 256, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n, m.face[f].total,
-          c->cell_base, c->cell_alive, c->pos[0], c->vel[0], c->vel[1], c->vel[2],
+          c->cell_base, c->cell_alive, c->pos[0], arr[0], arr[1], arr[2],
           c->peer.sync_recv[f] + half*((size_t)m.face[f].n + 3*(size_t)m.face[f].total),
           c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
       KERNEL_CHECK(c);
@@ -219,7 +237,7 @@ hcg_status multi_velocity_sync(hcg_ctx* c) {
   for (int f = 0; f < 2; f++) {
     if (!m.face[f].n) continue;
     k_pack_sync<<<m.face[f].n, 256, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n, m.face[f].total,
-        c->cell_base, c->cell_alive, c->pos[0], c->vel[0], c->vel[1], c->vel[2], m.sync_buf + off_send[f],
+        c->cell_base, c->cell_alive, c->pos[0], arr[0], arr[1], arr[2], m.sync_buf + off_send[f],
         c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
     KERNEL_CHECK(c);
   }
@@ -228,7 +246,7 @@ hcg_status multi_velocity_sync(hcg_ctx* c) {
   for (int f = 0; f < 2; f++) {
     if (!m.face[f].n) continue;
     k_unpack_sync<<<m.face[f].n, 256, 0, c->stream>>>(m.face[f].d_cells, m.face[f].d_off, m.face[f].n, m.face[f].total,
-        c->cell_base, c->cell_alive, c->pos[0], c->vel[0], c->vel[1], c->vel[2], m.sync_buf + off_recv[f],
+        c->cell_base, c->cell_alive, c->pos[0], arr[0], arr[1], arr[2], m.sync_buf + off_recv[f],
         c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
     KERNEL_CHECK(c);
   }
@@ -366,6 +384,7 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
     std::sort(list.begin(), list.end(), [&](int32_t a, int32_t b) { return c->h_cell_id[a] < c->h_cell_id[b]; });
     if ((s = upload_list(c, m.face[f], list))) return s;
   }
+  c->cell_gid_dirty = true;
   // union list + per-slot flag: the step advances unshared cells in the interpolation pass and the
   // shared ones after the velocity sync
   {

@@ -28,7 +28,7 @@ def _device_count():
     return n.value if rt.cudaGetDeviceCount(C.byref(n)) == 0 else 0
 
 
-def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, cadence, sync_every, f_limit, transport=1):
+def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, cadence, sync_every, f_limit, transport=1, rep=None):
     from hemocell_b200 import lib as H
     nx, ny, nz = dims
     nxl = nx // R
@@ -52,10 +52,13 @@ def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, 
             ctx.add_cells(t, cells, ids)                  # global list: the library keeps what it holds
             ctx.set_timescales(cadence, 1, 1)
             ctx.set_material_timescale(t, cadence)
+            if rep:
+                ctx.set_timescales(cadence, rep["every"], rep["every"])
+                ctx.set_repulsion(True, rep["k"], rep["cut"]); ctx.set_wall_repulsion(True, rep["kw"], rep["cutw"])
             ctx.iterate(steps)
             cid, _, alive = ctx.cells_info()
             out[r] = dict(pop=ctx.lattice_download(H.LAT_POP), pos=ctx.cells_download(H.P_POS),
-                          vel=ctx.cells_download(H.P_VEL), frc=ctx.cells_download(H.P_FORCE),
+                          vel=ctx.cells_download(H.P_VEL), frc=ctx.cells_download(H.P_FORCE), frep=ctx.cells_download(H.P_FREP),
                           ids=cid, alive=alive, count=ctx.count(), stats=ctx.exchange_stats())
             ctx.close()
         except Exception as e:          # noqa: BLE001
@@ -190,3 +193,55 @@ def test_two_processes_peer_ipc(tmp_path):
             seen.add(int(cid) - 100)
             U.assert_close(pos[slot], ref_pos[int(cid) - 100], f"rank {r} cell {cid} positions", rtol=1e-11, floor=1e-12)
     assert seen == set(range(len(centers)))
+
+
+@pytest.mark.parametrize("transport", [1, 0])
+def test_two_gpu_repulsion_matches_single_gpu(transport):
+    """cell-cell + wall repulsion across the slab face: bins over the padded slab, owner-computes, copies synced"""
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from hemocell_b200 import lib as H
+    R = 2
+    dims = (96, 32, 32); nx, ny, nz = dims
+    periodic = (1, 1, 0)
+    par = M.Parameters(dx=0.5e-6, dt=0.5e-7)
+    bc = np.zeros((6, 3)); bc[4] = (0.03, 0, 0); bc[5] = (0.01, 0, 0)
+    fl = U.couette_flags(nx, ny, nz).reshape(-1)
+    body = (1e-6, 0.0, 0.0); u0 = (0.02, 0.0, 0.0)
+    ct = O.rbc_celltype(par)
+    # two cells touching across the face x = 48, two across the periodic face x = 0/96, one hugging the z = 0 wall at the face
+    centers = [(44.0, 14.0, 16.0), (50.0, 16.2, 16.3), (93.0, 18.0, 12.0), (2.5, 16.0, 12.4), (47.0, 8.0, 9.3)]
+    cells = U.deformed_cells(ct, centers, 5, amp=0.0, stretch=(1, 1, 1))
+    # flat discs: rotate the wall cell so that it lies parallel to the wall (default orientation is fine for the others)
+    ids = np.arange(len(centers)) + 7
+    rep = dict(every=2, k=2e-22 / par.df * 50, cut=0.9e-6 / par.dx, kw=2e-22 / par.df * 50, cutw=1.2e-6 / par.dx)
+    steps, sync_every, cadence = 40, 5, 1
+    ctx = H.Context(nx, ny, nz, periodic, par.tau, device=0)
+    ctx.set_flags(fl)
+    for o in range(6):
+        ctx.set_bc_velocity(o, bc[o])
+    ctx.set_body_force(body); ctx.init_equilibrium(1.0, u0); ctx.set_force_limit(par.f_limit)
+    t = ctx.add_celltype(ct.model, ct.cc, ct.k)
+    ctx.add_cells(t, cells, ids)
+    ctx.set_timescales(cadence, rep["every"], rep["every"]); ctx.set_material_timescale(t, cadence)
+    ctx.set_repulsion(True, rep["k"], rep["cut"]); ctx.set_wall_repulsion(True, rep["kw"], rep["cutw"])
+    ctx.iterate(steps)
+    ref_pos = ctx.cells_download(H.P_POS).reshape(len(centers), ct.V, 3)
+    ref_frep = ctx.cells_download(H.P_FREP).reshape(len(centers), ct.V, 3)
+    alive_ref = ctx.count()[0]
+    ctx.close()
+    assert np.abs(ref_frep).max() > 0, "the set-up must produce repulsion forces"
+    out = _run_multi(R, dims, periodic, par.tau, fl, bc, body, ct, cells, ids, u0, steps, cadence, sync_every, par.f_limit, transport, rep)
+    assert sum(o["count"][0] for o in out) == alive_ref
+    seen = set()
+    for r in range(R):
+        o = out[r]
+        pos = o["pos"].reshape(-1, ct.V, 3); frep = o["frep"].reshape(-1, ct.V, 3)
+        for slot, (cid, al) in enumerate(zip(o["ids"], o["alive"])):
+            if cid < 0 or not al:
+                continue
+            k = int(cid) - 7
+            seen.add(k)
+            U.assert_close(pos[slot], ref_pos[k], f"rank {r} cell {cid} positions", rtol=1e-11, floor=1e-12)
+            U.assert_close(frep[slot], ref_frep[k], f"rank {r} cell {cid} repulsion forces", rtol=1e-9, floor=1e-14 * np.abs(ref_frep).max())
+    assert len(seen) == alive_ref
