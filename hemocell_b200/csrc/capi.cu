@@ -376,6 +376,10 @@ hcg_status hcg_lattice_download(hcg_ctx* c, int32_t field, double* out) {
       if ((s = lat_unpad(c, c->U, c->staging, 3, 1))) return s;
       CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*c->Nl, cudaMemcpyDeviceToHost, c->stream));
     }
+  } else if (field == HCG_LAT_PINEQ) {
+    if ((s = ensure_staging(c, sizeof(double)*6*c->Nl))) return s;
+    if ((s = lat_pineq(c, c->staging))) return s;
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*6*c->Nl, cudaMemcpyDeviceToHost, c->stream));
   } else return hcg_fail(c, HCG_ERR_ARG, "lattice_download: unknown field");
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return HCG_OK;
@@ -763,6 +767,18 @@ hcg_status hcg_cells_volume_area(hcg_ctx* c, double* volume, double* area) {
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   CUDA_TRY(c, cudaMemcpy(volume, c->staging, sizeof(double)*c->ncells, cudaMemcpyDeviceToHost));
   CUDA_TRY(c, cudaMemcpy(area, c->staging + c->ncells, sizeof(double)*c->ncells, cudaMemcpyDeviceToHost));
+  return HCG_OK;
+}
+
+hcg_status hcg_cells_stretch(hcg_ctx* c, double* stretch) {
+  if (!c || !stretch) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (c->ncells == 0) return HCG_OK;
+  hcg_status s = ensure_staging(c, sizeof(double)*c->ncells); if (s) return s;
+  CUDA_TRY(c, cudaMemsetAsync(c->staging, 0, sizeof(double)*c->ncells, c->stream));
+  if ((s = mech_stretch(c, c->staging))) return s;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  CUDA_TRY(c, cudaMemcpy(stretch, c->staging, sizeof(double)*c->ncells, cudaMemcpyDeviceToHost));
   return HCG_OK;
 }
 

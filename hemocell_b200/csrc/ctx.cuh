@@ -177,6 +177,7 @@ hcg_status lat_halo_exchange_u(hcg_ctx* c);
 hcg_status lat_exchange_byte_planes(hcg_ctx* c, uint8_t* buf, int ghost_default);   // per-node byte field: face planes -> neighbours' ghosts
 hcg_status lat_pop_to_reference(hcg_ctx* c, double* dst_dev);      // S_q(n) = g_q(n - c_q), compact slab
 hcg_status lat_pop_from_reference(hcg_ctx* c, const double* src_dev);
+hcg_status lat_pineq(hcg_ctx* c, double* dst_dev);                 // off-equilibrium momentum flux, compact SoA [6][Nl]
 hcg_status lat_velocity_stats(hcg_ctx* c, double* vmin, double* vmax, double* vmean);
 // ibm.cu
 hcg_status ibm_spread(hcg_ctx* c);
@@ -189,6 +190,7 @@ hcg_status ibm_advance_shared(hcg_ctx* c);                 // ... and the shared
 hcg_status mech_apply(hcg_ctx* c, int ctype, bool components);
 hcg_status mech_bbox(hcg_ctx* c, double* out_dev);
 hcg_status mech_volume_area(hcg_ctx* c, double* vol_dev, double* area_dev);
+hcg_status mech_stretch(hcg_ctx* c, double* out_dev);   // max pairwise vertex distance per cell slot
 // spread_sorted.cu
 bool spread_sorted_supported(const CellTypeHost& th);
 hcg_status spread_sorted_rebuild(hcg_ctx* c);

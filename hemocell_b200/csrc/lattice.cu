@@ -209,6 +209,40 @@ k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restri
   if (RESET) { double2* Fw = reinterpret_cast<double2*>(F + 4*n); Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0); }
 }
 
+// Off-equilibrium momentum flux of the post-stream populations (output path only: the "ShearStress"
+// and "StrainRate" fluid fields of io/FluidHdf5IO.hh:406-433, 503-541 are multiples of it):
+//   PiNeq_ab = sum_q c_qa c_qb fbar_q - cs2 rhoBar delta_ab - j_a j_b / rho,  order xx xy xz yy yz zz
+// (Palabos momentTemplates::compute_rhoBar_j_PiNeq, restated from memory).  BounceBack nodes: 0.
+// dst is compact SoA [6][Nl]; slot 6 (optional, dst7 != 0) receives rho for the strain-rate prefactor.
+__global__ void __launch_bounds__(256)
+k_pineq(const double* __restrict__ g, const uint8_t* __restrict__ flags, LatArgs a, int64_t count,
+        double* __restrict__ dst) {
+  constexpr int CX[19] = {0,-1,0,0,-1,-1,-1,-1,0,0, 1,0,0,1,1,1,1,0,0};
+  constexpr int CY[19] = {0,0,-1,0,-1,1,0,0,-1,-1, 0,1,0,1,-1,0,0,1,1};
+  constexpr int CZ[19] = {0,0,0,-1,0,0,-1,1,-1,1, 0,0,1,0,0,1,-1,1,-1};
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t n = i + a.P;
+  const int rem = (int)(i % a.P);
+  const int y = rem / a.nz, z = rem - y*a.nz;
+  double f[19];
+  pull19(g, a, n, y, z, f);
+  double rhoBar, j[3];
+  moments19(f, rhoBar, j);
+  double pi[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < 19; q++) {
+    pi[0] += CX[q]*CX[q]*f[q]; pi[1] += CX[q]*CY[q]*f[q]; pi[2] += CX[q]*CZ[q]*f[q];
+    pi[3] += CY[q]*CY[q]*f[q]; pi[4] += CY[q]*CZ[q]*f[q]; pi[5] += CZ[q]*CZ[q]*f[q];
+  }
+  const double invRho = 1.0/(1.0 + rhoBar), cs2 = 1.0/3.0;
+  pi[0] -= cs2*rhoBar + invRho*j[0]*j[0]; pi[1] -= invRho*j[0]*j[1]; pi[2] -= invRho*j[0]*j[2];
+  pi[3] -= cs2*rhoBar + invRho*j[1]*j[1]; pi[4] -= invRho*j[1]*j[2]; pi[5] -= cs2*rhoBar + invRho*j[2]*j[2];
+  const bool bb = flags[n] == HCG_BOUNCEBACK;
+#pragma unroll
+  for (int k = 0; k < 6; k++) dst[(int64_t)k*count + i] = bb ? 0.0 : pi[k];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Row-pipelined lattice kernels (EXPERIMENTAL, opt-in with HCG_K1_ROWS=1; nz even, a few rows must fit shared memory).
 // Measured on B200 (256^3): 1.05 ms vs 0.945 ms for the plain one-thread-per-node kernel, so the plain kernel is the default.
@@ -801,6 +835,13 @@ static hcg_status moments_rows(hcg_ctx* c, bool reset_force, int row0, int row1)
     if (reset_force) k_moments<true, false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, nullptr, nullptr);
     else k_moments<false, false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, nullptr, nullptr);
   }
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+
+hcg_status lat_pineq(hcg_ctx* c, double* dst_dev) {
+  LatArgs a = make_args(c);
+  k_pineq<<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->g[c->cur], c->flags, a, c->Nl, dst_dev);
   KERNEL_CHECK(c);
   return HCG_OK;
 }

@@ -284,6 +284,35 @@ __global__ void k_volume_area(const double* __restrict__ x, const double* __rest
   if (lane == 0) { vol[first_cell + c] = v/6.0; area[first_cell + c] = ar; }
 }
 
+// CellInformationFunctionals::calculateCellStretch (helper/cellInfo.cpp:103-121): largest pairwise vertex
+// distance of a cell.  One CTA per cell, positions staged in shared memory, each thread scans the pairs (i, j > i)
+// of its vertices i; block-wide max through warp shuffles.
+__global__ void __launch_bounds__(256)
+k_stretch(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+          int64_t first_cell, int64_t first_particle, int V, double* __restrict__ out) {
+  extern __shared__ double sp[];
+  double* sx = sp; double* sy = sp + V; double* sz = sp + 2*V;
+  __shared__ double wmax[8];
+  const int64_t base = first_particle + (int64_t)blockIdx.x*V;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) { sx[i] = x[base + i]; sy[i] = y[base + i]; sz[i] = z[base + i]; }
+  __syncthreads();
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const double ax = sx[i], ay = sy[i], az = sz[i];
+    for (int j = i + 1; j < V; j++) {
+      const double dx = ax - sx[j], dy = ay - sy[j], dz = az - sz[j];
+      mx = fmax(mx, dx*dx + dy*dy + dz*dz);
+    }
+  }
+  for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, wmax[w]);
+    out[first_cell + blockIdx.x] = sqrt(mx);
+  }
+}
+
 template <int MODEL, bool VISC>
 hcg_status launch(hcg_ctx* c, const MechArgs& a, int64_t ncells, size_t smem, int threads, bool comp) {
   if (comp) {
@@ -345,6 +374,16 @@ hcg_status mech_volume_area(hcg_ctx* c, double* vol_dev, double* area_dev) {
     if (th.n_cells == 0) continue;
     k_volume_area<<<(unsigned)((th.n_cells + 7)/8), 256, 0, c->stream>>>(c->pos[0], c->pos[1], c->pos[2],
         th.first_cell, th.first_particle, th.n_cells, th.d.V, th.d.T, th.d.tri, vol_dev, area_dev);
+    KERNEL_CHECK(c);
+  }
+  return HCG_OK;
+}
+
+hcg_status mech_stretch(hcg_ctx* c, double* out_dev) {
+  for (auto& th : c->types) {
+    if (th.n_cells == 0) continue;
+    k_stretch<<<(unsigned)th.n_cells, 256, sizeof(double)*3*th.d.V, c->stream>>>(c->pos[0], c->pos[1], c->pos[2],
+        th.first_cell, th.first_particle, th.d.V, out_dev);
     KERNEL_CHECK(c);
   }
   return HCG_OK;

@@ -5,6 +5,7 @@
 //              helper/fluidInfo.cpp, helper/profiler.cpp, io/writeCellInfoCSV.cpp
 #include "hemo_mesh.h"          // hemo::host:: set-up code (before hemocell.h: its enum names are macros there)
 #include "hemo_xml.h"
+#include "hemo_h5.h"
 #include "hemocell.h"
 
 #include <algorithm>
@@ -700,6 +701,230 @@ void HemoCell::loadCheckPoint() {
   loadParticlesIsCalled = true;
 }
 
+// ---- HDF5 output ---------------------------------------------------------------------------------------
+// File names, dataset names, shapes, element types, root attributes, SI scaling and chunking follow
+// io/ParticleHdf5IO.cpp:60-194 and io/FluidHdf5IO.hh:74-211; the container is written by hemo_h5 (no libhdf5 here).
+namespace {
+int h5_deflate_level() { const char* e = getenv("HEMOCELL_H5_DEFLATE"); return e ? atoi(e) : 7; }   // < 0: contiguous, uncompressed
+std::string h5_name(const HemoCell& h, const std::string& identifier) {
+  return plb::global::directories().getOutputDir() + "/hdf5/" + zeroPadNumber(h.iter) + '/' + identifier + "." + zeroPadNumber(h.iter) +
+         ".p." + std::to_string(plb::global::mpi().getRank()) + ".h5";
+}
+void h5_common_attrs(h5::Writer& w, const HemoCell& h) {
+  const double dx = param::dx, dt = param::dt; const int64_t it = h.iter; const int32_t id = plb::global::mpi().getRank();
+  w.attribute("dx", h5::F64, &dx, 1); w.attribute("dt", h5::F64, &dt, 1);
+  w.attribute("iteration", h5::I64, &it, 1); w.attribute("processorId", h5::I32, &id, 1);
+}
+void write_particle_h5(HemoCell& h, HemoCellField& field) {
+  hcg_ctx* c = h.ctx();
+  h5::Writer w(h5_name(h, field.name), h5_deflate_level());
+  if (!w.ok()) fatal("(HemoCell) (Output) cannot create " + h5_name(h, field.name));
+  h5_common_attrs(w, h);
+  const int64_t nproc = plb::global::mpi().getSize();
+  w.attribute("numberOfProcessors", h5::I64, &nproc, 1);
+  int64_t nc = 0, np = 0;
+  ck(c, hcg_cells_capacity(c, &nc, &np), "hcg_cells_capacity");
+  std::vector<int64_t> ids(nc), base(nc); std::vector<int32_t> types(nc); std::vector<uint8_t> alive(nc);
+  if (nc) ck(c, hcg_cells_info(c, ids.data(), types.data(), alive.data()), "hcg_cells_info");
+  { int64_t p = 0; for (int64_t k = 0; k < nc; k++) { base[k] = p; p += (*h.cellfields)[(unsigned)types[k]]->numVertex; } }
+  // cells of this type in ascending cell id (the reference walks a std::map keyed by cell id); multi-GPU: a cell
+  // shared by two ranks is written by the one that holds its centre, so every cell appears in exactly one file
+  const int t = field.impl->device_ctype, V = field.numVertex;
+  std::vector<double> pos((size_t)3*np);
+  if (np) ck(c, hcg_cells_download(c, HCG_P_POS, pos.data()), "download");
+  GpuLattice* g = h.lattice->gpu();
+  const double x_lo = (double)g->rank()*g->nxl() - 0.5, x_hi = x_lo + g->nxl();
+  std::vector<std::pair<int64_t, int64_t>> order;       // (cell id, slot)
+  for (int64_t k = 0; k < nc; k++) {
+    if (!alive[k] || ids[k] < 0 || types[k] != t) continue;
+    if (g->size() > 1) {
+      double cx = 0; for (int v = 0; v < V; v++) cx += pos[3*(base[k] + v)]; cx /= V;
+      cx = std::fmod(std::fmod(cx + 0.5, (double)g->nx) + g->nx, (double)g->nx) - 0.5;
+      if (!(cx >= x_lo && cx < x_hi)) continue;
+    }
+    order.push_back({ids[k], k});
+  }
+  std::sort(order.begin(), order.end());
+  const uint64_t N = (uint64_t)order.size()*V;
+  const std::vector<uint64_t> chunk3 = {std::max<uint64_t>(1, std::min<uint64_t>(1000, N)), 3}, chunk1 = {chunk3[0], 1};
+  std::vector<double> buf((size_t)3*np);
+  std::vector<float> out((size_t)3*N);
+  auto vector_field = [&](int fld, const char* name, double scale) {
+    if (np) ck(c, hcg_cells_download(c, fld, buf.data()), "download");
+    size_t n = 0;
+    for (auto& o : order) for (int v = 0; v < V; v++) for (int d = 0; d < 3; d++) out[n++] = (float)(buf[3*(base[o.second] + v) + d]*scale);
+    w.dataset(name, h5::F32, {N, 3}, out.data(), chunk3);
+  };
+  const bool si = h.outputInSiUnits;
+  for (int var : field.desiredOutputVariables) {
+    switch (var) {
+      case OUTPUT_POSITION: {
+        vector_field(HCG_P_POS, "Position", si ? param::dx : 1.0);
+        const int64_t nP = (int64_t)N; w.attribute("numberOfParticles", h5::I64, &nP, 1);
+        break; }
+      case OUTPUT_VELOCITY: vector_field(HCG_P_VEL, "Velocity", si ? param::dx/param::dt : 1.0); break;
+      case OUTPUT_FORCE: {
+        // force_total = sum of the constitutive parts + repulsion (core/hemoCellParticle.h), valid after the forced model update above
+        if (np) ck(c, hcg_cells_download(c, HCG_P_FORCE, buf.data()), "download");
+        std::vector<double> rep((size_t)3*np); if (np) ck(c, hcg_cells_download(c, HCG_P_FREP, rep.data()), "download");
+        size_t n = 0; const double sc = si ? param::df : 1.0;
+        for (auto& o : order) for (int v = 0; v < V; v++) for (int d = 0; d < 3; d++) { const size_t q = 3*(base[o.second] + v) + d; out[n++] = (float)((buf[q] + rep[q])*sc); }
+        w.dataset("Total force", h5::F32, {N, 3}, out.data(), chunk3);
+        break; }
+      case OUTPUT_FORCE_VOLUME: vector_field(HCG_P_F_VOLUME, "Volume force", si ? param::df : 1.0); break;
+      case OUTPUT_FORCE_AREA: vector_field(HCG_P_F_AREA, "Area force", si ? param::df : 1.0); break;
+      case OUTPUT_FORCE_LINK: vector_field(HCG_P_F_LINK, "Link force", si ? param::df : 1.0); break;
+      case OUTPUT_FORCE_BENDING: vector_field(HCG_P_F_BEND, "Bending force", si ? param::df : 1.0); break;
+      case OUTPUT_FORCE_VISC: vector_field(HCG_P_F_VISC, "Viscous force", si ? param::df : 1.0); break;
+      case OUTPUT_FORCE_INNER_LINK: vector_field(HCG_P_F_INNER, "Inner link force", si ? param::df : 1.0); break;
+      case OUTPUT_FORCE_REPULSION: vector_field(HCG_P_FREP, "Repulsion force", si ? param::df : 1.0); break;
+      case OUTPUT_VERTEX_ID: case OUTPUT_CELL_ID: case OUTPUT_RES_TIME: {
+        std::vector<float> one((size_t)N); size_t n = 0;
+        for (auto& o : order) for (int v = 0; v < V; v++) one[n++] = var == OUTPUT_VERTEX_ID ? (float)v : (var == OUTPUT_CELL_ID ? (float)o.first : 0.0f);   // residence time is not tracked on the device path
+        w.dataset(var == OUTPUT_VERTEX_ID ? "Vertex Id" : (var == OUTPUT_CELL_ID ? "Cell Id" : "Res Time"), h5::F32, {N, 1}, one.data(), chunk1);
+        break; }
+      default: break;      // the reference skips variables without a particle output function (io/hemoCellParticleFieldOutputFunctions.cpp:46-50)
+    }
+  }
+  if (field.outputTriangles) {
+    const auto& tri = field.impl->tables.cc.triangle_list;
+    const uint64_t nT = (uint64_t)order.size()*tri.size();
+    std::vector<int32_t> tt((size_t)3*nT); size_t n = 0; int32_t counter = 0;
+    for (size_t k = 0; k < order.size(); k++) { for (auto& q : tri) for (int d = 0; d < 3; d++) tt[n++] = q[d] + counter; counter += V; }
+    w.dataset("Triangles", h5::I32, {nT, 3}, tt.data(), {std::max<uint64_t>(1, std::min<uint64_t>(1000, nT)), 3});
+    const int64_t v = (int64_t)nT; w.attribute("numberOfTriangles", h5::I64, &v, 1);
+  }
+  if (std::find(field.desiredOutputVariables.begin(), field.desiredOutputVariables.end(), OUTPUT_INNER_LINKS) != field.desiredOutputVariables.end()) {
+    const auto& il = field.impl->tables.cc.inner_edge_list;
+    const uint64_t nL = (uint64_t)order.size()*il.size();
+    if (nL) {
+      std::vector<int32_t> ll((size_t)2*nL); size_t n = 0; int32_t counter = 0;
+      for (size_t k = 0; k < order.size(); k++) { for (auto& q : il) for (int d = 0; d < 2; d++) ll[n++] = q[d] + counter; counter += V; }
+      w.dataset("InnerLinks", h5::I32, {nL, 2}, ll.data(), {std::max<uint64_t>(1, std::min<uint64_t>(1000, nL)), 2});
+      const int64_t v = (int64_t)nL; w.attribute("numberOfInnerLinks", h5::I64, &v, 1);
+    }
+  }
+  if (!w.close()) fatal("(HemoCell) (Output) writing " + h5_name(h, field.name) + " failed: " + w.error());
+}
+
+void write_fluid_h5(HemoCell& h) {
+  const std::vector<int>& vars = h.cellfields->desiredFluidOutputVariables;
+  if (vars.empty()) return;
+  hcg_ctx* c = h.ctx();
+  GpuLattice* g = h.lattice->gpu();
+  h5::Writer w(h5_name(h, "Fluid"), h5_deflate_level());
+  if (!w.ok()) fatal("(HemoCell) (Output) cannot create " + h5_name(h, "Fluid"));
+  h5_common_attrs(w, h);
+  // the block of this rank plus an envelope of one node on every side "for paraview" (io/FluidHdf5IO.hh:103-120);
+  // datasets are [Nz][Ny][Nx][C]
+  const int nxl = g->nxl(), ny = g->ny, nz = g->nz, x0 = g->rank()*nxl;
+  const uint64_t Nx = nxl + 2, Ny = ny + 2, Nz = nz + 2, nCells = Nx*Ny*Nz;
+  const int32_t ncells = (int32_t)nCells, sub[3] = {(int32_t)Nz, (int32_t)Ny, (int32_t)Nx};
+  const bool si = h.outputInSiUnits;
+  float dxdydz[3] = {1.f, 1.f, 1.f}, rel[3] = {-1.5f, -1.5f, (float)(x0 - 1.5)};
+  if (si) for (int k = 0; k < 3; k++) { rel[k] *= (float)param::dx; dxdydz[k] = (float)param::dx; }
+  w.attribute("numberOfCells", h5::I32, &ncells, 1); w.attribute("subdomainSize", h5::I32, sub, 3);
+  w.attribute("relativePosition", h5::F32, rel, 3); w.attribute("dxdydz", h5::F32, dxdydz, 3);
+  const std::vector<uint64_t> chunk = {std::min<uint64_t>(1000, Nz), std::min<uint64_t>(1000, Ny), std::min<uint64_t>(1000, Nx)};
+  const int64_t Nl = (int64_t)nxl*ny*nz;
+  // envelope node -> source node of this rank's slab, or -1 (outside a non-periodic face, or in a neighbouring
+  // rank's slab: those envelope values are left at the Palabos background default, rho = 1, u = 0)
+  auto src = [&](int64_t ix, int64_t iy, int64_t iz) -> int64_t {
+    int64_t x = ix - 1, y = iy - 1, z = iz - 1;
+    if (x < 0 || x >= nxl) { if (g->size() > 1 || !g->periodic[0]) return -1; x = (x + nxl) % nxl; }
+    if (y < 0 || y >= ny) { if (!g->periodic[1]) return -1; y = (y + ny) % ny; }
+    if (z < 0 || z >= nz) { if (!g->periodic[2]) return -1; z = (z + nz) % nz; }
+    return z + (int64_t)nz*(y + (int64_t)ny*x);
+  };
+  std::vector<int64_t> map((size_t)nCells);
+  { size_t n = 0; for (uint64_t iz = 0; iz < Nz; iz++) for (uint64_t iy = 0; iy < Ny; iy++) for (uint64_t ix = 0; ix < Nx; ix++) map[n++] = src(ix, iy, iz); }
+  std::vector<double> buf;
+  std::vector<float> out;
+  // gather `C` components of a downloaded SoA field [C][Nl] into [Nz][Ny][Nx][C] floats
+  auto emit = [&](const std::string& name, int C, double scale, double outside) {
+    out.assign((size_t)nCells*C, 0.f);
+    for (size_t n = 0; n < (size_t)nCells; n++) for (int k = 0; k < C; k++) out[n*C + k] = (float)((map[n] >= 0 ? buf[(size_t)k*Nl + map[n]] : outside)*scale);
+    std::vector<uint64_t> ch = chunk; ch.push_back((uint64_t)C);
+    w.dataset(name, h5::F32, {Nz, Ny, Nx, (uint64_t)C}, out.data(), ch);
+  };
+  const uint8_t* flags = g->flags.data() + (int64_t)x0*ny*nz;
+  const double omega = g->omega;
+  for (int var : vars) {
+    switch (var) {
+      case OUTPUT_VELOCITY:
+        buf.resize((size_t)3*Nl); ck(c, hcg_lattice_download(c, HCG_LAT_VELOCITY, buf.data()), "download");
+        emit("Velocity", 3, si ? param::dx/param::dt : 1.0, 0.0); break;
+      case OUTPUT_FORCE:
+        buf.resize((size_t)3*Nl); ck(c, hcg_lattice_download(c, HCG_LAT_FORCE, buf.data()), "download");
+        emit("Force", 3, si ? param::df : 1.0, 0.0); break;
+      case OUTPUT_DENSITY:
+        buf.resize((size_t)Nl); ck(c, hcg_lattice_download(c, HCG_LAT_DENSITY, buf.data()), "download");
+        emit("Density", 1, si ? param::df/(param::dx*param::dx) : 1.0, 1.0); break;
+      case OUTPUT_BOUNDARY:
+        buf.resize((size_t)Nl); for (int64_t n = 0; n < Nl; n++) buf[n] = flags[n] == HCG_BOUNCEBACK ? 1.0 : 0.0;
+        emit("Boundary", 1, 1.0, 0.0); break;
+      case OUTPUT_OMEGA:
+        buf.resize((size_t)Nl); for (int64_t n = 0; n < Nl; n++) buf[n] = flags[n] == HCG_BOUNCEBACK ? 0.0 : omega;
+        emit("Omega", 1, si ? param::df/(param::dx*param::dx) : 1.0, omega); break;
+      case OUTPUT_CELL_DENSITY: {
+        // LSP count per nearest node x volumeFractionOfLspPerNode (io/FluidHdf5IO.hh:376-404)
+        int64_t nc = 0, np = 0; ck(c, hcg_cells_capacity(c, &nc, &np), "hcg_cells_capacity");
+        std::vector<int64_t> ids(nc); std::vector<int32_t> types(nc); std::vector<uint8_t> alive(nc);
+        if (nc) ck(c, hcg_cells_info(c, ids.data(), types.data(), alive.data()), "hcg_cells_info");
+        std::vector<double> pos((size_t)3*np); if (np) ck(c, hcg_cells_download(c, HCG_P_POS, pos.data()), "download");
+        for (unsigned i = 0; i < h.cellfields->size(); i++) {
+          HemoCellField& f = *(*h.cellfields)[i];
+          out.assign((size_t)nCells, 0.f);
+          int64_t p = 0;
+          for (int64_t k = 0; k < nc; k++) {
+            const int V = (*h.cellfields)[(unsigned)types[k]]->numVertex;
+            if (alive[k] && ids[k] >= 0 && types[k] == f.impl->device_ctype) for (int v = 0; v < V; v++) {
+              int64_t q[3]; const int64_t dims[3] = {g->nx, ny, nz};
+              for (int d = 0; d < 3; d++) { q[d] = (int64_t)std::floor(pos[3*(p + v) + d] + 0.5); if (g->periodic[d]) q[d] = ((q[d] % dims[d]) + dims[d]) % dims[d]; }
+              const int64_t lx = q[0] - x0;
+              if (lx < 0 || lx >= nxl || q[1] < 0 || q[1] >= ny || q[2] < 0 || q[2] >= nz) continue;
+              out[(size_t)((lx + 1) + (q[1] + 1)*(int64_t)Nx + (q[2] + 1)*(int64_t)(Nx*Ny))] += 1.f;
+            }
+            p += V;
+          }
+          if (si) for (auto& v : out) v *= (float)f.volumeFractionOfLspPerNode;
+          std::vector<uint64_t> ch = chunk; ch.push_back(1);
+          w.dataset("CellDensity_" + f.name, h5::F32, {Nz, Ny, Nx, 1}, out.data(), ch);
+        }
+        break; }
+      case OUTPUT_SHEAR_STRESS:
+        // Cell::computeShearStress of the BGK dynamics: (omega/2 - 1) PiNeq (Palabos, restated from memory)
+        buf.resize((size_t)6*Nl); ck(c, hcg_lattice_download(c, HCG_LAT_PINEQ, buf.data()), "download");
+        emit("ShearStress", 6, (0.5*omega - 1.0)*(si ? param::df/(param::dx*param::dx) : 1.0), 0.0); break;
+      case OUTPUT_STRAIN_RATE: {
+        // computeStrainRateFromStress: S = -omega invCs2 / (2 rho) PiNeq (Palabos, restated from memory)
+        buf.resize((size_t)6*Nl); ck(c, hcg_lattice_download(c, HCG_LAT_PINEQ, buf.data()), "download");
+        std::vector<double> rho((size_t)Nl); ck(c, hcg_lattice_download(c, HCG_LAT_DENSITY, rho.data()), "download");
+        for (int k = 0; k < 6; k++) for (int64_t n = 0; n < Nl; n++) buf[(size_t)k*Nl + n] *= -omega*3.0/(2.0*rho[n]);
+        emit("StrainRate", 6, si ? 1.0/param::dt : 1.0, 0.0); break; }
+      case OUTPUT_SHEAR_RATE: {
+        // central differences of the node velocity, [d u_a / d x_b] at index 3a + b (io/FluidHdf5IO.hh:437-501)
+        std::vector<double> u((size_t)3*Nl); ck(c, hcg_lattice_download(c, HCG_LAT_VELOCITY, u.data()), "download");
+        out.assign((size_t)nCells*9, 0.f);
+        const double sc = si ? 1.0/param::dt : 1.0;
+        size_t n = 0;
+        for (uint64_t iz = 0; iz < Nz; iz++) for (uint64_t iy = 0; iy < Ny; iy++) for (uint64_t ix = 0; ix < Nx; ix++, n++) {
+          const int64_t nb[3][2] = {{src(ix + 1, iy, iz), src((int64_t)ix - 1, iy, iz)}, {src(ix, iy + 1, iz), src(ix, (int64_t)iy - 1, iz)}, {src(ix, iy, iz + 1), src(ix, iy, (int64_t)iz - 1)}};
+          for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+            const double up = nb[b][0] >= 0 ? u[(size_t)a*Nl + nb[b][0]] : 0.0, um = nb[b][1] >= 0 ? u[(size_t)a*Nl + nb[b][1]] : 0.0;
+            out[n*9 + 3*a + b] = (float)((up - um)/2*sc);
+          }
+        }
+        std::vector<uint64_t> ch = chunk; ch.push_back(9);
+        w.dataset("ShearRate", h5::F32, {Nz, Ny, Nx, 9}, out.data(), ch);
+        break; }
+      default: break;
+    }
+  }
+  if (!w.close()) fatal("(HemoCell) (Output) writing " + h5_name(h, "Fluid") + " failed: " + w.error());
+}
+}  // namespace
+
 void HemoCell::writeOutput() {
   const double el = global.statistics.elapsed();
   const std::string tpi = (iter != lastOutputAt) ? Profiler::toString((el - lastOutput)/(iter - lastOutputAt)) : "0.00";
@@ -715,7 +940,10 @@ void HemoCell::writeOutput() {
   const std::string out = plb::global::directories().getOutputDir();
   if (plb::global::mpi().isMainProcessor()) { mkpath(out + "/hdf5/" + zeroPadNumber(iter)); mkpath(out + "/csv"); }
   plb::global::mpi().barrier();
-  // CSV cell info (io/writeCellInfoCSV.cpp:47-70); the HDF5 field/particle files are SURVEY.md 8(f1), not written yet
+  // HDF5 particle files per cell type and the fluid file of this rank's block (io/ParticleHdf5IO.cpp, io/FluidHdf5IO.hh)
+  for (unsigned i = 0; i < cellfields->size(); i++) write_particle_h5(*this, *(*cellfields)[i]);
+  write_fluid_h5(*this);
+  // CSV cell info (io/writeCellInfoCSV.cpp:47-70)
   CellInformationFunctionals::calculateCellInformation(this);
   if (plb::global::mpi().getSize() == 1) {
     std::vector<std::ofstream> csv(cellfields->size());
@@ -790,19 +1018,11 @@ void CellInformationFunctionals::calculateCellPosition(HemoCell* h) {
   }
 }
 void CellInformationFunctionals::calculateCellStretch(HemoCell* h) {
-  CellSnapshot s = snapshot(h); if (!s.np) return;
-  std::vector<double> pos(3*s.np);
-  ck(h->ctx(), hcg_cells_download(h->ctx(), HCG_P_POS, pos.data()), "download");
-  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0) {
-    const int V = (*h->cellfields)[(unsigned)s.types[k]]->numVertex;
-    const double* p = pos.data() + 3*s.base[k];
-    double mx = 0;
-    for (int i = 0; i < V; i++) for (int j = i + 1; j < V; j++) {
-      const double dx = p[3*i]-p[3*j], dy = p[3*i+1]-p[3*j+1], dz = p[3*i+2]-p[3*j+2];
-      mx = std::max(mx, dx*dx + dy*dy + dz*dz);
-    }
-    entry(s, k).stretch = std::sqrt(mx);
-  }
+  // max pairwise vertex distance per cell (helper/cellInfo.cpp:103-121), one CTA per cell on the device
+  CellSnapshot s = snapshot(h); if (!s.nc) return;
+  std::vector<double> st(s.nc);
+  ck(h->ctx(), hcg_cells_stretch(h->ctx(), st.data()), "hcg_cells_stretch");
+  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0) entry(s, k).stretch = st[k];
 }
 void CellInformationFunctionals::calculateCellInformation(HemoCell* h) {
   clear_list();

@@ -1,6 +1,7 @@
 // extern "C" view of the host-side set-up code (include/hemocell_host.h)
 #include "hemocell_host.h"
 #include "hemo_mesh.h"
+#include "hemo_h5.h"
 #include <cstring>
 #include <exception>
 #include <string>
@@ -68,6 +69,35 @@ int64_t hch_place_cells(const hch_celltype* h, const double* rows6, int64_t n_ro
     memcpy(out_ids, ids.data(), ids.size()*sizeof(int64_t));
     return (int64_t)ids.size();
   } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+struct hch_h5 { hemo::h5::Writer w; hch_h5(const char* p, int l) : w(p, l) {} };
+hch_h5* hch_h5_create(const char* path, int32_t deflate_level) {
+  if (!path) { g_err = "null argument"; return nullptr; }
+  hch_h5* h = new hch_h5(path, deflate_level);
+  if (!h->w.ok()) { g_err = h->w.error(); delete h; return nullptr; }
+  return h;
+}
+int32_t hch_h5_attribute(hch_h5* h, const char* name, int32_t type, const void* data, int64_t n) {
+  if (!h || !name || !data || type < 0 || type > 3 || n < 1) { g_err = "bad argument"; return -1; }
+  h->w.attribute(name, (hemo::h5::Type)type, data, (size_t)n);
+  return 0;
+}
+int32_t hch_h5_dataset(hch_h5* h, const char* name, int32_t type, int32_t rank, const uint64_t* dims,
+                       const void* data, const uint64_t* chunk) {
+  if (!h || !name || !dims || type < 0 || type > 3 || rank < 1 || rank > 8) { g_err = "bad argument"; return -1; }
+  std::vector<uint64_t> d(dims, dims + rank), c;
+  if (chunk) c.assign(chunk, chunk + rank);
+  h->w.dataset(name, (hemo::h5::Type)type, d, data, c);
+  if (!h->w.ok()) { g_err = h->w.error(); return -1; }
+  return 0;
+}
+int32_t hch_h5_close(hch_h5* h) {
+  if (!h) return -1;
+  const bool ok = h->w.close();
+  if (!ok) g_err = h->w.error();
+  delete h;
+  return ok ? 0 : -1;
 }
 
 }  // extern "C"

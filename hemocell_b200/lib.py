@@ -17,7 +17,7 @@ c_u8p = C.POINTER(C.c_uint8)
 
 FLUID, BOUNCEBACK, VEL_XN, VEL_XP, VEL_YN, VEL_YP, VEL_ZN, VEL_ZP = range(8)
 MODEL_RBC, MODEL_PLT = 0, 1
-LAT_POP, LAT_FORCE, LAT_VELOCITY, LAT_DENSITY = range(4)
+LAT_POP, LAT_FORCE, LAT_VELOCITY, LAT_DENSITY, LAT_PINEQ = range(5)
 P_POS, P_VEL, P_FORCE, P_FREP, P_F_AREA, P_F_VOLUME, P_F_BEND, P_F_LINK, P_F_VISC, P_F_INNER = range(10)
 
 
@@ -51,7 +51,7 @@ hcg_cells_upload hcg_cells_download hcg_cells_info hcg_cells_add_force hcg_cellt
 hcg_set_force_limit hcg_set_timescales hcg_set_material_timescale hcg_set_repulsion hcg_set_wall_repulsion
 hcg_set_spread_mode hcg_set_exchange hcg_set_transport hcg_exchange_stats hcg_set_iteration hcg_get_iteration hcg_iterate hcg_fluid_warmup hcg_op_repulsion hcg_op_wall_repulsion
 hcg_op_spread hcg_op_collide_stream hcg_op_interpolate hcg_op_sync hcg_op_advance hcg_op_mechanics
-hcg_op_zero_force hcg_cells_bbox hcg_cells_volume_area hcg_fluid_velocity_stats hcg_timers_enable
+hcg_op_zero_force hcg_cells_bbox hcg_cells_volume_area hcg_cells_stretch hcg_fluid_velocity_stats hcg_timers_enable
 hcg_timers hcg_timers_reset hcg_launch_count hcg_synchronize hcg_iterate_timed""".split()
 
 _lib = None
@@ -147,7 +147,7 @@ class Context:
         self._ck(self.L.hcg_lattice_upload(self.h, C.c_int32(field), _p(a)))
 
     def lattice_download(self, field):
-        n = {LAT_POP: 19, LAT_FORCE: 3, LAT_VELOCITY: 3, LAT_DENSITY: 1}[field] * self.Nl
+        n = {LAT_POP: 19, LAT_FORCE: 3, LAT_VELOCITY: 3, LAT_DENSITY: 1, LAT_PINEQ: 6}[field] * self.Nl
         out = np.empty(n)
         self._ck(self.L.hcg_lattice_download(self.h, C.c_int32(field), _p(out)))
         return out
@@ -289,6 +289,11 @@ class Context:
         self._ck(self.L.hcg_cells_volume_area(self.h, _p(v), _p(a)))
         return v, a
 
+    def stretch(self):
+        out = np.zeros(self.capacity()[0])
+        self._ck(self.L.hcg_cells_stretch(self.h, _p(out)))
+        return out
+
     def velocity_stats(self):
         a, b, m = C.c_double(), C.c_double(), C.c_double()
         self._ck(self.L.hcg_fluid_velocity_stats(self.h, C.byref(a), C.byref(b), C.byref(m)))
@@ -317,7 +322,8 @@ class Context:
 
 # ------------------------------------------------------------------ host-side set-up (C++ in the same .so)
 HOST_SYMBOLS = """hch_parameters hch_celltype_build hch_celltype_view hch_celltype_vertices hch_celltype_scalar
-hch_celltype_free hch_read_pos hch_place_cells hch_slab_membership hch_last_error""".split()
+hch_celltype_free hch_read_pos hch_place_cells hch_slab_membership hch_last_error
+hch_h5_create hch_h5_attribute hch_h5_dataset hch_h5_close""".split()
 
 RBC_MATERIAL = dict(kBend=80.0, kVolume=20.0, kArea=5.0, kLink=15.0, eta_m=0.0, minNumTriangles=600,
                     radius=3.91e-6, aspectRatio=0.3)
@@ -432,3 +438,38 @@ def read_pos(path):
     rows = np.empty((n, 6))
     fn(path.encode(), _p(rows), C.c_int64(n))
     return rows
+
+
+class H5Writer:
+    """hch_h5_*: the product's HDF5 container writer (hemocell_b200/host/hemo_h5.cpp)"""
+    TYPES = {np.dtype("float32"): 0, np.dtype("float64"): 1, np.dtype("int32"): 2, np.dtype("int64"): 3}
+
+    def __init__(self, path, deflate_level=7):
+        self.L = load()
+        self.L.hch_h5_create.restype = C.c_void_p
+        self.L.hch_last_error.restype = C.c_char_p
+        self.h = self.L.hch_h5_create(str(path).encode(), C.c_int32(deflate_level))
+        if not self.h:
+            raise HcgError("hch_h5_create: " + self.L.hch_last_error().decode())
+
+    def attribute(self, name, values):
+        a = np.ascontiguousarray(values)
+        rc = self.L.hch_h5_attribute(C.c_void_p(self.h), name.encode(), C.c_int32(self.TYPES[a.dtype]),
+                                     a.ctypes.data_as(C.c_void_p), C.c_int64(a.size))
+        if rc:
+            raise HcgError("hch_h5_attribute: " + self.L.hch_last_error().decode())
+
+    def dataset(self, name, array, chunk=None):
+        a = np.ascontiguousarray(array)
+        dims = (C.c_uint64 * a.ndim)(*a.shape)
+        ch = (C.c_uint64 * a.ndim)(*chunk) if chunk is not None else None
+        rc = self.L.hch_h5_dataset(C.c_void_p(self.h), name.encode(), C.c_int32(self.TYPES[a.dtype]), C.c_int32(a.ndim),
+                                   dims, a.ctypes.data_as(C.c_void_p), ch)
+        if rc:
+            raise HcgError("hch_h5_dataset: " + self.L.hch_last_error().decode())
+
+    def close(self):
+        rc = self.L.hch_h5_close(C.c_void_p(self.h))
+        self.h = None
+        if rc:
+            raise HcgError("hch_h5_close: " + self.L.hch_last_error().decode())

@@ -41,7 +41,9 @@ enum { HCG_FLUID = 0, HCG_BOUNCEBACK = 1, HCG_VEL_XN = 2, HCG_VEL_XP = 3, HCG_VE
        HCG_VEL_YP = 5, HCG_VEL_ZN = 6, HCG_VEL_ZP = 7 };
 enum { HCG_MODEL_RBC_HIGHORDER = 0, HCG_MODEL_PLT_SIMPLE = 1 };
 /* lattice fields */
-enum { HCG_LAT_POP = 0, HCG_LAT_FORCE = 1, HCG_LAT_VELOCITY = 2, HCG_LAT_DENSITY = 3 };
+enum { HCG_LAT_POP = 0, HCG_LAT_FORCE = 1, HCG_LAT_VELOCITY = 2, HCG_LAT_DENSITY = 3,
+       HCG_LAT_PINEQ = 4 /* off-equilibrium momentum flux, 6 components xx xy xz yy yz zz (output path:
+                            Cell::computeShearStress / computeStrainRateFromStress, io/FluidHdf5IO.hh:406-541) */ };
 /* particle fields */
 enum { HCG_P_POS = 0, HCG_P_VEL = 1, HCG_P_FORCE = 2, HCG_P_FREP = 3, HCG_P_F_AREA = 4,
        HCG_P_F_VOLUME = 5, HCG_P_F_BEND = 6, HCG_P_F_LINK = 7, HCG_P_F_VISC = 8, HCG_P_F_INNER = 9 };
@@ -109,7 +111,7 @@ hcg_status hcg_lattice_init_equilibrium(hcg_ctx*, double rho, const double u[3])
  * iterate() (examples/pipeflow/pipeflow.cpp:144-146): the value the node force is reset to */
 hcg_status hcg_lattice_set_body_force(hcg_ctx*, const double f[3]);
 hcg_status hcg_lattice_upload(hcg_ctx*, int32_t field /*POP|FORCE*/, const double* in);
-hcg_status hcg_lattice_download(hcg_ctx*, int32_t field /*POP|FORCE|VELOCITY|DENSITY*/, double* out);
+hcg_status hcg_lattice_download(hcg_ctx*, int32_t field /*POP|FORCE|VELOCITY|DENSITY|PINEQ*/, double* out);
 
 /* ---- cell types and cells */
 /* HemoCell::addCellType<Model>(name, constructType) (hemocell.h:122-128) */
@@ -181,6 +183,8 @@ hcg_status hcg_op_zero_force(hcg_ctx*);      /* setExternalVector(lattice, bbox,
 /* ---- observables (helper/cellInfo.cpp, helper/fluidInfo.cpp): per cell in storage order */
 hcg_status hcg_cells_bbox(hcg_ctx*, double* bbox /*[n_cells][6] xmin xmax ymin ymax zmin zmax*/);
 hcg_status hcg_cells_volume_area(hcg_ctx*, double* volume, double* area);
+/* CellInformationFunctionals::calculateCellStretch (helper/cellInfo.cpp:103-121): max pairwise vertex distance */
+hcg_status hcg_cells_stretch(hcg_ctx*, double* stretch);
 hcg_status hcg_fluid_velocity_stats(hcg_ctx*, double* vmin, double* vmax, double* vmean);
 
 /* ---- timing (helper/profiler.cpp): CUDA-event totals under the reference's key names */

@@ -47,6 +47,16 @@ int64_t hch_place_cells(const hch_celltype*, const double* rows6, int64_t n_rows
 void hch_slab_membership(int64_t n, const double* xlo, const double* xhi, int32_t nx, int32_t periodic_x,
                          int32_t nxl, int32_t rank, int32_t n_ranks, double margin,
                          uint8_t* held, uint8_t* share_left, uint8_t* share_right);
+/* HDF5 container writer behind HemoCell::writeOutput (replaces the H5Fcreate / H5LTset_attribute_* /
+ * H5Dcreate2 + H5Dwrite calls of io/ParticleHdf5IO.cpp:60-194 and io/FluidHdf5IO.hh:36-49).
+ * type: 0 = float32, 1 = float64, 2 = int32, 3 = int64.  deflate_level < 0 writes contiguous datasets;
+ * chunk may be NULL (contiguous).  hch_h5_close returns 0 on success and frees the handle. */
+typedef struct hch_h5 hch_h5;
+hch_h5* hch_h5_create(const char* path, int32_t deflate_level);
+int32_t hch_h5_attribute(hch_h5*, const char* name, int32_t type, const void* data, int64_t n);
+int32_t hch_h5_dataset(hch_h5*, const char* name, int32_t type, int32_t rank, const uint64_t* dims,
+                       const void* data, const uint64_t* chunk);
+int32_t hch_h5_close(hch_h5*);
 const char* hch_last_error(void);
 
 #ifdef __cplusplus

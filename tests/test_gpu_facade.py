@@ -65,6 +65,27 @@ def test_shear_cell_case_file_matches_oracle(tmp_path, cadence):
     stats = list((tmp_path / "tmp" / "log").glob("*.statistics"))
     assert stats and "collideAndStream" in stats[0].read_text() and "spreadParticleForce" in stats[0].read_text()
     assert list((tmp_path / "tmp" / "csv").glob("RBC.*.csv"))
+    # HDF5 output (io/ParticleHdf5IO.cpp, io/FluidHdf5IO.hh layout), read back with the format-level reader
+    import h5mini
+    par = M.Parameters(dx=0.5e-6, dt=0.5e-7)
+    it = "%012d" % 300
+    pf = h5mini.File(tmp_path / "tmp" / "hdf5" / it / f"RBC.{it}.p.0.h5")
+    assert pf.attrs["numberOfParticles"][0] == 642 and pf.attrs["numberOfTriangles"][0] == 1280
+    assert pf.attrs["iteration"][0] == 300 and abs(pf.attrs["dx"][0] - 0.5e-6) < 1e-18
+    pos = pf["Position"]
+    assert pos.shape == (642, 3) and pos.dtype == np.float32 and pf["Triangles"].shape == (1280, 3)
+    assert pf.datasets["Position"]["layout"] == "chunked" and pf.datasets["Position"]["deflate"] == 7
+    diam = (pos.max(0) - pos.min(0)) * 0.5 * 1e6               # SI output: metres
+    U.assert_close(diam.astype(float), ref[-1]["diam"] * par.dx * 1e6, "HDF5 positions vs oracle", rtol=1e-5)
+    assert np.isfinite(pf["Total force"]).all() and np.abs(pf["Total force"]).max() > 0
+    ff = h5mini.File(tmp_path / "tmp" / "hdf5" / it / f"Fluid.{it}.p.0.h5")
+    vel_f = ff["Velocity"]
+    assert vel_f.shape == (22, 42, 42, 3) and tuple(ff.attrs["subdomainSize"]) == (22, 42, 42)
+    # Couette profile: the velocity plane z = 0 moves with +vh, z = nz-1 with -vh (lattice -> SI: dx/dt)
+    vh = 19 * 111.0 * par.dt * 0.5 * par.dx / par.dt
+    assert abs(vel_f[1, 5, 5, 0] - vh) < 1e-6 * vh and abs(vel_f[20, 5, 5, 0] + vh) < 1e-6 * vh
+    assert np.all(vel_f[0] == 0)                               # envelope beyond the non-periodic z face
+    np.testing.assert_array_equal(vel_f[:, 0], vel_f[:, 40])   # periodic y envelope = wrapped plane
 
 
 def test_reference_oneCellShear_unmodified_binary(tmp_path):

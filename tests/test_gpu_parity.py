@@ -282,3 +282,31 @@ def test_experimental_row_pipeline_matches_default():
     r1 = subprocess.run([sys.executable, script, "24", "24", "64", "6"], env=dict(base, HCG_FUSED="1", HCG_K1_ROWS="1", HCG_OVERLAP="1"),
                         capture_output=True, text=True, timeout=300)
     assert r1.returncode == 0 and "fused == separate" in r1.stdout, r1.stdout + r1.stderr
+
+
+def test_output_observables_stretch_and_pineq():
+    """output-path kernels: per-cell largest vertex distance (helper/cellInfo.cpp:103-121) and the
+    off-equilibrium momentum flux behind the ShearStress / StrainRate fluid fields, vs numpy"""
+    H = _lib()
+    par, dom, fl, bc, ct, cells = _one_rbc_setup()
+    N = dom.nx * dom.ny * dom.nz
+    two = np.concatenate([cells, U.deformed_cells(ct, [cells[0].mean(0) + np.array([0.0, 0.0, 0.0])], 9, stretch=(1.2, 0.9, 0.95))])
+    pop = U.mask_inflow(dom, U.smooth_state(dom, 33))
+    ctx = U.gpu_context(dom, fl, bc)
+    t = U.gpu_add_type(ctx, ct)
+    ctx.add_cells(t, two, np.arange(two.shape[0]))
+    ctx.lattice_upload(H.LAT_POP, pop)
+    ref = []
+    for c in two:
+        d = c[:, None, :] - c[None, :, :]
+        ref.append(np.sqrt((d * d).sum(-1).max()))
+    U.assert_close(ctx.stretch(), np.array(ref), "cell stretch", rtol=1e-14)
+    C = np.array([[0,0,0],[-1,0,0],[0,-1,0],[0,0,-1],[-1,-1,0],[-1,1,0],[-1,0,-1],[-1,0,1],[0,-1,-1],[0,-1,1],
+                  [1,0,0],[0,1,0],[0,0,1],[1,1,0],[1,-1,0],[1,0,1],[1,0,-1],[0,1,1],[0,1,-1]], dtype=np.float64)
+    f = pop.reshape(19, N)
+    rhoBar = f.sum(0); j = C.T @ f; inv = 1.0 / (1.0 + rhoBar)
+    pairs = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+    pi = np.stack([(C[:, a] * C[:, b]) @ f - (rhoBar / 3.0 if a == b else 0.0) - inv * j[a] * j[b] for a, b in pairs])
+    pi[:, fl.reshape(-1) == 1] = 0.0
+    U.assert_close(ctx.lattice_download(H.LAT_PINEQ), pi, "PiNeq", rtol=1e-10, floor=1e-12)
+    ctx.close()
