@@ -331,12 +331,22 @@ HemoCellField::HemoCellField(HemoCellFields& cellFields_, const std::string& nam
   // model id is fixed once the mechanics object exists (HemoCell::addCellType); tables do not depend on it
   impl->tables.build(HCG_MODEL_RBC_HIGHORDER, constructType, impl->material, p);
   numVertex = impl->tables.mesh.getNumVertices();
+  meshmetric = new MeshMetrics();
+  meshmetric->volume = impl->tables.mesh.getVolume(); meshmetric->surface = impl->tables.mesh.getSurface();
+  {
+    const auto& el = impl->tables.cc.edge_length_eq_list;
+    if (!el.empty()) { meshmetric->meanLength = impl->tables.cc.edge_mean_eq; meshmetric->maxLength = *std::max_element(el.begin(), el.end()); meshmetric->minLength = *std::min_element(el.begin(), el.end()); }
+  }
   for (auto& t : impl->tables.cc.triangle_list) triangle_list.push_back({{t[0], t[1], t[2]}});
   volume = impl->material.volume;
   if (volume > 0) volumeFractionOfLspPerNode = (volume/numVertex)/std::pow(param::dx*1e6, 3);
   else hlog << "(HemoCell) (WARNING) (AddCellType) Volume of celltype " << name << " not present, volume set to zero" << endl;
 }
-HemoCellField::~HemoCellField() { delete mechanics; delete materialCfg; delete impl; }
+HemoCellField::~HemoCellField() { delete mechanics; delete materialCfg; delete impl; delete meshmetric; }
+hemo::Array<T, 6> HemoCellField::getOriginalBoundingBox() {
+  host::Vec3 lo, hi; impl->tables.mesh.boundingBox(lo, hi);
+  return hemo::Array<T, 6>{{lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]}};
+}
 void HemoCellField::setOutputVariables(const vector<int>& outputs) {
   desiredOutputVariables = outputs;
   auto it = std::find(desiredOutputVariables.begin(), desiredOutputVariables.end(), OUTPUT_TRIANGLES);
@@ -1040,6 +1050,74 @@ pluint CellInformationFunctionals::getNumberOfCellsFromType(HemoCell* h, std::st
   for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0 && s.types[k] == t) n++;
   return n;
 }
+// helper/particleInfo.cpp:28-119
+static ParticleStatistics particle_stats(HemoCell* h, bool force) {
+  CellSnapshot s = snapshot(h);
+  ParticleStatistics r;
+  if (!s.np) return r;
+  std::vector<double> a(3*s.np), b;
+  ck(h->ctx(), hcg_cells_download(h->ctx(), force ? HCG_P_FORCE : HCG_P_VEL, a.data()), "download");
+  if (force) { b.resize(3*s.np); ck(h->ctx(), hcg_cells_download(h->ctx(), HCG_P_FREP, b.data()), "download"); }
+  bool first = true; double sum = 0;
+  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0) {
+    const int V = (*h->cellfields)[(unsigned)s.types[k]]->numVertex;
+    for (int v = 0; v < V; v++) {
+      const int64_t q = 3*(s.base[k] + v);
+      double x = a[q], y = a[q+1], z = a[q+2];
+      if (force) { x += b[q]; y += b[q+1]; z += b[q+2]; }
+      const double m = std::sqrt(x*x + y*y + z*z);
+      if (first) { r.min = r.max = m; first = false; }
+      r.min = std::min(r.min, m); r.max = std::max(r.max, m); sum += m; r.ncells++;
+    }
+  }
+  if (r.ncells) r.avg = sum/r.ncells;
+  return r;
+}
+ParticleStatistics ParticleInfo::calculateVelocityStatistics(HemoCell* h) { return particle_stats(h, false); }
+ParticleStatistics ParticleInfo::calculateForceStatistics(HemoCell* h) { return particle_stats(h, true); }
+
+// helper/hemoCellStretch.cpp ------------------------------------------------------------------------------
+vector<plint> HemoCellStretch::lower_lsps = vector<plint>();
+vector<plint> HemoCellStretch::upper_lsps = vector<plint>();
+unsigned int HemoCellStretch::n_forced_lsps = 0;
+T HemoCellStretch::external_force = 0.0;
+T HemoCellStretch::scale = 1.0;
+HemoCellStretch::HemoCellStretch(HemoCellField& cellfield_, unsigned int n_forced_lsps_, T external_force_) : cellfield(cellfield_) {
+  HemoCell* h = &cellfield.cellFields.hemocell;
+  if (CellInformationFunctionals::getTotalNumberOfCells(h) != 1) { pcout << "(HemoCellStretch) Refusing to run with more or less than 1 cell" << endl; exit(1); }
+  n_forced_lsps = n_forced_lsps_;
+  external_force = external_force_/n_forced_lsps;
+  // the n LSPs with the smallest / largest x of cell 0 (stable order of the reference's bubble sort: ties keep vertex order)
+  CellSnapshot s = snapshot(h);
+  std::vector<double> pos(3*s.np);
+  ck(h->ctx(), hcg_cells_download(h->ctx(), HCG_P_POS, pos.data()), "download");
+  int64_t k0 = -1; for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] == 0) k0 = k;
+  if (k0 < 0) { cout << "Error -1 found in cell, exiting" << endl; exit(1); }
+  const int V = cellfield.numVertex;
+  std::vector<int> idx(V); for (int v = 0; v < V; v++) idx[v] = v;
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return pos[3*(s.base[k0] + a)] < pos[3*(s.base[k0] + b)]; });
+  for (unsigned i = 0; i < n_forced_lsps; i++) { lower_lsps.push_back(idx[i]); upper_lsps.push_back(idx[V - 1 - i]); }
+}
+void HemoCellStretch::applyForce() {
+  if (cellfield.timescale != 1) { pcout << "Refusing to stretch with particle update timestep larger than 1" << endl; exit(1); }
+  HemoCell* h = &cellfield.cellFields.hemocell;
+  // the single cell never changes its storage slot: resolve the particle indices once
+  static std::vector<int64_t> which; static hcg_ctx* which_ctx = nullptr;
+  if (which_ctx != h->ctx() || which.size() != lower_lsps.size() + upper_lsps.size()) {
+    CellSnapshot s = snapshot(h);
+    int64_t k0 = -1; for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] == 0) k0 = k;
+    if (k0 < 0) return;
+    which.clear();
+    for (plint v : lower_lsps) which.push_back(s.base[k0] + v);
+    for (plint v : upper_lsps) which.push_back(s.base[k0] + v);
+    which_ctx = h->ctx();
+  }
+  std::vector<double> f;
+  for (size_t i = 0; i < lower_lsps.size(); i++) { f.push_back(-external_force*scale); f.push_back(0); f.push_back(0); }
+  for (size_t i = 0; i < upper_lsps.size(); i++) { f.push_back(external_force*scale); f.push_back(0); f.push_back(0); }
+  ck(h->ctx(), hcg_cells_add_force(h->ctx(), (int64_t)which.size(), which.data(), f.data()), "hcg_cells_add_force");
+}
+
 FluidStatistics FluidInfo::calculateVelocityStatistics(HemoCell* h) {
   FluidStatistics f;
   ck(h->ctx(), hcg_fluid_velocity_stats(h->ctx(), &f.min, &f.max, &f.avg), "hcg_fluid_velocity_stats");

@@ -517,6 +517,14 @@ class HemoCellField {
   T getVolumeFraction();
   std::string getIdentifier() { return name; }
   CellTypeImpl* impl = nullptr;                     /* mesh + CommonCellConstants tables (host), device ctype id */
+  /* MeshMetrics of the undeformed mesh in lattice units (core/hemoCellField.h meshmetric; the case files use getVolume / getSurface) */
+  struct MeshMetrics {
+    T volume = 0, surface = 0, meanLength = 0, maxLength = 0, minLength = 0;
+    T getVolume() const { return volume; } T getSurface() const { return surface; }
+    T getMeanLength() const { return meanLength; } T getMaxLength() const { return maxLength; } T getMinLength() const { return minLength; }
+  };
+  MeshMetrics* meshmetric = nullptr;
+  hemo::Array<T, 6> getOriginalBoundingBox();       /* core/hemoCellField.cpp:149-165 */
 };
 
 /* ---- core/hemoCellFields.h ----------------------------------------------------------------------- */
@@ -623,6 +631,23 @@ class CellInformationFunctionals {
   static void calculateCellInformation(HemoCell*);
   static pluint getTotalNumberOfCells(HemoCell*);
   static pluint getNumberOfCellsFromType(HemoCell*, std::string type);
+};
+/* helper/particleInfo.h: |v| and |force + force_repulsion| over the live LSPs */
+struct ParticleStatistics { T min = 0, max = 0, avg = 0; pluint ncells = 0; };
+class ParticleInfo {
+ public:
+  static ParticleStatistics calculateVelocityStatistics(HemoCell* hemocell);
+  static ParticleStatistics calculateForceStatistics(HemoCell* hemocell);
+};
+/* helper/hemoCellStretch.h: opposite forces on the n outermost LSPs (along x) of the single cell in the domain */
+class HemoCellStretch {
+ public:
+  HemoCellStretch(HemoCellField& cellfield_, unsigned int n_forced_lsps_, T external_force_);
+  void applyForce();
+  static vector<plint> lower_lsps, upper_lsps;      /* vertex ids */
+  HemoCellField& cellfield;
+  static unsigned int n_forced_lsps;
+  static T external_force, scale;
 };
 struct FluidStatistics { T min = 0, max = 0, avg = 0; pluint ncells = 0; };
 class FluidInfo {

@@ -58,7 +58,7 @@ def test_example_fails_loudly_without_device(tmp_path):
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (authoring container only)")
 @pytest.mark.parametrize("case", ["examples/oneCellShear/oneCellShear.cpp", "cases/performance_testing/performance_testing.cpp",
-                                  "examples/cube/cube.cpp"])
+                                  "examples/cube/cube.cpp", "examples/stretchCell/stretchCell.cpp", "cases/stenosis/stenosis.cpp"])
 def test_reference_case_files_compile_unmodified(case):
     """drop-in check: the reference's own case files compile against include/hemocell.h as they are"""
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", f"-I{ROOT}/include", f"-I{ROOT}/include/compat", os.path.join(REF, case)],

@@ -112,3 +112,65 @@ def test_reference_oneCellShear_unmodified_binary(tmp_path):
         U.assert_close(g[6:7], np.array([o["largest_diam_um"]]), f"largest diameter at {o['iter']}", rtol=2e-6)
         assert abs(g[7] - o["deformation_index_pct"]) < 1e-3
     assert (tmp_path / "tmp" / "checkpoint" / "checkpoint.xml").exists()
+
+
+def _refcase(tmp_path, name, files):
+    src = os.path.join(ROOT, "build", "refcases", name)
+    if not os.path.exists(os.path.join(src, name)):
+        pytest.skip("build/refcases not present (built from /root/reference in the authoring container)")
+    for f in [name] + files:
+        shutil.copy(os.path.join(src, f), tmp_path / f)
+    return dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "hemocell_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+
+
+def test_reference_stretchCell_unmodified_binary(tmp_path):
+    """the REFERENCE's examples/stretchCell/stretchCell.cpp (HemoCellStretch, closed box of u = 0 velocity planes),
+    compiled unmodified, at 75 pN for the validation test's 10 000 iterations: reproduces the oracle trace, which
+    itself sits inside the reference's force-displacement bounds (tests/validation/stretch_cell/test_stretch_cell.cpp:158-162)"""
+    env = _refcase(tmp_path, "stretchCell", ["config.xml", "RBC.xml", "RBC.pos"])
+    cfg = (tmp_path / "config.xml").read_text()
+    cfg = re.sub(r"<stretchForce>.*?</stretchForce>", "<stretchForce> 75 </stretchForce>", cfg)
+    cfg = re.sub(r"<tmax>.*?</tmax>", "<tmax> 10000 </tmax>", cfg)
+    cfg = re.sub(r"<tmeas>.*?</tmeas>", "<tmeas> 200 </tmeas>", cfg)
+    cfg = re.sub(r"<tcheckpoint>.*?</tcheckpoint>", "<tcheckpoint> 100000 </tcheckpoint>", cfg)
+    (tmp_path / "config.xml").write_text(cfg)
+    env["HEMOCELL_H5_DEFLATE"] = "1"
+    r = subprocess.run([str(tmp_path / "stretchCell"), "config.xml"], cwd=tmp_path, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    log = np.loadtxt(tmp_path / "stretch-75.log", skiprows=1)
+    got = {int(row[0]): row[1:] for row in log}
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "stretch_oracle.json")))
+    run = [x for x in gold["runs"] if x["force_pN"] == 75][0]
+    for it in ("200", "10000"):
+        o = run["trace"][it]
+        U.assert_close(got[int(it)], np.array([o["axial_um"], o["transverse_um"]]), f"axial/transverse diameter at {it}", rtol=2e-5)
+    b = gold["bounds_um"]["75"]
+    assert b["axial"][0] <= got[10000][0] <= b["axial"][1] and b["transverse"][0] <= got[10000][1] <= b["transverse"][1]
+
+
+def test_reference_stenosis_unmodified_binary(tmp_path):
+    """the REFERENCE's cases/stenosis/stenosis.cpp compiled unmodified: 600x348x160 lattice, analytic stenosis of
+    bounce-back nodes, body force, Ht20 initial state (11 600 RBC + 812 PLT rows), velocity/material cadence 10;
+    a short run: placement count, finite forces, flow in +x, HDF5 + CSV output of the full-size case"""
+    env = _refcase(tmp_path, "stenosis", ["config.xml", "RBC.xml", "PLT.xml", "RBC.pos", "PLT.pos"])
+    cfg = (tmp_path / "config.xml").read_text()
+    cfg = re.sub(r"<tmax>.*?</tmax>", "<tmax> 40 </tmax>", cfg)
+    cfg = re.sub(r"<tmeas>.*?</tmeas>", "<tmeas> 40 </tmeas>", cfg)
+    (tmp_path / "config.xml").write_text(cfg)
+    env["HEMOCELL_H5_DEFLATE"] = "-1"                       # the fluid file of this case is ~1 GB of float32: skip deflate in the test
+    r = subprocess.run([str(tmp_path / "stenosis"), "config.xml"], cwd=tmp_path, capture_output=True, text=True, timeout=1500, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    m = re.findall(r"# of cells: (\d+) \| # of RBC: (\d+), PLT: (\d+)", r.stdout)
+    assert m, r.stdout[-3000:]
+    ncell, nrbc, nplt = map(int, m[-1])
+    # the shipped Ht20 packing spans 300 x 100 x 174 um while the case's box is 300 x 174 x 80 um: the reader keeps
+    # what lies inside the box and outside the stenosis, about a quarter of the rows
+    assert ncell == nrbc + nplt and 2500 < nrbc <= 11600 and 200 < nplt <= 812
+    f = re.findall(r"Force  -  min\.: (\S+) pN, max\.: (\S+) pN", r.stdout)
+    assert f and np.isfinite(float(f[-1][1])) and float(f[-1][1]) < 51.0          # FORCE_LIMIT 50 pN
+    v = re.findall(r"Velocity  -  max\.: (\S+) m/s, mean: (\S+) m/s", r.stdout)
+    assert v and float(v[-1][1]) > 0
+    import h5mini
+    it = "%012d" % 40
+    pf = h5mini.File(tmp_path / "tmp" / "hdf5" / it / f"RBC.{it}.p.0.h5")
+    assert pf["Position"].shape == (nrbc * 642, 3) and pf.attrs["numberOfTriangles"][0] == nrbc * 1280
