@@ -40,6 +40,7 @@ __device__ __forceinline__ double phi2(double x) { x = 1.0 - fabs(x); return x >
 // Kernel of one particle: up to 8 (node, weight) pairs in the reference's x-outer/z-inner
 // order, zero weights and boundary nodes skipped, normalised.  Returns the count, or -1 when a
 // candidate node is not addressable from this rank (particle irrelevant here).
+template <bool CHECK_FLAGS = true>
 __device__ __forceinline__ int ibm_kernel(const IbmArgs& a, const uint8_t* __restrict__ flags,
                                           double px, double py, double pz, int64_t node[8], double w[8]) {
   const int bx = (int)floor(px), by = (int)floor(py), bz = (int)floor(pz);
@@ -63,7 +64,7 @@ __device__ __forceinline__ int ibm_kernel(const IbmArgs& a, const uint8_t* __res
         const double weight = wx*wy*wz;
         if (weight == 0.0) continue;
         const int64_t id = (int64_t)z + (int64_t)a.nz*((int64_t)y + (int64_t)a.ny*lx);
-        if (flags[id] != HCG_FLUID) continue;
+        if (CHECK_FLAGS && flags[id] != HCG_FLUID) continue;     // !CHECK_FLAGS: every addressable node is plain fluid
         total += weight;
         node[n] = id; w[n] = weight; n++;
       }
@@ -112,7 +113,14 @@ k_advance_list(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __re
                int n, const int64_t* __restrict__ cell_base, uint8_t* alive, double* x, double* y, double* z,
                const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz);
 
-template <bool ADVANCE, bool INTERP>
+// one node of the AoS velocity field (u0, u1, u2, rho) as ONE 256-bit load (LDG.E.256 on sm_100a): the
+// interpolation is bound by the number of L1 requests of its scattered gathers, not by bytes
+__device__ __forceinline__ void ld_node4(const double* p, double& a, double& b, double& c) {
+  double d;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+template <bool ADVANCE, bool INTERP, bool CHECK_FLAGS>
 __global__ void __launch_bounds__(256)
 k_interp_advance(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __restrict__ p_cell,
                  uint8_t* alive, double* x, double* y, double* z,
@@ -125,18 +133,49 @@ k_interp_advance(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __
   double px = x[p], py = y[p], pz = z[p];
   double v0, v1, v2;
   if (INTERP) {
-    int64_t node[8]; double w[8];
-    const int n = ibm_kernel(a, flags, px, py, pz, node, w);
-    v0 = v1 = v2 = 0.0;
-    for (int k = 0; k < n; k++) {
-      const double2 ua = __ldg(reinterpret_cast<const double2*>(U + 4*node[k]));
-      const double ub = __ldg(U + 4*node[k] + 2);
-      v0 += ua.x*w[k];
-      v1 += ua.y*w[k];
-      v2 += ub*w[k];
+    // the 8 corners fully unrolled (registers only, no local-memory arrays): raw weights in the reference's
+    // x-outer / z-inner order, zero for corners outside the kernel, the domain or (CHECK_FLAGS) on non-fluid nodes
+    const int bx = (int)floor(px), by = (int)floor(py), bz = (int)floor(pz);
+    double ax[2], ay[2], az[2]; int64_t jx[2]; int jy[2], jz[2];
+    bool addressable = true;
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+      ax[d] = phi2(px - (double)(bx + d)); jx[d] = 0;
+      if (ax[d] != 0.0) {
+        int lx; bool out;
+        if (local_x(bx + d, a, lx, out)) jx[d] = (int64_t)lx*a.P;
+        else { ax[d] = 0.0; if (!out) addressable = false; }
+      }
+      ay[d] = phi2(py - (double)(by + d)); int yy = by + d;
+      if (ay[d] != 0.0 && !wrap_yz(yy, a.ny, a.py)) ay[d] = 0.0;
+      jy[d] = yy*a.nz;
+      az[d] = phi2(pz - (double)(bz + d)); int zz = bz + d;
+      if (az[d] != 0.0 && !wrap_yz(zz, a.nz, a.pz)) az[d] = 0.0;
+      jz[d] = zz;
     }
-    if (n >= 0) { vx[p] = v0; vy[p] = v1; vz[p] = v2; }
-    else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
+    if (addressable) {
+      double w[8]; double total = 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
+        w[c] = ax[dx]*ay[dy]*az[dz];
+        if (w[c] == 0.0) continue;
+        if (CHECK_FLAGS && flags[jx[dx] + jy[dy] + jz[dz]] != HCG_FLUID) { w[c] = 0.0; continue; }
+        total += w[c];
+      }
+      const double coeff = 1.0/total;
+      v0 = v1 = v2 = 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        if (w[c] == 0.0) continue;
+        const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
+        const double wn = w[c]*coeff;
+        double u0, u1, u2;
+        ld_node4(U + 4*(jx[dx] + jy[dy] + jz[dz]), u0, u1, u2);
+        v0 += u0*wn; v1 += u1*wn; v2 += u2*wn;
+      }
+      vx[p] = v0; vy[p] = v1; vz[p] = v2;
+    } else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
   } else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
   if (ADVANCE && !(hold_back && hold_back[cell])) {
     px += v0; py += v1; pz += v2;
@@ -197,7 +236,9 @@ hcg_status ibm_spread(hcg_ctx* c) {
 hcg_status ibm_interpolate(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   IbmArgs a = make_args(c);
-  k_interp_advance<false, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+  if (c->has_nonfluid) k_interp_advance<false, true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
+  else k_interp_advance<false, true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
       c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
   KERNEL_CHECK(c);
   return HCG_OK;
@@ -206,7 +247,7 @@ hcg_status ibm_interpolate(hcg_ctx* c) {
 hcg_status ibm_advance(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   IbmArgs a = make_args(c);
-  k_interp_advance<true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+  k_interp_advance<true, false, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
       c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
   KERNEL_CHECK(c);
   return HCG_OK;
@@ -215,7 +256,9 @@ hcg_status ibm_advance(hcg_ctx* c) {
 hcg_status ibm_interpolate_advance(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   IbmArgs a = make_args(c);
-  k_interp_advance<true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+  if (c->has_nonfluid) k_interp_advance<true, true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
+  else k_interp_advance<true, true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
       c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
   KERNEL_CHECK(c);
   return HCG_OK;
@@ -225,7 +268,9 @@ hcg_status ibm_interpolate_advance_unshared(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   if (!c->multi.d_cell_shared) return hcg_fail(c, HCG_ERR_STATE, "shared-cell flags missing (multi_rebalance has not run)");
   IbmArgs a = make_args(c);
-  k_interp_advance<true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+  if (c->has_nonfluid) k_interp_advance<true, true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared);
+  else k_interp_advance<true, true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
       c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared);
   KERNEL_CHECK(c);
   return HCG_OK;

@@ -13,6 +13,7 @@
 #include "ctx.cuh"
 #include <cub/block/block_radix_sort.cuh>
 #include <climits>
+#include <cstdlib>
 
 namespace {
 
@@ -115,10 +116,12 @@ __global__ void k_perm_identity(uint16_t* perm, int npair, int64_t total) {
 }
 
 // ---------------------------------------------------------------- spread
-// One CTA per cell.  Phase 1 (thread = vertex): force cap, the 8 kernel nodes and their NORMALISED
-// weights -> shared memory (key = -1 for corners outside the kernel or on a ghost plane).
-// Phase 2 (thread = chunk of 8 consecutive node-sorted pairs): walk the chunk sequentially, merge
-// runs of equal node in registers, one fp64 RED triple per run.
+// One CTA per cell.  Phase 1 (thread = vertex): force cap, the kernel's per-axis node offsets, the
+// normalisation coefficient and a mask of the corners that add to a real node -> shared memory
+// (81 B per vertex: 4 cells per SM instead of the 2 a full [8][V] weight/key table allows).
+// Phase 2 (thread = chunk of 8 consecutive node-sorted pairs): walk the chunk sequentially, rebuild the
+// pair's node and NORMALISED weight from the staged position (same expressions, same bits as phase 1),
+// merge runs of equal node in registers, one fp64 RED triple per run.
 template <int THREADS, bool CHECK_FLAGS>
 __global__ void __launch_bounds__(THREADS)
 k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ alive,
@@ -131,9 +134,11 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
   const int64_t cell = a.first_cell + blockIdx.x;
   if (!alive[cell]) return;
   const int64_t base = a.first_particle + (int64_t)blockIdx.x*V;
-  double* W = sm;                      // [8][V] normalised weights
-  double* t0 = W + 8*V; double* t1 = t0 + V; double* t2 = t1 + V;
-  int* K = reinterpret_cast<int*>(t2 + V);   // [8][V] node index, -1 = nothing to add
+  double* PX = sm; double* PY = PX + V; double* PZ = PY + V;      // position
+  double* CO = PZ + V;                                             // 1 / sum of the admitted raw weights
+  double* t0 = CO + V; double* t1 = t0 + V; double* t2 = t1 + V;   // force_repulsion + capped force
+  int* J = reinterpret_cast<int*>(t2 + V);                         // [6][V] node offsets: x(d=0,1), y(d=0,1), z(d=0,1)
+  uint8_t* M = reinterpret_cast<uint8_t*>(J + 6*V);                // bit c: corner c adds to a real node of this rank
 
   for (int v = threadIdx.x; v < V; v += THREADS) {
     const int64_t p = base + v;
@@ -163,26 +168,20 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
       if (az[d] != 0.0 && !sp_wrap(zz, a.nz, a.pz)) az[d] = 0.0;
       jz[d] = zz;
     }
-    double w[8]; int key[8];
-    double total = 0.0;
+    double total = 0.0; unsigned mask = 0;
 #pragma unroll
     for (int c = 0; c < 8; c++) {               // corner order == the reference's x-outer / z-inner order
       const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
-      w[c] = ax[dx]*ay[dy]*az[dz];
-      const int node = jx[dx] + jy[dy] + jz[dz];
-      key[c] = -1;
-      if (w[c] == 0.0) continue;
-      if (CHECK_FLAGS && flags[node] != HCG_FLUID) { w[c] = 0.0; continue; }
-      total += w[c];
-      if (realx[dx]) key[c] = node;             // ghost planes count in the normalisation only
+      const double w = ax[dx]*ay[dy]*az[dz];
+      if (w == 0.0) continue;
+      if (CHECK_FLAGS && flags[jx[dx] + jy[dy] + jz[dz]] != HCG_FLUID) continue;
+      total += w;
+      if (realx[dx]) mask |= 1u << c;            // ghost planes count in the normalisation only
     }
-    const double coeff = 1.0/total;
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-      W[c*V + v] = w[c]*coeff;
-      K[c*V + v] = skip ? -1 : key[c];           // multi-GPU: a candidate node is not addressable here
-    }
+    PX[v] = px; PY[v] = py; PZ[v] = pz; CO[v] = 1.0/total;
     t0[v] = rx[p] + f0; t1[v] = ry[p] + f1; t2[v] = rz[p] + f2;
+    J[v] = jx[0]; J[V + v] = jx[1]; J[2*V + v] = jy[0]; J[3*V + v] = jy[1]; J[4*V + v] = jz[0]; J[5*V + v] = jz[1];
+    M[v] = skip ? 0 : (uint8_t)mask;             // multi-GPU: a candidate node is not addressable here
   }
   __syncthreads();
 
@@ -195,9 +194,14 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
     for (int k = 0; k < 8; k++) {
       const unsigned e = (e8[k >> 1] >> ((k & 1)*16)) & 0xFFFFu;
       const int v = e >> 3, c = e & 7;
-      const int key = K[c*V + v];
-      if (key < 0) continue;
-      const double w = W[c*V + v];
+      if (!((M[v] >> c) & 1u)) continue;
+      const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
+      const int key = J[dx*V + v] + J[(2 + dy)*V + v] + J[(4 + dz)*V + v];
+      const double px = PX[v], py = PY[v], pz = PZ[v];
+      const double wx = sp_phi2(px - (double)((int)floor(px) + dx));
+      const double wy = sp_phi2(py - (double)((int)floor(py) + dy));
+      const double wz = sp_phi2(pz - (double)((int)floor(pz) + dz));
+      const double w = (wx*wy*wz)*CO[v];
       const double v0 = t0[v]*w, v1 = t1[v]*w, v2 = t2[v]*w;
       if (key != cur) {
         if (cur >= 0) { double* Fn = F + 4*(int64_t)cur; atomicAdd(Fn, a0); atomicAdd(Fn + 1, a1); atomicAdd(Fn + 2, a2); }
@@ -247,13 +251,18 @@ hcg_status spread_sorted(hcg_ctx* c) {
     if (th.n_cells == 0) continue;
     SpArgs a = make_args(c, th);
     const int V = th.d.V;
-    const size_t smem = sizeof(double)*11*V + sizeof(int)*8*V + 16;
+    const size_t smem = sizeof(double)*7*V + sizeof(int)*6*V + V + 16;
     const bool chk = c->has_nonfluid;
 #define SP_LAUNCH(T, C) do { \
       CUDA_TRY(c, cudaFuncSetAttribute(k_spread_sorted<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_spread_sorted<T, C><<<(unsigned)th.n_cells, T, smem, c->stream>>>(a, c->flags, c->cell_alive, c->pos[0], c->pos[1], c->pos[2], \
           c->frc[0], c->frc[1], c->frc[2], c->frep[0], c->frep[1], c->frep[2], th.perm, c->F); } while (0)
-    if (V >= 256) { if (chk) SP_LAUNCH(256, true); else SP_LAUNCH(256, false); }
+    static int thr = -1;
+    if (thr < 0) { const char* e = getenv("HCG_SPREAD_THREADS"); thr = e ? atoi(e) : 256; }
+    if (V >= 256 && thr == 352) { if (chk) SP_LAUNCH(352, true); else SP_LAUNCH(352, false); }
+    else if (V >= 256 && thr == 672) { if (chk) SP_LAUNCH(672, true); else SP_LAUNCH(672, false); }
+    else if (V >= 256 && thr == 128) { if (chk) SP_LAUNCH(128, true); else SP_LAUNCH(128, false); }
+    else if (V >= 256) { if (chk) SP_LAUNCH(256, true); else SP_LAUNCH(256, false); }
     else { if (chk) SP_LAUNCH(64, true); else SP_LAUNCH(64, false); }
 #undef SP_LAUNCH
     KERNEL_CHECK(c);

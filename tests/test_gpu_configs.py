@@ -1,0 +1,133 @@
+"""GPU parity on reduced-size versions of the BASELINE.json configurations (pipeflow, cube), and
+size-independent properties at the full benchmark size (cases/performance_testing unit, 256^3)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import mesh as M
+import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from hemocell_b200 import lib as H
+    return H
+
+
+def _run_pair(dom, fl, bc, body, par, types, cells, steps, vel_ts, mat_ts, rep=None, wall=None):
+    H = _lib()
+    body = (0.0, 0.0, 0.0) if body is None else body
+    sim = O.OracleSim(dom, fl, par.f_limit, body)
+    sim.vel_timescale = vel_ts
+    ctx = U.gpu_context(dom, fl, bc, body)
+    ctx.set_force_limit(par.f_limit)
+    cid = 0
+    for ct, cc in zip(types, cells):
+        sim.add_celltype(ct, mat_ts)
+        t = U.gpu_add_type(ctx, ct)
+        ids = np.arange(cid, cid + len(cc)); cid += len(cc)
+        sim.add_cells(len(sim.types) - 1, cc, ids)
+        ctx.add_cells(t, cc, ids)
+        ctx.set_material_timescale(t, mat_ts)
+    ctx.set_timescales(vel_ts, rep[2] if rep else 1, wall[2] if wall else 1)
+    if rep:
+        sim.rep_enabled, sim.rep_k, sim.rep_cutoff, sim.rep_timescale = True, rep[0], rep[1], rep[2]
+        ctx.set_repulsion(True, rep[0], rep[1])
+    if wall:
+        sim.wall_enabled, sim.wall_k, sim.wall_cutoff, sim.wall_timescale = True, wall[0], wall[1], wall[2]
+        ctx.set_wall_repulsion(True, wall[0], wall[1])
+    for _ in range(steps):
+        sim.iterate()
+    ctx.iterate(steps)
+    U.assert_close(ctx.cells_download(H.P_POS), sim.pos, "positions", rtol=1e-12)
+    U.assert_close(ctx.cells_download(H.P_VEL), sim.vel, "velocities", rtol=1e-8, floor=1e-11)
+    U.assert_close(ctx.cells_download(H.P_FREP), sim.frep, "repulsion force", rtol=1e-7, floor=1e-9)
+    U.assert_close(ctx.cells_download(H.P_FORCE), sim.pforce, "membrane force", rtol=1e-7, floor=1e-9)
+    U.assert_close(ctx.lattice_download(H.LAT_POP), sim.pop, "populations", rtol=1e-9, floor=1e-11)
+    assert ctx.count()[0] == len(sim.ctype)
+    ctx.close()
+
+
+def test_pipeflow_like_config():
+    """examples/pipeflow: cylinder of bounce-back nodes, x periodic, Poiseuille body force, RBC + PLT,
+    tau = 1.82 (dt 1e-7), material every 20 / velocity every 5, cell-cell + boundary-particle repulsion"""
+    par = M.Parameters(dx=0.5e-6, dt=1e-7)
+    nx, ny, nz = 40, 34, 34
+    y, z = np.meshgrid(np.arange(ny), np.arange(nz), indexing="ij")
+    outside = (y - (ny - 1) / 2.0) ** 2 + (z - (nz - 1) / 2.0) ** 2 > 15.0 ** 2
+    fl = np.zeros((nx, ny, nz), dtype=np.uint8); fl[:, outside] = 1
+    fl = fl.reshape(-1)
+    dom = O.make_domain(nx, ny, nz, (1, 0, 0), par.tau)
+    body = (8 * par.nu_lbm * 0.01 / 15.0 ** 2, 0.0, 0.0)
+    rbc, plt = O.rbc_celltype(par), O.plt_celltype(par)
+    # RBCs nearly touching each other (cell-cell repulsion active); a platelet 1.5 nodes from the wall (boundary repulsion)
+    rbc_cells = U.deformed_cells(rbc, [(12.0, 16.5, 14.0), (12.4, 16.8, 18.6), (31.0, 17.0, 16.0)], 5, amp=0.0, stretch=(1.0, 1.0, 1.0))
+    plt_cells = U.deformed_cells(plt, [(24.0, 16.5, 4.6), (38.5, 20.0, 20.0)], 6, amp=0.0, stretch=(1.0, 1.0, 1.0))
+    k_rep = 2e-22 / par.df; cut = 0.7e-6 / par.dx
+    _run_pair(dom, fl, None, body, par, [rbc, plt], [rbc_cells, plt_cells], steps=40, vel_ts=5, mat_ts=20,
+              rep=(k_rep, cut, 20), wall=(k_rep, cut * 1.5, 20))
+
+
+def test_cube_like_config():
+    """examples/cube: x periodic, bounce-back planes at y = 0 / ny-1, regularized moving walls at z = 0 / nz-1,
+    tau = 1 (dt < 0), RBCs + a platelet, material every 20 / velocity every 5"""
+    par = M.Parameters(dx=0.5e-6, dt=-1.0)
+    assert abs(par.tau - 1.0) < 1e-14
+    nx, ny, nz = 36, 36, 30
+    fl = U.couette_flags(nx, ny, nz)
+    fl[:, 0, :] = 1; fl[:, ny - 1, :] = 1
+    fl = fl.reshape(-1)
+    bc = np.zeros((6, 3)); bc[4] = (0.015, 0, 0); bc[5] = (-0.015, 0, 0)
+    dom = O.make_domain(nx, ny, nz, (1, 0, 0), par.tau, bc)
+    rbc, plt = O.rbc_celltype(par), O.plt_celltype(par)
+    rbc_cells = U.deformed_cells(rbc, [(10.0, 17.0, 9.0), (27.5, 18.0, 20.0), (35.0, 12.0, 12.0)], 7, amp=0.01, stretch=(1.03, 0.99, 0.98))
+    plt_cells = U.deformed_cells(plt, [(18.0, 8.0, 24.0)], 8, amp=0.0, stretch=(1.0, 1.0, 1.0))
+    _run_pair(dom, fl, bc, None, par, [rbc, plt], [rbc_cells, plt_cells], steps=40, vel_ts=5, mat_ts=20)
+
+
+def test_full_size_unit_properties():
+    """cases/performance_testing unit at full size (256^3, ~8.5 k RBC, 5.4 M LSPs): properties that hold at any size.
+    * mass: sum(rho) is conserved by collide-and-stream on the periodic box (to round-off);
+    * momentum: membrane and IBM forces are internal, so d/dt sum(rho u) = N * body force per step;
+    * every cell survives, volumes stay within 0.5 % of the equilibrium volume;
+    * the step is deterministic: two contexts fed the same input agree bit for bit."""
+    H = _lib()
+    import bench
+    par = H.parameters(bench.DX, -1.0)
+    ct = H.HostCellType(H.MODEL_RBC, H.RBC_FROM_SPHERE, par, H.RBC_MATERIAL)
+    n = 256
+    cells, ids = ct.place(bench.synthetic_rows(), bench.DX, (n, n, n))
+    body = bench.body_force(par["nu_lbm"], n)
+    N = n ** 3
+
+    def run(steps):
+        ctx = H.Context(n, n, n, (1, 1, 1), par["tau"])
+        ctx.set_flags(np.zeros(N, dtype=np.uint8))
+        ctx.set_body_force(body)
+        ctx.set_force_limit(par["f_limit"])
+        t = ct.add_to(ctx)
+        ctx.add_cells(t, cells, ids)
+        ctx.set_timescales(1, 1, 1)
+        ctx.set_material_timescale(t, 20)
+        rho0 = ctx.lattice_download(H.LAT_DENSITY)
+        ctx.iterate(steps)
+        rho = ctx.lattice_download(H.LAT_DENSITY)
+        u = ctx.lattice_download(H.LAT_VELOCITY).reshape(3, N)
+        vol, _ = ctx.volume_area()
+        pos = ctx.cells_download(H.P_POS)
+        out = dict(m0=rho0.sum(), m1=rho.sum(), mom=(u * rho[None]).sum(1), vol=vol, pos=pos, ncell=ctx.count()[0])
+        ctx.close()
+        return out
+
+    steps = 20
+    a = run(steps)
+    assert a["ncell"] == len(ids)
+    assert abs(a["m1"] - a["m0"]) <= 1e-12 * a["m0"]
+    # Cell::computeVelocity holds the half-force shift: sum(rho u) = sum(j) + sum(rho F)/2 with F = body after the reset
+    expect = N * np.array(body) * (steps + 0.5)
+    assert np.all(np.abs(a["mom"] - expect) <= 1e-6 * np.abs(expect).max()), (a["mom"], expect)
+    veq = ct.scalar(0)
+    assert np.all(np.abs(a["vol"] / veq - 1.0) < 5e-3)
+    b = run(steps)
+    assert np.array_equal(a["pos"], b["pos"]) or np.abs(a["pos"] - b["pos"]).max() < 1e-12   # fp64 atomics may reorder sums
