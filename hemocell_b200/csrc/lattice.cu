@@ -174,14 +174,89 @@ k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, doub
   }
 }
 
+// tau = 1 fast path.  With omega = 1 the BGK collision forgets the incoming populations: the post-collision
+// state of a fluid node is f*_q = feq_q(rhoBar, j + rho F/2) + Guo_q(u, F), a function of the node's four raw
+// moments and its force alone.  When the moments pass of the previous step kept (rhoBar, j) in W (it pulls the
+// same 19 populations this kernel would pull), a fluid node reads 32 B of W + 32 B of F instead of 152 B of
+// populations; wall nodes (bounce-back, velocity planes) take the generic pull path.  Same arithmetic as
+// guo_collide with om1 = 0, omega = 1 (0*f + 1*feq is exact), so the results are those of k_collide_stream.
+__device__ __forceinline__ void guo_collide_tau1(double f[19], double rhoBar, const double j[3], const double F[3]) {
+  constexpr int CX[19] = {0,-1,0,0,-1,-1,-1,-1,0,0, 1,0,0,1,1,1,1,0,0};
+  constexpr int CY[19] = {0,0,-1,0,-1,1,0,0,-1,-1, 0,1,0,1,-1,0,0,1,1};
+  constexpr int CZ[19] = {0,0,0,-1,0,0,-1,1,-1,1, 0,0,1,0,0,1,-1,1,-1};
+  constexpr double T0 = 1.0/3.0, T1 = 1.0/18.0, T2 = 1.0/36.0;
+  const double rho = 1.0 + rhoBar, invRho = 1.0/rho;
+  const double ux = j[0]*invRho + 0.5*F[0], uy = j[1]*invRho + 0.5*F[1], uz = j[2]*invRho + 0.5*F[2];
+  const double jx = rho*ux, jy = rho*uy, jz = rho*uz;
+  const double jSqr = jx*jx + jy*jy + jz*jz;
+  const double fpre = 1.0 - 1.0/2.0;
+  const double uF = ux*F[0] + uy*F[1] + uz*F[2];
+#pragma unroll
+  for (int q = 0; q < 19; q++) {
+    const double t = (q == 0) ? T0 : ((q <= 3 || (q >= 10 && q <= 12)) ? T1 : T2);
+    const double cj = CX[q]*jx + CY[q]*jy + CZ[q]*jz;
+    const double cu = CX[q]*ux + CY[q]*uy + CZ[q]*uz;
+    const double cF = CX[q]*F[0] + CY[q]*F[1] + CZ[q]*F[2];
+    const double ft = 3.0*(cF - uF) + 9.0*cu*cF;
+    f[q] = feq(t, cj, rhoBar, invRho, jSqr) + t*fpre*ft;
+  }
+}
+
+template <bool RESET, bool VELBC, bool PEER>
+__global__ void __launch_bounds__(256, 2)
+k_collide_tau1(const double* __restrict__ gin, double* __restrict__ gout, double* __restrict__ F,
+               const double* __restrict__ W, const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count,
+               double* __restrict__ peerL, double* __restrict__ peerR) {
+  const int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int64_t i = first + k;
+  const int64_t n = i + a.P;
+  const int rem = (int)(i % a.P);
+  double f[19];
+  const uint8_t fl = flags[n];
+  if (fl == HCG_FLUID) {
+    double w0, w1, w2, w3, f0, f1, f2, f3;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w0), "=d"(w1), "=d"(w2), "=d"(w3) : "l"(W + 4*n));
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(f0), "=d"(f1), "=d"(f2), "=d"(f3) : "l"(F + 4*n) : "memory");
+    const double j[3] = {w1, w2, w3}, Fn[3] = {f0, f1, f2};
+    guo_collide_tau1(f, w0, j, Fn);
+  } else {
+    const int y = rem / a.nz, z = rem - y*a.nz;
+    pull19(gin, a, n, y, z, f);
+    if (fl == HCG_BOUNCEBACK) {
+#pragma unroll
+      for (int q = 1; q <= 9; q++) { const double t = f[q]; f[q] = f[q+9]; f[q+9] = t; }
+    } else {
+      const double2 fa = *reinterpret_cast<const double2*>(F + 4*n);
+      double Fn[3] = {fa.x, fa.y, F[4*n + 2]};
+      if (VELBC && fl >= HCG_VEL_XN) { const double uw[3] = {a.bc[3*(fl-2)], a.bc[3*(fl-2)+1], a.bc[3*(fl-2)+2]}; regularized_complete(f, fl - 2, uw); }
+      guo_collide(f, Fn, a.omega);
+    }
+  }
+  if (RESET) { double2* Fw = reinterpret_cast<double2*>(F + 4*n); Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0); }
+#pragma unroll
+  for (int q = 0; q < 19; q++) gout[(int64_t)q*a.S + n] = f[q];
+  if (PEER) {
+    if (i < a.P && peerL) {
+      const int64_t off = (int64_t)(a.nxl + 1)*a.P + rem;
+      peerL[1*a.S + off] = f[1]; peerL[4*a.S + off] = f[4]; peerL[5*a.S + off] = f[5]; peerL[6*a.S + off] = f[6]; peerL[7*a.S + off] = f[7];
+    }
+    if (i >= (int64_t)(a.nxl - 1)*a.P && peerR) {
+      const int64_t off = rem;
+      peerR[10*a.S + off] = f[10]; peerR[13*a.S + off] = f[13]; peerR[14*a.S + off] = f[14]; peerR[15*a.S + off] = f[15]; peerR[16*a.S + off] = f[16];
+    }
+  }
+}
+
 // Moments pass: velocity the IBM interpolation sees, u = j/rho + F/2 of the POST-stream
 // populations with the spread force still on the node (Cell::computeVelocity through
 // core/hemoCellParticleField.cpp:833).  BounceBack: 0; velocity plane: wall velocity.
-template <bool RESET, bool PEER>
+// WOUT (tau = 1 fast path, see k_collide_tau1): also keep the raw moments (rhoBar, j) of the node in W.
+template <bool RESET, bool PEER, bool WOUT>
 __global__ void __launch_bounds__(256)
 k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restrict__ U,
           const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count,
-          double* __restrict__ peerL, double* __restrict__ peerR) {
+          double* __restrict__ peerL, double* __restrict__ peerR, double* __restrict__ W) {
   const int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (k >= count) return;
   const int64_t i = first + k;
@@ -192,6 +267,7 @@ k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restri
   pull19(g, a, n, y, z, f);
   double rhoBar, j[3];
   moments19(f, rhoBar, j);
+  if (WOUT) { double2* Ww = reinterpret_cast<double2*>(W + 4*n); Ww[0] = make_double2(rhoBar, j[0]); Ww[1] = make_double2(j[1], j[2]); }
   const uint8_t fl = flags[n];
   double u0, u1, u2, rho = 1.0 + rhoBar;
   if (fl == HCG_FLUID) {
@@ -791,6 +867,24 @@ hcg_status lat_collide_rows(hcg_ctx* c, bool reset_force, int row0, int row1, cu
   if (done) return hcg_fail(c, HCG_ERR_STATE, "plane counters need the row-pipelined kernel");
   const int64_t first = (int64_t)row0*a.nz, n = (int64_t)(row1 - row0)*a.nz;
   const unsigned nb = nblk(n, 256);
+  if (c->W && c->w_valid && c->omega == 1.0) {
+    // tau = 1 and the raw moments of the current populations are at hand (k_moments<.., WOUT>)
+    double* pL = nullptr; double* pR = nullptr;
+    const bool peer = peer_on(c);
+    if (peer) { pL = c->peer.link[0].rank >= 0 ? (double*)c->peer.link[0].ptr[1 - c->cur] : nullptr;
+                pR = c->peer.link[1].rank >= 0 ? (double*)c->peer.link[1].ptr[1 - c->cur] : nullptr; }
+#define K1T_LAUNCH(R, V, P) k_collide_tau1<R, V, P><<<nb, 256, 0, st>>>(gin, gout, c->F, c->W, c->flags, a, first, n, pL, pR)
+    if (peer) {
+      if (c->has_velbc) { if (reset_force) K1T_LAUNCH(true, true, true); else K1T_LAUNCH(false, true, true); }
+      else { if (reset_force) K1T_LAUNCH(true, false, true); else K1T_LAUNCH(false, false, true); }
+    } else {
+      if (c->has_velbc) { if (reset_force) K1T_LAUNCH(true, true, false); else K1T_LAUNCH(false, true, false); }
+      else { if (reset_force) K1T_LAUNCH(true, false, false); else K1T_LAUNCH(false, false, false); }
+    }
+#undef K1T_LAUNCH
+    KERNEL_CHECK(c);
+    return HCG_OK;
+  }
   if (peer_on(c)) {
     double* pL = c->peer.link[0].rank >= 0 ? (double*)c->peer.link[0].ptr[1 - c->cur] : nullptr;
     double* pR = c->peer.link[1].rank >= 0 ? (double*)c->peer.link[1].ptr[1 - c->cur] : nullptr;
@@ -810,31 +904,41 @@ hcg_status lat_collide_rows(hcg_ctx* c, bool reset_force, int row0, int row1, cu
 
 hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
   {
-    OpTimer tk(c, "kernel:k_collide_stream");
+    OpTimer tk(c, (c->W && c->w_valid && c->omega == 1.0) ? "kernel:k_collide_tau1" : "kernel:k_collide_stream");
     hcg_status s = lat_collide_rows(c, reset_force, 0, c->nxl*c->dom.ny, c->stream, nullptr); if (s) return s;
   }
   c->cur = 1 - c->cur;
-  c->u_valid = false;
+  c->u_valid = false; c->w_valid = false;
   if (peer_on(c)) return peer_barrier(c);          // the face planes were stored into the neighbours by the kernel itself
   return lat_halo_exchange_pop(c);
 }
 
 // moments of the rows [row0, row1): plain one-thread-per-node kernel (read-dominated, no register
 // pressure: it out-runs the row-pipelined variant)
+static bool tau1_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("HCG_TAU1"); on = e ? atoi(e) : 1; }
+  return on != 0;
+}
 static hcg_status moments_rows(hcg_ctx* c, bool reset_force, int row0, int row1) {
   if (row1 <= row0) return HCG_OK;
   LatArgs a = make_args(c);
   const int64_t first = (int64_t)row0*a.nz, n = (int64_t)(row1 - row0)*a.nz;
   const unsigned nb = nblk(n, 256);
-  if (peer_on(c)) {
-    double* pL = c->peer.link[0].rank >= 0 ? (double*)c->peer.link[0].ptr[2] : nullptr;
-    double* pR = c->peer.link[1].rank >= 0 ? (double*)c->peer.link[1].ptr[2] : nullptr;
-    if (reset_force) k_moments<true, true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, pL, pR);
-    else k_moments<false, true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, pL, pR);
+  double* pL = nullptr; double* pR = nullptr;
+  const bool peer = peer_on(c);
+  if (peer) { pL = c->peer.link[0].rank >= 0 ? (double*)c->peer.link[0].ptr[2] : nullptr;
+              pR = c->peer.link[1].rank >= 0 ? (double*)c->peer.link[1].ptr[2] : nullptr; }
+  const bool wout = c->W != nullptr;
+#define MOM_LAUNCH(R, P, WO) k_moments<R, P, WO><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, pL, pR, c->W)
+  if (peer) {
+    if (wout) { if (reset_force) MOM_LAUNCH(true, true, true); else MOM_LAUNCH(false, true, true); }
+    else { if (reset_force) MOM_LAUNCH(true, true, false); else MOM_LAUNCH(false, true, false); }
   } else {
-    if (reset_force) k_moments<true, false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, nullptr, nullptr);
-    else k_moments<false, false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, nullptr, nullptr);
+    if (wout) { if (reset_force) MOM_LAUNCH(true, false, true); else MOM_LAUNCH(false, false, true); }
+    else { if (reset_force) MOM_LAUNCH(true, false, false); else MOM_LAUNCH(false, false, false); }
   }
+#undef MOM_LAUNCH
   KERNEL_CHECK(c);
   return HCG_OK;
 }
@@ -850,9 +954,13 @@ hcg_status lat_moments(hcg_ctx* c, bool reset_force, bool want_rho) {
   (void)want_rho;   // the density always rides in slot 3 of the node velocity
   {
     OpTimer tk(c, "kernel:k_moments");
+    if (!c->W && c->omega == 1.0 && tau1_enabled()) {      // tau = 1: keep the raw moments for the next collision
+      CUDA_TRY(c, cudaMalloc(&c->W, sizeof(double)*4*c->S));
+      CUDA_TRY(c, cudaMemsetAsync(c->W, 0, sizeof(double)*4*c->S, c->stream));
+    }
     hcg_status s = moments_rows(c, reset_force, 0, c->nxl*c->dom.ny); if (s) return s;
   }
-  c->u_valid = true;
+  c->u_valid = true; c->w_valid = c->W != nullptr;
   if (peer_on(c)) return peer_barrier(c);
   return lat_halo_exchange_u(c);
 }
@@ -880,7 +988,7 @@ hcg_status lat_collide_moments_overlapped(hcg_ctx* c, bool* done_out) {
     OpTimer tk(c, "kernel:k_collide_stream");
     if ((s = lat_collide_rows(c, false, 0, nxl*ny, c->stream, c->fused_done))) return s;
   }
-  c->cur = 1 - c->cur;
+  c->cur = 1 - c->cur; c->w_valid = false;
   {
     // planes m_lo..m_hi; multi-GPU: the face planes need the neighbour's halo and follow after the exchange
     const int m_lo = R > 1 ? 2 : 1, m_hi = R > 1 ? nxl - 1 : nxl;
@@ -931,7 +1039,7 @@ hcg_status lat_init_equilibrium(hcg_ctx* c, double rho, const double u[3]) {
   KERNEL_CHECK(c);
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   cudaFree(dv);
-  c->u_valid = false;
+  c->u_valid = false; c->w_valid = false;
   return lat_halo_exchange_pop(c);
 }
 
@@ -954,7 +1062,7 @@ hcg_status lat_pop_from_reference(hcg_ctx* c, const double* src_dev) {
   CUDA_TRY(c, cudaMemsetAsync(c->g[c->cur], 0, sizeof(double)*19*c->S, c->stream));
   k_from_reference<<<nblk((int64_t)c->nxl*c->P, 256), 256, 0, c->stream>>>(s, c->g[c->cur], a);
   KERNEL_CHECK(c);
-  c->u_valid = false;
+  c->u_valid = false; c->w_valid = false;
   return lat_halo_exchange_pop(c);
 }
 

@@ -310,3 +310,37 @@ def test_output_observables_stretch_and_pineq():
     pi[:, fl.reshape(-1) == 1] = 0.0
     U.assert_close(ctx.lattice_download(H.LAT_PINEQ), pi, "PiNeq", rtol=1e-10, floor=1e-12)
     ctx.close()
+
+
+@pytest.mark.parametrize("flagkind", ["none", "bb_slab", "couette", "box"])
+def test_tau1_fast_path_matches_oracle(flagkind):
+    """omega = 1: after a moments pass the collision reads the node's raw moments instead of its 19 populations
+    (k_collide_tau1); walls take the generic path inside the same kernel"""
+    H = _lib()
+    nx, ny, nz = 20, 18, 32
+    bc = np.zeros((6, 3))
+    periodic = (1, 1, 1)
+    fl = np.zeros((nx, ny, nz), dtype=np.uint8)
+    if flagkind == "bb_slab":
+        fl[nx//4:nx//4+3, 3:ny//2+1, 2:7] = 1; fl[:, 0, :] = 1
+    elif flagkind == "couette":
+        fl = U.couette_flags(nx, ny, nz); bc[4] = (0.02, 0.0, 0.0); bc[5] = (-0.02, 0.001, 0.0); periodic = (1, 1, 0)
+    elif flagkind == "box":
+        fl = U.box_flags(nx, ny, nz); periodic = (0, 0, 0)
+    fl = fl.reshape(-1)
+    dom = O.make_domain(nx, ny, nz, periodic, 1.0, bc)
+    rng = np.random.default_rng(17)
+    pop = U.mask_inflow(dom, U.smooth_state(dom, 19))
+    force = np.ascontiguousarray(1e-5 * rng.standard_normal(3 * nx * ny * nz))
+    ctx = U.gpu_context(dom, fl, bc)
+    ctx.lattice_upload(H.LAT_POP, pop)
+    ctx.lattice_upload(H.LAT_FORCE, force)
+    ref = pop.copy()
+    launches = []
+    for step in range(1, 6):
+        rho, vel = O.moments(dom, fl, ref, force)
+        U.assert_close(ctx.lattice_download(H.LAT_DENSITY), rho, f"density before step {step}")   # moments pass: W becomes valid
+        O.collide_and_stream(dom, fl, ref, force)
+        ctx.op("collide_stream")
+        U.assert_close(ctx.lattice_download(H.LAT_POP), ref, f"populations after {step} steps ({flagkind}, tau = 1)")
+    ctx.close()
