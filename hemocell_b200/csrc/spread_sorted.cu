@@ -122,14 +122,44 @@ __global__ void k_perm_identity(uint16_t* perm, int npair, int64_t total) {
 // Phase 2 (thread = chunk of 8 consecutive node-sorted pairs): walk the chunk sequentially, rebuild the
 // pair's node and NORMALISED weight from the staged position (same expressions, same bits as phase 1),
 // merge runs of equal node in registers, one fp64 RED triple per run.
-template <int THREADS, bool CHECK_FLAGS>
+// bulk-async staging helpers (1-D TMA path: cp.async.bulk global -> shared, completion on an mbarrier)
+__device__ __forceinline__ uint32_t sp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sp_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(sp_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sp_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = sp_smem_u32(bar);
+  uint32_t ok = 0;
+  long long t_start = 0;
+  for (unsigned spin = 0; !ok; spin++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (!ok && (spin & 255u) == 255u) {       // a byte-count mismatch must not hang the device: trap after ~2 s
+      const long long now = clock64();
+      if (t_start == 0) t_start = now; else if (now - t_start > 4000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void sp_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(sp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sp_smem_u32(bar)) : "memory");
+}
+
+// BULK: the cell's nine particle arrays (V contiguous doubles each) arrive in shared memory as nine bulk-async
+// copies issued by one thread, and the first node-sorted pairs are already in registers when they land:
+// phase 1 no longer waits on global loads (they were ~35 % of the kernel's stall samples).  Needs V even
+// (16-byte aligned segments); otherwise the direct-load variant runs.
+template <int THREADS, bool CHECK_FLAGS, bool BULK>
 __global__ void __launch_bounds__(THREADS)
 k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ alive,
                 const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                 double* fx, double* fy, double* fz,
                 const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
                 const uint16_t* __restrict__ perm, double* __restrict__ F) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int V = a.V;
   const int64_t cell = a.first_cell + blockIdx.x;
   if (!alive[cell]) return;
@@ -139,11 +169,34 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
   double* t0 = CO + V; double* t1 = t0 + V; double* t2 = t1 + V;   // force_repulsion + capped force
   int* J = reinterpret_cast<int*>(t2 + V);                         // [6][V] node offsets: x(d=0,1), y(d=0,1), z(d=0,1)
   uint8_t* M = reinterpret_cast<uint8_t*>(J + 6*V);                // bit c: corner c adds to a real node of this rank
+  // BULK only: staged membrane force (3V doubles) and the mbarrier, behind M (rounded up to 16 bytes)
+  double* SF = reinterpret_cast<double*>(reinterpret_cast<char*>(sm) + (((size_t)80*V + V + 15) & ~(size_t)15));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(SF + 3*V);
+
+  const uint4* pp = reinterpret_cast<const uint4*>(perm + (int64_t)blockIdx.x*8*V);
+  constexpr int NPRE = 3;                                          // chunks of 8 pairs prefetched per thread
+  uint4 qpre[NPRE];
+  if (BULK) {
+    if (threadIdx.x == 0) {
+      sp_mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const uint32_t nb = (uint32_t)(V*sizeof(double));
+      sp_mbar_expect_tx(bar, 9*nb);
+      sp_bulk_g2s(PX, x + base, nb, bar); sp_bulk_g2s(PY, y + base, nb, bar); sp_bulk_g2s(PZ, z + base, nb, bar);
+      sp_bulk_g2s(t0, rx + base, nb, bar); sp_bulk_g2s(t1, ry + base, nb, bar); sp_bulk_g2s(t2, rz + base, nb, bar);
+      sp_bulk_g2s(SF, fx + base, nb, bar); sp_bulk_g2s(SF + V, fy + base, nb, bar); sp_bulk_g2s(SF + 2*V, fz + base, nb, bar);
+    }
+#pragma unroll
+    for (int r = 0; r < NPRE; r++) { const int j = threadIdx.x + r*THREADS; if (j < V) qpre[r] = __ldg(pp + j); }
+    __syncthreads();                                               // the barrier is initialised for everyone
+    sp_mbar_wait(bar, 0);
+  }
 
   for (int v = threadIdx.x; v < V; v += THREADS) {
     const int64_t p = base + v;
-    const double px = x[p], py = y[p], pz = z[p];
-    double f0 = fx[p], f1 = fy[p], f2 = fz[p];
+    double px, py, pz, f0, f1, f2, r0, r1, r2;
+    if (BULK) { px = PX[v]; py = PY[v]; pz = PZ[v]; f0 = SF[v]; f1 = SF[V + v]; f2 = SF[2*V + v]; r0 = t0[v]; r1 = t1[v]; r2 = t2[v]; }
+    else { px = x[p]; py = y[p]; pz = z[p]; f0 = fx[p]; f1 = fy[p]; f2 = fz[p]; r0 = rx[p]; r1 = ry[p]; r2 = rz[p]; }
     const double mag = sqrt(f0*f0 + f1*f1 + f2*f2);
     if (mag > a.f_limit) {                      // permanent cap (hemoCellParticleField.cpp:848-852)
       const double s = a.f_limit/mag;
@@ -178,16 +231,15 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
       total += w;
       if (realx[dx]) mask |= 1u << c;            // ghost planes count in the normalisation only
     }
-    PX[v] = px; PY[v] = py; PZ[v] = pz; CO[v] = 1.0/total;
-    t0[v] = rx[p] + f0; t1[v] = ry[p] + f1; t2[v] = rz[p] + f2;
+    if (!BULK) { PX[v] = px; PY[v] = py; PZ[v] = pz; }
+    CO[v] = 1.0/total;
+    t0[v] = r0 + f0; t1[v] = r1 + f1; t2[v] = r2 + f2;
     J[v] = jx[0]; J[V + v] = jx[1]; J[2*V + v] = jy[0]; J[3*V + v] = jy[1]; J[4*V + v] = jz[0]; J[5*V + v] = jz[1];
     M[v] = skip ? 0 : (uint8_t)mask;             // multi-GPU: a candidate node is not addressable here
   }
   __syncthreads();
 
-  const uint4* pp = reinterpret_cast<const uint4*>(perm + (int64_t)blockIdx.x*8*V);
-  for (int j = threadIdx.x; j < V; j += THREADS) {
-    const uint4 q = __ldg(pp + j);              // 8 consecutive sorted pairs
+  auto process = [&](const uint4 q) {            // 8 consecutive sorted pairs
     const unsigned e8[4] = {q.x, q.y, q.z, q.w};
     int cur = -1; double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll
@@ -209,6 +261,13 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
       } else { a0 += v0; a1 += v1; a2 += v2; }
     }
     if (cur >= 0) { double* Fn = F + 4*(int64_t)cur; atomicAdd(Fn, a0); atomicAdd(Fn + 1, a1); atomicAdd(Fn + 2, a2); }
+  };
+  if (BULK) {
+#pragma unroll
+    for (int r = 0; r < NPRE; r++) { const int j = threadIdx.x + r*THREADS; if (j < V) process(qpre[r]); }
+    for (int j = threadIdx.x + NPRE*THREADS; j < V; j += THREADS) process(__ldg(pp + j));
+  } else {
+    for (int j = threadIdx.x; j < V; j += THREADS) process(__ldg(pp + j));
   }
 }
 
@@ -247,23 +306,23 @@ hcg_status spread_sorted_rebuild(hcg_ctx* c) {
 }
 
 hcg_status spread_sorted(hcg_ctx* c) {
+  static int bulk_env = -1;
+  if (bulk_env < 0) { const char* e = getenv("HCG_SPREAD_BULK"); bulk_env = e ? atoi(e) : 1; }
   for (auto& th : c->types) {
     if (th.n_cells == 0) continue;
     SpArgs a = make_args(c, th);
     const int V = th.d.V;
-    const size_t smem = sizeof(double)*7*V + sizeof(int)*6*V + V + 16;
+    const bool bulk = bulk_env && (V % 2 == 0) && (th.first_particle % 2 == 0) && V >= 256;
+    const size_t core = (((size_t)80*V + V + 15) & ~(size_t)15);
+    const size_t smem = bulk ? core + sizeof(double)*3*V + 16 : core + 16;
     const bool chk = c->has_nonfluid;
-#define SP_LAUNCH(T, C) do { \
-      CUDA_TRY(c, cudaFuncSetAttribute(k_spread_sorted<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      k_spread_sorted<T, C><<<(unsigned)th.n_cells, T, smem, c->stream>>>(a, c->flags, c->cell_alive, c->pos[0], c->pos[1], c->pos[2], \
+#define SP_LAUNCH(T, C, B) do { \
+      CUDA_TRY(c, cudaFuncSetAttribute(k_spread_sorted<T, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_spread_sorted<T, C, B><<<(unsigned)th.n_cells, T, smem, c->stream>>>(a, c->flags, c->cell_alive, c->pos[0], c->pos[1], c->pos[2], \
           c->frc[0], c->frc[1], c->frc[2], c->frep[0], c->frep[1], c->frep[2], th.perm, c->F); } while (0)
-    static int thr = -1;
-    if (thr < 0) { const char* e = getenv("HCG_SPREAD_THREADS"); thr = e ? atoi(e) : 256; }
-    if (V >= 256 && thr == 352) { if (chk) SP_LAUNCH(352, true); else SP_LAUNCH(352, false); }
-    else if (V >= 256 && thr == 672) { if (chk) SP_LAUNCH(672, true); else SP_LAUNCH(672, false); }
-    else if (V >= 256 && thr == 128) { if (chk) SP_LAUNCH(128, true); else SP_LAUNCH(128, false); }
-    else if (V >= 256) { if (chk) SP_LAUNCH(256, true); else SP_LAUNCH(256, false); }
-    else { if (chk) SP_LAUNCH(64, true); else SP_LAUNCH(64, false); }
+    if (V >= 256 && bulk) { if (chk) SP_LAUNCH(256, true, true); else SP_LAUNCH(256, false, true); }
+    else if (V >= 256) { if (chk) SP_LAUNCH(256, true, false); else SP_LAUNCH(256, false, false); }
+    else { if (chk) SP_LAUNCH(64, true, false); else SP_LAUNCH(64, false, false); }
 #undef SP_LAUNCH
     KERNEL_CHECK(c);
   }
