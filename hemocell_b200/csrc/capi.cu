@@ -245,7 +245,7 @@ void hcg_destroy(hcg_ctx* c) {
   cudaDeviceSynchronize();
   peer_destroy(c);
   if (c->nccl) ncclCommDestroy((ncclComm_t)c->nccl);
-  cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); cudaFree(c->flags); cudaFree(c->d_bc);
+  cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); if (c->F0) cudaFree(c->F0); cudaFree(c->flags); cudaFree(c->d_bc);
   if (c->rho) cudaFree(c->rho);
   if (c->fused_done) cudaFree(c->fused_done);
   for (int k = 0; k < 3; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->frc[k]); cudaFree(c->frep[k]); }
@@ -331,7 +331,24 @@ hcg_status hcg_lattice_set_body_force(hcg_ctx* c, const double f[3]) {
   if (!c || !f) return HCG_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
   for (int k = 0; k < 3; k++) c->body[k] = f[k];
+  if (c->F0) { CUDA_TRY(c, cudaStreamSynchronize(c->stream)); cudaFree(c->F0); c->F0 = nullptr; }   // back to a uniform force
   hcg_status s = lat_reset_force(c); if (s) return s;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_lattice_set_body_force_field(hcg_ctx* c, const double* f) {
+  if (!c || !f) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  hcg_status s;
+  if (!c->F0) {
+    CUDA_TRY(c, cudaMalloc(&c->F0, sizeof(double)*4*c->S));
+    CUDA_TRY(c, cudaMemsetAsync(c->F0, 0, sizeof(double)*4*c->S, c->stream));
+  }
+  if ((s = ensure_staging(c, sizeof(double)*3*c->Nl))) return s;
+  CUDA_TRY(c, cudaMemcpyAsync(c->staging, f, sizeof(double)*3*c->Nl, cudaMemcpyHostToDevice, c->stream));
+  if ((s = lat_pad3(c, c->staging, c->F0))) return s;
+  if ((s = lat_reset_force(c))) return s;
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return HCG_OK;
 }

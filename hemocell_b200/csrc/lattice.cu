@@ -905,7 +905,9 @@ hcg_status lat_collide_rows(hcg_ctx* c, bool reset_force, int row0, int row1, cu
 hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
   {
     OpTimer tk(c, (c->W && c->w_valid && c->omega == 1.0) ? "kernel:k_collide_tau1" : "kernel:k_collide_stream");
-    hcg_status s = lat_collide_rows(c, reset_force, 0, c->nxl*c->dom.ny, c->stream, nullptr); if (s) return s;
+    // a per-node driving force (F0) is restored by a copy after the kernel instead of the in-kernel reset
+    hcg_status s = lat_collide_rows(c, reset_force && !c->F0, 0, c->nxl*c->dom.ny, c->stream, nullptr); if (s) return s;
+    if (reset_force && c->F0 && (s = lat_reset_force(c))) return s;
   }
   c->cur = 1 - c->cur;
   c->u_valid = false; c->w_valid = false;
@@ -958,7 +960,8 @@ hcg_status lat_moments(hcg_ctx* c, bool reset_force, bool want_rho) {
       CUDA_TRY(c, cudaMalloc(&c->W, sizeof(double)*4*c->S));
       CUDA_TRY(c, cudaMemsetAsync(c->W, 0, sizeof(double)*4*c->S, c->stream));
     }
-    hcg_status s = moments_rows(c, reset_force, 0, c->nxl*c->dom.ny); if (s) return s;
+    hcg_status s = moments_rows(c, reset_force && !c->F0, 0, c->nxl*c->dom.ny); if (s) return s;
+    if (reset_force && c->F0 && (s = lat_reset_force(c))) return s;
   }
   c->u_valid = true; c->w_valid = c->W != nullptr;
   if (peer_on(c)) return peer_barrier(c);
@@ -975,7 +978,7 @@ hcg_status lat_collide_moments_overlapped(hcg_ctx* c, bool* done_out) {
   if (env_on < 0) { const char* e = getenv("HCG_OVERLAP"); env_on = e ? atoi(e) : 0; }   // opt-in (needs HCG_K1_ROWS=1): measured slower, DESIGN.md §4
   const int ny = c->dom.ny, nxl = c->nxl;
   RowCfg rc = row_config(c, nxl*ny);
-  if (!env_on || !rc.ok || !rc.interleave || ny % rc.R || nxl < 4) return HCG_OK;
+  if (!env_on || !rc.ok || !rc.interleave || ny % rc.R || nxl < 4 || c->F0) return HCG_OK;
   const int R = c->dom.n_ranks;
   const int wrapx = (R == 1 && c->dom.periodic[0]) ? 1 : 0;
   if (!c->fused_done) CUDA_TRY(c, cudaMalloc(&c->fused_done, sizeof(int)*(nxl + 2)));
@@ -1013,6 +1016,7 @@ hcg_status lat_collide_moments_overlapped(hcg_ctx* c, bool* done_out) {
 }
 
 hcg_status lat_reset_force(hcg_ctx* c) {
+  if (c->F0) { CUDA_TRY(c, cudaMemcpyAsync(c->F, c->F0, sizeof(double)*4*c->S, cudaMemcpyDeviceToDevice, c->stream)); return HCG_OK; }
   k_fill4<<<nblk(c->S, 256), 256, 0, c->stream>>>(c->F, c->S, c->body[0], c->body[1], c->body[2]);
   KERNEL_CHECK(c);
   return HCG_OK;

@@ -84,6 +84,8 @@ class GpuLattice {
   std::vector<uint8_t> flags;                 // global, z + nz*(y + ny*x)
   double bc[6][3];
   double body[3] = {0, 0, 0};
+  std::vector<double> bodyfield;              // optional per-node driving force, global, [3][N]; empty = uniform `body`
+  bool bodyfield_dirty = false; int bodyfield_generation = -1;
   double eq_rho = 1.0, eq_u[3] = {0, 0, 0};
   bool eq_pending = true, body_pending = true;
   hcg_ctx* ctx = nullptr;
@@ -142,7 +144,18 @@ class GpuLattice {
       flags_dirty = false;
     }
     if (eq_pending) { ck(ctx, hcg_lattice_init_equilibrium(ctx, eq_rho, eq_u), "hcg_lattice_init_equilibrium"); eq_pending = false; }
-    if (body_pending) { ck(ctx, hcg_lattice_set_body_force(ctx, body), "hcg_lattice_set_body_force"); body_pending = false; }
+    if (body_pending) {
+      if (bodyfield.empty()) ck(ctx, hcg_lattice_set_body_force(ctx, body), "hcg_lattice_set_body_force");
+      else if (bodyfield_dirty || bodyfield_generation != generation) {
+        // this rank's slab of the global field, component-major
+        const size_t N = (size_t)nx*ny*nz, Nl = (size_t)nxl()*ny*nz, off = (size_t)rank()*Nl;
+        std::vector<double> slab(3*Nl);
+        for (int k = 0; k < 3; k++) std::copy(bodyfield.begin() + k*N + off, bodyfield.begin() + k*N + off + Nl, slab.begin() + k*Nl);
+        ck(ctx, hcg_lattice_set_body_force_field(ctx, slab.data()), "hcg_lattice_set_body_force_field");
+        bodyfield_dirty = false; bodyfield_generation = generation;
+      }
+      body_pending = false;
+    }
   }
   void touchFlags() { flags_dirty = true; }
 
@@ -1208,10 +1221,24 @@ void gpu_lattice_boundary_velocity(GpuLattice* gp, const Box3D& domain_, const d
 void gpu_lattice_external_vector(GpuLattice* gp, const Box3D& domain_, const double vec[3]) {
   GpuLattice& g = *gp;
   const Box3D domain = clip(g, domain_);
-  if (domain.nCells() != (plint)g.nx*g.ny*g.nz) fatal("(HemoCell) (setExternalVector) only the whole bounding box is supported (uniform driving force)");
+  if (domain.nCells() != (plint)g.nx*g.ny*g.nz) {
+    // a force on part of the lattice (cases/kolmogorovFlow/kolmogorovFlow.cpp:138-142): keep a per-node driving-force
+    // field on the host, upload it when it changes; iterate() resets the node force to it.  Regions never set keep the
+    // uniform value given before.
+    const size_t N = (size_t)g.nx*g.ny*g.nz;
+    if (g.bodyfield.empty()) { g.bodyfield.resize(3*N); for (int k = 0; k < 3; k++) std::fill(g.bodyfield.begin() + k*N, g.bodyfield.begin() + (k + 1)*N, g.body[k]); g.bodyfield_dirty = true; }
+    for (plint x = domain.x0; x <= domain.x1; x++) for (plint y = domain.y0; y <= domain.y1; y++) for (plint z = domain.z0; z <= domain.z1; z++) {
+      const size_t i = (size_t)g.idx((int)x, (int)y, (int)z);
+      for (int k = 0; k < 3; k++) if (g.bodyfield[k*N + i] != vec[k]) { g.bodyfield[k*N + i] = vec[k]; g.bodyfield_dirty = true; }
+    }
+    g.body_pending = true;
+    g.flush();
+    return;
+  }
   // after iterate() every node already carries the driving force again: re-applying the same value is free
-  if (g.ctx && !g.body_pending && vec[0] == g.body[0] && vec[1] == g.body[1] && vec[2] == g.body[2]) return;
+  if (g.ctx && !g.body_pending && g.bodyfield.empty() && vec[0] == g.body[0] && vec[1] == g.body[1] && vec[2] == g.body[2]) return;
   for (int k = 0; k < 3; k++) g.body[k] = vec[k];
+  g.bodyfield.clear(); g.bodyfield.shrink_to_fit(); g.bodyfield_dirty = false;
   g.body_pending = true;
   g.flush();
 }

@@ -45,7 +45,7 @@ class HcgTimer(C.Structure):
 
 # every symbol include/hemocell_gpu.h declares (tests check that the .so exports all of them)
 SYMBOLS = """hcg_last_error hcg_version hcg_create hcg_destroy hcg_comm_unique_id hcg_comm_init
-hcg_lattice_set_flags hcg_lattice_set_bc_velocity hcg_lattice_init_equilibrium hcg_lattice_set_body_force
+hcg_lattice_set_flags hcg_lattice_set_bc_velocity hcg_lattice_init_equilibrium hcg_lattice_set_body_force hcg_lattice_set_body_force_field
 hcg_lattice_upload hcg_lattice_download hcg_celltype_add hcg_cells_add hcg_cells_count hcg_cells_capacity
 hcg_cells_upload hcg_cells_download hcg_cells_info hcg_cells_add_force hcg_celltype_set_stiffness
 hcg_set_force_limit hcg_set_timescales hcg_set_material_timescale hcg_set_repulsion hcg_set_wall_repulsion
@@ -140,6 +140,11 @@ class Context:
 
     def set_body_force(self, f):
         self._ck(self.L.hcg_lattice_set_body_force(self.h, (C.c_double * 3)(*f)))
+
+    def set_body_force_field(self, f):
+        a = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        assert a.size == 3 * self.Nl
+        self._ck(self.L.hcg_lattice_set_body_force_field(self.h, _p(a)))
 
     def lattice_upload(self, field, arr):
         a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)

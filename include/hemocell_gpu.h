@@ -110,6 +110,10 @@ hcg_status hcg_lattice_init_equilibrium(hcg_ctx*, double rho, const double u[3])
 /* the setExternalVector(lattice, bbox, forceBeginsAt, f) every case file re-applies after
  * iterate() (examples/pipeflow/pipeflow.cpp:144-146): the value the node force is reset to */
 hcg_status hcg_lattice_set_body_force(hcg_ctx*, const double f[3]);
+/* the same with a different force per region, e.g. the two half-domains driven in opposite directions of
+ * cases/kolmogorovFlow/kolmogorovFlow.cpp:138-142: f[d*N + idx] over this rank's slab.  A later
+ * hcg_lattice_set_body_force() returns to the uniform value. */
+hcg_status hcg_lattice_set_body_force_field(hcg_ctx*, const double* f);
 hcg_status hcg_lattice_upload(hcg_ctx*, int32_t field /*POP|FORCE*/, const double* in);
 hcg_status hcg_lattice_download(hcg_ctx*, int32_t field /*POP|FORCE|VELOCITY|DENSITY|PINEQ*/, double* out);
 

@@ -344,3 +344,43 @@ def test_tau1_fast_path_matches_oracle(flagkind):
         ctx.op("collide_stream")
         U.assert_close(ctx.lattice_download(H.LAT_POP), ref, f"populations after {step} steps ({flagkind}, tau = 1)")
     ctx.close()
+
+
+def test_body_force_field_parity():
+    """per-node driving force (cases/kolmogorovFlow: the two half-domains pushed in opposite directions): the node
+    force is reset to the field after every step, on interpolation steps and on the others"""
+    H = _lib()
+    nx, ny, nz = 24, 20, 32
+    par = M.Parameters(dx=0.5e-6, dt=-1.0)
+    dom = O.make_domain(nx, ny, nz, (1, 1, 1), par.tau)
+    fl = np.zeros(nx * ny * nz, dtype=np.uint8)
+    N = nx * ny * nz
+    field = np.zeros((3, nx, ny, nz))
+    field[0, :, :, nz // 2:] = 3e-6; field[0, :, :, :nz // 2] = -3e-6; field[1, :, :5, :] = 1e-6
+    field = np.ascontiguousarray(field.reshape(-1))
+
+    class Sim(O.OracleSim):
+        def _reset_force(self):
+            self.force[:] = field
+
+    rbc = O.rbc_celltype(par)
+    cells = U.deformed_cells(rbc, [(11.0, 10.0, 15.0)], 2, amp=0.0, stretch=(1.04, 0.98, 0.98))
+    sim = Sim(dom, fl, par.f_limit)
+    sim.vel_timescale = 2
+    sim.add_celltype(rbc, 4); sim.add_cells(0, cells, [0])
+    ctx = U.gpu_context(dom, fl)
+    ctx.set_force_limit(par.f_limit)
+    ctx.set_body_force_field(field)
+    t = U.gpu_add_type(ctx, rbc)
+    ctx.add_cells(t, cells, [0])
+    ctx.set_timescales(2, 1, 1); ctx.set_material_timescale(t, 4)
+    U.assert_close(ctx.lattice_download(H.LAT_FORCE), field, "force field after upload", rtol=0, floor=0)
+    for _ in range(9):
+        sim.iterate()
+    ctx.iterate(9)
+    U.assert_close(ctx.lattice_download(H.LAT_FORCE), field, "node force reset to the field", rtol=0, floor=0)
+    U.assert_close(ctx.lattice_download(H.LAT_POP), sim.pop, "populations", rtol=1e-10, floor=1e-12)
+    U.assert_close(ctx.cells_download(H.P_POS), sim.pos, "positions", rtol=1e-13)
+    ctx.set_body_force((1e-6, 0.0, 0.0))                                   # back to a uniform force
+    assert np.all(ctx.lattice_download(H.LAT_FORCE).reshape(3, N)[0] == 1e-6)
+    ctx.close()
