@@ -211,3 +211,29 @@ def test_reference_case_smoke(tmp_path, name):
         if "Velocity" in h.datasets and os.path.basename(f).startswith("Fluid"):
             assert np.isfinite(h["Velocity"]).all()
     assert checked > 0 or name == "simple", "no particle output found"      # examples/simple never calls loadParticles()
+
+
+def test_reference_oneCellShear_long_run_observables(tmp_path):
+    """north_star long-run check: the reference's unmodified oneCellShear for its full 100 000 iterations on the GPU;
+    bounding-box diameters, largest diameter, volume, area and the deformation index of examples/oneCellShear's
+    stretch.log agree with the oracle's golden trace within 1 % at every one of the 50 measurement points"""
+    env = _refcase(tmp_path, "oneCellShear", ["config.xml", "RBC.xml", "RBC.pos"])
+    cfg = (tmp_path / "config.xml").read_text()
+    cfg = re.sub(r"<tcheckpoint>.*?</tcheckpoint>", "<tcheckpoint> 1000000 </tcheckpoint>", cfg)
+    (tmp_path / "config.xml").write_text(cfg)
+    env["HEMOCELL_H5_DEFLATE"] = "1"
+    r = subprocess.run([str(tmp_path / "oneCellShear"), "config.xml"], cwd=tmp_path, capture_output=True, text=True, timeout=1500, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    got = np.loadtxt(tmp_path / "stretch.log").reshape(-1, 8)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "shear_oracle.json")))["trace"]
+    assert got.shape[0] == len(gold) == 50
+    worst = 0.0
+    for g, o in zip(got, gold):
+        assert int(g[0]) == o["iter"]
+        ref = np.array(o["diam_um"] + [o["volume_pct"], o["area_pct"], o["largest_diam_um"]])
+        rel = np.abs(g[1:7] - ref) / np.abs(ref)
+        worst = max(worst, rel.max())
+        assert rel.max() < 0.01, (o["iter"], g[1:7], ref)
+        # the deformation index is a small difference of diameters: 1 % of its final value as absolute tolerance
+        assert abs(g[7] - o["deformation_index_pct"]) < 0.01 * max(abs(gold[-1]["deformation_index_pct"]), 1e-9) + 1e-3, (o["iter"], g[7], o["deformation_index_pct"])
+    print(f"oneCellShear 100k steps: worst relative deviation from the oracle trace {worst:.2e}")
