@@ -642,7 +642,7 @@ void HemoCell::saveCheckPoint() {
   hcg_ctx* c = ctx();
   GpuLattice* g = lattice->gpu();
   const std::string dir = plb::global::directories().getOutputDir() + "/checkpoint/";
-  if (plb::global::mpi().isMainProcessor()) mkpath(dir);
+  mkpath(dir);
   plb::global::mpi().barrier();
   const std::string base = dir + "rank" + std::to_string(plb::global::mpi().getRank());
   // keep the previous checkpoint as .old (core/hemoCellFields.cpp:240-262)
@@ -961,8 +961,8 @@ void HemoCell::writeOutput() {
   cellfields->separate_force_vectors();
   cellfields->applyConstitutiveModel(true);
   const std::string out = plb::global::directories().getOutputDir();
-  if (plb::global::mpi().isMainProcessor()) { mkpath(out + "/hdf5/" + zeroPadNumber(iter)); mkpath(out + "/csv"); }
-  plb::global::mpi().barrier();
+  // every rank creates the (shared) directories itself: ranks only meet inside the device exchanges, not on the host
+  mkpath(out + "/hdf5/" + zeroPadNumber(iter)); mkpath(out + "/csv");
   // HDF5 particle files per cell type and the fluid file of this rank's block (io/ParticleHdf5IO.cpp, io/FluidHdf5IO.hh)
   for (unsigned i = 0; i < cellfields->size(); i++) write_particle_h5(*this, *(*cellfields)[i]);
   write_fluid_h5(*this);

@@ -245,3 +245,39 @@ def test_two_gpu_repulsion_matches_single_gpu(transport):
             U.assert_close(pos[slot], ref_pos[k], f"rank {r} cell {cid} positions", rtol=1e-11, floor=1e-12)
             U.assert_close(frep[slot], ref_frep[k], f"rank {r} cell {cid} repulsion forces", rtol=1e-9, floor=1e-14 * np.abs(ref_frep).max())
     assert len(seen) == alive_ref
+
+
+@pytest.mark.skipif(_device_count() < 2, reason="needs 2 GPUs")
+def test_facade_two_ranks_case_file(tmp_path):
+    """the C++ API surface with two ranks (one process per GPU, RANK / WORLD_SIZE / LOCAL_RANK from the launcher as
+    under torchrun or mpirun): examples/shear_cell with the cell straddling the slab face reproduces the single-lattice
+    oracle trace, and each rank writes its own block's HDF5 files"""
+    import os, subprocess
+    import facade_cases as F
+    from test_gpu_facade import _oracle_shear
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "shear_cell", "shear_cell")
+    assert os.path.exists(exe)
+    rows = [(9.9, 9.5, 4.5, 70, 20, 0)]                       # centre at x = 19.8 lu: on the face between the two 20-plane slabs
+    F.write_shear_case(tmp_path, tmax=200, tmeas=100, rows=rows, material_every=1, particle_every=1)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_PORT="29533",
+                   HEMOCELL_RENDEZVOUS_DIR=str(tmp_path), HEMOCELL_H5_DEFLATE="1")
+        procs.append(subprocess.Popen([exe, "config.xml"], cwd=tmp_path, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n----\n".join(o[-2000:] for o in outs)
+    got = np.loadtxt(tmp_path / "shear.log").reshape(-1, 8)
+    ref = _oracle_shear(200, 100, rows, 1, 1)
+    assert got.shape[0] == len(ref) == 2
+    for g, o in zip(got, ref):
+        assert int(g[0]) == o["iter"]
+        U.assert_close(g[1:4], o["diam"], f"bounding-box diameters at {o['iter']} (2 ranks)", rtol=1e-9)
+    import h5mini
+    it = "%012d" % 200
+    n = 0
+    for r in range(2):
+        f = h5mini.File(tmp_path / "tmp" / "hdf5" / it / f"Fluid.{it}.p.{r}.h5")
+        assert f["Velocity"].shape == (22, 42, 22, 3) and f.attrs["processorId"][0] == r
+        n += h5mini.File(tmp_path / "tmp" / "hdf5" / it / f"RBC.{it}.p.{r}.h5")["Position"].shape[0]
+    assert n == 642                                          # the shared cell is written by exactly one rank
