@@ -60,6 +60,28 @@ def body_force(nu_lbm, n):
     return (f, f, f)
 
 
+def cube_setup(H, par):
+    """examples/cube (BASELINE.json configs[1]): 100^3 nodes (50 um), x periodic, bounce-back planes at y = 0 / ny-1,
+    regularized moving walls at z = 0 / nz-1 (shear rate 1 /s as in the config template), tau = 1, RBCs + PLTs at
+    ~30 % hematocrit from a seeded lattice packing (the reference seeds with the irreproducible tools/packCells)."""
+    n = 100
+    fl = np.zeros((n, n, n), dtype=np.uint8)
+    fl[:, :, 0] = H.VEL_ZN; fl[:, :, n - 1] = H.VEL_ZP
+    fl[:, 0, :] = H.BOUNCEBACK; fl[:, n - 1, :] = H.BOUNCEBACK
+    vhalf = (n - 1) * 1.0 * par["dt"] * 0.5
+    bc = np.zeros((6, 3)); bc[4] = (vhalf, 0, 0); bc[5] = (-vhalf, 0, 0)
+    rng = np.random.default_rng(4321)
+    ix, iy, iz = np.meshgrid(np.arange(5), np.arange(5), np.arange(14), indexing="ij")
+    ctr = np.stack([(ix + 0.5) * n / 5, 8.0 + (iy + 0.5) * (n - 16.0) / 5, 4.0 + (iz + 0.5) * (n - 8.0) / 14], -1).reshape(-1, 3)
+    ctr = ctr + rng.uniform(-0.2, 0.2, ctr.shape)
+    rbc_rows = np.zeros((ctr.shape[0], 6)); rbc_rows[:, 0:3] = ctr * (DX / 1e-6); rbc_rows[:, 3] = 90.0
+    # platelets in the gaps between RBC columns (x, y offset by half a pitch)
+    jx, jy, jz = np.meshgrid(np.arange(3), np.arange(3), np.arange(3), indexing="ij")
+    pc = np.stack([(jx + 1.0) * n / 5, 8.0 + (jy + 1.0) * (n - 16.0) / 5, 15.0 + jz * 30.0], -1).reshape(-1, 3)
+    plt_rows = np.zeros((pc.shape[0], 6)); plt_rows[:, 0:3] = pc * (DX / 1e-6)
+    return n, fl, bc, rbc_rows, plt_rows
+
+
 # ----------------------------------------------------------------------------- helpers
 def pinned_empty(n_doubles):
     """page-locked host buffer through cudart (the C ABI takes plain host pointers)"""
@@ -277,6 +299,68 @@ def run_cuda(args):
     return line
 
 
+def run_cube(args):
+    """extra line (not the default): examples/cube on one GPU.  A 10^6-node lattice is launch- and latency-bound on a
+    B200, so this line says little about the kernels; it is here because BASELINE.json lists the configuration."""
+    from hemocell_b200 import lib as H
+    par = H.parameters(DX, -1.0)
+    n, fl, bc, rbc_rows, plt_rows = cube_setup(H, par)
+    rbc = H.HostCellType(H.MODEL_RBC, H.RBC_FROM_SPHERE, par, H.RBC_MATERIAL)
+    plt = H.HostCellType(H.MODEL_PLT, H.ELLIPSOID_FROM_SPHERE, par, H.PLT_MATERIAL, H.PLT_INNER_EDGES)
+    ctx = H.Context(n, n, n, (1, 0, 0), par["tau"], device=args.local_rank)
+    ctx.set_flags(fl.reshape(-1))
+    for o in range(6):
+        ctx.set_bc_velocity(o, bc[o])
+    ctx.set_force_limit(par["f_limit"])
+    t0_, t1_ = rbc.add_to(ctx), plt.add_to(ctx)
+    rc, rid = rbc.place(rbc_rows, DX, (n, n, n), fl.reshape(-1))
+    pc, pid = plt.place(plt_rows, DX, (n, n, n), fl.reshape(-1), cell_id0=len(rbc_rows))
+    ctx.add_cells(t0_, rc, rid); ctx.add_cells(t1_, pc, pid)
+    ctx.set_timescales(5, 1, 1); ctx.set_material_timescale(t0_, 20); ctx.set_material_timescale(t1_, 20)
+    ctx.iterate(args.warmup)
+    launches0 = ctx.launch_count()
+    ctx.timers_enable(True); ctx.timers_reset()
+    sampler = ClockSampler(args.local_rank)
+    ctx.synchronize(); t0 = time.time()
+    ms = ctx.iterate_timed(args.steps)
+    ctx.synchronize(); t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    launches = ctx.launch_count() - launches0
+    timers = ctx.timers(); ctx.timers_enable(False)
+    ncell = ctx.count()[0]
+    npart = ctx.capacity()[1]
+    host = pinned_empty(3 * npart); out_pos = pinned_empty(3 * npart)
+    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), host.ctypes.data_as(H.c_dp))
+    ctx.synchronize(); te0 = time.time()
+    ctx.cells_upload(H.P_POS, host)
+    for _ in range(args.steps):
+        ctx.iterate(1); ctx.count()
+    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), out_pos.ctypes.data_as(H.c_dp))
+    ctx.synchronize(); e2e_ms = (time.time() - te0) * 1e3
+    nodes = n ** 3
+    peak, peak_src = measured_peak()
+    gen = timers.get("kernel:k_collide_stream", (0.0, 0)); t1k = timers.get("kernel:k_collide_tau1", (0.0, 0))
+    k_ms = (gen[0] + t1k[0]) / max(gen[1] + t1k[1], 1)
+    bytes_lu = (B_LU * gen[1] + B_LU_TAU1 * t1k[1]) / max(gen[1] + t1k[1], 1)
+    ach = bytes_lu * nodes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    line = {"metric": METRIC, "value": nodes * args.steps / (ms * 1e-3) / 1e6, "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "cell_steps_per_s": ncell * args.steps / (ms * 1e-3),
+            "config": {"workload": f"examples/cube: {n}^3 D3Q19 fp64, x periodic, bounce-back y planes, moving z walls, tau=1, "
+                                   f"{len(rid)} RBC + {len(pid)} PLT (seeded packing), material every 20, velocity every 5",
+                       "lattice": [n, n, n], "cells": int(ncell), "lsp": int(npart), "velocity_cadence": 5, "material_cadence": 20,
+                       "l2": "the 0.3 GB of populations exceed the 126 MB L2; no flush"},
+            "roofline": {"bound": "hbm", "kernel": "k_collide_stream / k_collide_tau1 (mix of the launches timed)", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_lu": bytes_lu, "launch_ms": k_ms, "launches_timed": gen[1] + t1k[1]},
+            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()},
+            "e2e": {"value": nodes * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 8 * 3 * npart / args.steps,
+                    "d2h_bytes_per_step": 8 * 3 * npart / args.steps + 16, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "clocks": clocks}
+    ctx.close()
+    return line
+
+
 # ----------------------------------------------------------------------------- CPU arm
 def run_cpu(steps, warmup, cadence, budget_s=150.0):
     """The reference cannot be built (Palabos/MPI/HDF5 absent): time the CPU oracle (a port) with
@@ -328,6 +412,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--cadence", type=int, default=1, help="velocity interpolation every n steps (stepParticleEvery)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="performance_testing", choices=["performance_testing", "cube"],
+                    help="performance_testing = the weak-scaling unit the metric is quoted on (default); cube = examples/cube, 1 GPU")
     args = ap.parse_args()
     args.rank = int(os.environ.get("RANK", "0"))
     args.world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -346,6 +432,10 @@ def main():
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
+        return
+    if args.workload == "cube":
+        if args.rank == 0:
+            print(json.dumps(run_cube(args)), flush=True)
         return
     line = run_cuda(args)
     if args.rank != 0:

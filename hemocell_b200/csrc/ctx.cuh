@@ -94,6 +94,7 @@ struct hcg_ctx {
   // lattice
   double *g[2]; int cur;       // double-buffered pre-streamed populations
   double *F, *U, *rho;         // node force, interpolation velocity (+ density scratch)
+  bool f_clean = false;         // the node force holds exactly the reset value (body / F0) everywhere: re-applying it is free
   double* F0 = nullptr;         // optional per-node driving force the node force is reset to (AoS [n][4]); null = uniform body[3]
   double* W = nullptr; bool w_valid = false;   // tau = 1 fast path: raw moments (rhoBar, j) of the current populations, AoS [n][4]
   uint8_t* flags;

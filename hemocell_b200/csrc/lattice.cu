@@ -1016,6 +1016,7 @@ hcg_status lat_collide_moments_overlapped(hcg_ctx* c, bool* done_out) {
 }
 
 hcg_status lat_reset_force(hcg_ctx* c) {
+  c->f_clean = true;
   if (c->F0) { CUDA_TRY(c, cudaMemcpyAsync(c->F, c->F0, sizeof(double)*4*c->S, cudaMemcpyDeviceToDevice, c->stream)); return HCG_OK; }
   k_fill4<<<nblk(c->S, 256), 256, 0, c->stream>>>(c->F, c->S, c->body[0], c->body[1], c->body[2]);
   KERNEL_CHECK(c);
