@@ -283,6 +283,23 @@ hcg_status hcg_comm_init(hcg_ctx* c, const void* id128) {
   c->nccl = comm;
   if (const char* e = getenv("HCG_TRANSPORT")) c->peer.transport = (strcmp(e, "nccl") == 0) ? 0 : 1;
   hcg_status s = peer_setup(c); if (s) return s;
+  if (c->peer.transport == 1) {
+    // every rank must use the same transport: fall back to NCCL send/recv everywhere if any rank cannot map its neighbours
+    int* d_ok = nullptr;
+    CUDA_TRY(c, cudaMalloc(&d_ok, sizeof(int)));
+    const int mine = c->peer.ready ? 1 : 0;
+    CUDA_TRY(c, cudaMemcpyAsync(d_ok, &mine, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    rc = ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, c->stream);
+    if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(rc));
+    int all = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&all, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_ok);
+    if (!all) {
+      if (c->dom.rank == 0) fprintf(stderr, "(hemocell_gpu) peer-memory transport unavailable on this box: using NCCL send/recv\n");
+      c->peer.ready = false; c->peer.transport = 0;
+    }
+  }
   s = exchange_flags(c); if (s) return s;
   if ((s = refresh_nonfluid(c))) return s;
   const double u0[3] = {0, 0, 0};

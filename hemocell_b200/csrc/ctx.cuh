@@ -71,6 +71,7 @@ struct PeerMap { unsigned char handle[64]; void* base; };
 struct PeerState {
   int transport = 1;               // 1 = peer memory (default), 0 = NCCL send/recv
   bool ready = false;
+  bool usable = true;              // false: this rank could not export / map peer memory (see peer_setup)
   PeerLink link[2];                // left, right
   unsigned long long* flags = nullptr;   // my flag words: [0] written by the left neighbour, [1] by the right
   unsigned long long epoch = 0, sync_count = 0;

@@ -404,6 +404,7 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
   if (c->peer.transport == 1) {
     if ((s = peer_reserve_sync(c, 2*((size_t)m.face[0].n + 3*(size_t)m.face[0].total), 2*((size_t)m.face[1].n + 3*(size_t)m.face[1].total), nullptr))) return s;
     if ((s = peer_setup(c))) return s;
+    if (!c->peer.ready) return hcg_fail(c, HCG_ERR_STATE, "peer transport: re-mapping the neighbours' buffers failed after a rebalance");
   }
   return HCG_OK;
 }

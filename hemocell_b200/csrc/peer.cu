@@ -13,6 +13,7 @@
 // the host-coordinated migration every `sync_every` steps).
 #include "ctx.cuh"
 #include <cstring>
+#include <cstdlib>
 #include <unistd.h>
 
 namespace {
@@ -125,11 +126,16 @@ hcg_status peer_setup(hcg_ctx* c) {
   PeerBlob mine; memset(&mine, 0, sizeof(mine));
   mine.pid = (int32_t)getpid(); mine.device = c->dom.device; mine.rank = r; mine.host = host_tag();
   void* ptrs[HCG_PEER_NPTR] = {c->g[0], c->g[1], c->U, p.flags, p.sync_recv[0], p.sync_recv[1]};
+  // Failures that only mean "no peer memory on this box" (IPC disabled in the container, no P2P path, neighbour on
+  // another host) must not leave the neighbours hanging in the collective below: they are recorded in p.usable and
+  // hcg_comm_init lets all ranks agree on a transport afterwards.
+  p.usable = true;
+  if (const char* e = getenv("HCG_PEER_SIMULATE_FAILURE")) if (atoi(e) == r + 1) p.usable = false;   // test hook: rank e-1 cannot use peer memory
   for (int k = 0; k < HCG_PEER_NPTR; k++) {
     if (!ptrs[k]) continue;
     mine.raw[k] = (uint64_t)ptrs[k]; mine.valid[k] = 1;
     cudaIpcMemHandle_t h;
-    CUDA_TRY(c, cudaIpcGetMemHandle(&h, ptrs[k]));
+    if (cudaIpcGetMemHandle(&h, ptrs[k]) != cudaSuccess) { cudaGetLastError(); p.usable = false; mine.valid[k] = 0; continue; }
     memcpy(mine.handle[k], &h, 64);
   }
   // blobs travel through device memory (NCCL): [mine][from right][from left]
@@ -145,11 +151,13 @@ hcg_status peer_setup(hcg_ctx* c) {
   for (int f = 0; f < 2; f++) {
     if (p.link[f].rank < 0) { for (auto& q : p.link[f].ptr) q = nullptr; continue; }
     if (got[f].rank != p.link[f].rank) return hcg_fail(c, HCG_ERR_STATE, "peer transport: neighbour blob from an unexpected rank");
-    if (got[f].host != mine.host) return hcg_fail(c, HCG_ERR_STATE, "peer transport: neighbour is on another host (select the NCCL transport)");
-    for (int k = 0; k < HCG_PEER_NPTR; k++)
-      if ((s = map_pointer(c, got[f], k, &p.link[f].ptr[k]))) return s;
+    if (got[f].host != mine.host) { p.usable = false; continue; }
+    for (int k = 0; k < HCG_PEER_NPTR; k++) {
+      if (ptrs[k] && !got[f].valid[k]) { p.usable = false; continue; }
+      if (map_pointer(c, got[f], k, &p.link[f].ptr[k]) != HCG_OK) { cudaGetLastError(); p.usable = false; }
+    }
   }
-  p.ready = true;
+  p.ready = p.usable;
   return HCG_OK;
 }
 

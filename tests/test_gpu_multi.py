@@ -281,3 +281,12 @@ def test_facade_two_ranks_case_file(tmp_path):
         assert f["Velocity"].shape == (22, 42, 22, 3) and f.attrs["processorId"][0] == r
         n += h5mini.File(tmp_path / "tmp" / "hdf5" / it / f"RBC.{it}.p.{r}.h5")["Position"].shape[0]
     assert n == 642                                          # the shared cell is written by exactly one rank
+
+
+def test_peer_transport_falls_back_to_nccl_when_a_rank_cannot_map(monkeypatch):
+    """a box without peer memory between two neighbours (simulated on rank 1): every rank agrees on the NCCL
+    transport in hcg_comm_init instead of hanging or failing, and the run still matches the single-GPU one"""
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("HCG_PEER_SIMULATE_FAILURE", "2")
+    test_two_gpu_matches_single_gpu(1, 1)
