@@ -174,6 +174,9 @@ k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, doub
   }
 }
 
+#ifndef TAU1_MINB
+#define TAU1_MINB 4
+#endif
 // tau = 1 fast path.  With omega = 1 the BGK collision forgets the incoming populations: the post-collision
 // state of a fluid node is f*_q = feq_q(rhoBar, j + rho F/2) + Guo_q(u, F), a function of the node's four raw
 // moments and its force alone.  When the moments pass of the previous step kept (rhoBar, j) in W (it pulls the
@@ -203,7 +206,7 @@ __device__ __forceinline__ void guo_collide_tau1(double f[19], double rhoBar, co
 }
 
 template <bool RESET, bool VELBC, bool PEER>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, TAU1_MINB)
 k_collide_tau1(const double* __restrict__ gin, double* __restrict__ gout, double* __restrict__ F,
                const double* __restrict__ W, const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count,
                double* __restrict__ peerL, double* __restrict__ peerR) {
@@ -893,7 +896,10 @@ hcg_status lat_collide_rows(hcg_ctx* c, bool reset_force, int row0, int row1, cu
     else { if (reset_force) K1_LAUNCH(true, false); else K1_LAUNCH(false, false); }
 #undef K1_LAUNCH
   } else {
-#define K1_LAUNCH(R, V) k_collide_stream<R, V, 2, false><<<nb, 256, 0, st>>>(gin, gout, c->F, c->flags, a, first, n, nullptr, nullptr)
+    static int minb = -1;
+    if (minb < 0) { const char* e = getenv("HCG_K1_MINB"); minb = e ? atoi(e) : 2; }
+#define K1_LAUNCH(R, V) do { if (minb == 3) k_collide_stream<R, V, 3, false><<<nb, 256, 0, st>>>(gin, gout, c->F, c->flags, a, first, n, nullptr, nullptr); \
+      else k_collide_stream<R, V, 2, false><<<nb, 256, 0, st>>>(gin, gout, c->F, c->flags, a, first, n, nullptr, nullptr); } while (0)
     if (c->has_velbc) { if (reset_force) K1_LAUNCH(true, true); else K1_LAUNCH(false, true); }
     else { if (reset_force) K1_LAUNCH(true, false); else K1_LAUNCH(false, false); }
 #undef K1_LAUNCH
