@@ -6,6 +6,7 @@
 #include "hemo_mesh.h"          // hemo::host:: set-up code (before hemocell.h: its enum names are macros there)
 #include "hemo_xml.h"
 #include "hemo_h5.h"
+#include "hemo_voxel.h"
 #include "hemocell.h"
 
 #include <algorithm>
@@ -246,6 +247,32 @@ void Parameters::lbm_base_parameters(Config& cfg) {
   if (cfg["domain"]["dt"].read<T>() < 0.0) hlog << "(HemoCell) dt is set to *auto*. Tau will be set to 1!" << std::endl;
   dt = p.dt; dx = p.dx; nu_p = p.nu_p; rho_p = p.rho_p; kBT_p = p.kBT_p; tau = p.tau; nu_lbm = p.nu_lbm;
   dm = p.dm; df = p.df; f_limit = p.f_limit; kBT_lbm = p.kBT_lbm;
+}
+void Parameters::lbm_pipe_parameters(Config& cfg, plb::MultiScalarField3D<int>* sf) {
+  // mechanics/constantConversion.cpp:61-73: radius of the circle with the fluid area of the first x slice
+  lbm_base_parameters(cfg);
+  re = cfg["domain"]["Re"].read<T>();
+  plb::Box3D d = sf->getBoundingBox(); d.x1 = d.x0;
+  const T fluidArea = plb::computeSum<int>(*sf, d);
+  pcout << fluidArea << endl;
+  pipe_radius = std::sqrt(fluidArea/PI);
+  hlog << "(Parameters) The channel has a calculated radius of " << pipe_radius << " LU, assuming a perfect circle cross-section." << endl;
+  u_lbm_max = re*nu_lbm/(pipe_radius*2);
+}
+void getFlagMatrixFromSTL(std::string meshFileName, plb::plint extendedEnvelopeWidth, plb::plint refDirLength, plb::plint refDir,
+                          plb::VoxelizedDomain3D<T>*& voxelizedDomain, plb::MultiScalarField3D<int>*& flagMatrix, plb::plint blockSize, int particleEnvelope) {
+  (void)blockSize; (void)particleEnvelope;            // one x-slab per GPU rank: no sparse block structure to tune
+  host::VoxelizedSTL v;
+  try { v = host::voxelizeSTL(meshFileName, (int)refDirLength, (int)refDir); }
+  catch (std::exception& e) { hlog << e.what() << endl; exit(1); }
+  voxelizedDomain = new plb::VoxelizedDomain3D<T>(v.nx, v.ny, v.nz, extendedEnvelopeWidth);
+  flagMatrix = new plb::MultiScalarField3D<int>(v.nx, v.ny, v.nz, 0);
+  for (int x = 0; x < v.nx; x++) for (int y = 0; y < v.ny; y++) for (int z = 0; z < v.nz; z++) {
+    const int f = v.flag[(size_t)z + (size_t)v.nz*((size_t)y + (size_t)v.ny*x)];
+    flagMatrix->get(x, y, z) = f; voxelizedDomain->getVoxelMatrix().get(x, y, z) = f ? 3 : 1;   // voxelFlag::inside / outside
+  }
+  hlog << "(main) Voxelisation is done. Resulting domain parameters are: " << endl;
+  hlog << "Size of the multi-block:     " << v.nx << "-by-" << v.ny << "-by-" << v.nz << endl;
 }
 void Parameters::lbm_pipe_parameters(Config& cfg, int nY) {
   lbm_base_parameters(cfg);
@@ -948,6 +975,28 @@ void write_fluid_h5(HemoCell& h) {
 }
 }  // namespace
 
+// io/writeCellInfoCSV.cpp:47-70
+void writeCellInfo_CSV(HemoCell& hemocell) {
+  HemoCell* self = &hemocell;
+  const std::string out = plb::global::directories().getOutputDir();
+  mkpath(out + "/csv");
+  CellInformationFunctionals::calculateCellInformation(self);
+  if (plb::global::mpi().getSize() == 1) {
+    std::vector<std::ofstream> csv(self->cellfields->size());
+    for (unsigned i = 0; i < self->cellfields->size(); i++) {
+      csv[i].open(out + "/csv/" + (*self->cellfields)[i]->name + "." + zeroPadNumber(self->iter) + ".csv", std::ofstream::trunc);
+      csv[i] << "X,Y,Z,area,volume,atomic_block,cellId,baseCellId,velocity_x,velocity_y,velocity_z" << endl;
+    }
+    for (auto& pr : CellInformationFunctionals::info_per_cell) {
+      CellInformation ci = pr.second;
+      if (self->outputInSiUnits) { ci.position *= param::dx; ci.area *= param::dx*param::dx; ci.velocity *= param::dx/param::dt; ci.volume *= param::dx*param::dx*param::dx; }
+      auto& o = csv[ci.cellType];
+      o << ci.position[0] << "," << ci.position[1] << "," << ci.position[2] << "," << ci.area << "," << ci.volume << "," << ci.blockId << ","
+        << pr.first << "," << ci.base_cell_id << "," << ci.velocity[0] << "," << ci.velocity[1] << "," << ci.velocity[2] << endl;
+    }
+  }
+}
+
 void HemoCell::writeOutput() {
   const double el = global.statistics.elapsed();
   const std::string tpi = (iter != lastOutputAt) ? Profiler::toString((el - lastOutput)/(iter - lastOutputAt)) : "0.00";
@@ -966,22 +1015,7 @@ void HemoCell::writeOutput() {
   // HDF5 particle files per cell type and the fluid file of this rank's block (io/ParticleHdf5IO.cpp, io/FluidHdf5IO.hh)
   for (unsigned i = 0; i < cellfields->size(); i++) write_particle_h5(*this, *(*cellfields)[i]);
   write_fluid_h5(*this);
-  // CSV cell info (io/writeCellInfoCSV.cpp:47-70)
-  CellInformationFunctionals::calculateCellInformation(this);
-  if (plb::global::mpi().getSize() == 1) {
-    std::vector<std::ofstream> csv(cellfields->size());
-    for (unsigned i = 0; i < cellfields->size(); i++) {
-      csv[i].open(out + "/csv/" + (*cellfields)[i]->name + "." + zeroPadNumber(iter) + ".csv", std::ofstream::trunc);
-      csv[i] << "X,Y,Z,area,volume,atomic_block,cellId,baseCellId,velocity_x,velocity_y,velocity_z" << endl;
-    }
-    for (auto& pr : CellInformationFunctionals::info_per_cell) {
-      CellInformation ci = pr.second;
-      if (outputInSiUnits) { ci.position *= param::dx; ci.area *= param::dx*param::dx; ci.velocity *= param::dx/param::dt; ci.volume *= param::dx*param::dx*param::dx; }
-      auto& o = csv[ci.cellType];
-      o << ci.position[0] << "," << ci.position[1] << "," << ci.position[2] << "," << ci.area << "," << ci.volume << "," << ci.blockId << ","
-        << pr.first << "," << ci.base_cell_id << "," << ci.velocity[0] << "," << ci.velocity[1] << "," << ci.velocity[2] << endl;
-    }
-  }
+  writeCellInfo_CSV(*this);
   cellfields->unify_force_vectors();
   (void)c;
 }

@@ -2,6 +2,7 @@
 #include "hemocell_host.h"
 #include "hemo_mesh.h"
 #include "hemo_h5.h"
+#include "hemo_voxel.h"
 #include <cstring>
 #include <exception>
 #include <string>
@@ -68,6 +69,21 @@ int64_t hch_place_cells(const hch_celltype* h, const double* rows6, int64_t n_ro
     memcpy(out_pos, out.data(), out.size()*sizeof(double));
     memcpy(out_ids, ids.data(), ids.size()*sizeof(int64_t));
     return (int64_t)ids.size();
+  } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+int32_t hch_voxelize_stl(const char* path, int32_t ref_dir_n, int32_t ref_dir, int32_t* dims_out, uint8_t* flags,
+                         int64_t cap, double* dx_out) {
+  if (!path || !dims_out) { g_err = "null argument"; return -1; }
+  try {
+    hemo::host::VoxelizedSTL v = hemo::host::voxelizeSTL(path, ref_dir_n, ref_dir);
+    dims_out[0] = v.nx; dims_out[1] = v.ny; dims_out[2] = v.nz;
+    if (dx_out) *dx_out = v.dx;
+    if (flags) {
+      if (cap < (int64_t)v.flag.size()) { g_err = "flags buffer too small"; return -1; }
+      for (size_t i = 0; i < v.flag.size(); i++) flags[i] = v.flag[i] ? HCG_FLUID : HCG_BOUNCEBACK;
+    }
+    return 0;
   } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 

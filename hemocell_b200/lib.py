@@ -328,7 +328,7 @@ class Context:
 # ------------------------------------------------------------------ host-side set-up (C++ in the same .so)
 HOST_SYMBOLS = """hch_parameters hch_celltype_build hch_celltype_view hch_celltype_vertices hch_celltype_scalar
 hch_celltype_free hch_read_pos hch_place_cells hch_slab_membership hch_last_error
-hch_h5_create hch_h5_attribute hch_h5_dataset hch_h5_close""".split()
+hch_h5_create hch_h5_attribute hch_h5_dataset hch_h5_close hch_voxelize_stl""".split()
 
 RBC_MATERIAL = dict(kBend=80.0, kVolume=20.0, kArea=5.0, kLink=15.0, eta_m=0.0, minNumTriangles=600,
                     radius=3.91e-6, aspectRatio=0.3)
@@ -478,3 +478,18 @@ class H5Writer:
         self.h = None
         if rc:
             raise HcgError("hch_h5_close: " + self.L.hch_last_error().decode())
+
+
+def voxelize_stl(path, ref_dir_n, ref_dir):
+    """hch_voxelize_stl -> (flags [nx, ny, nz] uint8, dx in STL units per lattice unit)"""
+    L = load()
+    L.hch_last_error.restype = C.c_char_p
+    dims = (C.c_int32 * 3)()
+    dx = C.c_double()
+    if L.hch_voxelize_stl(str(path).encode(), C.c_int32(ref_dir_n), C.c_int32(ref_dir), dims, None, C.c_int64(0), C.byref(dx)):
+        raise HcgError("hch_voxelize_stl: " + L.hch_last_error().decode())
+    n = dims[0] * dims[1] * dims[2]
+    fl = np.empty(n, dtype=np.uint8)
+    if L.hch_voxelize_stl(str(path).encode(), C.c_int32(ref_dir_n), C.c_int32(ref_dir), dims, fl.ctypes.data_as(c_u8p), C.c_int64(n), C.byref(dx)):
+        raise HcgError("hch_voxelize_stl: " + L.hch_last_error().decode())
+    return fl.reshape(dims[0], dims[1], dims[2]), dx.value

@@ -221,6 +221,35 @@ class MultiBlockLattice3D {
   PeriodicitySwitch3D per;
 };
 
+/* MultiScalarField3D<int>: the flag matrix of helper/voxelizeDomain.cpp (1 = fluid, 0 = solid), one global block */
+template <typename U>
+class MultiScalarField3D {
+ public:
+  MultiScalarField3D(plint nx_, plint ny_, plint nz_, U v = U()) : nx(nx_), ny(ny_), nz(nz_), data((size_t)nx_*ny_*nz_, v) {}
+  Box3D getBoundingBox() const { return Box3D(0, nx - 1, 0, ny - 1, 0, nz - 1); }
+  plint getNx() const { return nx; } plint getNy() const { return ny; } plint getNz() const { return nz; }
+  U& get(plint x, plint y, plint z) { return data[(size_t)z + (size_t)nz*((size_t)y + (size_t)ny*x)]; }
+  const U& get(plint x, plint y, plint z) const { return data[(size_t)z + (size_t)nz*((size_t)y + (size_t)ny*x)]; }
+ private:
+  plint nx, ny, nz; std::vector<U> data;
+};
+template <typename U>
+U computeSum(MultiScalarField3D<U>& f, Box3D d) {
+  U s = U();
+  for (plint x = d.x0; x <= d.x1; x++) for (plint y = d.y0; y <= d.y1; y++) for (plint z = d.z0; z <= d.z1; z++) s += f.get(x, y, z);
+  return s;
+}
+/* VoxelizedDomain3D<T>: only what the case files touch (the lattice size and the voxel matrix) */
+template <typename U>
+class VoxelizedDomain3D {
+ public:
+  VoxelizedDomain3D(plint nx, plint ny, plint nz, plint envelope) : mgmt(nx, ny, nz, envelope), voxels(nx, ny, nz, 0) {}
+  MultiBlockManagement3D const& getMultiBlockManagement() const { return mgmt; }
+  MultiScalarField3D<int>& getVoxelMatrix() { return voxels; }
+ private:
+  MultiBlockManagement3D mgmt; MultiScalarField3D<int> voxels;
+};
+
 namespace boundary { enum BcType { dirichlet, neumann, freeslip, density, outflow, normalOutflow }; }
 template <typename U, template <typename V> class Descriptor>
 class OnLatticeBoundaryCondition3D {
@@ -257,6 +286,19 @@ template <typename U, template <typename V> class Descriptor>
 void defineDynamics(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, DomainFunctional3D* functional, Dynamics<U, Descriptor>* dynamics) {
   hemo::gpu_lattice_define_flag(lattice.gpu(), domain, functional, dynamics->nodeFlag());
   delete dynamics; delete functional;
+}
+/* defineDynamics(lattice, flagMatrix, domain, dynamics, whichFlag): nodes whose flag equals whichFlag (examples/pipeflow/pipeflow.cpp:73) */
+struct FlagMatrixDomain : public DomainFunctional3D {
+  const MultiScalarField3D<int>& f; int which;
+  FlagMatrixDomain(const MultiScalarField3D<int>& f_, int w) : f(f_), which(w) {}
+  bool operator()(plint x, plint y, plint z) const override { return f.get(x, y, z) == which; }
+  DomainFunctional3D* clone() const override { return new FlagMatrixDomain(f, which); }
+};
+template <typename U, template <typename V> class Descriptor>
+void defineDynamics(MultiBlockLattice3D<U, Descriptor>& lattice, MultiScalarField3D<int>& flagMatrix, Box3D domain, Dynamics<U, Descriptor>* dynamics, int whichFlag) {
+  FlagMatrixDomain fun(flagMatrix, whichFlag);
+  hemo::gpu_lattice_define_flag(lattice.gpu(), domain, &fun, dynamics->nodeFlag());
+  delete dynamics;
 }
 template <typename U, template <typename V> class Descriptor>
 void initializeAtEquilibrium(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, U rho, Array<U, 3> velocity) {
@@ -429,10 +471,22 @@ class Parameters {
  public:
   static void lbm_base_parameters(Config& cfg);
   static void lbm_pipe_parameters(Config& cfg, int nY);
+  static void lbm_pipe_parameters(Config& cfg, plb::MultiScalarField3D<int>* flagMatrix);   /* radius from the fluid area of the x0 slice */
   static void lbm_shear_parameters(Config& cfg, T nx);
   static void printParameters();
   static T dt, dx, dm, df, nu_p, rho_p, tau, re, nu_lbm, u_lbm_max, pipe_radius, kBT_p, kBT_lbm, shearrate_lbm, f_limit;
 };
+
+/* ---- helper/voxelizeDomain.h: STL geometry -> flag matrix (1 = fluid, 0 = solid) + the lattice size ------------------ */
+void getFlagMatrixFromSTL(std::string meshFileName, plb::plint extendedEnvelopeWidth, plb::plint refDirLength, plb::plint refDir,
+                          plb::VoxelizedDomain3D<T>*& voxelizedDomain, plb::MultiScalarField3D<int>*& flagMatrix, plb::plint blockSize, int particleEnvelope = 0);
+template <class PtrVD, class PtrFM>   /* std::auto_ptr / std::unique_ptr overload of the case files */
+void getFlagMatrixFromSTL(std::string meshFileName, plb::plint extendedEnvelopeWidth, plb::plint refDirLength, plb::plint refDir,
+                          PtrVD& voxelizedDomain, PtrFM& flagMatrix, plb::plint blockSize, int particleEnvelope = 0) {
+  plb::VoxelizedDomain3D<T>* vd = nullptr; plb::MultiScalarField3D<int>* fm = nullptr;
+  getFlagMatrixFromSTL(meshFileName, extendedEnvelopeWidth, refDirLength, refDir, vd, fm, blockSize, particleEnvelope);
+  voxelizedDomain = PtrVD(vd); flagMatrix = PtrFM(fm);
+}
 
 /* ---- core/hemoCellParticle.h (host view of one Lagrangian surface point; see HemoCellFields::getParticles) */
 class HemoCellParticle {
@@ -506,7 +560,7 @@ class HemoCellField {
   int numVertex = 0;
   T volume = 0, volumeFractionOfLspPerNode = 0;
   unsigned int timescale = 1;
-  T minimumDistanceFromSolid = 0;
+  unsigned int minimumDistanceFromSolid = 0;        /* [um]; an unsigned int in the reference too (core/hemoCellField.h:64): 0.5 um truncates to 0 */
   bool outputTriangles = false;
   vector<hemo::Array<plint, 3>> triangle_list;
   CellMechanics* mechanics = nullptr;
@@ -649,6 +703,7 @@ class HemoCellStretch {
   static unsigned int n_forced_lsps;
   static T external_force, scale;
 };
+void writeCellInfo_CSV(HemoCell& hemocell);         /* io/writeCellInfoCSV.h */
 struct FluidStatistics { T min = 0, max = 0, avg = 0; pluint ncells = 0; };
 class FluidInfo {
  public:

@@ -47,6 +47,12 @@ int64_t hch_place_cells(const hch_celltype*, const double* rows6, int64_t n_rows
 void hch_slab_membership(int64_t n, const double* xlo, const double* xhi, int32_t nx, int32_t periodic_x,
                          int32_t nxl, int32_t rank, int32_t n_ranks, double margin,
                          uint8_t* held, uint8_t* share_left, uint8_t* share_right);
+/* STL voxeliser behind hemo::getFlagMatrixFromSTL (helper/voxelizeDomain.cpp:63-158; Palabos TriangleSet ->
+ * DEFscaledMesh -> VoxelizedDomain3D in the reference).  dims_out[3] = lattice size; flags (may be NULL to query the
+ * size) receives HCG_FLUID / HCG_BOUNCEBACK per node, index z + nz*(y + ny*x); dx_out = STL units per lattice unit.
+ * Returns 0, or -1 on error. */
+int32_t hch_voxelize_stl(const char* path, int32_t ref_dir_n, int32_t ref_dir, int32_t* dims_out, uint8_t* flags,
+                         int64_t flags_capacity, double* dx_out);
 /* HDF5 container writer behind HemoCell::writeOutput (replaces the H5Fcreate / H5LTset_attribute_* /
  * H5Dcreate2 + H5Dwrite calls of io/ParticleHdf5IO.cpp:60-194 and io/FluidHdf5IO.hh:36-49).
  * type: 0 = float32, 1 = float64, 2 = int32, 3 = int64.  deflate_level < 0 writes contiguous datasets;

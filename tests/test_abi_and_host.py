@@ -106,3 +106,25 @@ def test_host_placement_matches_oracle(tmp_path):
         pos_o, ids_o = M.place_cells(ct.verts, rows, 0.5e-6, dims, fl.reshape(-1), md, cell_id0=7)
         assert ids_h.tolist() == ids_o.tolist() and len(ids_h) > 0
         np.testing.assert_allclose(pos_h, pos_o, rtol=0, atol=1e-12)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (authoring container only)")
+def test_voxeliser_and_placement_reproduce_the_references_42_cells():
+    """known answer from the reference's own validation test (tests/validation/pipeflow/test_pipeflow.cpp:88-92):
+    after voxelising examples/pipeflow/tube.stl at refDirN 50 and placing the shipped RBC / PLT position files,
+    exactly 42 cells survive.  Pins the voxeliser conventions (dx = extent / refDirN, margin 1, N + 1 nodes) and the
+    placement filter, including the reference's quirk that the 0.5 um minimum wall distance is stored in an
+    unsigned int and therefore is 0 (core/hemoCellField.h:64)."""
+    from hemocell_b200 import lib as H
+    fl, dx = H.voxelize_stl("/root/reference/examples/pipeflow/tube.stl", 50, 1)
+    assert fl.shape == (103, 53, 53) and abs(dx - 0.2) < 1e-12
+    area = int((fl[0] == 0).sum())
+    assert area == int((fl[50] == 0).sum()) and abs(np.sqrt(area / np.pi) - 24.9) < 0.1     # open ends, radius ~ 25 lu
+    par = H.parameters(0.5e-6, 1e-7)
+    rbc = H.HostCellType(H.MODEL_RBC, H.RBC_FROM_SPHERE, par, H.RBC_MATERIAL)
+    plt = H.HostCellType(H.MODEL_PLT, H.ELLIPSOID_FROM_SPHERE, par, H.PLT_MATERIAL, H.PLT_INNER_EDGES)
+    d = "/root/reference/tests/validation/pipeflow"
+    rr, pr = H.read_pos(d + "/RBC.pos"), H.read_pos(d + "/PLT.pos")
+    _, rid = rbc.place(rr, 0.5e-6, fl.shape, fl.reshape(-1), min_dist_um=float(int(0.5)))
+    _, pid = plt.place(pr, 0.5e-6, fl.shape, fl.reshape(-1), min_dist_um=0.0, cell_id0=len(rr))
+    assert len(rid) + len(pid) == 42, (len(rid), len(pid))

@@ -63,7 +63,8 @@ def test_example_fails_loudly_without_device(tmp_path):
     "examples/parallelplanes/parallelplanes.cpp", "examples/flowaroundsphere/flowaroundsphere.cpp",
     "examples/microcontraction/microcontraction.cpp", "examples/capillary/wedge.cpp", "cases/atherosclerosis/atherosclerosis.cpp",
     "cases/cellCollision/cellCollision.cpp", "cases/kolmogorovFlow/kolmogorovFlow.cpp", "cases/microvessel_bended/microvessel_bended.cpp",
-    "cases/stentflow/stentflow.cpp", "cases/unbounded/unbounded.cpp", "cases/vasoconstriction_pipe/vasoconstriction_pipe.cpp"])
+    "cases/stentflow/stentflow.cpp", "cases/unbounded/unbounded.cpp", "cases/vasoconstriction_pipe/vasoconstriction_pipe.cpp",
+    "examples/pipeflow/pipeflow.cpp", "examples/parachuting/parachuting.cpp"])
 def test_reference_case_files_compile_unmodified(case):
     """drop-in check: the reference's own case files compile against include/hemocell.h as they are"""
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", f"-I{ROOT}/include", f"-I{ROOT}/include/compat", os.path.join(REF, case)],

@@ -237,3 +237,33 @@ def test_reference_oneCellShear_long_run_observables(tmp_path):
         # the deformation index is a small difference of diameters: 1 % of its final value as absolute tolerance
         assert abs(g[7] - o["deformation_index_pct"]) < 0.01 * max(abs(gold[-1]["deformation_index_pct"]), 1e-9) + 1e-3, (o["iter"], g[7], o["deformation_index_pct"])
     print(f"oneCellShear 100k steps: worst relative deviation from the oracle trace {worst:.2e}")
+
+
+def test_reference_pipeflow_unmodified_binary_validation_bounds(tmp_path):
+    """BASELINE configs[2]: the REFERENCE's examples/pipeflow/pipeflow.cpp compiled unmodified (STL voxeliser, flag
+    matrix, pipe parameters from the fluid area), run with the settings of the reference's own validation test
+    (tests/validation/pipeflow/test_pipeflow.cpp: 100 warm-up steps, material / velocity cadence 2, 1000 iterations)
+    and held to that test's known answers: 42 cells survive placement in the voxelised tube, relative apparent
+    viscosity in (1.03, 3.0) and mean particle force < 4 pN from iteration 100 on"""
+    env = _refcase(tmp_path, "pipeflow", ["config.xml", "RBC.xml", "PLT.xml", "RBC.pos", "PLT.pos", "tube.stl"])
+    cfg = (tmp_path / "config.xml").read_text()
+    for key, val in (("tmax", 1000), ("tmeas", 100), ("tcsv", 100000), ("tcheckpoint", 100000), ("warmup", 100),
+                     ("stepMaterialEvery", 2), ("stepParticleEvery", 2)):
+        cfg = re.sub(rf"<{key}>.*?</{key}>", f"<{key}> {val} </{key}>", cfg)
+    (tmp_path / "config.xml").write_text(cfg)
+    env["HEMOCELL_H5_DEFLATE"] = "1"
+    r = subprocess.run([str(tmp_path / "pipeflow"), "config.xml"], cwd=tmp_path, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = r.stdout
+    logs = list((tmp_path / "tmp").glob("**/log*")) + list((tmp_path / "tmp" / "log").glob("*"))
+    for f in logs:
+        if f.is_file():
+            out += f.read_text(errors="ignore")
+    cells = [int(x) for x in re.findall(r"# of cells: (\d+)", out)]
+    visc = [float(x) for x in re.findall(r"rel\. app\. viscosity: (\S+)", out)]
+    force = [float(x) for x in re.findall(r"pN \(\S+ lf\), mean: (\S+) pN", out)]
+    assert len(cells) >= 10 and len(visc) >= 10 and len(force) >= 10, out[-3000:]
+    assert all(c == 42 for c in cells), cells                      # test_pipeflow.cpp:92
+    assert all(1.03 < v < 3.0 for v in visc), visc                 # :101-102
+    assert all(f < 4.0 for f in force), force                      # :106
+    print("pipeflow validation: cells", cells[-1], "rel. apparent viscosity", visc, "mean force pN", force[-1])
