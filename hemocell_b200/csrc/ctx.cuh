@@ -122,6 +122,7 @@ struct hcg_ctx {
   int spread_mode; bool perm_valid; int perm_every;   // 1 = node-sorted pairs + warp reduction, 0 = plain atomics
   // execution
   cudaStream_t stream, stream_halo;
+  cudaStream_t stream_lo = nullptr;   // low-priority stream: bulk work that overlaps the exchange chain of the main stream
   cudaEvent_t ev_a, ev_b;
   void* nccl;                  // ncclComm_t
   MultiState multi;
@@ -190,6 +191,8 @@ hcg_status ibm_advance(hcg_ctx* c);
 hcg_status ibm_interpolate_advance(hcg_ctx* c);
 hcg_status ibm_interpolate_advance_unshared(hcg_ctx* c);   // multi-GPU: interpolate all, advance the cells no neighbour holds
 hcg_status ibm_advance_shared(hcg_ctx* c);                 // ... and the shared ones after the velocity sync
+hcg_status ibm_interpolate_shared(hcg_ctx* c);             // overlap variant: shared cells only (main stream)
+hcg_status ibm_interpolate_advance_unshared_on(hcg_ctx* c, cudaStream_t st);   // ... unshared cells only, on a second stream
 // mechanics.cu
 hcg_status mech_apply(hcg_ctx* c, int ctype, bool components);
 hcg_status mech_bbox(hcg_ctx* c, double* out_dev);

@@ -120,62 +120,70 @@ __device__ __forceinline__ void ld_node4(const double* p, double& a, double& b, 
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
+// interpolation of one vertex: the 8 corners fully unrolled (registers only, no local-memory arrays), raw weights in
+// the reference's x-outer / z-inner order, zero for corners outside the kernel, the domain or (CHECK_FLAGS) on
+// non-fluid nodes.  Returns false when a candidate node is not addressable from this rank (velocity left alone).
+template <bool CHECK_FLAGS>
+__device__ __forceinline__ bool interp_vertex(const IbmArgs& a, const uint8_t* __restrict__ flags, const double* __restrict__ U,
+                                              double px, double py, double pz, double& v0, double& v1, double& v2) {
+  const int bx = (int)floor(px), by = (int)floor(py), bz = (int)floor(pz);
+  double ax[2], ay[2], az[2]; int64_t jx[2]; int jy[2], jz[2];
+  bool addressable = true;
+#pragma unroll
+  for (int d = 0; d < 2; d++) {
+    ax[d] = phi2(px - (double)(bx + d)); jx[d] = 0;
+    if (ax[d] != 0.0) {
+      int lx; bool out;
+      if (local_x(bx + d, a, lx, out)) jx[d] = (int64_t)lx*a.P;
+      else { ax[d] = 0.0; if (!out) addressable = false; }
+    }
+    ay[d] = phi2(py - (double)(by + d)); int yy = by + d;
+    if (ay[d] != 0.0 && !wrap_yz(yy, a.ny, a.py)) ay[d] = 0.0;
+    jy[d] = yy*a.nz;
+    az[d] = phi2(pz - (double)(bz + d)); int zz = bz + d;
+    if (az[d] != 0.0 && !wrap_yz(zz, a.nz, a.pz)) az[d] = 0.0;
+    jz[d] = zz;
+  }
+  if (!addressable) return false;
+  double w[8]; double total = 0.0;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
+    w[c] = ax[dx]*ay[dy]*az[dz];
+    if (w[c] == 0.0) continue;
+    if (CHECK_FLAGS && flags[jx[dx] + jy[dy] + jz[dz]] != HCG_FLUID) { w[c] = 0.0; continue; }
+    total += w[c];
+  }
+  const double coeff = 1.0/total;
+  v0 = v1 = v2 = 0.0;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    if (w[c] == 0.0) continue;
+    const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
+    const double wn = w[c]*coeff;
+    double u0, u1, u2;
+    ld_node4(U + 4*(jx[dx] + jy[dy] + jz[dz]), u0, u1, u2);
+    v0 += u0*wn; v1 += u1*wn; v2 += u2*wn;
+  }
+  return true;
+}
+
 template <bool ADVANCE, bool INTERP, bool CHECK_FLAGS>
 __global__ void __launch_bounds__(256)
 k_interp_advance(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __restrict__ p_cell,
                  uint8_t* alive, double* x, double* y, double* z,
                  double* vx, double* vy, double* vz, const double* __restrict__ U,
-                 const uint8_t* __restrict__ hold_back) {
+                 const uint8_t* __restrict__ hold_back, int skip_held) {
   const int64_t p = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (p >= a.np) return;
   const int cell = p_cell[p];
   if (!alive[cell]) return;
+  if (skip_held && hold_back[cell]) return;       // shared cells are interpolated by k_interp_list on the main stream
   double px = x[p], py = y[p], pz = z[p];
   double v0, v1, v2;
   if (INTERP) {
-    // the 8 corners fully unrolled (registers only, no local-memory arrays): raw weights in the reference's
-    // x-outer / z-inner order, zero for corners outside the kernel, the domain or (CHECK_FLAGS) on non-fluid nodes
-    const int bx = (int)floor(px), by = (int)floor(py), bz = (int)floor(pz);
-    double ax[2], ay[2], az[2]; int64_t jx[2]; int jy[2], jz[2];
-    bool addressable = true;
-#pragma unroll
-    for (int d = 0; d < 2; d++) {
-      ax[d] = phi2(px - (double)(bx + d)); jx[d] = 0;
-      if (ax[d] != 0.0) {
-        int lx; bool out;
-        if (local_x(bx + d, a, lx, out)) jx[d] = (int64_t)lx*a.P;
-        else { ax[d] = 0.0; if (!out) addressable = false; }
-      }
-      ay[d] = phi2(py - (double)(by + d)); int yy = by + d;
-      if (ay[d] != 0.0 && !wrap_yz(yy, a.ny, a.py)) ay[d] = 0.0;
-      jy[d] = yy*a.nz;
-      az[d] = phi2(pz - (double)(bz + d)); int zz = bz + d;
-      if (az[d] != 0.0 && !wrap_yz(zz, a.nz, a.pz)) az[d] = 0.0;
-      jz[d] = zz;
-    }
-    if (addressable) {
-      double w[8]; double total = 0.0;
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
-        w[c] = ax[dx]*ay[dy]*az[dz];
-        if (w[c] == 0.0) continue;
-        if (CHECK_FLAGS && flags[jx[dx] + jy[dy] + jz[dz]] != HCG_FLUID) { w[c] = 0.0; continue; }
-        total += w[c];
-      }
-      const double coeff = 1.0/total;
-      v0 = v1 = v2 = 0.0;
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        if (w[c] == 0.0) continue;
-        const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
-        const double wn = w[c]*coeff;
-        double u0, u1, u2;
-        ld_node4(U + 4*(jx[dx] + jy[dy] + jz[dz]), u0, u1, u2);
-        v0 += u0*wn; v1 += u1*wn; v2 += u2*wn;
-      }
-      vx[p] = v0; vy[p] = v1; vz[p] = v2;
-    } else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
+    if (interp_vertex<CHECK_FLAGS>(a, flags, U, px, py, pz, v0, v1, v2)) { vx[p] = v0; vy[p] = v1; vz[p] = v2; }
+    else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
   } else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
   if (ADVANCE && !(hold_back && hold_back[cell])) {
     px += v0; py += v1; pz += v2;
@@ -211,6 +219,28 @@ k_advance_list(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __re
   }
 }
 
+
+// interpolation of the cells on a list (one CTA per cell): the shared cells of the multi-GPU run, ahead of the
+// velocity exchange, while the unshared majority is interpolated and advanced on a second stream
+template <bool CHECK_FLAGS>
+__global__ void __launch_bounds__(256)
+k_interp_list(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __restrict__ cells, const int64_t* __restrict__ off,
+              int n, const int64_t* __restrict__ cell_base, const uint8_t* __restrict__ alive,
+              const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+              double* vx, double* vy, double* vz, const double* __restrict__ U) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int cell = cells[i];
+  if (!alive[cell]) return;
+  const int64_t b = cell_base[cell];
+  const int V = (int)(off[i+1] - off[i]);
+  for (int k = threadIdx.x; k < V; k += blockDim.x) {
+    const int64_t p = b + k;
+    double v0, v1, v2;
+    if (interp_vertex<CHECK_FLAGS>(a, flags, U, x[p], y[p], z[p], v0, v1, v2)) { vx[p] = v0; vy[p] = v1; vz[p] = v2; }
+  }
+}
+
 IbmArgs make_args(const hcg_ctx* c) {
   IbmArgs a;
   a.nx = c->dom.nx; a.ny = c->dom.ny; a.nz = c->dom.nz;
@@ -237,9 +267,9 @@ hcg_status ibm_interpolate(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   IbmArgs a = make_args(c);
   if (c->has_nonfluid) k_interp_advance<false, true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0);
   else k_interp_advance<false, true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0);
   KERNEL_CHECK(c);
   return HCG_OK;
 }
@@ -248,7 +278,7 @@ hcg_status ibm_advance(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   IbmArgs a = make_args(c);
   k_interp_advance<true, false, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0);
   KERNEL_CHECK(c);
   return HCG_OK;
 }
@@ -257,9 +287,9 @@ hcg_status ibm_interpolate_advance(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   IbmArgs a = make_args(c);
   if (c->has_nonfluid) k_interp_advance<true, true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0);
   else k_interp_advance<true, true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr);
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0);
   KERNEL_CHECK(c);
   return HCG_OK;
 }
@@ -269,9 +299,34 @@ hcg_status ibm_interpolate_advance_unshared(hcg_ctx* c) {
   if (!c->multi.d_cell_shared) return hcg_fail(c, HCG_ERR_STATE, "shared-cell flags missing (multi_rebalance has not run)");
   IbmArgs a = make_args(c);
   if (c->has_nonfluid) k_interp_advance<true, true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared);
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared, 0);
   else k_interp_advance<true, true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared);
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared, 0);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+
+// multi-GPU overlap: (1) the shared cells on the main stream ...
+hcg_status ibm_interpolate_shared(hcg_ctx* c) {
+  const MultiFace& f = c->multi.all;
+  if (c->np == 0 || f.n == 0) return HCG_OK;
+  IbmArgs a = make_args(c);
+  if (c->has_nonfluid) k_interp_list<true><<<f.n, 256, 0, c->stream>>>(a, c->flags, f.d_cells, f.d_off, f.n, c->cell_base, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U);
+  else k_interp_list<false><<<f.n, 256, 0, c->stream>>>(a, c->flags, f.d_cells, f.d_off, f.n, c->cell_base, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+// ... (2) interpolation + advance of the cells no neighbour holds, on `st`
+hcg_status ibm_interpolate_advance_unshared_on(hcg_ctx* c, cudaStream_t st) {
+  if (c->np == 0) return HCG_OK;
+  if (!c->multi.d_cell_shared) return hcg_fail(c, HCG_ERR_STATE, "shared-cell flags missing (multi_rebalance has not run)");
+  IbmArgs a = make_args(c);
+  if (c->has_nonfluid) k_interp_advance<true, true, true><<<nblk(c->np, 256), 256, 0, st>>>(a, c->flags, c->p_cell, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared, 1);
+  else k_interp_advance<true, true, false><<<nblk(c->np, 256), 256, 0, st>>>(a, c->flags, c->p_cell, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared, 1);
   KERNEL_CHECK(c);
   return HCG_OK;
 }
