@@ -189,10 +189,12 @@ k_interp_advance(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __
     px += v0; py += v1; pz += v2;
     x[p] = px; y[p] = py; z[p] = pz;
     // particle on a boundary node => its cell is deleted (hemoCellParticleField.cpp:572-584, 512-553)
-    int lx; bool out;
-    int yy = (int)floor(py + 0.5), zz = (int)floor(pz + 0.5);
-    if (local_x((int)floor(px + 0.5), a, lx, out) && wrap_yz(yy, a.ny, a.py) && wrap_yz(zz, a.nz, a.pz)) {
-      if (flags[(int64_t)zz + (int64_t)a.nz*((int64_t)yy + (int64_t)a.ny*lx)] != HCG_FLUID) alive[cell] = 0;
+    if (CHECK_FLAGS) {                             // without non-fluid nodes no particle can land on one
+      int lx; bool out;
+      int yy = (int)floor(py + 0.5), zz = (int)floor(pz + 0.5);
+      if (local_x((int)floor(px + 0.5), a, lx, out) && wrap_yz(yy, a.ny, a.py) && wrap_yz(zz, a.nz, a.pz)) {
+        if (flags[(int64_t)zz + (int64_t)a.nz*((int64_t)yy + (int64_t)a.ny*lx)] != HCG_FLUID) alive[cell] = 0;
+      }
     }
   }
 }
@@ -277,7 +279,9 @@ hcg_status ibm_interpolate(hcg_ctx* c) {
 hcg_status ibm_advance(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   IbmArgs a = make_args(c);
-  k_interp_advance<true, false, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+  if (c->has_nonfluid) k_interp_advance<true, false, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
+      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0);
+  else k_interp_advance<true, false, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
       c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0);
   KERNEL_CHECK(c);
   return HCG_OK;
