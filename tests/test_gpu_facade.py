@@ -188,6 +188,17 @@ def test_reference_case_smoke(tmp_path, name):
     for f in os.listdir(src):
         shutil.copy(os.path.join(src, f), tmp_path / f)
     cfgname = "config_1.xml" if name == "performance_testing" else "config.xml"
+    if name == "cube" and (tmp_path / "config-template.xml").exists():
+        # examples/cube ships a config template (filled in by its pre-processing scripts) and no cell positions (they
+        # come from tools/packCells): 100^3 nodes at dx = 0.5 um as BASELINE.json names it, the bench's seeded packing
+        import bench
+        t = (tmp_path / "config-template.xml").read_text()
+        for k, v in (("shear-rate", 100), ("dx", 0.5e-6), ("nx", 100), ("ny", 100), ("nz", 100), ("tmax", 40), ("tmeas", 20)):
+            t = t.replace("{{%s}}" % k, str(v))
+        (tmp_path / "config.xml").write_text(t)
+        from hemocell_b200 import lib as H
+        rows = bench.cube_setup(H, H.parameters(0.5e-6, -1.0))[3]
+        (tmp_path / "RBC.pos").write_text(f"{len(rows)}\n" + "".join(" ".join("%.6f" % v for v in r) + "\n" for r in rows))
     if not (tmp_path / cfgname).exists():
         pytest.skip(f"{name}: the reference ships no {cfgname} (its config is generated by a pre-processing script)")
     cfg = (tmp_path / cfgname).read_text()
