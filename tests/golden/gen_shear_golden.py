@@ -4,9 +4,9 @@
 with the CPU ORACLE.  Recorded every `tmeas` steps, as the reference's stretch.log does
 (examples/oneCellShear/oneCellShear.cpp:147-161): bounding-box diameters, volume %, area %, largest
 diameter and the deformation index  DI = (D^2 - 1)/(D^2 + 1) * 100, D = D_max / (2 * 3.91 um).
-usage: tools/gen_shear_golden.py [iterations] [tmeas]"""
+usage: tests/golden/gen_shear_golden.py [iterations] [tmeas]"""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np

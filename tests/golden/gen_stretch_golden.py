@@ -3,9 +3,9 @@
 (tests/validation/stretch_cell/test_stretch_cell.cpp) run with the CPU ORACLE.
 One RBC in a closed 52x26x26 box with u = 0 regularized walls, 7 forced vertices per side,
 10 000 iterations (about 3 minutes per force on one core).
-usage: tools/gen_stretch_golden.py [iterations]"""
+usage: tests/golden/gen_stretch_golden.py [iterations]"""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import oracle as O

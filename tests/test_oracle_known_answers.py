@@ -193,7 +193,7 @@ def test_placement_rules():
 
 def test_stretch_cell_golden_against_reference_bounds():
     """tests/validation/stretch_cell/test_stretch_cell.cpp:158-162 with the oracle; the 10 000-iteration
-    runs are stored in tests/golden/stretch_oracle.json (tools/gen_stretch_golden.py); here the bounds
+    runs are stored in tests/golden/stretch_oracle.json (tests/golden/gen_stretch_golden.py); here the bounds
     are asserted on the stored values and the first 200 iterations are re-run live"""
     path = os.path.join(HERE, "golden", "stretch_oracle.json")
     g = json.load(open(path))
@@ -205,7 +205,7 @@ def test_stretch_cell_golden_against_reference_bounds():
         assert b["axial"][0] <= last["axial_um"] <= b["axial"][1], run
         assert 0.98 < last["volume_ratio"] <= 1.02
     import importlib.util
-    spec = importlib.util.spec_from_file_location("gen", os.path.join(os.path.dirname(HERE), "tools", "gen_stretch_golden.py"))
+    spec = importlib.util.spec_from_file_location("gen", os.path.join(HERE, "golden", "gen_stretch_golden.py"))
     gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
     live = gen.run(75, 200)
     ref = [r for r in g["runs"] if r["force_pN"] == 75][0]["trace"]["200"]
