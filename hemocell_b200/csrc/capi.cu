@@ -88,6 +88,20 @@ __global__ void k_count_alive(const uint8_t* __restrict__ alive, const int32_t* 
   atomicAdd(out, 1ULL); atomicAdd(out + 1, (unsigned long long)typeV[ctype[i]]);
 }
 
+__global__ void k_cells_owned(const uint8_t* __restrict__ alive, int64_t n, const int64_t* __restrict__ cell_base,
+                              const double* __restrict__ x, int nranks, int nx, int px, int x0, int nxl, uint8_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t o = alive[i] ? 1 : 0;
+  if (o && nranks > 1) {
+    int gx = (int)floor(x[cell_base[i]] + 0.5);
+    if (px) { gx %= nx; if (gx < 0) gx += nx; }
+    int rel = gx - x0; if (px && rel < 0) rel += nx;
+    if (rel < 0 || rel >= nxl) o = 0;
+  }
+  out[i] = o;
+}
+
 hcg_status ensure_staging(hcg_ctx* c, size_t bytes) {
   if (c->staging_bytes >= bytes) return HCG_OK;
   if (c->staging) cudaFree(c->staging);
@@ -209,11 +223,17 @@ extern "C" {
 const char* hcg_last_error(const hcg_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 const char* hcg_version(void) { return "hemocell_b200 0.1 (sm_100a)"; }
 
+void hcg_slab(int32_t nx, int32_t rank, int32_t n_ranks, int32_t* x0_out, int32_t* nxl_out) {
+  const int32_t base = nx / n_ranks, rem = nx % n_ranks;
+  if (x0_out) *x0_out = rank*base + (rank < rem ? rank : rem);
+  if (nxl_out) *nxl_out = base + (rank < rem ? 1 : 0);
+}
+
 hcg_status hcg_create(const hcg_domain* d, hcg_ctx** out) {
   if (!d || !out) return hcg_fail(nullptr, HCG_ERR_ARG, "null argument");
   if (d->nx < 1 || d->ny < 3 || d->nz < 3) return hcg_fail(nullptr, HCG_ERR_ARG, "lattice too small");
-  if (d->n_ranks < 1 || d->rank < 0 || d->rank >= d->n_ranks || d->nx % d->n_ranks)
-    return hcg_fail(nullptr, HCG_ERR_ARG, "bad rank/n_ranks (nx must be divisible by n_ranks)");
+  if (d->n_ranks < 1 || d->rank < 0 || d->rank >= d->n_ranks || d->nx < d->n_ranks)
+    return hcg_fail(nullptr, HCG_ERR_ARG, "bad rank/n_ranks");
   if (!(d->tau > 0.5)) return hcg_fail(nullptr, HCG_ERR_ARG, "tau must be > 0.5");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -221,7 +241,7 @@ hcg_status hcg_create(const hcg_domain* d, hcg_ctx** out) {
   if (d->device < 0 || d->device >= ndev) return hcg_fail(nullptr, HCG_ERR_ARG, "bad device ordinal");
   hcg_ctx* c = new hcg_ctx();
   c->dom = *d;
-  c->nxl = d->nx / d->n_ranks; c->x0 = c->nxl * d->rank;
+  { int32_t x0, nxl; hcg_slab(d->nx, d->rank, d->n_ranks, &x0, &nxl); c->x0 = x0; c->nxl = nxl; }
   if (d->n_ranks > 1 && c->nxl < 3) { delete c; return hcg_fail(nullptr, HCG_ERR_ARG, "slab thinner than 3 planes"); }
   c->P = (int64_t)d->ny * d->nz; c->S = (int64_t)(c->nxl + 2) * c->P; c->Nl = (int64_t)c->nxl * c->P;
   c->omega = 1.0 / d->tau;
@@ -544,7 +564,7 @@ hcg_status hcg_cells_add(hcg_ctx* c, int32_t ctype, int64_t n_cells, const int64
       lo[i] = a; hi[i] = b;
     }
     std::vector<uint8_t> held(n_cells), sl(n_cells), sr(n_cells);
-    hch_slab_membership(n_cells, lo.data(), hi.data(), c->dom.nx, c->dom.periodic[0], c->nxl, c->dom.rank,
+    hch_slab_membership_at(n_cells, lo.data(), hi.data(), c->dom.nx, c->dom.periodic[0], c->x0, c->nxl, c->dom.rank,
                         c->dom.n_ranks, c->multi.margin, held.data(), sl.data(), sr.data());
     for (int64_t i = 0; i < n_cells; i++) if (held[i]) {
       keep_id.push_back(cell_id[i]);
@@ -809,6 +829,34 @@ hcg_status hcg_op_mechanics(hcg_ctx* c, int32_t forced, int32_t components) {
   OP_PROLOGUE; if ((s = do_mechanics(c, forced != 0, components != 0))) return s; OP_EPILOGUE;
 }
 hcg_status hcg_op_zero_force(hcg_ctx* c) { OP_PROLOGUE; if ((s = lat_reset_force(c))) return s; OP_EPILOGUE; }
+
+hcg_status hcg_cells_owned(hcg_ctx* c, uint8_t* owned) {
+  if (!c || !owned) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (c->ncells == 0) return HCG_OK;
+  hcg_status s = ensure_staging(c, (size_t)c->ncells); if (s) return s;
+  k_cells_owned<<<nblk(c->ncells, 256), 256, 0, c->stream>>>(c->cell_alive, c->ncells, c->cell_base, c->pos[0], c->dom.n_ranks,
+      c->dom.nx, c->dom.periodic[0], c->x0, c->nxl, (uint8_t*)c->staging);
+  KERNEL_CHECK(c);
+  CUDA_TRY(c, cudaMemcpyAsync(owned, c->staging, (size_t)c->ncells, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_allreduce(hcg_ctx* c, double* inout, int64_t n, int32_t op) {
+  if (!c || !inout || n < 0 || op < 0 || op > 2) return HCG_ERR_ARG;
+  if (c->dom.n_ranks == 1 || n == 0) return HCG_OK;
+  if (!c->nccl) return hcg_fail(c, HCG_ERR_STATE, "hcg_allreduce: hcg_comm_init first");
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  hcg_status s = ensure_staging(c, sizeof(double)*(size_t)n); if (s) return s;
+  CUDA_TRY(c, cudaMemcpyAsync(c->staging, inout, sizeof(double)*n, cudaMemcpyHostToDevice, c->stream));
+  const ncclRedOp_t ops[3] = {ncclSum, ncclMin, ncclMax};
+  ncclResult_t rc = ncclAllReduce(c->staging, c->staging, (size_t)n, ncclDouble, ops[op], (ncclComm_t)c->nccl, c->stream);
+  if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(rc));
+  CUDA_TRY(c, cudaMemcpyAsync(inout, c->staging, sizeof(double)*n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
 
 hcg_status hcg_cells_bbox(hcg_ctx* c, double* bbox) {
   if (!c || !bbox) return HCG_ERR_ARG;

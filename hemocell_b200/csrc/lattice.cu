@@ -13,6 +13,8 @@ namespace {
 struct LatArgs {
   int nxl, ny, nz, py, pz;
   int64_t P, S;
+  int nxlL;             // planes of the LEFT slab neighbour (uneven decompositions: may differ from nxl by one)
+  int64_t SL, SR;       // padded slab sizes (population stride) of the left / right neighbour
   double omega;
   const double* bc;     // [6][3] wall velocity per orientation, device memory
   double body[3];
@@ -164,12 +166,12 @@ k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, doub
   if (PEER) {
     // my first real plane -> left neighbour's RIGHT ghost (c_x = -1 set); my last -> right neighbour's LEFT ghost (c_x = +1 set)
     if (i < a.P && peerL) {
-      const int64_t off = (int64_t)(a.nxl + 1)*a.P + rem;
-      peerL[1*a.S + off] = f[1]; peerL[4*a.S + off] = f[4]; peerL[5*a.S + off] = f[5]; peerL[6*a.S + off] = f[6]; peerL[7*a.S + off] = f[7];
+      const int64_t off = (int64_t)(a.nxlL + 1)*a.P + rem;
+      peerL[1*a.SL + off] = f[1]; peerL[4*a.SL + off] = f[4]; peerL[5*a.SL + off] = f[5]; peerL[6*a.SL + off] = f[6]; peerL[7*a.SL + off] = f[7];
     }
     if (i >= (int64_t)(a.nxl - 1)*a.P && peerR) {
       const int64_t off = rem;
-      peerR[10*a.S + off] = f[10]; peerR[13*a.S + off] = f[13]; peerR[14*a.S + off] = f[14]; peerR[15*a.S + off] = f[15]; peerR[16*a.S + off] = f[16];
+      peerR[10*a.SR + off] = f[10]; peerR[13*a.SR + off] = f[13]; peerR[14*a.SR + off] = f[14]; peerR[15*a.SR + off] = f[15]; peerR[16*a.SR + off] = f[16];
     }
   }
 }
@@ -241,12 +243,12 @@ k_collide_tau1(const double* __restrict__ gin, double* __restrict__ gout, double
   for (int q = 0; q < 19; q++) gout[(int64_t)q*a.S + n] = f[q];
   if (PEER) {
     if (i < a.P && peerL) {
-      const int64_t off = (int64_t)(a.nxl + 1)*a.P + rem;
-      peerL[1*a.S + off] = f[1]; peerL[4*a.S + off] = f[4]; peerL[5*a.S + off] = f[5]; peerL[6*a.S + off] = f[6]; peerL[7*a.S + off] = f[7];
+      const int64_t off = (int64_t)(a.nxlL + 1)*a.P + rem;
+      peerL[1*a.SL + off] = f[1]; peerL[4*a.SL + off] = f[4]; peerL[5*a.SL + off] = f[5]; peerL[6*a.SL + off] = f[6]; peerL[7*a.SL + off] = f[7];
     }
     if (i >= (int64_t)(a.nxl - 1)*a.P && peerR) {
       const int64_t off = rem;
-      peerR[10*a.S + off] = f[10]; peerR[13*a.S + off] = f[13]; peerR[14*a.S + off] = f[14]; peerR[15*a.S + off] = f[15]; peerR[16*a.S + off] = f[16];
+      peerR[10*a.SR + off] = f[10]; peerR[13*a.SR + off] = f[13]; peerR[14*a.SR + off] = f[14]; peerR[15*a.SR + off] = f[15]; peerR[16*a.SR + off] = f[16];
     }
   }
 }
@@ -282,7 +284,7 @@ k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restri
   double2* Uw = reinterpret_cast<double2*>(U + 4*n);
   Uw[0] = make_double2(u0, u1); Uw[1] = make_double2(u2, rho);      // slot 3 carries the density
   if (PEER) {                                                        // node velocity of the face planes -> neighbours' ghost planes
-    if (i < a.P && peerL) { double2* Pw = reinterpret_cast<double2*>(peerL + 4*((int64_t)(a.nxl + 1)*a.P + rem)); Pw[0] = make_double2(u0, u1); Pw[1] = make_double2(u2, rho); }
+    if (i < a.P && peerL) { double2* Pw = reinterpret_cast<double2*>(peerL + 4*((int64_t)(a.nxlL + 1)*a.P + rem)); Pw[0] = make_double2(u0, u1); Pw[1] = make_double2(u2, rho); }
     if (i >= (int64_t)(a.nxl - 1)*a.P && peerR) { double2* Pw = reinterpret_cast<double2*>(peerR + 4*(int64_t)rem); Pw[0] = make_double2(u0, u1); Pw[1] = make_double2(u2, rho); }
   }
   if (RESET) { double2* Fw = reinterpret_cast<double2*>(F + 4*n); Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0); }
@@ -749,6 +751,12 @@ LatArgs make_args(const hcg_ctx* c) {
   LatArgs a;
   a.nxl = c->nxl; a.ny = c->dom.ny; a.nz = c->dom.nz; a.py = c->dom.periodic[1]; a.pz = c->dom.periodic[2];
   a.P = c->P; a.S = c->S; a.omega = c->omega;
+  {
+    const int R = c->dom.n_ranks, r = c->dom.rank;
+    int32_t x0, nl, nr;
+    hcg_slab(c->dom.nx, (r + R - 1) % R, R, &x0, &nl); hcg_slab(c->dom.nx, (r + 1) % R, R, &x0, &nr);
+    a.nxlL = nl; a.SL = (int64_t)(nl + 2)*c->P; a.SR = (int64_t)(nr + 2)*c->P;
+  }
   a.bc = c->d_bc;
   for (int k = 0; k < 3; k++) a.body[k] = c->body[k];
   return a;

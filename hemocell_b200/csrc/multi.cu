@@ -164,10 +164,10 @@ hcg_status multi_neighbour_exchange(hcg_ctx* c, const void* sendL, size_t nsL, c
 }
 
 // pure host logic, exported for CPU tests (include/hemocell_host.h)
-extern "C" void hch_slab_membership(int64_t n, const double* xlo, const double* xhi, int32_t nx, int32_t periodic_x,
-                                    int32_t nxl, int32_t rank, int32_t n_ranks, double margin,
-                                    uint8_t* held, uint8_t* share_left, uint8_t* share_right) {
-  const double x0 = (double)nxl*rank, x1 = x0 + nxl;
+extern "C" void hch_slab_membership_at(int64_t n, const double* xlo, const double* xhi, int32_t nx, int32_t periodic_x,
+                                       int32_t x0_, int32_t nxl, int32_t rank, int32_t n_ranks, double margin,
+                                       uint8_t* held, uint8_t* share_left, uint8_t* share_right) {
+  const double x0 = (double)x0_, x1 = x0 + nxl;
   const bool px = periodic_x != 0;
   const bool has_left = n_ranks > 1 && (rank > 0 || px), has_right = n_ranks > 1 && (rank < n_ranks - 1 || px);
   for (int64_t i = 0; i < n; i++) {
@@ -176,6 +176,11 @@ extern "C" void hch_slab_membership(int64_t n, const double* xlo, const double* 
     share_left[i] = h && has_left && band_hit(xlo[i], xhi[i], x0 - margin, x0 + margin, nx, px);
     share_right[i] = h && has_right && band_hit(xlo[i], xhi[i], x1 - margin, x1 + margin, nx, px);
   }
+}
+extern "C" void hch_slab_membership(int64_t n, const double* xlo, const double* xhi, int32_t nx, int32_t periodic_x,
+                                    int32_t nxl, int32_t rank, int32_t n_ranks, double margin,
+                                    uint8_t* held, uint8_t* share_left, uint8_t* share_right) {
+  hch_slab_membership_at(n, xlo, xhi, nx, periodic_x, nxl*rank, nxl, rank, n_ranks, margin, held, share_left, share_right);
 }
 
 hcg_status multi_upload_cell_gid(hcg_ctx* c) {
@@ -276,7 +281,7 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
   std::vector<double> lo(nc), hi(nc);
   for (int64_t i = 0; i < nc; i++) { lo[i] = bbox[6*i]; hi[i] = bbox[6*i+1]; }
   std::vector<uint8_t> held(nc), shl(nc), shr(nc);
-  hch_slab_membership(nc, lo.data(), hi.data(), nx, px, c->nxl, c->dom.rank, c->dom.n_ranks, m.margin,
+  hch_slab_membership_at(nc, lo.data(), hi.data(), nx, px, c->x0, c->nxl, c->dom.rank, c->dom.n_ranks, m.margin,
                       held.data(), shl.data(), shr.data());
   // 2. drops and departures
   std::vector<int32_t> send[2];

@@ -102,7 +102,9 @@ class GpuLattice {
   int64_t idx(int x, int y, int z) const { return (int64_t)z + (int64_t)nz*((int64_t)y + (int64_t)ny*x); }
   int rank() const { return plb::global::mpi().getRank(); }
   int size() const { return plb::global::mpi().getSize(); }
-  int nxl() const { return nx / size(); }
+  // x-slab of this rank (hcg_slab: the first nx % size ranks own one plane more)
+  int nxl() const { int32_t x0, n; hcg_slab(nx, rank(), size(), &x0, &n); return n; }
+  int x0() const { int32_t x0, n; hcg_slab(nx, rank(), size(), &x0, &n); return x0; }
 
   // create the context on first device use; re-create if the periodicity was toggled afterwards
   void materialize() {
@@ -117,7 +119,6 @@ class GpuLattice {
     d.tau = 1.0/omega;
     d.device = plb::global::mpi().getLocalRank();
     d.rank = rank(); d.n_ranks = size();
-    if (nx % d.n_ranks) fatal("(HemoCell) (GPU) the lattice x-size must be divisible by the number of GPU ranks");
     hcg_status s = hcg_create(&d, &ctx);
     if (s != HCG_OK) fatal(std::string("(HemoCell) (GPU) cannot create the device context: ") + hcg_last_error(ctx));
     if (d.n_ranks > 1) {
@@ -128,7 +129,7 @@ class GpuLattice {
     memcpy(created_periodic, periodic, sizeof(periodic));
     generation++;
     const int64_t P = (int64_t)ny*nz;
-    ck(ctx, hcg_lattice_set_flags(ctx, flags.data() + (int64_t)rank()*nxl()*P), "hcg_lattice_set_flags");
+    ck(ctx, hcg_lattice_set_flags(ctx, flags.data() + (int64_t)x0()*P), "hcg_lattice_set_flags");
     for (int o = 0; o < 6; o++) ck(ctx, hcg_lattice_set_bc_velocity(ctx, o, bc[o]), "hcg_lattice_set_bc_velocity");
     flags_dirty = false;
     eq_pending = true; body_pending = true;
@@ -140,7 +141,7 @@ class GpuLattice {
     if (!ctx) return;
     if (flags_dirty) {
       const int64_t P = (int64_t)ny*nz;
-      ck(ctx, hcg_lattice_set_flags(ctx, flags.data() + (int64_t)rank()*nxl()*P), "hcg_lattice_set_flags");
+      ck(ctx, hcg_lattice_set_flags(ctx, flags.data() + (int64_t)x0()*P), "hcg_lattice_set_flags");
       for (int o = 0; o < 6; o++) ck(ctx, hcg_lattice_set_bc_velocity(ctx, o, bc[o]), "hcg_lattice_set_bc_velocity");
       flags_dirty = false;
     }
@@ -149,7 +150,7 @@ class GpuLattice {
       if (bodyfield.empty()) ck(ctx, hcg_lattice_set_body_force(ctx, body), "hcg_lattice_set_body_force");
       else if (bodyfield_dirty || bodyfield_generation != generation) {
         // this rank's slab of the global field, component-major
-        const size_t N = (size_t)nx*ny*nz, Nl = (size_t)nxl()*ny*nz, off = (size_t)rank()*Nl;
+        const size_t N = (size_t)nx*ny*nz, Nl = (size_t)nxl()*ny*nz, off = (size_t)x0()*ny*nz;
         std::vector<double> slab(3*Nl);
         for (int k = 0; k < 3; k++) std::copy(bodyfield.begin() + k*N + off, bodyfield.begin() + k*N + off + Nl, slab.begin() + k*Nl);
         ck(ctx, hcg_lattice_set_body_force_field(ctx, slab.data()), "hcg_lattice_set_body_force_field");
@@ -778,20 +779,15 @@ void write_particle_h5(HemoCell& h, HemoCellField& field) {
   if (nc) ck(c, hcg_cells_info(c, ids.data(), types.data(), alive.data()), "hcg_cells_info");
   { int64_t p = 0; for (int64_t k = 0; k < nc; k++) { base[k] = p; p += (*h.cellfields)[(unsigned)types[k]]->numVertex; } }
   // cells of this type in ascending cell id (the reference walks a std::map keyed by cell id); multi-GPU: a cell
-  // shared by two ranks is written by the one that holds its centre, so every cell appears in exactly one file
+  // shared by two ranks is written by the one that owns it (hcg_cells_owned), so every cell appears in exactly one file
   const int t = field.impl->device_ctype, V = field.numVertex;
   std::vector<double> pos((size_t)3*np);
   if (np) ck(c, hcg_cells_download(c, HCG_P_POS, pos.data()), "download");
-  GpuLattice* g = h.lattice->gpu();
-  const double x_lo = (double)g->rank()*g->nxl() - 0.5, x_hi = x_lo + g->nxl();
+  std::vector<uint8_t> owned(nc, 1);
+  if (nc) ck(c, hcg_cells_owned(c, owned.data()), "hcg_cells_owned");
   std::vector<std::pair<int64_t, int64_t>> order;       // (cell id, slot)
   for (int64_t k = 0; k < nc; k++) {
-    if (!alive[k] || ids[k] < 0 || types[k] != t) continue;
-    if (g->size() > 1) {
-      double cx = 0; for (int v = 0; v < V; v++) cx += pos[3*(base[k] + v)]; cx /= V;
-      cx = std::fmod(std::fmod(cx + 0.5, (double)g->nx) + g->nx, (double)g->nx) - 0.5;
-      if (!(cx >= x_lo && cx < x_hi)) continue;
-    }
+    if (!alive[k] || !owned[k] || ids[k] < 0 || types[k] != t) continue;
     order.push_back({ids[k], k});
   }
   std::sort(order.begin(), order.end());
@@ -867,7 +863,7 @@ void write_fluid_h5(HemoCell& h) {
   h5_common_attrs(w, h);
   // the block of this rank plus an envelope of one node on every side "for paraview" (io/FluidHdf5IO.hh:103-120);
   // datasets are [Nz][Ny][Nx][C]
-  const int nxl = g->nxl(), ny = g->ny, nz = g->nz, x0 = g->rank()*nxl;
+  const int nxl = g->nxl(), ny = g->ny, nz = g->nz, x0 = g->x0();
   const uint64_t Nx = nxl + 2, Ny = ny + 2, Nz = nz + 2, nCells = Nx*Ny*Nz;
   const int32_t ncells = (int32_t)nCells, sub[3] = {(int32_t)Nz, (int32_t)Ny, (int32_t)Nx};
   const bool si = h.outputInSiUnits;
@@ -1025,12 +1021,15 @@ namespace {
 struct CellSnapshot {
   int64_t nc = 0, np = 0;
   std::vector<int64_t> ids, base; std::vector<int32_t> types; std::vector<uint8_t> alive;
+  std::vector<uint8_t> owned;       // multi-rank: cells this rank owns (each cell is owned by exactly one rank)
 };
 CellSnapshot snapshot(HemoCell* h) {
   CellSnapshot s; hcg_ctx* c = h->ctx();
   ck(c, hcg_cells_capacity(c, &s.nc, &s.np), "hcg_cells_capacity");
   s.ids.resize(s.nc); s.types.resize(s.nc); s.alive.resize(s.nc); s.base.resize(s.nc);
   if (s.nc) ck(c, hcg_cells_info(c, s.ids.data(), s.types.data(), s.alive.data()), "hcg_cells_info");
+  s.owned.assign(s.nc, 1);
+  if (s.nc) ck(c, hcg_cells_owned(c, s.owned.data()), "hcg_cells_owned");
   int64_t p = 0;
   for (int64_t k = 0; k < s.nc; k++) { s.base[k] = p; p += (*h->cellfields)[(unsigned)s.types[k]]->numVertex; }
   return s;
@@ -1088,25 +1087,29 @@ void CellInformationFunctionals::calculateCellInformation(HemoCell* h) {
 pluint CellInformationFunctionals::getTotalNumberOfCells(HemoCell* h) {
   int64_t n = 0, p = 0;
   ck(h->ctx(), hcg_cells_count(h->ctx(), &n, &p), "hcg_cells_count");
-  return (pluint)n;
+  double g = (double)n;                                    // every cell is counted by the one rank that owns it
+  ck(h->ctx(), hcg_allreduce(h->ctx(), &g, 1, 0), "hcg_allreduce");
+  return (pluint)(g + 0.5);
 }
 pluint CellInformationFunctionals::getNumberOfCellsFromType(HemoCell* h, std::string type) {
   CellSnapshot s = snapshot(h);
   const int t = (*h->cellfields)[type]->impl->device_ctype;
   pluint n = 0;
-  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0 && s.types[k] == t) n++;
-  return n;
+  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.owned[k] && s.ids[k] >= 0 && s.types[k] == t) n++;
+  double g = (double)n;
+  ck(h->ctx(), hcg_allreduce(h->ctx(), &g, 1, 0), "hcg_allreduce");
+  return (pluint)(g + 0.5);
 }
 // helper/particleInfo.cpp:28-119
 static ParticleStatistics particle_stats(HemoCell* h, bool force) {
   CellSnapshot s = snapshot(h);
   ParticleStatistics r;
-  if (!s.np) return r;
+  if (!s.np && plb::global::mpi().getSize() == 1) return r;
   std::vector<double> a(3*s.np), b;
-  ck(h->ctx(), hcg_cells_download(h->ctx(), force ? HCG_P_FORCE : HCG_P_VEL, a.data()), "download");
-  if (force) { b.resize(3*s.np); ck(h->ctx(), hcg_cells_download(h->ctx(), HCG_P_FREP, b.data()), "download"); }
+  if (s.np) ck(h->ctx(), hcg_cells_download(h->ctx(), force ? HCG_P_FORCE : HCG_P_VEL, a.data()), "download");
+  if (force && s.np) { b.resize(3*s.np); ck(h->ctx(), hcg_cells_download(h->ctx(), HCG_P_FREP, b.data()), "download"); }
   bool first = true; double sum = 0;
-  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0) {
+  for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.owned[k] && s.ids[k] >= 0) {
     const int V = (*h->cellfields)[(unsigned)s.types[k]]->numVertex;
     for (int v = 0; v < V; v++) {
       const int64_t q = 3*(s.base[k] + v);
@@ -1116,6 +1119,13 @@ static ParticleStatistics particle_stats(HemoCell* h, bool force) {
       if (first) { r.min = r.max = m; first = false; }
       r.min = std::min(r.min, m); r.max = std::max(r.max, m); sum += m; r.ncells++;
     }
+  }
+  if (plb::global::mpi().getSize() > 1) {
+    double tot[2] = {sum, (double)r.ncells}, mn = first ? 1e300 : r.min, mx = first ? -1e300 : r.max;
+    ck(h->ctx(), hcg_allreduce(h->ctx(), tot, 2, 0), "hcg_allreduce");
+    ck(h->ctx(), hcg_allreduce(h->ctx(), &mn, 1, 1), "hcg_allreduce");
+    ck(h->ctx(), hcg_allreduce(h->ctx(), &mx, 1, 2), "hcg_allreduce");
+    sum = tot[0]; r.ncells = (pluint)(tot[1] + 0.5); r.min = mn; r.max = mx;
   }
   if (r.ncells) r.avg = sum/r.ncells;
   return r;
@@ -1168,6 +1178,17 @@ void HemoCellStretch::applyForce() {
 FluidStatistics FluidInfo::calculateVelocityStatistics(HemoCell* h) {
   FluidStatistics f;
   ck(h->ctx(), hcg_fluid_velocity_stats(h->ctx(), &f.min, &f.max, &f.avg), "hcg_fluid_velocity_stats");
+  if (plb::global::mpi().getSize() > 1) {
+    // the device statistics cover this rank's slab: weigh the means by the slabs' non-boundary node counts
+    GpuLattice* g = h->lattice->gpu();
+    const int64_t P = (int64_t)g->ny*g->nz; const uint8_t* fl = g->flags.data() + (int64_t)g->x0()*P;
+    double nfluid = 0; for (int64_t i = 0; i < (int64_t)g->nxl()*P; i++) nfluid += fl[i] != HCG_BOUNCEBACK;
+    double sum[2] = {f.avg*nfluid, nfluid}, mn = f.min, mx = f.max;
+    ck(h->ctx(), hcg_allreduce(h->ctx(), sum, 2, 0), "hcg_allreduce");
+    ck(h->ctx(), hcg_allreduce(h->ctx(), &mn, 1, 1), "hcg_allreduce");
+    ck(h->ctx(), hcg_allreduce(h->ctx(), &mx, 1, 2), "hcg_allreduce");
+    f.avg = sum[1] > 0 ? sum[0]/sum[1] : 0; f.min = mn; f.max = mx;
+  }
   return f;
 }
 

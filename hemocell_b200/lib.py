@@ -44,10 +44,10 @@ class HcgTimer(C.Structure):
 
 
 # every symbol include/hemocell_gpu.h declares (tests check that the .so exports all of them)
-SYMBOLS = """hcg_last_error hcg_version hcg_create hcg_destroy hcg_comm_unique_id hcg_comm_init
+SYMBOLS = """hcg_last_error hcg_version hcg_create hcg_slab hcg_destroy hcg_comm_unique_id hcg_comm_init
 hcg_lattice_set_flags hcg_lattice_set_bc_velocity hcg_lattice_init_equilibrium hcg_lattice_set_body_force hcg_lattice_set_body_force_field
 hcg_lattice_upload hcg_lattice_download hcg_celltype_add hcg_cells_add hcg_cells_count hcg_cells_capacity
-hcg_cells_upload hcg_cells_download hcg_cells_info hcg_cells_add_force hcg_celltype_set_stiffness
+hcg_cells_upload hcg_cells_download hcg_cells_info hcg_cells_owned hcg_allreduce hcg_cells_add_force hcg_celltype_set_stiffness
 hcg_set_force_limit hcg_set_timescales hcg_set_material_timescale hcg_set_repulsion hcg_set_wall_repulsion
 hcg_set_spread_mode hcg_set_exchange hcg_set_transport hcg_exchange_stats hcg_set_iteration hcg_get_iteration hcg_iterate hcg_fluid_warmup hcg_op_repulsion hcg_op_wall_repulsion
 hcg_op_spread hcg_op_collide_stream hcg_op_interpolate hcg_op_sync hcg_op_advance hcg_op_mechanics
@@ -94,7 +94,9 @@ class Context:
         if st != 0:
             msg = self.L.hcg_last_error(self.h if self.h else None)
             raise HcgError(f"hcg_create failed ({st}): {msg.decode() if msg else ''}")
-        self.nxl = nx // n_ranks
+        x0, nxl = C.c_int32(), C.c_int32()
+        self.L.hcg_slab(C.c_int32(nx), C.c_int32(rank), C.c_int32(n_ranks), C.byref(x0), C.byref(nxl))
+        self.x0, self.nxl = x0.value, nxl.value
         self.Nl = self.nxl * ny * nz
         self._keep = []
 
@@ -327,7 +329,7 @@ class Context:
 
 # ------------------------------------------------------------------ host-side set-up (C++ in the same .so)
 HOST_SYMBOLS = """hch_parameters hch_celltype_build hch_celltype_view hch_celltype_vertices hch_celltype_scalar
-hch_celltype_free hch_read_pos hch_place_cells hch_slab_membership hch_last_error
+hch_celltype_free hch_read_pos hch_place_cells hch_slab_membership hch_slab_membership_at hch_last_error
 hch_h5_create hch_h5_attribute hch_h5_dataset hch_h5_close hch_voxelize_stl""".split()
 
 RBC_MATERIAL = dict(kBend=80.0, kVolume=20.0, kArea=5.0, kLink=15.0, eta_m=0.0, minNumTriangles=600,

@@ -55,7 +55,8 @@ typedef struct {
   int32_t periodic[3];
   double tau;
   int32_t device;              /* CUDA device ordinal of this context */
-  int32_t rank, n_ranks;       /* slab decomposition along x; nx % n_ranks == 0 */
+  int32_t rank, n_ranks;       /* slab decomposition along x: rank r owns nx/n_ranks planes, the first nx % n_ranks
+                                  ranks one more (hcg_slab) */
 } hcg_domain;
 
 /* CommonCellConstants (mechanics/commonCellConstants.h:39-86) + the k_* of the model
@@ -90,6 +91,8 @@ const char* hcg_version(void);
 
 /* ---- lifetime: HemoCell ctor/dtor + initializeLattice (core/hemoCell.cpp:69-127, 438-583) */
 hcg_status hcg_create(const hcg_domain* d, hcg_ctx** out);
+/* the x-slab of a rank: first plane and number of planes (pure function of nx, rank, n_ranks) */
+void       hcg_slab(int32_t nx, int32_t rank, int32_t n_ranks, int32_t* x0_out, int32_t* nxl_out);
 void       hcg_destroy(hcg_ctx*);
 
 /* ---- multi-GPU plumbing (replaces plb::plbInit/MPI_Init + ParallelBlockCommunicator3D).
@@ -130,6 +133,13 @@ hcg_status hcg_cells_capacity(hcg_ctx*, int64_t* n_cells, int64_t* n_particles);
 hcg_status hcg_cells_upload(hcg_ctx*, int32_t field /*POS|VEL|FORCE|FREP*/, const double* in);
 hcg_status hcg_cells_download(hcg_ctx*, int32_t field, double* out);
 hcg_status hcg_cells_info(hcg_ctx*, int64_t* cell_id_out, int32_t* ctype_out, uint8_t* alive_out);
+/* multi-GPU: 1 for the cell slots this rank OWNS (it holds the nearest node of the cell's vertex 0; replicas held for
+ * the neighbour's sake are 0), so that per-cell output and statistics count every cell once.  All 1 on a single rank. */
+hcg_status hcg_cells_owned(hcg_ctx*, uint8_t* owned_out);
+/* element-wise reduction of a few host doubles over all ranks (the MPI reductions behind the reference's
+ * HemoCellGatheringFunctional, helper/cellInfo.cpp, fluidInfo.cpp, particleInfo.cpp); op: 0 sum, 1 min, 2 max.
+ * Collective; a no-op on a single rank. */
+hcg_status hcg_allreduce(hcg_ctx*, double* inout, int64_t n, int32_t op);
 /* HemoCellStretch::applyForce (helper/hemoCellStretch.cpp:63-78, 102-110): force[lsp] += f */
 hcg_status hcg_cells_add_force(hcg_ctx*, int64_t n, const int64_t* particle_index, const double* f /*[n][3]*/);
 /* stiffness update without re-uploading topology (CellMechanics k_* members) */

@@ -47,6 +47,10 @@ int64_t hch_place_cells(const hch_celltype*, const double* rows6, int64_t n_rows
 void hch_slab_membership(int64_t n, const double* xlo, const double* xhi, int32_t nx, int32_t periodic_x,
                          int32_t nxl, int32_t rank, int32_t n_ranks, double margin,
                          uint8_t* held, uint8_t* share_left, uint8_t* share_right);
+/* the same for a slab given by its first plane x0 and thickness nxl (uneven decompositions, hcg_slab) */
+void hch_slab_membership_at(int64_t n, const double* xlo, const double* xhi, int32_t nx, int32_t periodic_x,
+                            int32_t x0, int32_t nxl, int32_t rank, int32_t n_ranks, double margin,
+                            uint8_t* held, uint8_t* share_left, uint8_t* share_right);
 /* STL voxeliser behind hemo::getFlagMatrixFromSTL (helper/voxelizeDomain.cpp:63-158; Palabos TriangleSet ->
  * DEFscaledMesh -> VoxelizedDomain3D in the reference).  dims_out[3] = lattice size; flags (may be NULL to query the
  * size) receives HCG_FLUID / HCG_BOUNCEBACK per node, index z + nz*(y + ny*x); dx_out = STL units per lattice unit.

@@ -51,9 +51,18 @@ def test_argument_validation():
     d = H.HcgDomain(); d.nx, d.ny, d.nz = 10, 10, 10; d.tau = 0.4; d.n_ranks = 1
     h = C.c_void_p()
     assert L.hcg_create(C.byref(d), C.byref(h)) == -1            # tau <= 0.5
-    d.tau = 1.0; d.n_ranks = 3
-    assert L.hcg_create(C.byref(d), C.byref(h)) == -1            # nx not divisible by n_ranks
-    assert b"divisible" in L.hcg_last_error(None)
+    d.tau = 1.0; d.n_ranks = 3; d.rank = 3
+    assert L.hcg_create(C.byref(d), C.byref(h)) == -1            # rank outside [0, n_ranks)
+    assert b"rank" in L.hcg_last_error(None)
+    # uneven slabs: the first nx % n_ranks ranks own one plane more, the slabs tile [0, nx)
+    for nx, R in ((103, 2), (10, 3), (256, 8), (7, 7)):
+        x_next = 0
+        for r in range(R):
+            x0, nxl = C.c_int32(), C.c_int32()
+            L.hcg_slab(C.c_int32(nx), C.c_int32(r), C.c_int32(R), C.byref(x0), C.byref(nxl))
+            assert x0.value == x_next and nxl.value in (nx // R, nx // R + 1)
+            x_next += nxl.value
+        assert x_next == nx
 
 
 @pytest.mark.parametrize("kind", ["rbc", "plt"])

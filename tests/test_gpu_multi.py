@@ -31,7 +31,6 @@ def _device_count():
 def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, cadence, sync_every, f_limit, transport=1, rep=None):
     from hemocell_b200 import lib as H
     nx, ny, nz = dims
-    nxl = nx // R
     uid = H.Context.unique_id()
     out, err = [None] * R, [None] * R
     fl3 = fl.reshape(nx, ny, nz)
@@ -41,7 +40,7 @@ def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, 
             ctx = H.Context(nx, ny, nz, periodic, tau, device=r, rank=r, n_ranks=R)
             ctx.set_transport(transport)
             ctx.comm_init(uid)
-            ctx.set_flags(np.ascontiguousarray(fl3[r * nxl:(r + 1) * nxl]))
+            ctx.set_flags(np.ascontiguousarray(fl3[ctx.x0:ctx.x0 + ctx.nxl]))       # this rank's slab (hcg_slab)
             for o in range(6):
                 ctx.set_bc_velocity(o, bc[o])
             ctx.set_body_force(body)
@@ -57,7 +56,7 @@ def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, 
                 ctx.set_repulsion(True, rep["k"], rep["cut"]); ctx.set_wall_repulsion(True, rep["kw"], rep["cutw"])
             ctx.iterate(steps)
             cid, _, alive = ctx.cells_info()
-            out[r] = dict(pop=ctx.lattice_download(H.LAT_POP), pos=ctx.cells_download(H.P_POS),
+            out[r] = dict(x0=ctx.x0, nxl=ctx.nxl, pop=ctx.lattice_download(H.LAT_POP), pos=ctx.cells_download(H.P_POS),
                           vel=ctx.cells_download(H.P_VEL), frc=ctx.cells_download(H.P_FORCE), frep=ctx.cells_download(H.P_FREP),
                           ids=cid, alive=alive, count=ctx.count(), stats=ctx.exchange_stats())
             ctx.close()
@@ -76,12 +75,12 @@ def _run_multi(R, dims, periodic, tau, fl, bc, body, ct, cells, ids, u0, steps, 
 # transport 1 = NVLink peer memory (kernels store into the neighbour, flag barrier), 0 = NCCL send/recv
 @pytest.mark.parametrize("transport", [1, 0])
 @pytest.mark.parametrize("cadence", [1, 5])
-def test_two_gpu_matches_single_gpu(cadence, transport):
+def test_two_gpu_matches_single_gpu(cadence, transport, nx_global=96):
     if _device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from hemocell_b200 import lib as H
     R = 2
-    dims = (96, 32, 32)          # nz = 32: also eligible for the opt-in overlapped path
+    dims = (nx_global, 32, 32)   # nz = 32: also eligible for the opt-in overlapped path
     nx, ny, nz = dims
     periodic = (1, 1, 0)
     par = M.Parameters(dx=0.5e-6, dt=0.5e-7)
@@ -115,10 +114,11 @@ def test_two_gpu_matches_single_gpu(cadence, transport):
     assert (ref_pos[:, :, 0].mean(1) - cells[:, :, 0].mean(1)).min() > 3.0
 
     out = _run_multi(R, dims, periodic, par.tau, fl, bc, body, ct, cells, ids, u0, steps, cadence, sync_every, par.f_limit, transport)
-    nxl = nx // R
+    assert sum(o["nxl"] for o in out) == nx and out[0]["x0"] == 0
     for r in range(R):
+        x0, nxl = out[r]["x0"], out[r]["nxl"]
         got = out[r]["pop"].reshape(19, nxl, ny, nz)
-        U.assert_close(got, ref_pop[:, r * nxl:(r + 1) * nxl], f"populations of rank {r}", rtol=1e-9, floor=1e-11)
+        U.assert_close(got, ref_pop[:, x0:x0 + nxl], f"populations of rank {r}", rtol=1e-9, floor=1e-11)
     assert sum(o["count"][0] for o in out) == len(centers)          # every cell counted exactly once
     seen = set()
     for r in range(R):
@@ -290,3 +290,43 @@ def test_peer_transport_falls_back_to_nccl_when_a_rank_cannot_map(monkeypatch):
         pytest.skip("needs 2 GPUs")
     monkeypatch.setenv("HCG_PEER_SIMULATE_FAILURE", "2")
     test_two_gpu_matches_single_gpu(1, 1)
+
+
+@pytest.mark.parametrize("transport", [1, 0])
+def test_two_gpu_uneven_slabs(transport):
+    """nx not divisible by the number of ranks (e.g. the 103 planes of the voxelised examples/pipeflow tube): the
+    first nx % n_ranks ranks own one plane more; the peer stores address the neighbour's own slab layout"""
+    test_two_gpu_matches_single_gpu(1, transport, nx_global=97)
+
+
+def test_reference_pipeflow_decomposition_independence(tmp_path):
+    """second half of the reference's scripts/ci/pipeflow_sanity.sh: the log of the unmodified pipeflow binary must not
+    depend on the number of ranks (there: mpirun -n 4 vs -n 2; here 1 GPU vs 2 GPUs, 103 planes = 52 + 51)"""
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os, re, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "build", "refcases", "pipeflow")
+    if not os.path.exists(os.path.join(src, "pipeflow")):
+        pytest.skip("build/refcases not present (built from /root/reference in the authoring container)")
+    logs = {}
+    for R in (1, 2):
+        d = tmp_path / f"n{R}"; d.mkdir()
+        for f in os.listdir(src):
+            shutil.copy(os.path.join(src, f), d / f)
+        cfg = (d / "ci-config.xml").read_text()
+        for key, val in (("tmax", 300), ("tmeas", 100), ("tcheckpoint", 100000)):
+            cfg = re.sub(rf"<{key}>.*?</{key}>", f"<{key}> {val} </{key}>", cfg)
+        (d / "ci-config.xml").write_text(cfg)
+        procs = []
+        for r in range(R):
+            env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(R), LOCAL_RANK=str(r), MASTER_PORT=str(29540 + R),
+                       HEMOCELL_RENDEZVOUS_DIR=str(d), HEMOCELL_H5_DEFLATE="1",
+                       LD_LIBRARY_PATH=os.path.join(root, "hemocell_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+            procs.append(subprocess.Popen([str(d / "pipeflow"), "ci-config.xml"], cwd=d, env=env, stdout=subprocess.PIPE,
+                                          stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate(timeout=900)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), "\n----\n".join(o[-2500:] for o in outs)
+        logs[R] = [ln for ln in outs[0].splitlines() if re.search(r"# of cells|rel\. app\. viscosity|Force  -", ln)]
+    assert len(logs[1]) == 9 and logs[1] == logs[2], (logs[1], logs[2])
+    assert all("# of cells: 42" in ln for ln in logs[2] if "# of cells" in ln)
