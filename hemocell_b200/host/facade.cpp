@@ -236,6 +236,9 @@ void loadDirectories(Config* cfg, bool edit_out_dir) {
   std::string base = dirs.getLogOutDir() + logfilename, name = base;
   for (int i = 0; file_exists(name); i++) name = base + "." + std::to_string(i);
   hlog.open(name); hlogfile.open(name);
+  // config/config.cpp:168-173
+  try { global.checkpointDirectory = dirs.getOutputDir() + "/" + (*cfg)["parameters"]["checkpointDirectory"].read<std::string>() + "/"; }
+  catch (std::invalid_argument&) { global.checkpointDirectory = dirs.getOutputDir() + "/checkpoint/"; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -669,7 +672,7 @@ void HemoCell::saveCheckPoint() {
   hlog << "(HemoCell) (Saving Functions) Saving Checkpoint at timestep " << iter << endl;
   hcg_ctx* c = ctx();
   GpuLattice* g = lattice->gpu();
-  const std::string dir = plb::global::directories().getOutputDir() + "/checkpoint/";
+  const std::string dir = global.checkpointDirectory;
   mkpath(dir);
   plb::global::mpi().barrier();
   const std::string base = dir + "rank" + std::to_string(plb::global::mpi().getRank());
@@ -692,7 +695,9 @@ void HemoCell::saveCheckPoint() {
   if (plb::global::mpi().isMainProcessor()) {
     // checkpoint.xml: <Checkpoint><General><Iteration>..</Iteration></General> + the original <hemocell> tree (config/config.cpp:53-78)
     xml::Node root; xml::Node* cp = root.addChild("Checkpoint");
-    cp->addChild("General")->addChild("Iteration", std::to_string(iter));
+    xml::Node* gen = cp->addChild("General");
+    gen->addChild("Iteration", std::to_string(iter));
+    gen->addChild("OutDirectory", plb::global::directories().getOutputDir());      // core/hemoCellFields.cpp:248: where a restart continues
     std::function<void(const xml::Node*, xml::Node*)> copy = [&](const xml::Node* s, xml::Node* d) {
       for (auto& ch : s->children) { xml::Node* n = d->addChild(ch->name, ch->text); n->attributes = ch->attributes; copy(ch.get(), n); }
     };
@@ -706,15 +711,15 @@ void HemoCell::saveCheckPoint() {
 void HemoCell::loadCheckPoint() {
   hlog << "(HemoCell) (Saving Functions) Loading Checkpoint" << endl;
   if (!cfg->checkpointed) fatal("(HemoCell) loadCheckPoint() needs a checkpoint.xml as configuration file");
+  const xml::Node* cp = cfg->root()->firstChild("Checkpoint");
+  iter = (unsigned int)XMLElement(cp)["General"]["Iteration"].read<unsigned long>();
+  // core/hemoCellFields.cpp:246-252: the run continues in the output directory recorded in the checkpoint
+  try { plb::global::directories().setOutputDir(XMLElement(cp)["General"]["OutDirectory"].read<std::string>()); } catch (std::invalid_argument&) {}
   loadDirectories(cfg, false);
   hcg_ctx* c = ctx();
   upload_celltypes(*this);
   GpuLattice* g = lattice->gpu();
-  const xml::Node* cp = cfg->root()->firstChild("Checkpoint");
-  iter = (unsigned int)XMLElement(cp)["General"]["Iteration"].read<unsigned long>();
-  std::string dir = global.checkpointDirectory;
-  try { dir = XMLElement(cp)["General"]["Directory"].read<std::string>(); } catch (std::invalid_argument&) {}
-  const std::string base = dir + "/rank" + std::to_string(plb::global::mpi().getRank()) + ".bin";
+  const std::string base = global.checkpointDirectory + "/rank" + std::to_string(plb::global::mpi().getRank()) + ".bin";
   std::ifstream f(base, std::ios::binary);
   if (!f) fatal("(HemoCell) cannot open checkpoint data " + base);
   int64_t hdr[6]; f.read((char*)hdr, sizeof(hdr));

@@ -334,3 +334,33 @@ def test_reference_ci_stretchCell_sanity(tmp_path):
     assert all(129.34 < s < 133.04 for s in surf[1:]), surf
     assert 81.11 < vol[0][0] < 81.12 and 129.2 < surf[0] < 129.34, (vol[0], surf[0])
     print("stretchCell CI sanity: largest diameter", diam[-1], "volume", vol[-1], "surface", surf[-1])
+
+
+def test_checkpoint_restart_reproduces_uninterrupted_run(tmp_path):
+    """HemoCell::saveCheckPoint / loadCheckPoint through the reference's unmodified oneCellShear binary: a run
+    interrupted at iteration 200 and restarted from tmp/checkpoint/checkpoint.xml (tmax raised there, as a user
+    would) continues to the stretch.log lines of the uninterrupted run"""
+    env = None
+    logs = {}
+    for name, tmax in (("straight", 400), ("first", 200)):
+        d = tmp_path / name; d.mkdir()
+        env = _refcase(d, "oneCellShear", ["config.xml", "RBC.xml", "RBC.pos"])
+        cfg = (d / "config.xml").read_text()
+        for key, val in (("tmax", tmax), ("tmeas", 100), ("tcheckpoint", 200)):
+            cfg = re.sub(rf"<{key}>.*?</{key}>", f"<{key}> {val} </{key}>", cfg)
+        (d / "config.xml").write_text(cfg)
+        env["HEMOCELL_H5_DEFLATE"] = "1"
+        r = subprocess.run([str(d / "oneCellShear"), "config.xml"], cwd=d, capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        logs[name] = np.loadtxt(d / "stretch.log").reshape(-1, 8)
+    d = tmp_path / "first"
+    cp = d / "tmp" / "checkpoint" / "checkpoint.xml"
+    assert cp.exists()
+    x = cp.read_text()
+    assert "<Iteration>200</Iteration>" in x.replace(" ", "")
+    cp.write_text(re.sub(r"<tmax>.*?</tmax>", "<tmax> 400 </tmax>", x))
+    r = subprocess.run([str(d / "oneCellShear"), str(cp)], cwd=d, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "CHECKPOINT found" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    resumed = np.loadtxt(d / "stretch.log").reshape(-1, 8)
+    assert [int(v) for v in resumed[:, 0]] == [100, 200, 300, 400] == [int(v) for v in logs["straight"][:, 0]]
+    U.assert_close(resumed[:, 1:], logs["straight"][:, 1:], "stretch.log of the restarted run vs the uninterrupted one", rtol=1e-6, floor=1e-9)
