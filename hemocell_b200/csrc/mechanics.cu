@@ -5,6 +5,7 @@
 // and PltSimpleModel::ParticleMechanics (mechanics/pltSimpleModel.cpp:44-208) behind
 // HemoCellParticleField::applyConstitutiveModel (core/hemoCellParticleField.cpp:633-675).
 #include "ctx.cuh"
+#include <cstdlib>
 #include <cfloat>
 
 namespace {
@@ -34,7 +35,7 @@ __device__ __forceinline__ void tri_area_normal(V3 v0, V3 v1, V3 v2, double& are
 
 // MODEL 0 = RbcHighOrderModel, 1 = PltSimpleModel; VISC: membrane viscosity term evaluated
 template <int MODEL, bool VISC, bool COMP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MODEL == 0 ? 3 : 1)
 k_mechanics(MechArgs a) {
   extern __shared__ double sm[];
   const CellTypeDev& t = a.t;
@@ -42,11 +43,15 @@ k_mechanics(MechArgs a) {
   const int64_t cell = a.first_cell + blockIdx.x;
   if (!a.alive[cell]) return;
   const int64_t base = a.first_particle + (int64_t)blockIdx.x*V;
+  // RBC (MODEL 0): triangle areas / normals are NOT staged - the per-vertex gather recomputes them for its <= 6 incident
+  // triangles - so a cell needs 41 KB instead of 82 KB and 4 cells fit an SM (the kernel is latency-bound: 2.0 ms at two
+  // cells per SM, 3.6 ms at one).  PLT (small) keeps the tables: its dihedral bending reads the normals by edge.
+  constexpr bool TRI_TABLES = (MODEL != 0);
   double* X = sm;                    // [3V]
   double* VEL = X + 3*V;             // [3V] if VISC
-  double* TA = VEL + (VISC ? 3*V : 0);   // [T]
-  double* TN = TA + T;               // [3T]
-  double* VT = TN + 3*T;             // [T]
+  double* TA = VEL + (VISC ? 3*V : 0);   // [T]   (TRI_TABLES)
+  double* TN = TA + (TRI_TABLES ? T : 0);               // [3T]  (TRI_TABLES)
+  double* VT = TN + (TRI_TABLES ? 3*T : 0);             // [T]
   double* BF = VT + T;               // [3V] (RBC)
   __shared__ double s_volume;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -68,9 +73,11 @@ k_mechanics(MechArgs a) {
     const double v102 = __dmul_rn(__dmul_rn(v1.x, v0.y), v2.z);
     const double v012 = __dmul_rn(__dmul_rn(v0.x, v1.y), v2.z);
     VT[k] = __dadd_rn(__dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(-v210, v120), v201), v021), v102), v012);
-    double area; V3 n;
-    tri_area_normal(v0, v1, v2, area, n);
-    TA[k] = area; TN[3*k] = n.x; TN[3*k+1] = n.y; TN[3*k+2] = n.z;
+    if (TRI_TABLES) {
+      double area; V3 n;
+      tri_area_normal(v0, v1, v2, area, n);
+      TA[k] = area; TN[3*k] = n.x; TN[3*k+1] = n.y; TN[3*k+2] = n.z;
+    }
   }
   // ---- RBC: bending force of every vertex's own patch (rbcHighOrderModel.cpp:127-158)
   if (MODEL == 0) {
@@ -115,30 +122,29 @@ k_mechanics(MechArgs a) {
     const V3 xv = ldv(X, V, v);
     double F0 = 0.0, F1 = 0.0, F2 = 0.0;
     double c0, c1, c2;
-    // area force (rbcHighOrderModel.cpp:72-92)
+    // area force (rbcHighOrderModel.cpp:72-92) and volume force (:100-113) of the incident triangles
     c0 = c1 = c2 = 0.0;
+    double w0 = 0.0, w1 = 0.0, w2 = 0.0;          // volume-force sum (added after the area terms, as the reference's two loops do)
     for (int k = 0; k < 6; k++) {
       const int tr = t.vt[6*v + k]; if (tr < 0) break;
       const int i0 = t.tri[3*tr], i1 = t.tri[3*tr+1], i2 = t.tri[3*tr+2];
       const V3 v0 = ldv(X, V, i0), v1 = ldv(X, V, i1), v2 = ldv(X, V, i2);
+      double area; V3 n;
+      if (TRI_TABLES) { area = TA[tr]; n = {TN[3*tr], TN[3*tr+1], TN[3*tr+2]}; }
+      else tri_area_normal(v0, v1, v2, area, n);
       const double aeq = t.tri_area_eq[tr];
-      const double areaRatio = (TA[tr] - aeq)/aeq;
+      const double areaRatio = (area - aeq)/aeq;
       const double afm = t.k_area * (areaRatio + areaRatio/fabs(0.09 - areaRatio*areaRatio));
       const double cx = (v0.x+v1.x+v2.x)/3.0, cy = (v0.y+v1.y+v2.y)/3.0, cz = (v0.z+v1.z+v2.z)/3.0;
       const double a0 = afm*(cx - xv.x), a1 = afm*(cy - xv.y), a2 = afm*(cz - xv.z);
       F0 += a0; F1 += a1; F2 += a2;
       if (COMP) { c0 += a0; c1 += a1; c2 += a2; }
+      const double s = area/t.area_mean_eq;
+      w0 += (volume_force*n.x)*s; w1 += (volume_force*n.y)*s; w2 += (volume_force*n.z)*s;
     }
-    if (COMP) { a.comp[0][0][base+v] = c0; a.comp[0][1][base+v] = c1; a.comp[0][2][base+v] = c2; c0 = c1 = c2 = 0.0; }
-    // volume force (rbcHighOrderModel.cpp:100-113)
-    for (int k = 0; k < 6; k++) {
-      const int tr = t.vt[6*v + k]; if (tr < 0) break;
-      const double s = TA[tr]/t.area_mean_eq;
-      const double a0 = (volume_force*TN[3*tr])*s, a1 = (volume_force*TN[3*tr+1])*s, a2 = (volume_force*TN[3*tr+2])*s;
-      F0 += a0; F1 += a1; F2 += a2;
-      if (COMP) { c0 += a0; c1 += a1; c2 += a2; }
-    }
-    if (COMP) { a.comp[1][0][base+v] = c0; a.comp[1][1][base+v] = c1; a.comp[1][2][base+v] = c2; c0 = c1 = c2 = 0.0; }
+    if (COMP) { a.comp[0][0][base+v] = c0; a.comp[0][1][base+v] = c1; a.comp[0][2][base+v] = c2;
+                a.comp[1][0][base+v] = w0; a.comp[1][1][base+v] = w1; a.comp[1][2][base+v] = w2; c0 = c1 = c2 = 0.0; }
+    F0 += w0; F1 += w1; F2 += w2;
     if (MODEL == 0) {
       // bending: own patch force + reaction -F_i/n_i of every neighbour patch, by ascending i
       for (int k = 0; k < 7; k++) {
@@ -348,7 +354,8 @@ hcg_status mech_apply(hcg_ctx* c, int ctype, bool components) {
   const int V = th.d.V, T = th.d.T;
   const bool plt = th.d.model == HCG_MODEL_PLT_SIMPLE;
   const bool visc = plt || th.d.eta_m != 0.0;
-  const size_t smem = sizeof(double)*((size_t)3*V + (visc ? 3*V : 0) + 5*(size_t)T + (plt ? 0 : 3*V));
+  size_t smem = sizeof(double)*((size_t)3*V + (visc ? 3*V : 0) + (plt ? 5 : 1)*(size_t)T + (plt ? 0 : 3*V));
+  { static int pad = -1; if (pad < 0) { const char* e = getenv("HCG_MECH_SMEM_PAD"); pad = e ? atoi(e) : 0; } smem += (size_t)pad*1024; }   // experiment knob: occupancy sensitivity
   const int threads = V >= 256 ? 256 : (V >= 128 ? 128 : 64);
   if (plt) return launch<1, true>(c, a, th.n_cells, smem, threads, components);
   if (visc) return launch<0, true>(c, a, th.n_cells, smem, threads, components);
