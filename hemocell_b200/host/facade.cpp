@@ -831,7 +831,10 @@ void write_particle_h5(HemoCell& h, HemoCellField& field) {
       case OUTPUT_FORCE_REPULSION: vector_field(HCG_P_FREP, "Repulsion force", si ? param::df : 1.0); break;
       case OUTPUT_VERTEX_ID: case OUTPUT_CELL_ID: case OUTPUT_RES_TIME: {
         std::vector<float> one((size_t)N); size_t n = 0;
-        for (auto& o : order) for (int v = 0; v < V; v++) one[n++] = var == OUTPUT_VERTEX_ID ? (float)v : (var == OUTPUT_CELL_ID ? (float)o.first : 0.0f);   // residence time is not tracked on the device path
+        // residence time: writeOutput adds the iterations since the last output to every particle (core/hemoCell.cpp:226,
+        // HemoCellFields::updateResidenceTime); without a pre-inlet every cell exists from iteration 0, so it is the iteration count
+        const float res = (float)((double)h.iter*(si ? param::dt : 1.0));
+        for (auto& o : order) for (int v = 0; v < V; v++) one[n++] = var == OUTPUT_VERTEX_ID ? (float)v : (var == OUTPUT_CELL_ID ? (float)o.first : res);
         w.dataset(var == OUTPUT_VERTEX_ID ? "Vertex Id" : (var == OUTPUT_CELL_ID ? "Cell Id" : "Res Time"), h5::F32, {N, 1}, one.data(), chunk1);
         break; }
       default: break;      // the reference skips variables without a particle output function (io/hemoCellParticleFieldOutputFunctions.cpp:46-50)
