@@ -879,7 +879,13 @@ void write_fluid_h5(HemoCell& h) {
   if (si) for (int k = 0; k < 3; k++) { rel[k] *= (float)param::dx; dxdydz[k] = (float)param::dx; }
   w.attribute("numberOfCells", h5::I32, &ncells, 1); w.attribute("subdomainSize", h5::I32, sub, 3);
   w.attribute("relativePosition", h5::F32, rel, 3); w.attribute("dxdydz", h5::F32, dxdydz, 3);
-  const std::vector<uint64_t> chunk = {std::min<uint64_t>(1000, Nz), std::min<uint64_t>(1000, Ny), std::min<uint64_t>(1000, Nx)};
+  // chunk = min(1000, N) per axis x all components, as io/FluidHdf5IO.hh:133-137; HDF5 caps a chunk at 4 GiB, so very large
+  // blocks are split further along z
+  auto fluid_chunk = [&](int C) {
+    std::vector<uint64_t> ch = {std::min<uint64_t>(1000, Nz), std::min<uint64_t>(1000, Ny), std::min<uint64_t>(1000, Nx), (uint64_t)C};
+    while (ch[0] > 1 && ch[0]*ch[1]*ch[2]*ch[3]*4 > (1ull << 31)) ch[0] = (ch[0] + 1)/2;
+    return ch;
+  };
   const int64_t Nl = (int64_t)nxl*ny*nz;
   // envelope node -> source node of this rank's slab, or -1 (outside a non-periodic face, or in a neighbouring
   // rank's slab: those envelope values are left at the Palabos background default, rho = 1, u = 0)
@@ -898,8 +904,7 @@ void write_fluid_h5(HemoCell& h) {
   auto emit = [&](const std::string& name, int C, double scale, double outside) {
     out.assign((size_t)nCells*C, 0.f);
     for (size_t n = 0; n < (size_t)nCells; n++) for (int k = 0; k < C; k++) out[n*C + k] = (float)((map[n] >= 0 ? buf[(size_t)k*Nl + map[n]] : outside)*scale);
-    std::vector<uint64_t> ch = chunk; ch.push_back((uint64_t)C);
-    w.dataset(name, h5::F32, {Nz, Ny, Nx, (uint64_t)C}, out.data(), ch);
+    w.dataset(name, h5::F32, {Nz, Ny, Nx, (uint64_t)C}, out.data(), fluid_chunk(C));
   };
   const uint8_t* flags = g->flags.data() + (int64_t)x0*ny*nz;
   const double omega = g->omega;
@@ -942,8 +947,7 @@ void write_fluid_h5(HemoCell& h) {
             p += V;
           }
           if (si) for (auto& v : out) v *= (float)f.volumeFractionOfLspPerNode;
-          std::vector<uint64_t> ch = chunk; ch.push_back(1);
-          w.dataset("CellDensity_" + f.name, h5::F32, {Nz, Ny, Nx, 1}, out.data(), ch);
+          w.dataset("CellDensity_" + f.name, h5::F32, {Nz, Ny, Nx, 1}, out.data(), fluid_chunk(1));
         }
         break; }
       case OUTPUT_SHEAR_STRESS:
@@ -969,8 +973,7 @@ void write_fluid_h5(HemoCell& h) {
             out[n*9 + 3*a + b] = (float)((up - um)/2*sc);
           }
         }
-        std::vector<uint64_t> ch = chunk; ch.push_back(9);
-        w.dataset("ShearRate", h5::F32, {Nz, Ny, Nx, 9}, out.data(), ch);
+        w.dataset("ShearRate", h5::F32, {Nz, Ny, Nx, 9}, out.data(), fluid_chunk(9));
         break; }
       default: break;
     }
