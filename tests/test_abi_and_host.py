@@ -137,3 +137,27 @@ def test_voxeliser_and_placement_reproduce_the_references_42_cells():
     _, rid = rbc.place(rr, 0.5e-6, fl.shape, fl.reshape(-1), min_dist_um=float(int(0.5)))
     _, pid = plt.place(pr, 0.5e-6, fl.shape, fl.reshape(-1), min_dist_um=0.0, cell_id0=len(rr))
     assert len(rid) + len(pid) == 42, (len(rid), len(pid))
+
+
+def test_voxeliser_binary_stl_box(tmp_path):
+    """a 10 x 6 x 4 box written as a binary STL: dx = extent / refDirN, margin of one node, nodes on the (inflated)
+    surface count as inside, and the two x ends are opened as helper/voxelizeDomain.cpp:142-156 does"""
+    import struct
+    from hemocell_b200 import lib as H
+    lo, hi = np.array([2.0, -1.0, 5.0]), np.array([12.0, 5.0, 9.0])
+    c = [np.array([x, y, z]) for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])]
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]     # outward orientation
+    tris = []
+    for a, b, cc, d in quads:
+        tris += [(c[a], c[b], c[cc]), (c[a], c[cc], c[d])]
+    p = tmp_path / "box.stl"
+    with open(p, "wb") as f:
+        f.write(b"binary box".ljust(80, b" ")); f.write(struct.pack("<I", len(tris)))
+        for t in tris:
+            n = np.cross(t[1] - t[0], t[2] - t[0]); n = n / np.linalg.norm(n)
+            f.write(struct.pack("<12fH", *n, *t[0], *t[1], *t[2], 0))
+    fl, dx = H.voxelize_stl(p, 20, 0)                       # 20 cells along x: dx = 0.5
+    assert abs(dx - 0.5) < 1e-12 and fl.shape == (23, 15, 11)
+    fluid = fl == 0
+    assert fluid[:, 1:14, 1:10].all() and not fluid[:, 0, :].any() and not fluid[:, :, 10].any()   # open x ends, closed elsewhere
+    assert int(fluid.sum()) == 23 * 13 * 9
