@@ -330,3 +330,54 @@ def test_reference_pipeflow_decomposition_independence(tmp_path):
         logs[R] = [ln for ln in outs[0].splitlines() if re.search(r"# of cells|rel\. app\. viscosity|Force  -", ln)]
     assert len(logs[1]) == 9 and logs[1] == logs[2], (logs[1], logs[2])
     assert all("# of cells: 42" in ln for ln in logs[2] if "# of cells" in ln)
+
+
+@pytest.mark.parametrize("transport", [1, 0])
+def test_two_gpu_closed_box_non_periodic_x(transport):
+    """a closed box (velocity planes on all six faces, nothing periodic) cut into two slabs: the outer x ghosts lie outside
+    the domain, only the middle face exchanges; cells drift across it.  Must match the single-GPU run."""
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from hemocell_b200 import lib as H
+    R = 2
+    dims = (64, 28, 28)
+    nx, ny, nz = dims
+    periodic = (0, 0, 0)
+    par = M.Parameters(dx=0.5e-6, dt=1e-7)
+    bc = np.zeros((6, 3)); bc[4] = (0.03, 0, 0); bc[5] = (0.03, 0, 0)       # z walls drag the fluid along +x
+    fl = U.box_flags(nx, ny, nz).reshape(-1)
+    body = (2e-6, 0.0, 0.0)
+    u0 = (0.03, 0.0, 0.0)
+    ct = O.rbc_celltype(par)
+    centers = [(27.0, 14.0, 13.0), (36.5, 13.0, 15.0), (14.0, 15.0, 14.0), (50.0, 13.5, 13.0)]
+    cells = U.deformed_cells(ct, centers, 8, amp=0.0, stretch=(1.03, 0.99, 0.98))
+    ids = np.arange(len(centers)) + 7
+    steps = 100
+    ctx = H.Context(nx, ny, nz, periodic, par.tau, device=0)
+    ctx.set_flags(fl)
+    for o in range(6):
+        ctx.set_bc_velocity(o, bc[o])
+    ctx.set_body_force(body); ctx.init_equilibrium(1.0, u0); ctx.set_force_limit(par.f_limit)
+    t = ctx.add_celltype(ct.model, ct.cc, ct.k)
+    ctx.add_cells(t, cells, ids)
+    ctx.set_timescales(1, 1, 1); ctx.set_material_timescale(t, 1)
+    ctx.iterate(steps)
+    ref_pop = ctx.lattice_download(H.LAT_POP).reshape(19, nx, ny, nz)
+    ref_pos = ctx.cells_download(H.P_POS).reshape(len(centers), ct.V, 3)
+    assert ctx.count()[0] == len(centers)
+    ctx.close()
+    out = _run_multi(R, dims, periodic, par.tau, fl, bc, body, ct, cells, ids, u0, steps, 1, 5, par.f_limit, transport)
+    for r in range(R):
+        x0, nxl = out[r]["x0"], out[r]["nxl"]
+        U.assert_close(out[r]["pop"].reshape(19, nxl, ny, nz), ref_pop[:, x0:x0 + nxl], f"populations of rank {r}", rtol=1e-9, floor=1e-11)
+    assert sum(o["count"][0] for o in out) == len(centers)
+    seen = set()
+    for r in range(R):
+        o = out[r]
+        pos = o["pos"].reshape(-1, ct.V, 3)
+        for slot, (cid, al) in enumerate(zip(o["ids"], o["alive"])):
+            if cid < 0 or not al:
+                continue
+            seen.add(int(cid) - 7)
+            U.assert_close(pos[slot], ref_pos[int(cid) - 7], f"rank {r} cell {cid} positions", rtol=1e-11, floor=1e-12)
+    assert seen == set(range(len(centers)))
