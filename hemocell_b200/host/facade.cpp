@@ -757,6 +757,31 @@ void HemoCell::loadCheckPoint() {
   loadParticlesIsCalled = true;
 }
 
+// snapshot of the cell bookkeeping (ids, types, alive / owned flags), shared by output and observables
+namespace {
+struct CellSnapshot {
+  int64_t nc = 0, np = 0;
+  std::vector<int64_t> ids, base; std::vector<int32_t> types; std::vector<uint8_t> alive;
+  std::vector<uint8_t> owned;       // multi-rank: cells this rank owns (each cell is owned by exactly one rank)
+};
+CellSnapshot snapshot(HemoCell* h) {
+  CellSnapshot s; hcg_ctx* c = h->ctx();
+  ck(c, hcg_cells_capacity(c, &s.nc, &s.np), "hcg_cells_capacity");
+  s.ids.resize(s.nc); s.types.resize(s.nc); s.alive.resize(s.nc); s.base.resize(s.nc);
+  if (s.nc) ck(c, hcg_cells_info(c, s.ids.data(), s.types.data(), s.alive.data()), "hcg_cells_info");
+  s.owned.assign(s.nc, 1);
+  if (s.nc) ck(c, hcg_cells_owned(c, s.owned.data()), "hcg_cells_owned");
+  int64_t p = 0;
+  for (int64_t k = 0; k < s.nc; k++) { s.base[k] = p; p += (*h->cellfields)[(unsigned)s.types[k]]->numVertex; }
+  return s;
+}
+CellInformation& entry(const CellSnapshot& s, int64_t k) {
+  CellInformation& ci = CellInformationFunctionals::info_per_cell[(int)s.ids[k]];
+  ci.cellType = (pluint)s.types[k]; ci.base_cell_id = (int)s.ids[k]; ci.blockId = (pluint)plb::global::mpi().getRank();
+  return ci;
+}
+}  // namespace
+
 // ---- HDF5 output ---------------------------------------------------------------------------------------
 // File names, dataset names, shapes, element types, root attributes, SI scaling and chunking follow
 // io/ParticleHdf5IO.cpp:60-194 and io/FluidHdf5IO.hh:74-211; the container is written by hemo_h5 (no libhdf5 here).
@@ -982,25 +1007,50 @@ void write_fluid_h5(HemoCell& h) {
 }
 }  // namespace
 
-// io/writeCellInfoCSV.cpp:47-70
+// io/writeCellInfoCSV.cpp:47-70.  With several ranks every rank contributes the cells it owns; the rows travel through
+// hcg_allreduce (each rank fills its own slice of a zero-initialised table) and rank 0 writes the files.
 void writeCellInfo_CSV(HemoCell& hemocell) {
   HemoCell* self = &hemocell;
   const std::string out = plb::global::directories().getOutputDir();
   mkpath(out + "/csv");
   CellInformationFunctionals::calculateCellInformation(self);
-  if (plb::global::mpi().getSize() == 1) {
-    std::vector<std::ofstream> csv(self->cellfields->size());
-    for (unsigned i = 0; i < self->cellfields->size(); i++) {
-      csv[i].open(out + "/csv/" + (*self->cellfields)[i]->name + "." + zeroPadNumber(self->iter) + ".csv", std::ofstream::trunc);
-      csv[i] << "X,Y,Z,area,volume,atomic_block,cellId,baseCellId,velocity_x,velocity_y,velocity_z" << endl;
-    }
+  const int R = plb::global::mpi().getSize(), r = plb::global::mpi().getRank();
+  const int W = 12;      // cellType, X, Y, Z, area, volume, block, cellId, baseCellId, vx, vy, vz
+  std::vector<double> rows;
+  {
+    CellSnapshot s = snapshot(self);
+    std::map<int, bool> owned;
+    for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.ids[k] >= 0) owned[(int)s.ids[k]] = s.owned[k] != 0;
     for (auto& pr : CellInformationFunctionals::info_per_cell) {
+      if (R > 1 && !owned[pr.first]) continue;
       CellInformation ci = pr.second;
       if (self->outputInSiUnits) { ci.position *= param::dx; ci.area *= param::dx*param::dx; ci.velocity *= param::dx/param::dt; ci.volume *= param::dx*param::dx*param::dx; }
-      auto& o = csv[ci.cellType];
-      o << ci.position[0] << "," << ci.position[1] << "," << ci.position[2] << "," << ci.area << "," << ci.volume << "," << ci.blockId << ","
-        << pr.first << "," << ci.base_cell_id << "," << ci.velocity[0] << "," << ci.velocity[1] << "," << ci.velocity[2] << endl;
+      const double row[W] = {(double)ci.cellType, ci.position[0], ci.position[1], ci.position[2], ci.area, ci.volume, (double)ci.blockId,
+                             (double)pr.first, (double)ci.base_cell_id, ci.velocity[0], ci.velocity[1], ci.velocity[2]};
+      rows.insert(rows.end(), row, row + W);
     }
+  }
+  if (R > 1) {
+    std::vector<double> counts(R, 0.0); counts[r] = (double)(rows.size()/W);
+    ck(self->ctx(), hcg_allreduce(self->ctx(), counts.data(), R, 0), "hcg_allreduce");
+    size_t total = 0, off = 0;
+    for (int k = 0; k < R; k++) { if (k < r) off += (size_t)(counts[k] + 0.5); total += (size_t)(counts[k] + 0.5); }
+    std::vector<double> all(total*W, 0.0);
+    std::copy(rows.begin(), rows.end(), all.begin() + off*W);
+    if (total) ck(self->ctx(), hcg_allreduce(self->ctx(), all.data(), (int64_t)all.size(), 0), "hcg_allreduce");
+    rows.swap(all);
+  }
+  if (r != 0) return;
+  std::vector<std::ofstream> csv(self->cellfields->size());
+  for (unsigned i = 0; i < self->cellfields->size(); i++) {
+    csv[i].open(out + "/csv/" + (*self->cellfields)[i]->name + "." + zeroPadNumber(self->iter) + ".csv", std::ofstream::trunc);
+    csv[i] << "X,Y,Z,area,volume,atomic_block,cellId,baseCellId,velocity_x,velocity_y,velocity_z" << endl;
+  }
+  for (size_t k = 0; k < rows.size()/W; k++) {
+    const double* q = rows.data() + k*W;
+    auto& o = csv[(size_t)(q[0] + 0.5)];
+    o << q[1] << "," << q[2] << "," << q[3] << "," << q[4] << "," << q[5] << "," << (long)q[6] << "," << (long)q[7] << "," << (long)q[8] << ","
+      << q[9] << "," << q[10] << "," << q[11] << endl;
   }
 }
 
@@ -1028,29 +1078,6 @@ void HemoCell::writeOutput() {
 }
 
 // CellInformationFunctionals / FluidInfo ------------------------------------------------------------------
-namespace {
-struct CellSnapshot {
-  int64_t nc = 0, np = 0;
-  std::vector<int64_t> ids, base; std::vector<int32_t> types; std::vector<uint8_t> alive;
-  std::vector<uint8_t> owned;       // multi-rank: cells this rank owns (each cell is owned by exactly one rank)
-};
-CellSnapshot snapshot(HemoCell* h) {
-  CellSnapshot s; hcg_ctx* c = h->ctx();
-  ck(c, hcg_cells_capacity(c, &s.nc, &s.np), "hcg_cells_capacity");
-  s.ids.resize(s.nc); s.types.resize(s.nc); s.alive.resize(s.nc); s.base.resize(s.nc);
-  if (s.nc) ck(c, hcg_cells_info(c, s.ids.data(), s.types.data(), s.alive.data()), "hcg_cells_info");
-  s.owned.assign(s.nc, 1);
-  if (s.nc) ck(c, hcg_cells_owned(c, s.owned.data()), "hcg_cells_owned");
-  int64_t p = 0;
-  for (int64_t k = 0; k < s.nc; k++) { s.base[k] = p; p += (*h->cellfields)[(unsigned)s.types[k]]->numVertex; }
-  return s;
-}
-CellInformation& entry(const CellSnapshot& s, int64_t k) {
-  CellInformation& ci = CellInformationFunctionals::info_per_cell[(int)s.ids[k]];
-  ci.cellType = (pluint)s.types[k]; ci.base_cell_id = (int)s.ids[k]; ci.blockId = (pluint)plb::global::mpi().getRank();
-  return ci;
-}
-}  // namespace
 void CellInformationFunctionals::calculateCellVolume(HemoCell* h) {
   CellSnapshot s = snapshot(h); if (!s.nc) return;
   std::vector<double> vol(s.nc), area(s.nc);

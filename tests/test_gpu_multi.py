@@ -281,6 +281,11 @@ def test_facade_two_ranks_case_file(tmp_path):
         assert f["Velocity"].shape == (22, 42, 22, 3) and f.attrs["processorId"][0] == r
         n += h5mini.File(tmp_path / "tmp" / "hdf5" / it / f"RBC.{it}.p.{r}.h5")["Position"].shape[0]
     assert n == 642                                          # the shared cell is written by exactly one rank
+    # CSV: the owning rank's row travels to rank 0, which writes the one file (io/writeCellInfoCSV.cpp)
+    csv = (tmp_path / "tmp" / "csv" / f"RBC.{it}.csv").read_text().strip().splitlines()
+    assert len(csv) == 2 and csv[0].startswith("X,Y,Z,area,volume")
+    vol = float(csv[1].split(",")[4])
+    assert abs(vol / 81.116e-18 - 1.0) < 0.01                 # SI output: m^3
 
 
 def test_peer_transport_falls_back_to_nccl_when_a_rank_cannot_map(monkeypatch):
