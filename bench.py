@@ -367,8 +367,11 @@ def run_cpu(steps, warmup, cadence, budget_s=150.0):
     OpenMP on the host cores, on a bounded sub-box of the same workload (same packing density)."""
     import oracle as O
     from oracle import mesh as M
-    cores = os.cpu_count() or 1
-    O.set_parallel(1)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    O.set_parallel(max(cores, 1) if cores > 1 else 1)      # explicit thread count: torchrun exports OMP_NUM_THREADS=1
     par = M.Parameters(DX, -1.0)
     ct = O.rbc_celltype(par)
 

@@ -15,8 +15,17 @@
 
 /* OpenMP is used only by bench.py's cpu_baseline / --impl reference legs (ora_set_parallel(1));
  * the parity tests run the loops serially, in the reference's order. */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 static int ora_parallel = 0;
-void ora_set_parallel(int on) { ora_parallel = on; }
+/* on > 1 also fixes the thread count (a launcher such as torchrun exports OMP_NUM_THREADS=1 to its children) */
+void ora_set_parallel(int on) {
+  ora_parallel = on != 0;
+#ifdef _OPENMP
+  if (on > 1) omp_set_num_threads(on);
+#endif
+}
 
 /* D3Q19 of Palabos descriptors::D3Q19Descriptor (opposite = i+9,
  * patch/palabos.patch:492-497) */
