@@ -81,6 +81,38 @@ int main(int argc, char** argv) {
   CHECK("plt.k_area_face_scaling", pm && close_rel(pm->k_area, 8.0*(1280.0/128.0)*kBT_lbm/(5e-7/param::dx), 1e-13));
   CHECK("rbc.volume_eq_um3", std::fabs(rbc->mechanics->cellConstants.volume_eq*std::pow(0.5, 3) - 81.1) < 0.2);
   CHECK("cellfields.size", hemocell.cellfields->size() == 2);
+  // meshmetric / original bounding box (core/hemoCellField.h), used by the stretchCell case files
+  CHECK("rbc.meshmetric.volume", close_rel(rbc->meshmetric->getVolume(), rbc->mechanics->cellConstants.volume_eq, 1e-12));
+  CHECK("rbc.meshmetric.surface_um2", std::fabs(rbc->meshmetric->getSurface()*0.25 - 129.2) < 0.3);
+  { auto bb = rbc->getOriginalBoundingBox(); CHECK("rbc.original_bbox", std::fabs((bb[1] - bb[0])*0.5 - 7.82) < 0.01 && std::fabs((bb[3] - bb[2])*0.5 - 2.294) < 0.01 && close_rel(bb[5] - bb[4], bb[1] - bb[0], 1e-12));   // disc axis along y }
+  // the reference stores the minimum wall distance in an unsigned int (core/hemoCellField.h:64): 0.5 um -> 0
+  hemocell.setInitialMinimumDistanceFromSolid("RBC", 0.5);
+  CHECK("quirk.min_distance_truncates", rbc->minimumDistanceFromSolid == 0);
+  hemocell.setInitialMinimumDistanceFromSolid("RBC", 1);
+  CHECK("min_distance_1um", rbc->minimumDistanceFromSolid == 1);
+
+  // helper/voxelizeDomain.h on an ASCII STL written here: a 20 x 10 x 10 box, refDirN 50 along y -> dx = 0.2
+  {
+    std::ofstream f("box.stl");
+    f << "solid box\n";
+    const double lo[3] = {-10, -10, -5}, hi[3] = {10, 0, 5};
+    auto P = [&](int ix, int iy, int iz) { std::ostringstream o; o << "vertex " << (ix ? hi[0] : lo[0]) << " " << (iy ? hi[1] : lo[1]) << " " << (iz ? hi[2] : lo[2]) << "\n"; return o.str(); };
+    const int q[6][4][3] = {{{0,0,0},{0,0,1},{0,1,1},{0,1,0}}, {{1,0,0},{1,1,0},{1,1,1},{1,0,1}}, {{0,0,0},{1,0,0},{1,0,1},{0,0,1}},
+                            {{0,1,0},{0,1,1},{1,1,1},{1,1,0}}, {{0,0,0},{0,1,0},{1,1,0},{1,0,0}}, {{0,0,1},{1,0,1},{1,1,1},{0,1,1}}};
+    for (auto& fc : q) for (int t = 0; t < 2; t++) {
+      f << "facet normal 0 0 0\nouter loop\n" << P(fc[0][0], fc[0][1], fc[0][2]) << P(fc[t+1][0], fc[t+1][1], fc[t+1][2]) << P(fc[t+2][0], fc[t+2][1], fc[t+2][2]) << "endloop\nendfacet\n";
+    }
+    f << "endsolid box\n";
+  }
+  plb::VoxelizedDomain3D<T>* vd = nullptr; plb::MultiScalarField3D<int>* fm = nullptr;
+  getFlagMatrixFromSTL("box.stl", 2, 50, 1, vd, fm, -1, 25);
+  CHECK("voxelizer.size", fm && fm->getNx() == 103 && fm->getNy() == 53 && fm->getNz() == 53);
+  CHECK("voxelizer.fluid_inside", fm && fm->get(50, 26, 26) == 1 && fm->get(50, 1, 1) == 1 && fm->get(50, 0, 26) == 0 && fm->get(50, 26, 52) == 0);
+  CHECK("voxelizer.open_x_ends", fm && fm->get(0, 26, 26) == 1 && fm->get(102, 26, 26) == 1);
+  CHECK("voxelizer.management", vd && vd->getMultiBlockManagement().getBoundingBox().getNx() == 103);
+  param::lbm_pipe_parameters(*cfg, fm);
+  CHECK("param.pipe_radius_from_fluid_area", close_rel(param::pipe_radius, std::sqrt(51.0*51.0/PI), 1e-12));
+  delete vd; delete fm;
   std::printf("%d failures\n", failures);
   return failures;
 }
