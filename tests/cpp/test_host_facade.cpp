@@ -84,7 +84,7 @@ int main(int argc, char** argv) {
   // meshmetric / original bounding box (core/hemoCellField.h), used by the stretchCell case files
   CHECK("rbc.meshmetric.volume", close_rel(rbc->meshmetric->getVolume(), rbc->mechanics->cellConstants.volume_eq, 1e-12));
   CHECK("rbc.meshmetric.surface_um2", std::fabs(rbc->meshmetric->getSurface()*0.25 - 129.2) < 0.3);
-  { auto bb = rbc->getOriginalBoundingBox(); CHECK("rbc.original_bbox", std::fabs((bb[1] - bb[0])*0.5 - 7.82) < 0.01 && std::fabs((bb[3] - bb[2])*0.5 - 2.294) < 0.01 && close_rel(bb[5] - bb[4], bb[1] - bb[0], 1e-12));   // disc axis along y }
+  { auto bb = rbc->getOriginalBoundingBox(); CHECK("rbc.original_bbox", std::fabs((bb[1] - bb[0])*0.5 - 7.82) < 0.01 && std::fabs((bb[3] - bb[2])*0.5 - 2.294) < 0.01 && close_rel(bb[5] - bb[4], bb[1] - bb[0], 1e-12)); }   // disc axis along y
   // the reference stores the minimum wall distance in an unsigned int (core/hemoCellField.h:64): 0.5 um -> 0
   hemocell.setInitialMinimumDistanceFromSolid("RBC", 0.5);
   CHECK("quirk.min_distance_truncates", rbc->minimumDistanceFromSolid == 0);
