@@ -287,9 +287,10 @@ void hcg_destroy(hcg_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->dom.device);
   cudaDeviceSynchronize();
+  preinlet_destroy(c);
   peer_destroy(c);
   if (c->nccl) ncclCommDestroy((ncclComm_t)c->nccl);
-  cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); if (c->F0) cudaFree(c->F0); cudaFree(c->flags); cudaFree(c->d_bc);
+  cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); if (c->F0) cudaFree(c->F0); if (c->bcn) cudaFree(c->bcn); cudaFree(c->flags); cudaFree(c->d_bc);
   if (c->rho) cudaFree(c->rho);
   if (c->fused_done) cudaFree(c->fused_done);
   for (int k = 0; k < 3; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->frc[k]); cudaFree(c->frep[k]); }
@@ -354,12 +355,14 @@ hcg_status hcg_comm_init(hcg_ctx* c, const void* id128) {
 hcg_status hcg_lattice_set_flags(hcg_ctx* c, const uint8_t* flags) {
   if (!c || !flags) return HCG_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
-  bool vel = false;
+  bool vel = false, io = false;
   for (int64_t i = 0; i < c->Nl; i++) {
-    if (flags[i] > HCG_VEL_ZP) return hcg_fail(c, HCG_ERR_ARG, "unknown node flag");
+    if (flags[i] > HCG_ZH_PRES_ZP) return hcg_fail(c, HCG_ERR_ARG, "unknown node flag");
     vel = vel || flags[i] >= HCG_VEL_XN;
+    io = io || flags[i] >= HCG_ZH_VEL_XN;
   }
-  c->has_velbc = vel;
+  c->has_velbc = vel; c->has_iobc = io;
+  if (io) { hcg_status sb = lat_bcn_ensure(c); if (sb) return sb; }
   bool nonfluid = false;
   for (int64_t i = 0; i < c->Nl && !nonfluid; i++) nonfluid = flags[i] != HCG_FLUID;
   c->real_nonfluid = nonfluid; c->has_nonfluid = true;
@@ -377,6 +380,37 @@ hcg_status hcg_lattice_set_bc_velocity(hcg_ctx* c, int32_t o, const double u[3])
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
   for (int k = 0; k < 3; k++) c->bc_vel[o][k] = u[k];
   CUDA_TRY(c, cudaMemcpy(c->d_bc, c->bc_vel, sizeof(c->bc_vel), cudaMemcpyHostToDevice));
+  return HCG_OK;
+}
+
+hcg_status hcg_lattice_set_bc_nodes(hcg_ctx* c, int64_t n, const int64_t* node_idx, const double* val) {
+  if (!c || n < 0 || (n > 0 && (!node_idx || !val))) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  for (int64_t k = 0; k < n; k++) if (node_idx[k] < 0 || node_idx[k] >= c->Nl) return hcg_fail(c, HCG_ERR_ARG, "node index outside this rank's slab");
+  hcg_status s = lat_bcn_ensure(c); if (s) return s;
+  if (n == 0) return HCG_OK;
+  if ((s = ensure_staging(c, (size_t)n*(sizeof(int64_t) + 4*sizeof(double))))) return s;
+  int64_t* d_idx = (int64_t*)c->staging; double* d_val = (double*)((char*)c->staging + (size_t)n*sizeof(int64_t));
+  CUDA_TRY(c, cudaMemcpyAsync(d_idx, node_idx, (size_t)n*sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(d_val, val, (size_t)n*4*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if ((s = lat_bcn_scatter(c, n, d_idx, d_val, false, c->stream))) return s;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_lattice_node_velocity(hcg_ctx* c, int64_t n, const int64_t* node_idx, double* u_out) {
+  if (!c || n < 0 || (n > 0 && (!node_idx || !u_out))) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  for (int64_t k = 0; k < n; k++) if (node_idx[k] < 0 || node_idx[k] >= c->Nl) return hcg_fail(c, HCG_ERR_ARG, "node index outside this rank's slab");
+  if (n == 0) return HCG_OK;
+  hcg_status s = ensure_staging(c, (size_t)n*(sizeof(int64_t) + 4*sizeof(double))); if (s) return s;
+  int64_t* d_idx = (int64_t*)c->staging; double* d_val = (double*)((char*)c->staging + (size_t)n*sizeof(int64_t));
+  CUDA_TRY(c, cudaMemcpyAsync(d_idx, node_idx, (size_t)n*sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  if ((s = lat_node_velocity(c, n, d_idx, d_val, c->stream))) return s;
+  std::vector<double> h((size_t)4*n);
+  CUDA_TRY(c, cudaMemcpyAsync(h.data(), d_val, (size_t)n*4*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int64_t k = 0; k < n; k++) for (int d = 0; d < 3; d++) u_out[3*k + d] = h[4*k + d];
   return HCG_OK;
 }
 
@@ -574,6 +608,7 @@ hcg_status hcg_cells_add(hcg_ctx* c, int32_t ctype, int64_t n_cells, const int64
     cell_id = keep_id.data(); pos = keep_pos.data();
     n_slots = n_cells + (int64_t)(c->multi.slack*n_cells) + 64;
   }
+  n_slots += th.reserve;
   if (n_slots == 0) return HCG_OK;
   const int64_t add_p = n_slots*V, new_p = c->np + add_p, new_c = c->ncells + n_slots;
   if (new_p > 2000000000LL) return hcg_fail(c, HCG_ERR_CAPACITY, "more than 2e9 particles on one GPU");
@@ -631,6 +666,13 @@ hcg_status hcg_cells_add(hcg_ctx* c, int32_t ctype, int64_t n_cells, const int64
   if (c->dom.n_ranks > 1 && (s = multi_rebalance(c, true))) return s;            // builds the shared lists
   if (c->bin_items) { cudaFree(c->bin_items); cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->scan_tmp);
                       c->bin_items = c->bin_count = c->bin_start = nullptr; c->scan_tmp = nullptr; }
+  return HCG_OK;
+}
+
+hcg_status hcg_cells_reserve(hcg_ctx* c, int32_t ctype, int64_t spare_cells) {
+  if (!c || ctype < 0 || ctype >= (int)c->types.size() || spare_cells < 0) return HCG_ERR_ARG;
+  if (c->types[ctype].cap_cells > 0) return hcg_fail(c, HCG_ERR_STATE, "hcg_cells_reserve must precede hcg_cells_add of the type");
+  c->types[ctype].reserve = spare_cells;
   return HCG_OK;
 }
 

@@ -36,6 +36,7 @@ struct CellTypeHost {
   CellTypeDev d;
   int64_t n_cells = 0, first_cell = 0, first_particle = 0;   // n_cells = slots in use (high-water mark)
   int64_t cap_cells = 0;                                      // slots reserved (multi-GPU arrivals)
+  int64_t reserve = 0;                                        // extra spare slots asked for by hcg_cells_reserve (pre-inlet arrivals)
   uint16_t* perm = nullptr;                                   // node-sorted (vertex, corner) pairs per cell (spread_sorted.cu)
   int timescale = 1;
   std::vector<void*> allocs;
@@ -81,6 +82,8 @@ struct PeerState {
   void* d_blob = nullptr;
 };
 
+struct PreInletState;   // csrc/preinlet.cu
+
 struct TimerSlot { std::string name; double ms = 0; int64_t calls = 0; };
 struct TimerPending { int slot; cudaEvent_t a, b; };
 
@@ -100,6 +103,8 @@ struct hcg_ctx {
   double* W = nullptr; bool w_valid = false;   // tau = 1 fast path: raw moments (rhoBar, j) of the current populations, AoS [n][4]
   uint8_t* flags;
   bool u_valid, has_velbc, has_nonfluid;
+  bool has_iobc = false;       // Zou-He velocity / pressure nodes present (flags >= HCG_ZH_VEL_XN)
+  double* bcn = nullptr;       // their per-node values, AoS [n][4] = (u_x, u_y, u_z, rho) over the padded slab; allocated on first use
   bool real_nonfluid = false;  // any non-fluid flag on this rank's real nodes (has_nonfluid also covers the ghost planes)
   // particles
   int64_t np, ncells, cap_p, cap_c;
@@ -136,6 +141,7 @@ struct hcg_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   double* staging; size_t staging_bytes;   // device scratch for AoS<->SoA transposes
+  PreInletState* preinlet = nullptr;       // coupling to a pre-inlet context (this context is the main domain)
 };
 
 hcg_status hcg_fail(hcg_ctx* c, hcg_status code, const std::string& msg);
@@ -184,6 +190,9 @@ hcg_status lat_pop_to_reference(hcg_ctx* c, double* dst_dev);      // S_q(n) = g
 hcg_status lat_pop_from_reference(hcg_ctx* c, const double* src_dev);
 hcg_status lat_pineq(hcg_ctx* c, double* dst_dev);                 // off-equilibrium momentum flux, compact SoA [6][Nl]
 hcg_status lat_velocity_stats(hcg_ctx* c, double* vmin, double* vmax, double* vmean);
+hcg_status lat_bcn_ensure(hcg_ctx* c);
+hcg_status lat_bcn_scatter(hcg_ctx* c, int64_t n, const int64_t* idx_dev, const double* val_dev, bool keep_rho, cudaStream_t st);
+hcg_status lat_node_velocity(hcg_ctx* c, int64_t n, const int64_t* idx_dev, double* out_dev, cudaStream_t st);   // out [n][4] = (u, rho)
 // ibm.cu
 hcg_status ibm_spread(hcg_ctx* c);
 hcg_status ibm_interpolate(hcg_ctx* c);
@@ -215,6 +224,8 @@ hcg_status peer_setup(hcg_ctx* c);                        // collective over sla
 hcg_status peer_barrier(hcg_ctx* c);                      // publish "everything before this is stored", wait for both neighbours
 hcg_status peer_reserve_sync(hcg_ctx* c, size_t doubles_left, size_t doubles_right, bool* changed);
 void peer_destroy(hcg_ctx* c);
+// preinlet.cu
+void preinlet_destroy(hcg_ctx* c);
 // repulsion.cu
 hcg_status rep_apply(hcg_ctx* c);
 hcg_status rep_wall_apply(hcg_ctx* c);

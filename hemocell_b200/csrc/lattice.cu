@@ -17,6 +17,7 @@ struct LatArgs {
   int64_t SL, SR;       // padded slab sizes (population stride) of the left / right neighbour
   double omega;
   const double* bc;     // [6][3] wall velocity per orientation, device memory
+  const double* bcn;    // per-node boundary values of the Zou-He nodes, AoS [n][4] = (u_x, u_y, u_z, rho); null without such nodes
   double body[3];
 };
 
@@ -132,12 +133,107 @@ __device__ __forceinline__ void regularized_complete(double f[19], int o, const 
   }
 }
 
+// Zou-He velocity (pressure = false) / pressure (true) node with OUTWARD normal o (see oracle/hemo_oracle.c:zouhe_complete;
+// helper/preInlet.cpp:399-436, examples/pipeflow_with_preinlet/pipeflow_with_preinlet.cpp:125-133): density (or normal
+// velocity) from the known populations, bounce-back of the non-equilibrium part for the populations entering the
+// domain, tangential momentum excess removed through the unknown diagonals.  bc = (u_x, u_y, u_z, rho) of the node.
+__device__ __forceinline__ void zouhe_complete(double f[19], int o, bool pressure, double b0, double b1, double b2, double b3) {
+  constexpr int CC[19][3] = {{0,0,0},{-1,0,0},{0,-1,0},{0,0,-1},{-1,-1,0},{-1,1,0},{-1,0,-1},{-1,0,1},{0,-1,-1},{0,-1,1},
+                             {1,0,0},{0,1,0},{0,0,1},{1,1,0},{1,-1,0},{1,0,1},{1,0,-1},{0,1,1},{0,1,-1}};
+  constexpr double TW[19] = {1.0/3.0, 1.0/18.0,1.0/18.0,1.0/18.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0,
+                             1.0/18.0,1.0/18.0,1.0/18.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0};
+  const int dir = o >> 1, sgn = (o & 1) ? 1 : -1;
+  double rho_on = 0.0, rho_out = 0.0;
+#pragma unroll
+  for (int q = 0; q < 19; q++) {
+    const int cd = dir == 0 ? CC[q][0] : (dir == 1 ? CC[q][1] : CC[q][2]);
+    const int cn = cd*sgn;
+    if (cn == 0) rho_on += f[q] + TW[q]; else if (cn > 0) rho_out += f[q] + TW[q];
+  }
+  double rho, u[3];
+  if (pressure) {
+    rho = b3; u[0] = u[1] = u[2] = 0.0;
+    const double un = sgn*((rho_on + 2.0*rho_out)/rho - 1.0);
+    if (dir == 0) u[0] = un; else if (dir == 1) u[1] = un; else u[2] = un;
+  } else {
+    u[0] = b0; u[1] = b1; u[2] = b2;
+    const double un = dir == 0 ? b0 : (dir == 1 ? b1 : b2);
+    rho = (rho_on + 2.0*rho_out)/(1.0 + sgn*un);
+  }
+  const double rhoBar = rho - 1.0, invRho = 1.0/rho;
+  const double jx = rho*u[0], jy = rho*u[1], jz = rho*u[2];
+  const double jSqr = jx*jx + jy*jy + jz*jz;
+#pragma unroll
+  for (int q = 1; q < 19; q++) {
+    const int cd = dir == 0 ? CC[q][0] : (dir == 1 ? CC[q][1] : CC[q][2]);
+    if (cd*sgn < 0) {
+      const int p = q <= 9 ? q + 9 : q - 9;
+      const double cjq = CC[q][0]*jx + CC[q][1]*jy + CC[q][2]*jz;
+      f[q] = f[p] - feq(TW[p], -cjq, rhoBar, invRho, jSqr) + feq(TW[q], cjq, rhoBar, invRho, jSqr);
+    }
+  }
+  double jf[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int q = 0; q < 19; q++) { jf[0] += CC[q][0]*f[q]; jf[1] += CC[q][1]*f[q]; jf[2] += CC[q][2]*f[q]; }
+  const double jt[3] = {jx, jy, jz};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    if (k == dir) continue;
+    const double diff = 0.5*(jf[k] - jt[k]);
+#pragma unroll
+    for (int q = 1; q < 19; q++) {
+      const int cd = dir == 0 ? CC[q][0] : (dir == 1 ? CC[q][1] : CC[q][2]);
+      if (cd*sgn < 0 && CC[q][k] != 0) f[q] -= CC[q][k]*diff;
+    }
+  }
+}
+
+// boundary completion of a non-fluid, non-bounce-back node.  BC: 1 = regularized velocity planes only,
+// 2 = also Zou-He velocity / pressure nodes with per-node values (a.bcn).
+template <int BC>
+__device__ __forceinline__ void complete_boundary(double f[19], const LatArgs& a, int64_t n, uint8_t fl) {
+  if (BC == 2 && fl >= HCG_ZH_VEL_XN) {
+    const double2 b01 = *reinterpret_cast<const double2*>(a.bcn + 4*n), b23 = *reinterpret_cast<const double2*>(a.bcn + 4*n + 2);
+    if (fl >= HCG_ZH_PRES_XN) zouhe_complete(f, fl - HCG_ZH_PRES_XN, true, b01.x, b01.y, b23.x, b23.y);
+    else zouhe_complete(f, fl - HCG_ZH_VEL_XN, false, b01.x, b01.y, b23.x, b23.y);
+  } else {
+    const double uw[3] = {a.bc[3*(fl-2)], a.bc[3*(fl-2)+1], a.bc[3*(fl-2)+2]};
+    regularized_complete(f, fl - 2, uw);
+  }
+}
+
+// node velocity / density of a boundary node as Cell::computeVelocity reports it (moments pass)
+template <bool IOBC>
+__device__ __forceinline__ void boundary_velocity(const double f[19], const LatArgs& a, int64_t n, uint8_t fl,
+                                                  double& u0, double& u1, double& u2, double& rho) {
+  if (IOBC && fl >= HCG_ZH_VEL_XN) {
+    const double2 b01 = *reinterpret_cast<const double2*>(a.bcn + 4*n), b23 = *reinterpret_cast<const double2*>(a.bcn + 4*n + 2);
+    if (fl >= HCG_ZH_PRES_XN) {
+      constexpr int CC[19][3] = {{0,0,0},{-1,0,0},{0,-1,0},{0,0,-1},{-1,-1,0},{-1,1,0},{-1,0,-1},{-1,0,1},{0,-1,-1},{0,-1,1},
+                                 {1,0,0},{0,1,0},{0,0,1},{1,1,0},{1,-1,0},{1,0,1},{1,0,-1},{0,1,1},{0,1,-1}};
+      constexpr double TW[19] = {1.0/3.0, 1.0/18.0,1.0/18.0,1.0/18.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0,
+                                 1.0/18.0,1.0/18.0,1.0/18.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0,1.0/36.0};
+      const int o = fl - HCG_ZH_PRES_XN, dir = o >> 1, sgn = (o & 1) ? 1 : -1;
+      double rho_on = 0.0, rho_out = 0.0;
+#pragma unroll
+      for (int q = 0; q < 19; q++) {
+        const int cd = dir == 0 ? CC[q][0] : (dir == 1 ? CC[q][1] : CC[q][2]);
+        const int cn = cd*sgn;
+        if (cn == 0) rho_on += f[q] + TW[q]; else if (cn > 0) rho_out += f[q] + TW[q];
+      }
+      rho = b23.y;
+      const double un = sgn*((rho_on + 2.0*rho_out)/rho - 1.0);
+      u0 = dir == 0 ? un : 0.0; u1 = dir == 1 ? un : 0.0; u2 = dir == 2 ? un : 0.0;
+    } else { u0 = b01.x; u1 = b01.y; u2 = b23.x; }
+  } else { u0 = a.bc[3*(fl-2)]; u1 = a.bc[3*(fl-2)+1]; u2 = a.bc[3*(fl-2)+2]; }
+}
+
 // One thread per real node.  RESET: write the body force back after reading F (steps without
 // velocity interpolation).
 // PEER (multi-GPU, csrc/peer.cu): the face planes additionally store their 5 outgoing populations
 // into the slab neighbour's ghost plane over NVLink (peerL / peerR = the neighbours' output buffers),
 // which replaces the separate halo exchange.
-template <bool RESET, bool VELBC, int MINB, bool PEER>
+template <bool RESET, int BC /*0 none, 1 regularized planes, 2 + Zou-He nodes*/, int MINB, bool PEER>
 __global__ void __launch_bounds__(256, MINB)
 k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, double* __restrict__ F,
                  const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count,
@@ -157,7 +253,7 @@ k_collide_stream(const double* __restrict__ gin, double* __restrict__ gout, doub
   } else {
     const double2 fa = *reinterpret_cast<const double2*>(F + 4*n);
     double Fn[3] = {fa.x, fa.y, F[4*n + 2]};
-    if (VELBC && fl >= HCG_VEL_XN) { const double uw[3] = {a.bc[3*(fl-2)], a.bc[3*(fl-2)+1], a.bc[3*(fl-2)+2]}; regularized_complete(f, fl - 2, uw); }
+    if (BC >= 1 && fl >= HCG_VEL_XN) complete_boundary<BC>(f, a, n, fl);
     guo_collide(f, Fn, a.omega);
   }
   if (RESET) { double2* Fw = reinterpret_cast<double2*>(F + 4*n); Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0); }
@@ -207,7 +303,7 @@ __device__ __forceinline__ void guo_collide_tau1(double f[19], double rhoBar, co
   }
 }
 
-template <bool RESET, bool VELBC, bool PEER>
+template <bool RESET, int BC, bool PEER>
 __global__ void __launch_bounds__(256, TAU1_MINB)
 k_collide_tau1(const double* __restrict__ gin, double* __restrict__ gout, double* __restrict__ F,
                const double* __restrict__ W, const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count,
@@ -234,7 +330,7 @@ k_collide_tau1(const double* __restrict__ gin, double* __restrict__ gout, double
     } else {
       const double2 fa = *reinterpret_cast<const double2*>(F + 4*n);
       double Fn[3] = {fa.x, fa.y, F[4*n + 2]};
-      if (VELBC && fl >= HCG_VEL_XN) { const double uw[3] = {a.bc[3*(fl-2)], a.bc[3*(fl-2)+1], a.bc[3*(fl-2)+2]}; regularized_complete(f, fl - 2, uw); }
+      if (BC >= 1 && fl >= HCG_VEL_XN) complete_boundary<BC>(f, a, n, fl);
       guo_collide(f, Fn, a.omega);
     }
   }
@@ -257,7 +353,7 @@ k_collide_tau1(const double* __restrict__ gin, double* __restrict__ gout, double
 // populations with the spread force still on the node (Cell::computeVelocity through
 // core/hemoCellParticleField.cpp:833).  BounceBack: 0; velocity plane: wall velocity.
 // WOUT (tau = 1 fast path, see k_collide_tau1): also keep the raw moments (rhoBar, j) of the node in W.
-template <bool RESET, bool PEER, bool WOUT>
+template <bool RESET, bool PEER, bool WOUT, bool IOBC>
 __global__ void __launch_bounds__(256)
 k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restrict__ U,
           const uint8_t* __restrict__ flags, LatArgs a, int64_t first, int64_t count,
@@ -280,7 +376,7 @@ k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restri
     const double2 fa = *reinterpret_cast<const double2*>(F + 4*n);
     u0 = j[0]*invRho + 0.5*fa.x; u1 = j[1]*invRho + 0.5*fa.y; u2 = j[2]*invRho + 0.5*F[4*n + 2];
   } else if (fl == HCG_BOUNCEBACK) { u0 = u1 = u2 = 0.0; rho = 1.0; }
-  else { u0 = a.bc[3*(fl-2)]; u1 = a.bc[3*(fl-2)+1]; u2 = a.bc[3*(fl-2)+2]; }
+  else boundary_velocity<IOBC>(f, a, n, fl, u0, u1, u2, rho);
   double2* Uw = reinterpret_cast<double2*>(U + 4*n);
   Uw[0] = make_double2(u0, u1); Uw[1] = make_double2(u2, rho);      // slot 3 carries the density
   if (PEER) {                                                        // node velocity of the face planes -> neighbours' ghost planes
@@ -644,6 +740,44 @@ k_moments_wait(const double* __restrict__ g, double* __restrict__ F, double* __r
   __stcs(Fw, make_double2(a.body[0], a.body[1])); __stcs(Fw + 1, make_double2(a.body[2], 0.0));
 }
 
+// Cell::computeVelocity of a list of nodes (local slab indices) from the current populations and node force:
+// out[4*k] = (u_x, u_y, u_z, rho).  Fluid: u = j/rho + F/2; bounce-back: 0; boundary nodes as in the moments pass.
+__global__ void __launch_bounds__(256)
+k_node_velocity(const double* __restrict__ g, const double* __restrict__ F, const uint8_t* __restrict__ flags, LatArgs a,
+                int64_t count, const int64_t* __restrict__ idx, double* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int64_t i = idx[k];
+  const int64_t n = i + a.P;
+  const int rem = (int)(i % a.P);
+  const int y = rem / a.nz, z = rem - y*a.nz;
+  double f[19];
+  pull19(g, a, n, y, z, f);
+  double rhoBar, j[3];
+  moments19(f, rhoBar, j);
+  const uint8_t fl = flags[n];
+  double u0, u1, u2, rho = 1.0 + rhoBar;
+  if (fl == HCG_FLUID) {
+    const double invRho = 1.0/rho;
+    u0 = j[0]*invRho + 0.5*F[4*n]; u1 = j[1]*invRho + 0.5*F[4*n + 1]; u2 = j[2]*invRho + 0.5*F[4*n + 2];
+  } else if (fl == HCG_BOUNCEBACK) { u0 = u1 = u2 = 0.0; rho = 1.0; }
+  else if (a.bcn) boundary_velocity<true>(f, a, n, fl, u0, u1, u2, rho);
+  else boundary_velocity<false>(f, a, n, fl, u0, u1, u2, rho);
+  out[4*k] = u0; out[4*k + 1] = u1; out[4*k + 2] = u2; out[4*k + 3] = rho;
+}
+// per-node boundary values: scatter val[k] (4 doubles; slot 3 kept when keep_rho) to node idx[k]; fill with (0, 0, 0, 1)
+__global__ void k_bcn_scatter(double* __restrict__ bcn, int64_t P, int64_t count, const int64_t* __restrict__ idx,
+                              const double* __restrict__ val, int keep_rho) {
+  const int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  double* b = bcn + 4*(idx[k] + P);
+  b[0] = val[4*k]; b[1] = val[4*k + 1]; b[2] = val[4*k + 2];
+  if (!keep_rho) b[3] = val[4*k + 3];
+}
+__global__ void k_bcn_fill(double* bcn, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < total) { double2* b = reinterpret_cast<double2*>(bcn + 4*i); b[0] = make_double2(0.0, 0.0); b[1] = make_double2(0.0, 1.0); }
+}
 __global__ void k_fill4(double* F, int64_t total, double b0, double b1, double b2) {
   const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -757,7 +891,7 @@ LatArgs make_args(const hcg_ctx* c) {
     hcg_slab(c->dom.nx, (r + R - 1) % R, R, &x0, &nl); hcg_slab(c->dom.nx, (r + 1) % R, R, &x0, &nr);
     a.nxlL = nl; a.SL = (int64_t)(nl + 2)*c->P; a.SR = (int64_t)(nr + 2)*c->P;
   }
-  a.bc = c->d_bc;
+  a.bc = c->d_bc; a.bcn = c->bcn;
   for (int k = 0; k < 3; k++) a.body[k] = c->body[k];
   return a;
 }
@@ -827,7 +961,7 @@ RowCfg row_config(hcg_ctx* c, int nrows) {
   }
   RowCfg r; r.ok = false; r.stages = 0; r.grid = 0; r.smem = 0; r.R = 1; r.nt = 288;
   const int nz = c->dom.nz;
-  if (env_mode <= 0 || (nz & 1) || nz < 16 || peer_on(c)) return r;   // (the row kernel has no peer-store variant)
+  if (env_mode <= 0 || (nz & 1) || nz < 16 || peer_on(c) || c->has_iobc) return r;   // (the row kernel has no peer-store variant)
   if (c->sm_count <= 0) {
     int dev = c->dom.device, v = 0;
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); c->sm_count = v > 0 ? v : 148;
@@ -886,11 +1020,13 @@ hcg_status lat_collide_rows(hcg_ctx* c, bool reset_force, int row0, int row1, cu
                 pR = c->peer.link[1].rank >= 0 ? (double*)c->peer.link[1].ptr[1 - c->cur] : nullptr; }
 #define K1T_LAUNCH(R, V, P) k_collide_tau1<R, V, P><<<nb, 256, 0, st>>>(gin, gout, c->F, c->W, c->flags, a, first, n, pL, pR)
     if (peer) {
-      if (c->has_velbc) { if (reset_force) K1T_LAUNCH(true, true, true); else K1T_LAUNCH(false, true, true); }
-      else { if (reset_force) K1T_LAUNCH(true, false, true); else K1T_LAUNCH(false, false, true); }
+      if (c->has_iobc) { if (reset_force) K1T_LAUNCH(true, 2, true); else K1T_LAUNCH(false, 2, true); }
+      else if (c->has_velbc) { if (reset_force) K1T_LAUNCH(true, 1, true); else K1T_LAUNCH(false, 1, true); }
+      else { if (reset_force) K1T_LAUNCH(true, 0, true); else K1T_LAUNCH(false, 0, true); }
     } else {
-      if (c->has_velbc) { if (reset_force) K1T_LAUNCH(true, true, false); else K1T_LAUNCH(false, true, false); }
-      else { if (reset_force) K1T_LAUNCH(true, false, false); else K1T_LAUNCH(false, false, false); }
+      if (c->has_iobc) { if (reset_force) K1T_LAUNCH(true, 2, false); else K1T_LAUNCH(false, 2, false); }
+      else if (c->has_velbc) { if (reset_force) K1T_LAUNCH(true, 1, false); else K1T_LAUNCH(false, 1, false); }
+      else { if (reset_force) K1T_LAUNCH(true, 0, false); else K1T_LAUNCH(false, 0, false); }
     }
 #undef K1T_LAUNCH
     KERNEL_CHECK(c);
@@ -900,16 +1036,18 @@ hcg_status lat_collide_rows(hcg_ctx* c, bool reset_force, int row0, int row1, cu
     double* pL = c->peer.link[0].rank >= 0 ? (double*)c->peer.link[0].ptr[1 - c->cur] : nullptr;
     double* pR = c->peer.link[1].rank >= 0 ? (double*)c->peer.link[1].ptr[1 - c->cur] : nullptr;
 #define K1_LAUNCH(R, V) k_collide_stream<R, V, 2, true><<<nb, 256, 0, st>>>(gin, gout, c->F, c->flags, a, first, n, pL, pR)
-    if (c->has_velbc) { if (reset_force) K1_LAUNCH(true, true); else K1_LAUNCH(false, true); }
-    else { if (reset_force) K1_LAUNCH(true, false); else K1_LAUNCH(false, false); }
+    if (c->has_iobc) { if (reset_force) K1_LAUNCH(true, 2); else K1_LAUNCH(false, 2); }
+    else if (c->has_velbc) { if (reset_force) K1_LAUNCH(true, 1); else K1_LAUNCH(false, 1); }
+    else { if (reset_force) K1_LAUNCH(true, 0); else K1_LAUNCH(false, 0); }
 #undef K1_LAUNCH
   } else {
     static int minb = -1;
     if (minb < 0) { const char* e = getenv("HCG_K1_MINB"); minb = e ? atoi(e) : 3; }   // 3 CTAs/SM (80 registers, ~90 B spilled): 0.935 vs 0.950 ms at 2
 #define K1_LAUNCH(R, V) do { if (minb == 3) k_collide_stream<R, V, 3, false><<<nb, 256, 0, st>>>(gin, gout, c->F, c->flags, a, first, n, nullptr, nullptr); \
       else k_collide_stream<R, V, 2, false><<<nb, 256, 0, st>>>(gin, gout, c->F, c->flags, a, first, n, nullptr, nullptr); } while (0)
-    if (c->has_velbc) { if (reset_force) K1_LAUNCH(true, true); else K1_LAUNCH(false, true); }
-    else { if (reset_force) K1_LAUNCH(true, false); else K1_LAUNCH(false, false); }
+    if (c->has_iobc) { if (reset_force) K1_LAUNCH(true, 2); else K1_LAUNCH(false, 2); }
+    else if (c->has_velbc) { if (reset_force) K1_LAUNCH(true, 1); else K1_LAUNCH(false, 1); }
+    else { if (reset_force) K1_LAUNCH(true, 0); else K1_LAUNCH(false, 0); }
 #undef K1_LAUNCH
   }
   KERNEL_CHECK(c);
@@ -946,7 +1084,8 @@ static hcg_status moments_rows(hcg_ctx* c, bool reset_force, int row0, int row1)
   if (peer) { pL = c->peer.link[0].rank >= 0 ? (double*)c->peer.link[0].ptr[2] : nullptr;
               pR = c->peer.link[1].rank >= 0 ? (double*)c->peer.link[1].ptr[2] : nullptr; }
   const bool wout = c->W != nullptr;
-#define MOM_LAUNCH(R, P, WO) k_moments<R, P, WO><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, pL, pR, c->W)
+#define MOM_LAUNCH(R, P, WO) do { if (c->has_iobc) k_moments<R, P, WO, true><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, pL, pR, c->W); \
+    else k_moments<R, P, WO, false><<<nb, 256, 0, c->stream>>>(c->g[c->cur], c->F, c->U, c->flags, a, first, n, pL, pR, c->W); } while (0)
   if (peer) {
     if (wout) { if (reset_force) MOM_LAUNCH(true, true, true); else MOM_LAUNCH(false, true, true); }
     else { if (reset_force) MOM_LAUNCH(true, true, false); else MOM_LAUNCH(false, true, false); }
@@ -1106,4 +1245,26 @@ hcg_status lat_pad3(hcg_ctx* c, const double* src_dev, double* dst) {
 hcg_status lat_unpad(hcg_ctx* c, const double* src, double* dst_dev, int first, int ncomp) {
   k_unpad4<<<nblk(c->Nl, 256), 256, 0, c->stream>>>(src, dst_dev, c->Nl, c->P, first, ncomp);
   KERNEL_CHECK(c); return HCG_OK;
+}
+
+// per-node boundary values of the Zou-He nodes (allocated on first use, (0, 0, 0, 1) everywhere)
+hcg_status lat_bcn_ensure(hcg_ctx* c) {
+  if (c->bcn) return HCG_OK;
+  CUDA_TRY(c, cudaMalloc(&c->bcn, sizeof(double)*4*c->S));
+  k_bcn_fill<<<nblk(c->S, 256), 256, 0, c->stream>>>(c->bcn, c->S);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+hcg_status lat_bcn_scatter(hcg_ctx* c, int64_t n, const int64_t* idx_dev, const double* val_dev, bool keep_rho, cudaStream_t st) {
+  if (n <= 0) return HCG_OK;
+  k_bcn_scatter<<<nblk(n, 256), 256, 0, st>>>(c->bcn, c->P, n, idx_dev, val_dev, keep_rho ? 1 : 0);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+hcg_status lat_node_velocity(hcg_ctx* c, int64_t n, const int64_t* idx_dev, double* out_dev, cudaStream_t st) {
+  if (n <= 0) return HCG_OK;
+  LatArgs a = make_args(c);
+  k_node_velocity<<<nblk(n, 256), 256, 0, st>>>(c->g[c->cur], c->F, c->flags, a, n, idx_dev, out_dev);
+  KERNEL_CHECK(c);
+  return HCG_OK;
 }

@@ -16,6 +16,8 @@ c_i64p = C.POINTER(C.c_int64)
 c_u8p = C.POINTER(C.c_uint8)
 
 FLUID, BOUNCEBACK, VEL_XN, VEL_XP, VEL_YN, VEL_YP, VEL_ZN, VEL_ZP = range(8)
+ZH_VEL_XN, ZH_VEL_XP, ZH_VEL_YN, ZH_VEL_YP, ZH_VEL_ZN, ZH_VEL_ZP = range(8, 14)        # Zou-He velocity nodes
+ZH_PRES_XN, ZH_PRES_XP, ZH_PRES_YN, ZH_PRES_YP, ZH_PRES_ZN, ZH_PRES_ZP = range(14, 20)  # Zou-He pressure nodes
 MODEL_RBC, MODEL_PLT = 0, 1
 LAT_POP, LAT_FORCE, LAT_VELOCITY, LAT_DENSITY, LAT_PINEQ = range(5)
 P_POS, P_VEL, P_FORCE, P_FREP, P_F_AREA, P_F_VOLUME, P_F_BEND, P_F_LINK, P_F_VISC, P_F_INNER = range(10)
@@ -52,7 +54,9 @@ hcg_set_force_limit hcg_set_timescales hcg_set_material_timescale hcg_set_repuls
 hcg_set_spread_mode hcg_set_exchange hcg_set_transport hcg_exchange_stats hcg_set_iteration hcg_get_iteration hcg_iterate hcg_fluid_warmup hcg_op_repulsion hcg_op_wall_repulsion
 hcg_op_spread hcg_op_collide_stream hcg_op_interpolate hcg_op_sync hcg_op_advance hcg_op_mechanics
 hcg_op_zero_force hcg_cells_bbox hcg_cells_volume_area hcg_cells_stretch hcg_fluid_velocity_stats hcg_timers_enable
-hcg_timers hcg_timers_reset hcg_launch_count hcg_synchronize hcg_iterate_timed""".split()
+hcg_timers hcg_timers_reset hcg_launch_count hcg_synchronize hcg_iterate_timed
+hcg_lattice_set_bc_nodes hcg_lattice_node_velocity hcg_cells_reserve hcg_preinlet_map hcg_preinlet_apply_velocity
+hcg_preinlet_apply_cells""".split()
 
 _lib = None
 
@@ -136,6 +140,38 @@ class Context:
 
     def set_bc_velocity(self, orientation, u):
         self._ck(self.L.hcg_lattice_set_bc_velocity(self.h, C.c_int32(orientation), (C.c_double * 3)(*u)))
+
+    def set_bc_nodes(self, node_idx, val):
+        """per-node (u_x, u_y, u_z, rho) of Zou-He velocity / pressure nodes; node_idx = local node indices"""
+        idx = np.ascontiguousarray(node_idx, dtype=np.int64).reshape(-1)
+        v = np.ascontiguousarray(val, dtype=np.float64).reshape(-1)
+        assert v.size == 4 * idx.size
+        self._ck(self.L.hcg_lattice_set_bc_nodes(self.h, C.c_int64(idx.size), _p(idx, c_i64p), _p(v)))
+
+    def node_velocity(self, node_idx):
+        idx = np.ascontiguousarray(node_idx, dtype=np.int64).reshape(-1)
+        out = np.empty((idx.size, 3))
+        self._ck(self.L.hcg_lattice_node_velocity(self.h, C.c_int64(idx.size), _p(idx, c_i64p), _p(out)))
+        return out
+
+    # ---- pre-inlet coupling (this context = main domain)
+    def preinlet_map(self, pre, pre_idx, main_idx):
+        a = np.ascontiguousarray(pre_idx, dtype=np.int64).reshape(-1)
+        b = np.ascontiguousarray(main_idx, dtype=np.int64).reshape(-1)
+        assert a.size == b.size
+        self._ck(self.L.hcg_preinlet_map(self.h, pre.h, C.c_int64(a.size), _p(a, c_i64p), _p(b, c_i64p)))
+
+    def preinlet_apply_velocity(self):
+        self._ck(self.L.hcg_preinlet_apply_velocity(self.h))
+
+    def preinlet_apply_cells(self, axis, period, shift, slab_lo, slab_hi, id_stride):
+        n = C.c_int64()
+        self._ck(self.L.hcg_preinlet_apply_cells(self.h, C.c_int32(axis), C.c_double(period), (C.c_double * 3)(*shift),
+                                                 C.c_double(slab_lo), C.c_double(slab_hi), C.c_int64(id_stride), C.byref(n)))
+        return n.value
+
+    def reserve_cells(self, ctype, spare):
+        self._ck(self.L.hcg_cells_reserve(self.h, C.c_int32(ctype), C.c_int64(spare)))
 
     def init_equilibrium(self, rho=1.0, u=(0.0, 0.0, 0.0)):
         self._ck(self.L.hcg_lattice_init_equilibrium(self.h, C.c_double(rho), (C.c_double * 3)(*u)))

@@ -13,7 +13,8 @@
  *   populations   pop[q*N + idx], q = 0..18 in Palabos D3Q19 order, stored as f_q - t_q,
  *                 POST-STREAM (what Palabos holds between collideAndStream() calls)
  *   node vectors  a[d*N + idx], d = 0..2
- *   flags         uint8: HCG_FLUID, HCG_BOUNCEBACK, HCG_VEL_* (velocity plane, OUTWARD normal)
+ *   flags         uint8: HCG_FLUID, HCG_BOUNCEBACK, HCG_VEL_* (velocity plane, OUTWARD normal),
+ *                 HCG_ZH_VEL_* / HCG_ZH_PRES_* (Zou-He velocity / pressure node with per-node values)
  *   particles     AoS xyz, cells contiguous, vertices in vertexId order, cell types in the
  *                 order they were added:  a[3*(base(cell) + vertexId) + d]
  *   multi-GPU     one context per rank/GPU; the lattice is cut into n_ranks slabs along x.
@@ -38,7 +39,13 @@ typedef int32_t hcg_status;               /* 0 = ok, < 0 = error */
 #define HCG_ERR_CAPACITY (-5)
 
 enum { HCG_FLUID = 0, HCG_BOUNCEBACK = 1, HCG_VEL_XN = 2, HCG_VEL_XP = 3, HCG_VEL_YN = 4,
-       HCG_VEL_YP = 5, HCG_VEL_ZN = 6, HCG_VEL_ZP = 7 };
+       HCG_VEL_YP = 5, HCG_VEL_ZN = 6, HCG_VEL_ZP = 7,
+       /* Zou-He nodes with per-node values (hcg_lattice_set_bc_nodes), OUTWARD normal -x,+x,-y,+y,-z,+z:
+        * velocity nodes = createZouHeBoundaryCondition3D()->addVelocityBoundary{0,1,2}{N,P} (helper/preInlet.cpp:399-436),
+        * pressure nodes = WrappedZouHeBoundaryManager3D addPressureBoundary{0,1,2}{N,P} + setBoundaryDensity
+        * (examples/pipeflow_with_preinlet/pipeflow_with_preinlet.cpp:125-133) */
+       HCG_ZH_VEL_XN = 8, HCG_ZH_VEL_XP = 9, HCG_ZH_VEL_YN = 10, HCG_ZH_VEL_YP = 11, HCG_ZH_VEL_ZN = 12, HCG_ZH_VEL_ZP = 13,
+       HCG_ZH_PRES_XN = 14, HCG_ZH_PRES_XP = 15, HCG_ZH_PRES_YN = 16, HCG_ZH_PRES_YP = 17, HCG_ZH_PRES_ZN = 18, HCG_ZH_PRES_ZP = 19 };
 enum { HCG_MODEL_RBC_HIGHORDER = 0, HCG_MODEL_PLT_SIMPLE = 1 };
 /* lattice fields */
 enum { HCG_LAT_POP = 0, HCG_LAT_FORCE = 1, HCG_LAT_VELOCITY = 2, HCG_LAT_DENSITY = 3,
@@ -108,6 +115,14 @@ hcg_status hcg_lattice_set_flags(hcg_ctx*, const uint8_t* flags);
 /* setBoundaryVelocity(lattice, plane, u) (helper/hemocellInit.hh:75-77): one wall velocity per
  * velocity-plane orientation, index = flag - HCG_VEL_XN */
 hcg_status hcg_lattice_set_bc_velocity(hcg_ctx*, int32_t orientation, const double u[3]);
+/* setBoundaryVelocity(lattice, Box3D(point), u) / setBoundaryDensity(lattice, box, rho) on Zou-He nodes
+ * (helper/preInlet.cpp:380, examples/pipeflow_with_preinlet/pipeflow_with_preinlet.cpp:132): values of n nodes of this
+ * rank's slab, node_idx = local node index, val = [n][4] (u_x, u_y, u_z, rho).  Velocity nodes use u, pressure nodes
+ * rho; nodes never set hold (0, 0, 0, 1). */
+hcg_status hcg_lattice_set_bc_nodes(hcg_ctx*, int64_t n, const int64_t* node_idx, const double* val);
+/* Cell::computeVelocity of n nodes of this rank's slab from the CURRENT populations and node force
+ * (helper/preInlet.cpp:372: the velocity the pre-inlet sends to the main domain's inlet nodes): u_out [n][3] */
+hcg_status hcg_lattice_node_velocity(hcg_ctx*, int64_t n, const int64_t* node_idx, double* u_out);
 /* HemoCell::latticeEquilibrium -> initializeAtEquilibrium (core/hemoCell.cpp:129-133) */
 hcg_status hcg_lattice_init_equilibrium(hcg_ctx*, double rho, const double u[3]);
 /* the setExternalVector(lattice, bbox, forceBeginsAt, f) every case file re-applies after
@@ -126,6 +141,9 @@ hcg_status hcg_celltype_add(hcg_ctx*, const hcg_celltype* t, int32_t* ctype_out)
 /* HemoCell::loadParticles (core/hemoCell.cpp:191-197) after placement: all cells of one type,
  * call once per type in type order.  pos: [n_cells][V][3]. */
 hcg_status hcg_cells_add(hcg_ctx*, int32_t ctype, int64_t n_cells, const int64_t* cell_id, const double* pos);
+/* spare cell slots of a type for cells that arrive later (pre-inlet hand-over); must precede hcg_cells_add of the type,
+ * which may then be called with n_cells = 0 */
+hcg_status hcg_cells_reserve(hcg_ctx*, int32_t ctype, int64_t spare_cells);
 hcg_status hcg_cells_count(hcg_ctx*, int64_t* n_cells_alive, int64_t* n_particles_alive);
 /* whole-array particle access in storage order incl. deleted cells (alive_out marks them);
  * needed by per-operator parity tests and checkpoint restore.  n = hcg_cells_capacity */
@@ -182,6 +200,24 @@ hcg_status hcg_get_iteration(hcg_ctx*, int64_t* iter);
  * lattice->collideAndStream() warm-up loop when fluid_only != 0 */
 hcg_status hcg_iterate(hcg_ctx*, int64_t n_steps);
 hcg_status hcg_fluid_warmup(hcg_ctx*, int64_t n_steps);
+
+/* ---- pre-inlet (helper/preInlet.cpp): a second, periodic, force-driven context `pre` feeds the inlet of `main`.
+ * Both are single-rank contexts, on one GPU or on two GPUs of the box; they iterate independently (own streams). */
+/* PreInlet::initializePreInletVelocityBoundary (helper/preInlet.cpp:399-436): n node pairs, pre-inlet node pre_idx[k]
+ * (a fluid node of its coupling plane) drives main's Zou-He velocity node main_idx[k] */
+hcg_status hcg_preinlet_map(hcg_ctx* main, hcg_ctx* pre, int64_t n, const int64_t* pre_idx, const int64_t* main_idx);
+/* PreInlet::applyPreInletVelocityBoundary (helper/preInlet.cpp:344-397), device to device: Cell::computeVelocity of the
+ * pre-inlet nodes (current populations + node force) -> boundary velocity of the mapped main nodes; stream-ordered
+ * between the two contexts by events, no host synchronisation */
+hcg_status hcg_preinlet_apply_velocity(hcg_ctx* main);
+/* PreInlet::applyPreInletParticleBoundary (helper/preInlet.cpp:255-342) in whole cells: a cell of the pre-inlet is
+ * copied (positions + shift, velocity, force, repulsion force) into a free slot of main the first time its periodic
+ * image k (position + k*period along `axis`) lies wholly inside [slab_lo, slab_hi] (main coordinates, = the
+ * reference's inflow slab of particleEnvelope planes behind the inlet); its id becomes id + k*id_stride (the
+ * reference's cellId += offset*number_of_cells per wrap, core/hemoCellParticleDataTransfer.cpp:33-66).  The pre-inlet
+ * keeps its cell.  Deviation from the reference: partially entered cells are not mirrored vertex by vertex. */
+hcg_status hcg_preinlet_apply_cells(hcg_ctx* main, int32_t axis, double period, const double shift[3],
+                                    double slab_lo, double slab_hi, int64_t id_stride, int64_t* n_added);
 
 /* ---- per-operator entry points (single-step parity; same order as iterate()) */
 hcg_status hcg_op_repulsion(hcg_ctx*);       /* HemoCellFields::applyRepulsionForce          */

@@ -146,16 +146,19 @@ def init_equilibrium(dom, rho=1.0, u=(0.0, 0.0, 0.0)):
     return pop
 
 
-def collide_and_stream(dom, flags, pop, force, scratch=None):
+def collide_and_stream(dom, flags, pop, force, scratch=None, bc_node=None):
+    """bc_node: [4*N] (u_x, u_y, u_z, rho) planes for Zou-He velocity / pressure nodes (flags 8..19)"""
     if scratch is None:
         scratch = np.empty_like(pop)
-    lib().ora_collide_and_stream(C.byref(dom), _p(flags, c_u8p), _p(pop), _p(force), _p(scratch))
+    lib().ora_collide_and_stream_io(C.byref(dom), _p(flags, c_u8p), _p(pop), _p(force), _p(scratch),
+                                    None if bc_node is None else _p(bc_node))
 
 
-def moments(dom, flags, pop, force):
+def moments(dom, flags, pop, force, bc_node=None):
     N = dom.nx * dom.ny * dom.nz
     rho, vel = np.empty(N), np.empty(3 * N)
-    lib().ora_moments(C.byref(dom), _p(flags, c_u8p), _p(pop), _p(force), _p(rho), _p(vel))
+    lib().ora_moments_io(C.byref(dom), _p(flags, c_u8p), _p(pop), _p(force), _p(rho), _p(vel),
+                         None if bc_node is None else _p(bc_node))
     return rho, vel
 
 
@@ -230,6 +233,32 @@ class OracleSim:
         self.vel_timescale = 1
         self.rep_enabled = False; self.rep_timescale = 1; self.rep_k = 0.0; self.rep_cutoff = 0.0
         self.wall_enabled = False; self.wall_timescale = 1; self.wall_k = 0.0; self.wall_cutoff = 0.0
+        self.bc_node = None     # [4*N] (u_x, u_y, u_z, rho) of the Zou-He velocity / pressure nodes (flags 8..19)
+
+    def set_bc_nodes(self, node_idx, val):
+        """setBoundaryVelocity / setBoundaryDensity on single Zou-He nodes (helper/preInlet.cpp:380,
+        pipeflow_with_preinlet.cpp:132); val [n, 4]"""
+        if self.bc_node is None:
+            self.bc_node = np.zeros(4 * self.N); self.bc_node[3 * self.N:] = 1.0
+        b = self.bc_node.reshape(4, self.N)
+        b[:, np.asarray(node_idx, dtype=np.int64)] = np.asarray(val, dtype=np.float64).reshape(-1, 4).T
+
+    def node_velocity(self, node_idx):
+        """Cell::computeVelocity of the listed nodes from the current populations and node force"""
+        _, vel = moments(self.dom, self.flags, self.pop, self.force, self.bc_node)
+        return np.ascontiguousarray(vel.reshape(3, self.N)[:, np.asarray(node_idx, dtype=np.int64)].T)
+
+    def insert_cells(self, t, pos, vel, pforce, frep, cell_ids):
+        """cells that arrive later (pre-inlet hand-over): appended to the block of their type"""
+        off = self._offsets()
+        c_at = int(np.searchsorted(self.ctype, t, side='right'))
+        p_at = int(off[c_at])
+        ins = lambda a, b: np.ascontiguousarray(np.concatenate([a[:p_at], np.asarray(b).reshape(-1, 3), a[p_at:]]))
+        self.pos, self.vel = ins(self.pos, pos), ins(self.vel, vel)
+        self.pforce, self.frep = ins(self.pforce, pforce), ins(self.frep, frep)
+        n = len(cell_ids)
+        self.ctype = np.concatenate([self.ctype[:c_at], np.full(n, t, dtype=np.int32), self.ctype[c_at:]])
+        self.cell_id = np.concatenate([self.cell_id[:c_at], np.asarray(cell_ids, dtype=np.int64), self.cell_id[c_at:]])
 
     def _reset_force(self):
         for k in range(3):
@@ -279,7 +308,7 @@ class OracleSim:
         if self.wall_enabled and self.iter % self.wall_timescale == 0:
             wall_repulsion(d, fl, self.pos, self.wall_k, self.wall_cutoff, self.frep)
         spread(d, fl, self.pos, self.pforce, self.frep, self.f_limit, self.force)
-        collide_and_stream(d, fl, self.pop, self.force, self.scratch)
+        collide_and_stream(d, fl, self.pop, self.force, self.scratch, self.bc_node)
         if self.iter % self.vel_timescale == 0:
             self.vel = interpolate(d, fl, self.pos, self.pop, self.force)
         _, hit = advance(d, fl, self.pos, self.vel)
@@ -293,3 +322,47 @@ class OracleSim:
         self.apply_mechanics()
         self._reset_force()                            # setExternalVector(..., 0) + case-file body force
         self.iter += 1
+
+
+class PreInletCoupling:
+    """Restatement of PreInlet::applyPreInlet (helper/preInlet.cpp:255-397) between two OracleSims: `pre`, the
+    periodic force-driven pre-inlet, and `main`, whose Zou-He velocity nodes main_idx take the velocity of the
+    pre-inlet nodes pre_idx after every step.  Cells are handed over whole (see include/hemocell_gpu.h,
+    hcg_preinlet_apply_cells): the periodic image k of a pre-inlet cell is copied the first time it lies wholly
+    inside [slab_lo, slab_hi] along `axis` in main coordinates (= position + shift + k*period), id + k*id_stride."""
+
+    def __init__(self, pre, main, pre_idx, main_idx, axis, period, shift, slab_lo, slab_hi, id_stride):
+        self.pre, self.main = pre, main
+        self.pre_idx = np.asarray(pre_idx, dtype=np.int64); self.main_idx = np.asarray(main_idx, dtype=np.int64)
+        self.axis, self.period, self.shift = axis, float(period), np.asarray(shift, dtype=np.float64)
+        self.slab_lo, self.slab_hi, self.id_stride = float(slab_lo), float(slab_hi), int(id_stride)
+        self.last_lap = {}
+        if main.bc_node is None:
+            main.set_bc_nodes(np.zeros(0, dtype=np.int64), np.zeros((0, 4)))
+
+    def apply_velocity(self):
+        u = self.pre.node_velocity(self.pre_idx)
+        b = self.main.bc_node.reshape(4, self.main.N)
+        b[0:3, self.main_idx] = u.T
+
+    def apply_cells(self):
+        pre, main, ax = self.pre, self.main, self.axis
+        off = pre._offsets()
+        added = 0
+        for c in range(len(pre.ctype)):
+            x = pre.pos[off[c]:off[c + 1]]
+            lo, hi = x[:, ax].min() + self.shift[ax], x[:, ax].max() + self.shift[ax]
+            k = np.ceil((self.slab_lo - lo) / self.period)
+            if hi + k * self.period > self.slab_hi:
+                continue
+            k = int(k)
+            cid = int(pre.cell_id[c])
+            if self.last_lap.get(cid) == k:
+                continue
+            self.last_lap[cid] = k
+            sh = self.shift.copy(); sh[ax] += k * self.period
+            sl = slice(off[c], off[c + 1])
+            main.insert_cells(int(pre.ctype[c]), pre.pos[sl] + sh, pre.vel[sl], pre.pforce[sl], pre.frep[sl],
+                              [cid + k * self.id_stride])
+            added += 1
+        return added

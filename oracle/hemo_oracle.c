@@ -139,13 +139,59 @@ static void regularized_velocity_complete(double f[19], int o, const double uw[3
   }
 }
 
+/* Zou-He velocity / pressure boundary nodes (the pre-inlet coupling and the outlet of
+ * examples/pipeflow_with_preinlet/pipeflow_with_preinlet.cpp:125-133, helper/preInlet.cpp:399-436:
+ * createZouHeBoundaryCondition3D -> addVelocityBoundary{0,1,2}{N,P} on single nodes,
+ * WrappedZouHeBoundaryManager3D -> addPressureBoundary0N + setBoundaryDensity).  Palabos is not in the
+ * tree; restated from the published scheme (Zou & He 1997; 3-D form of Hecht & Harting 2010) as Palabos'
+ * ZouHeDynamics::completePopulations implements it:
+ *   velocity node: rho from the known populations and the imposed u (same closure as the regularized plane);
+ *   pressure node: rho imposed, normal velocity from the same closure, tangential velocity 0;
+ *   unknown populations (c.n_out < 0): bounce-back of the non-equilibrium part,
+ *   then the tangential momentum excess is removed through the unknown diagonal populations
+ *   (half of it on each of the two diagonals that carry the component), which makes rho and j exact.
+ * The base dynamics (Guo BGK) collides afterwards.  bc = (u_x, u_y, u_z, rho) of the node. */
+static void zouhe_complete(double f[19], int o, int pressure, const double bc[4]) {
+  int dir = o / 2, sgn = (o & 1) ? +1 : -1;
+  double rho_on = 0.0, rho_out = 0.0;
+  for (int i = 0; i < 19; i++) {
+    int cn = C[i][dir]*sgn;
+    if (cn == 0) rho_on += f[i] + TW[i];
+    else if (cn > 0) rho_out += f[i] + TW[i];
+  }
+  double rho, u[3];
+  if (pressure) {
+    rho = bc[3];
+    u[0] = u[1] = u[2] = 0.0;
+    u[dir] = sgn * ((rho_on + 2.0*rho_out) / rho - 1.0);
+  } else {
+    u[0] = bc[0]; u[1] = bc[1]; u[2] = bc[2];
+    rho = (rho_on + 2.0*rho_out) / (1.0 + sgn*u[dir]);
+  }
+  double rhoBar = rho - 1.0, invRho = 1.0 / rho;
+  double j[3] = {rho*u[0], rho*u[1], rho*u[2]};
+  double jSqr = j[0]*j[0] + j[1]*j[1] + j[2]*j[2];
+  for (int i = 1; i < 19; i++) {
+    if (C[i][dir]*sgn < 0) f[i] = f[opp(i)] - feq(opp(i), rhoBar, invRho, j, jSqr) + feq(i, rhoBar, invRho, j, jSqr);
+  }
+  double jf[3] = {0.0, 0.0, 0.0};
+  for (int i = 0; i < 19; i++) { jf[0] += C[i][0]*f[i]; jf[1] += C[i][1]*f[i]; jf[2] += C[i][2]*f[i]; }
+  for (int k = 0; k < 3; k++) {
+    if (k == dir) continue;
+    double diff = 0.5*(jf[k] - j[k]);
+    for (int i = 1; i < 19; i++)
+      if (C[i][dir]*sgn < 0 && C[i][k] != 0) f[i] -= C[i][k]*diff;
+  }
+}
+
 /* MultiBlockLattice3D::collideAndStream (core/hemoCell.cpp:317): collide every node with its
  * dynamics, then stream f_i(x + c_i) <- f_i(x) (Palabos' swap scheme is equivalent to this
  * push).  BounceBack::collide = swap with the opposite population (full-way bounce back).
  * Periodic axes wrap; what leaves a non-periodic face is dropped and what would enter
- * through it is the rest equilibrium (stored value 0). */
-void ora_collide_and_stream(const ora_domain* d, const uint8_t* flags, double* pop,
-                            const double* force, double* scratch) {
+ * through it is the rest equilibrium (stored value 0).
+ * bc_node (may be NULL): per-node boundary values [4][N] = (u_x, u_y, u_z, rho) of the Zou-He nodes. */
+void ora_collide_and_stream_io(const ora_domain* d, const uint8_t* flags, double* pop,
+                               const double* force, double* scratch, const double* bc_node) {
   int64_t N = nnodes(d);
   #pragma omp parallel for schedule(static) if(ora_parallel)
   for (int64_t n = 0; n < N; n++) {
@@ -156,7 +202,12 @@ void ora_collide_and_stream(const ora_domain* d, const uint8_t* flags, double* p
       for (int i = 1; i <= 9; i++) { double t = f[i]; f[i] = f[i+9]; f[i+9] = t; }
     } else {
       for (int k = 0; k < 3; k++) F[k] = force[k*N + n];
-      if (fl >= ORA_VEL_XN) regularized_velocity_complete(f, fl - 2, d->bc_vel[fl - 2]);
+      if (fl >= ORA_ZH_VEL_XN) {
+        double bc[4] = {0.0, 0.0, 0.0, 1.0};
+        if (bc_node) for (int k = 0; k < 4; k++) bc[k] = bc_node[k*N + n];
+        if (fl >= ORA_ZH_PRES_XN) zouhe_complete(f, fl - ORA_ZH_PRES_XN, 1, bc);
+        else zouhe_complete(f, fl - ORA_ZH_VEL_XN, 0, bc);
+      } else if (fl >= ORA_VEL_XN) regularized_velocity_complete(f, fl - 2, d->bc_vel[fl - 2]);
       guo_bgk_collide(f, F, d->omega);
     }
     for (int i = 0; i < 19; i++) pop[i*N + n] = f[i];
@@ -176,11 +227,19 @@ void ora_collide_and_stream(const ora_domain* d, const uint8_t* flags, double* p
   memcpy(pop, scratch, sizeof(double)*19*N);
 }
 
+void ora_collide_and_stream(const ora_domain* d, const uint8_t* flags, double* pop,
+                            const double* force, double* scratch) {
+  ora_collide_and_stream_io(d, flags, pop, force, scratch, NULL);
+}
+
 /* Cell::computeVelocity / computeDensity as used by IBM interpolation
- * (core/hemoCellParticleField.cpp:833) and FluidInfo (helper/fluidInfo.cpp:46):
- * Guo dynamics: u = j/rho + F/2; BounceBack: u = 0, rho = 1; velocity BC: u = wall velocity. */
-void ora_moments(const ora_domain* d, const uint8_t* flags, const double* pop,
-                 const double* force, double* rho_out, double* vel) {
+ * (core/hemoCellParticleField.cpp:833), FluidInfo (helper/fluidInfo.cpp:46) and the pre-inlet velocity
+ * coupling (helper/preInlet.cpp:372):
+ * Guo dynamics: u = j/rho + F/2; BounceBack: u = 0, rho = 1; velocity BC: u = wall velocity;
+ * Zou-He velocity node: the imposed u; Zou-He pressure node: the imposed rho, normal velocity from the
+ * known populations, tangential velocity 0. */
+void ora_moments_io(const ora_domain* d, const uint8_t* flags, const double* pop,
+                    const double* force, double* rho_out, double* vel, const double* bc_node) {
   int64_t N = nnodes(d);
   #pragma omp parallel for schedule(static) if(ora_parallel)
   for (int64_t n = 0; n < N; n++) {
@@ -191,15 +250,33 @@ void ora_moments(const ora_domain* d, const uint8_t* flags, const double* pop,
     }
     double rho = 1.0 + rhoBar, invRho = 1.0/rho;
     uint8_t fl = flags[n];
-    for (int k = 0; k < 3; k++) {
-      double u;
-      if (fl == ORA_BB) u = 0.0;
-      else if (fl >= ORA_VEL_XN) u = d->bc_vel[fl-2][k];
-      else u = j[k]*invRho + 0.5*force[k*N + n];
-      vel[k*N + n] = u;
+    if (fl >= ORA_ZH_PRES_XN) {
+      int o = fl - ORA_ZH_PRES_XN, dir = o / 2, sgn = (o & 1) ? +1 : -1;
+      double rho_on = 0.0, rho_o = 0.0;
+      for (int i = 0; i < 19; i++) {
+        int cn = C[i][dir]*sgn;
+        if (cn == 0) rho_on += pop[i*N + n] + TW[i]; else if (cn > 0) rho_o += pop[i*N + n] + TW[i];
+      }
+      rho = bc_node ? bc_node[3*N + n] : 1.0;
+      for (int k = 0; k < 3; k++) vel[k*N + n] = 0.0;
+      vel[dir*N + n] = sgn * ((rho_on + 2.0*rho_o) / rho - 1.0);
+    } else {
+      for (int k = 0; k < 3; k++) {
+        double u;
+        if (fl == ORA_BB) u = 0.0;
+        else if (fl >= ORA_ZH_VEL_XN) u = bc_node ? bc_node[k*N + n] : 0.0;
+        else if (fl >= ORA_VEL_XN) u = d->bc_vel[fl-2][k];
+        else u = j[k]*invRho + 0.5*force[k*N + n];
+        vel[k*N + n] = u;
+      }
     }
     if (rho_out) rho_out[n] = (fl == ORA_BB) ? 1.0 : rho;
   }
+}
+
+void ora_moments(const ora_domain* d, const uint8_t* flags, const double* pop,
+                 const double* force, double* rho_out, double* vel) {
+  ora_moments_io(d, flags, pop, force, rho_out, vel, NULL);
 }
 
 /* interpolationCoefficientsPhi2 (core/immersedBoundaryMethod.h:62-138), phi2 (:37-41).

@@ -21,7 +21,8 @@
  *                   (i.e. exactly what Palabos holds between collideAndStream calls)
  *   node force      force[d*N + idx], d = 0..2
  *   flags           uint8 per node: 0 fluid, 1 bounce-back, 2..7 velocity plane
- *                   whose OUTWARD normal is -x,+x,-y,+y,-z,+z
+ *                   whose OUTWARD normal is -x,+x,-y,+y,-z,+z; 8..13 Zou-He velocity node,
+ *                   14..19 Zou-He pressure node (same normal order)
  *   particles       AoS xyz: pos[3*p + d]
  */
 #ifndef HEMO_ORACLE_H
@@ -33,7 +34,10 @@ extern "C" {
 #endif
 
 enum { ORA_FLUID = 0, ORA_BB = 1, ORA_VEL_XN = 2, ORA_VEL_XP = 3, ORA_VEL_YN = 4,
-       ORA_VEL_YP = 5, ORA_VEL_ZN = 6, ORA_VEL_ZP = 7 };
+       ORA_VEL_YP = 5, ORA_VEL_ZN = 6, ORA_VEL_ZP = 7,
+       /* Zou-He velocity nodes (per-node velocity) and pressure nodes (per-node density), OUTWARD normal
+        * -x,+x,-y,+y,-z,+z (helper/preInlet.cpp:399-436, pipeflow_with_preinlet.cpp:125-133) */
+       ORA_ZH_VEL_XN = 8, ORA_ZH_VEL_ZP = 13, ORA_ZH_PRES_XN = 14, ORA_ZH_PRES_ZP = 19 };
 
 typedef struct {
   int32_t nx, ny, nz;
@@ -72,6 +76,11 @@ void ora_collide_and_stream(const ora_domain* d, const uint8_t* flags, double* p
                             const double* force, double* scratch /* 19*N */);
 void ora_moments(const ora_domain* d, const uint8_t* flags, const double* pop,
                  const double* force, double* rho /* N or NULL */, double* vel /* 3*N */);
+/* the same with Zou-He velocity / pressure nodes: bc_node [4][N] = (u_x, u_y, u_z, rho) per node (NULL: u = 0, rho = 1) */
+void ora_collide_and_stream_io(const ora_domain* d, const uint8_t* flags, double* pop,
+                               const double* force, double* scratch, const double* bc_node);
+void ora_moments_io(const ora_domain* d, const uint8_t* flags, const double* pop,
+                    const double* force, double* rho, double* vel, const double* bc_node);
 
 /* ---- IBM (core/immersedBoundaryMethod.h:62-138, hemoCellParticleField.cpp:819-863) ---- */
 int ora_ibm_kernel(const ora_domain* d, const uint8_t* flags, const double p[3],

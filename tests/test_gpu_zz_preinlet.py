@@ -1,0 +1,150 @@
+"""GPU parity of SURVEY.md section 8 row f4: Zou-He velocity / pressure nodes with per-node values and the pre-inlet
+coupling (helper/preInlet.cpp, examples/pipeflow_with_preinlet), against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+import oracle as O
+import util as U
+import preinlet_case as PC
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from hemocell_b200 import lib as H
+    return H
+
+
+def _io_flags(nx, ny, nz, axis):
+    """bounce-back duct around `axis`, Zou-He velocity nodes on its low face, pressure nodes on its high face,
+    plus one velocity node and one pressure node of every other orientation inside the fluid"""
+    fl = np.zeros((nx, ny, nz), dtype=np.uint8)
+    n = (nx, ny, nz)
+    for a in range(3):
+        if a == axis:
+            continue
+        sl = [slice(None)] * 3
+        sl[a] = 0; fl[tuple(sl)] = 1
+        sl[a] = n[a] - 1; fl[tuple(sl)] = 1
+    lo = [slice(None)] * 3; lo[axis] = 0
+    hi = [slice(None)] * 3; hi[axis] = n[axis] - 1
+    inner = fl[tuple(lo)] == 0
+    fl[tuple(lo)][inner] = 8 + 2 * axis            # outward normal -axis
+    fl[tuple(hi)][inner] = 14 + 2 * axis + 1       # outward normal +axis
+    for o in range(6):
+        fl[3 + o, 4, 5] = 8 + o
+        fl[4 + o, 6, 3] = 14 + o
+    return fl.reshape(-1)
+
+
+@pytest.mark.parametrize("axis,tau,shape", [(0, 0.8, (20, 12, 10)), (1, 1.0, (14, 18, 12)), (2, 1.3, (12, 10, 22))])
+def test_zouhe_nodes_collide_stream_parity(axis, tau, shape):
+    H = _lib()
+    nx, ny, nz = shape
+    N = nx * ny * nz
+    fl = _io_flags(nx, ny, nz, axis)
+    dom = O.make_domain(nx, ny, nz, (0, 0, 0), tau)
+    rng = np.random.default_rng(21 + axis)
+    pop = U.mask_inflow(dom, U.smooth_state(dom, 12))
+    force = np.ascontiguousarray(1e-5 * rng.standard_normal(3 * N))
+    nodes = np.nonzero(fl >= 8)[0]
+    val = np.column_stack([0.02 * rng.standard_normal((nodes.size, 3)), 1.0 + 2e-3 * rng.standard_normal(nodes.size)])
+    bc = np.zeros((4, N)); bc[3] = 1.0
+    bc[:, nodes] = val.T
+    bc = np.ascontiguousarray(bc.reshape(-1))
+    ctx = U.gpu_context(dom, fl)
+    ctx.set_bc_nodes(nodes, val)
+    ctx.lattice_upload(H.LAT_POP, pop)
+    ctx.lattice_upload(H.LAT_FORCE, force)
+    ref = pop.copy()
+    for step in range(1, 6):
+        if tau == 1.0 and step > 1:
+            ctx.lattice_download(H.LAT_DENSITY)          # a moments pass: the next collision takes the tau = 1 fast path
+        O.collide_and_stream(dom, fl, ref, force, bc_node=bc)
+        ctx.op("collide_stream")
+        if step in (1, 5):
+            U.assert_close(ctx.lattice_download(H.LAT_POP), ref, f"populations after {step} steps (axis {axis})")
+    rho, vel = O.moments(dom, fl, ref, force, bc_node=bc)
+    U.assert_close(ctx.lattice_download(H.LAT_VELOCITY), vel, "velocity field")
+    U.assert_close(ctx.lattice_download(H.LAT_DENSITY), rho, "density field")
+    pick = np.concatenate([nodes[:40], rng.integers(0, N, 60)])
+    U.assert_close(ctx.node_velocity(pick), vel.reshape(3, N)[:, pick].T, "hcg_lattice_node_velocity")
+    ctx.close()
+
+
+def _gpu_pair(c):
+    H = _lib()
+    pre = U.gpu_context(c['domp'], c['flp'], body=PC.BODY)
+    main = U.gpu_context(c['domm'], c['flm'])
+    for ctx in (pre, main):
+        ctx.init_equilibrium(1.0, PC.U0)
+        ctx.set_force_limit(c['par'].f_limit)
+    t = U.gpu_add_type(pre, c['rbc'])
+    pre.add_cells(t, c['cells'], [0, 1])
+    t = U.gpu_add_type(main, c['rbc'])
+    main.reserve_cells(t, 4)
+    main.add_cells(t, np.zeros((0, c['rbc'].V, 3)), np.zeros(0, dtype=np.int64))
+    main.preinlet_map(pre, c['pre_idx'], c['main_idx'])
+    return H, pre, main
+
+
+def _by_id(ctx, H, field):
+    ids, _, alive = ctx.cells_info()
+    a = ctx.cells_download(field).reshape(len(ids), -1, 3)
+    keep = np.nonzero((alive != 0) & (ids >= 0))[0]
+    order = keep[np.argsort(ids[keep])]
+    return ids[order], a[order]
+
+
+def _oracle_by_id(sim, arr):
+    a = arr.reshape(len(sim.cell_id), -1, 3)
+    order = np.argsort(sim.cell_id)
+    return sim.cell_id[order], a[order]
+
+
+def test_preinlet_two_domains_match_the_oracle():
+    """periodic force-driven pre-inlet duct -> Zou-He inlet of the main duct with a pressure outlet, tau = 1, two RBCs in
+    the pre-inlet of which one is handed over at the first step: 30 passes of the main loop of
+    pipeflow_with_preinlet.cpp (iterate both, applyPreInlet) on the GPU vs the oracle"""
+    c = PC.build()
+    opre, omain, cpl = PC.oracle_pair(c)
+    H, pre, main = _gpu_pair(c)
+    steps, handed_o, handed_g = 30, 0, 0
+    for _ in range(steps):
+        handed_o += PC.oracle_step(opre, omain, cpl)
+        pre.iterate(1); main.iterate(1)
+        main.preinlet_apply_velocity()
+        handed_g += main.preinlet_apply_cells(0, float(PC.NXP), c['shift'], PC.SLAB[0], PC.SLAB[1], PC.ID_STRIDE)
+    assert handed_o == handed_g == 1
+    assert main.count()[0] == 1 and pre.count()[0] == 2
+    U.assert_close(pre.lattice_download(H.LAT_POP), opre.pop, "pre-inlet populations", rtol=1e-9, floor=1e-11)
+    U.assert_close(main.lattice_download(H.LAT_POP), omain.pop, "main populations", rtol=1e-9, floor=1e-11)
+    for ctx, sim, name in ((pre, opre, "pre-inlet"), (main, omain, "main")):
+        gi, gp = _by_id(ctx, H, H.P_POS)
+        oi, op = _oracle_by_id(sim, sim.pos)
+        np.testing.assert_array_equal(gi, oi)
+        U.assert_close(gp, op, name + " positions", rtol=1e-11)
+        _, gv = _by_id(ctx, H, H.P_VEL)
+        _, ov = _oracle_by_id(sim, sim.vel)
+        U.assert_close(gv, ov, name + " velocities", rtol=1e-8, floor=1e-10)
+        _, gf = _by_id(ctx, H, H.P_FORCE)
+        _, of = _oracle_by_id(sim, sim.pforce)
+        U.assert_close(gf, of, name + " membrane forces", rtol=1e-6, floor=1e-8)
+    # the inlet nodes carry the pre-inlet's coupling-plane velocity
+    U.assert_close(main.node_velocity(c['main_idx']), opre.node_velocity(c['pre_idx']), "inlet node velocity", rtol=1e-9, floor=1e-11)
+    main.close(); pre.close()
+
+
+def test_preinlet_error_paths():
+    H = _lib()
+    c = PC.build()
+    _, pre, main = _gpu_pair(c)
+    with pytest.raises(H.HcgError):
+        pre.preinlet_apply_velocity()                       # no map on this context
+    with pytest.raises(H.HcgError):
+        main.preinlet_map(pre, [pre.Nl], [0])               # node outside the lattice
+    with pytest.raises(H.HcgError):
+        main.set_bc_nodes([main.Nl], [[0, 0, 0, 1.0]])
+    with pytest.raises(H.HcgError):
+        main.set_flags(np.full(main.Nl, 20, dtype=np.uint8))   # unknown flag
+    main.close(); pre.close()

@@ -1,0 +1,97 @@
+"""CPU checks of the oracle's Zou-He nodes and pre-inlet coupling (the checker of tests/test_gpu_zz_preinlet.py)."""
+import numpy as np
+
+import oracle as O
+import preinlet_case as PC
+
+
+def test_zouhe_channel_conserves_mass_and_meets_its_boundary_values():
+    """velocity inlet (parabolic profile) + pressure outlet (rho = 1) on a bounce-back channel: at steady state the
+    mass flux is the same through every interior plane, the outlet density is the imposed one, the inlet node
+    velocity is the imposed one, and the pressure falls monotonically along the channel"""
+    nx, ny, nz = 24, 11, 4
+    dom = O.make_domain(nx, ny, nz, (0, 0, 1), 0.8)
+    N = nx * ny * nz
+    fl = np.zeros((nx, ny, nz), np.uint8)
+    fl[:, 0, :] = 1; fl[:, -1, :] = 1
+    fl[0, 1:-1, :] = 8; fl[-1, 1:-1, :] = 15
+    bc = np.zeros((4, nx, ny, nz)); bc[3] = 1.0
+    y = np.arange(ny)
+    prof = 0.02 * 4 * (y - 0.5) * (ny - 1.5 - y) / (ny - 2) ** 2
+    bc[0, 0, :, :] = prof[:, None]
+    bc = np.ascontiguousarray(bc.reshape(-1)); fl = np.ascontiguousarray(fl.reshape(-1))
+    pop = O.init_equilibrium(dom); force = np.zeros(3 * N)
+    for _ in range(2500):
+        O.collide_and_stream(dom, fl, pop, force, bc_node=bc)
+    rho, vel = O.moments(dom, fl, pop, force, bc_node=bc)
+    u = vel.reshape(3, nx, ny, nz); rho = rho.reshape(nx, ny, nz)
+    flux = np.array([(rho[x, 1:-1, 0] * u[0, x, 1:-1, 0]).sum() for x in range(1, nx)])
+    assert np.all(np.abs(flux - flux[0]) < 1e-7 * abs(flux[0]))      # steady state: the same flux through every plane
+    assert abs(flux[0] - prof[1:-1].sum()) < 0.02 * prof[1:-1].sum()      # inlet density is within 2 % of 1
+    np.testing.assert_array_equal(u[0, 0, 1:-1, 0], prof[1:-1])
+    np.testing.assert_array_equal(rho[-1, 1:-1, :], 1.0)
+    assert np.all(np.abs(u[1:, -1]) == 0.0)                              # no tangential velocity on the outlet
+    mid = rho[1:, ny // 2, 0]
+    assert np.all(np.diff(mid) < 0) and mid[0] > 1.005
+
+
+def test_zouhe_completion_gives_exact_moments():
+    """after the completion + a collision without force, density and momentum of a Zou-He node are the imposed
+    ones (BGK conserves them), for every orientation"""
+    rng = np.random.default_rng(5)
+    n = 5
+    dom = O.make_domain(n, n, n, (0, 0, 0), 0.9)
+    N = n ** 3
+    C = np.array([[0,0,0],[-1,0,0],[0,-1,0],[0,0,-1],[-1,-1,0],[-1,1,0],[-1,0,-1],[-1,0,1],[0,-1,-1],[0,-1,1],
+                  [1,0,0],[0,1,0],[0,0,1],[1,1,0],[1,-1,0],[1,0,1],[1,0,-1],[0,1,1],[0,1,-1]])
+    centre = 2 + n * (2 + n * 2)
+    for o in range(6):
+        for pressure in (0, 1):
+            fl = np.zeros(N, np.uint8); fl[centre] = (14 if pressure else 8) + o
+            pop = O.init_equilibrium(dom, 1.0, (0.01, -0.02, 0.015)) + 1e-4 * rng.standard_normal(19 * N)
+            bc = np.zeros((4, N)); bc[3] = 1.0
+            bc[:, centre] = (0.03, -0.01, 0.02, 1.004)
+            before = pop.reshape(19, N)[:, centre].copy()
+            O.collide_and_stream(dom, fl, pop, np.zeros(3 * N), bc_node=np.ascontiguousarray(bc.reshape(-1)))
+            # gather the post-collision populations of the centre node from where they streamed to
+            p = pop.reshape(19, n, n, n)
+            f = np.array([p[q, 2 + C[q, 0], 2 + C[q, 1], 2 + C[q, 2]] for q in range(19)])
+            rho = 1.0 + f.sum(); j = f @ C
+            d, sgn = o // 2, (1 if o & 1 else -1)
+            if pressure:
+                assert abs(rho - 1.004) < 1e-14
+                for k in range(3):
+                    if k != d:
+                        assert abs(j[k]) < 1e-15
+                known = [q for q in range(19) if C[q, d] * sgn >= 0]
+                rho_on = sum(before[q] + (1/3 if q == 0 else 1/18 if (C[q] ** 2).sum() == 1 else 1/36) for q in known if C[q, d] == 0)
+                rho_out = sum(before[q] + (1/18 if (C[q] ** 2).sum() == 1 else 1/36) for q in known if C[q, d] * sgn > 0)
+                assert abs(j[d] / rho - sgn * ((rho_on + 2 * rho_out) / 1.004 - 1.0)) < 1e-14
+            else:
+                assert np.all(np.abs(j / rho - np.array([0.03, -0.01, 0.02])) < 1e-14)
+
+
+def test_preinlet_handover_rule_and_coupling():
+    c = PC.build()
+    pre, main, cpl = PC.oracle_pair(c)
+    handed = []
+    for it in range(12):
+        n = PC.oracle_step(pre, main, cpl)
+        if n:
+            handed.append((it, n))
+    # cell 0's periodic image lies inside the slab from the start: handed over once, at the first step, under id 0 + 1*stride
+    assert handed == [(0, 1)]
+    assert list(main.cell_id) == [0 + PC.ID_STRIDE] and list(pre.cell_id) == [0, 1]
+    # the copy starts at the pre-inlet cell's position in main coordinates (one lap ahead)
+    assert main.pos.shape == (c['rbc'].V, 3)
+    d = main.pos.mean(0) - (pre.pos[:c['rbc'].V].mean(0) + np.array([PC.NXP - PC.XC, 0, 0]))
+    assert np.all(np.abs(d) < 0.05)          # they drift apart slowly (different flow fields), not by a lattice shift
+    # inlet nodes carry the pre-inlet's velocity of the coupling plane
+    b = main.bc_node.reshape(4, main.N)
+    np.testing.assert_array_equal(b[0:3, c['main_idx']].T, pre.node_velocity(c['pre_idx']))
+    assert b[0, c['main_idx']].max() > 0.015
+    assert np.isfinite(main.pop).all() and np.isfinite(pre.pop).all()
+    # a second lap hands the same cell over again under a new id
+    V = c['rbc'].V
+    pre.pos[:V, 0] -= PC.NXP                 # as if the cell had gone round once more against the flow direction ...
+    assert cpl.apply_cells() == 1 and sorted(main.cell_id) == [2, 4]
