@@ -10,6 +10,7 @@
 //     (host coordinated like the multi-GPU migration of csrc/multi.cu: bounding boxes -> host -> pack -> copy -> unpack).
 #include "ctx.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <algorithm>
 
 struct PreInletState {
@@ -194,7 +195,7 @@ hcg_status hcg_preinlet_apply_cells(hcg_ctx* c, int32_t axis, double period, con
     dst.push_back(slot); src_ok.push_back(src[q]); lap_ok.push_back(lap[q]);
     off.push_back(off.back() + th.d.V);
     for (int d = 0; d < 3; d++) sh.push_back(shift[d] + (d == axis ? lap[q]*period : 0.0));
-    c->h_cell_id[slot] = pre->h_cell_id[src[q]] + lap[q]*id_stride;
+    c->h_cell_id[slot] = pre->h_cell_id[src[q]] + std::llabs(lap[q])*id_stride;   // (ids stay non-negative: -1 marks a free slot)
     p->last_lap[src[q]] = lap[q];
   }
   const int n = (int)dst.size();

@@ -93,6 +93,11 @@ class GpuLattice {
   bool created_periodic[3] = {false, false, false};
   bool has_cells = false;
   int generation = 0;                         // bumped whenever a new device context is created
+  std::map<int64_t, std::array<double, 4>> bcn;   // per-node (u, rho) of the Zou-He velocity / pressure nodes, keyed by global node index
+  bool bcn_dirty = false;
+  bool solo = false;                          // a single-rank context whatever the launcher says (the pre-inlet domain)
+  int device_override = -1;
+  GpuLattice* companion = nullptr;            // the pre-inlet lattice that warms up and iterates along with this one
 
   GpuLattice(int nx_, int ny_, int nz_, double omega_) : nx(nx_), ny(ny_), nz(nz_), omega(omega_), flags((size_t)nx_*ny_*nz_, HCG_FLUID) {
     memset(bc, 0, sizeof(bc));
@@ -100,8 +105,8 @@ class GpuLattice {
   ~GpuLattice() { if (ctx) hcg_destroy(ctx); }
 
   int64_t idx(int x, int y, int z) const { return (int64_t)z + (int64_t)nz*((int64_t)y + (int64_t)ny*x); }
-  int rank() const { return plb::global::mpi().getRank(); }
-  int size() const { return plb::global::mpi().getSize(); }
+  int rank() const { return solo ? 0 : plb::global::mpi().getRank(); }
+  int size() const { return solo ? 1 : plb::global::mpi().getSize(); }
   // x-slab of this rank (hcg_slab: the first nx % size ranks own one plane more)
   int nxl() const { int32_t x0, n; hcg_slab(nx, rank(), size(), &x0, &n); return n; }
   int x0() const { int32_t x0, n; hcg_slab(nx, rank(), size(), &x0, &n); return x0; }
@@ -117,7 +122,7 @@ class GpuLattice {
     d.nx = nx; d.ny = ny; d.nz = nz;
     for (int k = 0; k < 3; k++) d.periodic[k] = periodic[k];
     d.tau = 1.0/omega;
-    d.device = plb::global::mpi().getLocalRank();
+    d.device = device_override >= 0 ? device_override : plb::global::mpi().getLocalRank();
     d.rank = rank(); d.n_ranks = size();
     hcg_status s = hcg_create(&d, &ctx);
     if (s != HCG_OK) fatal(std::string("(HemoCell) (GPU) cannot create the device context: ") + hcg_last_error(ctx));
@@ -132,10 +137,9 @@ class GpuLattice {
     ck(ctx, hcg_lattice_set_flags(ctx, flags.data() + (int64_t)x0()*P), "hcg_lattice_set_flags");
     for (int o = 0; o < 6; o++) ck(ctx, hcg_lattice_set_bc_velocity(ctx, o, bc[o]), "hcg_lattice_set_bc_velocity");
     flags_dirty = false;
-    eq_pending = true; body_pending = true;
+    eq_pending = true; body_pending = true; bcn_dirty = !bcn.empty();
     flush();
-    global.statistics.setDeviceTimers(ctx);
-    hcg_timers_enable(ctx, 1);
+    if (!solo) { global.statistics.setDeviceTimers(ctx); hcg_timers_enable(ctx, 1); }
   }
   void flush() {
     if (!ctx) return;
@@ -144,6 +148,13 @@ class GpuLattice {
       ck(ctx, hcg_lattice_set_flags(ctx, flags.data() + (int64_t)x0()*P), "hcg_lattice_set_flags");
       for (int o = 0; o < 6; o++) ck(ctx, hcg_lattice_set_bc_velocity(ctx, o, bc[o]), "hcg_lattice_set_bc_velocity");
       flags_dirty = false;
+    }
+    if (bcn_dirty) {
+      const int64_t P = (int64_t)ny*nz, lo = (int64_t)x0()*P, hi = lo + (int64_t)nxl()*P;
+      std::vector<int64_t> idx; std::vector<double> val;
+      for (auto& kv : bcn) if (kv.first >= lo && kv.first < hi) { idx.push_back(kv.first - lo); val.insert(val.end(), kv.second.begin(), kv.second.end()); }
+      ck(ctx, hcg_lattice_set_bc_nodes(ctx, (int64_t)idx.size(), idx.data(), val.data()), "hcg_lattice_set_bc_nodes");
+      bcn_dirty = false;
     }
     if (eq_pending) { ck(ctx, hcg_lattice_init_equilibrium(ctx, eq_rho, eq_u), "hcg_lattice_init_equilibrium"); eq_pending = false; }
     if (body_pending) {
@@ -516,6 +527,7 @@ HemoCell::HemoCell(char* configFileName, int argc, char* argv[]) {
   global.statistics.start();
 }
 HemoCell::~HemoCell() {
+  delete preInlet; preInlet = nullptr;
   delete cellfields; delete cfg; delete lattice;
   global.statistics.setDeviceTimers(nullptr);
   global.hemoCellInitialized = false;
@@ -539,6 +551,12 @@ void HemoCell::registerCellType(HemoCellField* f) {
 }
 // cell types go to the device when it is first needed (the periodicity may be toggled until then,
 // which re-creates the context: hemocell.setSystemPeriodicity comes after addCellType in the case files)
+static hcg_celltype device_celltype(HemoCellField* f) {
+  hcg_celltype t = f->impl->tables.c;
+  if (auto* m = dynamic_cast<RbcHighOrderModel*>(f->mechanics)) { t.k_volume = m->k_volume; t.k_area = m->k_area; t.k_link = m->k_link; t.k_bend = m->k_bend; t.eta_m = m->eta_m; }
+  else if (auto* m2 = dynamic_cast<PltSimpleModel*>(f->mechanics)) { t.k_volume = m2->k_volume; t.k_area = m2->k_area; t.k_link = m2->k_link; t.k_bend = m2->k_bend; t.eta_m = m2->eta_m; }
+  return t;
+}
 static void upload_celltypes(HemoCell& h) {
   hcg_ctx* c = h.ctx();
   const int gen = h.lattice->gpu()->generation;
@@ -609,6 +627,7 @@ void HemoCell::initializeLattice(const plb::MultiBlockManagement3D& management) 
   hlog << "(HemoCell) Using default domain management." << endl;
   lattice = new plb::MultiBlockLattice3D<T, DESCRIPTOR>(management, nullptr, nullptr, nullptr,
                                                         new plb::GuoExternalForceBGKdynamics<T, DESCRIPTOR>(1.0/param::tau));
+  if (preInlet) preInlet->createLattice(1.0/param::tau);      // core/hemoCell.cpp:476-570: the pre-inlet's own lattice
 }
 
 // settings that live in host-side knobs until the device needs them
@@ -622,6 +641,16 @@ void HemoCell::pushSettings() {
   ck(c, hcg_set_wall_repulsion(c, boundaryRepulsionEnabled, cellfields->boundaryRepulsionConstant,
                                boundaryRepulsionEnabled ? cellfields->boundaryRepulsionCutoff : 1.0), "hcg_set_wall_repulsion");
   ck(c, hcg_set_iteration(c, iter), "hcg_set_iteration");
+  if (preInlet && preInlet->pre) {                            // the pre-inlet ranks of the reference run the same case file: same knobs
+    hcg_ctx* q = preInlet->preCtx();
+    ck(q, hcg_set_timescales(q, (int)cellfields->particleVelocityUpdateTimescale, (int)cellfields->repulsionTimescale,
+                             (int)cellfields->boundaryRepulsionTimescale), "hcg_set_timescales");
+    for (auto* f : cellfields->cellFields) ck(q, hcg_set_material_timescale(q, f->impl->device_ctype, (int)f->timescale), "hcg_set_material_timescale");
+    ck(q, hcg_set_repulsion(q, repulsionEnabled, cellfields->repulsionConstant, repulsionEnabled ? cellfields->repulsionCutoff : 1.0), "hcg_set_repulsion");
+    ck(q, hcg_set_wall_repulsion(q, boundaryRepulsionEnabled, cellfields->boundaryRepulsionConstant,
+                                 boundaryRepulsionEnabled ? cellfields->boundaryRepulsionCutoff : 1.0), "hcg_set_wall_repulsion");
+    ck(q, hcg_set_iteration(q, iter), "hcg_set_iteration");
+  }
 }
 
 void HemoCell::loadParticles() {
@@ -639,6 +668,26 @@ void HemoCell::loadParticles() {
     std::vector<T> pos;
     std::vector<int64_t> ids = host::placeCells(f->impl->tables.mesh, rows, param::dx, g->nx, g->ny, g->nz, g->flags.data(),
                                                 f->minimumDistanceFromSolid, cellid, pos);
+    if (preInlet && preInlet->pre) {
+      // the same .pos file seeds the pre-inlet (rows in its local coordinates); the main domain keeps spare slots for the cells it will feed in
+      ck(c, hcg_cells_reserve(c, f->impl->device_ctype, (int64_t)rows.size() + 64), "hcg_cells_reserve");
+      GpuLattice* q = preInlet->pre;
+      hcg_ctx* qc = preInlet->preCtx();
+      hcg_celltype t = device_celltype(f);
+      int32_t qid = -1;
+      ck(qc, hcg_celltype_add(qc, &t, &qid), "hcg_celltype_add");
+      if (qid != f->impl->device_ctype) fatal("(PreInlet) cell types of the pre-inlet and the main domain are out of step");
+      ck(qc, hcg_set_force_limit(qc, param::f_limit), "hcg_set_force_limit");
+      std::vector<std::array<T, 6>> prows = rows;
+      const T um = param::dx*1e6;
+      for (auto& r : prows) { r[0] -= preInlet->location.x0*um; r[1] -= preInlet->location.y0*um; r[2] -= preInlet->location.z0*um; }
+      std::vector<T> ppos;
+      std::vector<int64_t> pids = host::placeCells(f->impl->tables.mesh, prows, param::dx, q->nx, q->ny, q->nz, q->flags.data(),
+                                                   f->minimumDistanceFromSolid, cellid, ppos);
+      q->has_cells = q->has_cells || !pids.empty();
+      ck(qc, hcg_cells_add(qc, qid, (int64_t)pids.size(), pids.data(), ppos.data()), "hcg_cells_add");
+      hlog << "(readPositionsBloodCells) " << pids.size() << " " << f->name << " cells placed inside the pre-inlet." << endl;
+    }
     cellid += (int64_t)rows.size();
     g->has_cells = g->has_cells || !ids.empty();
     ck(c, hcg_cells_add(c, f->impl->device_ctype, (int64_t)ids.size(), ids.data(), pos.data()), "hcg_cells_add");
@@ -665,11 +714,13 @@ void HemoCell::iterate() {
   if (!sanityCheckDone) sanityCheck();
   hcg_ctx* c = ctx();
   ck(c, hcg_iterate(c, 1), "hcg_iterate");
+  if (preInlet) preInlet->iterate();                          // asynchronous, on the pre-inlet context's own stream (or GPU)
   iter++;
 }
 
 void HemoCell::saveCheckPoint() {
   hlog << "(HemoCell) (Saving Functions) Saving Checkpoint at timestep " << iter << endl;
+  if (preInlet && preInlet->pre) hlog << "(HemoCell) (Saving Functions) WARNING: the pre-inlet domain (PRE_lattice / PRE_particleField of the reference) is not part of this checkpoint" << endl;
   hcg_ctx* c = ctx();
   GpuLattice* g = lattice->gpu();
   const std::string dir = global.checkpointDirectory;
@@ -1233,6 +1284,247 @@ FluidStatistics FluidInfo::calculateVelocityStatistics(HemoCell* h) {
 }  // namespace hemo
 
 // ====================================================================================================
+// PreInlet (helper/preInlet.cpp): the periodic pre-inlet as a second device context of the same process
+// ====================================================================================================
+namespace hemo {
+using plb::Box3D;
+
+PreInlet::PreInlet(HemoCell* hemocell_, plb::MultiScalarField3D<int>* flagMatrix_) : hemocell(hemocell_), flagMatrix(flagMatrix_) {
+  preinlet_length = (*hemocell->cfg)["preInlet"]["parameters"]["lengthN"].read<int>();
+}
+PreInlet::~PreInlet() {
+  if (hemocell && hemocell->lattice && hemocell->lattice->gpu()->companion == pre) hemocell->lattice->gpu()->companion = nullptr;
+  delete pre;
+}
+hcg_ctx* PreInlet::preCtx() {
+  if (!pre) fatal("(PreInlet) the pre-inlet lattice does not exist yet: call preInletFromSlice / autoPreinletFromBoundary before initializeLattice");
+  pre->materialize();
+  return pre->ctx;
+}
+
+// helper/preInlet.cpp:463-560 / 592-700: bounding box of the fluid nodes of the slice, one node of solid around it, preinlet_length
+// planes outwards.  (The transverse extent is always clipped to the flag matrix here; the reference clips it to the lattice when one exists.)
+void PreInlet::locate(Box3D slice) {
+  inflow_length = (*hemocell->cfg)["domain"]["particleEnvelope"].read<int>();
+  const Box3D bb = flagMatrix->getBoundingBox();
+  bool found = false; Box3D d;
+  for (plint x = std::max(slice.x0, bb.x0); x <= std::min(slice.x1, bb.x1); x++)
+    for (plint y = std::max(slice.y0, bb.y0); y <= std::min(slice.y1, bb.y1); y++)
+      for (plint z = std::max(slice.z0, bb.z0); z <= std::min(slice.z1, bb.z1); z++) {
+        if (!flagMatrix->get(x, y, z)) continue;
+        if (!found) { d = Box3D(x, x, y, y, z, z); found = true; }
+        else { d.x0 = std::min(d.x0, x); d.x1 = std::max(d.x1, x); d.y0 = std::min(d.y0, y); d.y1 = std::max(d.y1, y); d.z0 = std::min(d.z0, z); d.z1 = std::max(d.z1, z); }
+      }
+  if (!found) { hlog << "(PreInlet) no preinlet found, is it in the correct location?" << endl; exit(1); }
+  location = d.enlarge(1);
+  switch (direction) {
+    case Direction::Xneg: location.x0 -= preinlet_length; break;
+    case Direction::Yneg: location.y0 -= preinlet_length; break;
+    case Direction::Zneg: location.z0 -= preinlet_length; break;
+    case Direction::Xpos: location.x1 += preinlet_length; break;
+    case Direction::Ypos: location.y1 += preinlet_length; break;
+    case Direction::Zpos: location.z1 += preinlet_length; break;
+  }
+  if (!hemocell->lattice) hlog << "(PreInlet) preInlet located before the lattice exists: transverse extent clipped to the flag matrix" << endl;
+  if (axis() != 0) { location.x0 = std::max(location.x0, bb.x0); location.x1 = std::min(location.x1, bb.x1); }
+  if (axis() != 1) { location.y0 = std::max(location.y0, bb.y0); location.y1 = std::min(location.y1, bb.y1); }
+  if (axis() != 2) { location.z0 = std::max(location.z0, bb.z0); location.z1 = std::min(location.z1, bb.z1); }
+}
+
+void PreInlet::preInletFromSlice(Direction direction_, Box3D boundary) {
+  direction = direction_; initialized = true;
+  const bool flat = axis() == 0 ? boundary.x0 == boundary.x1 : (axis() == 1 ? boundary.y0 == boundary.y1 : boundary.z0 == boundary.z1);
+  if (!flat) { hlog << "Not a flat slice, refusing to create preInlet" << endl; exit(1); }
+  locate(boundary);
+}
+
+void PreInlet::autoPreinletFromBoundary(Direction dir_) {
+  direction = dir_; initialized = true;
+  Box3D f = flagMatrix->getBoundingBox();                       // the second plane from the face the pre-inlet attaches to (helper/preInlet.cpp:594-618)
+  switch (direction) {
+    case Direction::Xneg: f.x1 = f.x0 + 1; f.x0 = f.x1; break;
+    case Direction::Yneg: f.y1 = f.y0 + 1; f.y0 = f.y1; break;
+    case Direction::Zneg: f.z1 = f.z0 + 1; f.z0 = f.z1; break;
+    case Direction::Xpos: f.x0 = f.x1 - 1; f.x1 = f.x0; break;
+    case Direction::Ypos: f.y0 = f.y1 - 1; f.y1 = f.y0; break;
+    case Direction::Zpos: f.z0 = f.z1 - 1; f.z1 = f.z0; break;
+  }
+  locate(f);
+}
+
+void PreInlet::createLattice(double omega) {
+  if (!initialized) fatal("(PreInlet) preInletFromSlice / autoPreinletFromBoundary must be called before initializeLattice");
+  if (plb::global::mpi().getSize() > 1) fatal("(PreInlet) the pre-inlet runs inside a single process next to the main domain; launch one rank");
+  delete pre;
+  pre = new GpuLattice((int)location.getNx(), (int)location.getNy(), (int)location.getNz(), omega);
+  pre->solo = true;
+  if (const char* e = getenv("HEMOCELL_PREINLET_DEVICE")) pre->device_override = atoi(e);
+  hemocell->lattice->gpu()->companion = pre;
+  hlog << "(PreInlet) pre-inlet lattice " << pre->nx << " x " << pre->ny << " x " << pre->nz << " at (" << location.x0 << ", " << location.y0
+       << ", " << location.z0 << "), as a second device context of this process" << endl;
+}
+
+// helper/preInlet.cpp:399-436: the plane of the main domain the pre-inlet feeds becomes Zou-He velocity nodes (fluid nodes only)
+void PreInlet::initializePreInletVelocityBoundary() {
+  const Box3D bb = flagMatrix->getBoundingBox();
+  Box3D d(std::max(bb.x0, location.x0), std::min(bb.x1, location.x1), std::max(bb.y0, location.y0), std::min(bb.y1, location.y1),
+          std::max(bb.z0, location.z0), std::min(bb.z1, location.z1));
+  switch (direction) {
+    case Direction::Xneg: d.x0 = d.x1; break;  case Direction::Yneg: d.y0 = d.y1; break;  case Direction::Zneg: d.z0 = d.z1; break;
+    case Direction::Xpos: d.x1 = d.x0; break;  case Direction::Ypos: d.y1 = d.y0; break;  case Direction::Zpos: d.z1 = d.z0; break;
+  }
+  fluidInlet = d;
+  // outward normal of the inlet plane: towards the pre-inlet.  orientation index 0..5 = -x +x -y +y -z +z
+  const int orientation = 2*axis() + ((int)direction % 2 == 0 ? 1 : 0);      // Xpos -> +x, Xneg -> -x, ...
+  GpuLattice* g = hemocell->lattice->gpu();
+  const double zero[3] = {0, 0, 0};
+  for (plint x = d.x0; x <= d.x1; x++) for (plint y = d.y0; y <= d.y1; y++) for (plint z = d.z0; z <= d.z1; z++) {
+    if (flagMatrix->get(x, y, z) != 1) continue;
+    const Box3D point(x, x, y, y, z, z);
+    gpu_lattice_zouhe(g, point, 0, orientation);
+    gpu_lattice_boundary_velocity(g, point, zero);
+  }
+}
+void PreInlet::initializePreInletParticleBoundary() {}      // (the reference maps MPI senders to receivers here)
+
+// helper/preInlet.cpp:950-993 on the pre-inlet side: solid wherever the inlet cross-section is solid, periodic along the flow
+void PreInlet::createBoundary() {
+  if (!pre) fatal("(PreInlet) createBoundary before initializeLattice");
+  const Box3D bb = flagMatrix->getBoundingBox();
+  for (int lx = 0; lx < pre->nx; lx++) for (int ly = 0; ly < pre->ny; ly++) for (int lz = 0; lz < pre->nz; lz++) {
+    plint gx = lx + location.x0, gy = ly + location.y0, gz = lz + location.z0;
+    if (axis() == 0) gx = fluidInlet.x0; else if (axis() == 1) gy = fluidInlet.y0; else gz = fluidInlet.z0;
+    const bool inside = gx >= bb.x0 && gx <= bb.x1 && gy >= bb.y0 && gy <= bb.y1 && gz >= bb.z0 && gz <= bb.z1;
+    const bool fluid = inside && flagMatrix->get(gx, gy, gz) != 0;
+    if (!fluid) pre->flags[pre->idx(lx, ly, lz)] = HCG_BOUNCEBACK;
+  }
+  pre->touchFlags();
+  pre->periodic[0] = pre->periodic[1] = pre->periodic[2] = false;
+  pre->periodic[axis()] = true;
+}
+
+// helper/preInlet.cpp:756-804: Poiseuille force for the Reynolds number of config.xml on the pre-inlet's cross-section
+void PreInlet::calculateDrivingForce() {
+  if (!pre) fatal("(PreInlet) calculateDrivingForce before initializeLattice");
+  const double re = (*hemocell->cfg)["preInlet"]["parameters"]["Re"].read<T>();
+  const int n[3] = {pre->nx, pre->ny, pre->nz};
+  const int plane = ((int)direction % 2 == 1) ? 2 : n[axis()] - 1 - 2;        // N: third plane from the low end, P: from the high end
+  plint fluidArea = 0;
+  for (int lx = 0; lx < pre->nx; lx++) for (int ly = 0; ly < pre->ny; ly++) for (int lz = 0; lz < pre->nz; lz++) {
+    const int l[3] = {lx, ly, lz};
+    if (l[axis()] != plane) continue;
+    if (pre->flags[pre->idx(lx, ly, lz)] == HCG_FLUID) fluidArea++;
+  }
+  const T pipe_radius = std::sqrt(fluidArea/PI);
+  hlog << "(Parameters) Your preInlet pipe has a calculated radius of " << pipe_radius << " LU, assuming a perfect circle" << std::endl;
+  const T u_lbm_max = re*param::nu_lbm/(pipe_radius*2);
+  drivingForce = 8*param::nu_lbm*(u_lbm_max*0.5)/pipe_radius/pipe_radius;
+}
+void PreInlet::applyForce(double f) {
+  if (!pre) return;
+  double v[3] = {0, 0, 0};
+  v[axis()] = ((int)direction % 2 == 1) ? f : -f;             // N: the pre-inlet sits on the negative side and pushes in +, P: the other way
+  gpu_lattice_external_vector(pre, Box3D(0, pre->nx - 1, 0, pre->ny - 1, 0, pre->nz - 1), v);
+}
+void PreInlet::setDrivingForce() { applyForce(drivingForce); }
+
+double PreInlet::average(vector<double> values) {
+  double s = 0.0;
+  for (double v : values) s += v;
+  return s/(double)values.size();
+}
+// helper/preInlet.cpp:820-857: "<time> <normalised velocity>" lines of the pulse file
+bool PreInlet::readNormalizedVelocities() {
+  const std::string name = (*hemocell->cfg)["preInlet"]["parameters"]["pulseFileName"].read<std::string>();
+  std::ifstream in(name);
+  if (!in.is_open()) { cout << "*** WARNING! pulsatility data file " << name << " does not exist!" << endl; return false; }
+  double t, v;
+  while (in >> t >> v) { normalizedVelocityTimes.push_back(t); normalizedVelocityValues.push_back(v); }
+  if (normalizedVelocityTimes.size() < 2) return false;
+  average_vel = average(normalizedVelocityValues);
+  pulseEndTime = normalizedVelocityTimes.back();
+  try { pFrequency = (*hemocell->cfg)["preInlet"]["parameters"]["pFrequency"].read<double>(); }
+  catch (const std::invalid_argument&) { pFrequency = 1.0/pulseEndTime; }
+  return true;
+}
+// piecewise-linear look-up, clamped at both ends unless `extrapolate` (helper/preInlet.cpp:860-890)
+double PreInlet::interpolate(vector<double>& xData, vector<double>& yData, double x, bool extrapolate) {
+  const int n = (int)xData.size();
+  int i = 0;
+  if (x >= xData[n - 2]) i = n - 2; else while (x > xData[i + 1]) i++;
+  double yl = yData[i], yr = yData[i + 1];
+  if (!extrapolate) { if (x < xData[i]) yr = yl; if (x > xData[i + 1]) yl = yr; }
+  return yl + (yr - yl)/(xData[i + 1] - xData[i])*(x - xData[i]);
+}
+void PreInlet::setDrivingForceTimeDependent(double t) {
+  t = std::fmod(t*pFrequency*pulseEndTime, pulseEndTime);     // position inside the (periodic) pulse
+  const double v = interpolate(normalizedVelocityTimes, normalizedVelocityValues, t, false);
+  applyForce(v/average_vel*drivingForce);
+}
+
+void PreInlet::iterate() {
+  if (!pre) return;
+  hcg_ctx* q = preCtx();
+  ck(q, hcg_iterate(q, 1), "hcg_iterate (pre-inlet)");
+}
+
+// node pairs of the coupling plane: fluid nodes of the inlet plane <-> the same nodes in the pre-inlet's local coordinates
+void PreInlet::coupleNodes() {
+  GpuLattice* g = hemocell->lattice->gpu();
+  std::vector<int64_t> pi, mi;
+  const Box3D& d = fluidInlet;
+  for (plint x = d.x0; x <= d.x1; x++) for (plint y = d.y0; y <= d.y1; y++) for (plint z = d.z0; z <= d.z1; z++) {
+    const uint8_t f = g->flags[g->idx((int)x, (int)y, (int)z)];
+    if (f < HCG_ZH_VEL_XN || f > HCG_ZH_VEL_ZP) continue;
+    const int lx = (int)(x - location.x0), ly = (int)(y - location.y0), lz = (int)(z - location.z0);
+    if (pre->flags[pre->idx(lx, ly, lz)] != HCG_FLUID) continue;
+    mi.push_back(g->idx((int)x, (int)y, (int)z)); pi.push_back(pre->idx(lx, ly, lz));
+  }
+  hcg_ctx* c = hemocell->ctx();
+  ck(c, hcg_preinlet_map(c, preCtx(), (int64_t)mi.size(), pi.data(), mi.data()), "hcg_preinlet_map");
+  hlog << "(PreInlet) " << mi.size() << " inlet nodes coupled to the pre-inlet" << endl;
+  coupled = true;
+}
+
+// helper/preInlet.cpp:344-397
+void PreInlet::applyPreInletVelocityBoundary() {
+  if (!pre) return;
+  // what the pre-inlet ranks of the reference do between iterate() and applyPreInlet() (`if (hemocell.partOfpreInlet) preInlet->setDrivingForce()`)
+  if (!normalizedVelocityTimes.empty()) setDrivingForceTimeDependent(hemocell->iter*param::dt); else setDrivingForce();
+  if (!coupled) coupleNodes();
+  hcg_ctx* c = hemocell->ctx();
+  ck(c, hcg_preinlet_apply_velocity(c), "hcg_preinlet_apply_velocity");
+}
+
+// helper/preInlet.cpp:255-342, in whole cells (include/hemocell_gpu.h: hcg_preinlet_apply_cells)
+void PreInlet::applyPreInletParticleBoundary() {
+  if (!pre || !hemocell->cellfields || hemocell->cellfields->size() == 0) return;
+  if (!coupled) coupleNodes();
+  static int every = -1;
+  if (every < 0) { const char* e = getenv("HEMOCELL_PREINLET_EVERY"); every = e ? std::max(1, atoi(e)) : 1; }
+  if (hemocell->iter % (unsigned)every != 0) return;
+  const int a = axis();
+  const double inlet = a == 0 ? fluidInlet.x0 : (a == 1 ? fluidInlet.y0 : fluidInlet.z0);
+  const bool neg = (int)direction % 2 == 1;                     // pre-inlet on the negative side: the slab lies on the positive side of the inlet plane
+  const double lo = neg ? inlet : inlet - inflow_length, hi = neg ? inlet + inflow_length : inlet;
+  const double shift[3] = {(double)location.x0, (double)location.y0, (double)location.z0};
+  const double period = a == 0 ? pre->nx : (a == 1 ? pre->ny : pre->nz);
+  int64_t n = 0;
+  hcg_ctx* c = hemocell->ctx();
+  ck(c, hcg_preinlet_apply_cells(c, a, period, shift, lo, hi, std::max<plint>(1, hemocell->cellfields->number_of_cells), &n), "hcg_preinlet_apply_cells");
+  cellsHandedOver += n;
+  if (n) { hemocell->lattice->gpu()->has_cells = true; hlog << "(PreInlet) iteration " << hemocell->iter << ": " << n << " cell(s) handed over to the main domain (" << cellsHandedOver << " so far)" << endl; }
+}
+
+// helper/genericFunctions.cpp:138-163: bounce-back wherever the flag matrix is solid (main domain only)
+void boundaryFromFlagMatrix(plb::MultiBlockLattice3D<T, DESCRIPTOR>* fluid, plb::MultiScalarField3D<int>* flagMatrix, bool partOfpreInlet) {
+  if (partOfpreInlet) return;
+  plb::defineDynamics(*fluid, *flagMatrix, flagMatrix->getBoundingBox(), new plb::BounceBack<T, DESCRIPTOR>(1.), 0);
+}
+
+}  // namespace hemo
+
+// ====================================================================================================
 // plb:: shim
 // ====================================================================================================
 namespace plb {
@@ -1280,6 +1572,7 @@ bool gpu_lattice_get_periodic(const GpuLattice* g, int axis) { return axis >= 0 
 void gpu_lattice_collide_and_stream(GpuLattice* g) {
   g->materialize();
   ck(g->ctx, hcg_fluid_warmup(g->ctx, 1), "collideAndStream");
+  if (g->companion) gpu_lattice_collide_and_stream(g->companion);     // the pre-inlet ranks of the reference run the same warm-up loop
 }
 void gpu_lattice_velocity_plane(GpuLattice* gp, const Box3D& plane_) {
   GpuLattice& g = *gp;
@@ -1306,7 +1599,13 @@ void gpu_lattice_boundary_velocity(GpuLattice* gp, const Box3D& domain_, const d
   bool seen[6] = {false, false, false, false, false, false};
   for (plint x = domain.x0; x <= domain.x1; x++) for (plint y = domain.y0; y <= domain.y1; y++) for (plint z = domain.z0; z <= domain.z1; z++) {
     const uint8_t f = g.flags[g.idx((int)x, (int)y, (int)z)];
-    if (f >= HCG_VEL_XN) seen[f - HCG_VEL_XN] = true;
+    if (f >= HCG_VEL_XN && f <= HCG_VEL_ZP) seen[f - HCG_VEL_XN] = true;
+    else if (f >= HCG_ZH_VEL_XN && f <= HCG_ZH_VEL_ZP) {                 // Zou-He velocity node: its own value
+      auto it = g.bcn.find(g.idx((int)x, (int)y, (int)z));
+      const double rho = it == g.bcn.end() ? 1.0 : it->second[3];
+      g.bcn[g.idx((int)x, (int)y, (int)z)] = {u[0], u[1], u[2], rho};
+      g.bcn_dirty = true;
+    }
   }
   for (int o = 0; o < 6; o++) if (seen[o]) for (int k = 0; k < 3; k++) g.bc[o][k] = u[k];
   g.touchFlags();
@@ -1346,6 +1645,34 @@ void gpu_lattice_equilibrium(GpuLattice* g, double rho, const double u[3]) {
   g->eq_rho = rho; for (int k = 0; k < 3; k++) g->eq_u[k] = u[k];
   g->eq_pending = true;
   g->flush();
+  if (g->companion) gpu_lattice_equilibrium(g->companion, rho, u);
+}
+// Zou-He velocity (pressure = 0) / pressure (1) nodes, orientation 0..5 = outward normal -x +x -y +y -z +z.  Bounce-back nodes
+// inside the box stay walls (Palabos would wrap the bounce-back dynamics; a wall node has nothing to impose).
+void gpu_lattice_zouhe(GpuLattice* gp, const Box3D& domain_, int pressure, int orientation) {
+  GpuLattice& g = *gp;
+  const Box3D domain = clip(g, domain_);
+  const uint8_t flag = (uint8_t)((pressure ? HCG_ZH_PRES_XN : HCG_ZH_VEL_XN) + orientation);
+  for (plint x = domain.x0; x <= domain.x1; x++) for (plint y = domain.y0; y <= domain.y1; y++) for (plint z = domain.z0; z <= domain.z1; z++) {
+    const int64_t i = g.idx((int)x, (int)y, (int)z);
+    if (g.flags[i] == HCG_BOUNCEBACK) continue;
+    g.flags[i] = flag;
+    if (!g.bcn.count(i)) g.bcn[i] = {0.0, 0.0, 0.0, 1.0};
+  }
+  g.bcn_dirty = true;
+  g.touchFlags();
+}
+void gpu_lattice_boundary_density(GpuLattice* gp, const Box3D& domain_, double rho) {
+  GpuLattice& g = *gp;
+  const Box3D domain = clip(g, domain_);
+  for (plint x = domain.x0; x <= domain.x1; x++) for (plint y = domain.y0; y <= domain.y1; y++) for (plint z = domain.z0; z <= domain.z1; z++) {
+    const int64_t i = g.idx((int)x, (int)y, (int)z);
+    if (g.flags[i] < HCG_ZH_PRES_XN) continue;
+    auto it = g.bcn.find(i);
+    if (it == g.bcn.end()) g.bcn[i] = {0.0, 0.0, 0.0, rho}; else it->second[3] = rho;
+    g.bcn_dirty = true;
+  }
+  if (g.ctx) g.flush();
 }
 std::string gpu_lattice_info(const GpuLattice* g) {
   std::ostringstream o;

@@ -78,7 +78,7 @@ typedef double T;
 
 namespace plb { struct Box3D; struct DomainFunctional3D; }
 namespace hemo {
-class GpuLattice; class HemoCell; class HemoCellFields; class HemoCellField; class Config;
+class GpuLattice; class HemoCell; class HemoCellFields; class HemoCellField; class Config; class PreInlet;
 /* non-template back end of the plb:: shim (hemocell_b200/host/facade.cpp) */
 GpuLattice* gpu_lattice_create(long nx, long ny, long nz, double omega);
 void gpu_lattice_destroy(GpuLattice*);
@@ -92,6 +92,8 @@ void gpu_lattice_boundary_velocity(GpuLattice*, const plb::Box3D& domain, const 
 void gpu_lattice_external_vector(GpuLattice*, const plb::Box3D& domain, const double v[3]);
 void gpu_lattice_define_flag(GpuLattice*, const plb::Box3D& domain, const plb::DomainFunctional3D* fun, int flag);
 void gpu_lattice_equilibrium(GpuLattice*, double rho, const double u[3]);
+void gpu_lattice_zouhe(GpuLattice*, const plb::Box3D& domain, int pressure, int orientation);   /* Zou-He velocity / pressure nodes */
+void gpu_lattice_boundary_density(GpuLattice*, const plb::Box3D& domain, double rho);
 std::string gpu_lattice_info(const GpuLattice*);
 }
 
@@ -262,7 +264,24 @@ class OnLatticeBoundaryCondition3D {
   void setVelocityConditionOnBlockBoundaries(MultiBlockLattice3D<U, Descriptor>& lattice, boundary::BcType = boundary::dirichlet) {
     hemo::gpu_lattice_velocity_all_faces(lattice.gpu());
   }
+  virtual ~OnLatticeBoundaryCondition3D() {}
+  /* Zou-He velocity / pressure nodes on any box of nodes, 0/1/2 = normal axis, N/P = OUTWARD normal -/+ (helper/preInlet.cpp:415-432,
+   * examples/pipeflow_with_preinlet/pipeflow_with_preinlet.cpp:131); bounce-back nodes inside the box stay walls */
+#define HEMO_ZH_BC(NAME, PRESSURE, ORIENT) \
+  void NAME(Box3D domain, MultiBlockLattice3D<U, Descriptor>& lattice, boundary::BcType = boundary::dirichlet) { hemo::gpu_lattice_zouhe(lattice.gpu(), domain, PRESSURE, ORIENT); }
+  HEMO_ZH_BC(addVelocityBoundary0N, 0, 0) HEMO_ZH_BC(addVelocityBoundary0P, 0, 1) HEMO_ZH_BC(addVelocityBoundary1N, 0, 2)
+  HEMO_ZH_BC(addVelocityBoundary1P, 0, 3) HEMO_ZH_BC(addVelocityBoundary2N, 0, 4) HEMO_ZH_BC(addVelocityBoundary2P, 0, 5)
+  HEMO_ZH_BC(addPressureBoundary0N, 1, 0) HEMO_ZH_BC(addPressureBoundary0P, 1, 1) HEMO_ZH_BC(addPressureBoundary1N, 1, 2)
+  HEMO_ZH_BC(addPressureBoundary1P, 1, 3) HEMO_ZH_BC(addPressureBoundary2N, 1, 4) HEMO_ZH_BC(addPressureBoundary2P, 1, 5)
+#undef HEMO_ZH_BC
 };
+template <typename U, template <typename V> class Descriptor> struct WrappedZouHeBoundaryManager3D {};
+template <typename U, template <typename V> class Descriptor, class Manager>
+class BoundaryConditionInstantiator3D : public OnLatticeBoundaryCondition3D<U, Descriptor> {};
+template <typename U, template <typename V> class Descriptor>
+OnLatticeBoundaryCondition3D<U, Descriptor>* createZouHeBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<U, Descriptor>(); }
+template <typename U, template <typename V> class Descriptor>
+void setBoundaryDensity(MultiBlockLattice3D<U, Descriptor>& lattice, Box3D domain, U rho) { hemo::gpu_lattice_boundary_density(lattice.gpu(), domain, rho); }
 template <typename U, template <typename V> class Descriptor>
 OnLatticeBoundaryCondition3D<U, Descriptor>* createLocalBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<U, Descriptor>(); }
 
@@ -619,6 +638,62 @@ class HemoCellFields {
   hcg_ctx* ctx();
 };
 
+/* ---- helper/preInlet.h --------------------------------------------------------------------------- */
+}  // namespace hemo
+enum Direction : int { Xpos, Xneg, Ypos, Yneg, Zpos, Zneg };
+namespace hemo {
+/* The reference splits the MPI ranks between the periodic pre-inlet and the main domain and couples them with messages.
+ * Here ONE process holds both: the pre-inlet is a second device context (same GPU, or GPU $HEMOCELL_PREINLET_DEVICE)
+ * that HemoCell::iterate() steps next to the main lattice, so `partOfpreInlet` is always false for the case file and the
+ * calls the reference makes on its pre-inlet ranks (bounce-back fill, periodicity, driving force, loading its cells) happen
+ * inside this class.  applyPreInlet() = hcg_preinlet_apply_velocity + hcg_preinlet_apply_cells (include/hemocell_gpu.h). */
+inline plint cellsInBoundingBox(plb::Box3D const& box) { return std::abs((box.x1 - box.x0)*(box.y1 - box.y0)*(box.z1 - box.z0)); }
+class PreInlet {
+ public:
+  PreInlet(HemoCell* hemocell_, plb::MultiScalarField3D<int>* flagMatrix_);
+  ~PreInlet();
+  plint getNumberOfNodes() { return cellsInBoundingBox(location); }
+  void createBoundary();
+  bool readNormalizedVelocities();
+  void setDrivingForce();
+  void setDrivingForceTimeDependent(double t);
+  void calculateDrivingForce();
+  double interpolate(vector<double>& xData, vector<double>& yData, double x, bool extrapolate);
+  double average(vector<double> values);
+  void applyPreInletVelocityBoundary();
+  void applyPreInletParticleBoundary();
+  void applyPreInlet() { applyPreInletVelocityBoundary(); applyPreInletParticleBoundary(); }
+  void initializePreInletParticleBoundary();
+  void initializePreInletVelocityBoundary();
+  void initializePreInlet() { initializePreInletVelocityBoundary(); initializePreInletParticleBoundary(); }
+  void autoPreinletFromBoundary(Direction);
+  void preInletFromSlice(Direction direction_, plb::Box3D boundary);
+  Direction direction = Direction::Zneg;
+  plb::Box3D location, fluidInlet;
+  int nProcs = 0;
+  bool initialized = false;
+  double drivingForce = 0.0, average_vel = 0.0, pulseEndTime = 1.0, pFrequency = 1.0;
+  std::vector<double> normalizedVelocityTimes, normalizedVelocityValues;
+  bool partOfpreInlet = false;
+  int inflow_length = 0, preinlet_length = 0;
+  HemoCell* hemocell;
+  plb::MultiScalarField3D<int>* flagMatrix = nullptr;
+  /* ---- B200 side ---- */
+  GpuLattice* pre = nullptr;                      /* the pre-inlet's own lattice (local coordinates: global - location.{x0,y0,z0}) */
+  hcg_ctx* preCtx();
+  void createLattice(double omega);               /* HemoCell::initializeLattice */
+  void iterate();                                 /* HemoCell::iterate: one step of the pre-inlet domain */
+  int64_t cellsHandedOver = 0;
+ private:
+  void locate(plb::Box3D slice);
+  void coupleNodes();
+  void applyForce(double f);
+  int axis() const { return (int)direction/2; }
+  bool coupled = false, force_applied = false;
+  friend class HemoCell;
+};
+void boundaryFromFlagMatrix(plb::MultiBlockLattice3D<T, DESCRIPTOR>* fluid, plb::MultiScalarField3D<int>* flagMatrix, bool partOfpreInlet);   /* helper/genericFunctions.cpp:138-163 */
+
 /* ---- hemocell.h ---------------------------------------------------------------------------------- */
 class HemoCell {
  public:
@@ -657,6 +732,8 @@ class HemoCell {
   Config* cfg = nullptr;
   HemoCellFields* cellfields = nullptr;
   unsigned int iter = 0;
+  PreInlet* preInlet = nullptr;                      /* owned (deleted with the HemoCell object, core/hemoCell.cpp:117-119) */
+  bool partOfpreInlet = false;                       /* always false here: one process holds both domains (see PreInlet) */
   hcg_ctx* ctx();                                    /* the device context behind `lattice` (created by lattice->initialize()) */
  private:
   void registerCellType(HemoCellField* f);
@@ -664,6 +741,7 @@ class HemoCell {
   void pushSettings();
   bool sanityCheckDone = false, loadParticlesIsCalled = false;
   unsigned int lastOutputAt = 0; double lastOutput = 0;
+  friend class PreInlet;
 };
 
 /* ---- helper/cellInfo.h, helper/fluidInfo.h ------------------------------------------------------------ */

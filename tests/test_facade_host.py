@@ -64,7 +64,10 @@ def test_example_fails_loudly_without_device(tmp_path):
     "examples/microcontraction/microcontraction.cpp", "examples/capillary/wedge.cpp", "cases/atherosclerosis/atherosclerosis.cpp",
     "cases/cellCollision/cellCollision.cpp", "cases/kolmogorovFlow/kolmogorovFlow.cpp", "cases/microvessel_bended/microvessel_bended.cpp",
     "cases/stentflow/stentflow.cpp", "cases/unbounded/unbounded.cpp", "cases/vasoconstriction_pipe/vasoconstriction_pipe.cpp",
-    "examples/pipeflow/pipeflow.cpp", "examples/parachuting/parachuting.cpp"])
+    "examples/pipeflow/pipeflow.cpp", "examples/parachuting/parachuting.cpp",
+    # pre-inlet cases (hemo::PreInlet, Zou-He inlet / pressure outlet)
+    "examples/pipeflow_with_preinlet/pipeflow_with_preinlet.cpp", "examples/curvedflow_with_preinlet/curvedflow_with_preinlet.cpp",
+    "cases/AR2/AR2.cpp", "cases/AR2_pulsatile/AR2_pulsatile.cpp", "cases/AR2_stiff/AR2_stiff.cpp"])
 def test_reference_case_files_compile_unmodified(case):
     """drop-in check: the reference's own case files compile against include/hemocell.h as they are"""
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", f"-I{ROOT}/include", f"-I{ROOT}/include/compat", os.path.join(REF, case)],
