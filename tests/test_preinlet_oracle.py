@@ -95,3 +95,38 @@ def test_preinlet_handover_rule_and_coupling():
     V = c['rbc'].V
     pre.pos[:V, 0] -= PC.NXP                 # as if the cell had gone round once more against the flow direction ...
     assert cpl.apply_cells() == 1 and sorted(main.cell_id) == [2, 4]
+
+
+def test_zouhe_channel_reproduces_plane_poiseuille_flow():
+    """known answer that pins the Zou-He nodes to physics (Palabos itself is not in the tree): plane Poiseuille flow between
+    bounce-back walls, parabolic Zou-He velocity inlet, Zou-He pressure outlet.  Half-way bounce-back puts the walls half a
+    node outside the last fluid node (channel width H = ny - 2); at steady state the pressure gradient must be
+    dp/dx = -12 nu rho U_mean / H^2 with p = rho / 3, and the profile stays the imposed parabola along the channel."""
+    nx, ny, nz = 40, 19, 3
+    tau = 0.9
+    nu = (tau - 0.5) / 3.0
+    dom = O.make_domain(nx, ny, nz, (0, 0, 1), tau)
+    N = nx * ny * nz
+    fl = np.zeros((nx, ny, nz), np.uint8)
+    fl[:, 0, :] = 1; fl[:, -1, :] = 1
+    fl[0, 1:-1, :] = 8; fl[-1, 1:-1, :] = 15
+    H = ny - 2
+    y = np.arange(ny) - 0.5                       # distance from the lower wall
+    umax = 0.03
+    prof = 4 * umax * y * (H - y) / H ** 2
+    bc = np.zeros((4, nx, ny, nz)); bc[3] = 1.0
+    bc[0, 0, 1:-1, :] = prof[1:-1, None]
+    bc = np.ascontiguousarray(bc.reshape(-1)); fl = np.ascontiguousarray(fl.reshape(-1))
+    pop = O.init_equilibrium(dom); force = np.zeros(3 * N)
+    for _ in range(6000):
+        O.collide_and_stream(dom, fl, pop, force, bc_node=bc)
+    rho, vel = O.moments(dom, fl, pop, force, bc_node=bc)
+    u = vel.reshape(3, nx, ny, nz); rho = rho.reshape(nx, ny, nz)
+    xs = np.arange(8, nx - 8)
+    dpdx = np.polyfit(xs, rho[xs, ny // 2, 0] / 3.0, 1)[0]
+    umean = prof[1:-1].sum() / H
+    expect = -12 * nu * umean / H ** 2
+    assert abs(dpdx / expect - 1.0) < 0.02, (dpdx, expect)
+    mid = u[0, nx // 2, 1:-1, 0]
+    assert np.max(np.abs(mid - prof[1:-1])) < 0.01 * umax
+    assert np.max(np.abs(u[1, nx // 2])) < 1e-6 * umax
