@@ -232,4 +232,15 @@ hcg_status hcg_preinlet_apply_cells(hcg_ctx* c, int32_t axis, double period, con
   return HCG_OK;
 }
 
+/* hand-over bookkeeping for checkpoints: the periodic image handed over last per pre-inlet cell slot (INT64_MIN = none);
+ * set != 0 writes, else reads; n = the pre-inlet's cell capacity */
+hcg_status hcg_preinlet_laps(hcg_ctx* c, int64_t n, int64_t* laps, int32_t set) {
+  if (!c || n < 0 || (n > 0 && !laps)) return HCG_ERR_ARG;
+  PreInletState* p = c->preinlet;
+  if (!p || !p->pre) return hcg_fail(c, HCG_ERR_STATE, "hcg_preinlet_map has not been called");
+  if ((int64_t)p->last_lap.size() < n) p->last_lap.resize(n, INT64_MIN);
+  for (int64_t i = 0; i < n; i++) { if (set) p->last_lap[i] = laps[i]; else laps[i] = p->last_lap[i]; }
+  return HCG_OK;
+}
+
 }  // extern "C"

@@ -720,7 +720,7 @@ void HemoCell::iterate() {
 
 void HemoCell::saveCheckPoint() {
   hlog << "(HemoCell) (Saving Functions) Saving Checkpoint at timestep " << iter << endl;
-  if (preInlet && preInlet->pre) hlog << "(HemoCell) (Saving Functions) WARNING: the pre-inlet domain (PRE_lattice / PRE_particleField of the reference) is not part of this checkpoint" << endl;
+
   hcg_ctx* c = ctx();
   GpuLattice* g = lattice->gpu();
   const std::string dir = global.checkpointDirectory;
@@ -743,6 +743,7 @@ void HemoCell::saveCheckPoint() {
   ck(c, hcg_cells_info(c, ids.data(), types.data(), alive.data()), "hcg_cells_info");
   f.write((const char*)ids.data(), 8*nc); f.write((const char*)types.data(), 4*nc); f.write((const char*)alive.data(), nc);
   f.close();
+  if (preInlet && preInlet->pre) preInlet->saveCheckPoint(dir);
   if (plb::global::mpi().isMainProcessor()) {
     // checkpoint.xml: <Checkpoint><General><Iteration>..</Iteration></General> + the original <hemocell> tree (config/config.cpp:53-78)
     xml::Node root; xml::Node* cp = root.addChild("Checkpoint");
@@ -796,8 +797,13 @@ void HemoCell::loadCheckPoint() {
       force.insert(force.end(), P[2].begin() + 3*base_of[k], P[2].begin() + 3*(base_of[k] + V));
       frep.insert(frep.end(), P[3].begin() + 3*base_of[k], P[3].begin() + 3*(base_of[k] + V));
     }
+    if (preInlet && preInlet->pre) ck(c, hcg_cells_reserve(c, fl->impl->device_ctype, 2*(int64_t)tid.size() + 256), "hcg_cells_reserve");
     ck(c, hcg_cells_add(c, fl->impl->device_ctype, (int64_t)tid.size(), tid.data(), tpos.data()), "hcg_cells_add");
     g->has_cells = g->has_cells || !tid.empty();
+    // the particle arrays of a type end with its spare slots (multi-GPU slack, pre-inlet reserve): the state arrays follow that layout
+    int64_t cap_c = 0, cap_p = 0;
+    ck(c, hcg_cells_capacity(c, &cap_c, &cap_p), "hcg_cells_capacity");
+    vel.resize((size_t)3*cap_p, 0.0); force.resize((size_t)3*cap_p, 0.0); frep.resize((size_t)3*cap_p, 0.0);
   }
   if (plb::global::mpi().getSize() == 1 && !vel.empty()) {
     ck(c, hcg_cells_upload(c, HCG_P_VEL, vel.data()), "upload"); ck(c, hcg_cells_upload(c, HCG_P_FORCE, force.data()), "upload");
@@ -806,6 +812,7 @@ void HemoCell::loadCheckPoint() {
   ck(c, hcg_lattice_upload(c, HCG_LAT_POP, pop.data()), "upload"); ck(c, hcg_lattice_upload(c, HCG_LAT_FORCE, frc.data()), "upload");
   g->eq_pending = false; g->body_pending = false;
   loadParticlesIsCalled = true;
+  if (preInlet && preInlet->pre) preInlet->loadCheckPoint(global.checkpointDirectory + "/");
 }
 
 // snapshot of the cell bookkeeping (ids, types, alive / owned flags), shared by output and observables
@@ -1514,6 +1521,86 @@ void PreInlet::applyPreInletParticleBoundary() {
   ck(c, hcg_preinlet_apply_cells(c, a, period, shift, lo, hi, std::max<plint>(1, hemocell->cellfields->number_of_cells), &n), "hcg_preinlet_apply_cells");
   cellsHandedOver += n;
   if (n) { hemocell->lattice->gpu()->has_cells = true; hlog << "(PreInlet) iteration " << hemocell->iter << ": " << n << " cell(s) handed over to the main domain (" << cellsHandedOver << " so far)" << endl; }
+}
+
+// The pre-inlet's share of a checkpoint (PRE_lattice / PRE_particleField in the reference, core/hemoCellFields.cpp:297-314):
+// populations, node force, live cells with their state, the hand-over bookkeeping and the id stride, in pre.bin beside the
+// main domain's rank file (rotated to .old like it).
+void PreInlet::saveCheckPoint(const std::string& dir) {
+  hcg_ctx* q = preCtx();
+  hcg_ctx* c = hemocell->ctx();
+  if (!coupled) coupleNodes();
+  const std::string base = dir + "pre";
+  if (file_exists(base + ".bin")) rename((base + ".bin").c_str(), (base + ".bin.old").c_str());
+  std::ofstream f(base + ".bin", std::ios::binary);
+  const int64_t Nl = (int64_t)pre->nx*pre->ny*pre->nz;
+  int64_t nc = 0, np = 0;
+  ck(q, hcg_cells_capacity(q, &nc, &np), "hcg_cells_capacity");
+  const int64_t hdr[8] = {0x48434750, (int64_t)hemocell->iter, Nl, nc, np, (int64_t)hemocell->cellfields->size(),
+                          (int64_t)hemocell->cellfields->number_of_cells, cellsHandedOver};
+  f.write((const char*)hdr, sizeof(hdr));
+  std::vector<double> buf((size_t)std::max<int64_t>(19*Nl, 3*np));
+  ck(q, hcg_lattice_download(q, HCG_LAT_POP, buf.data()), "download"); f.write((const char*)buf.data(), 8*19*Nl);
+  ck(q, hcg_lattice_download(q, HCG_LAT_FORCE, buf.data()), "download"); f.write((const char*)buf.data(), 8*3*Nl);
+  for (int fld : {HCG_P_POS, HCG_P_VEL, HCG_P_FORCE, HCG_P_FREP}) { ck(q, hcg_cells_download(q, fld, buf.data()), "download"); f.write((const char*)buf.data(), 8*3*np); }
+  std::vector<int64_t> ids(nc), laps(nc); std::vector<int32_t> types(nc); std::vector<uint8_t> alive(nc);
+  ck(q, hcg_cells_info(q, ids.data(), types.data(), alive.data()), "hcg_cells_info");
+  ck(c, hcg_preinlet_laps(c, nc, laps.data(), 0), "hcg_preinlet_laps");
+  f.write((const char*)ids.data(), 8*nc); f.write((const char*)types.data(), 4*nc); f.write((const char*)alive.data(), nc);
+  f.write((const char*)laps.data(), 8*nc);
+}
+void PreInlet::loadCheckPoint(const std::string& dir) {
+  hcg_ctx* q = preCtx();
+  hcg_ctx* c = hemocell->ctx();
+  std::ifstream f(dir + "pre.bin", std::ios::binary);
+  if (!f) fatal("(PreInlet) cannot open the pre-inlet's checkpoint data " + dir + "pre.bin");
+  int64_t hdr[8]; f.read((char*)hdr, sizeof(hdr));
+  const int64_t Nl = (int64_t)pre->nx*pre->ny*pre->nz;
+  HemoCellFields& cf = *hemocell->cellfields;
+  if (hdr[0] != 0x48434750 || hdr[2] != Nl || hdr[5] != (int64_t)cf.size()) fatal("(PreInlet) checkpoint does not match this pre-inlet / cell types");
+  const int64_t nc = hdr[3], np = hdr[4];
+  cf.number_of_cells = (plint)hdr[6]; cellsHandedOver = hdr[7];
+  std::vector<double> pop(19*Nl), frc(3*Nl);
+  f.read((char*)pop.data(), 8*19*Nl); f.read((char*)frc.data(), 8*3*Nl);
+  std::vector<double> P[4];
+  for (auto& v : P) { v.resize(3*np); f.read((char*)v.data(), 8*3*np); }
+  std::vector<int64_t> ids(nc), laps(nc); std::vector<int32_t> types(nc); std::vector<uint8_t> alive(nc);
+  f.read((char*)ids.data(), 8*nc); f.read((char*)types.data(), 4*nc); f.read((char*)alive.data(), nc); f.read((char*)laps.data(), 8*nc);
+  std::vector<int64_t> base_of(nc); { int64_t p = 0; for (int64_t k = 0; k < nc; k++) { base_of[k] = p; p += cf[(unsigned)types[k]]->numVertex; } }
+  std::vector<double> vel, force, frep; std::vector<int64_t> new_laps;
+  for (auto* fl : cf.cellFields) {
+    hcg_celltype t = device_celltype(fl);
+    int32_t qid = -1;
+    ck(q, hcg_celltype_add(q, &t, &qid), "hcg_celltype_add");
+    if (qid != fl->impl->device_ctype) fatal("(PreInlet) cell types of the pre-inlet and the main domain are out of step");
+    std::vector<int64_t> tid; std::vector<double> tpos;
+    for (int64_t k = 0; k < nc; k++) if (types[k] == qid && alive[k] && ids[k] >= 0) {
+      tid.push_back(ids[k]); new_laps.push_back(laps[k]);
+      const int V = fl->numVertex;
+      tpos.insert(tpos.end(), P[0].begin() + 3*base_of[k], P[0].begin() + 3*(base_of[k] + V));
+      vel.insert(vel.end(), P[1].begin() + 3*base_of[k], P[1].begin() + 3*(base_of[k] + V));
+      force.insert(force.end(), P[2].begin() + 3*base_of[k], P[2].begin() + 3*(base_of[k] + V));
+      frep.insert(frep.end(), P[3].begin() + 3*base_of[k], P[3].begin() + 3*(base_of[k] + V));
+    }
+    ck(q, hcg_cells_add(q, qid, (int64_t)tid.size(), tid.data(), tpos.data()), "hcg_cells_add");
+    pre->has_cells = pre->has_cells || !tid.empty();
+    int64_t cap_c = 0, cap_p = 0;
+    ck(q, hcg_cells_capacity(q, &cap_c, &cap_p), "hcg_cells_capacity");
+    vel.resize((size_t)3*cap_p, 0.0); force.resize((size_t)3*cap_p, 0.0); frep.resize((size_t)3*cap_p, 0.0);
+    new_laps.resize((size_t)cap_c, INT64_MIN);
+  }
+  ck(q, hcg_set_force_limit(q, param::f_limit), "hcg_set_force_limit");
+  if (!vel.empty()) {
+    ck(q, hcg_cells_upload(q, HCG_P_VEL, vel.data()), "upload"); ck(q, hcg_cells_upload(q, HCG_P_FORCE, force.data()), "upload");
+    ck(q, hcg_cells_upload(q, HCG_P_FREP, frep.data()), "upload");
+  }
+  setDrivingForce();                                  // the value the node force is reset to; the saved node force follows
+  ck(q, hcg_lattice_upload(q, HCG_LAT_POP, pop.data()), "upload"); ck(q, hcg_lattice_upload(q, HCG_LAT_FORCE, frc.data()), "upload");
+  pre->eq_pending = false; pre->body_pending = false;
+  if (!coupled) coupleNodes();
+  // live cells were re-created in slot order: their hand-over marks follow them
+  ck(c, hcg_preinlet_laps(c, (int64_t)new_laps.size(), new_laps.data(), 1), "hcg_preinlet_laps");
+  ck(c, hcg_preinlet_apply_velocity(c), "hcg_preinlet_apply_velocity");      // the inlet nodes' velocities are not in the main rank file
 }
 
 // helper/genericFunctions.cpp:138-163: bounce-back wherever the flag matrix is solid (main domain only)

@@ -56,7 +56,7 @@ hcg_op_spread hcg_op_collide_stream hcg_op_interpolate hcg_op_sync hcg_op_advanc
 hcg_op_zero_force hcg_cells_bbox hcg_cells_volume_area hcg_cells_stretch hcg_fluid_velocity_stats hcg_timers_enable
 hcg_timers hcg_timers_reset hcg_launch_count hcg_synchronize hcg_iterate_timed
 hcg_lattice_set_bc_nodes hcg_lattice_node_velocity hcg_cells_reserve hcg_preinlet_map hcg_preinlet_apply_velocity
-hcg_preinlet_apply_cells""".split()
+hcg_preinlet_apply_cells hcg_preinlet_laps""".split()
 
 _lib = None
 

@@ -688,6 +688,8 @@ class PreInlet {
   void locate(plb::Box3D slice);
   void coupleNodes();
   void applyForce(double f);
+  void saveCheckPoint(const std::string& dir);    /* the reference's PRE_lattice / PRE_particleField (core/hemoCellFields.cpp:297-314) */
+  void loadCheckPoint(const std::string& dir);
   int axis() const { return (int)direction/2; }
   bool coupled = false, force_applied = false;
   friend class HemoCell;

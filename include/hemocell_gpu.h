@@ -219,6 +219,10 @@ hcg_status hcg_preinlet_apply_velocity(hcg_ctx* main);
 hcg_status hcg_preinlet_apply_cells(hcg_ctx* main, int32_t axis, double period, const double shift[3],
                                     double slab_lo, double slab_hi, int64_t id_stride, int64_t* n_added);
 
+/* checkpoint support: read (set = 0) or write (set != 0) the periodic image handed over last per pre-inlet cell slot
+ * (INT64_MIN = never), n = the pre-inlet context's cell capacity */
+hcg_status hcg_preinlet_laps(hcg_ctx* main, int64_t n, int64_t* laps, int32_t set);
+
 /* ---- per-operator entry points (single-step parity; same order as iterate()) */
 hcg_status hcg_op_repulsion(hcg_ctx*);       /* HemoCellFields::applyRepulsionForce          */
 hcg_status hcg_op_wall_repulsion(hcg_ctx*);  /* HemoCellFields::applyBoundaryRepulsionForce  */

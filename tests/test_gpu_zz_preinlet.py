@@ -207,3 +207,46 @@ def test_reference_pipeflow_with_preinlet_unmodified_binary(tmp_path):
     h5 = glob.glob(str(tmp_path / "**" / "hdf5" / "*" / "*.h5"), recursive=True)
     assert any(os.path.basename(str(f)).startswith("Fluid") for f in h5) and any(os.path.basename(str(f)).startswith("RBC") for f in h5)
     print("pipeflow_with_preinlet: cells", cells, "mean velocity m/s", vmean, "handed over:", re.findall(r"\((\d+) so far\)", out)[-1:])
+
+
+def _preinlet_run(d, tmax, cfg_path=None):
+    name = "pipeflow_with_preinlet"
+    src = os.path.join(ROOT, "build", "refcases", name)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "hemocell_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""),
+               HEMOCELL_H5_DEFLATE="1")
+    if cfg_path is None:
+        d.mkdir()
+        for f in [name, "config.xml", "RBC.xml", "PLT.xml", "RBC.pos", "PLT.pos", "normal.stl"]:
+            shutil.copy(os.path.join(src, f), d / f)
+        cfg = (d / "config.xml").read_text()
+        for key, val in (("tmax", tmax), ("tmeas", 100), ("tcheckpoint", 200), ("tbalance", 100000)):
+            cfg = re.sub(rf"<{key}>.*?</{key}>", f"<{key}> {val} </{key}>", cfg)
+        (d / "config.xml").write_text(cfg)
+        cfg_path = "config.xml"
+    r = subprocess.run([str(d / name), str(cfg_path)], cwd=d, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = r.stdout
+    stats = re.findall(r"Stats\. @ (\d+) .*?# of cells: (\d+).*?Velocity  -  max\.: (\S+) m/s, mean: (\S+) m/s.*?Force  -  min\.: (\S+) pN, max\.: (\S+) pN \(\S+ lf\), mean: (\S+) pN",
+                       out, re.S)
+    return out, {int(s[0]): [float(v) for v in s[1:]] for s in stats}
+
+
+def test_preinlet_checkpoint_restart_reproduces_uninterrupted_run(tmp_path):
+    """saveCheckPoint / loadCheckPoint with a pre-inlet (PRE_lattice / PRE_particleField of the reference,
+    core/hemoCellFields.cpp:254-265, 297-314): the unmodified pipeflow_with_preinlet binary interrupted at iteration 200 and
+    restarted from checkpoint.xml reaches the iteration-300 statistics of the uninterrupted run, and hands over no cell twice"""
+    if not os.path.exists(os.path.join(ROOT, "build", "refcases", "pipeflow_with_preinlet", "pipeflow_with_preinlet")):
+        pytest.skip("build/refcases not present (built from /root/reference in the authoring container)")
+    _, straight = _preinlet_run(tmp_path / "straight", 300)
+    _, first = _preinlet_run(tmp_path / "first", 200)
+    assert sorted(straight) == [100, 200, 300] and sorted(first) == [100, 200]
+    U.assert_close(first[200], straight[200], "two runs of the same case", rtol=1e-4, floor=1e-6)
+    d = tmp_path / "first"
+    cp = d / "tmp" / "checkpoint" / "checkpoint.xml"
+    assert cp.exists() and (d / "tmp" / "checkpoint" / "pre.bin").exists()
+    cp.write_text(re.sub(r"<tmax>.*?</tmax>", "<tmax> 300 </tmax>", cp.read_text()))
+    out, resumed = _preinlet_run(d, 300, cfg_path=cp)
+    assert "CHECKPOINT found" in out or "Loading Checkpoint" in out
+    assert sorted(resumed) == [300]
+    assert resumed[300][0] == straight[300][0]                              # number of cells
+    U.assert_close(resumed[300][1:], straight[300][1:], "iteration-300 statistics of the restarted run", rtol=1e-4, floor=1e-6)
