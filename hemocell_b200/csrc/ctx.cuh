@@ -133,6 +133,7 @@ struct hcg_ctx {
   MultiState multi;
   PeerState peer;
   double* halo_send[2]; double* halo_recv[2];
+  int* d_qsets = nullptr;      // population index sets of the halo exchange (lattice.cu), on this context's device
   bool timers_on; std::vector<TimerSlot> timers; std::map<std::string,int> timer_idx;
   std::vector<cudaEvent_t> ev_pool; std::vector<TimerPending> ev_pending;
   int64_t launches;

@@ -897,7 +897,8 @@ LatArgs make_args(const hcg_ctx* c) {
 }
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1)/t); }
 
-int* d_qsets = nullptr;   // {10,13,14,15,16, 1,4,5,6,7, 0,1,2}
+// population index sets of the halo exchange {10,13,14,15,16, 1,4,5,6,7, 0,1,2}: one device copy per context (contexts of one
+// process may live on different GPUs without peer access, e.g. a pre-inlet on a second GPU)
 const int h_qsets[13] = {10,13,14,15,16, 1,4,5,6,7, 0,1,2};
 
 hcg_status exchange(hcg_ctx* c, double* buf, int64_t P /* elements per plane */, const int* hL, const int* dL, int nL, const int* hR, const int* dR, int nR) {
@@ -927,9 +928,9 @@ hcg_status exchange(hcg_ctx* c, double* buf, int64_t P /* elements per plane */,
 }
 
 hcg_status ensure_qsets(hcg_ctx* c) {
-  if (!d_qsets) {
-    CUDA_TRY(c, cudaMalloc(&d_qsets, sizeof(h_qsets)));
-    CUDA_TRY(c, cudaMemcpy(d_qsets, h_qsets, sizeof(h_qsets), cudaMemcpyHostToDevice));
+  if (!c->d_qsets) {
+    CUDA_TRY(c, cudaMalloc(&c->d_qsets, sizeof(h_qsets)));
+    CUDA_TRY(c, cudaMemcpy(c->d_qsets, h_qsets, sizeof(h_qsets), cudaMemcpyHostToDevice));
   }
   return HCG_OK;
 }
@@ -939,12 +940,12 @@ hcg_status ensure_qsets(hcg_ctx* c) {
 hcg_status lat_halo_exchange_pop(hcg_ctx* c) {
   hcg_status s = ensure_qsets(c); if (s) return s;
   // pull kernel: left ghost read by c_x = +1 populations, right ghost by c_x = -1
-  return exchange(c, c->g[c->cur], c->P, h_qsets, d_qsets, 5, h_qsets + 5, d_qsets + 5, 5);
+  return exchange(c, c->g[c->cur], c->P, h_qsets, c->d_qsets, 5, h_qsets + 5, c->d_qsets + 5, 5);
 }
 hcg_status lat_halo_exchange_u(hcg_ctx* c) {
   hcg_status s = ensure_qsets(c); if (s) return s;
   // node vectors are AoS [n][4]: one contiguous block of 4*P doubles per plane ("population" 0)
-  return exchange(c, c->U, 4*c->P, h_qsets + 10, d_qsets + 10, 1, h_qsets + 10, d_qsets + 10, 1);
+  return exchange(c, c->U, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1);
 }
 
 // row-pipelined path: eligibility and launch shape
@@ -1216,7 +1217,7 @@ hcg_status lat_pop_from_reference(hcg_ctx* c, const double* src_dev) {
   KERNEL_CHECK(c);
   hcg_status st = ensure_qsets(c); if (st) return st;
   // g_q(n) = S_q(n + c_q): c_x = -1 populations read the LEFT ghost, c_x = +1 the RIGHT ghost
-  st = exchange(c, s, c->P, h_qsets + 5, d_qsets + 5, 5, h_qsets, d_qsets, 5); if (st) return st;
+  st = exchange(c, s, c->P, h_qsets + 5, c->d_qsets + 5, 5, h_qsets, c->d_qsets, 5); if (st) return st;
   CUDA_TRY(c, cudaMemsetAsync(c->g[c->cur], 0, sizeof(double)*19*c->S, c->stream));
   k_from_reference<<<nblk((int64_t)c->nxl*c->P, 256), 256, 0, c->stream>>>(s, c->g[c->cur], a);
   KERNEL_CHECK(c);

@@ -71,9 +71,9 @@ void preinlet_destroy(hcg_ctx* c) {
   PreInletState* p = c->preinlet;
   if (!p) return;
   cudaSetDevice(p->pre_device); cudaFree(p->d_src_idx); if (p->buf_src != p->buf_dst) cudaFree(p->buf_src);   // (the pre-inlet context itself may be gone already)
+  if (p->ev_ready) cudaEventDestroy(p->ev_ready);
   cudaSetDevice(c->dom.device);
   cudaFree(p->d_dst_idx); cudaFree(p->buf_dst);
-  if (p->ev_ready) cudaEventDestroy(p->ev_ready);
   if (p->ev_done) cudaEventDestroy(p->ev_done);
   delete p;
   c->preinlet = nullptr;
@@ -100,14 +100,14 @@ hcg_status hcg_preinlet_map(hcg_ctx* c, hcg_ctx* pre, int64_t n, const int64_t* 
     CUDA_TRY(c, cudaMemcpy(p->d_src_idx, pre_idx, sizeof(int64_t)*n, cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaMalloc(&p->buf_src, sizeof(double)*4*n));
   }
+  CUDA_TRY(c, cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming));   // recorded on the pre-inlet's stream: lives on its device
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
   if (n) {
     CUDA_TRY(c, cudaMalloc(&p->d_dst_idx, sizeof(int64_t)*n));
     CUDA_TRY(c, cudaMemcpy(p->d_dst_idx, main_idx, sizeof(int64_t)*n, cudaMemcpyHostToDevice));
     if (same) p->buf_dst = p->buf_src; else CUDA_TRY(c, cudaMalloc(&p->buf_dst, sizeof(double)*4*n));
   }
-  CUDA_TRY(c, cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming));
-  CUDA_TRY(c, cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));    // recorded on the main stream
   return lat_bcn_ensure(c);
 }
 

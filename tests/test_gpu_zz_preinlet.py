@@ -77,9 +77,9 @@ def test_zouhe_nodes_collide_stream_parity(axis, tau, shape):
     ctx.close()
 
 
-def _gpu_pair(c):
+def _gpu_pair(c, pre_device=0):
     H = _lib()
-    pre = U.gpu_context(c['domp'], c['flp'], body=PC.BODY)
+    pre = U.gpu_context(c['domp'], c['flp'], body=PC.BODY, device=pre_device)
     main = U.gpu_context(c['domm'], c['flm'])
     for ctx in (pre, main):
         ctx.init_equilibrium(1.0, PC.U0)
@@ -107,13 +107,26 @@ def _oracle_by_id(sim, arr):
     return sim.cell_id[order], a[order]
 
 
-def test_preinlet_two_domains_match_the_oracle():
+def _n_gpus():
+    import ctypes as C
+    try:
+        rt = C.CDLL("libcudart.so.12"); n = C.c_int(0)
+        return n.value if rt.cudaGetDeviceCount(C.byref(n)) == 0 else 0
+    except OSError:
+        return 0
+
+
+@pytest.mark.parametrize("pre_device", [0, 1])
+def test_preinlet_two_domains_match_the_oracle(pre_device):
     """periodic force-driven pre-inlet duct -> Zou-He inlet of the main duct with a pressure outlet, tau = 1, two RBCs in
     the pre-inlet of which one is handed over at the first step: 30 passes of the main loop of
-    pipeflow_with_preinlet.cpp (iterate both, applyPreInlet) on the GPU vs the oracle"""
+    pipeflow_with_preinlet.cpp (iterate both, applyPreInlet) on the GPU vs the oracle.  pre_device = 1: the pre-inlet
+    context lives on a second GPU of the box (velocity buffer and cells cross by peer copies)"""
+    if pre_device >= max(_n_gpus(), 1):
+        pytest.skip("needs two GPUs")
     c = PC.build()
     opre, omain, cpl = PC.oracle_pair(c)
-    H, pre, main = _gpu_pair(c)
+    H, pre, main = _gpu_pair(c, pre_device)
     steps, handed_o, handed_g = 30, 0, 0
     for _ in range(steps):
         handed_o += PC.oracle_step(opre, omain, cpl)
