@@ -1761,6 +1761,10 @@ void gpu_lattice_boundary_density(GpuLattice* gp, const Box3D& domain_, double r
   }
   if (g.ctx) g.flush();
 }
+int gpu_lattice_flag(const GpuLattice* g, long x, long y, long z) {
+  if (x < 0 || y < 0 || z < 0 || x >= g->nx || y >= g->ny || z >= g->nz) return -1;
+  return g->flags[g->idx((int)x, (int)y, (int)z)];
+}
 std::string gpu_lattice_info(const GpuLattice* g) {
   std::ostringstream o;
   const int R = plb::global::mpi().getSize();

@@ -94,6 +94,7 @@ void gpu_lattice_define_flag(GpuLattice*, const plb::Box3D& domain, const plb::D
 void gpu_lattice_equilibrium(GpuLattice*, double rho, const double u[3]);
 void gpu_lattice_zouhe(GpuLattice*, const plb::Box3D& domain, int pressure, int orientation);   /* Zou-He velocity / pressure nodes */
 void gpu_lattice_boundary_density(GpuLattice*, const plb::Box3D& domain, double rho);
+int gpu_lattice_flag(const GpuLattice*, long x, long y, long z);   /* HCG_* node flag as recorded on the host */
 std::string gpu_lattice_info(const GpuLattice*);
 }
 

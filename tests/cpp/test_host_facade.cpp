@@ -23,6 +23,7 @@ int main(int argc, char** argv) {
         "<ibm><radius>3.91e-6</radius><stepMaterialEvery> 20 </stepMaterialEvery></ibm>\n"
         "<domain attr=\"x &amp; y\"><shearrate> 111.0 </shearrate><rhoP>1025</rhoP><nuP>1.1e-6</nuP><dx>0.5e-6</dx><dt>0.5e-7</dt>\n"
         "<particleEnvelope>20</particleEnvelope><kBT>4.100531391e-21</kBT><Re>0.5</Re><empty/></domain>\n"
+        "<preInlet><parameters><lengthN> 30 </lengthN><Re> 0.5 </Re></parameters></preInlet>\n"
         "<sim><tmax>10</tmax></sim></hemocell>\n");
   write("RBC.xml",
         "<?xml version=\"1.0\" ?><hemocell><MaterialModel><name>RBC</name><eta_m>0.0</eta_m><kBend>80.0</kBend><kVolume>20.0</kVolume>"
@@ -112,6 +113,54 @@ int main(int argc, char** argv) {
   CHECK("voxelizer.management", vd && vd->getMultiBlockManagement().getBoundingBox().getNx() == 103);
   param::lbm_pipe_parameters(*cfg, fm);
   CHECK("param.pipe_radius_from_fluid_area", close_rel(param::pipe_radius, std::sqrt(51.0*51.0/PI), 1e-12));
+  // helper/preInlet.h on that flag matrix (host side only: the pre-inlet is a second lattice of this process, no device yet)
+  {
+    hemocell.preInlet = new hemo::PreInlet(&hemocell, fm);
+    CHECK("preinlet.length", hemocell.preInlet->preinlet_length == 30 && !hemocell.partOfpreInlet);
+    Box3D slice = fm->getBoundingBox(); slice.x0 = slice.x1 = 2;
+    hemocell.preInlet->preInletFromSlice(Direction::Xneg, slice);
+    const Box3D loc = hemocell.preInlet->location;
+    // fluid cross-section 1..51 in y and z, one solid node around it, lengthN planes towards -x (helper/preInlet.cpp:511-519)
+    CHECK("preinlet.location", loc.x0 == 1 - 30 && loc.x1 == 3 && loc.y0 == 0 && loc.y1 == 52 && loc.z0 == 0 && loc.z1 == 52);
+    CHECK("preinlet.inflow_length", hemocell.preInlet->inflow_length == 20);
+    hemocell.cellfields->lattice = nullptr;
+    hemocell.initializeLattice(vd->getMultiBlockManagement());
+    long n[3]; hemo::gpu_lattice_size(hemocell.preInlet->pre, n);
+    CHECK("preinlet.lattice_size", n[0] == 33 && n[1] == 53 && n[2] == 53);
+    hemocell.lattice->periodicity().toggleAll(false);
+    hemocell.preInlet->initializePreInlet();
+    const Box3D in = hemocell.preInlet->fluidInlet;
+    CHECK("preinlet.fluidInlet_plane", in.x0 == 3 && in.x1 == 3 && in.y0 == 0 && in.y1 == 52);
+    boundaryFromFlagMatrix(hemocell.lattice, fm, hemocell.partOfpreInlet);
+    hemocell.preInlet->createBoundary();
+    int zh = 0, bb = 0;
+    for (int y = 0; y < 53; y++) for (int z = 0; z < 53; z++) {
+      const int f = hemo::gpu_lattice_flag(hemocell.lattice->gpu(), 3, y, z);
+      zh += f == HCG_ZH_VEL_XN; bb += f == HCG_BOUNCEBACK;
+    }
+    CHECK("preinlet.inlet_nodes", zh == 51*51 && bb == 53*53 - 51*51);
+    CHECK("preinlet.main_stays_fluid_elsewhere", hemo::gpu_lattice_flag(hemocell.lattice->gpu(), 4, 26, 26) == HCG_FLUID);
+    int pre_bb = 0;
+    for (int x = 0; x < 33; x++) for (int y = 0; y < 53; y++) for (int z = 0; z < 53; z++) pre_bb += hemo::gpu_lattice_flag(hemocell.preInlet->pre, x, y, z) == HCG_BOUNCEBACK;
+    CHECK("preinlet.extruded_cross_section", pre_bb == 33*(53*53 - 51*51));
+    CHECK("preinlet.periodic_along_the_flow", hemo::gpu_lattice_get_periodic(hemocell.preInlet->pre, 0) && !hemo::gpu_lattice_get_periodic(hemocell.preInlet->pre, 1)
+                                              && !hemo::gpu_lattice_get_periodic(hemocell.lattice->gpu(), 0));
+    hemocell.preInlet->calculateDrivingForce();
+    const double r = std::sqrt(51.0*51.0/PI), u = 0.5*param::nu_lbm/(2*r);
+    CHECK("preinlet.driving_force", close_rel(hemocell.preInlet->drivingForce, 8*param::nu_lbm*(u*0.5)/r/r, 1e-13));
+    // Zou-He outlet as pipeflow_with_preinlet.cpp:125-133 writes it (three planes, density 1)
+    Box3D lb = hemocell.lattice->getBoundingBox();
+    OnLatticeBoundaryCondition3D<T, DESCRIPTOR>* boundary = new BoundaryConditionInstantiator3D<T, DESCRIPTOR, WrappedZouHeBoundaryManager3D<T, DESCRIPTOR>>();
+    boundary->addPressureBoundary0P(Box3D(lb.x1 - 2, lb.x1, lb.y0, lb.y1, lb.z0, lb.z1), *hemocell.lattice, boundary::density);
+    setBoundaryDensity(*hemocell.lattice, Box3D(lb.x1 - 2, lb.x1, lb.y0, lb.y1, lb.z0, lb.z1), 1.0);
+    CHECK("zouhe.pressure_outlet", hemo::gpu_lattice_flag(hemocell.lattice->gpu(), lb.x1 - 1, 26, 26) == HCG_ZH_PRES_XP
+                                   && hemo::gpu_lattice_flag(hemocell.lattice->gpu(), lb.x1, 0, 0) == HCG_BOUNCEBACK);
+    delete boundary;
+    // pulsatile driving force helpers (helper/preInlet.cpp:860-890)
+    std::vector<double> xs = {0.0, 1.0, 2.0}, ys = {1.0, 3.0, 2.0};
+    CHECK("preinlet.interpolate", close_rel(hemocell.preInlet->interpolate(xs, ys, 0.5, false), 2.0, 1e-15) && close_rel(hemocell.preInlet->interpolate(xs, ys, 1.5, false), 2.5, 1e-15)
+                                  && close_rel(hemocell.preInlet->interpolate(xs, ys, 5.0, false), 2.0, 1e-15) && close_rel(hemocell.preInlet->average(ys), 2.0, 1e-15));
+  }
   delete vd; delete fm;
   std::printf("%d failures\n", failures);
   return failures;
