@@ -267,7 +267,11 @@ def run_cuda(args):
     # the contract figure) or, at tau = 1 after a moments pass, k_collide_tau1 (32 B raw moments + 32 B force read,
     # 19 populations written = 216 B/LU)
     gen = timers.get("kernel:k_collide_stream", (0.0, 0)); t1 = timers.get("kernel:k_collide_tau1", (0.0, 0))
-    if t1[0] > gen[0]:
+    mo = timers.get("kernel:k_moment_step", (0.0, 0))
+    if mo[0] > max(gen[0], t1[0]):
+        # opt-in moment-only update (HCG_MOMENT_ONLY=1): 64 B read + 96 B written per lattice update
+        k1_name, (k1_ms, k1_calls), b_lu = "k_moment_step", mo, 160.0
+    elif t1[0] > gen[0]:
         k1_name, (k1_ms, k1_calls), b_lu = "k_collide_tau1", t1, B_LU_TAU1
     else:
         k1_name, (k1_ms, k1_calls), b_lu = "k_collide_stream", gen, B_LU

@@ -169,7 +169,12 @@ hcg_status step(hcg_ctx* c) {
   if (have_p) { OpTimer t(c, "spreadParticleForce"); if ((s = do_spread(c))) return s; }
   const bool interp = have_p && (c->iter % c->ts_vel == 0);
   bool fused = false;
-  if (interp) { OpTimer t(c, "collideAndStream+moments"); if ((s = lat_collide_moments_overlapped(c, &fused))) return s; }
+  if (lat_moment_eligible(c)) {
+    // tau = 1, fully periodic, no walls, opt-in: the moments are the state, one kernel replaces collision + moments pass
+    OpTimer t(c, "collideAndStream"); if ((s = lat_moment_step(c, interp))) return s;
+    fused = true;
+  }
+  if (interp && !fused) { OpTimer t(c, "collideAndStream+moments"); if ((s = lat_collide_moments_overlapped(c, &fused))) return s; }
   if (!fused) { OpTimer t(c, "collideAndStream"); if ((s = lat_collide_stream(c, !interp))) return s; }
   if (interp) {
     // interpolation and advance share one pass over the particles (advance uses the velocity just interpolated)
@@ -290,7 +295,7 @@ void hcg_destroy(hcg_ctx* c) {
   preinlet_destroy(c);
   peer_destroy(c);
   if (c->nccl) ncclCommDestroy((ncclComm_t)c->nccl);
-  cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); if (c->F0) cudaFree(c->F0); if (c->bcn) cudaFree(c->bcn); if (c->d_qsets) cudaFree(c->d_qsets); cudaFree(c->flags); cudaFree(c->d_bc);
+  cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); if (c->F0) cudaFree(c->F0); if (c->bcn) cudaFree(c->bcn); if (c->W2) cudaFree(c->W2); if (c->F2) cudaFree(c->F2); if (c->d_qsets) cudaFree(c->d_qsets); cudaFree(c->flags); cudaFree(c->d_bc);
   if (c->rho) cudaFree(c->rho);
   if (c->fused_done) cudaFree(c->fused_done);
   for (int k = 0; k < 3; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->frc[k]); cudaFree(c->frep[k]); }
@@ -790,6 +795,13 @@ hcg_status hcg_set_repulsion(hcg_ctx* c, int32_t on, double k, double cut) {
 hcg_status hcg_set_wall_repulsion(hcg_ctx* c, int32_t on, double k, double cut) {
   if (!c || (on && !(cut > 0))) return HCG_ERR_ARG;
   c->wall_on = on != 0; c->wall_k = k; c->wall_cut = cut; return HCG_OK;
+}
+hcg_status hcg_set_moment_only(hcg_ctx* c, int32_t on) {
+  if (!c) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (!on) { hcg_status s = lat_ensure_pops(c); if (s) return s; }      // back to stored populations
+  c->mo_mode = on ? 1 : 0;
+  return HCG_OK;
 }
 hcg_status hcg_set_spread_mode(hcg_ctx* c, int32_t mode, int32_t resort_every) {
   if (!c || mode < 0 || mode > 1 || resort_every < 1) return HCG_ERR_ARG;

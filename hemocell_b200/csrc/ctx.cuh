@@ -101,6 +101,10 @@ struct hcg_ctx {
   bool f_clean = false;         // the node force holds exactly the reset value (body / F0) everywhere: re-applying it is free
   double* F0 = nullptr;         // optional per-node driving force the node force is reset to (AoS [n][4]); null = uniform body[3]
   double* W = nullptr; bool w_valid = false;   // tau = 1 fast path: raw moments (rhoBar, j) of the current populations, AoS [n][4]
+  // moment-only update at tau = 1 (lattice.cu: k_moment_step; opt-in): second W / F buffers = the inputs of the last such step
+  double* W2 = nullptr; double* F2 = nullptr;
+  bool pops_stale = false;     // the populations lag behind W (materialised on demand by lat_ensure_pops)
+  int mo_mode = -1;            // -1 = follow HCG_MOMENT_ONLY, 0 = off, 1 = on (hcg_set_moment_only)
   uint8_t* flags;
   bool u_valid, has_velbc, has_nonfluid;
   bool has_iobc = false;       // Zou-He velocity / pressure nodes present (flags >= HCG_ZH_VEL_XN)
@@ -191,6 +195,9 @@ hcg_status lat_pop_to_reference(hcg_ctx* c, double* dst_dev);      // S_q(n) = g
 hcg_status lat_pop_from_reference(hcg_ctx* c, const double* src_dev);
 hcg_status lat_pineq(hcg_ctx* c, double* dst_dev);                 // off-equilibrium momentum flux, compact SoA [6][Nl]
 hcg_status lat_velocity_stats(hcg_ctx* c, double* vmin, double* vmax, double* vmean);
+bool lat_moment_eligible(hcg_ctx* c);
+hcg_status lat_moment_step(hcg_ctx* c, bool write_u);
+hcg_status lat_ensure_pops(hcg_ctx* c);
 hcg_status lat_bcn_ensure(hcg_ctx* c);
 hcg_status lat_bcn_scatter(hcg_ctx* c, int64_t n, const int64_t* idx_dev, const double* val_dev, bool keep_rho, cudaStream_t st);
 hcg_status lat_node_velocity(hcg_ctx* c, int64_t n, const int64_t* idx_dev, double* out_dev, cudaStream_t st);   // out [n][4] = (u, rho)

@@ -386,6 +386,72 @@ k_moments(const double* __restrict__ g, double* __restrict__ F, double* __restri
   if (RESET) { double2* Fw = reinterpret_cast<double2*>(F + 4*n); Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0); }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Moment-only update at tau = 1 (EXPERIMENTAL, opt-in: HCG_MOMENT_ONLY=1 or hcg_set_moment_only; written at the end of round 1,
+// NOT yet run or measured on a GPU).  With omega = 1 the post-collision population f*_q(n) is a function of the four raw
+// moments and the force of node n alone (guo_collide_tau1), and the next post-stream moments of node m are sums over
+// S_q(m) = f*_q(m - c_q).  On a fully periodic lattice without walls the populations therefore need not be stored at all: one
+// kernel reads (W, F) of the 19 upstream neighbours (each node's 64 B come from HBM once and 18 more times from L1 / L2),
+// evaluates the 19 arriving populations in the summation order of moments19 and writes the new moments, the node velocity
+// the IBM interpolation reads (on interpolation steps) and the reset force: 64 B read + 96 B written per lattice update
+// instead of 216 + 280.  W and F are double-buffered (a neighbour still reads the old force while this node resets it); the
+// previous pair stays intact until the next step, so the populations can be materialised on demand (lat_ensure_pops) for
+// downloads, output, checkpoints and any operator that needs them.
+template <bool WRITE_U>
+__global__ void __launch_bounds__(256)
+k_moment_step(const double* __restrict__ Win, const double* Fin, double* __restrict__ Wout, double* __restrict__ Fout,
+              double* __restrict__ U, LatArgs a, int64_t count) {
+  constexpr int CX[19] = {0,-1,0,0,-1,-1,-1,-1,0,0, 1,0,0,1,1,1,1,0,0};
+  constexpr int CY[19] = {0,0,-1,0,-1,1,0,0,-1,-1, 0,1,0,1,-1,0,0,1,1};
+  constexpr int CZ[19] = {0,0,0,-1,0,0,-1,1,-1,1, 0,0,1,0,0,1,-1,1,-1};
+  constexpr double T0 = 1.0/3.0, T1 = 1.0/18.0, T2 = 1.0/36.0;
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t n = i + a.P;
+  const int rem = (int)(i % a.P);
+  const int y = rem / a.nz, z = rem - y*a.nz;
+  const int nz = a.nz, ny = a.ny;
+  // source = this - c (periodic in y and z; x through the ghost planes)
+  const int64_t oyp = (y + 1 < ny) ? nz : -(int64_t)(ny - 1)*nz, oym = (y > 0) ? -nz : (int64_t)(ny - 1)*nz;
+  const int64_t ozp = (z + 1 < nz) ? 1 : -(nz - 1), ozm = (z > 0) ? -1 : nz - 1;
+  double rb = 0.0, j0 = 0.0, j1 = 0.0, j2 = 0.0;
+  double own0 = 0.0, own1 = 0.0, own2 = 0.0;
+#pragma unroll
+  for (int q = 0; q < 19; q++) {
+    int64_t off = n - (int64_t)CX[q]*a.P;
+    if (CY[q] == 1) off += oym; else if (CY[q] == -1) off += oyp;
+    if (CZ[q] == 1) off += ozm; else if (CZ[q] == -1) off += ozp;
+    double w0, w1, w2, w3, f0, f1, f2, f3;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w0), "=d"(w1), "=d"(w2), "=d"(w3) : "l"(Win + 4*off));
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(f0), "=d"(f1), "=d"(f2), "=d"(f3) : "l"(Fin + 4*off) : "memory");
+    if (q == 0) { own0 = f0; own1 = f1; own2 = f2; }
+    const double rho = 1.0 + w0, invRho = 1.0/rho;
+    const double ux = w1*invRho + 0.5*f0, uy = w2*invRho + 0.5*f1, uz = w3*invRho + 0.5*f2;
+    const double jx = rho*ux, jy = rho*uy, jz = rho*uz;
+    const double jSqr = jx*jx + jy*jy + jz*jz;
+    const double uF = ux*f0 + uy*f1 + uz*f2;
+    const double t = (q == 0) ? T0 : ((q <= 3 || (q >= 10 && q <= 12)) ? T1 : T2);
+    const double cj = CX[q]*jx + CY[q]*jy + CZ[q]*jz;
+    const double cu = CX[q]*ux + CY[q]*uy + CZ[q]*uz;
+    const double cF = CX[q]*f0 + CY[q]*f1 + CZ[q]*f2;
+    const double ft = 3.0*(cF - uF) + 9.0*cu*cF;
+    const double fq = feq(t, cj, w0, invRho, jSqr) + t*0.5*ft;         // guo_collide_tau1, population q of the upstream node
+    rb += fq;                                                          // moments19's order
+    if (CX[q] == 1) j0 += fq; else if (CX[q] == -1) j0 -= fq;
+    if (CY[q] == 1) j1 += fq; else if (CY[q] == -1) j1 -= fq;
+    if (CZ[q] == 1) j2 += fq; else if (CZ[q] == -1) j2 -= fq;
+  }
+  double2* Ww = reinterpret_cast<double2*>(Wout + 4*n);
+  Ww[0] = make_double2(rb, j0); Ww[1] = make_double2(j1, j2);
+  if (WRITE_U) {
+    const double rho = 1.0 + rb, invRho = 1.0/rho;
+    double2* Uw = reinterpret_cast<double2*>(U + 4*n);
+    Uw[0] = make_double2(j0*invRho + 0.5*own0, j1*invRho + 0.5*own1); Uw[1] = make_double2(j2*invRho + 0.5*own2, rho);
+  }
+  double2* Fw = reinterpret_cast<double2*>(Fout + 4*n);
+  Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0);
+}
+
 // Off-equilibrium momentum flux of the post-stream populations (output path only: the "ShearStress"
 // and "StrainRate" fluid fields of io/FluidHdf5IO.hh:406-433, 503-541 are multiples of it):
 //   PiNeq_ab = sum_q c_qa c_qb fbar_q - cs2 rhoBar delta_ab - j_a j_b / rho,  order xx xy xz yy yz zz
@@ -1056,6 +1122,7 @@ hcg_status lat_collide_rows(hcg_ctx* c, bool reset_force, int row0, int row1, cu
 }
 
 hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
+  { hcg_status sp = lat_ensure_pops(c); if (sp) return sp; }
   {
     OpTimer tk(c, (c->W && c->w_valid && c->omega == 1.0) ? "kernel:k_collide_tau1" : "kernel:k_collide_stream");
     // a per-node driving force (F0) is restored by a copy after the kernel instead of the in-kernel reset
@@ -1099,7 +1166,50 @@ static hcg_status moments_rows(hcg_ctx* c, bool reset_force, int row0, int row1)
   return HCG_OK;
 }
 
+// ---- moment-only update (k_moment_step): eligibility, the step, and materialising the populations on demand
+static bool moment_only_env() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("HCG_MOMENT_ONLY"); on = e ? atoi(e) : 0; }
+  return on != 0;
+}
+bool lat_moment_eligible(hcg_ctx* c) {
+  const bool want = c->mo_mode < 0 ? moment_only_env() : c->mo_mode != 0;
+  return want && tau1_enabled() && c->omega == 1.0 && c->dom.n_ranks == 1 && c->dom.periodic[0] && c->dom.periodic[1] && c->dom.periodic[2]
+      && !c->has_nonfluid && !c->real_nonfluid && !c->has_velbc && !c->has_iobc && !c->F0 && c->W && c->w_valid;
+}
+hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
+  hcg_status s = ensure_qsets(c); if (s) return s;
+  if (!c->W2) {
+    CUDA_TRY(c, cudaMalloc(&c->W2, sizeof(double)*4*c->S)); CUDA_TRY(c, cudaMalloc(&c->F2, sizeof(double)*4*c->S));
+    CUDA_TRY(c, cudaMemsetAsync(c->W2, 0, sizeof(double)*4*c->S, c->stream)); CUDA_TRY(c, cudaMemsetAsync(c->F2, 0, sizeof(double)*4*c->S, c->stream));
+  }
+  // ghost planes of the moments and of the (spread) force: periodic images of the end planes
+  if ((s = exchange(c, c->W, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
+  if ((s = exchange(c, c->F, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
+  LatArgs a = make_args(c);
+  {
+    OpTimer tk(c, "kernel:k_moment_step");
+    if (write_u) k_moment_step<true><<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, c->Nl);
+    else k_moment_step<false><<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, c->Nl);
+    KERNEL_CHECK(c);
+  }
+  std::swap(c->W, c->W2); std::swap(c->F, c->F2);           // W2 / F2 now hold the inputs of this step (kept for lat_ensure_pops)
+  c->pops_stale = true; c->w_valid = true; c->u_valid = write_u; c->f_clean = true;
+  if (write_u) return lat_halo_exchange_u(c);
+  return HCG_OK;
+}
+// the populations of the current state from the inputs of the last moment-only step: g_q(n) = f*_q(n) (k_collide_tau1)
+hcg_status lat_ensure_pops(hcg_ctx* c) {
+  if (!c->pops_stale) return HCG_OK;
+  LatArgs a = make_args(c);
+  k_collide_tau1<false, 0, false><<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->g[1 - c->cur], c->g[c->cur], c->F2, c->W2, c->flags, a, 0, c->Nl, nullptr, nullptr);
+  KERNEL_CHECK(c);
+  c->pops_stale = false;
+  return lat_halo_exchange_pop(c);
+}
+
 hcg_status lat_pineq(hcg_ctx* c, double* dst_dev) {
+  { hcg_status sp = lat_ensure_pops(c); if (sp) return sp; }
   LatArgs a = make_args(c);
   k_pineq<<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->g[c->cur], c->flags, a, c->Nl, dst_dev);
   KERNEL_CHECK(c);
@@ -1108,6 +1218,7 @@ hcg_status lat_pineq(hcg_ctx* c, double* dst_dev) {
 
 hcg_status lat_moments(hcg_ctx* c, bool reset_force, bool want_rho) {
   (void)want_rho;   // the density always rides in slot 3 of the node velocity
+  { hcg_status sp = lat_ensure_pops(c); if (sp) return sp; }
   {
     OpTimer tk(c, "kernel:k_moments");
     if (!c->W && c->omega == 1.0 && tau1_enabled()) {      // tau = 1: keep the raw moments for the next collision
@@ -1128,6 +1239,7 @@ hcg_status lat_moments(hcg_ctx* c, bool reset_force, bool want_rho) {
 // (the caller then runs the two passes back to back).
 hcg_status lat_collide_moments_overlapped(hcg_ctx* c, bool* done_out) {
   *done_out = false;
+  { hcg_status sp = lat_ensure_pops(c); if (sp) return sp; }
   static int env_on = -1;
   if (env_on < 0) { const char* e = getenv("HCG_OVERLAP"); env_on = e ? atoi(e) : 0; }   // opt-in (needs HCG_K1_ROWS=1): measured slower, DESIGN.md §4
   const int ny = c->dom.ny, nxl = c->nxl;
@@ -1198,11 +1310,12 @@ hcg_status lat_init_equilibrium(hcg_ctx* c, double rho, const double u[3]) {
   KERNEL_CHECK(c);
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   cudaFree(dv);
-  c->u_valid = false; c->w_valid = false;
+  c->u_valid = false; c->w_valid = false; c->pops_stale = false;
   return lat_halo_exchange_pop(c);
 }
 
 hcg_status lat_pop_to_reference(hcg_ctx* c, double* dst_dev) {
+  { hcg_status sp = lat_ensure_pops(c); if (sp) return sp; }
   LatArgs a = make_args(c);
   k_to_reference<<<nblk((int64_t)c->nxl*c->P, 256), 256, 0, c->stream>>>(c->g[c->cur], dst_dev, a);
   KERNEL_CHECK(c);
@@ -1210,6 +1323,7 @@ hcg_status lat_pop_to_reference(hcg_ctx* c, double* dst_dev) {
 }
 
 hcg_status lat_pop_from_reference(hcg_ctx* c, const double* src_dev) {
+  c->pops_stale = false;                                  // the uploaded populations replace whatever state there was
   LatArgs a = make_args(c);
   double* s = c->g[1 - c->cur];
   CUDA_TRY(c, cudaMemsetAsync(s, 0, sizeof(double)*19*c->S, c->stream));
@@ -1264,6 +1378,7 @@ hcg_status lat_bcn_scatter(hcg_ctx* c, int64_t n, const int64_t* idx_dev, const 
 }
 hcg_status lat_node_velocity(hcg_ctx* c, int64_t n, const int64_t* idx_dev, double* out_dev, cudaStream_t st) {
   if (n <= 0) return HCG_OK;
+  { hcg_status sp = lat_ensure_pops(c); if (sp) return sp; }
   LatArgs a = make_args(c);
   k_node_velocity<<<nblk(n, 256), 256, 0, st>>>(c->g[c->cur], c->F, c->flags, a, n, idx_dev, out_dev);
   KERNEL_CHECK(c);

@@ -56,7 +56,7 @@ hcg_op_spread hcg_op_collide_stream hcg_op_interpolate hcg_op_sync hcg_op_advanc
 hcg_op_zero_force hcg_cells_bbox hcg_cells_volume_area hcg_cells_stretch hcg_fluid_velocity_stats hcg_timers_enable
 hcg_timers hcg_timers_reset hcg_launch_count hcg_synchronize hcg_iterate_timed
 hcg_lattice_set_bc_nodes hcg_lattice_node_velocity hcg_cells_reserve hcg_preinlet_map hcg_preinlet_apply_velocity
-hcg_preinlet_apply_cells hcg_preinlet_laps""".split()
+hcg_preinlet_apply_cells hcg_preinlet_laps hcg_set_moment_only""".split()
 
 _lib = None
 
@@ -279,6 +279,9 @@ class Context:
 
     def set_wall_repulsion(self, on, k, cutoff):
         self._ck(self.L.hcg_set_wall_repulsion(self.h, C.c_int32(int(on)), C.c_double(k), C.c_double(cutoff)))
+
+    def set_moment_only(self, on):
+        self._ck(self.L.hcg_set_moment_only(self.h, C.c_int32(int(on))))
 
     def set_spread_mode(self, mode=1, resort_every=20):
         self._ck(self.L.hcg_set_spread_mode(self.h, C.c_int32(mode), C.c_int32(resort_every)))

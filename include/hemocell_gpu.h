@@ -179,6 +179,11 @@ hcg_status hcg_set_wall_repulsion(hcg_ctx*, int32_t enabled, double k, double cu
 /* spreading strategy: 1 (default) = per-cell node-sorted (vertex, corner) pairs + warp-level reduction in
  * front of the fp64 atomics, permutation rebuilt every `resort_every` steps; 0 = one atomic per pair */
 hcg_status hcg_set_spread_mode(hcg_ctx*, int32_t mode, int32_t resort_every);
+/* EXPERIMENTAL (not yet measured): at tau = 1 on a fully periodic lattice without walls (cases/performance_testing) the lattice
+ * state can be the four raw moments per node instead of the 19 populations; 1 = one kernel per step reads the neighbours'
+ * moments and forces and writes the new moments (populations are materialised on demand), 0 = stored populations.  Default:
+ * environment HCG_MOMENT_ONLY (off). */
+hcg_status hcg_set_moment_only(hcg_ctx*, int32_t on);
 /* multi-GPU particle exchange (replaces particleEnvelope of config.xml and the comm. structure of
  * HemoCellFields::calculateCommunicationStructure, core/hemoCellFields.cpp:363-372): a rank holds
  * every cell within `margin_lu` of its slab, membership is re-evaluated every `sync_every` steps,
