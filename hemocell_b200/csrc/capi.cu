@@ -360,6 +360,7 @@ hcg_status hcg_comm_init(hcg_ctx* c, const void* id128) {
 hcg_status hcg_lattice_set_flags(hcg_ctx* c, const uint8_t* flags) {
   if (!c || !flags) return HCG_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  { hcg_status sp = lat_ensure_pops(c); if (sp) return sp; }    // (moment-only mode: materialise the populations under the old flags)
   bool vel = false, io = false;
   for (int64_t i = 0; i < c->Nl; i++) {
     if (flags[i] > HCG_ZH_PRES_ZP) return hcg_fail(c, HCG_ERR_ARG, "unknown node flag");
