@@ -67,6 +67,23 @@ Arr12 arrays_of(hcg_ctx* c) {
 
 }  // namespace
 
+// pure host logic of the hand-over (CPU-tested against the oracle's rule, tests/test_preinlet_oracle.py): cell i is taken when it is
+// alive, the periodic image k = ceil((slab_lo - (lo + shift)) / period) of its extent [lo, hi] + shift lies wholly inside
+// [slab_lo, slab_hi], and that image was not the one handed over last (last_lap)
+extern "C" void hch_preinlet_select(int64_t n, const double* lo, const double* hi, const uint8_t* alive, const int64_t* last_lap,
+                                    double shift, double period, double slab_lo, double slab_hi, int64_t* lap_out, uint8_t* take_out) {
+  for (int64_t i = 0; i < n; i++) {
+    take_out[i] = 0; lap_out[i] = 0;
+    if (!alive[i]) continue;
+    const double a = lo[i] + shift, b = hi[i] + shift;
+    const double k = std::ceil((slab_lo - a)/period);
+    if (b + k*period > slab_hi) continue;
+    lap_out[i] = (int64_t)k;
+    if (last_lap && last_lap[i] == (int64_t)k) continue;
+    take_out[i] = 1;
+  }
+}
+
 void preinlet_destroy(hcg_ctx* c) {
   PreInletState* p = c->preinlet;
   if (!p) return;
@@ -160,14 +177,11 @@ hcg_status hcg_preinlet_apply_cells(hcg_ctx* c, int32_t axis, double period, con
   if ((int64_t)p->last_lap.size() < npc) p->last_lap.resize(npc, INT64_MIN);
   // 2. candidates: the periodic image k of the cell lies wholly inside [slab_lo, slab_hi] (main coordinates, along `axis`)
   std::vector<int32_t> src; std::vector<int64_t> lap;
-  for (int64_t i = 0; i < npc; i++) {
-    if (!alive[i] || pre->h_cell_id[i] < 0) continue;
-    const double lo = bbox[6*i + 2*axis] + shift[axis], hi = bbox[6*i + 2*axis + 1] + shift[axis];
-    const double k = std::ceil((slab_lo - lo)/period);
-    if (hi + k*period > slab_hi) continue;
-    const int64_t kk = (int64_t)k;
-    if (p->last_lap[i] == kk) continue;
-    src.push_back((int32_t)i); lap.push_back(kk);
+  {
+    std::vector<double> lo(npc), hi(npc); std::vector<uint8_t> live(npc), take(npc); std::vector<int64_t> k(npc);
+    for (int64_t i = 0; i < npc; i++) { lo[i] = bbox[6*i + 2*axis]; hi[i] = bbox[6*i + 2*axis + 1]; live[i] = alive[i] && pre->h_cell_id[i] >= 0; }
+    hch_preinlet_select(npc, lo.data(), hi.data(), live.data(), p->last_lap.data(), shift[axis], period, slab_lo, slab_hi, k.data(), take.data());
+    for (int64_t i = 0; i < npc; i++) if (take[i]) { src.push_back((int32_t)i); lap.push_back(k[i]); }
   }
   if (src.empty()) return HCG_OK;
   // 3. free slots in the main domain: spare slots first, then slots of cells that have been deleted

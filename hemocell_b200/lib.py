@@ -369,7 +369,7 @@ class Context:
 # ------------------------------------------------------------------ host-side set-up (C++ in the same .so)
 HOST_SYMBOLS = """hch_parameters hch_celltype_build hch_celltype_view hch_celltype_vertices hch_celltype_scalar
 hch_celltype_free hch_read_pos hch_place_cells hch_slab_membership hch_slab_membership_at hch_last_error
-hch_h5_create hch_h5_attribute hch_h5_dataset hch_h5_close hch_voxelize_stl""".split()
+hch_h5_create hch_h5_attribute hch_h5_dataset hch_h5_close hch_voxelize_stl hch_preinlet_select""".split()
 
 RBC_MATERIAL = dict(kBend=80.0, kVolume=20.0, kArea=5.0, kLink=15.0, eta_m=0.0, minNumTriangles=600,
                     radius=3.91e-6, aspectRatio=0.3)
@@ -473,6 +473,20 @@ def slab_membership(xlo, xhi, nx, periodic_x, nxl, rank, n_ranks, margin):
     fn(C.c_int64(n), _p(xlo), _p(xhi), C.c_int32(nx), C.c_int32(int(periodic_x)), C.c_int32(nxl), C.c_int32(rank),
        C.c_int32(n_ranks), C.c_double(margin), *[_p(o, c_u8p) for o in out])
     return [o.astype(bool) for o in out]
+
+
+def preinlet_select(lo, hi, alive, last_lap, shift, period, slab_lo, slab_hi):
+    """hch_preinlet_select -> (lap, take)"""
+    lo = np.ascontiguousarray(lo, dtype=np.float64); hi = np.ascontiguousarray(hi, dtype=np.float64)
+    alive = np.ascontiguousarray(alive, dtype=np.uint8)
+    n = lo.shape[0]
+    lap = np.zeros(n, dtype=np.int64); take = np.zeros(n, dtype=np.uint8)
+    ll = None if last_lap is None else np.ascontiguousarray(last_lap, dtype=np.int64)
+    fn = load().hch_preinlet_select
+    fn.restype = None
+    fn(C.c_int64(n), _p(lo), _p(hi), _p(alive, c_u8p), None if ll is None else _p(ll, c_i64p), C.c_double(shift), C.c_double(period),
+       C.c_double(slab_lo), C.c_double(slab_hi), _p(lap, c_i64p), _p(take, c_u8p))
+    return lap, take.astype(bool)
 
 
 def read_pos(path):

@@ -51,6 +51,13 @@ void hch_slab_membership(int64_t n, const double* xlo, const double* xhi, int32_
 void hch_slab_membership_at(int64_t n, const double* xlo, const double* xhi, int32_t nx, int32_t periodic_x,
                             int32_t x0, int32_t nxl, int32_t rank, int32_t n_ranks, double margin,
                             uint8_t* held, uint8_t* share_left, uint8_t* share_right);
+/* hand-over rule of the pre-inlet (pure host logic of csrc/preinlet.cu; replaces the box tests of
+ * HemoCellParticleDataTransfer::send_preinlet / HemoCellParticleField::addParticlePreinlet, core/hemoCellParticleDataTransfer.cpp:99-121,
+ * core/hemoCellParticleField.cpp:237-282, in whole cells): from the extents [lo, hi] of the pre-inlet's cells along the flow axis decide
+ * which periodic image k (lap_out) lies wholly inside the inflow slab [slab_lo, slab_hi] of the main domain (extent + shift +
+ * k*period) and whether the cell is handed over now (take_out: alive, inside, and image k not handed over before: last_lap, may be NULL) */
+void hch_preinlet_select(int64_t n, const double* lo, const double* hi, const uint8_t* alive, const int64_t* last_lap,
+                         double shift, double period, double slab_lo, double slab_hi, int64_t* lap_out, uint8_t* take_out);
 /* STL voxeliser behind hemo::getFlagMatrixFromSTL (helper/voxelizeDomain.cpp:63-158; Palabos TriangleSet ->
  * DEFscaledMesh -> VoxelizedDomain3D in the reference).  dims_out[3] = lattice size; flags (may be NULL to query the
  * size) receives HCG_FLUID / HCG_BOUNCEBACK per node, index z + nz*(y + ny*x); dx_out = STL units per lattice unit.

@@ -130,3 +130,40 @@ def test_zouhe_channel_reproduces_plane_poiseuille_flow():
     mid = u[0, nx // 2, 1:-1, 0]
     assert np.max(np.abs(mid - prof[1:-1])) < 0.01 * umax
     assert np.max(np.abs(u[1, nx // 2])) < 1e-6 * umax
+
+
+def test_product_handover_rule_matches_the_oracle_rule():
+    """the host logic of hcg_preinlet_apply_cells (hch_preinlet_select, no device needed) takes the same cells under the same
+    periodic image as the oracle's PreInletCoupling.apply_cells, on random cell extents, both flow directions, repeated calls"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from hemocell_b200 import lib as H
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        n = int(rng.integers(1, 60))
+        period = float(rng.integers(20, 90))
+        shift = float(rng.integers(-50, 120))
+        slab_lo = float(rng.integers(0, 100)); slab_hi = slab_lo + float(rng.integers(5, 40))
+        lo = rng.uniform(-300, 300, n); hi = lo + rng.uniform(0.5, 18, n)
+        if trial % 5 == 0:                                   # exact hits on the slab edges
+            lo[0] = slab_lo - shift - 2 * period; hi[0] = slab_hi - shift - 2 * period
+        alive = rng.random(n) > 0.15
+        last = np.full(n, np.iinfo(np.int64).min, dtype=np.int64)
+        seen = {}
+        for step in range(4):
+            lap, take = H.preinlet_select(lo, hi, alive, last, shift, period, slab_lo, slab_hi)
+            for i in range(n):                               # the oracle's rule, cell by cell (oracle/__init__.py: PreInletCoupling.apply_cells)
+                a, b = lo[i] + shift, hi[i] + shift
+                k = np.ceil((slab_lo - a) / period)
+                inside = alive[i] and not (b + k * period > slab_hi)
+                want = inside and seen.get(i) != int(k)
+                assert bool(take[i]) == bool(want), (trial, step, i)
+                if inside:
+                    assert lap[i] == int(k)
+                    assert slab_lo <= a + k * period and b + k * period <= slab_hi
+                if want:
+                    seen[i] = int(k); last[i] = int(k)
+            drift = rng.uniform(-6, 6)
+            lo = lo + drift; hi = hi + drift
+    lap, take = H.preinlet_select([1.0], [3.0], [1], None, 0.0, 10.0, 0.0, 5.0)
+    assert take[0] and lap[0] == 0
