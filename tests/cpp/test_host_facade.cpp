@@ -161,6 +161,49 @@ int main(int argc, char** argv) {
     CHECK("preinlet.interpolate", close_rel(hemocell.preInlet->interpolate(xs, ys, 0.5, false), 2.0, 1e-15) && close_rel(hemocell.preInlet->interpolate(xs, ys, 1.5, false), 2.5, 1e-15)
                                   && close_rel(hemocell.preInlet->interpolate(xs, ys, 5.0, false), 2.0, 1e-15) && close_rel(hemocell.preInlet->average(ys), 2.0, 1e-15));
   }
+  // the other directions on a hand-made flag matrix: a 20 x 30 x 24 block, fluid inside a one-node solid shell that is open at both z ends
+  {
+    delete hemocell.preInlet; hemocell.preInlet = nullptr;
+    plb::MultiScalarField3D<int> box(20, 30, 24, 0);
+    for (int x = 1; x < 19; x++) for (int y = 1; y < 29; y++) for (int z = 0; z < 24; z++) box.get(x, y, z) = 1;
+    plb::VoxelizedDomain3D<T> vbox(20, 30, 24, 2);
+    hemocell.preInlet = new hemo::PreInlet(&hemocell, &box);
+    hemocell.preInlet->autoPreinletFromBoundary(Direction::Zpos);            // slice = second plane from the +z face
+    const Box3D loc = hemocell.preInlet->location;
+    CHECK("preinlet.zpos.location", loc.x0 == 0 && loc.x1 == 19 && loc.y0 == 0 && loc.y1 == 29 && loc.z0 == 21 && loc.z1 == 23 + 30);
+    hemocell.initializeLattice(vbox.getMultiBlockManagement());
+    long n[3]; hemo::gpu_lattice_size(hemocell.preInlet->pre, n);
+    CHECK("preinlet.zpos.lattice_size", n[0] == 20 && n[1] == 30 && n[2] == 33);
+    hemocell.preInlet->initializePreInlet();
+    const Box3D in = hemocell.preInlet->fluidInlet;
+    CHECK("preinlet.zpos.inlet_plane", in.z0 == 21 && in.z1 == 21 && in.x0 == 0 && in.x1 == 19);
+    boundaryFromFlagMatrix(hemocell.lattice, &box, false);
+    hemocell.preInlet->createBoundary();
+    int zh = 0;
+    for (int x = 0; x < 20; x++) for (int y = 0; y < 30; y++) zh += hemo::gpu_lattice_flag(hemocell.lattice->gpu(), x, y, 21) == HCG_ZH_VEL_ZP;
+    CHECK("preinlet.zpos.inlet_nodes_outward_plus_z", zh == 18*28);
+    CHECK("preinlet.zpos.periodic_z_only", hemo::gpu_lattice_get_periodic(hemocell.preInlet->pre, 2) && !hemo::gpu_lattice_get_periodic(hemocell.preInlet->pre, 0));
+    CHECK("preinlet.zpos.walls_extruded", hemo::gpu_lattice_flag(hemocell.preInlet->pre, 0, 5, 30) == HCG_BOUNCEBACK && hemo::gpu_lattice_flag(hemocell.preInlet->pre, 10, 15, 30) == HCG_FLUID);
+    hemocell.preInlet->calculateDrivingForce();
+    const double r = std::sqrt(18.0*28.0/PI), u = 0.5*param::nu_lbm/(2*r);
+    CHECK("preinlet.zpos.driving_force", close_rel(hemocell.preInlet->drivingForce, 8*param::nu_lbm*(u*0.5)/r/r, 1e-13));
+    // and a pre-inlet on the negative y side of the same block (opened at the y ends instead)
+    delete hemocell.preInlet; hemocell.preInlet = nullptr;
+    for (int x = 1; x < 19; x++) for (int z = 0; z < 24; z++) { box.get(x, 0, z) = z > 0 && z < 23; box.get(x, 29, z) = z > 0 && z < 23; }
+    for (int x = 0; x < 20; x++) for (int y = 0; y < 30; y++) { box.get(x, y, 0) = 0; box.get(x, y, 23) = 0; }
+    hemocell.preInlet = new hemo::PreInlet(&hemocell, &box);
+    Box3D sl = box.getBoundingBox(); sl.y0 = sl.y1 = 1;
+    hemocell.preInlet->preInletFromSlice(Direction::Yneg, sl);
+    const Box3D l2 = hemocell.preInlet->location;
+    CHECK("preinlet.yneg.location", l2.y0 == 0 - 30 && l2.y1 == 2 && l2.x0 == 0 && l2.x1 == 19 && l2.z0 == 0 && l2.z1 == 23);
+    hemocell.initializeLattice(vbox.getMultiBlockManagement());
+    hemocell.preInlet->initializePreInlet();
+    CHECK("preinlet.yneg.inlet_plane", hemocell.preInlet->fluidInlet.y0 == 2 && hemocell.preInlet->fluidInlet.y1 == 2);
+    int zy = 0;
+    for (int x = 0; x < 20; x++) for (int z = 0; z < 24; z++) zy += hemo::gpu_lattice_flag(hemocell.lattice->gpu(), x, 2, z) == HCG_ZH_VEL_YN;
+    CHECK("preinlet.yneg.inlet_nodes_outward_minus_y", zy == 18*22);
+    delete hemocell.preInlet; hemocell.preInlet = nullptr;
+  }
   delete vd; delete fm;
   std::printf("%d failures\n", failures);
   return failures;
