@@ -3,6 +3,7 @@
 // GuoExternalForceBGKdynamics / BounceBack / regularized velocity planes as HemoCell drives it
 // (reference core/hemoCell.cpp:317; arithmetic restated in SURVEY.md Appendix C).
 #include "ctx.cuh"
+#include "moment_step.cuh"
 #include <nccl.h>
 #include <cfloat>
 #include <cstdlib>
@@ -401,55 +402,10 @@ template <bool WRITE_U>
 __global__ void __launch_bounds__(256)
 k_moment_step(const double* __restrict__ Win, const double* Fin, double* __restrict__ Wout, double* __restrict__ Fout,
               double* __restrict__ U, LatArgs a, int64_t count) {
-  constexpr int CX[19] = {0,-1,0,0,-1,-1,-1,-1,0,0, 1,0,0,1,1,1,1,0,0};
-  constexpr int CY[19] = {0,0,-1,0,-1,1,0,0,-1,-1, 0,1,0,1,-1,0,0,1,1};
-  constexpr int CZ[19] = {0,0,0,-1,0,0,-1,1,-1,1, 0,0,1,0,0,1,-1,1,-1};
-  constexpr double T0 = 1.0/3.0, T1 = 1.0/18.0, T2 = 1.0/36.0;
   const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= count) return;
-  const int64_t n = i + a.P;
-  const int rem = (int)(i % a.P);
-  const int y = rem / a.nz, z = rem - y*a.nz;
-  const int nz = a.nz, ny = a.ny;
-  // source = this - c (periodic in y and z; x through the ghost planes)
-  const int64_t oyp = (y + 1 < ny) ? nz : -(int64_t)(ny - 1)*nz, oym = (y > 0) ? -nz : (int64_t)(ny - 1)*nz;
-  const int64_t ozp = (z + 1 < nz) ? 1 : -(nz - 1), ozm = (z > 0) ? -1 : nz - 1;
-  double rb = 0.0, j0 = 0.0, j1 = 0.0, j2 = 0.0;
-  double own0 = 0.0, own1 = 0.0, own2 = 0.0;
-#pragma unroll
-  for (int q = 0; q < 19; q++) {
-    int64_t off = n - (int64_t)CX[q]*a.P;
-    if (CY[q] == 1) off += oym; else if (CY[q] == -1) off += oyp;
-    if (CZ[q] == 1) off += ozm; else if (CZ[q] == -1) off += ozp;
-    double w0, w1, w2, w3, f0, f1, f2, f3;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w0), "=d"(w1), "=d"(w2), "=d"(w3) : "l"(Win + 4*off));
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(f0), "=d"(f1), "=d"(f2), "=d"(f3) : "l"(Fin + 4*off) : "memory");
-    if (q == 0) { own0 = f0; own1 = f1; own2 = f2; }
-    const double rho = 1.0 + w0, invRho = 1.0/rho;
-    const double ux = w1*invRho + 0.5*f0, uy = w2*invRho + 0.5*f1, uz = w3*invRho + 0.5*f2;
-    const double jx = rho*ux, jy = rho*uy, jz = rho*uz;
-    const double jSqr = jx*jx + jy*jy + jz*jz;
-    const double uF = ux*f0 + uy*f1 + uz*f2;
-    const double t = (q == 0) ? T0 : ((q <= 3 || (q >= 10 && q <= 12)) ? T1 : T2);
-    const double cj = CX[q]*jx + CY[q]*jy + CZ[q]*jz;
-    const double cu = CX[q]*ux + CY[q]*uy + CZ[q]*uz;
-    const double cF = CX[q]*f0 + CY[q]*f1 + CZ[q]*f2;
-    const double ft = 3.0*(cF - uF) + 9.0*cu*cF;
-    const double fq = feq(t, cj, w0, invRho, jSqr) + t*0.5*ft;         // guo_collide_tau1, population q of the upstream node
-    rb += fq;                                                          // moments19's order
-    if (CX[q] == 1) j0 += fq; else if (CX[q] == -1) j0 -= fq;
-    if (CY[q] == 1) j1 += fq; else if (CY[q] == -1) j1 -= fq;
-    if (CZ[q] == 1) j2 += fq; else if (CZ[q] == -1) j2 -= fq;
-  }
-  double2* Ww = reinterpret_cast<double2*>(Wout + 4*n);
-  Ww[0] = make_double2(rb, j0); Ww[1] = make_double2(j1, j2);
-  if (WRITE_U) {
-    const double rho = 1.0 + rb, invRho = 1.0/rho;
-    double2* Uw = reinterpret_cast<double2*>(U + 4*n);
-    Uw[0] = make_double2(j0*invRho + 0.5*own0, j1*invRho + 0.5*own1); Uw[1] = make_double2(j2*invRho + 0.5*own2, rho);
-  }
-  double2* Fw = reinterpret_cast<double2*>(Fout + 4*n);
-  Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0);
+  MomentArgs m; m.ny = a.ny; m.nz = a.nz; m.P = a.P; m.body[0] = a.body[0]; m.body[1] = a.body[1]; m.body[2] = a.body[2];
+  moment_node<WRITE_U>(Win, Fin, Wout, Fout, U, m, i);      // csrc/moment_step.cuh (also compiled for the host by tests/cpp/moment_host.cu)
 }
 
 // Off-equilibrium momentum flux of the post-stream populations (output path only: the "ShearStress"

@@ -48,3 +48,42 @@ def test_moment_only_update_equals_the_population_path():
         rho, vel = O.moments(dom, fl, pop, force)
         u = W[1:4] / (1.0 + W[0]) + 0.5 * force.reshape(3, nx, ny, nz)
         assert np.max(np.abs(u.reshape(-1) - vel)) < 1e-15
+
+
+def test_kernel_body_compiled_for_the_host_matches_the_numpy_restatement(tmp_path):
+    """the per-node body of k_moment_step (hemocell_b200/csrc/moment_step.cuh, host + device code) compiled for the CPU by nvcc
+    and run over a small lattice: node indexing with ghost planes, the y / z wrap, the arithmetic, the node velocity and the
+    force reset agree with the numpy restatement above (which the previous test ties to the oracle's population path)"""
+    import ctypes, os, shutil, subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        import pytest
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = tmp_path / "libmoment_host.so"
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+                           os.path.join(root, "tests", "cpp", "moment_host.cu"), "-o", str(so)])
+    lib = ctypes.CDLL(str(so))
+    nx, ny, nz = 7, 6, 5
+    rng = np.random.default_rng(9)
+    W = np.zeros((4, nx, ny, nz)); W[0] = 1e-3 * rng.standard_normal((nx, ny, nz)); W[1:] = 0.02 * rng.standard_normal((3, nx, ny, nz))
+    F = 1e-4 * rng.standard_normal((3, nx, ny, nz))
+    body = np.array([3e-6, -1e-6, 2e-6])
+
+    def padded(a4):      # [4, nx, ny, nz] -> AoS [(nx + 2), ny, nz, 4] with periodic ghost planes
+        a = np.moveaxis(a4, 0, -1)
+        return np.ascontiguousarray(np.concatenate([a[-1:], a, a[:1]], axis=0))
+
+    Win = padded(W); Fin = padded(np.concatenate([F, np.zeros((1, nx, ny, nz))]))
+    Wout = np.full_like(Win, np.nan); Fout = np.full_like(Win, np.nan); Uo = np.full_like(Win, np.nan)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.moment_host(nx, ny, nz, Win.ctypes.data_as(dp), Fin.ctypes.data_as(dp), Wout.ctypes.data_as(dp), Fout.ctypes.data_as(dp),
+                    Uo.ctypes.data_as(dp), body.ctypes.data_as(dp), 1)
+    ref = moment_step(W, F)
+    got = np.moveaxis(Wout[1:-1], -1, 0)
+    assert np.max(np.abs(got - ref)) < 1e-15 + 1e-13 * np.max(np.abs(ref))
+    u = ref[1:4] / (1.0 + ref[0]) + 0.5 * F
+    assert np.max(np.abs(np.moveaxis(Uo[1:-1], -1, 0)[:3] - u)) < 1e-15
+    assert np.max(np.abs(Uo[1:-1, ..., 3] - (1.0 + ref[0]))) < 1e-15
+    assert np.all(Fout[1:-1, ..., :3] == body) and np.all(Fout[1:-1, ..., 3] == 0.0)
+    assert np.isnan(Wout[0]).all() and np.isnan(Wout[-1]).all()            # ghost planes are the caller's business
