@@ -801,7 +801,7 @@ hcg_status hcg_set_moment_only(hcg_ctx* c, int32_t on) {
   if (!c) return HCG_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
   if (!on) { hcg_status s = lat_ensure_pops(c); if (s) return s; }      // back to stored populations
-  c->mo_mode = on ? 1 : 0;
+  c->mo_mode = on < 0 ? 0 : on;                                          // 1 = single rank, 2 = also slab-decomposed runs
   return HCG_OK;
 }
 hcg_status hcg_set_spread_mode(hcg_ctx* c, int32_t mode, int32_t resort_every) {

@@ -1123,14 +1123,16 @@ static hcg_status moments_rows(hcg_ctx* c, bool reset_force, int row0, int row1)
 }
 
 // ---- moment-only update (k_moment_step): eligibility, the step, and materialising the populations on demand
-static bool moment_only_env() {
+static int moment_only_env() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("HCG_MOMENT_ONLY"); on = e ? atoi(e) : 0; }
-  return on != 0;
+  return on;
 }
+// level 1 = single rank; level 2 = also slab-decomposed runs: the W and F face planes (and U on interpolation steps) go to the
+// neighbours' ghost planes through the NCCL send/recv exchange, whatever the transport of the population path is
 bool lat_moment_eligible(hcg_ctx* c) {
-  const bool want = c->mo_mode < 0 ? moment_only_env() : c->mo_mode != 0;
-  return want && tau1_enabled() && c->omega == 1.0 && c->dom.n_ranks == 1 && c->dom.periodic[0] && c->dom.periodic[1] && c->dom.periodic[2]
+  const int level = c->mo_mode < 0 ? moment_only_env() : c->mo_mode;
+  return level > 0 && (c->dom.n_ranks == 1 || level >= 2) && tau1_enabled() && c->omega == 1.0 && c->dom.periodic[0] && c->dom.periodic[1] && c->dom.periodic[2]
       && !c->has_nonfluid && !c->real_nonfluid && !c->has_velbc && !c->has_iobc && !c->F0 && c->W && c->w_valid;
 }
 hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {

@@ -181,7 +181,8 @@ hcg_status hcg_set_wall_repulsion(hcg_ctx*, int32_t enabled, double k, double cu
 hcg_status hcg_set_spread_mode(hcg_ctx*, int32_t mode, int32_t resort_every);
 /* EXPERIMENTAL (not yet measured): at tau = 1 on a fully periodic lattice without walls (cases/performance_testing) the lattice
  * state can be the four raw moments per node instead of the 19 populations; 1 = one kernel per step reads the neighbours'
- * moments and forces and writes the new moments (populations are materialised on demand), 0 = stored populations.  Default:
+ * moments and forces and writes the new moments (populations are materialised on demand), 2 = the same on slab-decomposed runs
+ * (W / F face planes exchanged with NCCL send/recv; every rank must use the same setting), 0 = stored populations.  Default:
  * environment HCG_MOMENT_ONLY (off). */
 hcg_status hcg_set_moment_only(hcg_ctx*, int32_t on);
 /* multi-GPU particle exchange (replaces particleEnvelope of config.xml and the comm. structure of
