@@ -73,3 +73,118 @@ def test_reference_curvedflow_with_preinlet_smoke(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     vmean = [float(x) for x in re.findall(r"m/s, mean: (\S+) m/s", r.stdout)]
     assert len(vmean) >= 3 and all(np.isfinite(v) and v > 0 for v in vmean), r.stdout[-2000:]
+
+
+def _two_rank_fluid(dims, periodic, tau, fl, transport, setup, steps, moment_only=0):
+    """two contexts (one per GPU, one thread each): fluid only; returns the per-rank population slabs"""
+    import threading
+    from hemocell_b200 import lib as H
+    nx, ny, nz = dims
+    uid = H.Context.unique_id()
+    out, err = [None, None], [None, None]
+    fl3 = fl.reshape(nx, ny, nz)
+
+    def work(r):
+        try:
+            ctx = H.Context(nx, ny, nz, periodic, tau, device=r, rank=r, n_ranks=2)
+            ctx.set_transport(transport)
+            ctx.comm_init(uid)
+            ctx.set_flags(np.ascontiguousarray(fl3[ctx.x0:ctx.x0 + ctx.nxl]))
+            setup(ctx)
+            if moment_only:
+                ctx.set_moment_only(moment_only)
+            for it in range(steps):
+                if moment_only and it % 4 == 0:
+                    ctx.lattice_download(H.LAT_DENSITY)        # a moments pass (materialises the populations): W is valid, the next steps are eligible
+                ctx.iterate(1)
+            out[r] = dict(x0=ctx.x0, nxl=ctx.nxl, pop=ctx.lattice_download(H.LAT_POP))
+            ctx.close()
+        except Exception as e:          # noqa: BLE001
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+def _ngpus():
+    import ctypes as C
+    try:
+        rt = C.CDLL("libcudart.so.12"); n = C.c_int(0)
+        return n.value if rt.cudaGetDeviceCount(C.byref(n)) == 0 else 0
+    except OSError:
+        return 0
+
+
+@pytest.mark.parametrize("transport", [1, 0])
+def test_two_gpu_zouhe_duct_matches_oracle(transport):
+    """Zou-He velocity inlet on rank 0's first plane, pressure outlet on rank 1's last plane, bounce-back duct walls, x not
+    periodic: the slab-decomposed lattice (BC = 2 kernels with peer stores / NCCL exchange) against the oracle"""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    nx, ny, nz = 40, 14, 12
+    N = nx * ny * nz
+    tau = 0.9
+    fl = np.zeros((nx, ny, nz), dtype=np.uint8)
+    fl[:, 0, :] = 1; fl[:, -1, :] = 1; fl[:, :, 0] = 1; fl[:, :, -1] = 1
+    inner = fl[0] == 0
+    fl[0][inner] = 8; fl[-1][inner] = 15
+    fl = fl.reshape(-1)
+    dom = O.make_domain(nx, ny, nz, (0, 0, 0), tau)
+    rng = np.random.default_rng(3)
+    nodes = np.nonzero(fl >= 8)[0]
+    val = np.column_stack([0.02 + 0.005 * rng.standard_normal(nodes.size), 0.002 * rng.standard_normal((nodes.size, 2)),
+                           1.0 + 1e-3 * rng.standard_normal(nodes.size)])
+    bc = np.zeros((4, N)); bc[3] = 1.0; bc[:, nodes] = val.T
+    bc = np.ascontiguousarray(bc.reshape(-1))
+    P = ny * nz
+
+    def setup(ctx):
+        lo, hi = ctx.x0 * P, (ctx.x0 + ctx.nxl) * P
+        mine = (nodes >= lo) & (nodes < hi)
+        ctx.set_bc_nodes(nodes[mine] - lo, val[mine])
+        ctx.init_equilibrium(1.0, (0.02, 0.0, 0.0))
+
+    steps = 25
+    out = _two_rank_fluid((nx, ny, nz), (0, 0, 0), tau, fl, transport, setup, steps)
+    pop = O.init_equilibrium(dom, 1.0, (0.02, 0.0, 0.0)); force = np.zeros(3 * N)
+    for _ in range(steps):
+        O.collide_and_stream(dom, fl, pop, force, bc_node=bc)
+    ref = pop.reshape(19, nx, ny, nz)
+    for o in out:
+        U.assert_close(o["pop"], np.ascontiguousarray(ref[:, o["x0"]:o["x0"] + o["nxl"]]), f"populations of the slab at x0 = {o['x0']}",
+                       rtol=1e-11, floor=1e-13)
+
+
+def test_two_gpu_moment_only_matches_oracle():
+    """HCG_MOMENT_ONLY level 2: the moment-only update on two x-slabs (W / F face planes through the NCCL exchange), fluid only,
+    fully periodic, tau = 1, body force, against the oracle"""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    nx, ny, nz = 32, 12, 10
+    N = nx * ny * nz
+    fl = np.zeros(N, dtype=np.uint8)
+    dom = O.make_domain(nx, ny, nz, (1, 1, 1), 1.0)
+    body = (2e-6, -1e-6, 0.5e-6)
+    u0 = (0.01, 0.02, -0.015)
+
+    def setup(ctx):
+        ctx.set_body_force(body)
+        ctx.init_equilibrium(1.0, u0)
+
+    steps = 12
+    out = _two_rank_fluid((nx, ny, nz), (1, 1, 1), 1.0, fl, 1, setup, steps, moment_only=2)
+    pop = O.init_equilibrium(dom, 1.0, u0)
+    force = np.empty(3 * N)
+    for k in range(3):
+        force[k * N:(k + 1) * N] = body[k]
+    for _ in range(steps):
+        O.collide_and_stream(dom, fl, pop, force)
+    ref = pop.reshape(19, nx, ny, nz)
+    for o in out:
+        U.assert_close(o["pop"], np.ascontiguousarray(ref[:, o["x0"]:o["x0"] + o["nxl"]]), f"populations of the slab at x0 = {o['x0']}",
+                       rtol=1e-11, floor=1e-13)
