@@ -1,7 +1,8 @@
 """GPU tests written at the end of round 1 with no GPU time left to run them: skipped unless HCG_TEST_MOMENT_ONLY=1.
 * parity of the EXPERIMENTAL moment-only update at tau = 1 (k_moment_step, hcg_set_moment_only); its algorithm is checked on the
   CPU in tests/test_moment_only_algorithm.py;
-* a smoke run of the reference's unmodified examples/curvedflow_with_preinlet."""
+* a smoke run of the reference's unmodified examples/curvedflow_with_preinlet;
+* two-GPU runs: a Zou-He duct cut into two slabs (both transports), the moment-only update at level 2."""
 import os
 
 import numpy as np
