@@ -14,5 +14,6 @@ HCG_MOMENT_ONLY=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-contr
   python bench.py --steps 4 --warmup 3 > gpurun_out/nr_ncu_a.log 2>&1
 HCG_MOMENT_ONLY=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_moment_step -c 2 -o gpurun_out/nr_k_moment_step \
   python bench.py --steps 4 --warmup 3 > gpurun_out/nr_ncu_b.log 2>&1
-# (multi-GPU, separate call: gpurun --gpus 2 -- 'HCG_MOMENT_ONLY=2 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 10')
+# (multi-GPU, separate calls: gpurun --gpus 2 -- 'HCG_TEST_MOMENT_ONLY=1 python -m pytest tests/test_gpu_zzz_unverified.py -q -k two_gpu';
+#  and gpurun --gpus 2 -- 'HCG_MOMENT_ONLY=2 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 10')
 tail -3 gpurun_out/nr_tests.log; cat gpurun_out/nr_bench_pops.json gpurun_out/nr_bench_moment_only.json | cut -c1-400
