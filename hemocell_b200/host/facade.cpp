@@ -1513,7 +1513,9 @@ void PreInlet::applyPreInletParticleBoundary() {
   const int a = axis();
   const double inlet = a == 0 ? fluidInlet.x0 : (a == 1 ? fluidInlet.y0 : fluidInlet.z0);
   const bool neg = (int)direction % 2 == 1;                     // pre-inlet on the negative side: the slab lies on the positive side of the inlet plane
-  const double lo = neg ? inlet : inlet - inflow_length, hi = neg ? inlet + inflow_length : inlet;
+  // the slab stops one node short of the inlet plane: the Zou-He inlet nodes count as boundary nodes for the IBM here, and a
+  // vertex whose nearest node is one of them would delete its cell at the next advance (hemoCellParticleField.cpp:579-584)
+  const double lo = neg ? inlet + 1 : inlet - inflow_length, hi = neg ? inlet + inflow_length : inlet - 1;
   const double shift[3] = {(double)location.x0, (double)location.y0, (double)location.z0};
   const double period = a == 0 ? pre->nx : (a == 1 ? pre->ny : pre->nz);
   int64_t n = 0;
