@@ -209,7 +209,7 @@ hcg_status hcg_preinlet_apply_cells(hcg_ctx* c, int32_t axis, double period, con
     dst.push_back(slot); src_ok.push_back(src[q]); lap_ok.push_back(lap[q]);
     off.push_back(off.back() + th.d.V);
     for (int d = 0; d < 3; d++) sh.push_back(shift[d] + (d == axis ? lap[q]*period : 0.0));
-    c->h_cell_id[slot] = pre->h_cell_id[src[q]] + std::llabs(lap[q])*id_stride;   // (ids stay non-negative: -1 marks a free slot)
+    c->h_cell_id[slot] = pre->h_cell_id[src[q]] + (2*std::llabs(lap[q]) - (lap[q] < 0 ? 1 : 0))*id_stride;   // images 0, -1, 1, -2, 2, ... -> 0, 1, 2, 3, 4, ...: unique and non-negative (-1 marks a free slot)
     p->last_lap[src[q]] = lap[q];
   }
   const int n = (int)dst.size();

@@ -219,7 +219,7 @@ hcg_status hcg_preinlet_apply_velocity(hcg_ctx* main);
 /* PreInlet::applyPreInletParticleBoundary (helper/preInlet.cpp:255-342) in whole cells: a cell of the pre-inlet is
  * copied (positions + shift, velocity, force, repulsion force) into a free slot of main the first time its periodic
  * image k (position + k*period along `axis`) lies wholly inside [slab_lo, slab_hi] (main coordinates, = the
- * reference's inflow slab of particleEnvelope planes behind the inlet); its id becomes id + |k|*id_stride (the
+ * reference's inflow slab of particleEnvelope planes behind the inlet); its id becomes id + z(k)*id_stride, z = 0, 1, 2, 3, 4, ... for k = 0, -1, 1, -2, 2, ... (unique and non-negative; the
  * reference's cellId += offset*number_of_cells per wrap, core/hemoCellParticleDataTransfer.cpp:33-66).  The pre-inlet
  * keeps its cell.  Deviation from the reference: partially entered cells are not mirrored vertex by vertex. */
 hcg_status hcg_preinlet_apply_cells(hcg_ctx* main, int32_t axis, double period, const double shift[3],

@@ -329,7 +329,7 @@ class PreInletCoupling:
     periodic force-driven pre-inlet, and `main`, whose Zou-He velocity nodes main_idx take the velocity of the
     pre-inlet nodes pre_idx after every step.  Cells are handed over whole (see include/hemocell_gpu.h,
     hcg_preinlet_apply_cells): the periodic image k of a pre-inlet cell is copied the first time it lies wholly
-    inside [slab_lo, slab_hi] along `axis` in main coordinates (= position + shift + k*period), id + |k|*id_stride."""
+    inside [slab_lo, slab_hi] along `axis` in main coordinates (= position + shift + k*period), id + z(k)*id_stride with z = 0, 1, 2, 3, 4 for k = 0, -1, 1, -2, 2 (unique, non-negative)."""
 
     def __init__(self, pre, main, pre_idx, main_idx, axis, period, shift, slab_lo, slab_hi, id_stride):
         self.pre, self.main = pre, main
@@ -363,6 +363,6 @@ class PreInletCoupling:
             sh = self.shift.copy(); sh[ax] += k * self.period
             sl = slice(off[c], off[c + 1])
             main.insert_cells(int(pre.ctype[c]), pre.pos[sl] + sh, pre.vel[sl], pre.pforce[sl], pre.frep[sl],
-                              [cid + abs(k) * self.id_stride])
+                              [cid + (2 * abs(k) - (1 if k < 0 else 0)) * self.id_stride])
             added += 1
         return added

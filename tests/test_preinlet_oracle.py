@@ -79,9 +79,9 @@ def test_preinlet_handover_rule_and_coupling():
         n = PC.oracle_step(pre, main, cpl)
         if n:
             handed.append((it, n))
-    # cell 0's periodic image lies inside the slab from the start: handed over once, at the first step, under id 0 + 1*stride
+    # cell 0's periodic image lies inside the slab from the start: handed over once, at the first step, as image k = +1 under id 0 + 2*stride
     assert handed == [(0, 1)]
-    assert list(main.cell_id) == [0 + PC.ID_STRIDE] and list(pre.cell_id) == [0, 1]
+    assert list(main.cell_id) == [0 + 2 * PC.ID_STRIDE] and list(pre.cell_id) == [0, 1]
     # the copy starts at the pre-inlet cell's position in main coordinates (one lap ahead)
     assert main.pos.shape == (c['rbc'].V, 3)
     d = main.pos.mean(0) - (pre.pos[:c['rbc'].V].mean(0) + np.array([PC.NXP - PC.XC, 0, 0]))
@@ -94,7 +94,7 @@ def test_preinlet_handover_rule_and_coupling():
     # a second lap hands the same cell over again under a new id
     V = c['rbc'].V
     pre.pos[:V, 0] -= PC.NXP                 # as if the cell had gone round once more against the flow direction ...
-    assert cpl.apply_cells() == 1 and sorted(main.cell_id) == [2, 4]
+    assert cpl.apply_cells() == 1 and sorted(main.cell_id) == [2 * PC.ID_STRIDE, 4 * PC.ID_STRIDE]
 
 
 def test_zouhe_channel_reproduces_plane_poiseuille_flow():
