@@ -1185,6 +1185,12 @@ pluint CellInformationFunctionals::getTotalNumberOfCells(HemoCell* h) {
   ck(h->ctx(), hcg_cells_count(h->ctx(), &n, &p), "hcg_cells_count");
   double g = (double)n;                                    // every cell is counted by the one rank that owns it
   ck(h->ctx(), hcg_allreduce(h->ctx(), &g, 1, 0), "hcg_allreduce");
+  if (h->preInlet && h->preInlet->pre) {                   // the reference gathers over all ranks, the pre-inlet's included
+    hcg_ctx* q = h->preInlet->preCtx();
+    int64_t qn = 0, qp = 0;
+    ck(q, hcg_cells_count(q, &qn, &qp), "hcg_cells_count");
+    g += (double)qn;
+  }
   return (pluint)(g + 0.5);
 }
 pluint CellInformationFunctionals::getNumberOfCellsFromType(HemoCell* h, std::string type) {
@@ -1194,6 +1200,14 @@ pluint CellInformationFunctionals::getNumberOfCellsFromType(HemoCell* h, std::st
   for (int64_t k = 0; k < s.nc; k++) if (s.alive[k] && s.owned[k] && s.ids[k] >= 0 && s.types[k] == t) n++;
   double g = (double)n;
   ck(h->ctx(), hcg_allreduce(h->ctx(), &g, 1, 0), "hcg_allreduce");
+  if (h->preInlet && h->preInlet->pre) {
+    hcg_ctx* q = h->preInlet->preCtx();
+    int64_t qc = 0, qp = 0;
+    ck(q, hcg_cells_capacity(q, &qc, &qp), "hcg_cells_capacity");
+    std::vector<int64_t> ids(qc); std::vector<int32_t> types(qc); std::vector<uint8_t> alive(qc);
+    if (qc) ck(q, hcg_cells_info(q, ids.data(), types.data(), alive.data()), "hcg_cells_info");
+    for (int64_t k = 0; k < qc; k++) if (alive[k] && ids[k] >= 0 && types[k] == t) g += 1.0;
+  }
   return (pluint)(g + 0.5);
 }
 // helper/particleInfo.cpp:28-119

@@ -211,7 +211,8 @@ def test_reference_pipeflow_with_preinlet_unmodified_binary(tmp_path):
     assert pre_cells and pre_cells[0] >= 1                      # the .pos file seeds the pre-inlet as well
     handed = [int(x) for x in re.findall(r"\((\d+) so far\)", out)]
     assert handed and handed[-1] >= 1
-    assert all(c >= 8 for c in cells) and cells[-1] >= 8 + 1, cells
+    # (the case's "# of cells" gathers over both domains, as the reference's MPI gather does)
+    assert all(c >= 8 + pre_cells[0] for c in cells) and cells[-1] >= 8 + pre_cells[0] + 1, cells
     assert all(np.isfinite(v) and v > 0 for v in vmean) and vmean[-1] > vmean[0], vmean
     dx, dt = 5e-7, 1e-7
     assert all(v * dt / dx < 0.2 for v in vmax), vmax            # lattice velocity well below the speed of sound
