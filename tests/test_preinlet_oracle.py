@@ -167,3 +167,27 @@ def test_product_handover_rule_matches_the_oracle_rule():
             lo = lo + drift; hi = hi + drift
     lap, take = H.preinlet_select([1.0], [3.0], [1], None, 0.0, 10.0, 0.0, 5.0)
     assert take[0] and lap[0] == 0
+
+
+def test_preinlet_coupling_carries_the_flow_into_the_main_domain():
+    """physics check of the coupling (fluid only): the force-driven periodic pre-inlet develops a duct flow; through the Zou-He inlet
+    the main domain must carry the same volume flux at every cross-section (up to the small compressibility of the pressure drop),
+    with the pre-inlet's profile at the inlet and density 1 at the outlet"""
+    c = PC.build()
+    pre = O.OracleSim(c['domp'], c['flp'], c['par'].f_limit, (4e-5, 0.0, 0.0))
+    main = O.OracleSim(c['domm'], c['flm'], c['par'].f_limit)
+    cpl = O.PreInletCoupling(pre, main, c['pre_idx'], c['main_idx'], 0, float(PC.NXP), c['shift'], PC.SLAB[0], PC.SLAB[1], 1)
+    for _ in range(1500):
+        pre.iterate(); main.iterate()
+        cpl.apply_velocity()
+    nxm, ny, nz = PC.NXM, PC.NY, PC.NZ
+    _, vp = O.moments(pre.dom, pre.flags, pre.pop, pre.force)
+    rho, vm = O.moments(main.dom, main.flags, main.pop, main.force, main.bc_node)
+    up = vp.reshape(3, PC.NXP, ny, nz)[0]; um = vm.reshape(3, nxm, ny, nz)[0]; rho = rho.reshape(nxm, ny, nz)
+    q_pre = up[PC.XC].sum()
+    assert q_pre > 0.2                                             # a developed flow: ~200 fluid nodes x ~1.5e-3
+    q_main = np.array([um[x, 1:-1, 1:-1].sum() for x in range(1, nxm - 1)])
+    assert np.all(np.abs(q_main / q_pre - 1.0) < 0.03), q_main / q_pre
+    np.testing.assert_array_equal(um[0][c['flm'].reshape(nxm, ny, nz)[0] == 8], up[PC.XC][c['flm'].reshape(nxm, ny, nz)[0] == 8])
+    assert np.all(rho[-1][c['flm'].reshape(nxm, ny, nz)[-1] == 15] == 1.0)
+    assert rho[1, ny // 2, nz // 2] > rho[nxm - 2, ny // 2, nz // 2] > 0.999      # pressure falls towards the outlet
