@@ -105,6 +105,9 @@ struct hcg_ctx {
   double* W2 = nullptr; double* F2 = nullptr;
   bool pops_stale = false;     // the populations lag behind W (materialised on demand by lat_ensure_pops)
   int mo_mode = -1;            // -1 = follow HCG_MOMENT_ONLY, 0 = off, 1 = on (hcg_set_moment_only)
+  // HCG_MOMENT_STATE=vel: the moment-only kernels keep (rhoBar, j / rho) in V / V2 instead of (rhoBar, j) in W / W2
+  double* V = nullptr; double* V2 = nullptr;
+  bool v_valid = false;        // V describes the current state (invalidated wherever the populations are advanced or replaced)
   uint8_t* flags;
   bool u_valid, has_velbc, has_nonfluid;
   bool has_iobc = false;       // Zou-He velocity / pressure nodes present (flags >= HCG_ZH_VEL_XN)

@@ -8,6 +8,7 @@
 #include <nccl.h>
 #include <cfloat>
 #include <cstdlib>
+#include <cstring>
 #include <cstdio>
 
 namespace {
@@ -245,6 +246,31 @@ k_moment_step(const double* __restrict__ Win, const double* Fin, double* __restr
   if (i >= count) return;
   MomentArgs m; m.ny = a.ny; m.nz = a.nz; m.P = a.P; m.body[0] = a.body[0]; m.body[1] = a.body[1]; m.body[2] = a.body[2];
   moment_node<WRITE_U>(Win, Fin, Wout, Fout, U, m, i);      // csrc/moment_step.cuh (also compiled for the host by tests/cpp/moment_host.cu)
+}
+
+template <bool WRITE_U>
+__global__ void __launch_bounds__(256)
+k_moment_step_vel(const double* __restrict__ Vin, const double* Fin, double* __restrict__ Vout, double* __restrict__ Fout,
+                  double* __restrict__ U, LatArgs a, int64_t count) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  MomentArgs m; m.ny = a.ny; m.nz = a.nz; m.P = a.P; m.body[0] = a.body[0]; m.body[1] = a.body[1]; m.body[2] = a.body[2];
+  moment_node_vel<WRITE_U>(Vin, Fin, Vout, Fout, U, m, i);
+}
+// (rhoBar, j) <-> (rhoBar, j / rho) on the real nodes (entering the velocity-state mode / materialising the populations)
+__global__ void k_w_to_v(const double* __restrict__ W, double* __restrict__ V, int64_t P, int64_t count) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t n = i + P;
+  const double rb = W[4*n], inv = 1.0/(1.0 + rb);
+  V[4*n] = rb; V[4*n + 1] = W[4*n + 1]*inv; V[4*n + 2] = W[4*n + 2]*inv; V[4*n + 3] = W[4*n + 3]*inv;
+}
+__global__ void k_v_to_w(const double* __restrict__ V, double* __restrict__ W, int64_t P, int64_t count) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t n = i + P;
+  const double rb = V[4*n], rho = 1.0 + rb;
+  W[4*n] = rb; W[4*n + 1] = V[4*n + 1]*rho; W[4*n + 2] = V[4*n + 2]*rho; W[4*n + 3] = V[4*n + 3]*rho;
 }
 
 // Off-equilibrium momentum flux of the post-stream populations (output path only: the "ShearStress"
@@ -925,7 +951,7 @@ hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
     if (reset_force && c->F0 && (s = lat_reset_force(c))) return s;
   }
   c->cur = 1 - c->cur;
-  c->u_valid = false; c->w_valid = false;
+  c->u_valid = false; c->w_valid = false; c->v_valid = false;
   if (peer_on(c)) return peer_barrier(c);          // the face planes were stored into the neighbours by the kernel itself
   return lat_halo_exchange_pop(c);
 }
@@ -967,12 +993,17 @@ static int moment_only_env() {
   if (on < 0) { const char* e = getenv("HCG_MOMENT_ONLY"); on = e ? atoi(e) : 0; }
   return on;
 }
+static bool moment_state_vel() {                          // (read on every call: a few times per step; lets a test switch it)
+  const char* e = getenv("HCG_MOMENT_STATE");
+  return e && strcmp(e, "vel") == 0;
+}
 // level 1 = single rank; level 2 = also slab-decomposed runs: the W and F face planes (and U on interpolation steps) go to the
 // neighbours' ghost planes through the NCCL send/recv exchange, whatever the transport of the population path is
 bool lat_moment_eligible(hcg_ctx* c) {
   const int level = c->mo_mode < 0 ? moment_only_env() : c->mo_mode;
   return level > 0 && (c->dom.n_ranks == 1 || level >= 2) && tau1_enabled() && c->omega == 1.0 && c->dom.periodic[0] && c->dom.periodic[1] && c->dom.periodic[2]
-      && !c->has_nonfluid && !c->real_nonfluid && !c->has_velbc && !c->has_iobc && !c->F0 && c->W && c->w_valid;
+      && !c->has_nonfluid && !c->real_nonfluid && !c->has_velbc && !c->has_iobc && !c->F0
+      && ((c->W && c->w_valid) || (moment_state_vel() && c->v_valid));
 }
 hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
   hcg_status s = ensure_qsets(c); if (s) return s;
@@ -980,18 +1011,38 @@ hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
     CUDA_TRY(c, cudaMalloc(&c->W2, sizeof(double)*4*c->S)); CUDA_TRY(c, cudaMalloc(&c->F2, sizeof(double)*4*c->S));
     CUDA_TRY(c, cudaMemsetAsync(c->W2, 0, sizeof(double)*4*c->S, c->stream)); CUDA_TRY(c, cudaMemsetAsync(c->F2, 0, sizeof(double)*4*c->S, c->stream));
   }
-  // ghost planes of the moments and of the (spread) force: periodic images of the end planes
-  if ((s = exchange(c, c->W, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
+  const bool vel = moment_state_vel();
+  if (vel) {
+    if (!c->V) {
+      CUDA_TRY(c, cudaMalloc(&c->V, sizeof(double)*4*c->S)); CUDA_TRY(c, cudaMalloc(&c->V2, sizeof(double)*4*c->S));
+      CUDA_TRY(c, cudaMemsetAsync(c->V, 0, sizeof(double)*4*c->S, c->stream)); CUDA_TRY(c, cudaMemsetAsync(c->V2, 0, sizeof(double)*4*c->S, c->stream));
+    }
+    if (!c->v_valid) {                                     // entering: (rhoBar, j) of the moments pass -> (rhoBar, j / rho)
+      k_w_to_v<<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->W, c->V, c->P, c->Nl);
+      KERNEL_CHECK(c);
+      c->v_valid = true;
+    }
+  }
+  double*& Sin = vel ? c->V : c->W; double*& Sout = vel ? c->V2 : c->W2;
+  // ghost planes of the state and of the (spread) force: periodic images of the end planes / the neighbours' face planes
+  if ((s = exchange(c, Sin, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
   if ((s = exchange(c, c->F, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
   LatArgs a = make_args(c);
   {
     OpTimer tk(c, "kernel:k_moment_step");
-    if (write_u) k_moment_step<true><<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, c->Nl);
-    else k_moment_step<false><<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, c->Nl);
+    const unsigned nb = nblk(c->Nl, 256);
+    if (vel) {
+      if (write_u) k_moment_step_vel<true><<<nb, 256, 0, c->stream>>>(Sin, c->F, Sout, c->F2, c->U, a, c->Nl);
+      else k_moment_step_vel<false><<<nb, 256, 0, c->stream>>>(Sin, c->F, Sout, c->F2, c->U, a, c->Nl);
+    } else {
+      if (write_u) k_moment_step<true><<<nb, 256, 0, c->stream>>>(Sin, c->F, Sout, c->F2, c->U, a, c->Nl);
+      else k_moment_step<false><<<nb, 256, 0, c->stream>>>(Sin, c->F, Sout, c->F2, c->U, a, c->Nl);
+    }
     KERNEL_CHECK(c);
   }
-  std::swap(c->W, c->W2); std::swap(c->F, c->F2);           // W2 / F2 now hold the inputs of this step (kept for lat_ensure_pops)
-  c->pops_stale = true; c->w_valid = true; c->u_valid = write_u; c->f_clean = true;
+  std::swap(Sin, Sout); std::swap(c->F, c->F2);             // the second buffers now hold the inputs of this step (kept for lat_ensure_pops)
+  c->pops_stale = true; c->u_valid = write_u; c->f_clean = true;
+  c->w_valid = !vel;                                        // j state: W is the current state; velocity state: V is, W lags
   if (write_u) return lat_halo_exchange_u(c);
   return HCG_OK;
 }
@@ -999,7 +1050,12 @@ hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
 hcg_status lat_ensure_pops(hcg_ctx* c) {
   if (!c->pops_stale) return HCG_OK;
   LatArgs a = make_args(c);
-  k_collide_tau1<false, 0, false><<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->g[1 - c->cur], c->g[c->cur], c->F2, c->W2, c->flags, a, 0, c->Nl, nullptr, nullptr);
+  const double* Wprev = c->W2;
+  if (moment_state_vel() && c->v_valid) {                  // velocity state: the previous inputs are (rhoBar, j / rho) in V2
+    k_v_to_w<<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->V2, c->W2, c->P, c->Nl);
+    KERNEL_CHECK(c);
+  }
+  k_collide_tau1<false, 0, false><<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->g[1 - c->cur], c->g[c->cur], c->F2, Wprev, c->flags, a, 0, c->Nl, nullptr, nullptr);
   KERNEL_CHECK(c);
   c->pops_stale = false;
   return lat_halo_exchange_pop(c);
@@ -1054,7 +1110,7 @@ hcg_status lat_collide_moments_overlapped(hcg_ctx* c, bool* done_out) {
     OpTimer tk(c, "kernel:k_collide_stream");
     if ((s = lat_collide_rows(c, false, 0, nxl*ny, c->stream, c->fused_done))) return s;
   }
-  c->cur = 1 - c->cur; c->w_valid = false;
+  c->cur = 1 - c->cur; c->w_valid = false; c->v_valid = false;
   {
     // planes m_lo..m_hi; multi-GPU: the face planes need the neighbour's halo and follow after the exchange
     const int m_lo = R > 1 ? 2 : 1, m_hi = R > 1 ? nxl - 1 : nxl;
@@ -1107,7 +1163,7 @@ hcg_status lat_init_equilibrium(hcg_ctx* c, double rho, const double u[3]) {
   KERNEL_CHECK(c);
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   cudaFree(dv);
-  c->u_valid = false; c->w_valid = false; c->pops_stale = false;
+  c->u_valid = false; c->w_valid = false; c->v_valid = false; c->pops_stale = false;
   return lat_halo_exchange_pop(c);
 }
 
@@ -1120,7 +1176,7 @@ hcg_status lat_pop_to_reference(hcg_ctx* c, double* dst_dev) {
 }
 
 hcg_status lat_pop_from_reference(hcg_ctx* c, const double* src_dev) {
-  c->pops_stale = false;                                  // the uploaded populations replace whatever state there was
+  c->pops_stale = false; c->v_valid = false;              // the uploaded populations replace whatever state there was
   LatArgs a = make_args(c);
   double* s = c->g[1 - c->cur];
   CUDA_TRY(c, cudaMemsetAsync(s, 0, sizeof(double)*19*c->S, c->stream));

@@ -11,3 +11,14 @@ extern "C" void moment_host(int nx, int ny, int nz, const double* Win, const dou
     else moment_node<false>(Win, Fin, Wout, Fout, U, a, i);
   }
 }
+
+// the velocity-state variant: Vin / Vout hold (rhoBar, j / rho)
+extern "C" void moment_host_vel(int nx, int ny, int nz, const double* Vin, const double* Fin, double* Vout, double* Fout, double* U,
+                                const double* body, int write_u) {
+  MomentArgs a; a.ny = ny; a.nz = nz; a.P = (int64_t)ny*nz; a.body[0] = body[0]; a.body[1] = body[1]; a.body[2] = body[2];
+  const int64_t Nl = (int64_t)nx*ny*nz;
+  for (int64_t i = 0; i < Nl; i++) {
+    if (write_u) moment_node_vel<true>(Vin, Fin, Vout, Fout, U, a, i);
+    else moment_node_vel<false>(Vin, Fin, Vout, Fout, U, a, i);
+  }
+}

@@ -17,9 +17,11 @@ pytestmark = [pytest.mark.gpu,
                                  reason="experimental path, not yet verified on a GPU: set HCG_TEST_MOMENT_ONLY=1")]
 
 
+@pytest.mark.parametrize("state", ["j", "vel"])
 @pytest.mark.parametrize("cadence", [1, 5])
-def test_moment_only_iterate_matches_oracle(cadence):
+def test_moment_only_iterate_matches_oracle(cadence, state, monkeypatch):
     from hemocell_b200 import lib as H
+    monkeypatch.setenv("HCG_MOMENT_STATE", state)          # j: (rhoBar, j) as the state; vel: (rhoBar, j / rho)
     par = M.Parameters(dx=0.5e-6, dt=-1.0)
     nx, ny, nz = 36, 30, 28
     N = nx * ny * nz

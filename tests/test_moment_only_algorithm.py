@@ -87,3 +87,14 @@ def test_kernel_body_compiled_for_the_host_matches_the_numpy_restatement(tmp_pat
     assert np.max(np.abs(Uo[1:-1, ..., 3] - (1.0 + ref[0]))) < 1e-15
     assert np.all(Fout[1:-1, ..., :3] == body) and np.all(Fout[1:-1, ..., 3] == 0.0)
     assert np.isnan(Wout[0]).all() and np.isnan(Wout[-1]).all()            # ghost planes are the caller's business
+    # the velocity-state variant (HCG_MOMENT_STATE=vel): (rhoBar, j / rho) in, (rhoBar', j' / rho') out
+    V = W.copy(); V[1:] = W[1:] / (1.0 + W[0])
+    Vin = padded(V)
+    Vout = np.full_like(Win, np.nan); Fout2 = np.full_like(Win, np.nan); Uo2 = np.full_like(Win, np.nan)
+    lib.moment_host_vel(nx, ny, nz, Vin.ctypes.data_as(dp), Fin.ctypes.data_as(dp), Vout.ctypes.data_as(dp), Fout2.ctypes.data_as(dp),
+                        Uo2.ctypes.data_as(dp), body.ctypes.data_as(dp), 1)
+    gv = np.moveaxis(Vout[1:-1], -1, 0)
+    assert np.max(np.abs(gv[0] - ref[0])) < 1e-15 + 1e-13 * np.max(np.abs(ref[0]))
+    assert np.max(np.abs(gv[1:] * (1.0 + gv[0]) - ref[1:])) < 1e-15 + 1e-13 * np.max(np.abs(ref[1:]))
+    assert np.max(np.abs(np.moveaxis(Uo2[1:-1], -1, 0)[:3] - u)) < 1e-15 + 1e-13 * np.max(np.abs(u))
+    assert np.all(Fout2[1:-1, ..., :3] == body)

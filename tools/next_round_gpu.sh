@@ -9,6 +9,7 @@ mkdir -p gpurun_out
 HCG_TEST_MOMENT_ONLY=1 timeout 300 python -m pytest tests/test_gpu_zzz_unverified.py -q 2>&1 | tail -30 > gpurun_out/nr_tests.log
 timeout 200 python bench.py --steps 100 --warmup 10 > gpurun_out/nr_bench_pops.json 2> gpurun_out/nr_bench_pops.err
 HCG_MOMENT_ONLY=1 timeout 200 python bench.py --steps 100 --warmup 10 > gpurun_out/nr_bench_moment_only.json 2> gpurun_out/nr_bench_moment_only.err
+HCG_MOMENT_ONLY=1 HCG_MOMENT_STATE=vel timeout 200 python bench.py --steps 100 --warmup 10 > gpurun_out/nr_bench_moment_only_vel.json 2>> gpurun_out/nr_bench_moment_only.err
 HCG_MOMENT_ONLY=1 timeout 200 python bench.py --steps 100 --warmup 10 --cadence 5 > gpurun_out/nr_bench_moment_only_c5.json 2>> gpurun_out/nr_bench_moment_only.err
 HCG_MOMENT_ONLY=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/nr_launches.csv \
   python bench.py --steps 4 --warmup 3 > gpurun_out/nr_ncu_a.log 2>&1
