@@ -1,6 +1,7 @@
 // Host-side harness of the immersed-boundary kernels' per-particle arithmetic: compiles hemocell_b200/csrc/ibm_node.cuh (host + device
 // code, inlined by k_spread / k_interp_advance / k_interp_list on the device) for the CPU (tests/test_ibm_node_host.py).
 #include "../../hemocell_b200/csrc/ibm_node.cuh"
+#include "../../hemocell_b200/csrc/spread_node.cuh"
 
 static IbmArgs make(int nx, int ny, int nz, const int* periodic, int x0, int nxl, int nranks) {
   IbmArgs a;
@@ -26,4 +27,21 @@ extern "C" int ibm_kernel_host(int nx, int ny, int nz, const int* periodic, int 
                                const uint8_t* flags, const double* p3, int64_t* node, double* w) {
   const IbmArgs a = make(nx, ny, nz, periodic, x0, nxl, nranks);
   return ibm_kernel<true>(a, flags, p3[0], p3[1], p3[2], node, w);
+}
+
+// the 8 (vertex, corner) pairs of one particle as the node-sorted spreading kernels rebuild them (spread_sorted.cu: corner_node):
+// valid[c], node[c] (local padded index), weight[c] (raw, not normalised); returns 1 if some corner is not addressable from this slab
+extern "C" int spread_corners_host(int nx, int ny, int nz, const int* periodic, int x0, int nxl, int nranks,
+                                   const uint8_t* flags, const double* p3, uint8_t* valid, int64_t* node, double* weight) {
+  SpArgs a;
+  a.nx = nx; a.ny = ny; a.nz = nz; a.px = periodic[0]; a.py = periodic[1]; a.pz = periodic[2];
+  a.nxl = nxl; a.x0 = x0; a.nranks = nranks; a.P = (int64_t)ny*nz; a.f_limit = 1e300; a.V = 1; a.first_cell = 0; a.first_particle = 0;
+  int any_unaddressable = 0;
+  for (int c = 0; c < 8; c++) {
+    int nd = -1; double w = 0.0; bool un = false;
+    const bool ok = corner_node(a, flags, p3[0], p3[1], p3[2], c, nd, w, un);
+    valid[c] = ok; node[c] = nd; weight[c] = w;
+    if (un) any_unaddressable = 1;
+  }
+  return any_unaddressable;
 }

@@ -93,5 +93,15 @@ def test_interpolation_and_kernel_match_the_oracle(lib, periodic):
                 gx = (lx - 1 + x0) % nx
                 np.testing.assert_array_equal(gx * ny * nz + rem, onode[:m])
                 U.assert_close(w[:n], ow[:m], "kernel weights", rtol=1e-14)
+                # the same pairs as the node-sorted spreading kernels rebuild them, corner by corner (raw weights, normalised here)
+                valid = np.zeros(8, dtype=np.uint8); cn = np.zeros(8, dtype=np.int64); cw = np.zeros(8)
+                un = lib.spread_corners_host(nx, ny, nz, per, x0, nxl, nranks, fs.ctypes.data_as(u8), pos[p].ctypes.data_as(dp),
+                                             valid.ctypes.data_as(u8), cn.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), cw.ctypes.data_as(dp))
+                assert un == 0
+                v = valid.astype(bool)
+                assert v.sum() == m
+                np.testing.assert_array_equal(cn[v], node[:n])
+                if m:
+                    U.assert_close(cw[v] / cw[v].sum(), ow[:m], "corner weights", rtol=1e-14)
         if nranks == 1:
             assert done.all() or not all(periodic)
