@@ -13,7 +13,10 @@
  * file:line it follows.  What *is* pinned (tests/test_oracle_known_answers.py):
  * RBC mesh volume/area windows (scripts/ci/stretchCell_sanity.sh:15-34), the
  * V/T/E counts, and the stretch-cell force-displacement bounds
- * (tests/validation/stretch_cell/test_stretch_cell.cpp:158-162).
+ * (tests/validation/stretch_cell/test_stretch_cell.cpp:158-162).  The Zou-He velocity / pressure
+ * nodes (Palabos code, not in the tree) are pinned by physics instead: imposed density and
+ * momentum reproduced to 1e-14, plane Poiseuille flow within 2 %, flux continuity through the
+ * pre-inlet coupling (tests/test_preinlet_oracle.py).
  *
  * Array conventions (identical to include/hemocell_gpu.h):
  *   node index      idx = z + nz*(y + ny*x)            (patch/palabos.patch:245)
