@@ -12,7 +12,7 @@ every 20 steps, velocity interpolation every `--cadence` steps (1 = configs/, 5 
     python bench.py --workload cube                          # extra line: examples/cube (BASELINE configs[1]), one GPU
 
 The JSON line carries `roofline` for the collision kernel that ran (generic pull kernel: 304 B/LU; tau = 1 kernel after a
-moments pass: 216 B/LU), `roofline_moments` for the moments pass, `e2e` (host buffers, copies inside the timed region),
+moments pass: 216 B/LU; the opt-in moment-only update, HCG_MOMENT_ONLY=1: 160 B/LU), `roofline_moments` for the moments pass, `e2e` (host buffers, copies inside the timed region),
 `cpu_baseline` (rank 0, N = 1), `gpu_launches` and the SM clocks sampled during the timed region.
 
 One JSON line on stdout (rank 0).  A "step" is one HemoCell::iterate().
