@@ -31,18 +31,15 @@ hcg_status lat_exchange_byte_planes(hcg_ctx* c, uint8_t* buf, int ghost_default)
     }
     return HCG_OK;
   }
-  if (!c->nccl) return HCG_OK;     // done again from hcg_comm_init
-  ncclComm_t comm = (ncclComm_t)c->nccl;
+  if (!comm_up(c)) return HCG_OK;     // done again from hcg_comm_init
   const int left = (r == 0) ? (px ? R - 1 : -1) : r - 1;
   const int right = (r == R - 1) ? (px ? 0 : -1) : r + 1;
-  ncclGroupStart();
-  if (left >= 0) ncclSend(buf + P, P, ncclUint8, left, comm, c->stream);
-  if (right >= 0) ncclSend(buf + (int64_t)c->nxl*P, P, ncclUint8, right, comm, c->stream);
-  if (right >= 0) ncclRecv(buf + (int64_t)(c->nxl+1)*P, P, ncclUint8, right, comm, c->stream);
-  if (left >= 0) ncclRecv(buf, P, ncclUint8, left, comm, c->stream);
-  ncclResult_t rc = ncclGroupEnd();
-  if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("byte-plane exchange: ") + ncclGetErrorString(rc));
-  return HCG_OK;
+  hcg_status s = comm_group_begin(c); if (s) return s;
+  if (left >= 0) comm_send(c, buf + P, P, left);
+  if (right >= 0) comm_send(c, buf + (int64_t)c->nxl*P, P, right);
+  if (right >= 0) comm_recv(c, buf + (int64_t)(c->nxl+1)*P, P, right);
+  if (left >= 0) comm_recv(c, buf, P, left);
+  return comm_group_end(c, "byte-plane exchange");
 }
 
 namespace {
@@ -228,6 +225,12 @@ extern "C" {
 const char* hcg_last_error(const hcg_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 const char* hcg_version(void) { return "hemocell_b200 0.1 (sm_100a)"; }
 
+int32_t hcg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 void hcg_slab(int32_t nx, int32_t rank, int32_t n_ranks, int32_t* x0_out, int32_t* nxl_out) {
   const int32_t base = nx / n_ranks, rem = nx % n_ranks;
   if (x0_out) *x0_out = rank*base + (rank < rem ? rank : rem);
@@ -294,7 +297,7 @@ void hcg_destroy(hcg_ctx* c) {
   cudaDeviceSynchronize();
   preinlet_destroy(c);
   peer_destroy(c);
-  if (c->nccl) ncclCommDestroy((ncclComm_t)c->nccl);
+  comm_destroy(c);
   cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); if (c->F0) cudaFree(c->F0); if (c->bcn) cudaFree(c->bcn); if (c->W2) cudaFree(c->W2); if (c->F2) cudaFree(c->F2); if (c->V) cudaFree(c->V); if (c->V2) cudaFree(c->V2); if (c->d_qsets) cudaFree(c->d_qsets); cudaFree(c->flags); cudaFree(c->d_bc);
   if (c->rho) cudaFree(c->rho);
   if (c->fused_done) cudaFree(c->fused_done);
@@ -321,29 +324,13 @@ hcg_status hcg_comm_unique_id(void* out128) {
   return HCG_OK;
 }
 
-hcg_status hcg_comm_init(hcg_ctx* c, const void* id128) {
-  if (!c || !id128) return HCG_ERR_ARG;
-  CUDA_TRY(c, cudaSetDevice(c->dom.device));
-  if (c->dom.n_ranks == 1) return HCG_OK;
-  ncclUniqueId id; memcpy(&id, id128, 128);
-  ncclComm_t comm;
-  ncclResult_t rc = ncclCommInitRank(&comm, c->dom.n_ranks, id, c->dom.rank);
-  if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(rc));
-  c->nccl = comm;
+static hcg_status comm_finish_init(hcg_ctx* c) {
   if (const char* e = getenv("HCG_TRANSPORT")) c->peer.transport = (strcmp(e, "nccl") == 0) ? 0 : 1;
   hcg_status s = peer_setup(c); if (s) return s;
   if (c->peer.transport == 1) {
-    // every rank must use the same transport: fall back to NCCL send/recv everywhere if any rank cannot map its neighbours
-    int* d_ok = nullptr;
-    CUDA_TRY(c, cudaMalloc(&d_ok, sizeof(int)));
-    const int mine = c->peer.ready ? 1 : 0;
-    CUDA_TRY(c, cudaMemcpyAsync(d_ok, &mine, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    rc = ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, c->stream);
-    if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(rc));
-    int all = 0;
-    CUDA_TRY(c, cudaMemcpyAsync(&all, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    cudaFree(d_ok);
+    // every rank must use the same transport: fall back to send/recv everywhere if any rank cannot map its neighbours
+    int all = c->peer.ready ? 1 : 0;
+    if ((s = comm_allreduce_min_host(c, &all))) return s;
     if (!all) {
       if (c->dom.rank == 0) fprintf(stderr, "(hemocell_gpu) peer-memory transport unavailable on this box: using NCCL send/recv\n");
       c->peer.ready = false; c->peer.transport = 0;
@@ -355,6 +342,24 @@ hcg_status hcg_comm_init(hcg_ctx* c, const void* id128) {
   s = lat_init_equilibrium(c, 1.0, u0); if (s) return s;
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return HCG_OK;
+}
+
+hcg_status hcg_comm_init(hcg_ctx* c, const void* id128) {
+  if (!c || !id128) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (c->dom.n_ranks == 1) return HCG_OK;
+  if (comm_up(c)) return hcg_fail(c, HCG_ERR_STATE, "communicator already initialised");
+  hcg_status s = comm_nccl_init(c, id128); if (s) return s;
+  return comm_finish_init(c);
+}
+
+hcg_status hcg_comm_init_local(hcg_ctx* c, const void* id128) {
+  if (!c || !id128) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (c->dom.n_ranks == 1) return HCG_OK;
+  if (comm_up(c)) return hcg_fail(c, HCG_ERR_STATE, "communicator already initialised");
+  hcg_status s = comm_local_init(c, id128); if (s) return s;
+  return comm_finish_init(c);
 }
 
 hcg_status hcg_lattice_set_flags(hcg_ctx* c, const uint8_t* flags) {
@@ -818,7 +823,7 @@ hcg_status hcg_set_exchange(hcg_ctx* c, double margin_lu, int32_t sync_every, do
 }
 hcg_status hcg_set_transport(hcg_ctx* c, int32_t transport) {
   if (!c || transport < 0 || transport > 1) return HCG_ERR_ARG;
-  if (c->nccl) return hcg_fail(c, HCG_ERR_STATE, "hcg_set_transport must precede hcg_comm_init");
+  if (comm_up(c)) return hcg_fail(c, HCG_ERR_STATE, "hcg_set_transport must precede hcg_comm_init");
   c->peer.transport = transport;
   return HCG_OK;
 }
@@ -901,13 +906,11 @@ hcg_status hcg_cells_owned(hcg_ctx* c, uint8_t* owned) {
 hcg_status hcg_allreduce(hcg_ctx* c, double* inout, int64_t n, int32_t op) {
   if (!c || !inout || n < 0 || op < 0 || op > 2) return HCG_ERR_ARG;
   if (c->dom.n_ranks == 1 || n == 0) return HCG_OK;
-  if (!c->nccl) return hcg_fail(c, HCG_ERR_STATE, "hcg_allreduce: hcg_comm_init first");
+  if (!comm_up(c)) return hcg_fail(c, HCG_ERR_STATE, "hcg_allreduce: hcg_comm_init first");
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
   hcg_status s = ensure_staging(c, sizeof(double)*(size_t)n); if (s) return s;
   CUDA_TRY(c, cudaMemcpyAsync(c->staging, inout, sizeof(double)*n, cudaMemcpyHostToDevice, c->stream));
-  const ncclRedOp_t ops[3] = {ncclSum, ncclMin, ncclMax};
-  ncclResult_t rc = ncclAllReduce(c->staging, c->staging, (size_t)n, ncclDouble, ops[op], (ncclComm_t)c->nccl, c->stream);
-  if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(rc));
+  if ((s = comm_allreduce_f64(c, c->staging, (size_t)n, op))) return s;
   CUDA_TRY(c, cudaMemcpyAsync(inout, c->staging, sizeof(double)*n, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return HCG_OK;

@@ -137,6 +137,7 @@ struct hcg_ctx {
   cudaStream_t stream_lo = nullptr;   // low-priority stream: bulk work that overlaps the exchange chain of the main stream
   cudaEvent_t ev_a, ev_b;
   void* nccl;                  // ncclComm_t
+  void* local = nullptr;       // in-process communicator endpoint (comm.cu; hcg_comm_init_local)
   MultiState multi;
   PeerState peer;
   double* halo_send[2]; double* halo_recv[2];
@@ -229,6 +230,17 @@ hcg_status multi_upload_cell_gid(hcg_ctx* c);
 hcg_status multi_rebalance(hcg_ctx* c, bool initial);
 hcg_status multi_neighbour_exchange(hcg_ctx* c, const void* sendL, size_t nsL, const void* sendR, size_t nsR,
                                     void* recvR, size_t nrR, void* recvL, size_t nrL);
+// comm.cu: send/recv + reductions over NCCL or over the in-process communicator
+bool comm_up(const hcg_ctx* c);
+hcg_status comm_group_begin(hcg_ctx* c);
+void comm_send(hcg_ctx* c, const void* p, size_t bytes, int peer);
+void comm_recv(hcg_ctx* c, void* p, size_t bytes, int peer);
+hcg_status comm_group_end(hcg_ctx* c, const char* what);
+hcg_status comm_allreduce_f64(hcg_ctx* c, double* dev, size_t n, int op);
+hcg_status comm_allreduce_min_host(hcg_ctx* c, int* value);
+hcg_status comm_nccl_init(hcg_ctx* c, const void* id128);
+hcg_status comm_local_init(hcg_ctx* c, const void* id128);
+void comm_destroy(hcg_ctx* c);
 // peer.cu
 inline bool peer_on(const hcg_ctx* c) { return c->dom.n_ranks > 1 && c->peer.transport == 1 && c->peer.ready; }
 hcg_status peer_setup(hcg_ctx* c);                        // collective over slab neighbours (NCCL must be up)

@@ -798,20 +798,17 @@ hcg_status exchange(hcg_ctx* c, double* buf, int64_t P /* elements per plane */,
     KERNEL_CHECK(c);
     return HCG_OK;
   }
-  if (!c->nccl) return hcg_fail(c, HCG_ERR_STATE, "n_ranks > 1 but hcg_comm_init was not called");
-  ncclComm_t comm = (ncclComm_t)c->nccl;
   const int left = (r == 0) ? (px ? R - 1 : -1) : r - 1;
   const int right = (r == R - 1) ? (px ? 0 : -1) : r + 1;
   const int64_t S = c->S;
-  ncclGroupStart();
+  const size_t B = sizeof(double)*(size_t)P;
+  hcg_status s = comm_group_begin(c); if (s) return s;
   // my first real plane -> left neighbour's RIGHT ghost (sets R); my last -> right neighbour's LEFT ghost (sets L)
-  if (left >= 0) for (int k = 0; k < nR; k++) ncclSend(buf + (int64_t)hR[k]*S + P, P, ncclDouble, left, comm, c->stream);
-  if (right >= 0) for (int k = 0; k < nL; k++) ncclSend(buf + (int64_t)hL[k]*S + (int64_t)c->nxl*P, P, ncclDouble, right, comm, c->stream);
-  if (right >= 0) for (int k = 0; k < nR; k++) ncclRecv(buf + (int64_t)hR[k]*S + (int64_t)(c->nxl+1)*P, P, ncclDouble, right, comm, c->stream);
-  if (left >= 0) for (int k = 0; k < nL; k++) ncclRecv(buf + (int64_t)hL[k]*S, P, ncclDouble, left, comm, c->stream);
-  ncclResult_t rc = ncclGroupEnd();
-  if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("halo exchange: ") + ncclGetErrorString(rc));
-  return HCG_OK;
+  if (left >= 0) for (int k = 0; k < nR; k++) comm_send(c, buf + (int64_t)hR[k]*S + P, B, left);
+  if (right >= 0) for (int k = 0; k < nL; k++) comm_send(c, buf + (int64_t)hL[k]*S + (int64_t)c->nxl*P, B, right);
+  if (right >= 0) for (int k = 0; k < nR; k++) comm_recv(c, buf + (int64_t)hR[k]*S + (int64_t)(c->nxl+1)*P, B, right);
+  if (left >= 0) for (int k = 0; k < nL; k++) comm_recv(c, buf + (int64_t)hL[k]*S, B, left);
+  return comm_group_end(c, "halo exchange");
 }
 
 hcg_status ensure_qsets(hcg_ctx* c) {

@@ -107,25 +107,18 @@ __global__ void k_unpack_cells(const int32_t* __restrict__ cells, const int64_t*
   if (threadIdx.x == 0) alive[c] = 1;
 }
 
-hcg_status nccl_fail(hcg_ctx* c, const char* what, ncclResult_t rc) {
-  return hcg_fail(c, HCG_ERR_NCCL, std::string(what) + ": " + ncclGetErrorString(rc));
-}
-
 // grouped neighbour exchange of raw bytes; order keeps the 2-rank periodic case matched
 hcg_status neighbour_exchange(hcg_ctx* c, const void* sendL, size_t nsL, const void* sendR, size_t nsR,
                               void* recvR, size_t nrR, void* recvL, size_t nrL) {
-  ncclComm_t comm = (ncclComm_t)c->nccl;
   const int R = c->dom.n_ranks, r = c->dom.rank; const bool px = c->dom.periodic[0];
   const int left = (r == 0) ? (px ? R - 1 : -1) : r - 1;
   const int right = (r == R - 1) ? (px ? 0 : -1) : r + 1;
-  ncclGroupStart();
-  if (left >= 0 && nsL) ncclSend(sendL, nsL, ncclUint8, left, comm, c->stream);
-  if (right >= 0 && nsR) ncclSend(sendR, nsR, ncclUint8, right, comm, c->stream);
-  if (right >= 0 && nrR) ncclRecv(recvR, nrR, ncclUint8, right, comm, c->stream);
-  if (left >= 0 && nrL) ncclRecv(recvL, nrL, ncclUint8, left, comm, c->stream);
-  ncclResult_t rc = ncclGroupEnd();
-  if (rc != ncclSuccess) return nccl_fail(c, "neighbour exchange", rc);
-  return HCG_OK;
+  hcg_status s = comm_group_begin(c); if (s) return s;
+  if (left >= 0 && nsL) comm_send(c, sendL, nsL, left);
+  if (right >= 0 && nsR) comm_send(c, sendR, nsR, right);
+  if (right >= 0 && nrR) comm_recv(c, recvR, nrR, right);
+  if (left >= 0 && nrL) comm_recv(c, recvL, nrL, left);
+  return comm_group_end(c, "neighbour exchange");
 }
 
 hcg_status ensure_buf(hcg_ctx* c, double** p, size_t* cap, size_t doubles) {
@@ -283,6 +276,11 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
   std::vector<uint8_t> held(nc), shl(nc), shr(nc);
   hch_slab_membership_at(nc, lo.data(), hi.data(), nx, px, c->x0, c->nxl, c->dom.rank, c->dom.n_ranks, m.margin,
                       held.data(), shl.data(), shr.data());
+  // a cell held through BOTH faces (slab thinner than cell extent + 2 margin) would need a three-way velocity exchange: the
+  // per-face swap below assumes that every vertex this rank does not own belongs to the one neighbour of that face
+  for (int64_t i = 0; i < nc; i++)
+    if (m.h_held[i] && held[i] && alive[i] && shl[i] && shr[i])
+      return hcg_fail(c, HCG_ERR_ARG, "slab decomposition too fine: a cell reaches both faces of a slab (need nx / n_ranks >= cell extent + 2 * margin; use fewer ranks)");
   // 2. drops and departures
   std::vector<int32_t> send[2];
   bool alive_dirty = false;

@@ -113,7 +113,7 @@ hcg_status peer_setup(hcg_ctx* c) {
   PeerState& p = c->peer;
   p.ready = false;
   if (c->dom.n_ranks == 1 || p.transport != 1) return HCG_OK;
-  if (!c->nccl) return hcg_fail(c, HCG_ERR_STATE, "peer transport: hcg_comm_init first");
+  if (!comm_up(c)) return hcg_fail(c, HCG_ERR_STATE, "peer transport: hcg_comm_init first");
   const int R = c->dom.n_ranks, r = c->dom.rank; const bool px = c->dom.periodic[0];
   p.link[0].rank = (r == 0) ? (px ? R - 1 : -1) : r - 1;
   p.link[1].rank = (r == R - 1) ? (px ? 0 : -1) : r + 1;

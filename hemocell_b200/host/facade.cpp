@@ -122,14 +122,20 @@ class GpuLattice {
     d.nx = nx; d.ny = ny; d.nz = nz;
     for (int k = 0; k < 3; k++) d.periodic[k] = periodic[k];
     d.tau = 1.0/omega;
-    d.device = device_override >= 0 ? device_override : plb::global::mpi().getLocalRank();
+    // more ranks than GPUs on the box (or HEMOCELL_COMM=host): the ranks share the GPUs and talk through the host-staged
+    // communicator (hcg_comm_init_local) - NCCL refuses two ranks on one device
+    const int ndev = hcg_device_count();
+    const char* comm_env = getenv("HEMOCELL_COMM");
+    const bool host_comm = (comm_env && !strcmp(comm_env, "host")) || (ndev > 0 && size() > ndev);
+    d.device = device_override >= 0 ? device_override : (ndev > 0 ? plb::global::mpi().getLocalRank() % ndev : 0);
     d.rank = rank(); d.n_ranks = size();
     hcg_status s = hcg_create(&d, &ctx);
     if (s != HCG_OK) fatal(std::string("(HemoCell) (GPU) cannot create the device context: ") + hcg_last_error(ctx));
     if (d.n_ranks > 1) {
       unsigned char id[128];
       rendezvous(id);
-      ck(ctx, hcg_comm_init(ctx, id), "hcg_comm_init");
+      if (host_comm) ck(ctx, hcg_comm_init_local(ctx, id), "hcg_comm_init_local");
+      else ck(ctx, hcg_comm_init(ctx, id), "hcg_comm_init");
     }
     memcpy(created_periodic, periodic, sizeof(periodic));
     generation++;
@@ -718,6 +724,13 @@ void HemoCell::iterate() {
   iter++;
 }
 
+// ranks meet on the device communicator (the facade has no host-side MPI)
+static void rank_barrier(hcg_ctx* c) {
+  if (plb::global::mpi().getSize() <= 1) return;
+  double one = 1.0;
+  ck(c, hcg_allreduce(c, &one, 1, 0), "hcg_allreduce");
+}
+
 void HemoCell::saveCheckPoint() {
   hlog << "(HemoCell) (Saving Functions) Saving Checkpoint at timestep " << iter << endl;
 
@@ -725,7 +738,6 @@ void HemoCell::saveCheckPoint() {
   GpuLattice* g = lattice->gpu();
   const std::string dir = global.checkpointDirectory;
   mkpath(dir);
-  plb::global::mpi().barrier();
   const std::string base = dir + "rank" + std::to_string(plb::global::mpi().getRank());
   // keep the previous checkpoint as .old (core/hemoCellFields.cpp:240-262)
   if (file_exists(base + ".bin")) rename((base + ".bin").c_str(), (base + ".bin.old").c_str());
@@ -743,7 +755,9 @@ void HemoCell::saveCheckPoint() {
   ck(c, hcg_cells_info(c, ids.data(), types.data(), alive.data()), "hcg_cells_info");
   f.write((const char*)ids.data(), 8*nc); f.write((const char*)types.data(), 4*nc); f.write((const char*)alive.data(), nc);
   f.close();
+  if (!f) fatal("(HemoCell) (Saving Functions) writing " + base + ".bin failed");
   if (preInlet && preInlet->pre) preInlet->saveCheckPoint(dir);
+  rank_barrier(c);                                            // checkpoint.xml appears only once every rank's block is complete
   if (plb::global::mpi().isMainProcessor()) {
     // checkpoint.xml: <Checkpoint><General><Iteration>..</Iteration></General> + the original <hemocell> tree (config/config.cpp:53-78)
     xml::Node root; xml::Node* cp = root.addChild("Checkpoint");
@@ -786,28 +800,41 @@ void HemoCell::loadCheckPoint() {
   f.read((char*)ids.data(), 8*nc); f.read((char*)types.data(), 4*nc); f.read((char*)alive.data(), nc);
   // re-create the cells slot by slot (live ones only; slot order = type order), then overwrite the state
   std::vector<int64_t> base_of(nc); { int64_t p = 0; for (int64_t k = 0; k < nc; k++) { base_of[k] = p; p += (*cellfields)[(unsigned)types[k]]->numVertex; } }
-  std::vector<double> vel, force, frep;
+  if (!f) fatal("(HemoCell) checkpoint data " + base + " is truncated");
   for (auto* fl : cellfields->cellFields) {
     std::vector<int64_t> tid; std::vector<double> tpos;
     for (int64_t k = 0; k < nc; k++) if (types[k] == fl->impl->device_ctype && alive[k] && ids[k] >= 0) {
       tid.push_back(ids[k]);
       const int V = fl->numVertex;
       tpos.insert(tpos.end(), P[0].begin() + 3*base_of[k], P[0].begin() + 3*(base_of[k] + V));
-      vel.insert(vel.end(), P[1].begin() + 3*base_of[k], P[1].begin() + 3*(base_of[k] + V));
-      force.insert(force.end(), P[2].begin() + 3*base_of[k], P[2].begin() + 3*(base_of[k] + V));
-      frep.insert(frep.end(), P[3].begin() + 3*base_of[k], P[3].begin() + 3*(base_of[k] + V));
     }
     if (preInlet && preInlet->pre) ck(c, hcg_cells_reserve(c, fl->impl->device_ctype, 2*(int64_t)tid.size() + 256), "hcg_cells_reserve");
     ck(c, hcg_cells_add(c, fl->impl->device_ctype, (int64_t)tid.size(), tid.data(), tpos.data()), "hcg_cells_add");
     g->has_cells = g->has_cells || !tid.empty();
-    // the particle arrays of a type end with its spare slots (multi-GPU slack, pre-inlet reserve): the state arrays follow that layout
+  }
+  // velocity, membrane force and repulsion force (the reference serialises sv.v, sv.force, force_repulsion): scattered by cell
+  // id into the slot layout of the new context (spare slots of the multi-GPU slack / pre-inlet reserve, any number of ranks)
+  {
     int64_t cap_c = 0, cap_p = 0;
     ck(c, hcg_cells_capacity(c, &cap_c, &cap_p), "hcg_cells_capacity");
-    vel.resize((size_t)3*cap_p, 0.0); force.resize((size_t)3*cap_p, 0.0); frep.resize((size_t)3*cap_p, 0.0);
-  }
-  if (plb::global::mpi().getSize() == 1 && !vel.empty()) {
-    ck(c, hcg_cells_upload(c, HCG_P_VEL, vel.data()), "upload"); ck(c, hcg_cells_upload(c, HCG_P_FORCE, force.data()), "upload");
-    ck(c, hcg_cells_upload(c, HCG_P_FREP, frep.data()), "upload");
+    if (cap_c > 0) {
+      std::vector<int64_t> sid(cap_c); std::vector<int32_t> stype(cap_c); std::vector<uint8_t> salive(cap_c);
+      ck(c, hcg_cells_info(c, sid.data(), stype.data(), salive.data()), "hcg_cells_info");
+      std::map<int64_t, int64_t> saved;
+      for (int64_t k = 0; k < nc; k++) if (alive[k] && ids[k] >= 0) saved[ids[k]] = k;
+      std::vector<double> st[3];
+      for (auto& v : st) v.assign((size_t)3*cap_p, 0.0);
+      int64_t p = 0;
+      for (int64_t slot = 0; slot < cap_c; slot++) {
+        const int V = (*cellfields)[(unsigned)stype[slot]]->numVertex;
+        auto it = (sid[slot] >= 0 && salive[slot]) ? saved.find(sid[slot]) : saved.end();
+        if (it != saved.end())
+          for (int a = 0; a < 3; a++) std::copy(P[1 + a].begin() + 3*base_of[it->second], P[1 + a].begin() + 3*(base_of[it->second] + V), st[a].begin() + 3*p);
+        p += V;
+      }
+      ck(c, hcg_cells_upload(c, HCG_P_VEL, st[0].data()), "upload"); ck(c, hcg_cells_upload(c, HCG_P_FORCE, st[1].data()), "upload");
+      ck(c, hcg_cells_upload(c, HCG_P_FREP, st[2].data()), "upload");
+    }
   }
   ck(c, hcg_lattice_upload(c, HCG_LAT_POP, pop.data()), "upload"); ck(c, hcg_lattice_upload(c, HCG_LAT_FORCE, frc.data()), "upload");
   g->eq_pending = false; g->body_pending = false;

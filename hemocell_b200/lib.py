@@ -46,7 +46,7 @@ class HcgTimer(C.Structure):
 
 
 # every symbol include/hemocell_gpu.h declares (tests check that the .so exports all of them)
-SYMBOLS = """hcg_last_error hcg_version hcg_create hcg_slab hcg_destroy hcg_comm_unique_id hcg_comm_init
+SYMBOLS = """hcg_last_error hcg_version hcg_create hcg_device_count hcg_slab hcg_destroy hcg_comm_unique_id hcg_comm_init hcg_comm_init_local
 hcg_lattice_set_flags hcg_lattice_set_bc_velocity hcg_lattice_init_equilibrium hcg_lattice_set_body_force hcg_lattice_set_body_force_field
 hcg_lattice_upload hcg_lattice_download hcg_celltype_add hcg_cells_add hcg_cells_count hcg_cells_capacity
 hcg_cells_upload hcg_cells_download hcg_cells_info hcg_cells_owned hcg_allreduce hcg_cells_add_force hcg_celltype_set_stiffness
@@ -128,9 +128,10 @@ class Context:
             raise HcgError("hcg_comm_unique_id failed")
         return bytes(buf)
 
-    def comm_init(self, id128):
+    def comm_init(self, id128, local=False):
+        """local=True: in-process communicator (all ranks are contexts of this process, possibly on one GPU)"""
         buf = (C.c_uint8 * 128).from_buffer_copy(id128)
-        self._ck(self.L.hcg_comm_init(self.h, buf))
+        self._ck((self.L.hcg_comm_init_local if local else self.L.hcg_comm_init)(self.h, buf))
 
     # ---- lattice
     def set_flags(self, flags):

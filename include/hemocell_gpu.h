@@ -98,6 +98,8 @@ const char* hcg_version(void);
 
 /* ---- lifetime: HemoCell ctor/dtor + initializeLattice (core/hemoCell.cpp:69-127, 438-583) */
 hcg_status hcg_create(const hcg_domain* d, hcg_ctx** out);
+/* number of CUDA devices visible to the process (0 when there is none) */
+int32_t    hcg_device_count(void);
 /* the x-slab of a rank: first plane and number of planes (pure function of nx, rank, n_ranks) */
 void       hcg_slab(int32_t nx, int32_t rank, int32_t n_ranks, int32_t* x0_out, int32_t* nxl_out);
 void       hcg_destroy(hcg_ctx*);
@@ -107,6 +109,12 @@ void       hcg_destroy(hcg_ctx*);
  * broadcast); one context per process/GPU. */
 hcg_status hcg_comm_unique_id(void* out128);
 hcg_status hcg_comm_init(hcg_ctx*, const void* id128);
+/* Same role for a run whose n_ranks contexts all live in ONE process (one host thread per context; collective: returns
+ * when every rank has joined the group named by id128, any 128 bytes unique to the run).  The contexts may share a GPU -
+ * NCCL refuses two ranks on one device - so the slab decomposition (the reference's `mpirun -n 2` vs `-n 4` identity
+ * check, scripts/ci/pipeflow_sanity.sh:25-32) can be verified on a single-GPU box.  Messages are matched like NCCL's
+ * grouped send/recv and moved with cudaMemcpyPeerAsync (host-synchronous); the peer-store transport works unchanged. */
+hcg_status hcg_comm_init_local(hcg_ctx*, const void* id128);
 
 /* ---- lattice set-up */
 /* defineDynamics(lattice, domain, new BounceBack) / setVelocityConditionOnBlockBoundaries

@@ -2,6 +2,10 @@ import os
 import sys
 import pytest
 
+# several slab contexts may share one GPU in the tests (host-staged communicator): their flag-barrier kernels spin on each
+# other, so their streams must not be folded onto the same hardware queue (default: 8 connections per device)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

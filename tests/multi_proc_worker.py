@@ -30,9 +30,11 @@ else:
         time.sleep(0.05)
     uid = open(uid_path, "rb").read()
 nxl = nx // R
-ctx = H.Context(nx, ny, nz, periodic, par.tau, device=rank, rank=rank, n_ranks=R)
+ndev = H.load().hcg_device_count()
+local = ndev < R or os.environ.get("HCG_TEST_LOCAL") == "1"      # fewer GPUs than ranks: share them (host-staged communicator)
+ctx = H.Context(nx, ny, nz, periodic, par.tau, device=rank % max(ndev, 1), rank=rank, n_ranks=R)
 ctx.set_transport(transport)
-ctx.comm_init(uid)
+ctx.comm_init(uid, local=local)
 fl3 = cfg["flags"].reshape(nx, ny, nz)
 ctx.set_flags(np.ascontiguousarray(fl3[rank * nxl:(rank + 1) * nxl]))
 for o in range(6):
