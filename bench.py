@@ -2,18 +2,23 @@
 """bench.py -- throughput of the HemoCell per-timestep IB-LBM hot path on B200.
 
 Metric (BASELINE.json): MLUPS (D3Q19 fp64, with RBCs) and cell-steps/s.
-Workload at N GPUs: the cases/performance_testing weak-scaling unit, 256^3 lattice nodes per
-GPU (domain 256*N x 256 x 256, slabs along x), fully periodic, tau = 1, body force (f,f,f),
-RBCs seeded to ~33 % hematocrit per unit (synthetic, seeded lattice packing), material update
-every 20 steps, velocity interpolation every `--cadence` steps (1 = configs/, 5 = configs_timestep_5/).
+Workload at N GPUs: the cases/performance_testing unit, 256^3 lattice nodes per GPU (domain 256*N x 256 x 256, slabs
+along x), fully periodic, tau = 1, body force (f,f,f), the reference's own cases/performance_testing/hematocrit_33/RBC.pos
+(10 935 rows packed into a 135 um cube; placed on the 128 um unit with the reference's reader rule - a cell survives iff
+every vertex lies inside the domain, pinned by the 42-cell known answer of tests/validation/pipeflow - 7736 randomly
+oriented RBC = 4.97 M LSP survive; fixtures/, sha256 in the line), tiled along x for N > 1 as
+examples/cube/preprocess/analysis.py:cell_positions does; material update every 20 steps, velocity interpolation every
+`--cadence` steps (1 = configs/, 5 = configs_timestep_5/).  `--workload synthetic` = round 1's crystal packing (8464 aligned discs).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
     python bench.py --impl reference --gpus N --steps K ...  # CPU oracle on the host cores
     python bench.py --workload cube                          # extra line: examples/cube (BASELINE configs[1]), one GPU
 
-The JSON line carries `roofline` for the collision kernel that ran (generic pull kernel: 304 B/LU; tau = 1 kernel after a
-moments pass: 216 B/LU; the opt-in moment-only update, HCG_MOMENT_ONLY=1: 160 B/LU), `roofline_moments` for the moments pass, `e2e` (host buffers, copies inside the timed region),
-`cpu_baseline` (rank 0, N = 1), `gpu_launches` and the SM clocks sampled during the timed region.
+The JSON line carries `roofline` for the WHOLE lattice update (every lattice kernel of a step - collision + moments pass, or
+the moment-only kernel - against SURVEY 8(d)'s 304 B/LU), `roofline_kernels` (each kernel against its own algorithmic bytes),
+`roofline_step` (whole step against 304 + (264 + 72 + 216/c) N_LSP/N_nodes B/LU), `parity_check` (a small slab-decomposed
+problem of the same code path checked against the CPU oracle before the timed region, on all N ranks), `e2e` (host buffers,
+copies inside the timed region), `cpu_baseline` (rank 0, N = 1), `gpu_launches` and the SM clocks sampled during the timed region.
 
 One JSON line on stdout (rank 0).  A "step" is one HemoCell::iterate().
 """
@@ -164,6 +169,102 @@ def ncu_traffic(kernel="k_collide_stream"):
 
 
 # ----------------------------------------------------------------------------- our arm
+FIXTURE_POS = os.path.join(ROOT, "fixtures", "performance_testing_hematocrit_33_RBC.pos")
+
+# algorithmic bytes per lattice update of each lattice kernel (DESIGN.md section 4)
+KERNEL_B_LU = {"k_collide_stream": 304.0, "k_collide_tau1": B_LU_TAU1, "k_moments": B_MOM, "k_moment_step": 160.0, "k_moment_tile": 160.0}
+
+
+def unit_rows(workload):
+    """.pos rows of one 256^3 unit and the sha256 of their source"""
+    import hashlib
+    if workload == "synthetic":
+        rows = synthetic_rows()
+        return rows, "sha256:" + hashlib.sha256(np.ascontiguousarray(rows).tobytes()).hexdigest(), "synthetic crystal packing (seed 1234)"
+    from hemocell_b200 import lib as H
+    rows = H.read_pos(FIXTURE_POS)
+    return rows, "sha256:" + hashlib.sha256(open(FIXTURE_POS, "rb").read()).hexdigest(), \
+        "cases/performance_testing/hematocrit_33/RBC.pos (reference data file, fixtures/)"
+
+
+def parity_check(args, dist, H, par):
+    """Before the timed region: a small slab-decomposed problem on the SAME code path as the benchmark (fully periodic,
+    tau = 1, body force, RBCs sitting on every slab face incl. the periodic one, velocity cadence as benchmarked), 20
+    iterate() steps on all ranks against the CPU oracle on rank 0 (checker leg; outside the timed region)."""
+    rank, world = args.rank, args.world
+    nxl, ny, nz, steps = 32, 28, 28, 20
+    nx = nxl * world
+    ct = H.HostCellType(H.MODEL_RBC, H.RBC_FROM_SPHERE, par, H.RBC_MATERIAL)
+    um = DX / 1e-6
+    # one RBC centred on every slab face (the first one on the periodic face x = 0), one in the bulk of slab 0
+    rows = [(((k * nxl) % nx + (0.4 if k else 0.0)) * um, (13.0 + 0.7 * (k % 3)) * um, (14.0 - 0.5 * (k % 2)) * um, 90.0, 20.0 * k, 0.0) for k in range(world)]
+    rows.append((16.3 * um, 14.2 * um, 13.6 * um, 70.0, 20.0, 10.0))
+    rows = np.array(rows)
+    # the reader's placement rule prunes cells that stick out of the domain: place on a domain shifted by half a slab
+    # and shift back, so that the face cells (incl. the one on the periodic face) survive with unwrapped coordinates
+    shifted = rows.copy(); shifted[:, 0] += 0.5 * nxl * um
+    cells, ids = ct.place(shifted, DX, (nx + nxl, ny, nz))
+    cells = cells - np.array([0.5 * nxl, 0.0, 0.0])
+    assert len(ids) == len(rows)
+    body = body_force(par["nu_lbm"], UNIT_N)
+    body = tuple(50.0 * b for b in body)
+    ctx = H.Context(nx, ny, nz, (1, 1, 1), par["tau"], device=args.local_rank, rank=rank, n_ranks=world)
+    if world > 1:
+        import torch
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idbuf.copy_(torch.frombuffer(bytearray(H.Context.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        ctx.comm_init(bytes(idbuf.cpu().numpy().tobytes()))
+    ctx.set_flags(np.zeros(ctx.Nl, dtype=np.uint8))
+    ctx.set_body_force(body); ctx.set_force_limit(par["f_limit"])
+    t = ct.add_to(ctx)
+    if world > 1:
+        ctx.set_exchange(4.0, 5, 1.0)
+    ctx.add_cells(t, cells, ids)
+    ctx.set_timescales(args.cadence, 1, 1); ctx.set_material_timescale(t, 5 * args.cadence)
+    ctx.iterate(steps)
+    pop = ctx.lattice_download(H.LAT_POP).reshape(19, ctx.nxl, ny, nz)
+    pos = ctx.cells_download(H.P_POS).reshape(-1, ct.V, 3)
+    cid, _, alive = ctx.cells_info()
+    mine = {int(c): pos[k] for k, (c, a) in enumerate(zip(cid, alive)) if c >= 0 and a}
+    mode = ctx.lattice_mode() if hasattr(ctx, "lattice_mode") else None
+    ctx.close()
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((ctx.x0, pop, mine), gathered, dst=0)
+    else:
+        gathered = [(0, pop, mine)]
+    if rank != 0:
+        return None
+    import oracle as O
+    from oracle import mesh as M
+    opar = M.Parameters(DX, -1.0)
+    oct_ = O.rbc_celltype(opar)
+    dom = O.make_domain(nx, ny, nz, (1, 1, 1), opar.tau)
+    sim = O.OracleSim(dom, np.zeros(nx * ny * nz, dtype=np.uint8), opar.f_limit, body)
+    sim.vel_timescale = args.cadence
+    sim.add_celltype(oct_, 5 * args.cadence)
+    sim.add_cells(0, cells, ids)
+    for _ in range(steps):
+        sim.iterate()
+    ref_pop = sim.pop.reshape(19, nx, ny, nz)
+    ref_pos = sim.pos.reshape(-1, ct.V, 3)
+    scale = float(np.abs(ref_pop).max())
+    e_pop, e_pos, seen = 0.0, 0.0, set()
+    for x0, gp, gm in gathered:
+        e_pop = max(e_pop, float(np.abs(gp - ref_pop[:, x0:x0 + gp.shape[1]]).max()) / scale)
+        for c, pp in gm.items():
+            k = int(np.where(sim.cell_id == c)[0][0])
+            e_pos = max(e_pos, float(np.abs(pp - ref_pos[k]).max()) / float(np.abs(ref_pos[k]).max()))
+            seen.add(c)
+    ok = e_pop <= 1e-10 and e_pos <= 1e-10 and seen == set(int(i) for i in ids)
+    return {"max_rel": max(e_pop, e_pos), "max_rel_populations": e_pop, "max_rel_positions": e_pos, "tolerance": 1e-10, "ok": bool(ok),
+            "against": "CPU oracle (oracle/hemo_oracle.c), rank 0", "steps": steps, "lattice": [nx, ny, nz], "slabs": world,
+            "cells": int(len(ids)), "cells_on_slab_faces": world, "every_cell_found": seen == set(int(i) for i in ids),
+            "lattice_update": mode}
+
+
 def run_cuda(args):
     rank, world = args.rank, args.world
     from hemocell_b200 import lib as H
@@ -174,10 +275,11 @@ def run_cuda(args):
         torch.cuda.set_device(args.local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", args.local_rank))
     par = H.parameters(DX, -1.0)
+    pcheck = None if args.no_parity_check else parity_check(args, dist, H, par)
     ct = H.HostCellType(H.MODEL_RBC, H.RBC_FROM_SPHERE, par, H.RBC_MATERIAL)
-    rows = synthetic_rows()
+    rows, pos_hash, pos_src = unit_rows(args.workload)
     nx = UNIT_N * world
-    # every unit gets the same packing, shifted along x (examples/cube/preprocess/analysis.py:cell_positions)
+    # every unit gets the same cells, shifted along x (examples/cube/preprocess/analysis.py:cell_positions)
     unit_cells, unit_ids = ct.place(rows, DX, (UNIT_N, UNIT_N, UNIT_N))
     n_unit = len(unit_ids)
     ctx = H.Context(nx, UNIT_N, UNIT_N, (1, 1, 1), par["tau"], device=args.local_rank, rank=rank, n_ranks=world)
@@ -193,11 +295,16 @@ def run_cuda(args):
     ctx.set_force_limit(par["f_limit"])
     t = ct.add_to(ctx)
     if world > 1:
-        # own unit plus the neighbouring units; the library keeps the cells within its hold region
-        ctx.set_exchange(4.0, 20, 0.3)
-        units = sorted({(rank - 1) % world, rank, (rank + 1) % world})
-        cells = np.concatenate([unit_cells + np.array([u * UNIT_N, 0.0, 0.0]) for u in units])
-        ids = np.concatenate([unit_ids + u * len(rows) for u in units])
+        # own unit plus the cells of the neighbouring units that reach into this slab's hold region (the library keeps
+        # what it holds); spare slots for later arrivals: 15 % of the held cells
+        ctx.set_exchange(4.0, 20, 0.15)
+        parts_c, parts_i = [unit_cells + np.array([rank * UNIT_N, 0.0, 0.0])], [unit_ids + rank * len(rows)]
+        lo, hi = unit_cells[:, :, 0].min(1), unit_cells[:, :, 0].max(1)
+        for u, sel in (((rank - 1) % world, hi > UNIT_N - 12.0), ((rank + 1) % world, lo < 12.0)):
+            if u == rank:
+                continue
+            parts_c.append(unit_cells[sel] + np.array([u * UNIT_N, 0.0, 0.0])); parts_i.append(unit_ids[sel] + u * len(rows))
+        cells, ids = np.concatenate(parts_c), np.concatenate(parts_i)
     else:
         cells, ids = unit_cells, unit_ids
     pos_host = pinned_empty(cells.size)
@@ -238,70 +345,89 @@ def run_cuda(args):
     ctx.timers_enable(False)
     alive_cells = ctx.count()[0]
 
-    # ---- end-to-end leg through the C ABI with HOST buffers (pinned): state upload, K x
-    # (body force H2D + iterate(1) + cell-count D2H), final read-back of positions and forces
+    # ---- end-to-end leg through the C ABI with HOST buffers (pinned), the loop of the case file
+    # (performance_testing.cpp:126-133): cell state H2D, then K x { iterate(); setExternalVector(force) (24 B host argument);
+    # cell count of the step D2H into pinned memory, not waited for }, one wait, positions and forces D2H (writeOutput)
     npart = ctx.capacity()[1]
     out_pos = pinned_empty(3 * npart); out_frc = pinned_empty(3 * npart)
     state_host = pinned_empty(3 * npart)          # the particle state as the host holds it (pinned)
+    counts = pinned_empty(2 * args.steps)         # 2 int64 per step
     ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), state_host.ctypes.data_as(H.c_dp))
     ctx.set_iteration(0)
+    bf = body_force(par["nu_lbm"], UNIT_N)
     barrier()
     te0 = time.time()
     ctx.cells_upload(H.P_POS, state_host)
-    bf = body_force(par["nu_lbm"], UNIT_N)
-    for _ in range(args.steps):
-        ctx.set_body_force(bf)                    # setExternalVector after every iterate (performance_testing.cpp:132-135)
-        ctx.iterate(1)
-        ctx.count()
+    for k in range(args.steps):
+        ctx.iterate_async(1)
+        ctx.set_body_force(bf)                    # setExternalVector after every iterate
+        ctx.count_async(counts.ctypes.data + 16 * k)
+    ctx.synchronize()
     ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), out_pos.ctypes.data_as(H.c_dp))
     ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_FORCE), out_frc.ctypes.data_as(H.c_dp))
     barrier()
     e2e_ms = max_over_ranks((time.time() - te0) * 1e3)
     h2d = (8 * 3 * npart) / args.steps + 24
     d2h = (2 * 8 * 3 * npart) / args.steps + 16
+    last_count = int(counts.view(np.int64)[2 * (args.steps - 1)])
+    if dist is not None:
+        import torch
+        tt = torch.tensor([last_count], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tt)
+        last_count = int(tt.item())
 
     if rank != 0:
         ctx.close()
         return None
-    # dominant kernel = the collide-and-stream kernel that ran most: the generic pull kernel (19 r + 19 w = 304 B/LU,
-    # the contract figure) or, at tau = 1 after a moments pass, k_collide_tau1 (32 B raw moments + 32 B force read,
-    # 19 populations written = 216 B/LU)
-    gen = timers.get("kernel:k_collide_stream", (0.0, 0)); t1 = timers.get("kernel:k_collide_tau1", (0.0, 0))
-    mo = timers.get("kernel:k_moment_step", (0.0, 0))
-    if mo[0] > max(gen[0], t1[0]):
-        # opt-in moment-only update (HCG_MOMENT_ONLY=1): 64 B read + 96 B written per lattice update
-        k1_name, (k1_ms, k1_calls), b_lu = "k_moment_step", mo, 160.0
-    elif t1[0] > gen[0]:
-        k1_name, (k1_ms, k1_calls), b_lu = "k_collide_tau1", t1, B_LU_TAU1
-    else:
-        k1_name, (k1_ms, k1_calls), b_lu = "k_collide_stream", gen, B_LU
     peak, peak_src = measured_peak()
     nodes_local = UNIT_N ** 3
-    k1_avg_ms = k1_ms / max(k1_calls, 1)
-    achieved = b_lu * nodes_local / (k1_avg_ms * 1e-3) / 1e9 if k1_calls else None
-    mom_ms, mom_calls = timers.get("kernel:k_moments", (0.0, 0))
-    b_mom = B_MOM_TAU1 if k1_name == "k_collide_tau1" else B_MOM
-    mom_ach = b_mom * nodes_local / (mom_ms / max(mom_calls, 1) * 1e-3) / 1e9 if mom_calls else None
+    # ---- rooflines.  (1) the whole lattice update = every lattice kernel of a step, against SURVEY 8(d)'s 304 B/LU
+    lat = {k[len("kernel:"):]: v for k, v in timers.items() if k.startswith("kernel:") and k[len("kernel:"):] in KERNEL_B_LU}
+    lat_ms_per_step = sum(v[0] for v in lat.values()) / args.steps
+    lat_ach = B_LU * nodes_local / (lat_ms_per_step * 1e-3) / 1e9 if lat_ms_per_step > 0 else None
+    kernels = {}
+    for name, (kms, calls) in lat.items():
+        if not calls:
+            continue
+        b = KERNEL_B_LU[name]
+        if name == "k_moments" and "k_collide_tau1" in lat:
+            b = B_MOM_TAU1
+        ach = b * nodes_local / (kms / calls * 1e-3) / 1e9
+        kernels[name] = {"bytes_per_lu": b, "launch_ms": kms / calls, "launches_timed": calls, "achieved": ach, "frac": ach / peak,
+                         "traffic": ncu_traffic(name)}
+    traffic = [kernels[k]["traffic"] for k in kernels]
+    traffic_update = None
+    if kernels and all(v is not None for v in traffic):
+        traffic_update = sum(kernels[k]["traffic"] * kernels[k]["launches_timed"] for k in kernels) / args.steps
+    lsp = n_unit * ct.V
+    b_step = B_LU + (264.0 + 72.0 + 216.0 / args.cadence) * lsp / nodes_local
+    step_ach = b_step * nodes_local / (ms / args.steps * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": nodes * args.steps / (ms * 1e-3) / 1e6, "unit": "MLUPS",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "cell_steps_per_s": (alive_cells if world == 1 else n_cells_global) * args.steps / (ms * 1e-3),
         "config": {"workload": f"cases/performance_testing unit: {nx}x{UNIT_N}x{UNIT_N} D3Q19 fp64, fully periodic, tau=1, "
-                               f"body force, {n_cells_global} RBC (642 LSP each, ~33% hematocrit), material every 20, "
+                               f"body force, {n_cells_global} RBC (642 LSP each; {pos_src}), material every 20, "
                                f"velocity every {args.cadence}",
                    "lattice": [nx, UNIT_N, UNIT_N], "cells": n_cells_global, "lsp": n_cells_global * ct.V,
+                   "cells_alive_after_run": int(last_count), "pos_rows": int(len(rows)), "pos_source": pos_src, "pos_sha256": pos_hash,
+                   "hematocrit": n_unit * 81.116 / (UNIT_N * DX * 1e6) ** 3,
                    "velocity_cadence": args.cadence, "material_cadence": 20, "decomposition": f"{world} x-slabs",
-                   "l2": "inputs (5.1 GB of populations per GPU) are far larger than the 126 MB L2; no flush needed"},
-        "roofline": {"bound": "hbm", "kernel": k1_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(k1_name),
-                     "peak_source": peak_src, "bytes_per_lu": b_lu, "launch_ms": k1_avg_ms, "launches_timed": k1_calls},
-        "roofline_moments": {"bound": "hbm", "kernel": "k_moments", "achieved": mom_ach, "peak": peak, "unit": "GB/s",
-                             "frac": mom_ach / peak if mom_ach else None, "bytes_per_lu": b_mom,
-                             "launch_ms": mom_ms / max(mom_calls, 1), "launches_timed": mom_calls},
+                   "l2": "inputs (0.5 - 5 GB of lattice state per GPU) are far larger than the 126 MB L2; no flush needed"},
+        "roofline": {"bound": "hbm", "kernel": " + ".join(sorted(kernels)) + " (whole lattice update)", "achieved": lat_ach, "peak": peak,
+                     "unit": "GB/s", "frac": lat_ach / peak if lat_ach else None, "traffic": traffic_update,
+                     "peak_source": peak_src, "bytes_per_lu": B_LU, "launch_ms": lat_ms_per_step,
+                     "note": "achieved = 304 B/LU (SURVEY 8d contract: 19 populations read + written) x 256^3 / time of ALL lattice kernels of a step; "
+                             "a fraction above 1 means the update moved fewer bytes than the contract (tau = 1: the populations are never stored)"},
+        "roofline_kernels": kernels,
+        "roofline_step": {"bound": "hbm", "bytes_per_lu": b_step, "achieved": step_ach, "peak": peak, "unit": "GB/s", "frac": step_ach / peak,
+                          "formula": "304 + (264 + 72 + 216/c) N_LSP/N_nodes B/LU (SURVEY 8d)"},
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()},
         "e2e": {"value": nodes * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "MLUPS",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                "loop": "cells H2D; K x {iterate, body force, async cell-count D2H}; wait; positions + forces D2H"},
+        "parity_check": pcheck,
         "gpu_launches": launches, "clocks": clocks,
     }
     ctx.close()
@@ -371,7 +497,7 @@ def run_cube(args):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def run_cpu(steps, warmup, cadence, budget_s=150.0):
+def run_cpu(steps, warmup, cadence, budget_s=150.0, workload="performance_testing"):
     """The reference cannot be built (Palabos/MPI/HDF5 absent): time the CPU oracle (a port) with
     OpenMP on the host cores, on a bounded sub-box of the same workload (same packing density)."""
     import oracle as O
@@ -385,7 +511,10 @@ def run_cpu(steps, warmup, cadence, budget_s=150.0):
     ct = O.rbc_celltype(par)
 
     def make(n):
-        rows = synthetic_rows(n)
+        # the same .pos rows on an n^3 sub-box of the unit: the reader's rule keeps the cells that lie wholly inside it
+        rows = synthetic_rows(n) if workload == "synthetic" else M.read_pos(FIXTURE_POS)
+        if workload != "synthetic":
+            rows = rows[np.all(rows[:, :3] < n * DX / 1e-6 + 4.0, axis=1)]
         cells, ids = M.place_cells(ct.verts, rows, DX, (n, n, n))
         dom = O.make_domain(n, n, n, (1, 1, 1), par.tau)
         sim = O.OracleSim(dom, np.zeros(n ** 3, dtype=np.uint8), par.f_limit, body_force(par.nu_lbm, UNIT_N))
@@ -424,8 +553,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--cadence", type=int, default=1, help="velocity interpolation every n steps (stepParticleEvery)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="performance_testing", choices=["performance_testing", "cube"],
-                    help="performance_testing = the weak-scaling unit the metric is quoted on (default); cube = examples/cube, 1 GPU")
+    ap.add_argument("--workload", default="performance_testing", choices=["performance_testing", "synthetic", "cube"],
+                    help="performance_testing = the reference's unit with its own RBC.pos (default); synthetic = round 1's crystal packing; cube = examples/cube, 1 GPU")
+    ap.add_argument("--no-parity-check", action="store_true")
     args = ap.parse_args()
     args.rank = int(os.environ.get("RANK", "0"))
     args.world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -435,7 +565,7 @@ def main():
     if args.impl == "reference":
         if args.rank != 0:
             return
-        cb = run_cpu(args.steps, args.warmup, args.cadence)
+        cb = run_cpu(args.steps, args.warmup, args.cadence, workload=args.workload)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "MLUPS", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -453,7 +583,7 @@ def main():
     if args.rank != 0:
         return
     if args.world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = run_cpu(6, 1, args.cadence, budget_s=30.0)
+        line["cpu_baseline"] = run_cpu(6, 1, args.cadence, budget_s=30.0, workload=args.workload)
     print(json.dumps(line), flush=True)
 
 

@@ -300,6 +300,7 @@ void hcg_destroy(hcg_ctx* c) {
   comm_destroy(c);
   cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); if (c->F0) cudaFree(c->F0); if (c->bcn) cudaFree(c->bcn); if (c->W2) cudaFree(c->W2); if (c->F2) cudaFree(c->F2); if (c->V) cudaFree(c->V); if (c->V2) cudaFree(c->V2); if (c->d_qsets) cudaFree(c->d_qsets); cudaFree(c->flags); cudaFree(c->d_bc);
   if (c->rho) cudaFree(c->rho);
+  if (c->count_dev) cudaFree(c->count_dev); if (c->count_typeV) cudaFree(c->count_typeV);
   if (c->fused_done) cudaFree(c->fused_done);
   for (int k = 0; k < 3; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->frc[k]); cudaFree(c->frep[k]); }
   for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) if (c->comp[k][d]) cudaFree(c->comp[k][d]);
@@ -694,25 +695,42 @@ hcg_status hcg_cells_capacity(hcg_ctx* c, int64_t* n_cells, int64_t* n_particles
   return HCG_OK;
 }
 
+// launches the count of alive cells (multi-GPU: cells this rank owns) and alive particles into c->count_dev (2 words)
+static hcg_status count_launch(hcg_ctx* c) {
+  if (!c->count_dev) CUDA_TRY(c, cudaMalloc(&c->count_dev, sizeof(unsigned long long)*2));
+  if ((int)c->types.size() != c->count_ntypes) {
+    std::vector<int> hv; for (auto& t : c->types) hv.push_back(t.d.V);
+    if (c->count_typeV) { CUDA_TRY(c, cudaStreamSynchronize(c->stream)); cudaFree(c->count_typeV); c->count_typeV = nullptr; }
+    CUDA_TRY(c, cudaMalloc(&c->count_typeV, sizeof(int)*std::max<size_t>(hv.size(), 1)));
+    if (!hv.empty()) CUDA_TRY(c, cudaMemcpy(c->count_typeV, hv.data(), sizeof(int)*hv.size(), cudaMemcpyHostToDevice));
+    c->count_ntypes = (int)c->types.size();
+  }
+  CUDA_TRY(c, cudaMemsetAsync(c->count_dev, 0, sizeof(unsigned long long)*2, c->stream));
+  if (c->ncells > 0) {
+    k_count_alive<<<nblk(c->ncells, 256), 256, 0, c->stream>>>(c->cell_alive, c->cell_type, c->count_typeV, c->ncells, c->count_dev,
+        c->cell_base, c->pos[0], c->dom.n_ranks, c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
+    KERNEL_CHECK(c);
+  }
+  return HCG_OK;
+}
+
 hcg_status hcg_cells_count(hcg_ctx* c, int64_t* n_cells_alive, int64_t* n_particles_alive) {
   if (!c) return HCG_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
   unsigned long long h[2] = {0, 0};
-  if (c->ncells > 0) {
-    std::vector<int> hv; for (auto& t : c->types) hv.push_back(t.d.V);
-    int* dv; unsigned long long* dout;
-    CUDA_TRY(c, cudaMalloc(&dv, sizeof(int)*hv.size())); CUDA_TRY(c, cudaMalloc(&dout, sizeof(h)));
-    CUDA_TRY(c, cudaMemcpyAsync(dv, hv.data(), sizeof(int)*hv.size(), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemsetAsync(dout, 0, sizeof(h), c->stream));
-    k_count_alive<<<nblk(c->ncells, 256), 256, 0, c->stream>>>(c->cell_alive, c->cell_type, dv, c->ncells, dout,
-        c->cell_base, c->pos[0], c->dom.n_ranks, c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
-    KERNEL_CHECK(c);
-    CUDA_TRY(c, cudaMemcpyAsync(h, dout, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    cudaFree(dv); cudaFree(dout);
-  }
+  hcg_status s = count_launch(c); if (s) return s;
+  CUDA_TRY(c, cudaMemcpyAsync(h, c->count_dev, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   if (n_cells_alive) *n_cells_alive = (int64_t)h[0];
   if (n_particles_alive) *n_particles_alive = (int64_t)h[1];
+  return HCG_OK;
+}
+
+hcg_status hcg_cells_count_async(hcg_ctx* c, int64_t* out2) {
+  if (!c || !out2) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  hcg_status s = count_launch(c); if (s) return s;
+  CUDA_TRY(c, cudaMemcpyAsync(out2, c->count_dev, sizeof(int64_t)*2, cudaMemcpyDeviceToHost, c->stream));
   return HCG_OK;
 }
 
@@ -846,6 +864,15 @@ hcg_status hcg_iterate(hcg_ctx* c, int64_t n) {
   if (c->rep_on && c->ts_rep % c->ts_vel) return hcg_fail(c, HCG_ERR_STATE, "repulsion timescale must be a multiple of the velocity timescale");
   for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) return s; }
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_iterate_async(hcg_ctx* c, int64_t n) {
+  if (!c || n < 0) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  for (auto& t : c->types) if (t.timescale % c->ts_vel) return hcg_fail(c, HCG_ERR_STATE, "material timescale must be a multiple of the velocity timescale");
+  if (c->rep_on && c->ts_rep % c->ts_vel) return hcg_fail(c, HCG_ERR_STATE, "repulsion timescale must be a multiple of the velocity timescale");
+  for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) return s; }
   return HCG_OK;
 }
 

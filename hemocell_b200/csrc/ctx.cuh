@@ -145,6 +145,7 @@ struct hcg_ctx {
   bool timers_on; std::vector<TimerSlot> timers; std::map<std::string,int> timer_idx;
   std::vector<cudaEvent_t> ev_pool; std::vector<TimerPending> ev_pending;
   int64_t launches;
+  unsigned long long* count_dev = nullptr; int* count_typeV = nullptr; int count_ntypes = -1;   // hcg_cells_count scratch
   int sm_count = 0, smem_optin = 0;
   int* fused_done = nullptr;   // per-plane completion counters (collision kernel -> overlapped moments kernel)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

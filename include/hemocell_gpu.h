@@ -153,6 +153,10 @@ hcg_status hcg_cells_add(hcg_ctx*, int32_t ctype, int64_t n_cells, const int64_t
  * which may then be called with n_cells = 0 */
 hcg_status hcg_cells_reserve(hcg_ctx*, int32_t ctype, int64_t spare_cells);
 hcg_status hcg_cells_count(hcg_ctx*, int64_t* n_cells_alive, int64_t* n_particles_alive);
+/* the same two numbers without waiting: out2 = {cells, particles} must be page-locked host memory and is valid after the
+ * next synchronising call (hcg_synchronize, hcg_iterate, any download); lets a host loop read a per-step result without
+ * draining the launch queue every step */
+hcg_status hcg_cells_count_async(hcg_ctx*, int64_t* out2);
 /* whole-array particle access in storage order incl. deleted cells (alive_out marks them);
  * needed by per-operator parity tests and checkpoint restore.  n = hcg_cells_capacity */
 hcg_status hcg_cells_capacity(hcg_ctx*, int64_t* n_cells, int64_t* n_particles);
@@ -213,6 +217,9 @@ hcg_status hcg_get_iteration(hcg_ctx*, int64_t* iter);
 /* ---- run: HemoCell::iterate() x n (core/hemoCell.cpp:299-376), incl. the case file's
  * lattice->collideAndStream() warm-up loop when fluid_only != 0 */
 hcg_status hcg_iterate(hcg_ctx*, int64_t n_steps);
+/* the same steps enqueued without the final wait (the case-file loop `iterate(); setExternalVector(...)` then keeps the
+ * launch queue full); errors of the device work surface at the next synchronising call */
+hcg_status hcg_iterate_async(hcg_ctx*, int64_t n_steps);
 hcg_status hcg_fluid_warmup(hcg_ctx*, int64_t n_steps);
 
 /* ---- pre-inlet (helper/preInlet.cpp): a second, periodic, force-driven context `pre` feeds the inlet of `main`.
