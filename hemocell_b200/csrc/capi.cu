@@ -112,7 +112,7 @@ template <class T> hcg_status upload_table(hcg_ctx* c, CellTypeHost& th, T** dst
   const size_t bytes = sizeof(T)*(n > 0 ? n : 1);
   CUDA_TRY(c, cudaMalloc(dst, bytes));
   th.allocs.push_back(*dst);
-  if (n > 0) CUDA_TRY(c, cudaMemcpy(*dst, src, sizeof(T)*n, cudaMemcpyHostToDevice));
+  if (n > 0) CUDA_TRY(c, hcg_h2d(c, *dst, src, sizeof(T)*n));
   return HCG_OK;
 }
 
@@ -298,7 +298,7 @@ void hcg_destroy(hcg_ctx* c) {
   preinlet_destroy(c);
   peer_destroy(c);
   comm_destroy(c);
-  cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); if (c->F0) cudaFree(c->F0); if (c->bcn) cudaFree(c->bcn); if (c->W2) cudaFree(c->W2); if (c->F2) cudaFree(c->F2); if (c->V) cudaFree(c->V); if (c->V2) cudaFree(c->V2); if (c->d_qsets) cudaFree(c->d_qsets); cudaFree(c->flags); cudaFree(c->d_bc);
+  cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); if (c->F0) cudaFree(c->F0); if (c->bcn) cudaFree(c->bcn); if (c->W2) cudaFree(c->W2); if (c->F2) cudaFree(c->F2); if (c->d_qsets) cudaFree(c->d_qsets); cudaFree(c->flags); cudaFree(c->d_bc);
   if (c->rho) cudaFree(c->rho);
   if (c->count_dev) cudaFree(c->count_dev); if (c->count_typeV) cudaFree(c->count_typeV);
   if (c->fused_done) cudaFree(c->fused_done);
@@ -391,7 +391,7 @@ hcg_status hcg_lattice_set_bc_velocity(hcg_ctx* c, int32_t o, const double u[3])
   if (!c || !u || o < 0 || o > 5) return HCG_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
   for (int k = 0; k < 3; k++) c->bc_vel[o][k] = u[k];
-  CUDA_TRY(c, cudaMemcpy(c->d_bc, c->bc_vel, sizeof(c->bc_vel), cudaMemcpyHostToDevice));
+  CUDA_TRY(c, hcg_h2d(c, c->d_bc, c->bc_vel, sizeof(c->bc_vel)));
   return HCG_OK;
 }
 
@@ -655,14 +655,14 @@ hcg_status hcg_cells_add(hcg_ctx* c, int32_t ctype, int64_t n_cells, const int64
   int32_t* npc;
   CUDA_TRY(c, cudaMalloc(&npc, sizeof(int32_t)*new_p));
   if (c->p_cell && c->np) CUDA_TRY(c, cudaMemcpy(npc, c->p_cell, sizeof(int32_t)*c->np, cudaMemcpyDeviceToDevice));
-  CUDA_TRY(c, cudaMemcpy(npc + c->np, pc.data(), sizeof(int32_t)*add_p, cudaMemcpyHostToDevice));
+  CUDA_TRY(c, hcg_h2d(c, npc + c->np, pc.data(), sizeof(int32_t)*add_p));
   cudaFree(c->p_cell); c->p_cell = npc;
   CUDA_TRY(c, cudaMalloc(&c->cell_alive, new_c));
-  CUDA_TRY(c, cudaMemcpy(c->cell_alive, alive_all.data(), new_c, cudaMemcpyHostToDevice));
+  CUDA_TRY(c, hcg_h2d(c, c->cell_alive, alive_all.data(), new_c));
   CUDA_TRY(c, cudaMalloc(&c->cell_type, sizeof(int32_t)*new_c));
   CUDA_TRY(c, cudaMalloc(&c->cell_base, sizeof(int64_t)*new_c));
-  CUDA_TRY(c, cudaMemcpy(c->cell_type, c->h_cell_type.data(), sizeof(int32_t)*new_c, cudaMemcpyHostToDevice));
-  CUDA_TRY(c, cudaMemcpy(c->cell_base, c->h_cell_base.data(), sizeof(int64_t)*new_c, cudaMemcpyHostToDevice));
+  CUDA_TRY(c, hcg_h2d(c, c->cell_type, c->h_cell_type.data(), sizeof(int32_t)*new_c));
+  CUDA_TRY(c, hcg_h2d(c, c->cell_base, c->h_cell_base.data(), sizeof(int64_t)*new_c));
   // positions
   const int64_t live_p = n_cells*V;
   hcg_status s = ensure_staging(c, sizeof(double)*3*(live_p + 1)); if (s) return s;
@@ -702,7 +702,7 @@ static hcg_status count_launch(hcg_ctx* c) {
     std::vector<int> hv; for (auto& t : c->types) hv.push_back(t.d.V);
     if (c->count_typeV) { CUDA_TRY(c, cudaStreamSynchronize(c->stream)); cudaFree(c->count_typeV); c->count_typeV = nullptr; }
     CUDA_TRY(c, cudaMalloc(&c->count_typeV, sizeof(int)*std::max<size_t>(hv.size(), 1)));
-    if (!hv.empty()) CUDA_TRY(c, cudaMemcpy(c->count_typeV, hv.data(), sizeof(int)*hv.size(), cudaMemcpyHostToDevice));
+    if (!hv.empty()) CUDA_TRY(c, hcg_h2d(c, c->count_typeV, hv.data(), sizeof(int)*hv.size()));
     c->count_ntypes = (int)c->types.size();
   }
   CUDA_TRY(c, cudaMemsetAsync(c->count_dev, 0, sizeof(unsigned long long)*2, c->stream));

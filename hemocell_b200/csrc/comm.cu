@@ -45,6 +45,7 @@ hcg_status local_put(hcg_ctx* c, LocalEndpoint& ep, int peer, const void* data, 
   if (!f) return hcg_fail(c, HCG_ERR_NCCL, std::string(what) + ": cannot create " + tmp);
   const bool ok = bytes == 0 || fwrite(data, 1, bytes, f) == bytes;
   fclose(f);
+  if (getenv("HCG_COMM_DEBUG")) fprintf(stderr, "[comm %d pid %d] put %s bytes %zu first %d %d %d %d\n", c->dom.rank, (int)getpid(), name.c_str(), bytes, bytes >= 16 ? ((const int*)data)[0] : -1, bytes >= 16 ? ((const int*)data)[1] : -1, bytes >= 16 ? ((const int*)data)[2] : -1, bytes >= 16 ? ((const int*)data)[3] : -1);
   if (!ok || rename(tmp.c_str(), name.c_str()) != 0) { unlink(tmp.c_str()); return hcg_fail(c, HCG_ERR_NCCL, std::string(what) + ": cannot write " + name); }
   return HCG_OK;
 }
@@ -63,6 +64,7 @@ hcg_status local_get(hcg_ctx* c, LocalEndpoint& ep, int peer, void* data, size_t
   if (!f) return hcg_fail(c, HCG_ERR_NCCL, std::string(what) + ": cannot open " + name);
   const bool ok = bytes == 0 || fread(data, 1, bytes, f) == bytes;
   fclose(f); unlink(name.c_str());
+  if (getenv("HCG_COMM_DEBUG")) fprintf(stderr, "[comm %d pid %d] got %s bytes %zu first %d %d %d %d\n", c->dom.rank, (int)getpid(), name.c_str(), bytes, bytes >= 16 ? ((const int*)data)[0] : -1, bytes >= 16 ? ((const int*)data)[1] : -1, bytes >= 16 ? ((const int*)data)[2] : -1, bytes >= 16 ? ((const int*)data)[3] : -1);
   if (!ok) return hcg_fail(c, HCG_ERR_NCCL, std::string(what) + ": short read of " + name);
   return HCG_OK;
 }
@@ -73,13 +75,17 @@ hcg_status local_group_end(hcg_ctx* c, const char* what) {
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));               // my send buffers are final
   for (auto& s : ep.sends) {
     if (ep.host.size() < s.bytes) ep.host.resize(s.bytes);
-    CUDA_TRY(c, cudaMemcpy(ep.host.data(), s.ptr, s.bytes, cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemcpyAsync(ep.host.data(), s.ptr, s.bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if ((rc = local_put(c, ep, s.peer, ep.host.data(), s.bytes, what))) break;
   }
   if (!rc) for (auto& q : ep.recvs) {
     if (ep.host.size() < q.bytes) ep.host.resize(q.bytes);
     if ((rc = local_get(c, ep, q.peer, ep.host.data(), q.bytes, what))) break;
-    CUDA_TRY(c, cudaMemcpy(q.ptr, ep.host.data(), q.bytes, cudaMemcpyHostToDevice));
+    // on the context's stream and waited for: a plain cudaMemcpy from pageable memory may return before the DMA has landed,
+    // and the (non-blocking) stream that reads the buffer next is not ordered behind the legacy default stream
+    CUDA_TRY(c, cudaMemcpyAsync(q.ptr, ep.host.data(), q.bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   }
   ep.sends.clear(); ep.recvs.clear();
   return rc;

@@ -105,9 +105,6 @@ struct hcg_ctx {
   double* W2 = nullptr; double* F2 = nullptr;
   bool pops_stale = false;     // the populations lag behind W (materialised on demand by lat_ensure_pops)
   int mo_mode = -1;            // -1 = follow HCG_MOMENT_ONLY, 0 = off, 1 = on (hcg_set_moment_only)
-  // HCG_MOMENT_STATE=vel: the moment-only kernels keep (rhoBar, j / rho) in V / V2 instead of (rhoBar, j) in W / W2
-  double* V = nullptr; double* V2 = nullptr;
-  bool v_valid = false;        // V describes the current state (invalidated wherever the populations are advanced or replaced)
   uint8_t* flags;
   bool u_valid, has_velbc, has_nonfluid;
   bool has_iobc = false;       // Zou-He velocity / pressure nodes present (flags >= HCG_ZH_VEL_XN)
@@ -159,6 +156,13 @@ hcg_status hcg_fail(hcg_ctx* c, hcg_status code, const std::string& msg);
   return hcg_fail((c), HCG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
 #define KERNEL_CHECK(c) do { (c)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
   return hcg_fail((c), HCG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); } while (0)
+
+// host -> device copy that has LANDED when the call returns: a plain cudaMemcpy from pageable memory may return once the data is
+// staged, and the context's non-blocking stream is not ordered behind the legacy default stream
+inline cudaError_t hcg_h2d(hcg_ctx* c, void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(c->stream);
+}
 
 // CUDA-event timers under the reference's Profiler key names (helper/profiler.cpp).  Events are
 // recorded on the launching stream without any host synchronisation; they are resolved in

@@ -7,6 +7,7 @@
 #include "lattice_node.cuh"
 #include <nccl.h>
 #include <cfloat>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <cstdio>
@@ -248,29 +249,85 @@ k_moment_step(const double* __restrict__ Win, const double* Fin, double* __restr
   moment_node<WRITE_U>(Win, Fin, Wout, Fout, U, m, i);      // csrc/moment_step.cuh (also compiled for the host by tests/cpp/moment_host.cu)
 }
 
-template <bool WRITE_U>
-__global__ void __launch_bounds__(256)
-k_moment_step_vel(const double* __restrict__ Vin, const double* Fin, double* __restrict__ Vout, double* __restrict__ Fout,
-                  double* __restrict__ U, LatArgs a, int64_t count) {
-  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  MomentArgs m; m.ny = a.ny; m.nz = a.nz; m.P = a.P; m.body[0] = a.body[0]; m.body[1] = a.body[1]; m.body[2] = a.body[2];
-  moment_node_vel<WRITE_U>(Vin, Fin, Vout, Fout, U, m, i);
-}
-// (rhoBar, j) <-> (rhoBar, j / rho) on the real nodes (entering the velocity-state mode / materialising the populations)
-__global__ void k_w_to_v(const double* __restrict__ W, double* __restrict__ V, int64_t P, int64_t count) {
-  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const int64_t n = i + P;
-  const double rb = W[4*n], inv = 1.0/(1.0 + rb);
-  V[4*n] = rb; V[4*n + 1] = W[4*n + 1]*inv; V[4*n + 2] = W[4*n + 2]*inv; V[4*n + 3] = W[4*n + 3]*inv;
-}
-__global__ void k_v_to_w(const double* __restrict__ V, double* __restrict__ W, int64_t P, int64_t count) {
-  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const int64_t n = i + P;
-  const double rb = V[4*n], rho = 1.0 + rb;
-  W[4*n] = rb; W[4*n + 1] = V[4*n + 1]*rho; W[4*n + 2] = V[4*n + 2]*rho; W[4*n + 3] = V[4*n + 3]*rho;
+// Tile-marching form of the same update (default).  k_moment_step re-evaluates each neighbour's prologue 19 times and pulls
+// 38 x 32 B per node through L1 (measured: 1.20 ms at 256^3, L1 data pipe 63 %, fp64 pipe 39 %).  Here a CTA owns a (TY x TZ)
+// column of the (y, z) plane plus a one-node halo and marches along x: per plane every thread evaluates the 19 post-collision
+// populations of ITS node once (tau1_pops_fast, ~100 fp64 operations) and hands them to the neighbours through shared memory
+// (19 stores + 19 loads of 8 B per node instead of 1216 B of L1 traffic); the populations with c_x = +1 / 0 / -1 are added
+// to the moment accumulators of the planes x + 1 / x / x - 1, which live in registers, so plane x - 1 is complete - and written
+// (new moments, node velocity, reset force: 96 B) - as soon as plane x has been evaluated.  Shared memory is double-buffered:
+// one __syncthreads per plane.  HBM traffic = 64 B read (+ halo re-reads served by L2) + 96 B written per lattice update.
+template <bool WRITE_U, int TY, int TZ>
+__global__ void __launch_bounds__(((TY + 2)*(TZ + 2) + 31)/32*32, 2)
+k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, double* __restrict__ Wout, double* __restrict__ Fout,
+              double* __restrict__ U, LatArgs a, int xc) {
+  constexpr int HY = TY + 2, HZ = TZ + 2, HN = HY*HZ;
+  extern __shared__ double sm_pop[];                     // [2][19][HN]
+  const int t = threadIdx.x;
+  const int hy = t / HZ, hz = t - hy*HZ;
+  const int y = (int)blockIdx.y*TY + hy - 1, z = (int)blockIdx.x*TZ + hz - 1;
+  const int ny = a.ny, nz = a.nz;
+  const bool halo_ok = t < HN && y <= ny && z <= nz;
+  const bool interior = halo_ok && hy >= 1 && hy <= TY && hz >= 1 && hz <= TZ && y < ny && z < nz;
+  const int yw = y < 0 ? ny - 1 : (y >= ny ? 0 : y), zw = z < 0 ? nz - 1 : (z >= nz ? 0 : z);
+  const int64_t col = (int64_t)yw*nz + zw;
+  const int x_lo = 1 + (int)blockIdx.z*xc, x_hi = min(x_lo + xc - 1, a.nxl);
+  if (x_lo > a.nxl) return;
+  double w0 = 0, w1 = 0, w2 = 0, w3 = 0, f0 = 0, f1 = 0, f2 = 0, f3;
+  if (halo_ok) {
+    const int64_t n = (int64_t)(x_lo - 1)*a.P + col;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w0), "=d"(w1), "=d"(w2), "=d"(w3) : "l"(Win + 4*n));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(f0), "=d"(f1), "=d"(f2), "=d"(f3) : "l"(Fin + 4*n));
+  }
+  // moment accumulators (rhoBar, j) of the planes lx - 1, lx, lx + 1
+  double a0r = 0, a0x = 0, a0y = 0, a0z = 0, a1r = 0, a1x = 0, a1y = 0, a1z = 0;
+  double p0 = 0, p1 = 0, p2 = 0;                         // this column's own force on plane lx - 1 (node velocity of that plane)
+  const int i = hy*HZ + hz;
+  for (int lx = x_lo - 1; lx <= x_hi + 1; lx++) {
+    double* sb = sm_pop + (size_t)((lx - x_lo + 1) & 1)*19*HN;
+    const double c0 = f0, c1 = f1, c2 = f2;              // own force on plane lx
+    if (halo_ok) {
+      double p[19];
+      tau1_pops_fast(w0, w1, w2, w3, f0, f1, f2, p);
+#pragma unroll
+      for (int q = 0; q < 19; q++) sb[q*HN + t] = p[q];
+      if (lx < x_hi + 1) {                               // next plane's state: in flight during the gather
+        const int64_t n = (int64_t)(lx + 1)*a.P + col;
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w0), "=d"(w1), "=d"(w2), "=d"(w3) : "l"(Win + 4*n));
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(f0), "=d"(f1), "=d"(f2), "=d"(f3) : "l"(Fin + 4*n));
+      }
+    }
+    __syncthreads();
+    if (interior) {
+      // arriving population q comes from the node at -c_q: index i - c_y HZ - c_z
+      const double q0 = sb[0*HN + i];
+      const double q2 = sb[2*HN + i + HZ], q11 = sb[11*HN + i - HZ], q3 = sb[3*HN + i + 1], q12 = sb[12*HN + i - 1];
+      const double q8 = sb[8*HN + i + HZ + 1], q9 = sb[9*HN + i + HZ - 1], q17 = sb[17*HN + i - HZ - 1], q18 = sb[18*HN + i - HZ + 1];
+      const double q10 = sb[10*HN + i], q13 = sb[13*HN + i - HZ], q14 = sb[14*HN + i + HZ], q15 = sb[15*HN + i - 1], q16 = sb[16*HN + i + 1];
+      const double q1 = sb[1*HN + i], q4 = sb[4*HN + i + HZ], q5 = sb[5*HN + i - HZ], q6 = sb[6*HN + i + 1], q7 = sb[7*HN + i - 1];
+      // c_x = -1 -> plane lx - 1 (complete now)
+      const double sm = ((q1 + q4) + (q5 + q6)) + q7;
+      a0r += sm; a0x -= sm; a0y += q5 - q4; a0z += q7 - q6;
+      if (lx - 1 >= x_lo) {
+        const int64_t n = (int64_t)(lx - 1)*a.P + col;
+        double2* Ww = reinterpret_cast<double2*>(Wout + 4*n);
+        Ww[0] = make_double2(a0r, a0x); Ww[1] = make_double2(a0y, a0z);
+        if (WRITE_U) {
+          const double rho = 1.0 + a0r, inv = 1.0/rho;
+          double2* Uw = reinterpret_cast<double2*>(U + 4*n);
+          Uw[0] = make_double2(a0x*inv + 0.5*p0, a0y*inv + 0.5*p1); Uw[1] = make_double2(a0z*inv + 0.5*p2, rho);
+        }
+        double2* Fw = reinterpret_cast<double2*>(Fout + 4*n);
+        Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0);
+      }
+      // c_x = 0 -> plane lx; c_x = +1 -> plane lx + 1; then rotate the accumulators one plane on
+      const double s0 = (((q0 + q2) + (q3 + q8)) + ((q9 + q11) + (q12 + q17))) + q18;
+      const double sp = ((q10 + q13) + (q14 + q15)) + q16;
+      a0r = a1r + s0; a0x = a1x; a0y = a1y + (((q11 - q2) + (q17 - q8)) + (q18 - q9)); a0z = a1z + (((q12 - q3) + (q17 - q8)) + (q9 - q18));
+      a1r = sp; a1x = sp; a1y = q13 - q14; a1z = q15 - q16;
+      p0 = c0; p1 = c1; p2 = c2;
+    }
+  }
 }
 
 // Off-equilibrium momentum flux of the post-stream populations (output path only: the "ShearStress"
@@ -814,7 +871,7 @@ hcg_status exchange(hcg_ctx* c, double* buf, int64_t P /* elements per plane */,
 hcg_status ensure_qsets(hcg_ctx* c) {
   if (!c->d_qsets) {
     CUDA_TRY(c, cudaMalloc(&c->d_qsets, sizeof(h_qsets)));
-    CUDA_TRY(c, cudaMemcpy(c->d_qsets, h_qsets, sizeof(h_qsets), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, hcg_h2d(c, c->d_qsets, h_qsets, sizeof(h_qsets)));
   }
   return HCG_OK;
 }
@@ -948,7 +1005,7 @@ hcg_status lat_collide_stream(hcg_ctx* c, bool reset_force) {
     if (reset_force && c->F0 && (s = lat_reset_force(c))) return s;
   }
   c->cur = 1 - c->cur;
-  c->u_valid = false; c->w_valid = false; c->v_valid = false;
+  c->u_valid = false; c->w_valid = false;
   if (peer_on(c)) return peer_barrier(c);          // the face planes were stored into the neighbours by the kernel itself
   return lat_halo_exchange_pop(c);
 }
@@ -990,17 +1047,22 @@ static int moment_only_env() {
   if (on < 0) { const char* e = getenv("HCG_MOMENT_ONLY"); on = e ? atoi(e) : 0; }
   return on;
 }
-static bool moment_state_vel() {                          // (read on every call: a few times per step; lets a test switch it)
-  const char* e = getenv("HCG_MOMENT_STATE");
-  return e && strcmp(e, "vel") == 0;
-}
-// level 1 = single rank; level 2 = also slab-decomposed runs: the W and F face planes (and U on interpolation steps) go to the
-// neighbours' ghost planes through the NCCL send/recv exchange, whatever the transport of the population path is
+// level 1 = single rank; level 2 = also slab-decomposed runs: the W face planes (and U on interpolation steps) go to the
+// neighbours' ghost planes through the send/recv exchange, whatever the transport of the population path is
 bool lat_moment_eligible(hcg_ctx* c) {
   const int level = c->mo_mode < 0 ? moment_only_env() : c->mo_mode;
   return level > 0 && (c->dom.n_ranks == 1 || level >= 2) && tau1_enabled() && c->omega == 1.0 && c->dom.periodic[0] && c->dom.periodic[1] && c->dom.periodic[2]
       && !c->has_nonfluid && !c->real_nonfluid && !c->has_velbc && !c->has_iobc && !c->F0
-      && ((c->W && c->w_valid) || (moment_state_vel() && c->v_valid));
+      && c->W && c->w_valid;
+}
+static int moment_kernel_env() {                          // HCG_MOMENT_KERNEL=simple: one thread per node, 19 neighbour loads (k_moment_step)
+  const char* e = getenv("HCG_MOMENT_KERNEL");            // (read per step: lets a test compare the two kernels in one process)
+  return (e && strcmp(e, "simple") == 0) ? 0 : 1;
+}
+static int moment_chunk_env() {                           // planes per CTA of k_moment_tile
+  static int xc = -1;
+  if (xc < 0) { const char* e = getenv("HCG_MOMENT_XC"); xc = e ? atoi(e) : 32; if (xc < 1) xc = 32; }
+  return xc;
 }
 hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
   hcg_status s = ensure_qsets(c); if (s) return s;
@@ -1008,38 +1070,34 @@ hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
     CUDA_TRY(c, cudaMalloc(&c->W2, sizeof(double)*4*c->S)); CUDA_TRY(c, cudaMalloc(&c->F2, sizeof(double)*4*c->S));
     CUDA_TRY(c, cudaMemsetAsync(c->W2, 0, sizeof(double)*4*c->S, c->stream)); CUDA_TRY(c, cudaMemsetAsync(c->F2, 0, sizeof(double)*4*c->S, c->stream));
   }
-  const bool vel = moment_state_vel();
-  if (vel) {
-    if (!c->V) {
-      CUDA_TRY(c, cudaMalloc(&c->V, sizeof(double)*4*c->S)); CUDA_TRY(c, cudaMalloc(&c->V2, sizeof(double)*4*c->S));
-      CUDA_TRY(c, cudaMemsetAsync(c->V, 0, sizeof(double)*4*c->S, c->stream)); CUDA_TRY(c, cudaMemsetAsync(c->V2, 0, sizeof(double)*4*c->S, c->stream));
-    }
-    if (!c->v_valid) {                                     // entering: (rhoBar, j) of the moments pass -> (rhoBar, j / rho)
-      k_w_to_v<<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->W, c->V, c->P, c->Nl);
-      KERNEL_CHECK(c);
-      c->v_valid = true;
-    }
-  }
-  double*& Sin = vel ? c->V : c->W; double*& Sout = vel ? c->V2 : c->W2;
   // ghost planes of the state and of the (spread) force: periodic images of the end planes / the neighbours' face planes
-  if ((s = exchange(c, Sin, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
+  if ((s = exchange(c, c->W, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
   if ((s = exchange(c, c->F, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
   LatArgs a = make_args(c);
-  {
-    OpTimer tk(c, "kernel:k_moment_step");
-    const unsigned nb = nblk(c->Nl, 256);
-    if (vel) {
-      if (write_u) k_moment_step_vel<true><<<nb, 256, 0, c->stream>>>(Sin, c->F, Sout, c->F2, c->U, a, c->Nl);
-      else k_moment_step_vel<false><<<nb, 256, 0, c->stream>>>(Sin, c->F, Sout, c->F2, c->U, a, c->Nl);
+  if (moment_kernel_env()) {
+    OpTimer tk(c, "kernel:k_moment_tile");
+    constexpr int TY = 8, TZ = 32;
+    constexpr int NT = ((TY + 2)*(TZ + 2) + 31)/32*32;
+    const size_t smem = sizeof(double)*2*19*(TY + 2)*(TZ + 2);
+    const int xc = std::min(moment_chunk_env(), c->nxl);
+    dim3 grid((unsigned)((a.nz + TZ - 1)/TZ), (unsigned)((a.ny + TY - 1)/TY), (unsigned)((c->nxl + xc - 1)/xc));
+    if (write_u) {
+      CUDA_TRY(c, cudaFuncSetAttribute(k_moment_tile<true, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_moment_tile<true, TY, TZ><<<grid, NT, smem, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, xc);
     } else {
-      if (write_u) k_moment_step<true><<<nb, 256, 0, c->stream>>>(Sin, c->F, Sout, c->F2, c->U, a, c->Nl);
-      else k_moment_step<false><<<nb, 256, 0, c->stream>>>(Sin, c->F, Sout, c->F2, c->U, a, c->Nl);
+      CUDA_TRY(c, cudaFuncSetAttribute(k_moment_tile<false, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_moment_tile<false, TY, TZ><<<grid, NT, smem, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, xc);
     }
     KERNEL_CHECK(c);
+  } else {
+    OpTimer tk(c, "kernel:k_moment_step");
+    const unsigned nb = nblk(c->Nl, 256);
+    if (write_u) k_moment_step<true><<<nb, 256, 0, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, c->Nl);
+    else k_moment_step<false><<<nb, 256, 0, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, c->Nl);
+    KERNEL_CHECK(c);
   }
-  std::swap(Sin, Sout); std::swap(c->F, c->F2);             // the second buffers now hold the inputs of this step (kept for lat_ensure_pops)
-  c->pops_stale = true; c->u_valid = write_u; c->f_clean = true;
-  c->w_valid = !vel;                                        // j state: W is the current state; velocity state: V is, W lags
+  std::swap(c->W, c->W2); std::swap(c->F, c->F2);           // the second buffers now hold the inputs of this step (kept for lat_ensure_pops)
+  c->pops_stale = true; c->u_valid = write_u; c->f_clean = true; c->w_valid = true;
   if (write_u) return lat_halo_exchange_u(c);
   return HCG_OK;
 }
@@ -1047,12 +1105,7 @@ hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
 hcg_status lat_ensure_pops(hcg_ctx* c) {
   if (!c->pops_stale) return HCG_OK;
   LatArgs a = make_args(c);
-  const double* Wprev = c->W2;
-  if (moment_state_vel() && c->v_valid) {                  // velocity state: the previous inputs are (rhoBar, j / rho) in V2
-    k_v_to_w<<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->V2, c->W2, c->P, c->Nl);
-    KERNEL_CHECK(c);
-  }
-  k_collide_tau1<false, 0, false><<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->g[1 - c->cur], c->g[c->cur], c->F2, Wprev, c->flags, a, 0, c->Nl, nullptr, nullptr);
+  k_collide_tau1<false, 0, false><<<nblk(c->Nl, 256), 256, 0, c->stream>>>(c->g[1 - c->cur], c->g[c->cur], c->F2, c->W2, c->flags, a, 0, c->Nl, nullptr, nullptr);
   KERNEL_CHECK(c);
   c->pops_stale = false;
   return lat_halo_exchange_pop(c);
@@ -1107,7 +1160,7 @@ hcg_status lat_collide_moments_overlapped(hcg_ctx* c, bool* done_out) {
     OpTimer tk(c, "kernel:k_collide_stream");
     if ((s = lat_collide_rows(c, false, 0, nxl*ny, c->stream, c->fused_done))) return s;
   }
-  c->cur = 1 - c->cur; c->w_valid = false; c->v_valid = false;
+  c->cur = 1 - c->cur; c->w_valid = false;
   {
     // planes m_lo..m_hi; multi-GPU: the face planes need the neighbour's halo and follow after the exchange
     const int m_lo = R > 1 ? 2 : 1, m_hi = R > 1 ? nxl - 1 : nxl;
@@ -1160,7 +1213,7 @@ hcg_status lat_init_equilibrium(hcg_ctx* c, double rho, const double u[3]) {
   KERNEL_CHECK(c);
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   cudaFree(dv);
-  c->u_valid = false; c->w_valid = false; c->v_valid = false; c->pops_stale = false;
+  c->u_valid = false; c->w_valid = false; c->pops_stale = false;
   return lat_halo_exchange_pop(c);
 }
 
@@ -1173,7 +1226,7 @@ hcg_status lat_pop_to_reference(hcg_ctx* c, double* dst_dev) {
 }
 
 hcg_status lat_pop_from_reference(hcg_ctx* c, const double* src_dev) {
-  c->pops_stale = false; c->v_valid = false;              // the uploaded populations replace whatever state there was
+  c->pops_stale = false;                                  // the uploaded populations replace whatever state there was
   LatArgs a = make_args(c);
   double* s = c->g[1 - c->cur];
   CUDA_TRY(c, cudaMemsetAsync(s, 0, sizeof(double)*19*c->S, c->stream));

@@ -184,7 +184,7 @@ hcg_status multi_upload_cell_gid(hcg_ctx* c) {
     CUDA_TRY(c, cudaMalloc(&c->cell_gid, sizeof(int64_t)*(size_t)std::max<int64_t>(nc, 1)));
     c->cell_gid_cap = nc;
   }
-  if (nc) CUDA_TRY(c, cudaMemcpy(c->cell_gid, c->h_cell_id.data(), sizeof(int64_t)*nc, cudaMemcpyHostToDevice));
+  if (nc) CUDA_TRY(c, hcg_h2d(c, c->cell_gid, c->h_cell_id.data(), sizeof(int64_t)*nc));
   c->cell_gid_dirty = false;
   return HCG_OK;
 }
@@ -356,7 +356,7 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
     double* h_arr[12];
     for (int k = 0; k < 3; k++) { h_arr[k] = c->pos[k]; h_arr[3+k] = c->vel[k]; h_arr[6+k] = c->frc[k]; h_arr[9+k] = c->frep[k]; }
     CUDA_TRY(c, cudaMalloc(&m.d_arr, sizeof(h_arr)));
-    CUDA_TRY(c, cudaMemcpy(m.d_arr, h_arr, sizeof(h_arr), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, hcg_h2d(c, m.d_arr, h_arr, sizeof(h_arr)));
   }
   for (int f = 0; f < 2; f++) if (tmp_send[f].n) {
     k_pack_cells<<<tmp_send[f].n, 256, 0, c->stream>>>(tmp_send[f].d_cells, tmp_send[f].d_off, tmp_send[f].n, c->cell_base,
@@ -401,7 +401,7 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
       CUDA_TRY(c, cudaMalloc(&m.d_cell_shared, (size_t)std::max<int64_t>(nc, 1)));
       m.cell_shared_cap = nc;
     }
-    CUDA_TRY(c, cudaMemcpy(m.d_cell_shared, flag.data(), (size_t)std::max<int64_t>(nc, 1), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, hcg_h2d(c, m.d_cell_shared, flag.data(), (size_t)std::max<int64_t>(nc, 1)));
   }
   // peer transport: receive buffers sized for the new lists, mappings re-published (collective, cheap)
   if (c->peer.transport == 1) {

@@ -163,6 +163,14 @@ hcg_status peer_setup(hcg_ctx* c) {
 
 hcg_status peer_barrier(hcg_ctx* c) {
   PeerState& p = c->peer;
+  if (c->local) {
+    // host-staged communicator (ranks may share a GPU): a spinning flag kernel would deadlock against any device-wide
+    // synchronising call (cudaFree, cudaMalloc) of the rank it waits for, so the neighbours meet on the host instead:
+    // my stream is drained (my peer stores have landed), then one token goes each way
+    if (!p.d_blob) CUDA_TRY(c, cudaMalloc(&p.d_blob, 3*sizeof(PeerBlob)));
+    char* d = (char*)p.d_blob;
+    return multi_neighbour_exchange(c, d, 8, d + 8, 8, d + 16, 8, d + 24, 8);
+  }
   p.epoch++;
   // my left neighbour watches its word [1] (written by ITS right neighbour = me), and vice versa
   unsigned long long* lw = p.link[0].rank >= 0 ? (unsigned long long*)p.link[0].ptr[3] + 1 : nullptr;

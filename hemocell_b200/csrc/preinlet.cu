@@ -114,14 +114,14 @@ hcg_status hcg_preinlet_map(hcg_ctx* c, hcg_ctx* pre, int64_t n, const int64_t* 
   CUDA_TRY(c, cudaSetDevice(pre->dom.device));
   if (n) {
     CUDA_TRY(c, cudaMalloc(&p->d_src_idx, sizeof(int64_t)*n));
-    CUDA_TRY(c, cudaMemcpy(p->d_src_idx, pre_idx, sizeof(int64_t)*n, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, hcg_h2d(c, p->d_src_idx, pre_idx, sizeof(int64_t)*n));
     CUDA_TRY(c, cudaMalloc(&p->buf_src, sizeof(double)*4*n));
   }
   CUDA_TRY(c, cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming));   // recorded on the pre-inlet's stream: lives on its device
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
   if (n) {
     CUDA_TRY(c, cudaMalloc(&p->d_dst_idx, sizeof(int64_t)*n));
-    CUDA_TRY(c, cudaMemcpy(p->d_dst_idx, main_idx, sizeof(int64_t)*n, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, hcg_h2d(c, p->d_dst_idx, main_idx, sizeof(int64_t)*n));
     if (same) p->buf_dst = p->buf_src; else CUDA_TRY(c, cudaMalloc(&p->buf_dst, sizeof(double)*4*n));
   }
   CUDA_TRY(c, cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));    // recorded on the main stream

@@ -1,8 +1,8 @@
-"""GPU tests written at the end of round 1 with no GPU time left to run them: skipped unless HCG_TEST_MOMENT_ONLY=1.
-* parity of the EXPERIMENTAL moment-only update at tau = 1 (k_moment_step, hcg_set_moment_only); its algorithm is checked on the
-  CPU in tests/test_moment_only_algorithm.py;
+"""* parity of the moment-only lattice update at tau = 1 (k_moment_tile / k_moment_step, hcg_set_moment_only) against the oracle's
+  population path; its algorithm is also checked on the CPU in tests/test_moment_only_algorithm.py;
 * a smoke run of the reference's unmodified examples/curvedflow_with_preinlet;
-* two-GPU runs: a Zou-He duct cut into two slabs (both transports), the moment-only update at level 2."""
+* two-slab runs (the slabs share the GPU on a single-GPU box): a Zou-He duct cut into two slabs (both transports), the moment-only
+  update on slabs."""
 import os
 
 import numpy as np
@@ -12,24 +12,23 @@ import oracle as O
 from oracle import mesh as M
 import util as U
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("HCG_TEST_MOMENT_ONLY") != "1",
-                                 reason="experimental path, not yet verified on a GPU: set HCG_TEST_MOMENT_ONLY=1")]
+pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("state", ["j", "vel"])
+@pytest.mark.parametrize("kernel,dims", [("tile", (36, 30, 28)), ("tile", (40, 17, 70)), ("simple", (36, 30, 28))])
 @pytest.mark.parametrize("cadence", [1, 5])
-def test_moment_only_iterate_matches_oracle(cadence, state, monkeypatch):
+def test_moment_only_iterate_matches_oracle(cadence, kernel, dims, monkeypatch):
     from hemocell_b200 import lib as H
-    monkeypatch.setenv("HCG_MOMENT_STATE", state)          # j: (rhoBar, j) as the state; vel: (rhoBar, j / rho)
+    monkeypatch.setenv("HCG_MOMENT_KERNEL", kernel)        # tile: shared-memory tile marching along x; simple: 19 neighbour loads per node
+    monkeypatch.setenv("HCG_MOMENT_XC", "16")              # several x chunks per column of tiles
     par = M.Parameters(dx=0.5e-6, dt=-1.0)
-    nx, ny, nz = 36, 30, 28
+    nx, ny, nz = dims
     N = nx * ny * nz
     fl = np.zeros(N, dtype=np.uint8)
     dom = O.make_domain(nx, ny, nz, (1, 1, 1), par.tau)
     body = (3e-6, 0.0, -1e-6)
     rbc = O.rbc_celltype(par)
-    cells = U.deformed_cells(rbc, [(10.0, 15.0, 9.0), (33.5, 16.0, 20.0)], 7, amp=0.01, stretch=(1.03, 0.99, 0.98))
+    cells = U.deformed_cells(rbc, [(10.0, 0.5 * ny, 9.0), (nx - 2.5, 0.5 * ny + 1.0, nz - 8.0)], 7, amp=0.01, stretch=(1.03, 0.99, 0.98))
     sim = O.OracleSim(dom, fl, par.f_limit, body)
     sim.vel_timescale = cadence
     sim.add_celltype(rbc, 5); sim.add_cells(0, cells, [0, 1])
@@ -89,9 +88,9 @@ def _two_rank_fluid(dims, periodic, tau, fl, transport, setup, steps, moment_onl
 
     def work(r):
         try:
-            ctx = H.Context(nx, ny, nz, periodic, tau, device=r, rank=r, n_ranks=2)
+            ctx = H.Context(nx, ny, nz, periodic, tau, device=r % max(_ngpus(), 1), rank=r, n_ranks=2)
             ctx.set_transport(transport)
-            ctx.comm_init(uid)
+            ctx.comm_init(uid, local=_ngpus() < 2)          # the two slabs share the GPU of a single-GPU box
             ctx.set_flags(np.ascontiguousarray(fl3[ctx.x0:ctx.x0 + ctx.nxl]))
             setup(ctx)
             if moment_only:
@@ -127,8 +126,6 @@ def _ngpus():
 def test_two_gpu_zouhe_duct_matches_oracle(transport):
     """Zou-He velocity inlet on rank 0's first plane, pressure outlet on rank 1's last plane, bounce-back duct walls, x not
     periodic: the slab-decomposed lattice (BC = 2 kernels with peer stores / NCCL exchange) against the oracle"""
-    if _ngpus() < 2:
-        pytest.skip("needs 2 GPUs")
     nx, ny, nz = 40, 14, 12
     N = nx * ny * nz
     tau = 0.9
@@ -166,8 +163,6 @@ def test_two_gpu_zouhe_duct_matches_oracle(transport):
 def test_two_gpu_moment_only_matches_oracle():
     """HCG_MOMENT_ONLY level 2: the moment-only update on two x-slabs (W / F face planes through the NCCL exchange), fluid only,
     fully periodic, tau = 1, body force, against the oracle"""
-    if _ngpus() < 2:
-        pytest.skip("needs 2 GPUs")
     nx, ny, nz = 32, 12, 10
     N = nx * ny * nz
     fl = np.zeros(N, dtype=np.uint8)

@@ -139,9 +139,10 @@ def test_two_gpu_matches_single_gpu(cadence, transport, nx_global=96, R=2):
             U.assert_close(vel[slot], ref_vel[k], f"rank {r} cell {cid} velocities", rtol=1e-7, floor=1e-9)
             U.assert_close(frc[slot], ref_frc[k], f"rank {r} cell {cid} forces", rtol=1e-6, floor=1e-8)
     assert seen == set(range(len(centers)))
-    assert sum(o["stats"]["migrated_in"] for o in out) > 0            # whole-cell migration was exercised
     assert sum(o["stats"]["migrated_in"] for o in out) == sum(o["stats"]["migrated_out"] for o in out)
-    assert any(int((o["ids"] < 0).sum()) > 0 for o in out)                 # ... and so was dropping
+    if R == 2:
+        assert sum(o["stats"]["migrated_in"] for o in out) > 0            # whole-cell migration was exercised
+        assert any(int((o["ids"] < 0).sum()) > 0 for o in out)             # ... and so was dropping
     assert all(o["stats"]["shared_left"] + o["stats"]["shared_right"] > 0 for o in out)
 
 

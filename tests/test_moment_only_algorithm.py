@@ -87,14 +87,10 @@ def test_kernel_body_compiled_for_the_host_matches_the_numpy_restatement(tmp_pat
     assert np.max(np.abs(Uo[1:-1, ..., 3] - (1.0 + ref[0]))) < 1e-15
     assert np.all(Fout[1:-1, ..., :3] == body) and np.all(Fout[1:-1, ..., 3] == 0.0)
     assert np.isnan(Wout[0]).all() and np.isnan(Wout[-1]).all()            # ghost planes are the caller's business
-    # the velocity-state variant (HCG_MOMENT_STATE=vel): (rhoBar, j / rho) in, (rhoBar', j' / rho') out
-    V = W.copy(); V[1:] = W[1:] / (1.0 + W[0])
-    Vin = padded(V)
-    Vout = np.full_like(Win, np.nan); Fout2 = np.full_like(Win, np.nan); Uo2 = np.full_like(Win, np.nan)
-    lib.moment_host_vel(nx, ny, nz, Vin.ctypes.data_as(dp), Fin.ctypes.data_as(dp), Vout.ctypes.data_as(dp), Fout2.ctypes.data_as(dp),
-                        Uo2.ctypes.data_as(dp), body.ctypes.data_as(dp), 1)
-    gv = np.moveaxis(Vout[1:-1], -1, 0)
-    assert np.max(np.abs(gv[0] - ref[0])) < 1e-15 + 1e-13 * np.max(np.abs(ref[0]))
-    assert np.max(np.abs(gv[1:] * (1.0 + gv[0]) - ref[1:])) < 1e-15 + 1e-13 * np.max(np.abs(ref[1:]))
-    assert np.max(np.abs(np.moveaxis(Uo2[1:-1], -1, 0)[:3] - u)) < 1e-15 + 1e-13 * np.max(np.abs(u))
-    assert np.all(Fout2[1:-1, ..., :3] == body)
+    # the re-associated evaluation of the 19 post-collision populations (k_moment_tile) against guo_collide_tau1
+    n = 5000
+    w = np.zeros((n, 4)); w[:, 0] = 5e-3 * rng.standard_normal(n); w[:, 1:] = 0.05 * rng.standard_normal((n, 3))
+    f = 1e-3 * rng.standard_normal((n, 3))
+    fast = np.empty((n, 19)); ref = np.empty((n, 19))
+    lib.tau1_pops_both(n, w.ctypes.data_as(dp), f.ctypes.data_as(dp), fast.ctypes.data_as(dp), ref.ctypes.data_as(dp))
+    assert np.max(np.abs(fast - ref)) < 2e-17 + 1e-14 * np.max(np.abs(ref))
