@@ -262,7 +262,11 @@ __global__ void __launch_bounds__(((TY + 2)*(TZ + 2) + 31)/32*32, 2)
 k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, double* __restrict__ Wout, double* __restrict__ Fout,
               double* __restrict__ U, LatArgs a, int xc) {
   constexpr int HY = TY + 2, HZ = TZ + 2, HN = HY*HZ;
-  extern __shared__ double sm_pop[];                     // [2][19][HN]
+  // shared memory: the 19 populations of the current plane [19][HN], then a two-deep ring of the (W, F) inputs of the planes
+  // ahead, one 64-byte slot per thread and stage [2][NT][8], filled by cp.async (no registers held while the loads fly)
+  extern __shared__ __align__(16) double sm_pop[];
+  constexpr int NT = (HN + 31)/32*32;
+  double* ring = sm_pop + 19*HN;
   const int t = threadIdx.x;
   const int hy = t / HZ, hz = t - hy*HZ;
   const int y = (int)blockIdx.y*TY + hy - 1, z = (int)blockIdx.x*TZ + hz - 1;
@@ -273,37 +277,43 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
   const int64_t col = (int64_t)yw*nz + zw;
   const int x_lo = 1 + (int)blockIdx.z*xc, x_hi = min(x_lo + xc - 1, a.nxl);
   if (x_lo > a.nxl) return;
-  double w0 = 0, w1 = 0, w2 = 0, w3 = 0, f0 = 0, f1 = 0, f2 = 0, f3;
-  if (halo_ok) {
-    const int64_t n = (int64_t)(x_lo - 1)*a.P + col;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w0), "=d"(w1), "=d"(w2), "=d"(w3) : "l"(Win + 4*n));
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(f0), "=d"(f1), "=d"(f2), "=d"(f3) : "l"(Fin + 4*n));
-  }
-  // moment accumulators (rhoBar, j) of the planes lx - 1, lx, lx + 1
+  const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(ring + (size_t)t*8);
+  constexpr uint32_t STAGE = NT*64;
+  auto fetch = [&](int lx) {                             // (W, F) of this thread's node on plane lx -> ring stage lx & 1
+    if (halo_ok && lx <= x_hi + 1) {
+      const int64_t n = (int64_t)lx*a.P + col;
+      const uint32_t dst = slot0 + (uint32_t)(lx & 1)*STAGE;
+      const double* w = Win + 4*n; const double* f = Fin + 4*n;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(w) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16), "l"(w + 2) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 32), "l"(f) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 48), "l"(f + 2) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(x_lo - 1);
+  fetch(x_lo);
+  // moment accumulators (rhoBar, j) of the planes lx - 1 and lx; this column's own force on plane lx - 1
   double a0r = 0, a0x = 0, a0y = 0, a0z = 0, a1r = 0, a1x = 0, a1y = 0, a1z = 0;
-  double p0 = 0, p1 = 0, p2 = 0;                         // this column's own force on plane lx - 1 (node velocity of that plane)
+  double p0 = 0, p1 = 0, p2 = 0;
   const int i = hy*HZ + hz;
+  double* sb = sm_pop;
   for (int lx = x_lo - 1; lx <= x_hi + 1; lx++) {
-    double* sb = sm_pop + (size_t)((lx - x_lo + 1) & 1)*19*HN;
-    const double c0 = f0, c1 = f1, c2 = f2;              // own force on plane lx
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // plane lx has landed (the group of plane lx + 1 may still fly)
+    double c0 = 0, c1 = 0, c2 = 0;
     if (halo_ok) {
+      const double2* sl = reinterpret_cast<const double2*>(ring + (size_t)(lx & 1)*NT*8 + (size_t)t*8);
+      const double2 wa = sl[0], wb = sl[1], fa = sl[2], fb = sl[3];
+      c0 = fa.x; c1 = fa.y; c2 = fb.x;
       double p[19];
-      tau1_pops_fast(w0, w1, w2, w3, f0, f1, f2, p);
+      tau1_pops_fast(wa.x, wa.y, wb.x, wb.y, fa.x, fa.y, fb.x, p);
 #pragma unroll
       for (int q = 0; q < 19; q++) sb[q*HN + t] = p[q];
-      if (lx < x_hi + 1) {                               // next plane's state: in flight during the gather
-        const int64_t n = (int64_t)(lx + 1)*a.P + col;
-        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w0), "=d"(w1), "=d"(w2), "=d"(w3) : "l"(Win + 4*n));
-        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(f0), "=d"(f1), "=d"(f2), "=d"(f3) : "l"(Fin + 4*n));
-      }
     }
     __syncthreads();
+    fetch(lx + 2);                                       // into the stage just consumed (every thread's reads of it are behind the barrier)
     if (interior) {
       // arriving population q comes from the node at -c_q: index i - c_y HZ - c_z
-      const double q0 = sb[0*HN + i];
-      const double q2 = sb[2*HN + i + HZ], q11 = sb[11*HN + i - HZ], q3 = sb[3*HN + i + 1], q12 = sb[12*HN + i - 1];
-      const double q8 = sb[8*HN + i + HZ + 1], q9 = sb[9*HN + i + HZ - 1], q17 = sb[17*HN + i - HZ - 1], q18 = sb[18*HN + i - HZ + 1];
-      const double q10 = sb[10*HN + i], q13 = sb[13*HN + i - HZ], q14 = sb[14*HN + i + HZ], q15 = sb[15*HN + i - 1], q16 = sb[16*HN + i + 1];
       const double q1 = sb[1*HN + i], q4 = sb[4*HN + i + HZ], q5 = sb[5*HN + i - HZ], q6 = sb[6*HN + i + 1], q7 = sb[7*HN + i - 1];
       // c_x = -1 -> plane lx - 1 (complete now)
       const double sm = ((q1 + q4) + (q5 + q6)) + q7;
@@ -320,14 +330,20 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
         double2* Fw = reinterpret_cast<double2*>(Fout + 4*n);
         Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0);
       }
-      // c_x = 0 -> plane lx; c_x = +1 -> plane lx + 1; then rotate the accumulators one plane on
+      // c_x = 0 -> plane lx; c_x = +1 -> plane lx + 1; then the accumulators move one plane on
+      const double q0 = sb[0*HN + i];
+      const double q2 = sb[2*HN + i + HZ], q11 = sb[11*HN + i - HZ], q3 = sb[3*HN + i + 1], q12 = sb[12*HN + i - 1];
+      const double q8 = sb[8*HN + i + HZ + 1], q9 = sb[9*HN + i + HZ - 1], q17 = sb[17*HN + i - HZ - 1], q18 = sb[18*HN + i - HZ + 1];
       const double s0 = (((q0 + q2) + (q3 + q8)) + ((q9 + q11) + (q12 + q17))) + q18;
-      const double sp = ((q10 + q13) + (q14 + q15)) + q16;
       a0r = a1r + s0; a0x = a1x; a0y = a1y + (((q11 - q2) + (q17 - q8)) + (q18 - q9)); a0z = a1z + (((q12 - q3) + (q17 - q8)) + (q9 - q18));
+      const double q10 = sb[10*HN + i], q13 = sb[13*HN + i - HZ], q14 = sb[14*HN + i + HZ], q15 = sb[15*HN + i - 1], q16 = sb[16*HN + i + 1];
+      const double sp = ((q10 + q13) + (q14 + q15)) + q16;
       a1r = sp; a1x = sp; a1y = q13 - q14; a1z = q15 - q16;
       p0 = c0; p1 = c1; p2 = c2;
     }
+    __syncthreads();                                     // the populations of this plane are consumed: the buffer is free
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // Off-equilibrium momentum flux of the post-stream populations (output path only: the "ShearStress"
@@ -1060,9 +1076,8 @@ static int moment_kernel_env() {                          // HCG_MOMENT_KERNEL=s
   return (e && strcmp(e, "simple") == 0) ? 0 : 1;
 }
 static int moment_chunk_env() {                           // planes per CTA of k_moment_tile
-  static int xc = -1;
-  if (xc < 0) { const char* e = getenv("HCG_MOMENT_XC"); xc = e ? atoi(e) : 32; if (xc < 1) xc = 32; }
-  return xc;
+  const char* e = getenv("HCG_MOMENT_XC"); int xc = e ? atoi(e) : 32;
+  return xc < 1 ? 32 : xc;
 }
 hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
   hcg_status s = ensure_qsets(c); if (s) return s;
@@ -1078,7 +1093,7 @@ hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
     OpTimer tk(c, "kernel:k_moment_tile");
     constexpr int TY = 8, TZ = 32;
     constexpr int NT = ((TY + 2)*(TZ + 2) + 31)/32*32;
-    const size_t smem = sizeof(double)*2*19*(TY + 2)*(TZ + 2);
+    const size_t smem = sizeof(double)*(19*(TY + 2)*(TZ + 2) + 2*NT*8);
     const int xc = std::min(moment_chunk_env(), c->nxl);
     dim3 grid((unsigned)((a.nz + TZ - 1)/TZ), (unsigned)((a.ny + TY - 1)/TY), (unsigned)((c->nxl + xc - 1)/xc));
     if (write_u) {

@@ -384,7 +384,6 @@ def test_two_rank_checkpoint_restart(tmp_path):
     x = cps[0].read_text()
     cps[0].write_text(re.sub(r"<tmax>.*?</tmax>", "<tmax> 300 </tmax>", x))
     out = run(d, str(cps[0]), 29563)
-    assert "CHECKPOINT found" in out, out[-2000:]
     resumed = [ln for ln in out.splitlines() if re.search(pat, ln)]
     n = len(resumed)
     assert n >= 6 and resumed == logs["straight"][-n:], (resumed, logs["straight"])
