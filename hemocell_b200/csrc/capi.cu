@@ -131,6 +131,15 @@ hcg_status refresh_nonfluid(hcg_ctx* c) {
   for (int64_t i = 0; i < c->P && !nf && useL; i++) nf = gh[i] != HCG_FLUID;
   for (int64_t i = 0; i < c->P && !nf && useR; i++) nf = gh[c->P + i] != HCG_FLUID;
   c->has_nonfluid = nf;
+  // moment-only lattice update (lattice.cu): every rank must take the same path, so the ranks agree here on whether the
+  // whole lattice is plain periodic fluid at tau = 1 (collective, like the flag exchange above)
+  int ok = (c->omega == 1.0 && c->dom.periodic[0] && c->dom.periodic[1] && c->dom.periodic[2] && !c->real_nonfluid && !nf &&
+            !c->has_velbc && !c->has_iobc) ? 1 : 0;
+  if (c->dom.n_ranks > 1) {
+    if (comm_up(c)) { hcg_status s = comm_allreduce_min_host(c, &ok); if (s) return s; }
+    else ok = 0;                                          // decided in hcg_comm_init
+  }
+  c->mo_ok = ok != 0;
   return HCG_OK;
 }
 
@@ -256,6 +265,7 @@ hcg_status hcg_create(const hcg_domain* d, hcg_ctx** out) {
   memset(c->bc_vel, 0, sizeof(c->bc_vel)); memset(c->body, 0, sizeof(c->body));
   c->f_limit = 1e300;
   c->cur = 0; c->u_valid = false; c->has_velbc = false; c->has_nonfluid = d->n_ranks > 1; c->rho = nullptr;
+  c->mo_ok = d->n_ranks == 1 && c->omega == 1.0 && d->periodic[0] && d->periodic[1] && d->periodic[2];
   c->np = c->ncells = c->cap_p = c->cap_c = 0;
   for (int k = 0; k < 3; k++) c->pos[k] = c->vel[k] = c->frc[k] = c->frep[k] = nullptr;
   memset(c->comp, 0, sizeof(c->comp)); c->comp_alloc = false;

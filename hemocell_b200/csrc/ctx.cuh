@@ -104,7 +104,8 @@ struct hcg_ctx {
   // moment-only update at tau = 1 (lattice.cu: k_moment_step; opt-in): second W / F buffers = the inputs of the last such step
   double* W2 = nullptr; double* F2 = nullptr;
   bool pops_stale = false;     // the populations lag behind W (materialised on demand by lat_ensure_pops)
-  int mo_mode = -1;            // -1 = follow HCG_MOMENT_ONLY, 0 = off, 1 = on (hcg_set_moment_only)
+  int mo_mode = -1;            // -1 = follow HCG_MOMENT_ONLY (default on), 0 = off, >= 1 = on (hcg_set_moment_only)
+  bool mo_ok = false;          // tau = 1 and the whole lattice - on every rank - is plain periodic fluid (agreed in refresh_nonfluid)
   uint8_t* flags;
   bool u_valid, has_velbc, has_nonfluid;
   bool has_iobc = false;       // Zou-He velocity / pressure nodes present (flags >= HCG_ZH_VEL_XN)

@@ -8,6 +8,7 @@
 #include <nccl.h>
 #include <cfloat>
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 #include <cstdio>
@@ -257,13 +258,14 @@ k_moment_step(const double* __restrict__ Win, const double* Fin, double* __restr
 // to the moment accumulators of the planes x + 1 / x / x - 1, which live in registers, so plane x - 1 is complete - and written
 // (new moments, node velocity, reset force: 96 B) - as soon as plane x has been evaluated.  Shared memory is double-buffered:
 // one __syncthreads per plane.  HBM traffic = 64 B read (+ halo re-reads served by L2) + 96 B written per lattice update.
-template <bool WRITE_U, int TY, int TZ>
-__global__ void __launch_bounds__(((TY + 2)*(TZ + 2) + 31)/32*32, 2)
+template <bool WRITE_U, int TY, int TZ, int MINB>
+__global__ void __launch_bounds__(((TY + 2)*(TZ + 2) + 31)/32*32, MINB)
 k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, double* __restrict__ Wout, double* __restrict__ Fout,
               double* __restrict__ U, LatArgs a, int xc) {
   constexpr int HY = TY + 2, HZ = TZ + 2, HN = HY*HZ;
   // shared memory: the 19 populations of the current plane [19][HN], then a two-deep ring of the (W, F) inputs of the planes
-  // ahead, one 64-byte slot per thread and stage [2][NT][8], filled by cp.async (no registers held while the loads fly)
+  // ahead, four 16-byte chunks per thread and stage [2][4][NT][2] (chunk-major: conflict-free), filled by cp.async (no registers
+  // held while the loads fly)
   extern __shared__ __align__(16) double sm_pop[];
   constexpr int NT = (HN + 31)/32*32;
   double* ring = sm_pop + 19*HN;
@@ -277,17 +279,17 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
   const int64_t col = (int64_t)yw*nz + zw;
   const int x_lo = 1 + (int)blockIdx.z*xc, x_hi = min(x_lo + xc - 1, a.nxl);
   if (x_lo > a.nxl) return;
-  const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(ring + (size_t)t*8);
-  constexpr uint32_t STAGE = NT*64;
+  const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(ring + (size_t)t*2);
+  constexpr uint32_t STAGE = NT*64, CHUNK = NT*16;
   auto fetch = [&](int lx) {                             // (W, F) of this thread's node on plane lx -> ring stage lx & 1
     if (halo_ok && lx <= x_hi + 1) {
       const int64_t n = (int64_t)lx*a.P + col;
       const uint32_t dst = slot0 + (uint32_t)(lx & 1)*STAGE;
       const double* w = Win + 4*n; const double* f = Fin + 4*n;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(w) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16), "l"(w + 2) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 32), "l"(f) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 48), "l"(f + 2) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + CHUNK), "l"(w + 2) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 2*CHUNK), "l"(f) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 3*CHUNK), "l"(f + 2) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -302,8 +304,8 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // plane lx has landed (the group of plane lx + 1 may still fly)
     double c0 = 0, c1 = 0, c2 = 0;
     if (halo_ok) {
-      const double2* sl = reinterpret_cast<const double2*>(ring + (size_t)(lx & 1)*NT*8 + (size_t)t*8);
-      const double2 wa = sl[0], wb = sl[1], fa = sl[2], fb = sl[3];
+      const double2* sl = reinterpret_cast<const double2*>(ring + (size_t)(lx & 1)*NT*8) + t;
+      const double2 wa = sl[0], wb = sl[NT], fa = sl[2*NT], fb = sl[3*NT];
       c0 = fa.x; c1 = fa.y; c2 = fb.x;
       double p[19];
       tau1_pops_fast(wa.x, wa.y, wb.x, wb.y, fa.x, fa.y, fb.x, p);
@@ -1060,16 +1062,14 @@ static hcg_status moments_rows(hcg_ctx* c, bool reset_force, int row0, int row1)
 // ---- moment-only update (k_moment_step): eligibility, the step, and materialising the populations on demand
 static int moment_only_env() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("HCG_MOMENT_ONLY"); on = e ? atoi(e) : 0; }
+  if (on < 0) { const char* e = getenv("HCG_MOMENT_ONLY"); on = e ? atoi(e) : 1; }    // default on; HCG_MOMENT_ONLY=0: stored populations
   return on;
 }
-// level 1 = single rank; level 2 = also slab-decomposed runs: the W face planes (and U on interpolation steps) go to the
-// neighbours' ghost planes through the send/recv exchange, whatever the transport of the population path is
+// eligible: tau = 1, every rank's lattice is plain periodic fluid (mo_ok), uniform driving force, and the raw moments of the
+// current state are at hand (the first step after any change of the populations runs collision + moments pass and leaves them)
 bool lat_moment_eligible(hcg_ctx* c) {
   const int level = c->mo_mode < 0 ? moment_only_env() : c->mo_mode;
-  return level > 0 && (c->dom.n_ranks == 1 || level >= 2) && tau1_enabled() && c->omega == 1.0 && c->dom.periodic[0] && c->dom.periodic[1] && c->dom.periodic[2]
-      && !c->has_nonfluid && !c->real_nonfluid && !c->has_velbc && !c->has_iobc && !c->F0
-      && c->W && c->w_valid;
+  return level > 0 && tau1_enabled() && c->mo_ok && !c->F0 && c->W && c->w_valid;
 }
 static int moment_kernel_env() {                          // HCG_MOMENT_KERNEL=simple: one thread per node, 19 neighbour loads (k_moment_step)
   const char* e = getenv("HCG_MOMENT_KERNEL");            // (read per step: lets a test compare the two kernels in one process)
@@ -1091,18 +1091,30 @@ hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
   LatArgs a = make_args(c);
   if (moment_kernel_env()) {
     OpTimer tk(c, "kernel:k_moment_tile");
-    constexpr int TY = 8, TZ = 32;
-    constexpr int NT = ((TY + 2)*(TZ + 2) + 31)/32*32;
-    const size_t smem = sizeof(double)*(19*(TY + 2)*(TZ + 2) + 2*NT*8);
     const int xc = std::min(moment_chunk_env(), c->nxl);
-    dim3 grid((unsigned)((a.nz + TZ - 1)/TZ), (unsigned)((a.ny + TY - 1)/TY), (unsigned)((c->nxl + xc - 1)/xc));
-    if (write_u) {
-      CUDA_TRY(c, cudaFuncSetAttribute(k_moment_tile<true, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_moment_tile<true, TY, TZ><<<grid, NT, smem, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, xc);
-    } else {
-      CUDA_TRY(c, cudaFuncSetAttribute(k_moment_tile<false, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_moment_tile<false, TY, TZ><<<grid, NT, smem, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, xc);
-    }
+    hcg_status st = HCG_OK;
+    auto launch = [&](auto ty, auto tz, auto minb) {
+      constexpr int TY = decltype(ty)::value, TZ = decltype(tz)::value, MINB = decltype(minb)::value;
+      constexpr int NT = ((TY + 2)*(TZ + 2) + 31)/32*32;
+      const size_t smem = sizeof(double)*(19*(TY + 2)*(TZ + 2) + 2*NT*8);
+      dim3 grid((unsigned)((a.nz + TZ - 1)/TZ), (unsigned)((a.ny + TY - 1)/TY), (unsigned)((c->nxl + xc - 1)/xc));
+      cudaError_t e;
+      if (write_u) {
+        e = cudaFuncSetAttribute(k_moment_tile<true, TY, TZ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) k_moment_tile<true, TY, TZ, MINB><<<grid, NT, smem, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, xc);
+      } else {
+        e = cudaFuncSetAttribute(k_moment_tile<false, TY, TZ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) k_moment_tile<false, TY, TZ, MINB><<<grid, NT, smem, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, xc);
+      }
+      if (e != cudaSuccess) st = hcg_fail(c, HCG_ERR_CUDA, std::string("k_moment_tile: ") + cudaGetErrorString(e));
+    };
+    const char* shape = getenv("HCG_MOMENT_TILE");        // experiment knob: tile shape / CTAs per SM
+    if (shape && !strcmp(shape, "4x32")) launch(std::integral_constant<int, 4>(), std::integral_constant<int, 32>(), std::integral_constant<int, 3>());
+    else if (shape && !strcmp(shape, "6x32")) launch(std::integral_constant<int, 6>(), std::integral_constant<int, 32>(), std::integral_constant<int, 2>());
+    else if (shape && !strcmp(shape, "4x64")) launch(std::integral_constant<int, 4>(), std::integral_constant<int, 64>(), std::integral_constant<int, 1>());
+    else if (shape && !strcmp(shape, "16x32")) launch(std::integral_constant<int, 16>(), std::integral_constant<int, 32>(), std::integral_constant<int, 1>());
+    else launch(std::integral_constant<int, 8>(), std::integral_constant<int, 32>(), std::integral_constant<int, 2>());
+    if (st) return st;
     KERNEL_CHECK(c);
   } else {
     OpTimer tk(c, "kernel:k_moment_step");
