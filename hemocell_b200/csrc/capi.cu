@@ -527,7 +527,7 @@ hcg_status hcg_celltype_add(hcg_ctx* c, const hcg_celltype* t, int32_t* ctype_ou
   if (!c || !t) return HCG_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
   if (c->types.size() >= HCG_MAX_TYPES) return hcg_fail(c, HCG_ERR_CAPACITY, "too many cell types");
-  if (t->model != HCG_MODEL_RBC_HIGHORDER && t->model != HCG_MODEL_PLT_SIMPLE) return hcg_fail(c, HCG_ERR_ARG, "unknown model");
+  if (t->model != HCG_MODEL_RBC_HIGHORDER && t->model != HCG_MODEL_PLT_SIMPLE && t->model != HCG_MODEL_HOST) return hcg_fail(c, HCG_ERR_ARG, "unknown model");
   const int V = t->n_vertices, T = t->n_triangles, E = t->n_edges, I = t->n_inner_edges;
   if (V < 4 || T < 4 || E < 6 || I < 0) return hcg_fail(c, HCG_ERR_ARG, "degenerate mesh");
   // ---- per-vertex gather tables
@@ -920,7 +920,17 @@ hcg_status hcg_op_collide_stream(hcg_ctx* c) { OP_PROLOGUE; if ((s = lat_collide
 hcg_status hcg_op_interpolate(hcg_ctx* c) {
   OP_PROLOGUE; if ((s = lat_moments(c, false, false))) return s; if ((s = ibm_interpolate(c))) return s; OP_EPILOGUE;
 }
-hcg_status hcg_op_sync(hcg_ctx* c) { OP_PROLOGUE; s = HCG_OK; (void)s; OP_EPILOGUE; }
+// syncEnvelopes as iterate() performs it after the interpolation (core/hemoCell.cpp:333-341): the holders of every shared cell
+// exchange the velocities (and alive flags) of the vertices they own; then, like the reference's envelope update, membership is
+// re-evaluated and whole cells migrate.  Collective over the ranks; a single-rank context has nothing to exchange.
+hcg_status hcg_op_sync(hcg_ctx* c) {
+  OP_PROLOGUE;
+  if (c->dom.n_ranks > 1) {
+    if ((s = multi_velocity_sync(c))) return s;
+    if ((s = multi_rebalance(c, false))) return s;
+  }
+  OP_EPILOGUE;
+}
 hcg_status hcg_op_advance(hcg_ctx* c) { OP_PROLOGUE; if ((s = ibm_advance(c))) return s; OP_EPILOGUE; }
 hcg_status hcg_op_mechanics(hcg_ctx* c, int32_t forced, int32_t components) {
   OP_PROLOGUE; if ((s = do_mechanics(c, forced != 0, components != 0))) return s; OP_EPILOGUE;

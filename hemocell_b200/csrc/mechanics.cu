@@ -344,6 +344,7 @@ hcg_status mech_apply(hcg_ctx* c, int ctype, bool components) {
     }
     c->comp_alloc = true;
   }
+  if (th.d.model == HCG_MODEL_HOST) return HCG_OK;        // the caller's own model: forces arrive through hcg_cells_upload
   MechArgs a;
   a.t = th.d; a.first_cell = th.first_cell; a.first_particle = th.first_particle;
   a.alive = c->cell_alive;

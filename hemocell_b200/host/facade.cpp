@@ -355,6 +355,7 @@ struct CellTypeImpl {
   int device_ctype = -1;
   int device_generation = -1;                 // GpuLattice::generation the type was uploaded to
   int64_t n_cells_loaded = 0;
+  bool host_model = false;                    // user subclass of CellMechanics without a device kernel: ParticleMechanics runs on the host
 };
 
 static host::MaterialModel read_material(Config& m, int constructType) {
@@ -493,7 +494,62 @@ void HemoCellFields::interpolateFluidVelocity() { ck(ctx(), hcg_op_interpolate(c
 void HemoCellFields::spreadParticleForce() { ck(ctx(), hcg_op_spread(ctx()), "spreadParticleForce"); }
 void HemoCellFields::applyRepulsionForce() { ck(ctx(), hcg_op_repulsion(ctx()), "applyRepulsionForce"); }
 void HemoCellFields::applyBoundaryRepulsionForce() { ck(ctx(), hcg_op_wall_repulsion(ctx()), "applyBoundaryRepulsionForce"); }
-void HemoCellFields::applyConstitutiveModel(bool forced) { ck(ctx(), hcg_op_mechanics(ctx(), forced ? 1 : 0, separateForces ? 1 : 0), "applyConstitutiveModel"); }
+// CellMechanics::ParticleMechanics of the cell types whose model has no device kernel (a user subclass, mechanics/cellMechanics.h:45):
+// the reference's call sequence of HemoCellParticleField::applyConstitutiveModel (core/hemoCellParticleField.cpp:633-675) on host
+// copies of the particles - download positions / velocities, zero the type's forces, call the model, upload the forces.  Slow path
+// by construction (two PCIe round trips per material step); the built-in models never take it.
+static void host_constitutive_model(HemoCellFields& cf, bool forced, plint iter) {
+  bool any = false;
+  for (auto* f : cf.cellFields) any = any || (f->impl->host_model && (forced || iter % f->timescale == 0));
+  if (!any) return;
+  hcg_ctx* c = cf.ctx();
+  int64_t nc = 0, np = 0;
+  ck(c, hcg_cells_capacity(c, &nc, &np), "hcg_cells_capacity");
+  if (np == 0) return;
+  std::vector<double> pos(3*np), vel(3*np), frc(3*np), frep(3*np);
+  ck(c, hcg_cells_download(c, HCG_P_POS, pos.data()), "download"); ck(c, hcg_cells_download(c, HCG_P_VEL, vel.data()), "download");
+  ck(c, hcg_cells_download(c, HCG_P_FORCE, frc.data()), "download"); ck(c, hcg_cells_download(c, HCG_P_FREP, frep.data()), "download");
+  std::vector<int64_t> ids(nc); std::vector<int32_t> types(nc); std::vector<uint8_t> alive(nc);
+  ck(c, hcg_cells_info(c, ids.data(), types.data(), alive.data()), "hcg_cells_info");
+  for (auto* f : cf.cellFields) {
+    if (!f->impl->host_model || !(forced || iter % f->timescale == 0)) continue;
+    std::vector<HemoCellParticle> store;
+    std::vector<int64_t> first;                           // first particle (device order) of each cell in `store`
+    int64_t p = 0;
+    for (int64_t k = 0; k < nc; k++) {
+      const int V = cf.cellFields[types[k]]->numVertex;
+      if (types[k] == f->impl->device_ctype && alive[k] && ids[k] >= 0) {
+        first.push_back(p);
+        for (int v = 0; v < V; v++) {
+          HemoCellParticle q;
+          for (int d = 0; d < 3; d++) { q.sv.position[d] = pos[3*(p+v)+d]; q.sv.v[d] = vel[3*(p+v)+d]; q.sv.force[d] = 0.0; q.sv.force_repulsion[d] = frep[3*(p+v)+d]; }
+          q.sv.cellId = ids[k]; q.sv.vertexId = (uint16_t)v; q.sv.restime = 0; q.sv.celltype = (unsigned char)types[k];
+          store.push_back(q);
+        }
+      }
+      p += V;
+    }
+    const int V = f->numVertex;
+    std::map<int, std::vector<HemoCellParticle*>> ppc; std::map<int, bool> lpc;
+    for (size_t k = 0; k < first.size(); k++) {
+      auto& vec = ppc[(int)store[k*V].sv.cellId];
+      vec.resize(V);
+      for (int v = 0; v < V; v++) {
+        HemoCellParticle* q = &store[k*V + v];
+        q->force_volume = q->force_bending = q->force_link = q->force_area = q->force_visc = q->force_inner_link = &q->sv.force;
+        vec[v] = q;
+      }
+      lpc[(int)store[k*V].sv.cellId] = true;
+    }
+    f->mechanics->ParticleMechanics(ppc, lpc, f->ctype);
+    for (size_t k = 0; k < first.size(); k++) for (int v = 0; v < V; v++) for (int d = 0; d < 3; d++) frc[3*(first[k]+v)+d] = store[k*V + v].sv.force[d];
+  }
+  ck(c, hcg_cells_upload(c, HCG_P_FORCE, frc.data()), "upload");
+}
+void HemoCellFields::applyConstitutiveModel(bool forced) {
+  ck(ctx(), hcg_op_mechanics(ctx(), forced ? 1 : 0, separateForces ? 1 : 0), "applyConstitutiveModel");
+  host_constitutive_model(*this, forced, hemocell.iter);
+}
 void HemoCellFields::syncEnvelopes() { ck(ctx(), hcg_op_sync(ctx()), "syncEnvelopes"); }
 void HemoCellFields::getParticles(vector<HemoCellParticle>& particles) {
   particles.clear();
@@ -552,8 +608,12 @@ void HemoCell::initializeCellfield() {
   cellfields = new HemoCellFields(*lattice, (*cfg)["domain"]["particleEnvelope"].read<int>(), *this);
 }
 void HemoCell::registerCellType(HemoCellField* f) {
-  if (f->mechanics->deviceModel() < 0) fatal("(HemoCell) (AddCellType) " + f->name + ": this mechanics class has no device kernel (deviceModel() < 0)");
-  f->impl->tables.c.model = f->mechanics->deviceModel();
+  if (f->mechanics->deviceModel() < 0) {
+    // a user subclass of CellMechanics: its ParticleMechanics(map<...>) is honoured on host copies of the particles
+    hlog << "(HemoCell) (AddCellType) " << f->name << ": mechanics class without a device kernel, ParticleMechanics runs on the host (slow path)" << endl;
+    f->impl->host_model = true;
+    f->impl->tables.c.model = HCG_MODEL_HOST;
+  } else f->impl->tables.c.model = f->mechanics->deviceModel();
 }
 // cell types go to the device when it is first needed (the periodicity may be toggled until then,
 // which re-creates the context: hemocell.setSystemPeriodicity comes after addCellType in the case files)
@@ -720,6 +780,7 @@ void HemoCell::iterate() {
   if (!sanityCheckDone) sanityCheck();
   hcg_ctx* c = ctx();
   ck(c, hcg_iterate(c, 1), "hcg_iterate");
+  host_constitutive_model(*cellfields, false, iter);          // user models without a device kernel (last operator of iterate(), core/hemoCell.cpp:362)
   if (preInlet) preInlet->iterate();                          // asynchronous, on the pre-inlet context's own stream (or GPU)
   iter++;
 }

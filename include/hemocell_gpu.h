@@ -46,7 +46,9 @@ enum { HCG_FLUID = 0, HCG_BOUNCEBACK = 1, HCG_VEL_XN = 2, HCG_VEL_XP = 3, HCG_VE
         * (examples/pipeflow_with_preinlet/pipeflow_with_preinlet.cpp:125-133) */
        HCG_ZH_VEL_XN = 8, HCG_ZH_VEL_XP = 9, HCG_ZH_VEL_YN = 10, HCG_ZH_VEL_YP = 11, HCG_ZH_VEL_ZN = 12, HCG_ZH_VEL_ZP = 13,
        HCG_ZH_PRES_XN = 14, HCG_ZH_PRES_XP = 15, HCG_ZH_PRES_YN = 16, HCG_ZH_PRES_YP = 17, HCG_ZH_PRES_ZN = 18, HCG_ZH_PRES_ZP = 19 };
-enum { HCG_MODEL_RBC_HIGHORDER = 0, HCG_MODEL_PLT_SIMPLE = 1 };
+enum { HCG_MODEL_RBC_HIGHORDER = 0, HCG_MODEL_PLT_SIMPLE = 1,
+       HCG_MODEL_HOST = 2 /* no device kernel: the caller evaluates the constitutive model itself (a user subclass of
+                             CellMechanics, mechanics/cellMechanics.h:45) and uploads HCG_P_FORCE at the material cadence */ };
 /* lattice fields */
 enum { HCG_LAT_POP = 0, HCG_LAT_FORCE = 1, HCG_LAT_VELOCITY = 2, HCG_LAT_DENSITY = 3,
        HCG_LAT_PINEQ = 4 /* off-equilibrium momentum flux, 6 components xx xy xz yy yz zz (output path:
@@ -250,7 +252,8 @@ hcg_status hcg_op_wall_repulsion(hcg_ctx*);  /* HemoCellFields::applyBoundaryRep
 hcg_status hcg_op_spread(hcg_ctx*);          /* HemoCellFields::spreadParticleForce          */
 hcg_status hcg_op_collide_stream(hcg_ctx*);  /* lattice->collideAndStream()                  */
 hcg_status hcg_op_interpolate(hcg_ctx*);     /* HemoCellFields::interpolateFluidVelocity     */
-hcg_status hcg_op_sync(hcg_ctx*);            /* HemoCellFields::syncEnvelopes (multi-GPU)    */
+hcg_status hcg_op_sync(hcg_ctx*);            /* HemoCellFields::syncEnvelopes: velocity swap of the shared cells + whole-cell
+                                                migration (collective over the ranks; nothing to do on one rank) */
 hcg_status hcg_op_advance(hcg_ctx*);         /* HemoCellFields::advanceParticles             */
 hcg_status hcg_op_mechanics(hcg_ctx*, int32_t forced, int32_t components); /* applyConstitutiveModel */
 hcg_status hcg_op_zero_force(hcg_ctx*);      /* setExternalVector(lattice, bbox, 0 | body)   */

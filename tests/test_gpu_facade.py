@@ -364,3 +364,35 @@ def test_checkpoint_restart_reproduces_uninterrupted_run(tmp_path):
     resumed = np.loadtxt(d / "stretch.log").reshape(-1, 8)
     assert [int(v) for v in resumed[:, 0]] == [100, 200, 300, 400] == [int(v) for v in logs["straight"][:, 0]]
     U.assert_close(resumed[:, 1:], logs["straight"][:, 1:], "stretch.log of the restarted run vs the uninterrupted one", rtol=1e-6, floor=1e-9)
+
+
+def test_user_defined_cell_mechanics_runs_through_particle_mechanics(tmp_path):
+    """the plug-in interface itself (mechanics/cellMechanics.h:45): examples/user_model defines its own CellMechanics subclass (a
+    link-only membrane, no device kernel) and passes it to addCellType<>; the facade calls its ParticleMechanics(map<...>) on host
+    copies of the particles at the material cadence.  Checked against the oracle running the RBC model with every stiffness but
+    kLink set to zero: positions and forces of all 642 vertices after 20 / 40 / 60 iterate() steps in shear flow."""
+    exe = os.path.join(ROOT, "examples", "user_model", "user_model")
+    assert os.path.exists(exe), "examples/user_model/user_model is not built (python __graft_entry__.py)"
+    rows = [(9.5, 9.5, 4.5, 70, 20, 0)]
+    F.write_shear_case(tmp_path, tmax=60, tmeas=20, rows=rows, material_every=2, particle_every=1, shearrate=2000.0)
+    r = subprocess.run([exe, "config.xml"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "ParticleMechanics runs on the host" in r.stdout
+    got = np.loadtxt(tmp_path / "user_model.log").reshape(3, 642, 8)
+    nx, ny, nz = 40, 40, 20
+    par = M.Parameters(dx=0.5e-6, dt=0.5e-7)
+    vh = (nz - 1) * 2000.0 * par.dt * 0.5
+    bc = np.zeros((6, 3)); bc[4] = (vh, 0, 0); bc[5] = (-vh, 0, 0)
+    fl = U.couette_flags(nx, ny, nz).reshape(-1)
+    dom = O.make_domain(nx, ny, nz, (1, 1, 0), par.tau, bc)
+    ct = O.rbc_celltype(par, dict(M.RBC_MATERIAL, kBend=0.0, kVolume=0.0, kArea=0.0))
+    cells, ids = M.place_cells(ct.verts, np.array(rows, dtype=float), par.dx, (nx, ny, nz), fl)
+    sim = O.OracleSim(dom, fl, par.f_limit)
+    sim.add_celltype(ct, 2); sim.add_cells(0, cells, ids)
+    for k in range(3):
+        for _ in range(20):
+            sim.iterate()
+        assert int(got[k, 0, 0]) == sim.iter and np.array_equal(got[k, :, 1], np.arange(642))
+        U.assert_close(got[k, :, 2:5], sim.pos, f"positions at {sim.iter} (user model on the host path)", rtol=1e-11)
+        U.assert_close(got[k, :, 5:8], sim.pforce, f"forces at {sim.iter} (user model on the host path)", rtol=1e-9, floor=1e-11)
+    assert np.abs(got[-1, :, 5:8]).max() > 0
