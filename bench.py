@@ -434,64 +434,296 @@ def run_cuda(args):
     return line
 
 
-def run_cube(args):
-    """extra line (not the default): examples/cube on one GPU.  A 10^6-node lattice is launch- and latency-bound on a
-    B200, so this line says little about the kernels; it is here because BASELINE.json lists the configuration."""
-    from hemocell_b200 import lib as H
-    par = H.parameters(DX, -1.0)
-    n, fl, bc, rbc_rows, plt_rows = cube_setup(H, par)
+# ----------------------------------------------------------------------------- BASELINE configs 2 - 4 (strong scaling over x-slabs)
+def read_pos_multi(path, counts):
+    """a .pos file that holds several cell types one after the other (examples/pipeflow/initial_states/*/cells.pos: the
+    counts on the first lines, then the rows of each type)"""
+    tok = open(path).read().split()
+    n = [int(tok[k]) for k in range(counts)]
+    vals = np.array(tok[counts:counts + 6 * sum(n)], dtype=np.float64).reshape(-1, 6)
+    out, at = [], 0
+    for k in n:
+        out.append(vals[at:at + k]); at += k
+    return out
+
+
+def case_spec(name, H):
+    """domain, boundary nodes, driving force, cells and cadences of a BASELINE.json configuration, from the reference's case file"""
+    fx = os.path.join(ROOT, "fixtures")
+    if name == "pipeflow":
+        # examples/pipeflow/pipeflow.cpp:51-146 on the D = 64 um, L = 128 um vessel of initial_states/D64_Ht21 (SURVEY 8d C3):
+        # bounce-back outside the radius, x periodic, body force 8 nu (u_max / 2) / R^2 at Re 0.5, dt = 1e-7 (tau 1.82)
+        par = H.parameters(DX, 1e-7)
+        nx, ny, nz, R = 256, 130, 130, 64.0
+        yy, zz = np.meshgrid(np.arange(ny), np.arange(nz), indexing="ij")
+        wall = ((yy - 64.5) ** 2 + (zz - 64.5) ** 2) >= R * R
+        fl = np.zeros((nx, ny, nz), dtype=np.uint8); fl[:, wall] = H.BOUNCEBACK
+        u_max = 0.5 * par["nu_lbm"] / (2 * R)
+        body = (8 * par["nu_lbm"] * (u_max * 0.5) / R / R, 0.0, 0.0)
+        rbc_rows, plt_rows = read_pos_multi(os.path.join(fx, "pipeflow_D64_Ht21_cells.pos"), 2)
+        return dict(label="examples/pipeflow, D64_Ht21 vessel", par=par, dims=(nx, ny, nz), periodic=(1, 0, 0), flags=fl, bc=None, body=body,
+                    cells=[("RBC", rbc_rows, 0.0), ("PLT", plt_rows, 0.0)], material=20, velocity=5, rep=None,
+                    pos=["pipeflow_D64_Ht21_cells.pos"])
+    if name == "stenosis":
+        # cases/stenosis/stenosis.cpp:37-74, 112-230: 600 x 348 x 160, bounce-back y / z faces + the analytic stenosis shape,
+        # x periodic, body force dpdz_lbm, nu = 3e-6, dt = 1e-8 (tau 0.86), Ht20 cells, minimum wall distance 1 um
+        par = H.parameters(DX, 1e-8, 3.0e-6)
+        nx, ny, nz = 600, 348, 160
+        rc, ytop, xbl = 15, 316, 100
+        xtr, xcirc, ycirc = xbl + 2 * rc, xbl + rc, ytop - rc
+        ix, iy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        shape = ((ix - xcirc) ** 2 + (iy - ycirc) ** 2 <= rc * rc) | ((ix <= xtr) & (ix >= xbl) & (iy <= ycirc)) | \
+                ((ix <= (iy - 514.16683048) / -1.60677134525) & (ix >= 127.73502714) & (iy <= 308.92584909))
+        fl = np.zeros((nx, ny, nz), dtype=np.uint8)
+        fl[shape] = H.BOUNCEBACK
+        fl[:, :, 0] = H.BOUNCEBACK; fl[:, :, nz - 1] = H.BOUNCEBACK; fl[:, 0, :] = H.BOUNCEBACK; fl[:, ny - 1, :] = H.BOUNCEBACK
+        flow_q = 1800.0 * 130e-6 * 80e-6 * 80e-6 / 6
+        dpdz = flow_q * 12 * 3.0e-3 / (80e-6 ** 3 * 130e-6)
+        body = (dpdz * DX * DX * par["dt"] ** 2 / par["dm"], 0.0, 0.0)
+        return dict(label="cases/stenosis, Ht20", par=par, dims=(nx, ny, nz), periodic=(1, 0, 0), flags=fl, bc=None, body=body,
+                    cells=[("RBC", H.read_pos(os.path.join(fx, "stenosis_Ht20_RBC.pos")), 1.0), ("PLT", H.read_pos(os.path.join(fx, "stenosis_Ht20_PLT.pos")), 0.0)],
+                    material=10, velocity=10, rep=None, pos=["stenosis_Ht20_RBC.pos", "stenosis_Ht20_PLT.pos"])
+    if name == "cube":
+        # examples/cube/cube.cpp:48-133: 100^3, x periodic, bounce-back y planes, moving z walls, tau = 1; the reference seeds it
+        # with the irreproducible tools/packCells, here a seeded lattice packing at ~30 % hematocrit (RBC + PLT)
+        par = H.parameters(DX, -1.0)
+        n, fl, bc, rbc_rows, plt_rows = cube_setup(H, par)
+        return dict(label="examples/cube, seeded packing", par=par, dims=(n, n, n), periodic=(1, 0, 0), flags=fl, bc=bc, body=(0.0, 0.0, 0.0),
+                    cells=[("RBC", rbc_rows, 0.0), ("PLT", plt_rows, 0.0)], material=20, velocity=5, rep=None, pos=[])
+    raise ValueError(name)
+
+
+def case_parity_check(args, dist, H, spec):
+    """a small problem with the boundary kinds, relaxation time, cell types and cadences of the case (and repulsion when the case
+    has it), cut into the same number of slabs, 20 iterate() steps against the CPU oracle on rank 0"""
+    rank, world = args.rank, args.world
+    par = spec["par"]
+    nxl, ny, nz, steps = 32, 30, 30, 20
+    nx = nxl * world
+    fl = np.zeros((nx, ny, nz), dtype=np.uint8)
+    bc = np.zeros((6, 3))
+    if spec["bc"] is not None:                            # cube-like: bounce-back y planes, moving z walls
+        fl[:, :, 0] = H.VEL_ZN; fl[:, :, nz - 1] = H.VEL_ZP; fl[:, 0, :] = H.BOUNCEBACK; fl[:, ny - 1, :] = H.BOUNCEBACK
+        bc[4] = (0.02, 0, 0); bc[5] = (-0.02, 0, 0)
+    else:                                                 # vessel-like: bounce-back outside a cylinder along x
+        yy, zz = np.meshgrid(np.arange(ny), np.arange(nz), indexing="ij")
+        fl[:, ((yy - 14.5) ** 2 + (zz - 14.5) ** 2) >= 13.5 ** 2] = H.BOUNCEBACK
+    um = DX / 1e-6
     rbc = H.HostCellType(H.MODEL_RBC, H.RBC_FROM_SPHERE, par, H.RBC_MATERIAL)
     plt = H.HostCellType(H.MODEL_PLT, H.ELLIPSOID_FROM_SPHERE, par, H.PLT_MATERIAL, H.PLT_INNER_EDGES)
-    ctx = H.Context(n, n, n, (1, 0, 0), par["tau"], device=args.local_rank)
-    ctx.set_flags(fl.reshape(-1))
+    rrows = np.array([(((k * nxl) % nx + (0.3 if k else 0.0)) * um, 14.5 * um, 14.5 * um, 0.0, 90.0, 15.0 * k) for k in range(world)])
+    prows = np.array([(16.0 * um, 14.5 * um, 14.5 * um, 30.0, 0.0, 0.0)])
+    fl_big = np.concatenate([fl, fl[:nxl]], axis=0)       # place on a domain shifted by half a slab: the face cells stay whole
+    def place(ct, rows, id0):
+        sh = rows.copy(); sh[:, 0] += 0.5 * nxl * um
+        cells, ids = ct.place(sh, DX, (nx + nxl, ny, nz), fl_big.reshape(-1), 0.0, id0)
+        return cells - np.array([0.5 * nxl, 0.0, 0.0]), ids
+    rc, rid = place(rbc, rrows, 0); pc, pid = place(plt, prows, len(rrows))
+    body = tuple(20.0 * b for b in spec["body"]) if any(spec["body"]) else (0.0, 0.0, 0.0)
+    ctx = H.Context(nx, ny, nz, spec["periodic"], par["tau"], device=args.local_rank, rank=rank, n_ranks=world)
+    if world > 1:
+        import torch
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idbuf.copy_(torch.frombuffer(bytearray(H.Context.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        ctx.comm_init(bytes(idbuf.cpu().numpy().tobytes()))
+    ctx.set_flags(np.ascontiguousarray(fl[ctx.x0:ctx.x0 + ctx.nxl]))
     for o in range(6):
         ctx.set_bc_velocity(o, bc[o])
-    ctx.set_force_limit(par["f_limit"])
-    t0_, t1_ = rbc.add_to(ctx), plt.add_to(ctx)
-    rc, rid = rbc.place(rbc_rows, DX, (n, n, n), fl.reshape(-1))
-    pc, pid = plt.place(plt_rows, DX, (n, n, n), fl.reshape(-1), cell_id0=len(rbc_rows))
-    ctx.add_cells(t0_, rc, rid); ctx.add_cells(t1_, pc, pid)
-    ctx.set_timescales(5, 1, 1); ctx.set_material_timescale(t0_, 20); ctx.set_material_timescale(t1_, 20)
+    ctx.set_body_force(body); ctx.set_force_limit(par["f_limit"])
+    t0, t1 = rbc.add_to(ctx), plt.add_to(ctx)
+    if world > 1:
+        ctx.set_exchange(4.0, 5, 1.0)
+    ctx.add_cells(t0, rc, rid); ctx.add_cells(t1, pc, pid)
+    vel = min(spec["velocity"], 5)
+    ctx.set_timescales(vel, vel, vel); ctx.set_material_timescale(t0, vel); ctx.set_material_timescale(t1, vel)
+    if spec["rep"]:
+        ctx.set_repulsion(True, spec["rep"]["k"], spec["rep"]["cut"]); ctx.set_wall_repulsion(True, spec["rep"]["k"], spec["rep"]["cut"])
+    ctx.iterate(steps)
+    pop = ctx.lattice_download(H.LAT_POP).reshape(19, ctx.nxl, ny, nz)
+    cid, ctp, alive = ctx.cells_info()
+    pos = ctx.cells_download(H.P_POS)
+    mine, at = {}, 0
+    for c, tp, al in zip(cid, ctp, alive):
+        V = rbc.V if tp == t0 else plt.V
+        if c >= 0 and al:
+            mine[int(c)] = pos.reshape(-1, 3)[at:at + V].copy()
+        at += V
+    x0 = ctx.x0
+    ctx.close()
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((x0, pop, mine), gathered, dst=0)
+    else:
+        gathered = [(x0, pop, mine)]
+    if rank != 0:
+        return None
+    import oracle as O
+    from oracle import mesh as M
+    opar = M.Parameters(DX, par["dt"] if spec["par"]["tau"] != 1.0 else -1.0, nu_p=par.get("nu_p", 1.1e-6))
+    ort, opt = O.rbc_celltype(opar), O.plt_celltype(opar)
+    dom = O.make_domain(nx, ny, nz, spec["periodic"], opar.tau, bc)
+    sim = O.OracleSim(dom, fl.reshape(-1), opar.f_limit, body)
+    sim.vel_timescale = vel
+    sim.add_celltype(ort, vel); sim.add_celltype(opt, vel)
+    sim.add_cells(0, rc, rid); sim.add_cells(1, pc, pid)
+    if spec["rep"]:
+        sim.rep_enabled = sim.wall_enabled = True; sim.rep_timescale = sim.wall_timescale = vel
+        sim.rep_k = sim.wall_k = spec["rep"]["k"]; sim.rep_cutoff = sim.wall_cutoff = spec["rep"]["cut"]
+    for _ in range(steps):
+        sim.iterate()
+    ref_pop = sim.pop.reshape(19, nx, ny, nz)
+    off = sim._offsets()
+    scale = float(np.abs(ref_pop).max())
+    e_pop, e_pos, seen = 0.0, 0.0, set()
+    for gx0, gp, gm in gathered:
+        e_pop = max(e_pop, float(np.abs(gp - ref_pop[:, gx0:gx0 + gp.shape[1]]).max()) / scale)
+        for c, pp in gm.items():
+            k = int(np.where(sim.cell_id == c)[0][0])
+            rp = sim.pos[off[k]:off[k + 1]]
+            e_pos = max(e_pos, float(np.abs(pp - rp).max()) / float(np.abs(rp).max())); seen.add(c)
+    want = set(int(i) for i in list(rid) + list(pid))
+    ok = e_pop <= 1e-10 and e_pos <= 1e-10 and seen == want
+    return {"max_rel": max(e_pop, e_pos), "max_rel_populations": e_pop, "max_rel_positions": e_pos, "tolerance": 1e-10, "ok": bool(ok),
+            "against": "CPU oracle (oracle/hemo_oracle.c), rank 0", "steps": steps, "lattice": [nx, ny, nz], "slabs": world,
+            "cells": len(want), "every_cell_found": seen == want,
+            "setup": "reduced problem with the case's boundary kinds, tau, cell types, cadences" + (" and both repulsions" if spec["rep"] else "")}
+
+
+def run_case(args):
+    """BASELINE.json configs[1..3] (examples/cube, examples/pipeflow, cases/stenosis): the whole domain of the case cut into
+    x-slabs over the N ranks (strong scaling), same measurements as the main line"""
+    import hashlib
+    rank, world = args.rank, args.world
+    from hemocell_b200 import lib as H
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(args.local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", args.local_rank))
+    spec = case_spec(args.workload, H)
+    par = spec["par"]
+    if args.repulsion:
+        # HemoCell::setRepulsion / enableBoundaryParticles with the constants of examples/pipeflow/config.xml (kRep 2e-22, cut-off 0.7 um)
+        spec["rep"] = dict(k=2e-22 / par["df"], cut=0.7e-6 / DX)
+    pcheck = None if args.no_parity_check else case_parity_check(args, dist, H, spec)
+    nx, ny, nz = spec["dims"]
+    fl = spec["flags"]
+    ctx = H.Context(nx, ny, nz, spec["periodic"], par["tau"], device=args.local_rank, rank=rank, n_ranks=world)
+    if world > 1:
+        import torch
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idbuf.copy_(torch.frombuffer(bytearray(H.Context.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        ctx.comm_init(bytes(idbuf.cpu().numpy().tobytes()))
+    ctx.set_flags(np.ascontiguousarray(fl[ctx.x0:ctx.x0 + ctx.nxl]))
+    if spec["bc"] is not None:
+        for o in range(6):
+            ctx.set_bc_velocity(o, spec["bc"][o])
+    ctx.set_body_force(spec["body"]); ctx.set_force_limit(par["f_limit"])
+    types, n_cells, n_lsp, id0 = [], {}, 0, 0
+    if world > 1:
+        ctx.set_exchange(4.0, 20, 0.3)
+    for cname, rows, min_dist in spec["cells"]:
+        ct = (H.HostCellType(H.MODEL_RBC, H.RBC_FROM_SPHERE, par, H.RBC_MATERIAL) if cname == "RBC" else
+              H.HostCellType(H.MODEL_PLT, H.ELLIPSOID_FROM_SPHERE, par, H.PLT_MATERIAL, H.PLT_INNER_EDGES))
+        t = ct.add_to(ctx)
+        cells, ids = ct.place(rows, DX, (nx, ny, nz), fl.reshape(-1), min_dist, id0)
+        id0 += len(rows)
+        ctx.add_cells(t, cells, ids)
+        ctx.set_material_timescale(t, spec["material"])
+        types.append(ct); n_cells[cname] = len(ids); n_lsp += len(ids) * ct.V
+    ctx.set_timescales(spec["velocity"], spec["material"], spec["material"])
+    if spec["rep"]:
+        ctx.set_repulsion(True, spec["rep"]["k"], spec["rep"]["cut"]); ctx.set_wall_repulsion(True, spec["rep"]["k"], spec["rep"]["cut"])
+    nodes = nx * ny * nz
+    cells_total = sum(n_cells.values())
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+        tt = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     ctx.iterate(args.warmup)
     launches0 = ctx.launch_count()
     ctx.timers_enable(True); ctx.timers_reset()
-    sampler = ClockSampler(args.local_rank)
-    ctx.synchronize(); t0 = time.time()
+    sampler = ClockSampler(args.local_rank) if rank == 0 else None
+    barrier(); t0 = time.time()
     ms = ctx.iterate_timed(args.steps)
-    ctx.synchronize(); t1 = time.time()
-    clocks = sampler.stop(t0, t1)
+    barrier(); t1 = time.time()
+    ms = max_over_ranks(ms)
+    clocks = sampler.stop(t0, t1) if sampler else None
     launches = ctx.launch_count() - launches0
     timers = ctx.timers(); ctx.timers_enable(False)
-    ncell = ctx.count()[0]
+    # end-to-end: the loop of the case file through the C ABI with host buffers (see run_cuda)
     npart = ctx.capacity()[1]
-    host = pinned_empty(3 * npart); out_pos = pinned_empty(3 * npart)
-    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), host.ctypes.data_as(H.c_dp))
-    ctx.synchronize(); te0 = time.time()
-    ctx.cells_upload(H.P_POS, host)
-    for _ in range(args.steps):
-        ctx.iterate(1); ctx.count()
+    state_host = pinned_empty(max(3 * npart, 1)); out_pos = pinned_empty(max(3 * npart, 1)); out_frc = pinned_empty(max(3 * npart, 1))
+    counts = pinned_empty(2 * args.steps)
+    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), state_host.ctypes.data_as(H.c_dp))
+    barrier(); te0 = time.time()
+    ctx.cells_upload(H.P_POS, state_host[:3 * npart])
+    for k in range(args.steps):
+        ctx.iterate_async(1)
+        ctx.set_body_force(spec["body"])
+        ctx.count_async(counts.ctypes.data + 16 * k)
+    ctx.synchronize()
     ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), out_pos.ctypes.data_as(H.c_dp))
-    ctx.synchronize(); e2e_ms = (time.time() - te0) * 1e3
-    nodes = n ** 3
+    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_FORCE), out_frc.ctypes.data_as(H.c_dp))
+    barrier()
+    e2e_ms = max_over_ranks((time.time() - te0) * 1e3)
+    alive = int(counts.view(np.int64)[2 * (args.steps - 1)])
+    if dist is not None:
+        import torch
+        tt = torch.tensor([alive], dtype=torch.int64, device="cuda"); dist.all_reduce(tt); alive = int(tt.item())
+    nodes_local = ctx.nxl * ny * nz
+    if rank != 0:
+        ctx.close()
+        return None
     peak, peak_src = measured_peak()
-    gen = timers.get("kernel:k_collide_stream", (0.0, 0)); t1k = timers.get("kernel:k_collide_tau1", (0.0, 0))
-    k_ms = (gen[0] + t1k[0]) / max(gen[1] + t1k[1], 1)
-    bytes_lu = (B_LU * gen[1] + B_LU_TAU1 * t1k[1]) / max(gen[1] + t1k[1], 1)
-    ach = bytes_lu * nodes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
-    line = {"metric": METRIC, "value": nodes * args.steps / (ms * 1e-3) / 1e6, "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "cell_steps_per_s": ncell * args.steps / (ms * 1e-3),
-            "config": {"workload": f"examples/cube: {n}^3 D3Q19 fp64, x periodic, bounce-back y planes, moving z walls, tau=1, "
-                                   f"{len(rid)} RBC + {len(pid)} PLT (seeded packing), material every 20, velocity every 5",
-                       "lattice": [n, n, n], "cells": int(ncell), "lsp": int(npart), "velocity_cadence": 5, "material_cadence": 20,
-                       "l2": "the 0.3 GB of populations exceed the 126 MB L2; no flush"},
-            "roofline": {"bound": "hbm", "kernel": "k_collide_stream / k_collide_tau1 (mix of the launches timed)", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": None, "peak_source": peak_src,
-                         "bytes_per_lu": bytes_lu, "launch_ms": k_ms, "launches_timed": gen[1] + t1k[1]},
-            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()},
-            "e2e": {"value": nodes * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 8 * 3 * npart / args.steps,
-                    "d2h_bytes_per_step": 8 * 3 * npart / args.steps + 16, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches, "clocks": clocks}
+    lat = {k[len("kernel:"):]: v for k, v in timers.items() if k.startswith("kernel:") and k[len("kernel:"):] in KERNEL_B_LU}
+    lat_ms = sum(v[0] for v in lat.values()) / args.steps
+    lat_ach = B_LU * nodes_local / (lat_ms * 1e-3) / 1e9 if lat_ms > 0 else None
+    kernels = {}
+    for kname, (kms, calls) in lat.items():
+        if calls:
+            b = B_MOM_TAU1 if (kname == "k_moments" and "k_collide_tau1" in lat) else KERNEL_B_LU[kname]
+            ach = b * nodes_local / (kms / calls * 1e-3) / 1e9
+            kernels[kname] = {"bytes_per_lu": b, "launch_ms": kms / calls, "launches_timed": calls, "achieved": ach, "frac": ach / peak}
+    b_step = B_LU + (264.0 + 72.0 + 216.0 / spec["velocity"]) * n_lsp / nodes
+    step_ach = b_step * nodes_local / (ms / args.steps * 1e-3) / 1e9
+    sha = {f: "sha256:" + hashlib.sha256(open(os.path.join(ROOT, "fixtures", f), "rb").read()).hexdigest() for f in spec["pos"]}
+    line = {
+        "metric": METRIC, "value": nodes * args.steps / (ms * 1e-3) / 1e6, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "cell_steps_per_s": cells_total * args.steps / (ms * 1e-3),
+        "config": {"workload": f"{spec['label']}: {nx}x{ny}x{nz} D3Q19 fp64, tau={par['tau']:.3f}, " +
+                               " + ".join(f"{v} {k}" for k, v in n_cells.items()) + f", material every {spec['material']}, velocity every {spec['velocity']}" +
+                               (", cell-cell + wall repulsion" if spec["rep"] else ""),
+                   "lattice": [nx, ny, nz], "cells": cells_total, "cells_by_type": n_cells, "lsp": n_lsp, "cells_alive_after_run": alive,
+                   "fluid_fraction": float((fl == 0).mean()), "pos_sha256": sha, "velocity_cadence": spec["velocity"],
+                   "material_cadence": spec["material"], "repulsion": bool(spec["rep"]), "decomposition": f"{world} x-slabs of the one domain",
+                   "l2": "lattice state per GPU far larger than the 126 MB L2 (cube: 0.3 GB); no flush"},
+        "roofline": {"bound": "hbm", "kernel": " + ".join(sorted(kernels)) + " (whole lattice update, averaged over the cadence)", "achieved": lat_ach,
+                     "peak": peak, "unit": "GB/s", "frac": lat_ach / peak if lat_ach else None, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_lu": B_LU, "launch_ms": lat_ms},
+        "roofline_kernels": kernels,
+        "roofline_step": {"bound": "hbm", "bytes_per_lu": b_step, "achieved": step_ach, "peak": peak, "unit": "GB/s", "frac": step_ach / peak,
+                          "formula": "304 + (264 + 72 + 216/c) N_LSP/N_nodes B/LU (SURVEY 8d)"},
+        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()},
+        "e2e": {"value": nodes * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 8 * 3 * npart / args.steps + 24,
+                "d2h_bytes_per_step": 2 * 8 * 3 * npart / args.steps + 16, "ms_per_step": e2e_ms / args.steps},
+        "parity_check": pcheck, "gpu_launches": launches, "clocks": clocks}
     ctx.close()
     return line
 
@@ -553,8 +785,10 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--cadence", type=int, default=1, help="velocity interpolation every n steps (stepParticleEvery)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="performance_testing", choices=["performance_testing", "synthetic", "cube"],
-                    help="performance_testing = the reference's unit with its own RBC.pos (default); synthetic = round 1's crystal packing; cube = examples/cube, 1 GPU")
+    ap.add_argument("--workload", default="performance_testing", choices=["performance_testing", "synthetic", "cube", "pipeflow", "stenosis"],
+                    help="performance_testing = the reference's unit with its own RBC.pos (default; weak scaling); synthetic = round 1's crystal "
+                         "packing; cube / pipeflow / stenosis = BASELINE configs 1 - 3 (one domain cut into N slabs: strong scaling)")
+    ap.add_argument("--repulsion", action="store_true", help="cube / pipeflow / stenosis: cell-cell and wall repulsion on (kRep 2e-22, 0.7 um)")
     ap.add_argument("--no-parity-check", action="store_true")
     args = ap.parse_args()
     args.rank = int(os.environ.get("RANK", "0"))
@@ -575,9 +809,10 @@ def main():
                 "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
-    if args.workload == "cube":
+    if args.workload in ("cube", "pipeflow", "stenosis"):
+        line = run_case(args)
         if args.rank == 0:
-            print(json.dumps(run_cube(args)), flush=True)
+            print(json.dumps(line), flush=True)
         return
     line = run_cuda(args)
     if args.rank != 0:

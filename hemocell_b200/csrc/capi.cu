@@ -295,6 +295,8 @@ hcg_status hcg_create(const hcg_domain* d, hcg_ctx** out) {
   CUDA_TRY(c, cudaMemsetAsync(c->U, 0, sizeof(double)*4*c->S, c->stream));
   CUDA_TRY(c, cudaMemsetAsync(c->flags, HCG_FLUID, c->S, c->stream));
   hcg_status s = exchange_flags(c); if (s) return s;
+  // tau = 1 on a fully periodic box: the buffers of the moment-only update exist from the start (the slab neighbours map them in hcg_comm_init)
+  if (c->omega == 1.0 && d->periodic[0] && d->periodic[1] && d->periodic[2] && (s = lat_moment_buffers(c))) return s;
   const double u0[3] = {0, 0, 0};
   if (d->n_ranks == 1) { s = lat_init_equilibrium(c, 1.0, u0); if (s) return s; }
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));

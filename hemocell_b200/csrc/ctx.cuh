@@ -63,10 +63,10 @@ struct MultiState {
 // velocity-sync receive buffers mapped into this context (CUDA IPC across processes, direct peer
 // access inside one process), so that halo planes and shared-cell velocities are STORED into the
 // neighbour by the producing kernel and a one-CTA flag kernel replaces the NCCL send/recv pair.
-#define HCG_PEER_NPTR 6            // g[0], g[1], U, flag words, sync_recv[left face], sync_recv[right face]
+#define HCG_PEER_NPTR 10           // g[0], g[1], U, flag words, sync_recv[left face], sync_recv[right face], W / F buffers of the moment-only update (2 each)
 struct PeerLink {
   int rank = -1;                   // neighbour rank, -1 = none (non-periodic end)
-  void* ptr[HCG_PEER_NPTR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* ptr[HCG_PEER_NPTR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 struct PeerMap { unsigned char handle[64]; void* base; };
 struct PeerState {
@@ -104,6 +104,8 @@ struct hcg_ctx {
   // moment-only update at tau = 1 (lattice.cu: k_moment_step; opt-in): second W / F buffers = the inputs of the last such step
   double* W2 = nullptr; double* F2 = nullptr;
   bool pops_stale = false;     // the populations lag behind W (materialised on demand by lat_ensure_pops)
+  double* Wphys[2] = {nullptr, nullptr}; double* Fphys[2] = {nullptr, nullptr};   // the two W / F buffers by identity (what the slab neighbours map)
+  int mo_flip = 0;             // W == Wphys[mo_flip], F == Fphys[mo_flip]: flips with every moment-only step, in lockstep on all ranks
   int mo_mode = -1;            // -1 = follow HCG_MOMENT_ONLY (default on), 0 = off, >= 1 = on (hcg_set_moment_only)
   bool mo_ok = false;          // tau = 1 and the whole lattice - on every rank - is plain periodic fluid (agreed in refresh_nonfluid)
   uint8_t* flags;
@@ -208,6 +210,7 @@ hcg_status lat_velocity_stats(hcg_ctx* c, double* vmin, double* vmax, double* vm
 bool lat_moment_eligible(hcg_ctx* c);
 hcg_status lat_moment_step(hcg_ctx* c, bool write_u);
 hcg_status lat_ensure_pops(hcg_ctx* c);
+hcg_status lat_moment_buffers(hcg_ctx* c);   // W, W2, F2 of the moment-only update (idempotent)
 hcg_status lat_bcn_ensure(hcg_ctx* c);
 hcg_status lat_bcn_scatter(hcg_ctx* c, int64_t n, const int64_t* idx_dev, const double* val_dev, bool keep_rho, cudaStream_t st);
 hcg_status lat_node_velocity(hcg_ctx* c, int64_t n, const int64_t* idx_dev, double* out_dev, cudaStream_t st);   // out [n][4] = (u, rho)

@@ -258,10 +258,14 @@ k_moment_step(const double* __restrict__ Win, const double* Fin, double* __restr
 // to the moment accumulators of the planes x + 1 / x / x - 1, which live in registers, so plane x - 1 is complete - and written
 // (new moments, node velocity, reset force: 96 B) - as soon as plane x has been evaluated.  Shared memory is double-buffered:
 // one __syncthreads per plane.  HBM traffic = 64 B read (+ halo re-reads served by L2) + 96 B written per lattice update.
+struct MomentPeer {      // slab neighbours' buffers (null: read the own ghost planes, filled by the send/recv exchange)
+  const double *WL, *FL, *WR, *FR;   // the left neighbour's last real plane / the right neighbour's first real plane of (W, F)
+  double *UL, *UR;                   // the left neighbour's right ghost plane / the right neighbour's left ghost plane of U
+};
 template <bool WRITE_U, int TY, int TZ, int MINB>
 __global__ void __launch_bounds__(((TY + 2)*(TZ + 2) + 31)/32*32, MINB)
 k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, double* __restrict__ Wout, double* __restrict__ Fout,
-              double* __restrict__ U, LatArgs a, int xc) {
+              double* __restrict__ U, LatArgs a, int xc, MomentPeer pr) {
   constexpr int HY = TY + 2, HZ = TZ + 2, HN = HY*HZ;
   // shared memory: the 19 populations of the current plane [19][HN], then a two-deep ring of the (W, F) inputs of the planes
   // ahead, four 16-byte chunks per thread and stage [2][4][NT][2] (chunk-major: conflict-free), filled by cp.async (no registers
@@ -286,6 +290,9 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
       const int64_t n = (int64_t)lx*a.P + col;
       const uint32_t dst = slot0 + (uint32_t)(lx & 1)*STAGE;
       const double* w = Win + 4*n; const double* f = Fin + 4*n;
+      // slab faces (multi-GPU, peer transport): the ghost planes are the neighbours' own face planes, read over NVLink
+      if (lx == 0 && pr.WL) { w = pr.WL + 4*col; f = pr.FL + 4*col; }
+      else if (lx == a.nxl + 1 && pr.WR) { w = pr.WR + 4*col; f = pr.FR + 4*col; }
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(w) : "memory");
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + CHUNK), "l"(w + 2) : "memory");
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 2*CHUNK), "l"(f) : "memory");
@@ -327,7 +334,11 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
         if (WRITE_U) {
           const double rho = 1.0 + a0r, inv = 1.0/rho;
           double2* Uw = reinterpret_cast<double2*>(U + 4*n);
-          Uw[0] = make_double2(a0x*inv + 0.5*p0, a0y*inv + 0.5*p1); Uw[1] = make_double2(a0z*inv + 0.5*p2, rho);
+          const double2 u01 = make_double2(a0x*inv + 0.5*p0, a0y*inv + 0.5*p1), u23 = make_double2(a0z*inv + 0.5*p2, rho);
+          Uw[0] = u01; Uw[1] = u23;
+          // node velocity of my face planes -> the neighbours' ghost planes (the interpolation of their shared cells reads it)
+          if (lx - 1 == 1 && pr.UL) { double2* Pw = reinterpret_cast<double2*>(pr.UL + 4*col); Pw[0] = u01; Pw[1] = u23; }
+          if (lx - 1 == a.nxl && pr.UR) { double2* Pw = reinterpret_cast<double2*>(pr.UR + 4*col); Pw[0] = u01; Pw[1] = u23; }
         }
         double2* Fw = reinterpret_cast<double2*>(Fout + 4*n);
         Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0);
@@ -1079,15 +1090,38 @@ static int moment_chunk_env() {                           // planes per CTA of k
   const char* e = getenv("HCG_MOMENT_XC"); int xc = e ? atoi(e) : 32;
   return xc < 1 ? 32 : xc;
 }
+// W (moments of the current state), W2 / F2 (second buffers of the moment-only update); by identity in Wphys / Fphys
+hcg_status lat_moment_buffers(hcg_ctx* c) {
+  auto ensure = [&](double** p) -> cudaError_t {
+    if (*p) return cudaSuccess;
+    cudaError_t e = cudaMalloc(p, sizeof(double)*4*c->S); if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(*p, 0, sizeof(double)*4*c->S, c->stream);
+  };
+  CUDA_TRY(c, ensure(&c->W)); CUDA_TRY(c, ensure(&c->W2)); CUDA_TRY(c, ensure(&c->F2));
+  if (!c->Wphys[0]) { c->Wphys[0] = c->W; c->Wphys[1] = c->W2; c->Fphys[0] = c->F; c->Fphys[1] = c->F2; c->mo_flip = 0; }
+  return HCG_OK;
+}
 hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
   hcg_status s = ensure_qsets(c); if (s) return s;
-  if (!c->W2) {
-    CUDA_TRY(c, cudaMalloc(&c->W2, sizeof(double)*4*c->S)); CUDA_TRY(c, cudaMalloc(&c->F2, sizeof(double)*4*c->S));
-    CUDA_TRY(c, cudaMemsetAsync(c->W2, 0, sizeof(double)*4*c->S, c->stream)); CUDA_TRY(c, cudaMemsetAsync(c->F2, 0, sizeof(double)*4*c->S, c->stream));
+  if ((s = lat_moment_buffers(c))) return s;
+  // ghost planes of the state and of the (spread) force.  Peer transport: the kernel reads the neighbours' face planes where
+  // they lie (after a flag barrier: their spreading and their previous update are complete) and stores the node velocity of
+  // its own face planes into their ghost planes; otherwise: periodic images / the send-recv exchange into the own ghost planes
+  MomentPeer pr = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const PeerLink* L = c->peer.link;
+  const bool peer = peer_on(c) && moment_kernel_env() && (L[0].rank < 0 || (L[0].ptr[6] && L[0].ptr[7] && L[0].ptr[8] && L[0].ptr[9]))
+                    && (L[1].rank < 0 || (L[1].ptr[6] && L[1].ptr[7] && L[1].ptr[8] && L[1].ptr[9]));
+  if (peer) {
+    LatArgs b = make_args(c);
+    const int fl = c->mo_flip;                              // the neighbours flip in lockstep: their current buffers carry the same index
+    if (L[0].rank >= 0) { pr.WL = (const double*)L[0].ptr[6 + fl] + 4*(int64_t)b.nxlL*c->P; pr.FL = (const double*)L[0].ptr[8 + fl] + 4*(int64_t)b.nxlL*c->P;
+                          pr.UL = (double*)L[0].ptr[2] + 4*(int64_t)(b.nxlL + 1)*c->P; }
+    if (L[1].rank >= 0) { pr.WR = (const double*)L[1].ptr[6 + fl] + 4*c->P; pr.FR = (const double*)L[1].ptr[8 + fl] + 4*c->P; pr.UR = (double*)L[1].ptr[2]; }
+    if ((s = peer_barrier(c))) return s;
+  } else {
+    if ((s = exchange(c, c->W, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
+    if ((s = exchange(c, c->F, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
   }
-  // ghost planes of the state and of the (spread) force: periodic images of the end planes / the neighbours' face planes
-  if ((s = exchange(c, c->W, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
-  if ((s = exchange(c, c->F, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
   LatArgs a = make_args(c);
   if (moment_kernel_env()) {
     OpTimer tk(c, "kernel:k_moment_tile");
@@ -1101,10 +1135,10 @@ hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
       cudaError_t e;
       if (write_u) {
         e = cudaFuncSetAttribute(k_moment_tile<true, TY, TZ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) k_moment_tile<true, TY, TZ, MINB><<<grid, NT, smem, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, xc);
+        if (e == cudaSuccess) k_moment_tile<true, TY, TZ, MINB><<<grid, NT, smem, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, xc, pr);
       } else {
         e = cudaFuncSetAttribute(k_moment_tile<false, TY, TZ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) k_moment_tile<false, TY, TZ, MINB><<<grid, NT, smem, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, xc);
+        if (e == cudaSuccess) k_moment_tile<false, TY, TZ, MINB><<<grid, NT, smem, c->stream>>>(c->W, c->F, c->W2, c->F2, c->U, a, xc, pr);
       }
       if (e != cudaSuccess) st = hcg_fail(c, HCG_ERR_CUDA, std::string("k_moment_tile: ") + cudaGetErrorString(e));
     };
@@ -1124,8 +1158,9 @@ hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
     KERNEL_CHECK(c);
   }
   std::swap(c->W, c->W2); std::swap(c->F, c->F2);           // the second buffers now hold the inputs of this step (kept for lat_ensure_pops)
+  c->mo_flip ^= 1;
   c->pops_stale = true; c->u_valid = write_u; c->f_clean = true; c->w_valid = true;
-  if (write_u) return lat_halo_exchange_u(c);
+  if (write_u) return peer ? peer_barrier(c) : lat_halo_exchange_u(c);
   return HCG_OK;
 }
 // the populations of the current state from the inputs of the last moment-only step: g_q(n) = f*_q(n) (k_collide_tau1)

@@ -125,7 +125,7 @@ hcg_status peer_setup(hcg_ctx* c) {
   if (!p.sync_recv[0] || !p.sync_recv[1]) { if ((s = peer_reserve_sync(c, 0, 0, nullptr))) return s; }
   PeerBlob mine; memset(&mine, 0, sizeof(mine));
   mine.pid = (int32_t)getpid(); mine.device = c->dom.device; mine.rank = r; mine.host = host_tag();
-  void* ptrs[HCG_PEER_NPTR] = {c->g[0], c->g[1], c->U, p.flags, p.sync_recv[0], p.sync_recv[1]};
+  void* ptrs[HCG_PEER_NPTR] = {c->g[0], c->g[1], c->U, p.flags, p.sync_recv[0], p.sync_recv[1], c->Wphys[0], c->Wphys[1], c->Fphys[0], c->Fphys[1]};
   // Failures that only mean "no peer memory on this box" (IPC disabled in the container, no P2P path, neighbour on
   // another host) must not leave the neighbours hanging in the collective below: they are recorded in p.usable and
   // hcg_comm_init lets all ranks agree on a transport afterwards.
