@@ -29,7 +29,8 @@ __device__ __forceinline__ V3 ldv(const double* X, int V, int i) { return {X[i],
 __device__ __forceinline__ void tri_area_normal(V3 v0, V3 v1, V3 v2, double& area, V3& n) {
   n = cross(sub(v1, v0), sub(v2, v0));
   const double nn = norm(n);
-  if (nn != 0.0) { area = 0.5*nn; n.x /= nn; n.y /= nn; n.z /= nn; }
+  // one reciprocal shared by the three components (1 ulp from the reference's three divisions; nothing downstream cancels it)
+  if (nn != 0.0) { area = 0.5*nn; const double inv = 1.0/nn; n.x *= inv; n.y *= inv; n.z *= inv; }
   else { area = 0.0; n = {0.0, 0.0, 0.0}; }
 }
 
@@ -52,7 +53,8 @@ k_mechanics(MechArgs a) {
   double* TA = VEL + (VISC ? 3*V : 0);   // [T]   (TRI_TABLES)
   double* TN = TA + (TRI_TABLES ? T : 0);               // [3T]  (TRI_TABLES)
   double* VT = TN + (TRI_TABLES ? 3*T : 0);             // [T]
-  double* BF = VT + T;               // [3V] (RBC)
+  double* BF = VT + T;               // [3V] (RBC) bending force of every vertex's own patch
+  double* BFN = BF + 3*V;            // [3V] (RBC) ... divided by the patch's ring size: the reaction each ring neighbour takes
   __shared__ double s_volume;
   const int tid = threadIdx.x, nt = blockDim.x;
 
@@ -79,9 +81,19 @@ k_mechanics(MechArgs a) {
       TA[k] = area; TN[3*k] = n.x; TN[3*k+1] = n.y; TN[3*k+2] = n.z;
     }
   }
+  __syncthreads();
+  // ---- the signed volume is summed sequentially in triangle order (== the reference's rounding: the absolute-coordinate
+  // formula loses ~7 digits, any other order changes the volume force at 1e-10) by ONE lane, while the other warps compute
+  // the bending forces of the vertex patches - the two do not depend on each other
+  if (tid == 0) {
+    double vol = 0.0;
+    for (int k = 0; k < T; k++) vol = __dadd_rn(vol, VT[k]);
+    s_volume = __dmul_rn(vol, 1.0/6.0);
+  }
   // ---- RBC: bending force of every vertex's own patch (rbcHighOrderModel.cpp:127-158)
-  if (MODEL == 0) {
-    for (int i = tid; i < V; i += nt) {
+  if (MODEL == 0 && (tid >= 32 || nt <= 32)) {
+    const int lane0 = nt > 32 ? 32 : 0, span = nt > 32 ? nt - 32 : nt;
+    for (int i = tid - lane0; i < V; i += span) {
       const int nn = t.nring[i];
       const int* ring = t.ring + 6*i;
       const V3 xi = ldv(X, V, i);
@@ -95,29 +107,27 @@ k_mechanics(MechArgs a) {
       for (int j = 0; j < nn; j++) {
         const V3 nxt = (j + 1 < nn) ? sub(ldv(X, V, ring[j+1]), xi) : first;
         V3 tn = cross(prev, nxt);
-        const double l = norm(tn);
-        pn.x += tn.x/l; pn.y += tn.y/l; pn.z += tn.z/l;
+        const double il = 1.0/norm(tn);
+        pn.x += tn.x*il; pn.y += tn.y*il; pn.z += tn.z*il;
         prev = nxt;
       }
-      const double l = norm(pn);
-      pn.x /= l; pn.y /= l; pn.z /= l;
+      const double il = 1.0/norm(pn);
+      pn.x *= il; pn.y *= il; pn.z *= il;
       const double ndev = dot(pn, dev);
       const double dDev = (ndev - t.patch_eq[i]) / t.edge_mean_eq;
       const double s = t.k_bend * (dDev + dDev/fabs(0.0555 - dDev*dDev));
-      BF[i] = s*pn.x; BF[V+i] = s*pn.y; BF[2*V+i] = s*pn.z;
+      const double b0 = s*pn.x, b1 = s*pn.y, b2 = s*pn.z;
+      BF[i] = b0; BF[V+i] = b1; BF[2*V+i] = b2;
+      BFN[i] = -b0/nn; BFN[V+i] = -b1/nn; BFN[2*V+i] = -b2/nn;
     }
-  }
-  __syncthreads();
-  if (tid == 0) {   // sequential sum in triangle order == the reference's rounding
-    double vol = 0.0;
-    for (int k = 0; k < T; k++) vol = __dadd_rn(vol, VT[k]);
-    s_volume = __dmul_rn(vol, 1.0/6.0);
   }
   __syncthreads();
   const double volume_frac = (s_volume - t.volume_eq)/t.volume_eq;
   const double volume_force = -t.k_volume * volume_frac/fabs(0.01 - volume_frac*volume_frac);
 
-  // ---- per vertex gather
+  // ---- per vertex gather.  Divisions whose result is only scaled afterwards share a reciprocal (fp64 division is ~30
+  // instructions and was 3/4 of this kernel's instruction count); those that feed a cancelling difference stay divisions.
+  const double third = 1.0/3.0, inv_area_mean = 1.0/t.area_mean_eq;
   for (int v = tid; v < V; v += nt) {
     const V3 xv = ldv(X, V, v);
     double F0 = 0.0, F1 = 0.0, F2 = 0.0;
@@ -135,11 +145,11 @@ k_mechanics(MechArgs a) {
       const double aeq = t.tri_area_eq[tr];
       const double areaRatio = (area - aeq)/aeq;
       const double afm = t.k_area * (areaRatio + areaRatio/fabs(0.09 - areaRatio*areaRatio));
-      const double cx = (v0.x+v1.x+v2.x)/3.0, cy = (v0.y+v1.y+v2.y)/3.0, cz = (v0.z+v1.z+v2.z)/3.0;
+      const double cx = (v0.x+v1.x+v2.x)*third, cy = (v0.y+v1.y+v2.y)*third, cz = (v0.z+v1.z+v2.z)*third;
       const double a0 = afm*(cx - xv.x), a1 = afm*(cy - xv.y), a2 = afm*(cz - xv.z);
       F0 += a0; F1 += a1; F2 += a2;
       if (COMP) { c0 += a0; c1 += a1; c2 += a2; }
-      const double s = area/t.area_mean_eq;
+      const double s = area*inv_area_mean;
       w0 += (volume_force*n.x)*s; w1 += (volume_force*n.y)*s; w2 += (volume_force*n.z)*s;
     }
     if (COMP) { a.comp[0][0][base+v] = c0; a.comp[0][1][base+v] = c1; a.comp[0][2][base+v] = c2;
@@ -151,7 +161,7 @@ k_mechanics(MechArgs a) {
         const int i = t.vb[7*v + k]; if (i < 0) break;
         double a0, a1, a2;
         if (i == v) { a0 = BF[i]; a1 = BF[V+i]; a2 = BF[2*V+i]; }
-        else { const int nn = t.nring[i]; a0 = -BF[i]/nn; a1 = -BF[V+i]/nn; a2 = -BF[2*V+i]/nn; }
+        else { a0 = BFN[i]; a1 = BFN[V+i]; a2 = BFN[2*V+i]; }
         F0 += a0; F1 += a1; F2 += a2;
         if (COMP) { c0 += a0; c1 += a1; c2 += a2; }
       }
@@ -164,7 +174,8 @@ k_mechanics(MechArgs a) {
         const int ia = t.edge[2*e], ib = t.edge[2*e+1];
         const V3 ev = sub(ldv(X, V, ib), ldv(X, V, ia));
         const double len = norm(ev);
-        const V3 uv = {ev.x/len, ev.y/len, ev.z/len};
+        const double ilen = 1.0/len;
+        const V3 uv = {ev.x*ilen, ev.y*ilen, ev.z*ilen};
         const double leq = t.edge_len_eq[e];
         const double frac = (len - leq)/leq;
         const double fs = t.k_link * (frac + frac/fabs(9.0 - frac*frac));
@@ -195,7 +206,8 @@ k_mechanics(MechArgs a) {
         const int ia = t.edge[2*e], ib = t.edge[2*e+1];
         const V3 ev = sub(ldv(X, V, ib), ldv(X, V, ia));
         const double len = sqrt(ev.x*ev.x + ev.y*ev.y + ev.z*ev.z);
-        const V3 uv = {ev.x/len, ev.y/len, ev.z/len};
+        const double ilen = 1.0/len;
+        const V3 uv = {ev.x*ilen, ev.y*ilen, ev.z*ilen};
         if (role < 2) {
           const double sg = role ? -1.0 : 1.0;
           const double leq = t.edge_len_eq[e];
@@ -233,7 +245,8 @@ k_mechanics(MechArgs a) {
         const double leq = t.inner_len_eq[e];
         const double frac = (len - leq)/leq;
         const double fs = t.k_link*5.0*frac;
-        const double a0 = (ev.x/len)*fs, a1 = (ev.y/len)*fs, a2 = (ev.z/len)*fs;
+        const double ilen = 1.0/len;
+        const double a0 = (ev.x*ilen)*fs, a1 = (ev.y*ilen)*fs, a2 = (ev.z*ilen)*fs;
         F0 += sg*a0; F1 += sg*a1; F2 += sg*a2;
         if (COMP) { n0 += sg*a0; n1_ += sg*a1; n2_ += sg*a2; }
       }
@@ -355,7 +368,7 @@ hcg_status mech_apply(hcg_ctx* c, int ctype, bool components) {
   const int V = th.d.V, T = th.d.T;
   const bool plt = th.d.model == HCG_MODEL_PLT_SIMPLE;
   const bool visc = plt || th.d.eta_m != 0.0;
-  size_t smem = sizeof(double)*((size_t)3*V + (visc ? 3*V : 0) + (plt ? 5 : 1)*(size_t)T + (plt ? 0 : 3*V));
+  size_t smem = sizeof(double)*((size_t)3*V + (visc ? 3*V : 0) + (plt ? 5 : 1)*(size_t)T + (plt ? 0 : 6*V));
   { static int pad = -1; if (pad < 0) { const char* e = getenv("HCG_MECH_SMEM_PAD"); pad = e ? atoi(e) : 0; } smem += (size_t)pad*1024; }   // experiment knob: occupancy sensitivity
   const int threads = V >= 256 ? 256 : (V >= 128 ? 128 : 64);
   if (plt) return launch<1, true>(c, a, th.n_cells, smem, threads, components);
