@@ -258,6 +258,45 @@ k_moment_step(const double* __restrict__ Win, const double* Fin, double* __restr
 // to the moment accumulators of the planes x + 1 / x / x - 1, which live in registers, so plane x - 1 is complete - and written
 // (new moments, node velocity, reset force: 96 B) - as soon as plane x has been evaluated.  Shared memory is double-buffered:
 // one __syncthreads per plane.  HBM traffic = 64 B read (+ halo re-reads served by L2) + 96 B written per lattice update.
+// mbarrier / bulk-async (1-D TMA) helpers, shared by k_moment_tile and the row-pipelined kernels below
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  long long t_start = 0;
+  for (unsigned spin = 0; !ok; spin++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (!ok && (spin & 255u) == 255u) {       // a byte-count mismatch must not hang the device: trap after ~2 s
+      const long long now = clock64();
+      if (t_start == 0) t_start = now; else if (now - t_start > 4000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// one 32-byte node record as ONE 256-bit store (STG.E.256 on sm_100a): half the store requests of two 128-bit stores, whole sectors
+__device__ __forceinline__ void st_node4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 struct MomentPeer {      // slab neighbours' buffers (null: read the own ghost planes, filled by the send/recv exchange)
   const double *WL, *FL, *WR, *FR;   // the left neighbour's last real plane / the right neighbour's first real plane of (W, F)
   double *UL, *UR;                   // the left neighbour's right ghost plane / the right neighbour's left ghost plane of U
@@ -268,11 +307,12 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
               double* __restrict__ U, LatArgs a, int xc, MomentPeer pr) {
   constexpr int HY = TY + 2, HZ = TZ + 2, HN = HY*HZ;
   // shared memory: the 19 populations of the current plane [19][HN], then a two-deep ring of the (W, F) inputs of the planes
-  // ahead, four 16-byte chunks per thread and stage [2][4][NT][2] (chunk-major: conflict-free), filled by cp.async (no registers
-  // held while the loads fly)
-  extern __shared__ __align__(16) double sm_pop[];
+  // ahead as node records [2 stages][W | F][HY][HZ][4], filled row by row with bulk-async copies (1-D TMA: one request per
+  // 1 KB row instead of four 16-byte cp.async per node, whole sectors, no registers held while the loads fly)
+  extern __shared__ __align__(128) double sm_pop[];
   constexpr int NT = (HN + 31)/32*32;
-  double* ring = sm_pop + 19*HN;
+  double* ring = sm_pop + 19*HN;                         // [2][2][HN][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + 2*2*HN*4);
   const int t = threadIdx.x;
   const int hy = t / HZ, hz = t - hy*HZ;
   const int y = (int)blockIdx.y*TY + hy - 1, z = (int)blockIdx.x*TZ + hz - 1;
@@ -283,22 +323,37 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
   const int64_t col = (int64_t)yw*nz + zw;
   const int x_lo = 1 + (int)blockIdx.z*xc, x_hi = min(x_lo + xc - 1, a.nxl);
   if (x_lo > a.nxl) return;
-  const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(ring + (size_t)t*2);
-  constexpr uint32_t STAGE = NT*64, CHUNK = NT*16;
-  auto fetch = [&](int lx) {                             // (W, F) of this thread's node on plane lx -> ring stage lx & 1
-    if (halo_ok && lx <= x_hi + 1) {
-      const int64_t n = (int64_t)lx*a.P + col;
-      const uint32_t dst = slot0 + (uint32_t)(lx & 1)*STAGE;
-      const double* w = Win + 4*n; const double* f = Fin + 4*n;
+  if (t == 0) {
+    mbar_init(full, 1); mbar_init(full + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // the row of halo'd nodes a lane of warp 0 fetches: y row `t` of the tile (z0 - 1 .. z0 + TZ, wrapped at the ends of the z axis)
+  const int z0 = (int)blockIdx.x*TZ;
+  const int zmain0 = max(z0 - 1, 0), zmain1 = min(z0 + TZ, nz - 1);            // contiguous part [zmain0, zmain1]
+  const bool wrapL = z0 == 0, wrapR = z0 + TZ >= nz;                            // hz = 0 <- node nz - 1; hz = nz - z0 + 1 <- node 0
+  const int rows_ok = min(HY, ny - (int)blockIdx.y*TY + 2);                     // rows with y <= ny
+  const uint32_t row_bytes = 32u*(uint32_t)((zmain1 - zmain0 + 1) + (wrapL ? 1 : 0) + (wrapR ? 1 : 0));
+  auto fetch = [&](int lx) {                             // (W, F) of the tile's nodes on plane lx -> ring stage lx & 1 (warp 0 issues)
+    if (t >= 32 || lx > x_hi + 1) return;
+    uint64_t* bar = full + (lx & 1);
+    if (t == 0) mbar_expect_tx(bar, 2u*row_bytes*(uint32_t)rows_ok);
+    __syncwarp();
+    if (t < rows_ok) {
+      const int ry = (int)blockIdx.y*TY + t - 1;
+      const int ryw = ry < 0 ? ny - 1 : (ry >= ny ? 0 : ry);
+      const double* w = Win + 4*(int64_t)lx*a.P; const double* f = Fin + 4*(int64_t)lx*a.P;
       // slab faces (multi-GPU, peer transport): the ghost planes are the neighbours' own face planes, read over NVLink
-      if (lx == 0 && pr.WL) { w = pr.WL + 4*col; f = pr.FL + 4*col; }
-      else if (lx == a.nxl + 1 && pr.WR) { w = pr.WR + 4*col; f = pr.FR + 4*col; }
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(w) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + CHUNK), "l"(w + 2) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 2*CHUNK), "l"(f) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 3*CHUNK), "l"(f + 2) : "memory");
+      if (lx == 0 && pr.WL) { w = pr.WL; f = pr.FL; }
+      else if (lx == a.nxl + 1 && pr.WR) { w = pr.WR; f = pr.FR; }
+      const int64_t rowoff = 4*(int64_t)ryw*nz;
+      double* dw = ring + (size_t)(lx & 1)*2*HN*4 + (size_t)t*HZ*4; double* df = dw + HN*4;
+      const int hz0 = zmain0 - (z0 - 1);                 // slot of the first contiguous node
+      const uint32_t nb = 32u*(uint32_t)(zmain1 - zmain0 + 1);
+      bulk_g2s(dw + 4*hz0, w + rowoff + 4*zmain0, nb, bar); bulk_g2s(df + 4*hz0, f + rowoff + 4*zmain0, nb, bar);
+      if (wrapL) { bulk_g2s(dw, w + rowoff + 4*(int64_t)(nz - 1), 32u, bar); bulk_g2s(df, f + rowoff + 4*(int64_t)(nz - 1), 32u, bar); }
+      if (wrapR) { const int hzr = nz - z0 + 1; bulk_g2s(dw + 4*hzr, w + rowoff, 32u, bar); bulk_g2s(df + 4*hzr, f + rowoff, 32u, bar); }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   fetch(x_lo - 1);
   fetch(x_lo);
@@ -308,11 +363,11 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
   const int i = hy*HZ + hz;
   double* sb = sm_pop;
   for (int lx = x_lo - 1; lx <= x_hi + 1; lx++) {
-    asm volatile("cp.async.wait_group 1;" ::: "memory");  // plane lx has landed (the group of plane lx + 1 may still fly)
+    mbar_wait(full + (lx & 1), (uint32_t)(((lx - x_lo + 1) >> 1) & 1));   // plane lx has landed (the copies of plane lx + 1 may still fly)
     double c0 = 0, c1 = 0, c2 = 0;
     if (halo_ok) {
-      const double2* sl = reinterpret_cast<const double2*>(ring + (size_t)(lx & 1)*NT*8) + t;
-      const double2 wa = sl[0], wb = sl[NT], fa = sl[2*NT], fb = sl[3*NT];
+      const double2* sl = reinterpret_cast<const double2*>(ring + (size_t)(lx & 1)*2*HN*4 + (size_t)t*4);
+      const double2 wa = sl[0], wb = sl[1], fa = sl[2*HN], fb = sl[2*HN + 1];
       c0 = fa.x; c1 = fa.y; c2 = fb.x;
       double p[19];
       tau1_pops_fast(wa.x, wa.y, wb.x, wb.y, fa.x, fa.y, fb.x, p);
@@ -329,19 +384,16 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
       a0r += sm; a0x -= sm; a0y += q5 - q4; a0z += q7 - q6;
       if (lx - 1 >= x_lo) {
         const int64_t n = (int64_t)(lx - 1)*a.P + col;
-        double2* Ww = reinterpret_cast<double2*>(Wout + 4*n);
-        Ww[0] = make_double2(a0r, a0x); Ww[1] = make_double2(a0y, a0z);
+        st_node4(Wout + 4*n, a0r, a0x, a0y, a0z);
         if (WRITE_U) {
           const double rho = 1.0 + a0r, inv = 1.0/rho;
-          double2* Uw = reinterpret_cast<double2*>(U + 4*n);
-          const double2 u01 = make_double2(a0x*inv + 0.5*p0, a0y*inv + 0.5*p1), u23 = make_double2(a0z*inv + 0.5*p2, rho);
-          Uw[0] = u01; Uw[1] = u23;
+          const double u0 = a0x*inv + 0.5*p0, u1 = a0y*inv + 0.5*p1, u2 = a0z*inv + 0.5*p2;
+          st_node4(U + 4*n, u0, u1, u2, rho);
           // node velocity of my face planes -> the neighbours' ghost planes (the interpolation of their shared cells reads it)
-          if (lx - 1 == 1 && pr.UL) { double2* Pw = reinterpret_cast<double2*>(pr.UL + 4*col); Pw[0] = u01; Pw[1] = u23; }
-          if (lx - 1 == a.nxl && pr.UR) { double2* Pw = reinterpret_cast<double2*>(pr.UR + 4*col); Pw[0] = u01; Pw[1] = u23; }
+          if (lx - 1 == 1 && pr.UL) st_node4(pr.UL + 4*col, u0, u1, u2, rho);
+          if (lx - 1 == a.nxl && pr.UR) st_node4(pr.UR + 4*col, u0, u1, u2, rho);
         }
-        double2* Fw = reinterpret_cast<double2*>(Fout + 4*n);
-        Fw[0] = make_double2(a.body[0], a.body[1]); Fw[1] = make_double2(a.body[2], 0.0);
+        st_node4(Fout + 4*n, a.body[0], a.body[1], a.body[2], 0.0);
       }
       // c_x = 0 -> plane lx; c_x = +1 -> plane lx + 1; then the accumulators move one plane on
       const double q0 = sb[0*HN + i];
@@ -356,7 +408,6 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
     }
     __syncthreads();                                     // the populations of this plane are consumed: the buffer is free
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // Off-equilibrium momentum flux of the post-stream populations (output path only: the "ShearStress"
@@ -405,40 +456,6 @@ k_pineq(const double* __restrict__ g, const uint8_t* __restrict__ flags, LatArgs
 // pull becomes a shared-memory index, wrap included), collide in registers and store coalesced.
 // The loads of a row are in flight while the previous rows are being collided, independent of the
 // register-limited occupancy that bounds the plain one-thread-per-node kernel.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
-  long long t_start = 0;
-  for (unsigned spin = 0; !ok; spin++) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (!ok && (spin & 255u) == 255u) {       // a byte-count mismatch must not hang the device: trap after ~2 s
-      const long long now = clock64();
-      if (t_start == 0) t_start = now; else if (now - t_start > 4000000000LL) __trap();
-    }
-  }
-}
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 // Guo-forced BGK collision, opposite pairs sharing their symmetric part (same algebra as guo_collide,
 // re-associated: differences are a few ulp of the intermediate terms).
 __device__ __forceinline__ void guo_collide_pairs(double f[19], const double F[3], double omega) {
@@ -1130,7 +1147,7 @@ hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
     auto launch = [&](auto ty, auto tz, auto minb) {
       constexpr int TY = decltype(ty)::value, TZ = decltype(tz)::value, MINB = decltype(minb)::value;
       constexpr int NT = ((TY + 2)*(TZ + 2) + 31)/32*32;
-      const size_t smem = sizeof(double)*(19*(TY + 2)*(TZ + 2) + 2*NT*8);
+      const size_t smem = sizeof(double)*(19*(TY + 2)*(TZ + 2) + 2*2*(TY + 2)*(TZ + 2)*4) + 16;   // populations + input ring + 2 mbarriers
       dim3 grid((unsigned)((a.nz + TZ - 1)/TZ), (unsigned)((a.ny + TY - 1)/TY), (unsigned)((c->nxl + xc - 1)/xc));
       cudaError_t e;
       if (write_u) {

@@ -8,6 +8,6 @@ for env in sys.argv[1:]:
     r = subprocess.run([sys.executable, "bench.py", "--steps", "30", "--warmup", "4", "--no-cpu-baseline", "--no-parity-check"], env=e, capture_output=True, text=True)
     try:
         d = json.loads(r.stdout.strip().splitlines()[-1])
-        print(env, "ms/step", round(d["ms_per_step"], 4), {k: round(v, 4) for k, v in d["kernel_ms_per_step"].items() if k.startswith("kernel:")}, flush=True)
+        print(env, "ms/step", round(d["ms_per_step"], 4), {k.replace("kernel:", ""): round(v, 4) for k, v in d["kernel_ms_per_step"].items()}, flush=True)
     except Exception as ex:
         print(env, "FAILED", r.stderr[-500:], flush=True)
