@@ -192,8 +192,7 @@ hcg_status step(hcg_ctx* c) {
       if (overlap < 0) { const char* e = getenv("HCG_SYNC_OVERLAP"); overlap = e ? atoi(e) : 0; }   // opt-in: measured no faster (2 B200: 2.305 vs 2.291 ms), the exchange chain is work, not idle time
       if (!overlap) {
         { OpTimer t(c, "interpolateFluidVelocity"); if (!fused && (s = lat_moments(c, true, false))) return s; if ((s = ibm_interpolate_advance_unshared(c))) return s; }
-        { OpTimer t(c, "syncEnvelopes"); if ((s = multi_velocity_sync(c))) return s; }
-        { OpTimer t(c, "advanceParticles"); if ((s = ibm_advance_shared(c))) return s; }
+        { OpTimer t(c, "syncEnvelopes"); if ((s = multi_velocity_sync_advance(c))) return s; }
       } else {
         // the velocity exchange of the shared cells (pack -> neighbour -> unpack -> advance) runs on the main stream
         // while the cells no neighbour holds are interpolated and advanced on a low-priority stream

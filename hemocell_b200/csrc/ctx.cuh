@@ -234,6 +234,7 @@ hcg_status spread_sorted_rebuild(hcg_ctx* c);
 hcg_status spread_sorted(hcg_ctx* c);
 // multi.cu
 hcg_status multi_velocity_sync(hcg_ctx* c);                // = multi_field_sync(c, 0)
+hcg_status multi_velocity_sync_advance(hcg_ctx* c);        // ... fused with the advance of the shared cells
 hcg_status multi_field_sync(hcg_ctx* c, int field);        // 0 = velocity + alive flags, 1 = repulsion force
 hcg_status multi_upload_cell_gid(hcg_ctx* c);
 hcg_status multi_rebalance(hcg_ctx* c, bool initial);

@@ -16,6 +16,7 @@
 //    entered a neighbour's hold region are shipped whole (pos, vel, force, frep), cells that left
 //    the own region are dropped.  M = 2 (kernel support) + drift allowance.
 #include "ctx.cuh"
+#include "ibm_node.cuh"
 #include <nccl.h>
 #include <algorithm>
 #include <cmath>
@@ -80,6 +81,57 @@ k_unpack_sync(const int32_t* __restrict__ cells, const int64_t* __restrict__ off
   for (int k = threadIdx.x; k < V; k += blockDim.x) {
     if (owns_vertex(x[b+k], nx, px, x0, nxl)) continue;      // authoritative here
     vx[b+k] = v[k]; vy[b+k] = v[total + k]; vz[b+k] = v[2*total + k];
+  }
+}
+
+// The two faces in one launch, and the unpack fused with the advance of the shared cells (a shared cell sits on exactly one
+// face list - multi_rebalance refuses slabs thin enough for a cell to reach both faces - so one CTA owns it): per velocity
+// sync 3 launches (pack, flag barrier, unpack + advance) instead of 6.
+struct SyncFace { const int32_t* cells; const int64_t* off; int n; int64_t total; double* send; const double* recv; };
+__global__ void __launch_bounds__(256)
+k_pack_sync2(SyncFace f0, SyncFace f1, const int64_t* __restrict__ cell_base, const uint8_t* __restrict__ alive,
+             const double* __restrict__ x, const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
+             int nx, int px, int x0, int nxl) {
+  const bool second = (int)blockIdx.x >= f0.n;
+  const SyncFace& f = second ? f1 : f0;
+  const int i = second ? (int)blockIdx.x - f0.n : (int)blockIdx.x;
+  if (i >= f.n || !f.send) return;
+  const int c = f.cells[i];
+  const int64_t b = cell_base[c], o = f.off[i];
+  const int V = (int)(f.off[i+1] - o);
+  if (threadIdx.x == 0) f.send[i] = alive[c] ? 1.0 : 0.0;
+  double* v = f.send + f.n + o;
+  for (int k = threadIdx.x; k < V; k += blockDim.x) {
+    if (!owns_vertex(x[b+k], nx, px, x0, nxl)) continue;
+    v[k] = vx[b+k]; v[f.total + k] = vy[b+k]; v[2*f.total + k] = vz[b+k];
+  }
+}
+__global__ void __launch_bounds__(256)
+k_unpack_advance2(SyncFace f0, SyncFace f1, IbmArgs a, const uint8_t* __restrict__ flags, const int64_t* __restrict__ cell_base,
+                  uint8_t* alive, double* x, double* y, double* z, double* vx, double* vy, double* vz) {
+  const bool second = (int)blockIdx.x >= f0.n;
+  const SyncFace& f = second ? f1 : f0;
+  const int i = second ? (int)blockIdx.x - f0.n : (int)blockIdx.x;
+  if (i >= f.n) return;
+  const int c = f.cells[i];
+  const int64_t b = cell_base[c], o = f.off[i];
+  const int V = (int)(f.off[i+1] - o);
+  const bool live = alive[c] && (!f.recv || f.recv[i] != 0.0);   // deleted on either holder = deleted
+  __syncthreads();                                        // every thread has read the flag before thread 0 may clear it
+  if (!live) { if (threadIdx.x == 0) alive[c] = 0; return; }
+  const double* v = f.recv ? f.recv + f.n + o : nullptr;
+  for (int k = threadIdx.x; k < V; k += blockDim.x) {
+    const int64_t p = b + k;
+    double v0 = vx[p], v1 = vy[p], v2 = vz[p];
+    if (v && !owns_vertex(x[p], a.nx, a.px, a.x0, a.nxl)) { v0 = v[k]; v1 = v[f.total + k]; v2 = v[2*f.total + k]; vx[p] = v0; vy[p] = v1; vz[p] = v2; }
+    const double qx = x[p] + v0, qy = y[p] + v1, qz = z[p] + v2;
+    x[p] = qx; y[p] = qy; z[p] = qz;
+    // particle on a boundary node => its cell is deleted (hemoCellParticleField.cpp:572-584)
+    int lx; bool out;
+    int yy = (int)floor(qy + 0.5), zz = (int)floor(qz + 0.5);
+    if (local_x((int)floor(qx + 0.5), a, lx, out) && wrap_yz(yy, a.ny, a.py) && wrap_yz(zz, a.nz, a.pz)) {
+      if (flags[(int64_t)zz + (int64_t)a.nz*((int64_t)yy + (int64_t)a.ny*lx)] != HCG_FLUID) alive[c] = 0;
+    }
   }
 }
 
@@ -190,6 +242,46 @@ hcg_status multi_upload_cell_gid(hcg_ctx* c) {
 }
 
 hcg_status multi_velocity_sync(hcg_ctx* c) { return multi_field_sync(c, 0); }
+
+// velocity sync of the shared cells + their advance (the step's syncEnvelopes + advanceParticles for the cells a neighbour
+// also holds).  Peer transport: pack (both faces) -> flag barrier -> unpack + advance; otherwise the separate kernels.
+hcg_status multi_velocity_sync_advance(hcg_ctx* c) {
+  if (c->dom.n_ranks == 1) return HCG_OK;
+  MultiState& m = c->multi;
+  hcg_status s;
+  if (!peer_on(c)) {
+    if ((s = multi_field_sync(c, 0))) return s;
+    return ibm_advance_shared(c);
+  }
+  const size_t half = (size_t)(c->peer.sync_count++ & 1ULL);
+  SyncFace f[2];
+  for (int k = 0; k < 2; k++) {
+    const bool on = m.face[k].n > 0 && c->peer.link[k].rank >= 0;
+    f[k].cells = m.face[k].d_cells; f[k].off = m.face[k].d_off; f[k].n = on ? m.face[k].n : 0; f[k].total = m.face[k].total;
+    f[k].send = nullptr; f[k].recv = nullptr;
+    if (!on) continue;
+    double* dst = (double*)c->peer.link[k].ptr[4 + (1 - k)];
+    if (!dst) return hcg_fail(c, HCG_ERR_STATE, "peer transport: neighbour receive buffer not mapped");
+    const size_t span = (size_t)m.face[k].n + 3*(size_t)m.face[k].total;
+    f[k].send = dst + half*span; f[k].recv = c->peer.sync_recv[k] + half*span;
+  }
+  const int nblocks = f[0].n + f[1].n;
+  if (nblocks > 0) {
+    k_pack_sync2<<<nblocks, 256, 0, c->stream>>>(f[0], f[1], c->cell_base, c->cell_alive, c->pos[0], c->vel[0], c->vel[1], c->vel[2],
+                                                 c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
+    KERNEL_CHECK(c);
+  }
+  if ((s = peer_barrier(c))) return s;
+  if (nblocks > 0) {
+    IbmArgs a;
+    a.nx = c->dom.nx; a.ny = c->dom.ny; a.nz = c->dom.nz; a.px = c->dom.periodic[0]; a.py = c->dom.periodic[1]; a.pz = c->dom.periodic[2];
+    a.nxl = c->nxl; a.x0 = c->x0; a.nranks = c->dom.n_ranks; a.P = c->P; a.S = c->S; a.np = c->np; a.f_limit = c->f_limit;
+    k_unpack_advance2<<<nblocks, 256, 0, c->stream>>>(f[0], f[1], a, c->flags, c->cell_base, c->cell_alive, c->pos[0], c->pos[1], c->pos[2],
+                                                      c->vel[0], c->vel[1], c->vel[2]);
+    KERNEL_CHECK(c);
+  }
+  return HCG_OK;
+}
 
 // per-vertex swap of a particle field of the shared cells: the rank that OWNS a vertex is authoritative.
 // field 0: velocity (every interpolation step; the alive flags are AND-ed in the same message);

@@ -1091,7 +1091,7 @@ void write_fluid_h5(HemoCell& h) {
         buf.resize((size_t)Nl); ck(c, hcg_lattice_download(c, HCG_LAT_DENSITY, buf.data()), "download");
         emit("Density", 1, si ? param::df/(param::dx*param::dx) : 1.0, 1.0); break;
       case OUTPUT_BOUNDARY:
-        buf.resize((size_t)Nl); for (int64_t n = 0; n < Nl; n++) buf[n] = flags[n] == HCG_BOUNCEBACK ? 1.0 : 0.0;
+        buf.resize((size_t)Nl); for (int64_t n = 0; n < Nl; n++) buf[n] = flags[n] != HCG_FLUID ? 1.0 : 0.0;   // isBoundary(): bounce-back, velocity-plane and Zou-He nodes alike (io/FluidHdf5IO.hh:288-305)
         emit("Boundary", 1, 1.0, 0.0); break;
       case OUTPUT_OMEGA:
         buf.resize((size_t)Nl); for (int64_t n = 0; n < Nl; n++) buf[n] = flags[n] == HCG_BOUNCEBACK ? 0.0 : omega;

@@ -68,3 +68,59 @@ def test_many_datasets_single_symbol_node(tmp_path):
     assert f.leaf_k >= 12
     for k, v in arrays.items():
         np.testing.assert_array_equal(f[k], v)
+
+
+def _libhdf5():
+    """h5py, else libhdf5 through ctypes, else None (neither is in the authoring image; the test runs wherever one exists)"""
+    try:
+        import h5py                                   # noqa: F401
+        return "h5py"
+    except Exception:
+        pass
+    import ctypes.util
+    for name in ("hdf5", "hdf5_serial"):
+        if ctypes.util.find_library(name):
+            return ctypes.util.find_library(name)
+    return None
+
+
+@pytest.mark.skipif(_libhdf5() is None, reason="neither h5py nor libhdf5 on this machine")
+def test_files_open_with_the_real_hdf5_library(tmp_path):
+    """the consumers of the reference's output (scripts/*XMF.py, ParaView) use libhdf5: wherever h5py or libhdf5 exists, the
+    files of our writer must open with it and show the layout of io/ParticleHdf5IO.cpp:60-194 (dataset names, shapes, element
+    types, root attributes)"""
+    rng = np.random.default_rng(5)
+    n = 642*3
+    arrays = {"Position": rng.normal(size=(n, 3)).astype(np.float32), "Total force": rng.normal(size=(n, 3)).astype(np.float32),
+              "Cell Id": rng.integers(0, 99, size=(n, 1)).astype(np.float32), "Triangles": rng.integers(0, n, size=(1280*3, 3)).astype(np.int32)}
+    chunks = {k: (min(1000, v.shape[0]), v.shape[1]) for k, v in arrays.items()}
+    attrs = {"dx": np.array([5e-7]), "dt": np.array([1e-7]), "iteration": np.array([1200], dtype=np.int64),
+             "processorId": np.array([0], dtype=np.int32), "numberOfParticles": np.array([n], dtype=np.int64)}
+    p = tmp_path / "RBC.000000001200.p.0.h5"
+    _write(p, 7, arrays, attrs, chunks)
+    how = _libhdf5()
+    if how == "h5py":
+        import h5py
+        with h5py.File(p, "r") as f:
+            assert sorted(f.keys()) == sorted(arrays)
+            for k, v in arrays.items():
+                assert f[k].shape == v.shape and f[k].dtype == v.dtype and f[k].chunks == chunks[k] and f[k].compression == "gzip"
+                np.testing.assert_array_equal(f[k][...], v)
+            for k, v in attrs.items():
+                np.testing.assert_array_equal(np.asarray(f.attrs[k]).reshape(-1), v)
+    else:
+        import ctypes as C
+        h5 = C.CDLL(how)
+        h5.H5open()
+        h5.H5Fopen.restype = C.c_int64; h5.H5Dopen2.restype = C.c_int64; h5.H5Dget_space.restype = C.c_int64
+        fid = h5.H5Fopen(str(p).encode(), C.c_uint(0), C.c_int64(0))
+        assert fid >= 0, "H5Fopen rejected the file"
+        for k, v in arrays.items():
+            did = h5.H5Dopen2(C.c_int64(fid), k.encode(), C.c_int64(0))
+            assert did >= 0, k
+            sid = h5.H5Dget_space(C.c_int64(did))
+            dims = (C.c_uint64 * 8)()
+            rank = h5.H5Sget_simple_extent_dims(C.c_int64(sid), dims, None)
+            assert tuple(dims[:rank]) == v.shape
+            h5.H5Sclose(C.c_int64(sid)); h5.H5Dclose(C.c_int64(did))
+        h5.H5Fclose(C.c_int64(fid))
