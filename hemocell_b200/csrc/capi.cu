@@ -316,6 +316,8 @@ void hcg_destroy(hcg_ctx* c) {
   for (int k = 0; k < 3; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->frc[k]); cudaFree(c->frep[k]); }
   for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) if (c->comp[k][d]) cudaFree(c->comp[k][d]);
   if (c->multi.d_cell_shared) cudaFree(c->multi.d_cell_shared);
+  if (c->multi.d_meta) cudaFree(c->multi.d_meta); if (c->multi.d_bbox) cudaFree(c->multi.d_bbox);
+  for (int f = 0; f < 2; f++) { cudaFree(c->multi.tmp_send[f].d_cells); cudaFree(c->multi.tmp_send[f].d_off); cudaFree(c->multi.tmp_recv[f].d_cells); cudaFree(c->multi.tmp_recv[f].d_off); }
   if (c->cell_gid) cudaFree(c->cell_gid);
   cudaFree(c->p_cell); cudaFree(c->cell_alive); cudaFree(c->cell_type); cudaFree(c->cell_base);
   cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->bin_items); cudaFree(c->wall_nodes); cudaFree(c->scan_tmp);

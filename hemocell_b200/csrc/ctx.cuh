@@ -57,6 +57,10 @@ struct MultiState {
   double* mig_buf = nullptr; size_t mig_cap = 0;
   int64_t* d_cnt = nullptr; double** d_arr = nullptr;
   int64_t migrated_in = 0, migrated_out = 0;
+  int64_t* d_meta = nullptr; size_t meta_cap = 0;  // migration meta messages (ids, types)
+  MultiFace tmp_send[2], tmp_recv[2];              // device lists of the cells leaving / arriving in a rebalance
+  double* d_bbox = nullptr; size_t bbox_cap = 0;   // bounding boxes of the cell slots (multi_rebalance)
+  size_t sync_half = 0;           // receive-buffer half of the velocity sync in flight (multi_sync_pack_post .. wait_unpack_advance)
 };
 
 // NVLink peer-memory transport (csrc/peer.cu): the slab neighbours' lattice buffers, flag words and
@@ -235,6 +239,8 @@ hcg_status spread_sorted(hcg_ctx* c);
 // multi.cu
 hcg_status multi_velocity_sync(hcg_ctx* c);                // = multi_field_sync(c, 0)
 hcg_status multi_velocity_sync_advance(hcg_ctx* c);        // ... fused with the advance of the shared cells
+hcg_status multi_sync_pack_post(hcg_ctx* c);               // the same in two halves: pack + publish ...
+hcg_status multi_sync_wait_unpack_advance(hcg_ctx* c);     // ... wait + unpack + advance
 hcg_status multi_field_sync(hcg_ctx* c, int field);        // 0 = velocity + alive flags, 1 = repulsion force
 hcg_status multi_upload_cell_gid(hcg_ctx* c);
 hcg_status multi_rebalance(hcg_ctx* c, bool initial);
@@ -255,6 +261,8 @@ void comm_destroy(hcg_ctx* c);
 inline bool peer_on(const hcg_ctx* c) { return c->dom.n_ranks > 1 && c->peer.transport == 1 && c->peer.ready; }
 hcg_status peer_setup(hcg_ctx* c);                        // collective over slab neighbours (NCCL must be up)
 hcg_status peer_barrier(hcg_ctx* c);                      // publish "everything before this is stored", wait for both neighbours
+hcg_status peer_post(hcg_ctx* c);                         // ... the two halves as separate launches
+hcg_status peer_wait(hcg_ctx* c);
 hcg_status peer_reserve_sync(hcg_ctx* c, size_t doubles_left, size_t doubles_right, bool* changed);
 void peer_destroy(hcg_ctx* c);
 // preinlet.cu

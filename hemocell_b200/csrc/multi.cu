@@ -245,16 +245,8 @@ hcg_status multi_velocity_sync(hcg_ctx* c) { return multi_field_sync(c, 0); }
 
 // velocity sync of the shared cells + their advance (the step's syncEnvelopes + advanceParticles for the cells a neighbour
 // also holds).  Peer transport: pack (both faces) -> flag barrier -> unpack + advance; otherwise the separate kernels.
-hcg_status multi_velocity_sync_advance(hcg_ctx* c) {
-  if (c->dom.n_ranks == 1) return HCG_OK;
+static hcg_status sync_faces(hcg_ctx* c, SyncFace f[2], size_t half) {
   MultiState& m = c->multi;
-  hcg_status s;
-  if (!peer_on(c)) {
-    if ((s = multi_field_sync(c, 0))) return s;
-    return ibm_advance_shared(c);
-  }
-  const size_t half = (size_t)(c->peer.sync_count++ & 1ULL);
-  SyncFace f[2];
   for (int k = 0; k < 2; k++) {
     const bool on = m.face[k].n > 0 && c->peer.link[k].rank >= 0;
     f[k].cells = m.face[k].d_cells; f[k].off = m.face[k].d_off; f[k].n = on ? m.face[k].n : 0; f[k].total = m.face[k].total;
@@ -265,13 +257,27 @@ hcg_status multi_velocity_sync_advance(hcg_ctx* c) {
     const size_t span = (size_t)m.face[k].n + 3*(size_t)m.face[k].total;
     f[k].send = dst + half*span; f[k].recv = c->peer.sync_recv[k] + half*span;
   }
+  return HCG_OK;
+}
+// pack the shared cells' velocities (both faces) into the neighbours' receive buffers and publish them; the caller may put
+// independent work (the interpolation of the unshared cells) before multi_sync_wait_unpack_advance
+hcg_status multi_sync_pack_post(hcg_ctx* c) {
+  c->multi.sync_half = (size_t)(c->peer.sync_count++ & 1ULL);
+  SyncFace f[2];
+  hcg_status s = sync_faces(c, f, c->multi.sync_half); if (s) return s;
   const int nblocks = f[0].n + f[1].n;
   if (nblocks > 0) {
     k_pack_sync2<<<nblocks, 256, 0, c->stream>>>(f[0], f[1], c->cell_base, c->cell_alive, c->pos[0], c->vel[0], c->vel[1], c->vel[2],
                                                  c->dom.nx, c->dom.periodic[0], c->x0, c->nxl);
     KERNEL_CHECK(c);
   }
-  if ((s = peer_barrier(c))) return s;
+  return peer_post(c);
+}
+hcg_status multi_sync_wait_unpack_advance(hcg_ctx* c) {
+  hcg_status s = peer_wait(c); if (s) return s;
+  SyncFace f[2];
+  if ((s = sync_faces(c, f, c->multi.sync_half))) return s;
+  const int nblocks = f[0].n + f[1].n;
   if (nblocks > 0) {
     IbmArgs a;
     a.nx = c->dom.nx; a.ny = c->dom.ny; a.nz = c->dom.nz; a.px = c->dom.periodic[0]; a.py = c->dom.periodic[1]; a.pz = c->dom.periodic[2];
@@ -281,6 +287,16 @@ hcg_status multi_velocity_sync_advance(hcg_ctx* c) {
     KERNEL_CHECK(c);
   }
   return HCG_OK;
+}
+hcg_status multi_velocity_sync_advance(hcg_ctx* c) {
+  if (c->dom.n_ranks == 1) return HCG_OK;
+  hcg_status s;
+  if (!peer_on(c)) {
+    if ((s = multi_field_sync(c, 0))) return s;
+    return ibm_advance_shared(c);
+  }
+  if ((s = multi_sync_pack_post(c))) return s;
+  return multi_sync_wait_unpack_advance(c);
 }
 
 // per-vertex swap of a particle field of the shared cells: the rank that OWNS a vertex is authoritative.
@@ -356,12 +372,16 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
   std::vector<double> bbox(6*(size_t)std::max<int64_t>(nc, 1));
   std::vector<uint8_t> alive(std::max<int64_t>(nc, 1));
   if (nc) {
-    double* d_bbox;
-    CUDA_TRY(c, cudaMalloc(&d_bbox, sizeof(double)*6*nc));
-    if ((s = mech_bbox(c, d_bbox))) return s;
-    CUDA_TRY(c, cudaMemcpy(bbox.data(), d_bbox, sizeof(double)*6*nc, cudaMemcpyDeviceToHost));
-    CUDA_TRY(c, cudaMemcpy(alive.data(), c->cell_alive, nc, cudaMemcpyDeviceToHost));
-    cudaFree(d_bbox);
+    if (m.bbox_cap < (size_t)nc) {
+      if (m.d_bbox) cudaFree(m.d_bbox);
+      m.d_bbox = nullptr; m.bbox_cap = 0;
+      CUDA_TRY(c, cudaMalloc(&m.d_bbox, sizeof(double)*6*(size_t)nc));
+      m.bbox_cap = (size_t)nc;
+    }
+    if ((s = mech_bbox(c, m.d_bbox))) return s;
+    CUDA_TRY(c, cudaMemcpyAsync(bbox.data(), m.d_bbox, sizeof(double)*6*nc, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(alive.data(), c->cell_alive, nc, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   }
   std::vector<double> lo(nc), hi(nc);
   for (int64_t i = 0; i < nc; i++) { lo[i] = bbox[6*i]; hi[i] = bbox[6*i+1]; }
@@ -404,14 +424,26 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
   // meta
   std::vector<int64_t> meta_send[2], meta_recv[2];
   int64_t *d_ms[2] = {nullptr, nullptr}, *d_mr[2] = {nullptr, nullptr};
+  {
+    // scratch of the migration messages lives across calls (no cudaMalloc / cudaFree - a device-wide sync - per rebalance)
+    size_t want = 0;
+    for (int f = 0; f < 2; f++) want += 2*send[f].size() + 2*(size_t)(has[f] ? n_recv[f] : 0);
+    if (m.meta_cap < want) {
+      if (m.d_meta) cudaFree(m.d_meta);
+      m.d_meta = nullptr; m.meta_cap = 0;
+      CUDA_TRY(c, cudaMalloc(&m.d_meta, sizeof(int64_t)*(want + want/2 + 256)));
+      m.meta_cap = want + want/2 + 256;
+    }
+  }
+  size_t meta_at = 0;
   for (int f = 0; f < 2; f++) {
     for (int32_t sl : send[f]) { meta_send[f].push_back(c->h_cell_id[sl]); meta_send[f].push_back(c->h_cell_type[sl]); }
     if (!meta_send[f].empty()) {
-      CUDA_TRY(c, cudaMalloc(&d_ms[f], sizeof(int64_t)*meta_send[f].size()));
+      d_ms[f] = m.d_meta + meta_at; meta_at += meta_send[f].size();
       CUDA_TRY(c, cudaMemcpyAsync(d_ms[f], meta_send[f].data(), sizeof(int64_t)*meta_send[f].size(), cudaMemcpyHostToDevice, c->stream));
     }
     meta_recv[f].resize(2*(size_t)(has[f] ? n_recv[f] : 0));
-    if (!meta_recv[f].empty()) CUDA_TRY(c, cudaMalloc(&d_mr[f], sizeof(int64_t)*meta_recv[f].size()));
+    if (!meta_recv[f].empty()) { d_mr[f] = m.d_meta + meta_at; meta_at += meta_recv[f].size(); }
   }
   if ((s = neighbour_exchange(c, d_ms[0], 8*meta_send[0].size(), d_ms[1], 8*meta_send[1].size(),
                               d_mr[1], 8*meta_recv[1].size(), d_mr[0], 8*meta_recv[0].size()))) return s;
@@ -419,7 +451,7 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
     if (!meta_recv[f].empty()) CUDA_TRY(c, cudaMemcpyAsync(meta_recv[f].data(), d_mr[f], 8*meta_recv[f].size(), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   // payload
-  MultiFace tmp_send[2], tmp_recv[2];
+  MultiFace* tmp_send = m.tmp_send; MultiFace* tmp_recv = m.tmp_recv;      // device lists reused across calls
   std::vector<int32_t> arrive[2];
   for (int f = 0; f < 2; f++) {
     for (size_t k = 0; k < meta_recv[f].size()/2; k++) {
@@ -465,10 +497,6 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
     KERNEL_CHECK(c);
   }
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  for (int f = 0; f < 2; f++) {
-    cudaFree(d_ms[f]); cudaFree(d_mr[f]);
-    cudaFree(tmp_send[f].d_cells); cudaFree(tmp_send[f].d_off); cudaFree(tmp_recv[f].d_cells); cudaFree(tmp_recv[f].d_off);
-  }
   m.migrated_in += (int64_t)arrive[0].size() + (int64_t)arrive[1].size();
   m.migrated_out += (int64_t)send[0].size() + (int64_t)send[1].size();
   // 4. shared lists, sorted by global cell id so that both holders pack in the same order
@@ -497,9 +525,16 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
   }
   // peer transport: receive buffers sized for the new lists, mappings re-published (collective, cheap)
   if (c->peer.transport == 1) {
-    if ((s = peer_reserve_sync(c, 2*((size_t)m.face[0].n + 3*(size_t)m.face[0].total), 2*((size_t)m.face[1].n + 3*(size_t)m.face[1].total), nullptr))) return s;
-    if ((s = peer_setup(c))) return s;
-    if (!c->peer.ready) return hcg_fail(c, HCG_ERR_STATE, "peer transport: re-mapping the neighbours' buffers failed after a rebalance");
+    // the mappings are re-published only when some rank's receive buffer was outgrown (they carry 50 % headroom): one small
+    // reduction instead of the IPC-handle exchange on every rebalance
+    bool changed = false;
+    if ((s = peer_reserve_sync(c, 2*((size_t)m.face[0].n + 3*(size_t)m.face[0].total), 2*((size_t)m.face[1].n + 3*(size_t)m.face[1].total), &changed))) return s;
+    int keep = (changed || !c->peer.ready) ? 0 : 1;
+    if ((s = comm_allreduce_min_host(c, &keep))) return s;
+    if (!keep) {
+      if ((s = peer_setup(c))) return s;
+      if (!c->peer.ready) return hcg_fail(c, HCG_ERR_STATE, "peer transport: re-mapping the neighbours' buffers failed after a rebalance");
+    }
   }
   return HCG_OK;
 }

@@ -55,6 +55,28 @@ __global__ void k_peer_barrier(unsigned long long* left_word, unsigned long long
   }
 }
 
+// the two halves of k_peer_barrier as separate launches, so that independent work can sit between "my stores are published"
+// and "the neighbours' stores have arrived"
+__global__ void k_peer_post(unsigned long long* left_word, unsigned long long* right_word, unsigned long long epoch) {
+  const int t = threadIdx.x;
+  if (t > 1) return;
+  unsigned long long* out = t == 0 ? left_word : right_word;
+  if (!out) return;
+  __threadfence_system();
+  st_release_sys(out, epoch);
+}
+__global__ void k_peer_wait(bool has_left, bool has_right, const unsigned long long* mine, unsigned long long epoch) {
+  const int t = threadIdx.x;
+  if (t > 1 || !(t == 0 ? has_left : has_right)) return;
+  long long t_start = 0;
+  for (unsigned spin = 0; ld_acquire_sys(mine + t) < epoch; spin++) {
+    if ((spin & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t_start == 0) t_start = now; else if (now - t_start > 120000000000LL) __trap();   // ~60 s: a lost neighbour must not hang the device
+    }
+  }
+}
+
 hcg_status map_pointer(hcg_ctx* c, const PeerBlob& b, int k, void** out) {
   *out = nullptr;
   if (!b.valid[k]) return HCG_OK;
@@ -176,6 +198,25 @@ hcg_status peer_barrier(hcg_ctx* c) {
   unsigned long long* lw = p.link[0].rank >= 0 ? (unsigned long long*)p.link[0].ptr[3] + 1 : nullptr;
   unsigned long long* rw = p.link[1].rank >= 0 ? (unsigned long long*)p.link[1].ptr[3] + 0 : nullptr;
   k_peer_barrier<<<1, 32, 0, c->stream>>>(lw, rw, p.flags, p.epoch);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+
+// split barrier: peer_post publishes "everything before this is stored", peer_wait waits for both neighbours' posts
+hcg_status peer_post(hcg_ctx* c) {
+  PeerState& p = c->peer;
+  if (c->local) return HCG_OK;                           // host-staged communicator: the whole barrier happens in peer_wait
+  p.epoch++;
+  unsigned long long* lw = p.link[0].rank >= 0 ? (unsigned long long*)p.link[0].ptr[3] + 1 : nullptr;
+  unsigned long long* rw = p.link[1].rank >= 0 ? (unsigned long long*)p.link[1].ptr[3] + 0 : nullptr;
+  k_peer_post<<<1, 32, 0, c->stream>>>(lw, rw, p.epoch);
+  KERNEL_CHECK(c);
+  return HCG_OK;
+}
+hcg_status peer_wait(hcg_ctx* c) {
+  PeerState& p = c->peer;
+  if (c->local) return peer_barrier(c);
+  k_peer_wait<<<1, 32, 0, c->stream>>>(p.link[0].rank >= 0, p.link[1].rank >= 0, p.flags, p.epoch);
   KERNEL_CHECK(c);
   return HCG_OK;
 }
