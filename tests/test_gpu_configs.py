@@ -191,3 +191,94 @@ def test_pipe_long_run_observables():
             off += ct.V; k += 1
     U.assert_close(ctx.cells_download(H.P_POS), sim.pos, "positions after 1500 steps", rtol=1e-6, floor=1e-6)
     ctx.close()
+
+
+# ------------------------------------------------------------------ per-operator parity on the reference's own initial positions
+def _operators_vs_oracle(H, par, dims, periodic, fl, types, cells_by_type, body, tag):
+    """one pass of the operators of HemoCell::iterate() (core/hemoCell.cpp:299-376), each checked on its own against the
+    oracle at 1e-12: constitutive forces, spreading, collide-and-stream, interpolation, advance"""
+    nx, ny, nz = dims
+    N = nx * ny * nz
+    dom = O.make_domain(nx, ny, nz, periodic, par.tau)
+    ctx = U.gpu_context(dom, fl, None, body)
+    ctx.set_force_limit(par.f_limit)
+    pos_all, id0 = [], 0
+    for ct, cells in zip(types, cells_by_type):
+        t = U.gpu_add_type(ctx, ct)
+        ctx.add_cells(t, cells, np.arange(cells.shape[0]) + id0)
+        id0 += cells.shape[0]
+        pos_all.append(cells.reshape(-1, 3))
+    pos = np.ascontiguousarray(np.concatenate(pos_all))
+    # constitutive models on the undeformed, rotated cells of the .pos file, then on slightly deformed ones
+    rng = np.random.default_rng(11)
+    pos = pos + 0.02 * rng.standard_normal(pos.shape)
+    ctx.cells_upload(H.P_POS, pos)
+    ctx.op("mechanics", 1, 0)
+    pforce, at = np.zeros_like(pos), 0
+    for ct, cells in zip(types, cells_by_type):
+        n = cells.shape[0] * ct.V
+        f = np.zeros((n, 3))
+        O.mechanics(ct, np.ascontiguousarray(pos[at:at + n]), np.zeros((n, 3)), f)
+        pforce[at:at + n] = f
+        at += n
+    U.assert_close(ctx.cells_download(H.P_FORCE), pforce, f"{tag}: membrane forces")
+    # spreading, collide-and-stream, interpolation, advance
+    frep = np.zeros_like(pos)
+    node_force = np.empty(3 * N)
+    for k in range(3):
+        node_force[k * N:(k + 1) * N] = body[k]
+    pf = pforce.copy()
+    O.spread(dom, fl, pos, pf, frep, par.f_limit, node_force)
+    ctx.op("spread")
+    U.assert_close(ctx.lattice_download(H.LAT_FORCE), node_force, f"{tag}: spread node force")
+    pop = O.init_equilibrium(dom, 1.0, (0.0, 0.0, 0.0))
+    O.collide_and_stream(dom, fl, pop, node_force)
+    ctx.op("collide_stream")
+    U.assert_close(ctx.lattice_download(H.LAT_POP), pop, f"{tag}: populations after collide-and-stream")
+    vel = O.interpolate(dom, fl, pos, pop, node_force)
+    ctx.op("interpolate")
+    U.assert_close(ctx.cells_download(H.P_VEL), vel, f"{tag}: interpolated velocities")
+    pos2 = pos.copy()
+    O.advance(dom, fl, pos2, vel)
+    ctx.op("advance")
+    U.assert_close(ctx.cells_download(H.P_POS), pos2, f"{tag}: advanced positions", rtol=1e-15, floor=0)
+    ctx.close()
+
+
+def _fixture(name):
+    import os
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fixtures", name)
+
+
+def test_operators_on_the_first_cells_of_the_references_performance_testing_positions():
+    """cases/performance_testing/hematocrit_33/RBC.pos (fixtures/): the cells of a 96^3 corner of the unit (the reader's rule keeps
+    those that lie wholly inside), the first 200 of them, fully periodic, tau = 1, body force: every operator against the oracle"""
+    from hemocell_b200 import lib as H
+    par = M.Parameters(dx=0.5e-6, dt=-1.0)
+    n = 96
+    rows = M.read_pos(_fixture("performance_testing_hematocrit_33_RBC.pos"))
+    rows = rows[np.all(rows[:, :3] < n * 0.5 + 4.0, axis=1)]
+    ct = O.rbc_celltype(par)
+    fl = np.zeros(n ** 3, dtype=np.uint8)
+    cells, _ = M.place_cells(ct.verts, rows, par.dx, (n, n, n), fl)
+    cells = cells[:200]
+    assert cells.shape[0] == 200
+    _operators_vs_oracle(H, par, (n, n, n), (1, 1, 1), fl, [ct], [cells], (2e-7, 2e-7, 2e-7), "performance_testing RBC.pos")
+
+
+def test_operators_on_a_sub_box_of_the_references_stenosis_positions():
+    """cases/stenosis/initial_states/Ht20 (fixtures/): RBCs and platelets of the corner x < 60 um, y < 40 um of the channel with
+    its bounce-back y / z faces, x periodic, nu = 3e-6, dt = 1e-8 (tau 0.86): every operator against the oracle"""
+    from hemocell_b200 import lib as H
+    par = M.Parameters(dx=0.5e-6, dt=1e-8, nu_p=3.0e-6)
+    nx, ny, nz = 120, 80, 160
+    fl = np.zeros((nx, ny, nz), dtype=np.uint8)
+    fl[:, :, 0] = 1; fl[:, :, nz - 1] = 1; fl[:, 0, :] = 1; fl[:, ny - 1, :] = 1
+    fl = fl.reshape(-1)
+    rbc, plt = O.rbc_celltype(par), O.plt_celltype(par)
+    rr = M.read_pos(_fixture("stenosis_Ht20_RBC.pos")); pr = M.read_pos(_fixture("stenosis_Ht20_PLT.pos"))
+    rr = rr[(rr[:, 0] < 62) & (rr[:, 1] < 42) & (rr[:, 2] < 82)]; pr = pr[(pr[:, 0] < 62) & (pr[:, 1] < 42) & (pr[:, 2] < 82)]
+    rc, _ = M.place_cells(rbc.verts, rr, par.dx, (nx, ny, nz), fl, 1.0)      # setInitialMinimumDistanceFromSolid("RBC", 1)
+    pc, _ = M.place_cells(plt.verts, pr, par.dx, (nx, ny, nz), fl, 0.0)
+    assert rc.shape[0] > 50 and pc.shape[0] > 3
+    _operators_vs_oracle(H, par, (nx, ny, nz), (1, 0, 0), fl, [rbc, plt], [rc[:150], pc[:20]], (3e-7, 0.0, 0.0), "stenosis Ht20")

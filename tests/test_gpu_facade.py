@@ -394,5 +394,5 @@ def test_user_defined_cell_mechanics_runs_through_particle_mechanics(tmp_path):
             sim.iterate()
         assert int(got[k, 0, 0]) == sim.iter and np.array_equal(got[k, :, 1], np.arange(642))
         U.assert_close(got[k, :, 2:5], sim.pos, f"positions at {sim.iter} (user model on the host path)", rtol=1e-11)
-        U.assert_close(got[k, :, 5:8], sim.pforce, f"forces at {sim.iter} (user model on the host path)", rtol=1e-9, floor=1e-11)
+        U.assert_close(got[k, :, 5:8], sim.pforce, f"forces at {sim.iter} (user model on the host path)", rtol=1e-9, floor=1e-9)   # per-edge sums cancel to ~1e-3 of the largest force
     assert np.abs(got[-1, :, 5:8]).max() > 0
