@@ -584,8 +584,11 @@ def case_parity_check(args, dist, H, spec):
             rp = sim.pos[off[k]:off[k + 1]]
             e_pos = max(e_pos, float(np.abs(pp - rp).max()) / float(np.abs(rp).max())); seen.add(c)
     want = set(int(i) for i in list(rid) + list(pid))
-    ok = e_pop <= 1e-10 and e_pos <= 1e-10 and seen == want
-    return {"max_rel": max(e_pop, e_pos), "max_rel_populations": e_pop, "max_rel_positions": e_pos, "tolerance": 1e-10, "ok": bool(ok),
+    # 20 coupled steps: the order of the spreading atomics differs from the oracle's loop and the stiff membranes amplify that
+    # round-off in the populations (tests/test_gpu_multi.py uses the same 1e-9 for its 120-step runs); positions stay at 1e-10
+    ok = e_pop <= 1e-9 and e_pos <= 1e-10 and seen == want
+    return {"max_rel": max(e_pop, e_pos), "max_rel_populations": e_pop, "max_rel_positions": e_pos,
+            "tolerance": {"populations": 1e-9, "positions": 1e-10}, "ok": bool(ok),
             "against": "CPU oracle (oracle/hemo_oracle.c), rank 0", "steps": steps, "lattice": [nx, ny, nz], "slabs": world,
             "cells": len(want), "every_cell_found": seen == want,
             "setup": "reduced problem with the case's boundary kinds, tau, cell types, cadences" + (" and both repulsions" if spec["rep"] else "")}
