@@ -109,6 +109,35 @@ def pinned_empty(n_doubles):
 _PINNED = []
 
 
+def pinned_empty_f32(n):
+    rt = C.CDLL("libcudart.so.12")
+    ptr = C.c_void_p()
+    rc = rt.cudaHostAlloc(C.byref(ptr), C.c_size_t(4 * max(n, 1)), C.c_uint(0))
+    if rc != 0:
+        raise RuntimeError(f"cudaHostAlloc failed: {rc}")
+    buf = (C.c_float * max(n, 1)).from_address(ptr.value)
+    _PINNED.append((rt, ptr, buf))
+    return np.frombuffer(buf, dtype=np.float32)
+
+
+def bind_to_gpu_numa_node(index):
+    """what `numactl` / the MPI launcher does for the reference: run this rank on the cores next to its GPU, so that its pinned
+    host buffers are allocated on that socket's memory (8 ranks copying at once otherwise meet on one socket's memory controller)"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return 0
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -274,6 +303,7 @@ def run_cuda(args):
         import torch.distributed as dist
         torch.cuda.set_device(args.local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", args.local_rank))
+    numa_cpus = bind_to_gpu_numa_node(args.local_rank)
     par = H.parameters(DX, -1.0)
     pcheck = None if args.no_parity_check else parity_check(args, dist, H, par)
     ct = H.HostCellType(H.MODEL_RBC, H.RBC_FROM_SPHERE, par, H.RBC_MATERIAL)
@@ -349,9 +379,10 @@ def run_cuda(args):
     # (performance_testing.cpp:126-133): cell state H2D, then K x { iterate(); setExternalVector(force) (24 B host argument);
     # cell count of the step D2H into pinned memory, not waited for }, one wait, positions and forces D2H (writeOutput)
     npart = ctx.capacity()[1]
-    out_pos = pinned_empty(3 * npart); out_frc = pinned_empty(3 * npart)
+    out_pos = pinned_empty_f32(3 * npart); out_frc = pinned_empty_f32(3 * npart)   # what writeOutput stores: float32, SI units
     state_host = pinned_empty(3 * npart)          # the particle state as the host holds it (pinned)
     counts = pinned_empty(2 * args.steps)         # 2 int64 per step
+    c_fp = C.POINTER(C.c_float)
     ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), state_host.ctypes.data_as(H.c_dp))
     ctx.set_iteration(0)
     bf = body_force(par["nu_lbm"], UNIT_N)
@@ -363,12 +394,12 @@ def run_cuda(args):
         ctx.set_body_force(bf)                    # setExternalVector after every iterate
         ctx.count_async(counts.ctypes.data + 16 * k)
     ctx.synchronize()
-    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), out_pos.ctypes.data_as(H.c_dp))
-    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_FORCE), out_frc.ctypes.data_as(H.c_dp))
+    ctx._ck(ctx.L.hcg_cells_download_f32(ctx.h, C.c_int32(H.P_POS), C.c_double(DX), out_pos.ctypes.data_as(c_fp)))
+    ctx._ck(ctx.L.hcg_cells_download_f32(ctx.h, C.c_int32(H.P_FORCE), C.c_double(par["df"]), out_frc.ctypes.data_as(c_fp)))
     barrier()
     e2e_ms = max_over_ranks((time.time() - te0) * 1e3)
     h2d = (8 * 3 * npart) / args.steps + 24
-    d2h = (2 * 8 * 3 * npart) / args.steps + 16
+    d2h = (2 * 4 * 3 * npart) / args.steps + 16
     last_count = int(counts.view(np.int64)[2 * (args.steps - 1)])
     if dist is not None:
         import torch
@@ -426,7 +457,8 @@ def run_cuda(args):
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()},
         "e2e": {"value": nodes * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "MLUPS",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                "loop": "cells H2D; K x {iterate, body force, async cell-count D2H}; wait; positions + forces D2H"},
+                "loop": "cell positions H2D (fp64); K x {iterate, body force, async cell-count D2H}; wait; positions + forces D2H as "
+                        "writeOutput stores them (float32, SI)", "cpus_bound_to_gpu_numa_node": numa_cpus},
         "parity_check": pcheck,
         "gpu_launches": launches, "clocks": clocks,
     }
@@ -606,6 +638,7 @@ def run_case(args):
         import torch.distributed as dist
         torch.cuda.set_device(args.local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", args.local_rank))
+    bind_to_gpu_numa_node(args.local_rank)
     spec = case_spec(args.workload, H)
     par = spec["par"]
     if args.repulsion:
@@ -671,7 +704,8 @@ def run_case(args):
     timers = ctx.timers(); ctx.timers_enable(False)
     # end-to-end: the loop of the case file through the C ABI with host buffers (see run_cuda)
     npart = ctx.capacity()[1]
-    state_host = pinned_empty(max(3 * npart, 1)); out_pos = pinned_empty(max(3 * npart, 1)); out_frc = pinned_empty(max(3 * npart, 1))
+    state_host = pinned_empty(max(3 * npart, 1)); out_pos = pinned_empty_f32(3 * npart); out_frc = pinned_empty_f32(3 * npart)
+    c_fp = C.POINTER(C.c_float)
     counts = pinned_empty(2 * args.steps)
     ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), state_host.ctypes.data_as(H.c_dp))
     barrier(); te0 = time.time()
@@ -681,8 +715,8 @@ def run_case(args):
         ctx.set_body_force(spec["body"])
         ctx.count_async(counts.ctypes.data + 16 * k)
     ctx.synchronize()
-    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_POS), out_pos.ctypes.data_as(H.c_dp))
-    ctx.L.hcg_cells_download(ctx.h, C.c_int32(H.P_FORCE), out_frc.ctypes.data_as(H.c_dp))
+    ctx._ck(ctx.L.hcg_cells_download_f32(ctx.h, C.c_int32(H.P_POS), C.c_double(DX), out_pos.ctypes.data_as(c_fp)))
+    ctx._ck(ctx.L.hcg_cells_download_f32(ctx.h, C.c_int32(H.P_FORCE), C.c_double(par["df"]), out_frc.ctypes.data_as(c_fp)))
     barrier()
     e2e_ms = max_over_ranks((time.time() - te0) * 1e3)
     alive = int(counts.view(np.int64)[2 * (args.steps - 1)])
@@ -725,7 +759,7 @@ def run_case(args):
                           "formula": "304 + (264 + 72 + 216/c) N_LSP/N_nodes B/LU (SURVEY 8d)"},
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()},
         "e2e": {"value": nodes * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 8 * 3 * npart / args.steps + 24,
-                "d2h_bytes_per_step": 2 * 8 * 3 * npart / args.steps + 16, "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": 2 * 4 * 3 * npart / args.steps + 16, "ms_per_step": e2e_ms / args.steps},
         "parity_check": pcheck, "gpu_launches": launches, "clocks": clocks}
     ctx.close()
     return line

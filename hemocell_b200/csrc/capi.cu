@@ -57,6 +57,13 @@ __global__ void k_soa_to_aos(const double* __restrict__ x, const double* __restr
   if (i >= n) return;
   out[3*i] = x[i]; out[3*i+1] = y[i]; out[3*i+2] = z[i];
 }
+// particle field as the output writers want it: float32 triples scaled to SI (io/ParticleHdf5IO.cpp writes float datasets)
+__global__ void k_soa_to_aos_f32(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                 float* out, int64_t n, double scale) {
+  const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[3*i] = (float)(x[i]*scale); out[3*i+1] = (float)(y[i]*scale); out[3*i+2] = (float)(z[i]*scale);
+}
 __global__ void k_add_force(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ f,
                             double* fx, double* fy, double* fz, int64_t np) {
   const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
@@ -786,6 +793,19 @@ hcg_status hcg_cells_download(hcg_ctx* c, int32_t field, double* out) {
   k_soa_to_aos<<<nblk(c->np, 256), 256, 0, c->stream>>>(a[0], a[1], a[2], c->staging, c->np);
   KERNEL_CHECK(c);
   CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(double)*3*c->np, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return HCG_OK;
+}
+
+hcg_status hcg_cells_download_f32(hcg_ctx* c, int32_t field, double scale, float* out) {
+  if (!c || !out) return HCG_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->dom.device));
+  if (c->np == 0) return HCG_OK;
+  double* a[3]; hcg_status s = field_arrays(c, field, a); if (s) return s;
+  if ((s = ensure_staging(c, sizeof(float)*3*c->np))) return s;
+  k_soa_to_aos_f32<<<nblk(c->np, 256), 256, 0, c->stream>>>(a[0], a[1], a[2], (float*)c->staging, c->np, scale);
+  KERNEL_CHECK(c);
+  CUDA_TRY(c, cudaMemcpyAsync(out, c->staging, sizeof(float)*3*c->np, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return HCG_OK;
 }

@@ -49,7 +49,7 @@ class HcgTimer(C.Structure):
 SYMBOLS = """hcg_last_error hcg_version hcg_create hcg_device_count hcg_slab hcg_destroy hcg_comm_unique_id hcg_comm_init hcg_comm_init_local
 hcg_lattice_set_flags hcg_lattice_set_bc_velocity hcg_lattice_init_equilibrium hcg_lattice_set_body_force hcg_lattice_set_body_force_field
 hcg_lattice_upload hcg_lattice_download hcg_celltype_add hcg_cells_add hcg_cells_count hcg_cells_count_async hcg_cells_capacity
-hcg_cells_upload hcg_cells_download hcg_cells_info hcg_cells_owned hcg_allreduce hcg_cells_add_force hcg_celltype_set_stiffness
+hcg_cells_upload hcg_cells_download hcg_cells_download_f32 hcg_cells_info hcg_cells_owned hcg_allreduce hcg_cells_add_force hcg_celltype_set_stiffness
 hcg_set_force_limit hcg_set_timescales hcg_set_material_timescale hcg_set_repulsion hcg_set_wall_repulsion
 hcg_set_spread_mode hcg_set_exchange hcg_set_transport hcg_exchange_stats hcg_set_iteration hcg_get_iteration hcg_iterate hcg_iterate_async hcg_fluid_warmup hcg_op_repulsion hcg_op_wall_repulsion
 hcg_op_spread hcg_op_collide_stream hcg_op_interpolate hcg_op_sync hcg_op_advance hcg_op_mechanics
