@@ -366,8 +366,12 @@ k_moment_tile(const double* __restrict__ Win, const double* __restrict__ Fin, do
     mbar_wait(full + (lx & 1), (uint32_t)(((lx - x_lo + 1) >> 1) & 1));   // plane lx has landed (the copies of plane lx + 1 may still fly)
     double c0 = 0, c1 = 0, c2 = 0;
     if (halo_ok) {
+      // the records lie 32 bytes apart: lanes 4..7 of every group of eight read their two 16-byte halves in the opposite
+      // order, so that each 128-bit load of a quarter-warp touches all 32 banks once (no 2-way conflict)
       const double2* sl = reinterpret_cast<const double2*>(ring + (size_t)(lx & 1)*2*HN*4 + (size_t)t*4);
-      const double2 wa = sl[0], wb = sl[1], fa = sl[2*HN], fb = sl[2*HN + 1];
+      const int h = (t >> 2) & 1;
+      const double2 w_first = sl[h], w_second = sl[1 - h], f_first = sl[2*HN + h], f_second = sl[2*HN + 1 - h];
+      const double2 wa = h ? w_second : w_first, wb = h ? w_first : w_second, fa = h ? f_second : f_first, fb = h ? f_first : f_second;
       c0 = fa.x; c1 = fa.y; c2 = fb.x;
       double p[19];
       tau1_pops_fast(wa.x, wa.y, wb.x, wb.y, fa.x, fa.y, fb.x, p);
