@@ -806,7 +806,7 @@ void HemoCell::saveCheckPoint() {
   const int64_t Nl = (int64_t)g->nxl()*g->ny*g->nz;
   int64_t nc = 0, np = 0;
   ck(c, hcg_cells_capacity(c, &nc, &np), "hcg_cells_capacity");
-  const int64_t hdr[6] = {0x48434731, (int64_t)iter, Nl, nc, np, (int64_t)cellfields->size()};
+  const int64_t hdr[8] = {0x48434732, (int64_t)iter, Nl, nc, np, (int64_t)cellfields->size(), (int64_t)plb::global::mpi().getSize(), (int64_t)g->x0()};
   f.write((const char*)hdr, sizeof(hdr));
   std::vector<double> buf((size_t)std::max<int64_t>(19*Nl, 3*np));
   ck(c, hcg_lattice_download(c, HCG_LAT_POP, buf.data()), "download"); f.write((const char*)buf.data(), 8*19*Nl);
@@ -849,9 +849,10 @@ void HemoCell::loadCheckPoint() {
   const std::string base = global.checkpointDirectory + "/rank" + std::to_string(plb::global::mpi().getRank()) + ".bin";
   std::ifstream f(base, std::ios::binary);
   if (!f) fatal("(HemoCell) cannot open checkpoint data " + base);
-  int64_t hdr[6]; f.read((char*)hdr, sizeof(hdr));
+  int64_t hdr[8]; f.read((char*)hdr, sizeof(hdr));
   const int64_t Nl = (int64_t)g->nxl()*g->ny*g->nz;
-  if (hdr[0] != 0x48434731 || hdr[2] != Nl || hdr[5] != (int64_t)cellfields->size()) fatal("(HemoCell) checkpoint does not match this domain / cell types");
+  if (!f || hdr[0] != 0x48434732 || hdr[2] != Nl || hdr[5] != (int64_t)cellfields->size() || hdr[6] != (int64_t)plb::global::mpi().getSize() || hdr[7] != (int64_t)g->x0())
+    fatal("(HemoCell) checkpoint does not match this domain / cell types / number of ranks (a restart needs the decomposition it was written with)");
   const int64_t nc = hdr[3], np = hdr[4];
   std::vector<double> pop(19*Nl), frc(3*Nl);
   f.read((char*)pop.data(), 8*19*Nl); f.read((char*)frc.data(), 8*3*Nl);
