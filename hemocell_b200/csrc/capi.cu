@@ -168,6 +168,9 @@ hcg_status do_spread(hcg_ctx* c) {
   if (!c->perm_valid || c->iter % c->perm_every == 0) {
     hcg_status s = spread_sorted_rebuild(c); if (s) return s;
     c->perm_valid = true;
+    // lattices with walls: which cells cannot meet a non-fluid node until the next rebuild (iterate() only: the cadence is
+    // what bounds the drift; the per-operator entry points leave every cell checked)
+    if (c->in_iterate && (s = ibm_far_classify(c, c->perm_every))) return s;
   }
   return spread_sorted(c);
 }
@@ -319,6 +322,7 @@ void hcg_destroy(hcg_ctx* c) {
   cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); if (c->F0) cudaFree(c->F0); if (c->bcn) cudaFree(c->bcn); if (c->W2) cudaFree(c->W2); if (c->F2) cudaFree(c->F2); if (c->d_qsets) cudaFree(c->d_qsets); cudaFree(c->flags); cudaFree(c->d_bc);
   if (c->rho) cudaFree(c->rho);
   if (c->count_dev) cudaFree(c->count_dev); if (c->count_typeV) cudaFree(c->count_typeV);
+  if (c->wall_coarse) cudaFree(c->wall_coarse); if (c->cell_far) cudaFree(c->cell_far); if (c->far_typeV) cudaFree(c->far_typeV);
   if (c->fused_done) cudaFree(c->fused_done);
   for (int k = 0; k < 3; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->frc[k]); cudaFree(c->frep[k]); }
   for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) if (c->comp[k][d]) cudaFree(c->comp[k][d]);
@@ -403,7 +407,7 @@ hcg_status hcg_lattice_set_flags(hcg_ctx* c, const uint8_t* flags) {
   k_pad_flags<<<nblk(c->Nl, 256), 256, 0, c->stream>>>((const uint8_t*)c->staging, c->flags, c->Nl, c->P);
   KERNEL_CHECK(c);
   s = exchange_flags(c); if (s) return s;
-  c->wall_built = false;
+  c->wall_built = false; c->wall_coarse_valid = false; c->far_steps_left = 0;
   return refresh_nonfluid(c);                   // (collective for n_ranks > 1: every rank sets its flags)
 }
 
@@ -694,7 +698,7 @@ hcg_status hcg_cells_add(hcg_ctx* c, int32_t ctype, int64_t n_cells, const int64
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->np = new_p; c->ncells = new_c; c->cap_p = new_p; c->cap_c = new_c;
   if (c->multi.d_arr) { cudaFree(c->multi.d_arr); c->multi.d_arr = nullptr; }     // array pointers changed
-  c->perm_valid = false; c->cell_gid_dirty = true;
+  c->perm_valid = false; c->cell_gid_dirty = true; c->far_steps_left = 0;
   if (c->dom.n_ranks > 1 && (s = multi_rebalance(c, true))) return s;            // builds the shared lists
   if (c->bin_items) { cudaFree(c->bin_items); cudaFree(c->bin_count); cudaFree(c->bin_start); cudaFree(c->scan_tmp);
                       c->bin_items = c->bin_count = c->bin_start = nullptr; c->scan_tmp = nullptr; }
@@ -780,6 +784,7 @@ hcg_status hcg_cells_upload(hcg_ctx* c, int32_t field, const double* in) {
   CUDA_TRY(c, cudaMemcpyAsync(c->staging, in, sizeof(double)*3*c->np, cudaMemcpyHostToDevice, c->stream));
   k_aos_to_soa<<<nblk(c->np, 256), 256, 0, c->stream>>>(c->staging, a[0], a[1], a[2], c->np);
   KERNEL_CHECK(c);
+  if (field == HCG_P_POS) c->far_steps_left = 0;        // positions set from outside: every cell is checked against the walls again
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return HCG_OK;
 }
@@ -862,7 +867,7 @@ hcg_status hcg_set_moment_only(hcg_ctx* c, int32_t on) {
 }
 hcg_status hcg_set_spread_mode(hcg_ctx* c, int32_t mode, int32_t resort_every) {
   if (!c || mode < 0 || mode > 1 || resort_every < 1) return HCG_ERR_ARG;
-  c->spread_mode = mode; c->perm_every = resort_every; c->perm_valid = false;
+  c->spread_mode = mode; c->perm_every = resort_every; c->perm_valid = false; c->far_steps_left = 0;
   return HCG_OK;
 }
 hcg_status hcg_set_exchange(hcg_ctx* c, double margin_lu, int32_t sync_every, double slack) {
@@ -895,7 +900,9 @@ hcg_status hcg_iterate(hcg_ctx* c, int64_t n) {
   // sanityCheck (core/hemoCell.cpp:600-627): material / repulsion cadences are multiples of the velocity cadence
   for (auto& t : c->types) if (t.timescale % c->ts_vel) return hcg_fail(c, HCG_ERR_STATE, "material timescale must be a multiple of the velocity timescale");
   if (c->rep_on && c->ts_rep % c->ts_vel) return hcg_fail(c, HCG_ERR_STATE, "repulsion timescale must be a multiple of the velocity timescale");
-  for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) return s; }
+  c->in_iterate = true;
+  for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) { c->in_iterate = false; return s; } }
+  c->in_iterate = false;
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return HCG_OK;
 }
@@ -905,7 +912,9 @@ hcg_status hcg_iterate_async(hcg_ctx* c, int64_t n) {
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
   for (auto& t : c->types) if (t.timescale % c->ts_vel) return hcg_fail(c, HCG_ERR_STATE, "material timescale must be a multiple of the velocity timescale");
   if (c->rep_on && c->ts_rep % c->ts_vel) return hcg_fail(c, HCG_ERR_STATE, "repulsion timescale must be a multiple of the velocity timescale");
-  for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) return s; }
+  c->in_iterate = true;
+  for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) { c->in_iterate = false; return s; } }
+  c->in_iterate = false;
   return HCG_OK;
 }
 
@@ -916,7 +925,9 @@ hcg_status hcg_iterate_timed(hcg_ctx* c, int64_t n, double* ms_out) {
   CUDA_TRY(c, cudaEventCreate(&a)); CUDA_TRY(c, cudaEventCreate(&b));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   CUDA_TRY(c, cudaEventRecord(a, c->stream));
-  for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) return s; }
+  c->in_iterate = true;
+  for (int64_t i = 0; i < n; i++) { hcg_status s = step(c); if (s) { c->in_iterate = false; return s; } }
+  c->in_iterate = false;
   CUDA_TRY(c, cudaEventRecord(b, c->stream));
   CUDA_TRY(c, cudaEventSynchronize(b));
   float ms = 0; CUDA_TRY(c, cudaEventElapsedTime(&ms, a, b));

@@ -117,6 +117,11 @@ struct hcg_ctx {
   bool has_iobc = false;       // Zou-He velocity / pressure nodes present (flags >= HCG_ZH_VEL_XN)
   double* bcn = nullptr;       // their per-node values, AoS [n][4] = (u_x, u_y, u_z, rho) over the padded slab; allocated on first use
   bool real_nonfluid = false;  // any non-fluid flag on this rank's real nodes (has_nonfluid also covers the ghost planes)
+  // lattices with walls: cells with no non-fluid node within reach skip the flag look-ups of the IBM kernels (ibm.cu: far_classify)
+  uint8_t* wall_coarse = nullptr; int wc_dim[3] = {0, 0, 0}; bool wall_coarse_valid = false;   // 8^3 blocks of the padded slab holding a non-fluid node
+  int* far_typeV = nullptr; int far_ntypes = -1;
+  bool in_iterate = false;     // inside hcg_iterate*: the step cadence bounds how far a cell can drift between classifications
+  uint8_t* cell_far = nullptr; int64_t cell_far_cap = 0; int far_steps_left = 0;               // per cell slot; valid for far_steps_left more advances
   // particles
   int64_t np, ncells, cap_p, cap_c;
   double *pos[3], *vel[3], *frc[3], *frep[3];
@@ -219,6 +224,8 @@ hcg_status lat_bcn_ensure(hcg_ctx* c);
 hcg_status lat_bcn_scatter(hcg_ctx* c, int64_t n, const int64_t* idx_dev, const double* val_dev, bool keep_rho, cudaStream_t st);
 hcg_status lat_node_velocity(hcg_ctx* c, int64_t n, const int64_t* idx_dev, double* out_dev, cudaStream_t st);   // out [n][4] = (u, rho)
 // ibm.cu
+hcg_status ibm_far_classify(hcg_ctx* c, int valid_steps);  // which cells cannot meet a non-fluid node during the next valid_steps advances
+inline const uint8_t* ibm_far(const hcg_ctx* c) { return (c->far_steps_left > 0) ? c->cell_far : nullptr; }
 hcg_status ibm_spread(hcg_ctx* c);
 hcg_status ibm_interpolate(hcg_ctx* c);
 hcg_status ibm_advance(hcg_ctx* c);

@@ -91,7 +91,7 @@ __host__ __device__ __forceinline__ void ld_node4(const double* p, double& a, do
 // non-fluid nodes.  Returns false when a candidate node is not addressable from this rank (velocity left alone).
 template <bool CHECK_FLAGS>
 __host__ __device__ __forceinline__ bool interp_vertex(const IbmArgs& a, const uint8_t* __restrict__ flags, const double* __restrict__ U,
-                                              double px, double py, double pz, double& v0, double& v1, double& v2) {
+                                              double px, double py, double pz, double& v0, double& v1, double& v2, bool check = true) {
   const int bx = (int)floor(px), by = (int)floor(py), bz = (int)floor(pz);
   double ax[2], ay[2], az[2]; int64_t jx[2]; int jy[2], jz[2];
   bool addressable = true;
@@ -117,7 +117,7 @@ __host__ __device__ __forceinline__ bool interp_vertex(const IbmArgs& a, const u
     const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
     w[c] = ax[dx]*ay[dy]*az[dz];
     if (w[c] == 0.0) continue;
-    if (CHECK_FLAGS && flags[jx[dx] + jy[dy] + jz[dz]] != HCG_FLUID) { w[c] = 0.0; continue; }
+    if (CHECK_FLAGS && check && flags[jx[dx] + jy[dy] + jz[dz]] != HCG_FLUID) { w[c] = 0.0; continue; }
     total += w[c];
   }
   const double coeff = 1.0/total;

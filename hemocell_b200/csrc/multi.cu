@@ -507,7 +507,7 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
     std::sort(list.begin(), list.end(), [&](int32_t a, int32_t b) { return c->h_cell_id[a] < c->h_cell_id[b]; });
     if ((s = upload_list(c, m.face[f], list))) return s;
   }
-  c->cell_gid_dirty = true;
+  c->cell_gid_dirty = true; c->far_steps_left = 0;       // slots changed hands: every cell is checked against the walls until the next classification
   // union list + per-slot flag: the step advances unshared cells in the interpolation pass and the
   // shared ones after the velocity sync
   {

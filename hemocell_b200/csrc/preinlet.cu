@@ -240,7 +240,7 @@ hcg_status hcg_preinlet_apply_cells(hcg_ctx* c, int32_t axis, double period, con
   CUDA_TRY(c, cudaSetDevice(pre->dom.device));
   cudaFree(d_src); cudaFree(d_off_s); cudaFree(d_buf_s);
   CUDA_TRY(c, cudaSetDevice(c->dom.device));
-  c->perm_valid = false; c->cell_gid_dirty = true;
+  c->perm_valid = false; c->cell_gid_dirty = true; c->far_steps_left = 0;
   p->handed += n;
   if (n_added) *n_added = n;
   return HCG_OK;

@@ -110,11 +110,12 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
                 const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                 double* fx, double* fy, double* fz,
                 const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
-                const uint16_t* __restrict__ perm, double* __restrict__ F) {
+                const uint16_t* __restrict__ perm, double* __restrict__ F, const uint8_t* __restrict__ far) {
   extern __shared__ __align__(16) double sm[];
   const int V = a.V;
   const int64_t cell = a.first_cell + blockIdx.x;
   if (!alive[cell]) return;
+  const bool chk = !(CHECK_FLAGS && far && far[cell]);   // no non-fluid node within this cell's reach: skip the flag look-ups
   const int64_t base = a.first_particle + (int64_t)blockIdx.x*V;
   double* PX = sm; double* PY = PX + V; double* PZ = PY + V;      // position
   double* CO = PZ + V;                                             // 1 / sum of the admitted raw weights
@@ -179,7 +180,7 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
       const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
       const double w = ax[dx]*ay[dy]*az[dz];
       if (w == 0.0) continue;
-      if (CHECK_FLAGS && flags[jx[dx] + jy[dy] + jz[dz]] != HCG_FLUID) continue;
+      if (CHECK_FLAGS && chk && flags[jx[dx] + jy[dy] + jz[dz]] != HCG_FLUID) continue;
       total += w;
       if (realx[dx]) mask |= 1u << c;            // ghost planes count in the normalisation only
     }
@@ -271,7 +272,7 @@ hcg_status spread_sorted(hcg_ctx* c) {
 #define SP_LAUNCH(T, C, B) do { \
       CUDA_TRY(c, cudaFuncSetAttribute(k_spread_sorted<T, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_spread_sorted<T, C, B><<<(unsigned)th.n_cells, T, smem, c->stream>>>(a, c->flags, c->cell_alive, c->pos[0], c->pos[1], c->pos[2], \
-          c->frc[0], c->frc[1], c->frc[2], c->frep[0], c->frep[1], c->frep[2], th.perm, c->F); } while (0)
+          c->frc[0], c->frc[1], c->frc[2], c->frep[0], c->frep[1], c->frep[2], th.perm, c->F, ibm_far(c)); } while (0)
     if (V >= 256 && bulk) { if (chk) SP_LAUNCH(256, true, true); else SP_LAUNCH(256, false, true); }
     else if (V >= 256) { if (chk) SP_LAUNCH(256, true, false); else SP_LAUNCH(256, false, false); }
     else { if (chk) SP_LAUNCH(64, true, false); else SP_LAUNCH(64, false, false); }
