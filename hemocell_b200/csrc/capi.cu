@@ -230,8 +230,8 @@ hcg_status step(hcg_ctx* c) {
   if (have_p && (s = do_mechanics(c, false, false))) return s;
   c->f_clean = true;            // the collision (or moments) kernel of this step wrote the reset value on every node
   c->iter++;
-  if (c->dom.n_ranks > 1 && c->iter % c->multi.sync_every == 0) {
-    OpTimer t(c, "syncEnvelopes"); if ((s = multi_rebalance(c, false))) return s;
+  if (c->dom.n_ranks > 1 && c->iter >= c->multi.next_sync_iter) {
+    OpTimer t(c, "syncEnvelopes (membership + migration)"); if ((s = multi_rebalance(c, false))) return s;
   }
   return HCG_OK;
 }
@@ -322,12 +322,12 @@ void hcg_destroy(hcg_ctx* c) {
   cudaFree(c->g[0]); cudaFree(c->g[1]); cudaFree(c->F); cudaFree(c->U); if (c->W) cudaFree(c->W); if (c->F0) cudaFree(c->F0); if (c->bcn) cudaFree(c->bcn); if (c->W2) cudaFree(c->W2); if (c->F2) cudaFree(c->F2); if (c->d_qsets) cudaFree(c->d_qsets); cudaFree(c->flags); cudaFree(c->d_bc);
   if (c->rho) cudaFree(c->rho);
   if (c->count_dev) cudaFree(c->count_dev); if (c->count_typeV) cudaFree(c->count_typeV);
-  if (c->wall_coarse) cudaFree(c->wall_coarse); if (c->cell_far) cudaFree(c->cell_far); if (c->far_typeV) cudaFree(c->far_typeV);
+  if (c->wall_coarse) cudaFree(c->wall_coarse); if (c->cell_far) cudaFree(c->cell_far); if (c->far_typeV) cudaFree(c->far_typeV); if (c->bbox_typeV) cudaFree(c->bbox_typeV);
   if (c->fused_done) cudaFree(c->fused_done);
   for (int k = 0; k < 3; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->frc[k]); cudaFree(c->frep[k]); }
   for (int k = 0; k < 6; k++) for (int d = 0; d < 3; d++) if (c->comp[k][d]) cudaFree(c->comp[k][d]);
   if (c->multi.d_cell_shared) cudaFree(c->multi.d_cell_shared);
-  if (c->multi.d_meta) cudaFree(c->multi.d_meta); if (c->multi.d_bbox) cudaFree(c->multi.d_bbox);
+  if (c->multi.d_meta) cudaFree(c->multi.d_meta); if (c->multi.d_bbox) cudaFree(c->multi.d_bbox); if (c->multi.d_vmax) cudaFree(c->multi.d_vmax);
   for (int f = 0; f < 2; f++) { cudaFree(c->multi.tmp_send[f].d_cells); cudaFree(c->multi.tmp_send[f].d_off); cudaFree(c->multi.tmp_recv[f].d_cells); cudaFree(c->multi.tmp_recv[f].d_off); }
   if (c->cell_gid) cudaFree(c->cell_gid);
   cudaFree(c->p_cell); cudaFree(c->cell_alive); cudaFree(c->cell_type); cudaFree(c->cell_base);
@@ -891,7 +891,7 @@ hcg_status hcg_exchange_stats(hcg_ctx* c, int64_t* shared_left, int64_t* shared_
   if (migrated_out) *migrated_out = c->multi.migrated_out;
   return HCG_OK;
 }
-hcg_status hcg_set_iteration(hcg_ctx* c, int64_t it) { if (!c || it < 0) return HCG_ERR_ARG; c->iter = it; return HCG_OK; }
+hcg_status hcg_set_iteration(hcg_ctx* c, int64_t it) { if (!c || it < 0) return HCG_ERR_ARG; c->iter = it; c->multi.next_sync_iter = it + c->multi.sync_every; return HCG_OK; }
 hcg_status hcg_get_iteration(hcg_ctx* c, int64_t* it) { if (!c || !it) return HCG_ERR_ARG; *it = c->iter; return HCG_OK; }
 
 hcg_status hcg_iterate(hcg_ctx* c, int64_t n) {
@@ -1003,7 +1003,8 @@ hcg_status hcg_cells_bbox(hcg_ctx* c, double* bbox) {
   if (c->ncells == 0) return HCG_OK;
   hcg_status s = ensure_staging(c, sizeof(double)*6*c->ncells); if (s) return s;
   if ((s = mech_bbox(c, c->staging))) return s;
-  CUDA_TRY(c, cudaMemcpy(bbox, c->staging, sizeof(double)*6*c->ncells, cudaMemcpyDeviceToHost));
+  CUDA_TRY(c, cudaMemcpyAsync(bbox, c->staging, sizeof(double)*6*c->ncells, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return HCG_OK;
 }
 

@@ -155,24 +155,24 @@ hcg_status comm_allreduce_f64(hcg_ctx* c, double* dev, size_t n, int op) {
   return HCG_OK;
 }
 
-// host value, minimum over the ranks (set-up agreement)
-hcg_status comm_allreduce_min_host(hcg_ctx* c, int* value) {
-  if (c->dom.n_ranks == 1) return HCG_OK;
+// host values, element-wise minimum over the ranks (set-up agreement, rebalance decisions)
+hcg_status comm_allreduce_min_host(hcg_ctx* c, int* value, int n) {
+  if (c->dom.n_ranks == 1 || n <= 0) return HCG_OK;
   if (c->local) {
-    std::vector<double> v(1, (double)*value);
+    std::vector<double> v(value, value + n);
     hcg_status s = local_allreduce(c, v, 1); if (s) return s;
-    *value = (int)v[0];
+    for (int k = 0; k < n; k++) value[k] = (int)v[k];
     return HCG_OK;
   }
   if (!c->nccl) return hcg_fail(c, HCG_ERR_STATE, "allreduce: hcg_comm_init first");
-  int* d = nullptr;
-  CUDA_TRY(c, cudaMalloc(&d, sizeof(int)));
-  CUDA_TRY(c, cudaMemcpyAsync(d, value, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  ncclResult_t rc = ncclAllReduce(d, d, 1, ncclInt, ncclMin, (ncclComm_t)c->nccl, c->stream);
-  if (rc != ncclSuccess) { cudaFree(d); return hcg_fail(c, HCG_ERR_NCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(rc)); }
-  CUDA_TRY(c, cudaMemcpyAsync(value, d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (!c->comm_scratch) CUDA_TRY(c, cudaMalloc(&c->comm_scratch, sizeof(int)*16));
+  if (n > 16) return hcg_fail(c, HCG_ERR_ARG, "allreduce: at most 16 values");
+  int* d = c->comm_scratch;
+  CUDA_TRY(c, cudaMemcpyAsync(d, value, sizeof(int)*n, cudaMemcpyHostToDevice, c->stream));
+  ncclResult_t rc = ncclAllReduce(d, d, n, ncclInt, ncclMin, (ncclComm_t)c->nccl, c->stream);
+  if (rc != ncclSuccess) return hcg_fail(c, HCG_ERR_NCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(rc));
+  CUDA_TRY(c, cudaMemcpyAsync(value, d, sizeof(int)*n, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  cudaFree(d);
   return HCG_OK;
 }
 
@@ -204,6 +204,7 @@ hcg_status comm_local_init(hcg_ctx* c, const void* id128) {
 }
 
 void comm_destroy(hcg_ctx* c) {
+  if (c->comm_scratch) { cudaFree(c->comm_scratch); c->comm_scratch = nullptr; }
   if (c->nccl) { ncclCommDestroy((ncclComm_t)c->nccl); c->nccl = nullptr; }
   if (c->local) { delete (LocalEndpoint*)c->local; c->local = nullptr; }
 }

@@ -46,7 +46,9 @@ struct CellTypeHost {
 struct MultiFace { int32_t* d_cells = nullptr; int64_t* d_off = nullptr; int n = 0, cap = 0; int64_t total = 0; };
 struct MultiState {
   double margin = 4.0;            // hold region = slab +- margin lattice units
-  int sync_every = 20;            // membership re-evaluation cadence
+  int sync_every = 20;            // membership re-evaluation: at least this many steps apart ...
+  int64_t next_sync_iter = 0;     // ... and due at this iteration (multi_rebalance sets it from the fastest vertex: see there)
+  double* d_vmax = nullptr;       // largest velocity component of the held particles (device scalar)
   double slack = 0.3;             // spare cell slots per type for arrivals
   MultiFace face[2];              // cells shared through the left / right face, sorted by global id
   MultiFace all;                  // union of the two lists (each shared cell once)
@@ -120,6 +122,7 @@ struct hcg_ctx {
   // lattices with walls: cells with no non-fluid node within reach skip the flag look-ups of the IBM kernels (ibm.cu: far_classify)
   uint8_t* wall_coarse = nullptr; int wc_dim[3] = {0, 0, 0}; bool wall_coarse_valid = false;   // 8^3 blocks of the padded slab holding a non-fluid node
   int* far_typeV = nullptr; int far_ntypes = -1;
+  int* bbox_typeV = nullptr; int bbox_ntypes = -1;   // mech_bbox scratch
   bool in_iterate = false;     // inside hcg_iterate*: the step cadence bounds how far a cell can drift between classifications
   uint8_t* cell_far = nullptr; int64_t cell_far_cap = 0; int far_steps_left = 0;               // per cell slot; valid for far_steps_left more advances
   // particles
@@ -146,7 +149,8 @@ struct hcg_ctx {
   cudaStream_t stream_lo = nullptr;   // low-priority stream: bulk work that overlaps the exchange chain of the main stream
   cudaEvent_t ev_a, ev_b;
   void* nccl;                  // ncclComm_t
-  void* local = nullptr;       // in-process communicator endpoint (comm.cu; hcg_comm_init_local)
+  void* local = nullptr;       // host-staged communicator endpoint (comm.cu; hcg_comm_init_local)
+  int* comm_scratch = nullptr; // device scratch of the small host-value reductions
   MultiState multi;
   PeerState peer;
   double* halo_send[2]; double* halo_recv[2];
@@ -260,7 +264,7 @@ void comm_send(hcg_ctx* c, const void* p, size_t bytes, int peer);
 void comm_recv(hcg_ctx* c, void* p, size_t bytes, int peer);
 hcg_status comm_group_end(hcg_ctx* c, const char* what);
 hcg_status comm_allreduce_f64(hcg_ctx* c, double* dev, size_t n, int op);
-hcg_status comm_allreduce_min_host(hcg_ctx* c, int* value);
+hcg_status comm_allreduce_min_host(hcg_ctx* c, int* value, int n = 1);
 hcg_status comm_nccl_init(hcg_ctx* c, const void* id128);
 hcg_status comm_local_init(hcg_ctx* c, const void* id128);
 void comm_destroy(hcg_ctx* c);

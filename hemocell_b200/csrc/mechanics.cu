@@ -378,15 +378,16 @@ hcg_status mech_apply(hcg_ctx* c, int ctype, bool components) {
 
 hcg_status mech_bbox(hcg_ctx* c, double* out_dev) {
   if (c->ncells == 0) return HCG_OK;
-  std::vector<int> hv; for (auto& t : c->types) hv.push_back(t.d.V);
-  int* dv;
-  CUDA_TRY(c, cudaMalloc(&dv, sizeof(int)*hv.size()));
-  CUDA_TRY(c, cudaMemcpyAsync(dv, hv.data(), sizeof(int)*hv.size(), cudaMemcpyHostToDevice, c->stream));
+  if ((int)c->types.size() != c->bbox_ntypes) {            // vertex counts per type: kept on the device across calls
+    std::vector<int> hv; for (auto& t : c->types) hv.push_back(t.d.V);
+    if (c->bbox_typeV) { CUDA_TRY(c, cudaStreamSynchronize(c->stream)); cudaFree(c->bbox_typeV); c->bbox_typeV = nullptr; }
+    CUDA_TRY(c, cudaMalloc(&c->bbox_typeV, sizeof(int)*hv.size()));
+    CUDA_TRY(c, hcg_h2d(c, c->bbox_typeV, hv.data(), sizeof(int)*hv.size()));
+    c->bbox_ntypes = (int)c->types.size();
+  }
   k_bbox<<<(unsigned)((c->ncells + 7)/8), 256, 0, c->stream>>>(c->pos[0], c->pos[1], c->pos[2], c->cell_base,
-                                                               c->cell_type, dv, c->ncells, out_dev);
+                                                               c->cell_type, c->bbox_typeV, c->ncells, out_dev);
   KERNEL_CHECK(c);
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  cudaFree(dv);
   return HCG_OK;
 }
 

@@ -135,6 +135,16 @@ k_unpack_advance2(SyncFace f0, SyncFace f1, IbmArgs a, const uint8_t* __restrict
   }
 }
 
+// largest velocity component over the particles of live cells (non-negative doubles order like their bit patterns)
+__global__ void k_vmax(const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
+                       const int32_t* __restrict__ p_cell, const uint8_t* __restrict__ alive, int64_t np, unsigned long long* out) {
+  double m = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x*blockDim.x + threadIdx.x; p < np; p += (int64_t)gridDim.x*blockDim.x)
+    if (alive[p_cell[p]]) m = fmax(m, fmax(fabs(vx[p]), fmax(fabs(vy[p]), fabs(vz[p]))));
+  for (int s = 16; s > 0; s >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
 // whole-cell migration payload: per cell 12*V doubles (pos, vel, force, frep as xyz triples)
 __global__ void k_pack_cells(const int32_t* __restrict__ cells, const int64_t* __restrict__ off, int n,
                              const int64_t* __restrict__ cell_base,
@@ -369,6 +379,7 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
   // 0. agree on the alive flags first (a boundary hit is seen only by the rank that holds the node)
   if (!initial && (s = multi_velocity_sync(c))) return s;
   // 1. bounding boxes and alive flags of every slot
+  double vmax = 0.0;
   std::vector<double> bbox(6*(size_t)std::max<int64_t>(nc, 1));
   std::vector<uint8_t> alive(std::max<int64_t>(nc, 1));
   if (nc) {
@@ -379,6 +390,13 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
       m.bbox_cap = (size_t)nc;
     }
     if ((s = mech_bbox(c, m.d_bbox))) return s;
+    if (!m.d_vmax) CUDA_TRY(c, cudaMalloc(&m.d_vmax, sizeof(double)));
+    CUDA_TRY(c, cudaMemsetAsync(m.d_vmax, 0, sizeof(double), c->stream));
+    if (c->np > 0) {
+      k_vmax<<<296, 256, 0, c->stream>>>(c->vel[0], c->vel[1], c->vel[2], c->p_cell, c->cell_alive, c->np, (unsigned long long*)m.d_vmax);
+      KERNEL_CHECK(c);
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(&vmax, m.d_vmax, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(bbox.data(), m.d_bbox, sizeof(double)*6*nc, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(alive.data(), c->cell_alive, nc, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -523,18 +541,22 @@ hcg_status multi_rebalance(hcg_ctx* c, bool initial) {
     }
     CUDA_TRY(c, hcg_h2d(c, m.d_cell_shared, flag.data(), (size_t)std::max<int64_t>(nc, 1)));
   }
-  // peer transport: receive buffers sized for the new lists, mappings re-published (collective, cheap)
-  if (c->peer.transport == 1) {
-    // the mappings are re-published only when some rank's receive buffer was outgrown (they carry 50 % headroom): one small
-    // reduction instead of the IPC-handle exchange on every rebalance
-    bool changed = false;
-    if ((s = peer_reserve_sync(c, 2*((size_t)m.face[0].n + 3*(size_t)m.face[0].total), 2*((size_t)m.face[1].n + 3*(size_t)m.face[1].total), &changed))) return s;
-    int keep = (changed || !c->peer.ready) ? 0 : 1;
-    if ((s = comm_allreduce_min_host(c, &keep))) return s;
-    if (!keep) {
-      if ((s = peer_setup(c))) return s;
-      if (!c->peer.ready) return hcg_fail(c, HCG_ERR_STATE, "peer transport: re-mapping the neighbours' buffers failed after a rebalance");
-    }
+  // one small reduction settles (a) whether the peer mappings must be re-published - only when some rank's receive buffer was
+  // outgrown (they carry 50 % headroom) - and (b) when membership is looked at next: the hold margin leaves 2 lu of drift
+  // beyond the kernel support; the next rebalance comes when the fastest vertex of any rank could have used 1 lu of it at
+  // its present speed (the other half is left for acceleration in between), at least sync_every and at most 8 sync_every
+  // steps from now.  Slow suspensions (the benchmark: 1e-3 lu per step) thus pay the host round trip 8 times less often.
+  bool changed = false;
+  if (c->peer.transport == 1 &&
+      (s = peer_reserve_sync(c, 2*((size_t)m.face[0].n + 3*(size_t)m.face[0].total), 2*((size_t)m.face[1].n + 3*(size_t)m.face[1].total), &changed))) return s;
+  int agree[2] = {(c->peer.transport != 1 || (!changed && c->peer.ready)) ? 1 : 0, -(int)std::min(1.0e9, std::ceil(vmax*1.0e6))};
+  if ((s = comm_allreduce_min_host(c, agree, 2))) return s;
+  const double vmax_all = -agree[1]*1.0e-6;
+  const int64_t interval = std::min<int64_t>(8*(int64_t)m.sync_every, std::max<int64_t>(m.sync_every, (int64_t)std::floor(1.0/(vmax_all + 1.0e-3))));
+  m.next_sync_iter = c->iter + (initial ? m.sync_every : interval);
+  if (c->peer.transport == 1 && !agree[0]) {
+    if ((s = peer_setup(c))) return s;
+    if (!c->peer.ready) return hcg_fail(c, HCG_ERR_STATE, "peer transport: re-mapping the neighbours' buffers failed after a rebalance");
   }
   return HCG_OK;
 }

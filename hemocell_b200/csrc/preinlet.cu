@@ -170,6 +170,7 @@ hcg_status hcg_preinlet_apply_cells(hcg_ctx* c, int32_t axis, double period, con
     double* d_bbox;
     CUDA_TRY(c, cudaMalloc(&d_bbox, sizeof(double)*6*npc));
     if ((s = mech_bbox(pre, d_bbox))) { cudaFree(d_bbox); return hcg_fail(c, s, pre->err); }
+    CUDA_TRY(c, cudaStreamSynchronize(pre->stream));
     CUDA_TRY(c, cudaMemcpy(bbox.data(), d_bbox, sizeof(double)*6*npc, cudaMemcpyDeviceToHost));
     CUDA_TRY(c, cudaMemcpy(alive.data(), pre->cell_alive, npc, cudaMemcpyDeviceToHost));
     cudaFree(d_bbox);

@@ -199,13 +199,16 @@ hcg_status hcg_set_spread_mode(hcg_ctx*, int32_t mode, int32_t resort_every);
 /* EXPERIMENTAL (not yet measured): at tau = 1 on a fully periodic lattice without walls (cases/performance_testing) the lattice
  * state can be the four raw moments per node instead of the 19 populations; 1 = one kernel per step reads the neighbours'
  * moments and forces and writes the new moments (populations are materialised on demand), 2 = the same on slab-decomposed runs
- * (W / F face planes exchanged with NCCL send/recv; every rank must use the same setting), 0 = stored populations.  Default:
- * environment HCG_MOMENT_ONLY (off). */
+ * (face planes read from the neighbours over NVLink, or exchanged with send/recv; every rank must use the same setting),
+ * 0 = stored populations.  Default: on (environment HCG_MOMENT_ONLY=0 switches it off); it applies only where every rank's
+ * lattice is plain periodic fluid at tau = 1, which the ranks agree on when the flags are set. */
 hcg_status hcg_set_moment_only(hcg_ctx*, int32_t on);
 /* multi-GPU particle exchange (replaces particleEnvelope of config.xml and the comm. structure of
  * HemoCellFields::calculateCommunicationStructure, core/hemoCellFields.cpp:363-372): a rank holds
- * every cell within `margin_lu` of its slab, membership is re-evaluated every `sync_every` steps,
- * `slack` = fraction of spare cell slots for arrivals.  Must precede hcg_cells_add. */
+ * every cell within `margin_lu` of its slab (2 lu of kernel support + the drift allowed between two looks at the
+ * membership), membership is re-evaluated when the fastest vertex of any rank could have drifted 1 lu at its present speed,
+ * at least `sync_every` and at most 8 x `sync_every` steps after the previous time; `slack` = fraction of spare cell
+ * slots for arrivals.  Must precede hcg_cells_add. */
 hcg_status hcg_set_exchange(hcg_ctx*, double margin_lu, int32_t sync_every, double slack);
 /* multi-GPU transport of the per-step exchanges (lattice ghost planes, node velocity ghosts, shared-cell
  * velocity sync; replaces the MPI messages of Palabos' block communicator and of
