@@ -1139,10 +1139,16 @@ hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
                           pr.UL = (double*)L[0].ptr[2] + 4*(int64_t)(b.nxlL + 1)*c->P; }
     if (L[1].rank >= 0) { pr.WR = (const double*)L[1].ptr[6 + fl] + 4*c->P; pr.FR = (const double*)L[1].ptr[8 + fl] + 4*c->P; pr.UR = (double*)L[1].ptr[2]; }
     if ((s = peer_barrier(c))) return s;
+  } else if (c->dom.n_ranks == 1 && moment_kernel_env()) {
+    // one rank, periodic in x: the "neighbours" are this slab's own end planes - the kernel reads them where they lie and writes
+    // the node velocity of its end planes into its own ghost planes (no ghost-fill launches at all)
+    pr.WL = c->W + 4*(int64_t)c->nxl*c->P; pr.FL = c->F + 4*(int64_t)c->nxl*c->P; pr.UL = c->U + 4*(int64_t)(c->nxl + 1)*c->P;
+    pr.WR = c->W + 4*c->P; pr.FR = c->F + 4*c->P; pr.UR = c->U;
   } else {
     if ((s = exchange(c, c->W, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
     if ((s = exchange(c, c->F, 4*c->P, h_qsets + 10, c->d_qsets + 10, 1, h_qsets + 10, c->d_qsets + 10, 1))) return s;
   }
+  const bool self_wrap = !peer && pr.WL != nullptr;
   LatArgs a = make_args(c);
   if (moment_kernel_env()) {
     OpTimer tk(c, "kernel:k_moment_tile");
@@ -1181,7 +1187,7 @@ hcg_status lat_moment_step(hcg_ctx* c, bool write_u) {
   std::swap(c->W, c->W2); std::swap(c->F, c->F2);           // the second buffers now hold the inputs of this step (kept for lat_ensure_pops)
   c->mo_flip ^= 1;
   c->pops_stale = true; c->u_valid = write_u; c->f_clean = true; c->w_valid = true;
-  if (write_u) return peer ? peer_barrier(c) : lat_halo_exchange_u(c);
+  if (write_u && !self_wrap) return peer ? peer_barrier(c) : lat_halo_exchange_u(c);
   return HCG_OK;
 }
 // the populations of the current state from the inputs of the last moment-only step: g_q(n) = f*_q(n) (k_collide_tau1)
