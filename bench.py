@@ -120,6 +120,12 @@ def pinned_empty_f32(n):
     return np.frombuffer(buf, dtype=np.float32)
 
 
+try:
+    _AFFINITY0 = os.sched_getaffinity(0)
+except Exception:
+    _AFFINITY0 = set()
+
+
 def bind_to_gpu_numa_node(index):
     """what `numactl` / the MPI launcher does for the reference: run this rank on the cores next to its GPU, so that its pinned
     host buffers are allocated on that socket's memory (8 ranks copying at once otherwise meet on one socket's memory controller)"""
@@ -855,6 +861,10 @@ def main():
     if args.rank != 0:
         return
     if args.world == 1 and not args.no_cpu_baseline:
+        try:
+            os.sched_setaffinity(0, _AFFINITY0)           # the CPU baseline gets every host core again (the GPU leg ran NUMA-bound)
+        except Exception:
+            pass
         line["cpu_baseline"] = run_cpu(6, 1, args.cadence, budget_s=30.0, workload=args.workload)
     print(json.dumps(line), flush=True)
 
