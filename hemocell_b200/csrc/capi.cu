@@ -3,6 +3,7 @@
 #include "ctx.cuh"
 #include <nccl.h>
 #include <algorithm>
+#include <unordered_map>
 #include <cstring>
 #include <cstdio>
 #include <cstdlib>
@@ -544,9 +545,10 @@ hcg_status hcg_celltype_add(hcg_ctx* c, const hcg_celltype* t, int32_t* ctype_ou
   if (t->model != HCG_MODEL_RBC_HIGHORDER && t->model != HCG_MODEL_PLT_SIMPLE && t->model != HCG_MODEL_HOST) return hcg_fail(c, HCG_ERR_ARG, "unknown model");
   const int V = t->n_vertices, T = t->n_triangles, E = t->n_edges, I = t->n_inner_edges;
   if (V < 4 || T < 4 || E < 6 || I < 0) return hcg_fail(c, HCG_ERR_ARG, "degenerate mesh");
+  if (V > 65535 || E > 65534 || T > 65534) return hcg_fail(c, HCG_ERR_CAPACITY, "mesh too large for the packed gather tables");
   // ---- per-vertex gather tables
-  std::vector<int> vt(6*(size_t)V, -1), ve(6*(size_t)V, -1), vb(7*(size_t)V, -1), vpe(12*(size_t)V, -1), vin(4*(size_t)V, -1);
-  std::vector<int> nvt(V, 0), nve(V, 0), nvpe(V, 0), nvin(V, 0);
+  std::vector<int> vt(6*(size_t)V, -1), vpe(12*(size_t)V, -1), vin(4*(size_t)V, -1);
+  std::vector<int> nvt(V, 0), nvpe(V, 0), nvin(V, 0);
   for (int k = 0; k < T; k++) for (int m = 0; m < 3; m++) {
     const int v = t->triangles[3*k+m];
     if (v < 0 || v >= V) return hcg_fail(c, HCG_ERR_ARG, "triangle index out of range");
@@ -556,16 +558,49 @@ hcg_status hcg_celltype_add(hcg_ctx* c, const hcg_celltype* t, int32_t* ctype_ou
   for (int e = 0; e < E; e++) for (int m = 0; m < 2; m++) {
     const int v = t->edges[2*e+m];
     if (v < 0 || v >= V) return hcg_fail(c, HCG_ERR_ARG, "edge index out of range");
-    if (nve[v] >= 6) return hcg_fail(c, HCG_ERR_ARG, "vertex with more than 6 edges");
-    ve[6*v + nve[v]++] = 2*e + m;
   }
   for (int v = 0; v < V; v++) {
     const int nn = t->vertex_n_vertexes[v];
     if (nn < 3 || nn > 6) return hcg_fail(c, HCG_ERR_ARG, "vertex ring size must be 3..6");
-    std::vector<int> s(t->vertex_vertexes + 6*v, t->vertex_vertexes + 6*v + nn);
-    s.push_back(v);
-    std::sort(s.begin(), s.end());
-    for (size_t k = 0; k < s.size(); k++) vb[7*v + k] = s[k];
+    for (int j = 0; j < nn; j++) {
+      const int r = t->vertex_vertexes[6*v + j];
+      if (r < 0 || r >= V || r == v) return hcg_fail(c, HCG_ERR_ARG, "ring vertex out of range");
+    }
+  }
+  // RBC: one packed word per (ring slot j, vertex) - the ring vertex r_j, the edge (v, r_j), the triangle (v, r_j, r_j+1),
+  // the ring size of r_j, which of (v, r_j, r_j+1) is the triangle's third vertex (its centroid sum is rebuilt in the
+  // reference's order) and whether (v, r_j, r_j+1) runs against the triangle's orientation.  Slots past the ring size
+  // repeat r_0 with the null edge E, the null triangle T and ring size 0: they add +0.0.
+  std::vector<unsigned long long> rg(6*(size_t)V, 0ull);
+  if (t->model == HCG_MODEL_RBC_HIGHORDER) {
+    std::unordered_map<unsigned long long, int> emap, tmap;
+    auto ekey = [](int x, int y) { if (x > y) std::swap(x, y); return ((unsigned long long)x << 20) | (unsigned long long)y; };
+    auto tkey = [](int x, int y, int z) { int q[3] = {x, y, z}; std::sort(q, q + 3);
+                                          return ((unsigned long long)q[0] << 40) | ((unsigned long long)q[1] << 20) | (unsigned long long)q[2]; };
+    for (int e = 0; e < E; e++) emap[ekey(t->edges[2*e], t->edges[2*e+1])] = e;
+    for (int k = 0; k < T; k++) tmap[tkey(t->triangles[3*k], t->triangles[3*k+1], t->triangles[3*k+2])] = k;
+    for (int v = 0; v < V; v++) {
+      const int nn = t->vertex_n_vertexes[v];
+      const int* ring = t->vertex_vertexes + 6*v;
+      for (int j = 0; j < 6; j++) {
+        unsigned long long w;
+        if (j < nn) {
+          const int ia = ring[j], ib = ring[(j + 1) % nn];
+          auto ei = emap.find(ekey(v, ia));
+          auto ti = tmap.find(tkey(v, ia, ib));
+          if (ei == emap.end()) return hcg_fail(c, HCG_ERR_ARG, "ring neighbour without an edge");
+          if (ti == tmap.end()) return hcg_fail(c, HCG_ERR_ARG, "consecutive ring neighbours without a triangle");
+          const int* q = t->triangles + 3*ti->second;
+          const int last = q[2] == v ? 0 : (q[2] == ia ? 1 : 2);
+          const bool same = (q[0] == v && q[1] == ia) || (q[0] == ia && q[1] == ib) || (q[0] == ib && q[1] == v);
+          w = (unsigned long long)ia | ((unsigned long long)ei->second << 16) | ((unsigned long long)ti->second << 32) |
+              ((unsigned long long)t->vertex_n_vertexes[ia] << 48) | ((unsigned long long)last << 51) | ((unsigned long long)(same ? 0 : 1) << 53);
+        } else {
+          w = (unsigned long long)ring[0] | ((unsigned long long)E << 16) | ((unsigned long long)T << 32);
+        }
+        rg[(size_t)j*V + v] = w;
+      }
+    }
   }
   if (t->model == HCG_MODEL_PLT_SIMPLE) {
     for (int e = 0; e < E; e++) {
@@ -595,7 +630,7 @@ hcg_status hcg_celltype_add(hcg_ctx* c, const hcg_celltype* t, int32_t* ctype_ou
   UP(bend_tri, t->edge_bending_triangles, 2*E); UP(bend_outer, t->edge_bending_outer_points, 2*E);
   UP(edge_len_eq, t->edge_length_eq, E); UP(edge_ang_eq, t->edge_angle_eq, E);
   UP(tri_area_eq, t->triangle_area_eq, T); UP(patch_eq, t->patch_dist_eq, V); UP(inner_len_eq, t->inner_edge_length_eq, I);
-  UP(vt, vt.data(), vt.size()); UP(ve, ve.data(), ve.size()); UP(vb, vb.data(), vb.size());
+  UP(vt, vt.data(), vt.size()); UP(rg, rg.data(), rg.size());
   UP(vpe, vpe.data(), vpe.size()); UP(vin, vin.data(), vin.size());
 #undef UP
   d.volume_eq = t->volume_eq; d.area_mean_eq = t->area_mean_eq; d.edge_mean_eq = t->edge_mean_eq;

@@ -23,9 +23,8 @@ struct CellTypeDev {
   int *tri, *edge, *inner, *ring, *nring, *bend_tri, *bend_outer;
   double *edge_len_eq, *edge_ang_eq, *tri_area_eq, *patch_eq, *inner_len_eq;
   // per-vertex gather tables (built on the host in hcg_celltype_add)
-  int *vt;    // [V][6]  incident triangles, ascending, -1 padded
-  int *ve;    // [V][6]  incident edges, ascending: 2*e + (v == edge[e][1]), -1 padded
-  int *vb;    // [V][7]  ring(v) U {v}, ascending, -1 padded  (RBC bending contributions)
+  int *vt;    // [V][6]  incident triangles, ascending, -1 padded (PLT)
+  unsigned long long *rg;   // [6][V]  RBC, per ring slot: ring vertex | edge << 16 | triangle << 32 | ring size << 48 | codes (hcg_celltype_add)
   int *vpe;   // [V][12] PLT: edges touching v as end or outer point: 4*e + role, ascending
   int *vin;   // [V][4]  PLT inner edges: 2*e + side
   double volume_eq, area_mean_eq, edge_mean_eq;

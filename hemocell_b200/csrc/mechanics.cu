@@ -1,6 +1,5 @@
-// K3: membrane constitutive forces, one CTA per cell, positions staged in shared memory,
-// per-vertex GATHER over precomputed adjacency so that every vertex accumulates its terms in
-// exactly the order the reference's sequential loops produce them (no atomics, deterministic).
+// K3: membrane constitutive forces, one CTA per cell, positions staged in shared memory, no atomics, deterministic.
+// Every term is a GATHER: per mesh element first (triangle, edge, vertex patch), then per vertex over its ring.
 // Replaces RbcHighOrderModel::ParticleMechanics (reference mechanics/rbcHighOrderModel.cpp:38-207)
 // and PltSimpleModel::ParticleMechanics (mechanics/pltSimpleModel.cpp:44-208) behind
 // HemoCellParticleField::applyConstitutiveModel (core/hemoCellParticleField.cpp:633-675).
@@ -24,7 +23,9 @@ __device__ __forceinline__ V3 sub(V3 a, V3 b) { return {a.x-b.x, a.y-b.y, a.z-b.
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return {a.y*b.z - a.z*b.y, a.z*b.x - a.x*b.z, a.x*b.y - a.y*b.x}; }
 __device__ __forceinline__ double dot(V3 a, V3 b) { return a.x*b.x + a.y*b.y + a.z*b.z; }
 __device__ __forceinline__ double norm(V3 a) { return sqrt(a.x*a.x + a.y*a.y + a.z*a.z); }
-__device__ __forceinline__ V3 ldv(const double* X, int V, int i) { return {X[i], X[V+i], X[2*V+i]}; }
+// staged vectors are [V][3]: one address per vertex, and a stride of three 8-byte words spreads consecutive or random
+// vertices over all sixteen bank pairs
+__device__ __forceinline__ V3 ldv(const double* X, int, int i) { return {X[3*i], X[3*i+1], X[3*i+2]}; }
 // helper/array.h:271-285
 __device__ __forceinline__ void tri_area_normal(V3 v0, V3 v1, V3 v2, double& area, V3& n) {
   n = cross(sub(v1, v0), sub(v2, v0));
@@ -35,169 +36,253 @@ __device__ __forceinline__ void tri_area_normal(V3 v0, V3 v1, V3 v2, double& are
 }
 
 // MODEL 0 = RbcHighOrderModel, 1 = PltSimpleModel; VISC: membrane viscosity term evaluated
-template <int MODEL, bool VISC, bool COMP>
-__global__ void __launch_bounds__(256, MODEL == 0 ? 3 : 1)
+//
+// RBC, in four steps between three barriers:
+//  1. per triangle: the signed-volume term and the area-force magnitude (AFM);
+//  2. lane 0 sums the volume terms sequentially while the other warps evaluate, per edge, the link (and viscous) force
+//     divided by the edge length (EF, EG) and, per vertex, the bending force of its patch (BF);
+//  3. per vertex, one walk around its ring: slot j brings the neighbour r_j, the edge (v, r_j) and the triangle
+//     (v, r_j, r_j+1) from one packed table word, and the vertex only scales difference vectors it rebuilds from the
+//     staged positions: AFM * (centroid - x_v), EF * (r_j - x_v), BF[r_j] / n, the volume force along the raw cross
+//     product (area * unit normal == cross / 2).
+// Everything with a square root or a division in it is thus evaluated once per mesh element (20 k division-class
+// operations per cell; the first version of the gather re-evaluated a triangle three times and an edge twice, 45 k), and
+// every position is loaded once per ring walk (54 shared-memory loads per vertex against 108: after the divisions had
+// gone the kernel was bound by shared-memory wavefronts, profiles/README.md r2x).  The signed-volume term and the
+// centroid are formed exactly as the reference forms them (no contraction, the reference's operand order: both cancel
+// five to seven digits); the other products differ from the reference's by an ulp or two in places where nothing cancels
+// afterwards, and the four force families reach a vertex in ring order instead of element order
+// (tests/test_gpu_parity.py::test_mechanics_parity holds 1e-12 on the total and on each family).
+template <int MODEL, bool VISC, bool COMP, int NT>
+__global__ void __launch_bounds__(NT, MODEL == 0 ? 3 : 1)
 k_mechanics(MechArgs a) {
   extern __shared__ double sm[];
   const CellTypeDev& t = a.t;
-  const int V = t.V, T = t.T;
+  const int V = t.V, T = t.T, E = t.E;
   const int64_t cell = a.first_cell + blockIdx.x;
   if (!a.alive[cell]) return;
   const int64_t base = a.first_particle + (int64_t)blockIdx.x*V;
-  // RBC (MODEL 0): triangle areas / normals are NOT staged - the per-vertex gather recomputes them for its <= 6 incident
-  // triangles - so a cell needs 41 KB instead of 82 KB and 4 cells fit an SM (the kernel is latency-bound: 2.0 ms at two
-  // cells per SM, 3.6 ms at one).  PLT (small) keeps the tables: its dihedral bending reads the normals by edge.
-  constexpr bool TRI_TABLES = (MODEL != 0);
+  constexpr bool RBC = (MODEL == 0);
   double* X = sm;                    // [3V]
   double* VEL = X + 3*V;             // [3V] if VISC
-  double* TA = VEL + (VISC ? 3*V : 0);   // [T]   (TRI_TABLES)
-  double* TN = TA + (TRI_TABLES ? T : 0);               // [3T]  (TRI_TABLES)
-  double* VT = TN + (TRI_TABLES ? 3*T : 0);             // [T]
-  double* BF = VT + T;               // [3V] (RBC) bending force of every vertex's own patch
-  double* BFN = BF + 3*V;            // [3V] (RBC) ... divided by the patch's ring size: the reaction each ring neighbour takes
+  double* VT = VEL + (VISC ? 3*V : 0);    // [T]  signed-volume terms
+  double* TA = VT + T;               // [T+1] PLT: area          RBC: AFM, area-force magnitude (+ the null triangle's 0)
+  double* TN = TA + T + 1;           // [3T]  PLT: unit normal
+  double* BF = TN + (RBC ? 0 : 3*T); // [3V]  RBC: bending force of every vertex's own patch
+  double* EF = BF + (RBC ? 3*V : 0); // [E+1] RBC: link force / edge length (+ the null edge's 0)
+  double* EG = EF + (RBC ? E + 1 : 0);    // [E+1] RBC + VISC: viscous force / edge length
   __shared__ double s_volume;
+  __shared__ double s_ninv[8];       // -1/n: the share of a patch's bending force that each of its n ring vertices takes
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid < 8) s_ninv[tid] = tid ? -1.0/(double)tid : 0.0;
+  if (RBC && tid == 8) { TA[T] = 0.0; EF[E] = 0.0; if (VISC) EG[E] = 0.0; }   // the null triangle / edge of unused ring slots
 
   for (int i = tid; i < V; i += nt) {
-    X[i] = a.x[base+i]; X[V+i] = a.y[base+i]; X[2*V+i] = a.z[base+i];
-    if (VISC) { VEL[i] = a.vx[base+i]; VEL[V+i] = a.vy[base+i]; VEL[2*V+i] = a.vz[base+i]; }
+    X[3*i] = a.x[base+i]; X[3*i+1] = a.y[base+i]; X[3*i+2] = a.z[base+i];
+    if (VISC) { VEL[3*i] = a.vx[base+i]; VEL[3*i+1] = a.vy[base+i]; VEL[3*i+2] = a.vz[base+i]; }
   }
   __syncthreads();
 
-  // ---- per triangle: signed-volume term (bit-exact, no contraction), area, unit normal
-  for (int k = tid; k < T; k += nt) {
-    const int i0 = t.tri[3*k], i1 = t.tri[3*k+1], i2 = t.tri[3*k+2];
-    const V3 v0 = ldv(X, V, i0), v1 = ldv(X, V, i1), v2 = ldv(X, V, i2);
-    const double v210 = __dmul_rn(__dmul_rn(v2.x, v1.y), v0.z);
-    const double v120 = __dmul_rn(__dmul_rn(v1.x, v2.y), v0.z);
-    const double v201 = __dmul_rn(__dmul_rn(v2.x, v0.y), v1.z);
-    const double v021 = __dmul_rn(__dmul_rn(v0.x, v2.y), v1.z);
-    const double v102 = __dmul_rn(__dmul_rn(v1.x, v0.y), v2.z);
-    const double v012 = __dmul_rn(__dmul_rn(v0.x, v1.y), v2.z);
-    VT[k] = __dadd_rn(__dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(-v210, v120), v201), v021), v102), v012);
-    if (TRI_TABLES) {
-      double area; V3 n;
-      tri_area_normal(v0, v1, v2, area, n);
-      TA[k] = area; TN[3*k] = n.x; TN[3*k+1] = n.y; TN[3*k+2] = n.z;
+  // ---- per triangle: signed-volume term (bit-exact, no contraction), area (and unit normal / area-force magnitude).
+  // The vertex indices of the thread's next triangle are fetched while this one is computed.
+  {
+    int k = tid;
+    int i0 = 0, i1 = 0, i2 = 0;
+    if (k < T) { i0 = t.tri[3*k]; i1 = t.tri[3*k+1]; i2 = t.tri[3*k+2]; }
+    while (k < T) {
+      const int kn = k + nt;
+      int n0 = 0, n1 = 0, n2 = 0;
+      if (kn < T) { n0 = t.tri[3*kn]; n1 = t.tri[3*kn+1]; n2 = t.tri[3*kn+2]; }
+      const double aeq = RBC ? t.tri_area_eq[k] : 0.0;
+      const V3 v0 = ldv(X, V, i0), v1 = ldv(X, V, i1), v2 = ldv(X, V, i2);
+      const double v210 = __dmul_rn(__dmul_rn(v2.x, v1.y), v0.z);
+      const double v120 = __dmul_rn(__dmul_rn(v1.x, v2.y), v0.z);
+      const double v201 = __dmul_rn(__dmul_rn(v2.x, v0.y), v1.z);
+      const double v021 = __dmul_rn(__dmul_rn(v0.x, v2.y), v1.z);
+      const double v102 = __dmul_rn(__dmul_rn(v1.x, v0.y), v2.z);
+      const double v012 = __dmul_rn(__dmul_rn(v0.x, v1.y), v2.z);
+      VT[k] = __dadd_rn(__dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(-v210, v120), v201), v021), v102), v012);
+      if (RBC) {
+        // rbcHighOrderModel.cpp:72-92
+        const double area = 0.5*norm(cross(sub(v1, v0), sub(v2, v0)));
+        const double areaRatio = (area - aeq)/aeq;
+        TA[k] = t.k_area * (areaRatio + areaRatio/fabs(0.09 - areaRatio*areaRatio));
+      } else {
+        double area; V3 n;
+        tri_area_normal(v0, v1, v2, area, n);
+        TA[k] = area; TN[3*k] = n.x; TN[3*k+1] = n.y; TN[3*k+2] = n.z;
+      }
+      k = kn; i0 = n0; i1 = n1; i2 = n2;
     }
   }
   __syncthreads();
   // ---- the signed volume is summed sequentially in triangle order (== the reference's rounding: the absolute-coordinate
-  // formula loses ~7 digits, any other order changes the volume force at 1e-10) by ONE lane, while the other warps compute
-  // the bending forces of the vertex patches - the two do not depend on each other
+  // formula loses ~7 digits, any other order changes the volume force at 1e-10) by ONE lane: 1280 dependent additions,
+  // the longest chain in the kernel (about 40 % of a cell's time on the SM).  It starts as soon as the terms exist and runs
+  // beside everything that does not need the volume: the other warps' edge and bending passes.
   if (tid == 0) {
     double vol = 0.0;
-    for (int k = 0; k < T; k++) vol = __dadd_rn(vol, VT[k]);
+    int k = 0;
+    if ((reinterpret_cast<uintptr_t>(VT) & 15) == 0)
+      for (; k + 1 < T; k += 2) { const double2 p = *reinterpret_cast<const double2*>(VT + k); vol = __dadd_rn(__dadd_rn(vol, p.x), p.y); }
+    for (; k < T; k++) vol = __dadd_rn(vol, VT[k]);
     s_volume = __dmul_rn(vol, 1.0/6.0);
   }
-  // ---- RBC: bending force of every vertex's own patch (rbcHighOrderModel.cpp:127-158)
-  if (MODEL == 0 && (tid >= 32 || nt <= 32)) {
+  if (RBC && (tid >= 32 || nt <= 32)) {
     const int lane0 = nt > 32 ? 32 : 0, span = nt > 32 ? nt - 32 : nt;
+    // ---- per edge: link force (+ membrane viscosity) over the edge length (rbcHighOrderModel.cpp:169-201)
+    {
+      int e = tid - lane0;
+      int ia = 0, ib = 0;
+      if (e < E) { ia = t.edge[2*e]; ib = t.edge[2*e+1]; }
+      while (e < E) {
+        const int en = e + span;
+        int na = 0, nb = 0;
+        if (en < E) { na = t.edge[2*en]; nb = t.edge[2*en+1]; }
+        const double leq = t.edge_len_eq[e];
+        const V3 ev = sub(ldv(X, V, ib), ldv(X, V, ia));
+        const double len = norm(ev);
+        const double ilen = 1.0/len;
+        const double frac = (len - leq)/leq;
+        EF[e] = (t.k_link * (frac + frac/fabs(9.0 - frac*frac)))*ilen;
+        if (VISC) {
+          const V3 uv = {ev.x*ilen, ev.y*ilen, ev.z*ilen};
+          const V3 rv = sub(ldv(VEL, V, ib), ldv(VEL, V, ia));
+          const double pr = dot(rv, uv);
+          const double g0 = t.eta_m*(pr*uv.x), g1 = t.eta_m*(pr*uv.y), g2 = t.eta_m*(pr*uv.z);
+          const double m2 = g0*g0 + g1*g1 + g2*g2;
+          double gs = (t.eta_m*pr)*ilen;
+          if (m2 > 12.5*12.5) gs *= 12.5/sqrt(m2);
+          EG[e] = gs;
+        }
+        e = en; ia = na; ib = nb;
+      }
+    }
+    // ---- bending force of every vertex's own patch (rbcHighOrderModel.cpp:127-158); ring vertices from the packed table
+    const double inv_edge_mean = 1.0/t.edge_mean_eq;
+    const uint2* rgt = reinterpret_cast<const uint2*>(t.rg);
     for (int i = tid - lane0; i < V; i += span) {
       const int nn = t.nring[i];
-      const int* ring = t.ring + 6*i;
+      const double peq = t.patch_eq[i];
+      int ring[6];
+#pragma unroll
+      for (int j = 0; j < 6; j++) ring[j] = (int)(rgt[j*V + i].x & 0xffff);
       const V3 xi = ldv(X, V, i);
-      V3 sum = {0.0, 0.0, 0.0};
-      for (int j = 0; j < nn; j++) { const V3 r = ldv(X, V, ring[j]); sum.x += r.x; sum.y += r.y; sum.z += r.z; }
+      V3 pn = {0.0, 0.0, 0.0};
+      const V3 r0 = ldv(X, V, ring[0]);
+      V3 prev = sub(r0, xi);
+      const V3 first = prev;
+      V3 sum = r0;
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        if (j < nn) {
+          V3 nxt = first;
+          if (j + 1 < nn) { const V3 r = ldv(X, V, ring[j < 5 ? j + 1 : 0]); sum.x += r.x; sum.y += r.y; sum.z += r.z; nxt = sub(r, xi); }
+          const V3 tn = cross(prev, nxt);
+          const double il = rsqrt(tn.x*tn.x + tn.y*tn.y + tn.z*tn.z);
+          pn.x += tn.x*il; pn.y += tn.y*il; pn.z += tn.z*il;
+          prev = nxt;
+        }
+      }
+      // the ring mean minus the vertex cancels five digits: a true division, as the reference does
       const V3 mid = {sum.x/nn, sum.y/nn, sum.z/nn};
       const V3 dev = sub(mid, xi);
-      V3 pn = {0.0, 0.0, 0.0};
-      V3 prev = sub(ldv(X, V, ring[0]), xi);
-      const V3 first = prev;
-      for (int j = 0; j < nn; j++) {
-        const V3 nxt = (j + 1 < nn) ? sub(ldv(X, V, ring[j+1]), xi) : first;
-        V3 tn = cross(prev, nxt);
-        const double il = 1.0/norm(tn);
-        pn.x += tn.x*il; pn.y += tn.y*il; pn.z += tn.z*il;
-        prev = nxt;
-      }
-      const double il = 1.0/norm(pn);
+      const double il = rsqrt(pn.x*pn.x + pn.y*pn.y + pn.z*pn.z);
       pn.x *= il; pn.y *= il; pn.z *= il;
       const double ndev = dot(pn, dev);
-      const double dDev = (ndev - t.patch_eq[i]) / t.edge_mean_eq;
+      const double dDev = (ndev - peq) * inv_edge_mean;
       const double s = t.k_bend * (dDev + dDev/fabs(0.0555 - dDev*dDev));
-      const double b0 = s*pn.x, b1 = s*pn.y, b2 = s*pn.z;
-      BF[i] = b0; BF[V+i] = b1; BF[2*V+i] = b2;
-      BFN[i] = -b0/nn; BFN[V+i] = -b1/nn; BFN[2*V+i] = -b2/nn;
+      BF[3*i] = s*pn.x; BF[3*i+1] = s*pn.y; BF[3*i+2] = s*pn.z;
     }
   }
   __syncthreads();
   const double volume_frac = (s_volume - t.volume_eq)/t.volume_eq;
   const double volume_force = -t.k_volume * volume_frac/fabs(0.01 - volume_frac*volume_frac);
 
-  // ---- per vertex gather.  Divisions whose result is only scaled afterwards share a reciprocal (fp64 division is ~30
-  // instructions and was 3/4 of this kernel's instruction count); those that feed a cancelling difference stay divisions.
   const double third = 1.0/3.0, inv_area_mean = 1.0/t.area_mean_eq;
+  if (RBC) {
+    // ---- RBC, per vertex: one pass around the ring.  Slot j brings the ring vertex r_j (its position and its patch's
+    // bending force), the link (v, r_j) and the triangle (v, r_j, r_j+1); every position is loaded once.  The four force
+    // families are summed separately and added in the reference's order area, volume, bending, link (, viscosity);
+    // within a family the terms arrive in ring order instead of element order (a re-association, ~1e-16 of the largest term).
+    const double vf_half = (volume_force*0.5)*inv_area_mean;
+    for (int v = tid; v < V; v += nt) {
+      const V3 xv = ldv(X, V, v);
+      const uint2* rgp = reinterpret_cast<const uint2*>(t.rg) + v;      // [6][V]: consecutive lanes read consecutive words
+      uint2 cnext = rgp[0];
+      V3 fa = {0.0, 0.0, 0.0}, fw = {0.0, 0.0, 0.0}, fl = {0.0, 0.0, 0.0}, fs = {0.0, 0.0, 0.0};
+      V3 fb = ldv(BF, V, v);
+      const V3 r0 = ldv(X, V, (int)(cnext.x & 0xffff));
+      V3 ra = r0;
+#pragma unroll 1      // unrolling the ring walk spills at the 80 registers three cells per SM allow, and measured slower
+      for (int j = 0; j < 6; j++) {
+        const uint2 cj = cnext;
+        if (j < 5) cnext = rgp[(j + 1)*V];
+        const int ia = (int)(cj.x & 0xffff), e = (int)(cj.x >> 16), tr = (int)(cj.y & 0xffff);
+        const V3 rb = (j < 5) ? ldv(X, V, (int)(cnext.x & 0xffff)) : r0;
+        const V3 da = sub(ra, xv), db = sub(rb, xv);
+        // link (+ viscosity): the edge's scalar along (r_j - x_v)   (rbcHighOrderModel.cpp:169-201)
+        const double ef = EF[e];
+        fl.x += da.x*ef; fl.y += da.y*ef; fl.z += da.z*ef;
+        if (VISC) { const double eg = EG[e]; fs.x += da.x*eg; fs.y += da.y*eg; fs.z += da.z*eg; }
+        // bending: the reaction -F_i/n_i of the neighbour's patch (:127-158)
+        const double w = s_ninv[(cj.y >> 16) & 7];
+        fb.x += BF[3*ia]*w; fb.y += BF[3*ia+1]*w; fb.z += BF[3*ia+2]*w;
+        // area force towards the centroid, summed (v0 + v1) + v2 as the reference does (:72-92); volume force along the
+        // triangle's cross product == 2 * area * unit normal (:100-113)
+        const int last = (int)((cj.y >> 19) & 3);
+        const V3 p = (last == 0) ? ra : xv, q = (last == 2) ? ra : rb, l = (last == 0) ? xv : ((last == 1) ? ra : rb);
+        const double afm = TA[tr];
+        // (no contraction: the centroid is rounded before the vertex is subtracted, five digits cancel there)
+        const double cx = __dmul_rn((p.x + q.x) + l.x, third), cy = __dmul_rn((p.y + q.y) + l.y, third), cz = __dmul_rn((p.z + q.z) + l.z, third);
+        fa.x += afm*__dsub_rn(cx, xv.x); fa.y += afm*__dsub_rn(cy, xv.y); fa.z += afm*__dsub_rn(cz, xv.z);
+        const V3 cr = cross(da, db);
+        const double vs = ((cj.y >> 21) & 1) ? -vf_half : vf_half;
+        fw.x += vs*cr.x; fw.y += vs*cr.y; fw.z += vs*cr.z;
+        ra = rb;
+      }
+      if (COMP) {
+        a.comp[0][0][base+v] = fa.x; a.comp[0][1][base+v] = fa.y; a.comp[0][2][base+v] = fa.z;
+        a.comp[1][0][base+v] = fw.x; a.comp[1][1][base+v] = fw.y; a.comp[1][2][base+v] = fw.z;
+        a.comp[2][0][base+v] = fb.x; a.comp[2][1][base+v] = fb.y; a.comp[2][2][base+v] = fb.z;
+        a.comp[3][0][base+v] = fl.x; a.comp[3][1][base+v] = fl.y; a.comp[3][2][base+v] = fl.z;
+        a.comp[4][0][base+v] = fs.x; a.comp[4][1][base+v] = fs.y; a.comp[4][2][base+v] = fs.z;
+        a.comp[5][0][base+v] = 0.0; a.comp[5][1][base+v] = 0.0; a.comp[5][2][base+v] = 0.0;
+      }
+      double F0 = ((fa.x + fw.x) + fb.x) + fl.x, F1 = ((fa.y + fw.y) + fb.y) + fl.y, F2 = ((fa.z + fw.z) + fb.z) + fl.z;
+      if (VISC) { F0 += fs.x; F1 += fs.y; F2 += fs.z; }
+      a.fx[base+v] = F0; a.fy[base+v] = F1; a.fz[base+v] = F2;
+    }
+    return;
+  }
+
+  // ---- PLT, per vertex gather, every sum in the order the reference's loops reach the vertex
   for (int v = tid; v < V; v += nt) {
     const V3 xv = ldv(X, V, v);
     double F0 = 0.0, F1 = 0.0, F2 = 0.0;
     double c0, c1, c2;
-    // area force (rbcHighOrderModel.cpp:72-92) and volume force (:100-113) of the incident triangles
+    // area force (pltSimpleModel.cpp:73-90) and volume force (:105-117) of the incident triangles
     c0 = c1 = c2 = 0.0;
     double w0 = 0.0, w1 = 0.0, w2 = 0.0;          // volume-force sum (added after the area terms, as the reference's two loops do)
     for (int k = 0; k < 6; k++) {
       const int tr = t.vt[6*v + k]; if (tr < 0) break;
       const int i0 = t.tri[3*tr], i1 = t.tri[3*tr+1], i2 = t.tri[3*tr+2];
       const V3 v0 = ldv(X, V, i0), v1 = ldv(X, V, i1), v2 = ldv(X, V, i2);
-      double area; V3 n;
-      if (TRI_TABLES) { area = TA[tr]; n = {TN[3*tr], TN[3*tr+1], TN[3*tr+2]}; }
-      else tri_area_normal(v0, v1, v2, area, n);
+      const double area = TA[tr];
       const double aeq = t.tri_area_eq[tr];
       const double areaRatio = (area - aeq)/aeq;
       const double afm = t.k_area * (areaRatio + areaRatio/fabs(0.09 - areaRatio*areaRatio));
+      const double s = area*inv_area_mean;
+      w0 += (volume_force*TN[3*tr])*s; w1 += (volume_force*TN[3*tr+1])*s; w2 += (volume_force*TN[3*tr+2])*s;
       const double cx = (v0.x+v1.x+v2.x)*third, cy = (v0.y+v1.y+v2.y)*third, cz = (v0.z+v1.z+v2.z)*third;
       const double a0 = afm*(cx - xv.x), a1 = afm*(cy - xv.y), a2 = afm*(cz - xv.z);
       F0 += a0; F1 += a1; F2 += a2;
       if (COMP) { c0 += a0; c1 += a1; c2 += a2; }
-      const double s = area*inv_area_mean;
-      w0 += (volume_force*n.x)*s; w1 += (volume_force*n.y)*s; w2 += (volume_force*n.z)*s;
     }
     if (COMP) { a.comp[0][0][base+v] = c0; a.comp[0][1][base+v] = c1; a.comp[0][2][base+v] = c2;
                 a.comp[1][0][base+v] = w0; a.comp[1][1][base+v] = w1; a.comp[1][2][base+v] = w2; c0 = c1 = c2 = 0.0; }
     F0 += w0; F1 += w1; F2 += w2;
-    if (MODEL == 0) {
-      // bending: own patch force + reaction -F_i/n_i of every neighbour patch, by ascending i
-      for (int k = 0; k < 7; k++) {
-        const int i = t.vb[7*v + k]; if (i < 0) break;
-        double a0, a1, a2;
-        if (i == v) { a0 = BF[i]; a1 = BF[V+i]; a2 = BF[2*V+i]; }
-        else { a0 = BFN[i]; a1 = BFN[V+i]; a2 = BFN[2*V+i]; }
-        F0 += a0; F1 += a1; F2 += a2;
-        if (COMP) { c0 += a0; c1 += a1; c2 += a2; }
-      }
-      if (COMP) { a.comp[2][0][base+v] = c0; a.comp[2][1][base+v] = c1; a.comp[2][2][base+v] = c2; }
-      // links (+ membrane viscosity) (rbcHighOrderModel.cpp:169-201)
-      double l0 = 0, l1 = 0, l2 = 0, s0 = 0, s1 = 0, s2 = 0;
-      for (int k = 0; k < 6; k++) {
-        const int code = t.ve[6*v + k]; if (code < 0) break;
-        const int e = code >> 1; const double sg = (code & 1) ? -1.0 : 1.0;
-        const int ia = t.edge[2*e], ib = t.edge[2*e+1];
-        const V3 ev = sub(ldv(X, V, ib), ldv(X, V, ia));
-        const double len = norm(ev);
-        const double ilen = 1.0/len;
-        const V3 uv = {ev.x*ilen, ev.y*ilen, ev.z*ilen};
-        const double leq = t.edge_len_eq[e];
-        const double frac = (len - leq)/leq;
-        const double fs = t.k_link * (frac + frac/fabs(9.0 - frac*frac));
-        const double a0 = uv.x*fs, a1 = uv.y*fs, a2 = uv.z*fs;
-        F0 += sg*a0; F1 += sg*a1; F2 += sg*a2;
-        if (COMP) { l0 += sg*a0; l1 += sg*a1; l2 += sg*a2; }
-        if (VISC) {
-          const V3 rv = sub(ldv(VEL, V, ib), ldv(VEL, V, ia));
-          const double pr = dot(rv, uv);
-          double g0 = t.eta_m*(pr*uv.x), g1 = t.eta_m*(pr*uv.y), g2 = t.eta_m*(pr*uv.z);
-          const double mag = sqrt(g0*g0 + g1*g1 + g2*g2);
-          if (mag > 12.5) { const double s = 12.5/mag; g0 *= s; g1 *= s; g2 *= s; }
-          F0 += sg*g0; F1 += sg*g1; F2 += sg*g2;
-          if (COMP) { s0 += sg*g0; s1 += sg*g1; s2 += sg*g2; }
-        }
-      }
-      if (COMP) {
-        a.comp[3][0][base+v] = l0; a.comp[3][1][base+v] = l1; a.comp[3][2][base+v] = l2;
-        a.comp[4][0][base+v] = s0; a.comp[4][1][base+v] = s1; a.comp[4][2][base+v] = s2;
-        a.comp[5][0][base+v] = 0.0; a.comp[5][1][base+v] = 0.0; a.comp[5][2][base+v] = 0.0;
-      }
-    } else {
+    {
       // PLT: per edge link, viscosity, dihedral bending (pltSimpleModel.cpp:119-185)
       double l0 = 0, l1 = 0, l2 = 0, s0 = 0, s1 = 0, s2 = 0, b0 = 0, b1 = 0, b2 = 0;
       for (int k = 0; k < 12; k++) {
@@ -332,14 +417,14 @@ k_stretch(const double* __restrict__ x, const double* __restrict__ y, const doub
   }
 }
 
-template <int MODEL, bool VISC>
+template <int MODEL, bool VISC, int NT>
 hcg_status launch(hcg_ctx* c, const MechArgs& a, int64_t ncells, size_t smem, int threads, bool comp) {
   if (comp) {
-    CUDA_TRY(c, cudaFuncSetAttribute(k_mechanics<MODEL, VISC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_mechanics<MODEL, VISC, true><<<(unsigned)ncells, threads, smem, c->stream>>>(a);
+    CUDA_TRY(c, cudaFuncSetAttribute(k_mechanics<MODEL, VISC, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_mechanics<MODEL, VISC, true, NT><<<(unsigned)ncells, threads, smem, c->stream>>>(a);
   } else {
-    CUDA_TRY(c, cudaFuncSetAttribute(k_mechanics<MODEL, VISC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_mechanics<MODEL, VISC, false><<<(unsigned)ncells, threads, smem, c->stream>>>(a);
+    CUDA_TRY(c, cudaFuncSetAttribute(k_mechanics<MODEL, VISC, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_mechanics<MODEL, VISC, false, NT><<<(unsigned)ncells, threads, smem, c->stream>>>(a);
   }
   KERNEL_CHECK(c);
   return HCG_OK;
@@ -368,12 +453,13 @@ hcg_status mech_apply(hcg_ctx* c, int ctype, bool components) {
   const int V = th.d.V, T = th.d.T;
   const bool plt = th.d.model == HCG_MODEL_PLT_SIMPLE;
   const bool visc = plt || th.d.eta_m != 0.0;
-  size_t smem = sizeof(double)*((size_t)3*V + (visc ? 3*V : 0) + (plt ? 5 : 1)*(size_t)T + (plt ? 0 : 6*V));
-  { static int pad = -1; if (pad < 0) { const char* e = getenv("HCG_MECH_SMEM_PAD"); pad = e ? atoi(e) : 0; } smem += (size_t)pad*1024; }   // experiment knob: occupancy sensitivity
+  const size_t E = th.d.E;
+  const size_t smem = sizeof(double)*((size_t)3*V + (visc ? 3*V : 0) + 1 +
+                                     (plt ? 5*(size_t)T : 2*(size_t)T + 3*V + E + 1 + (visc ? E + 1 : 0)));
+  if (plt) return launch<1, true, 256>(c, a, th.n_cells, smem, V >= 256 ? 256 : (V >= 128 ? 128 : 64), components);
+  // RBC: three cells per SM (67 kB of shared memory each)
   const int threads = V >= 256 ? 256 : (V >= 128 ? 128 : 64);
-  if (plt) return launch<1, true>(c, a, th.n_cells, smem, threads, components);
-  if (visc) return launch<0, true>(c, a, th.n_cells, smem, threads, components);
-  return launch<0, false>(c, a, th.n_cells, smem, threads, components);
+  return visc ? launch<0, true, 256>(c, a, th.n_cells, smem, threads, components) : launch<0, false, 256>(c, a, th.n_cells, smem, threads, components);
 }
 
 hcg_status mech_bbox(hcg_ctx* c, double* out_dev) {
