@@ -47,25 +47,39 @@ k_advance_list(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __re
                const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz);
 
 
+// One launch per cell type, one thread per vertex.  The kernel is bound by the latency of its dependent loads, so the
+// chain is kept two deep: the vertex's cell follows from its index (the cells of a type are V consecutive vertices each -
+// no particle -> cell table), and position, liveness and the cell's flags are requested together before the eight node
+// loads they decide.  (Tried and dropped, profiles/README.md r2y: two lanes per vertex, one per z offset of the corners, so
+// that a lane pair reads two neighbouring node records - 0.34 ms instead of 0.23; five or six CTAs per SM at 48 / 40
+// registers - 0.237 / 0.245 ms.)
+struct TypeSpan { int64_t first_particle, first_cell, n; int V; double inv_V; };
+
 template <bool ADVANCE, bool INTERP, bool CHECK_FLAGS>
-__global__ void __launch_bounds__(256)
-k_interp_advance(IbmArgs a, const uint8_t* __restrict__ flags, const int32_t* __restrict__ p_cell,
+__global__ void __launch_bounds__(256, 4)
+k_interp_advance(IbmArgs a, TypeSpan ts, const uint8_t* __restrict__ flags,
                  uint8_t* alive, double* x, double* y, double* z,
                  double* vx, double* vy, double* vz, const double* __restrict__ U,
                  const uint8_t* __restrict__ hold_back, int skip_held, const uint8_t* __restrict__ far) {
-  const int64_t p = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
-  if (p >= a.np) return;
-  const int cell = p_cell[p];
-  if (!alive[cell]) return;
-  const bool chk = !(CHECK_FLAGS && far && far[cell]);   // cells with no non-fluid node within reach skip the flag look-ups
-  if (skip_held && hold_back[cell]) return;       // shared cells are interpolated by k_interp_list on the main stream
+  const int64_t q = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if (q >= ts.n) return;
+  const int64_t p = ts.first_particle + q;
+  int64_t lc = (int64_t)((double)q*ts.inv_V);                       // q / V, corrected for the rounding of the reciprocal
+  if (lc*ts.V > q) lc--; else if ((lc + 1)*ts.V <= q) lc++;
+  const int64_t cell = ts.first_cell + lc;
   double px = x[p], py = y[p], pz = z[p];
+  const uint8_t live = alive[cell];
+  const uint8_t is_far = (CHECK_FLAGS && far) ? far[cell] : 0;
+  const uint8_t held = hold_back ? hold_back[cell] : 0;
+  if (!live) return;
+  const bool chk = !(CHECK_FLAGS && is_far);      // cells with no non-fluid node within reach skip the flag look-ups
+  if (skip_held && held) return;                  // shared cells are interpolated by k_interp_list on the main stream
   double v0, v1, v2;
   if (INTERP) {
     if (interp_vertex<CHECK_FLAGS>(a, flags, U, px, py, pz, v0, v1, v2, chk)) { vx[p] = v0; vy[p] = v1; vz[p] = v2; }
     else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
   } else { v0 = vx[p]; v1 = vy[p]; v2 = vz[p]; }
-  if (ADVANCE && !(hold_back && hold_back[cell])) {
+  if (ADVANCE && !held) {
     px += v0; py += v1; pz += v2;
     x[p] = px; y[p] = py; z[p] = pz;
     // particle on a boundary node => its cell is deleted (hemoCellParticleField.cpp:572-584, 512-553)
@@ -229,52 +243,44 @@ hcg_status ibm_spread(hcg_ctx* c) {
   return HCG_OK;
 }
 
+// interpolation and / or advance of every vertex: one launch per cell type
+template <bool ADVANCE, bool INTERP>
+static hcg_status launch_interp_advance(hcg_ctx* c, cudaStream_t st, const uint8_t* hold_back, int skip_held) {
+  IbmArgs a = make_args(c);
+  for (auto& th : c->types) {
+    if (th.n_cells == 0) continue;
+    TypeSpan ts{th.first_particle, th.first_cell, th.n_cells*(int64_t)th.d.V, th.d.V, 1.0/(double)th.d.V};
+    if (c->has_nonfluid) k_interp_advance<ADVANCE, INTERP, true><<<nblk(ts.n, 256), 256, 0, st>>>(a, ts, c->flags, c->cell_alive,
+        c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, hold_back, skip_held, ibm_far(c));
+    else k_interp_advance<ADVANCE, INTERP, false><<<nblk(ts.n, 256), 256, 0, st>>>(a, ts, c->flags, c->cell_alive,
+        c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, hold_back, skip_held, ibm_far(c));
+    KERNEL_CHECK(c);
+  }
+  return HCG_OK;
+}
+
 hcg_status ibm_interpolate(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
-  IbmArgs a = make_args(c);
-  if (c->has_nonfluid) k_interp_advance<false, true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0, ibm_far(c));
-  else k_interp_advance<false, true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0, ibm_far(c));
-  KERNEL_CHECK(c);
-  return HCG_OK;
+  return launch_interp_advance<false, true>(c, c->stream, nullptr, 0);
 }
 
 hcg_status ibm_advance(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   struct FarTick { hcg_ctx* c; ~FarTick() { if (c->far_steps_left > 0) c->far_steps_left--; } } far_tick{c};
-  IbmArgs a = make_args(c);
-  if (c->has_nonfluid) k_interp_advance<true, false, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0, ibm_far(c));
-  else k_interp_advance<true, false, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0, ibm_far(c));
-  KERNEL_CHECK(c);
-  return HCG_OK;
+  return launch_interp_advance<true, false>(c, c->stream, nullptr, 0);
 }
 
 hcg_status ibm_interpolate_advance(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   struct FarTick { hcg_ctx* c; ~FarTick() { if (c->far_steps_left > 0) c->far_steps_left--; } } far_tick{c};
-  IbmArgs a = make_args(c);
-  if (c->has_nonfluid) k_interp_advance<true, true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0, ibm_far(c));
-  else k_interp_advance<true, true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, nullptr, 0, ibm_far(c));
-  KERNEL_CHECK(c);
-  return HCG_OK;
+  return launch_interp_advance<true, true>(c, c->stream, nullptr, 0);
 }
 
 hcg_status ibm_interpolate_advance_unshared(hcg_ctx* c) {
   if (c->np == 0) return HCG_OK;
   struct FarTick { hcg_ctx* c; ~FarTick() { if (c->far_steps_left > 0) c->far_steps_left--; } } far_tick{c};
   if (!c->multi.d_cell_shared) return hcg_fail(c, HCG_ERR_STATE, "shared-cell flags missing (multi_rebalance has not run)");
-  IbmArgs a = make_args(c);
-  if (c->has_nonfluid) k_interp_advance<true, true, true><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared, 0, ibm_far(c));
-  else k_interp_advance<true, true, false><<<nblk(c->np, 256), 256, 0, c->stream>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared, 0, ibm_far(c));
-  KERNEL_CHECK(c);
-  return HCG_OK;
+  return launch_interp_advance<true, true>(c, c->stream, c->multi.d_cell_shared, 0);
 }
 
 // multi-GPU overlap: (1) the shared cells on the main stream ...
@@ -294,13 +300,7 @@ hcg_status ibm_interpolate_advance_unshared_on(hcg_ctx* c, cudaStream_t st) {
   if (c->np == 0) return HCG_OK;
   struct FarTick { hcg_ctx* c; ~FarTick() { if (c->far_steps_left > 0) c->far_steps_left--; } } far_tick{c};
   if (!c->multi.d_cell_shared) return hcg_fail(c, HCG_ERR_STATE, "shared-cell flags missing (multi_rebalance has not run)");
-  IbmArgs a = make_args(c);
-  if (c->has_nonfluid) k_interp_advance<true, true, true><<<nblk(c->np, 256), 256, 0, st>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared, 1, ibm_far(c));
-  else k_interp_advance<true, true, false><<<nblk(c->np, 256), 256, 0, st>>>(a, c->flags, c->p_cell, c->cell_alive,
-      c->pos[0], c->pos[1], c->pos[2], c->vel[0], c->vel[1], c->vel[2], c->U, c->multi.d_cell_shared, 1, ibm_far(c));
-  KERNEL_CHECK(c);
-  return HCG_OK;
+  return launch_interp_advance<true, true>(c, st, c->multi.d_cell_shared, 1);
 }
 
 hcg_status ibm_advance_shared(hcg_ctx* c) {

@@ -68,12 +68,14 @@ __global__ void k_perm_identity(uint16_t* perm, int npair, int64_t total) {
 }
 
 // ---------------------------------------------------------------- spread
-// One CTA per cell.  Phase 1 (thread = vertex): force cap, the kernel's per-axis node offsets, the
-// normalisation coefficient and a mask of the corners that add to a real node -> shared memory
-// (81 B per vertex: 4 cells per SM instead of the 2 a full [8][V] weight/key table allows).
-// Phase 2 (thread = chunk of 8 consecutive node-sorted pairs): walk the chunk sequentially, rebuild the
-// pair's node and NORMALISED weight from the staged position (same expressions, same bits as phase 1),
-// merge runs of equal node in registers, one fp64 RED triple per run.
+// One CTA per cell.  Phase 1 (thread = vertex): force cap, the kernel's per-axis weights and node offsets, the
+// normalisation, a mask of the corners that add to a real node.  What phase 2 needs per (vertex, corner) pair is left in
+// shared memory FACTORISED, 96 B per vertex (three cells per SM): the packed node key {K0, dX, dY, dZ | mask << 24}
+// (node of corner (dx,dy,dz) = K0 + dx*dX + dy*dY + dz*dZ), the four products wx[dx]*wy[dy] and the six values
+// (frep + f)_k * wz[dz] / (sum of the admitted weights).  Phase 2 (thread = chunk of 8 consecutive node-sorted pairs)
+// then takes FIVE shared-memory loads per pair (one of them 128-bit) where rebuilding node and weight from the staged
+// position took eleven - the kernel is bound by shared-memory wavefronts, vertex indices being random across a warp -
+// merges runs of equal node in registers and issues one fp64 RED triple per run.
 // bulk-async staging helpers (1-D TMA path: cp.async.bulk global -> shared, completion on an mbarrier)
 __device__ __forceinline__ uint32_t sp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sp_mbar_init(uint64_t* bar, uint32_t count) {
@@ -105,7 +107,8 @@ __device__ __forceinline__ void sp_bulk_g2s(void* dst, const void* src, uint32_t
 // phase 1 no longer waits on global loads (they were ~35 % of the kernel's stall samples).  Needs V even
 // (16-byte aligned segments); otherwise the direct-load variant runs.
 template <int THREADS, bool CHECK_FLAGS, bool BULK>
-__global__ void __launch_bounds__(THREADS)
+// three cells per SM: with the registers of two (90) the kernel measured 0.45 ms instead of 0.39
+__global__ void __launch_bounds__(THREADS, 3)
 k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ alive,
                 const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                 double* fx, double* fy, double* fz,
@@ -117,14 +120,13 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
   if (!alive[cell]) return;
   const bool chk = !(CHECK_FLAGS && far && far[cell]);   // no non-fluid node within this cell's reach: skip the flag look-ups
   const int64_t base = a.first_particle + (int64_t)blockIdx.x*V;
-  double* PX = sm; double* PY = PX + V; double* PZ = PY + V;      // position
-  double* CO = PZ + V;                                             // 1 / sum of the admitted raw weights
-  double* t0 = CO + V; double* t1 = t0 + V; double* t2 = t1 + V;   // force_repulsion + capped force
-  int* J = reinterpret_cast<int*>(t2 + V);                         // [6][V] node offsets: x(d=0,1), y(d=0,1), z(d=0,1)
-  uint8_t* M = reinterpret_cast<uint8_t*>(J + 6*V);                // bit c: corner c adds to a real node of this rank
-  // BULK only: staged membrane force (3V doubles) and the mbarrier, behind M (rounded up to 16 bytes)
-  double* SF = reinterpret_cast<double*>(reinterpret_cast<char*>(sm) + (((size_t)80*V + V + 15) & ~(size_t)15));
-  uint64_t* bar = reinterpret_cast<uint64_t*>(SF + 3*V);
+  // twelve arrays of V doubles.  Slots 0-8 receive the inputs (position, repulsion force, membrane force: BULK only);
+  // every thread reads its vertex's nine values into registers before it writes that vertex's outputs over them.
+  double* IN = sm;                                                 // [9][V]  x y z  rx ry rz  fx fy fz
+  double* AB = sm;                                                 // [4][V]  wx[dx]*wy[dy] at (2*dx + dy)
+  double* TC = sm + 4*V;                                           // [2][3][V]  (frep + f)_k * wz[dz]/total at (3*dz + k)
+  int4* KV = reinterpret_cast<int4*>(sm + 10*V);                   // [V]  K0, dX, dY, dZ (low 24 bits) | corner mask << 24
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 12*V);
 
   const uint4* pp = reinterpret_cast<const uint4*>(perm + (int64_t)blockIdx.x*8*V);
   constexpr int NPRE = 3;                                          // chunks of 8 pairs prefetched per thread
@@ -135,9 +137,9 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       const uint32_t nb = (uint32_t)(V*sizeof(double));
       sp_mbar_expect_tx(bar, 9*nb);
-      sp_bulk_g2s(PX, x + base, nb, bar); sp_bulk_g2s(PY, y + base, nb, bar); sp_bulk_g2s(PZ, z + base, nb, bar);
-      sp_bulk_g2s(t0, rx + base, nb, bar); sp_bulk_g2s(t1, ry + base, nb, bar); sp_bulk_g2s(t2, rz + base, nb, bar);
-      sp_bulk_g2s(SF, fx + base, nb, bar); sp_bulk_g2s(SF + V, fy + base, nb, bar); sp_bulk_g2s(SF + 2*V, fz + base, nb, bar);
+      sp_bulk_g2s(IN, x + base, nb, bar); sp_bulk_g2s(IN + V, y + base, nb, bar); sp_bulk_g2s(IN + 2*V, z + base, nb, bar);
+      sp_bulk_g2s(IN + 3*V, rx + base, nb, bar); sp_bulk_g2s(IN + 4*V, ry + base, nb, bar); sp_bulk_g2s(IN + 5*V, rz + base, nb, bar);
+      sp_bulk_g2s(IN + 6*V, fx + base, nb, bar); sp_bulk_g2s(IN + 7*V, fy + base, nb, bar); sp_bulk_g2s(IN + 8*V, fz + base, nb, bar);
     }
 #pragma unroll
     for (int r = 0; r < NPRE; r++) { const int j = threadIdx.x + r*THREADS; if (j < V) qpre[r] = __ldg(pp + j); }
@@ -148,7 +150,8 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
   for (int v = threadIdx.x; v < V; v += THREADS) {
     const int64_t p = base + v;
     double px, py, pz, f0, f1, f2, r0, r1, r2;
-    if (BULK) { px = PX[v]; py = PY[v]; pz = PZ[v]; f0 = SF[v]; f1 = SF[V + v]; f2 = SF[2*V + v]; r0 = t0[v]; r1 = t1[v]; r2 = t2[v]; }
+    if (BULK) { px = IN[v]; py = IN[V + v]; pz = IN[2*V + v]; r0 = IN[3*V + v]; r1 = IN[4*V + v]; r2 = IN[5*V + v];
+                f0 = IN[6*V + v]; f1 = IN[7*V + v]; f2 = IN[8*V + v]; }
     else { px = x[p]; py = y[p]; pz = z[p]; f0 = fx[p]; f1 = fy[p]; f2 = fz[p]; r0 = rx[p]; r1 = ry[p]; r2 = rz[p]; }
     const double mag = sqrt(f0*f0 + f1*f1 + f2*f2);
     if (mag > a.f_limit) {                      // permanent cap (hemoCellParticleField.cpp:848-852)
@@ -184,11 +187,16 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
       total += w;
       if (realx[dx]) mask |= 1u << c;            // ghost planes count in the normalisation only
     }
-    if (!BULK) { PX[v] = px; PY[v] = py; PZ[v] = pz; }
-    CO[v] = 1.0/total;
-    t0[v] = r0 + f0; t1[v] = r1 + f1; t2[v] = r2 + f2;
-    J[v] = jx[0]; J[V + v] = jx[1]; J[2*V + v] = jy[0]; J[3*V + v] = jy[1]; J[4*V + v] = jz[0]; J[5*V + v] = jz[1];
-    M[v] = skip ? 0 : (uint8_t)mask;             // multi-GPU: a candidate node is not addressable here
+    const double co = 1.0/total;
+    const double g0 = r0 + f0, g1 = r1 + f1, g2 = r2 + f2;
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+      AB[(2*d)*V + v] = ax[d]*ay[0]; AB[(2*d + 1)*V + v] = ax[d]*ay[1];
+      const double cz = az[d]*co;
+      TC[(3*d)*V + v] = g0*cz; TC[(3*d + 1)*V + v] = g1*cz; TC[(3*d + 2)*V + v] = g2*cz;
+    }
+    const unsigned m = skip ? 0u : mask;          // multi-GPU: a candidate node is not addressable here
+    KV[v] = make_int4(jx[0] + jy[0] + jz[0], jx[1] - jx[0], jy[1] - jy[0], (int)(((unsigned)(jz[1] - jz[0]) & 0x00FFFFFFu) | (m << 24)));
   }
   __syncthreads();
 
@@ -199,15 +207,12 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
     for (int k = 0; k < 8; k++) {
       const unsigned e = (e8[k >> 1] >> ((k & 1)*16)) & 0xFFFFu;
       const int v = e >> 3, c = e & 7;
-      if (!((M[v] >> c) & 1u)) continue;
-      const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
-      const int key = J[dx*V + v] + J[(2 + dy)*V + v] + J[(4 + dz)*V + v];
-      const double px = PX[v], py = PY[v], pz = PZ[v];
-      const double wx = sp_phi2(px - (double)((int)floor(px) + dx));
-      const double wy = sp_phi2(py - (double)((int)floor(py) + dy));
-      const double wz = sp_phi2(pz - (double)((int)floor(pz) + dz));
-      const double w = (wx*wy*wz)*CO[v];
-      const double v0 = t0[v]*w, v1 = t1[v]*w, v2 = t2[v]*w;
+      const int4 kv = KV[v];
+      if (!(((unsigned)kv.w >> (24 + c)) & 1u)) continue;
+      const int key = kv.x + ((c & 4) ? kv.y : 0) + ((c & 2) ? kv.z : 0) + ((c & 1) ? ((int)((unsigned)kv.w << 8) >> 8) : 0);
+      const double ab = AB[(c >> 1)*V + v];
+      const double* tc = TC + (3*(c & 1))*V + v;
+      const double v0 = tc[0]*ab, v1 = tc[V]*ab, v2 = tc[2*V]*ab;
       if (key != cur) {
         if (cur >= 0) { double* Fn = F + 4*(int64_t)cur; atomicAdd(Fn, a0); atomicAdd(Fn + 1, a1); atomicAdd(Fn + 2, a2); }
         cur = key; a0 = v0; a1 = v1; a2 = v2;
@@ -266,8 +271,7 @@ hcg_status spread_sorted(hcg_ctx* c) {
     SpArgs a = make_args(c, th);
     const int V = th.d.V;
     const bool bulk = bulk_env && (V % 2 == 0) && (th.first_particle % 2 == 0) && V >= 256;
-    const size_t core = (((size_t)80*V + V + 15) & ~(size_t)15);
-    const size_t smem = bulk ? core + sizeof(double)*3*V + 16 : core + 16;
+    const size_t smem = sizeof(double)*12*(size_t)V + 16;
     const bool chk = c->has_nonfluid;
 #define SP_LAUNCH(T, C, B) do { \
       CUDA_TRY(c, cudaFuncSetAttribute(k_spread_sorted<T, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
