@@ -70,12 +70,12 @@ __global__ void k_perm_identity(uint16_t* perm, int npair, int64_t total) {
 // ---------------------------------------------------------------- spread
 // One CTA per cell.  Phase 1 (thread = vertex): force cap, the kernel's per-axis weights and node offsets, the
 // normalisation, a mask of the corners that add to a real node.  What phase 2 needs per (vertex, corner) pair is left in
-// shared memory FACTORISED, 96 B per vertex (three cells per SM): the packed node key {K0, dX, dY, dZ | mask << 24}
-// (node of corner (dx,dy,dz) = K0 + dx*dX + dy*dY + dz*dZ), the four products wx[dx]*wy[dy] and the six values
-// (frep + f)_k * wz[dz] / (sum of the admitted weights).  Phase 2 (thread = chunk of 8 consecutive node-sorted pairs)
-// then takes FIVE shared-memory loads per pair (one of them 128-bit) where rebuilding node and weight from the staged
-// position took eleven - the kernel is bound by shared-memory wavefronts, vertex indices being random across a warp -
-// merges runs of equal node in registers and issues one fp64 RED triple per run.
+// shared memory FACTORISED, 80 B per vertex (four cells per SM): the node key K0 of the lower corner with a word of flags
+// (corner mask; per axis, whether the upper corner wraps around a periodic axis instead of lying one stride on), the four
+// products wx[dx]*wy[dy], the two wz[dz] / (sum of the admitted weights) and the three (frep + f)_k.  Phase 2 (thread =
+// chunk of 8 consecutive node-sorted pairs) then takes SIX 64-bit shared-memory loads per pair where rebuilding node and
+// weight from the staged position took eleven - the kernel is bound by shared-memory wavefronts and their latency, vertex
+// indices being random across a warp - merges runs of equal node in registers and issues one fp64 RED triple per run.
 // bulk-async staging helpers (1-D TMA path: cp.async.bulk global -> shared, completion on an mbarrier)
 __device__ __forceinline__ uint32_t sp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sp_mbar_init(uint64_t* bar, uint32_t count) {
@@ -108,7 +108,7 @@ __device__ __forceinline__ void sp_bulk_g2s(void* dst, const void* src, uint32_t
 // (16-byte aligned segments); otherwise the direct-load variant runs.
 template <int THREADS, bool CHECK_FLAGS, bool BULK>
 // three cells per SM: with the registers of two (90) the kernel measured 0.45 ms instead of 0.39
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, 4)
 k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ alive,
                 const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                 double* fx, double* fy, double* fz,
@@ -124,9 +124,13 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
   // every thread reads its vertex's nine values into registers before it writes that vertex's outputs over them.
   double* IN = sm;                                                 // [9][V]  x y z  rx ry rz  fx fy fz
   double* AB = sm;                                                 // [4][V]  wx[dx]*wy[dy] at (2*dx + dy)
-  double* TC = sm + 4*V;                                           // [2][3][V]  (frep + f)_k * wz[dz]/total at (3*dz + k)
-  int4* KV = reinterpret_cast<int4*>(sm + 10*V);                   // [V]  K0, dX, dY, dZ (low 24 bits) | corner mask << 24
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 12*V);
+  double* G = sm + 4*V;                                            // [3][V]  (frep + f)_k
+  double* CZ = sm + 7*V;                                           // [2][V]  wz[dz]/total
+  int2* KV = reinterpret_cast<int2*>(sm + 9*V);                    // [V]  K0 ; corner mask | wrap flags of the x, y, z offsets << 8
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 10*V);
+  // node of corner (dx, dy, dz) = K0 + dx*(DX or WX) + dy*(DY or WY) + dz*(1 or WZ): the offset of the upper corner along an
+  // axis is the plane / row / node stride, or the way back to the start of a periodic axis
+  const int DX = a.ny*a.nz, WX = (1 - a.nxl)*DX, DY = a.nz, WY = -(a.ny - 1)*a.nz, WZ = -(a.nz - 1);
 
   const uint4* pp = reinterpret_cast<const uint4*>(perm + (int64_t)blockIdx.x*8*V);
   constexpr int NPRE = 3;                                          // chunks of 8 pairs prefetched per thread
@@ -188,15 +192,19 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
       if (realx[dx]) mask |= 1u << c;            // ghost planes count in the normalisation only
     }
     const double co = 1.0/total;
-    const double g0 = r0 + f0, g1 = r1 + f1, g2 = r2 + f2;
+    G[v] = r0 + f0; G[V + v] = r1 + f1; G[2*V + v] = r2 + f2;
 #pragma unroll
     for (int d = 0; d < 2; d++) {
       AB[(2*d)*V + v] = ax[d]*ay[0]; AB[(2*d + 1)*V + v] = ax[d]*ay[1];
-      const double cz = az[d]*co;
-      TC[(3*d)*V + v] = g0*cz; TC[(3*d + 1)*V + v] = g1*cz; TC[(3*d + 2)*V + v] = g2*cz;
+      CZ[d*V + v] = az[d]*co;
     }
-    const unsigned m = skip ? 0u : mask;          // multi-GPU: a candidate node is not addressable here
-    KV[v] = make_int4(jx[0] + jy[0] + jz[0], jx[1] - jx[0], jy[1] - jy[0], (int)(((unsigned)(jz[1] - jz[0]) & 0x00FFFFFFu) | (m << 24)));
+    // lower x corner not addressable (left of a non-periodic domain): its plane is the virtual one below the upper corner's
+    const int kx0 = ax[0] != 0.0 ? jx[0] : jx[1] - DX;
+    unsigned fl = skip ? 0u : mask;               // multi-GPU: a candidate node is not addressable here
+    if (ax[1] != 0.0 && jx[1] - kx0 != DX) { if (jx[1] - kx0 != WX) __trap(); fl |= 1u << 8; }   // (no third plane offset exists)
+    if (jy[1] - jy[0] != DY) fl |= 1u << 9;
+    if (jz[1] - jz[0] != 1) fl |= 1u << 10;
+    KV[v] = make_int2(kx0 + jy[0] + jz[0], (int)fl);
   }
   __syncthreads();
 
@@ -207,12 +215,13 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
     for (int k = 0; k < 8; k++) {
       const unsigned e = (e8[k >> 1] >> ((k & 1)*16)) & 0xFFFFu;
       const int v = e >> 3, c = e & 7;
-      const int4 kv = KV[v];
-      if (!(((unsigned)kv.w >> (24 + c)) & 1u)) continue;
-      const int key = kv.x + ((c & 4) ? kv.y : 0) + ((c & 2) ? kv.z : 0) + ((c & 1) ? ((int)((unsigned)kv.w << 8) >> 8) : 0);
-      const double ab = AB[(c >> 1)*V + v];
-      const double* tc = TC + (3*(c & 1))*V + v;
-      const double v0 = tc[0]*ab, v1 = tc[V]*ab, v2 = tc[2*V]*ab;
+      const int2 kv = KV[v];
+      const unsigned fl = (unsigned)kv.y;
+      if (!((fl >> c) & 1u)) continue;
+      const int key = kv.x + ((c & 4) ? ((fl & 0x100u) ? WX : DX) : 0) + ((c & 2) ? ((fl & 0x200u) ? WY : DY) : 0)
+                           + ((c & 1) ? ((fl & 0x400u) ? WZ : 1) : 0);
+      const double w = AB[(c >> 1)*V + v]*CZ[(c & 1)*V + v];
+      const double v0 = G[v]*w, v1 = G[V + v]*w, v2 = G[2*V + v]*w;
       if (key != cur) {
         if (cur >= 0) { double* Fn = F + 4*(int64_t)cur; atomicAdd(Fn, a0); atomicAdd(Fn + 1, a1); atomicAdd(Fn + 2, a2); }
         cur = key; a0 = v0; a1 = v1; a2 = v2;
@@ -271,7 +280,7 @@ hcg_status spread_sorted(hcg_ctx* c) {
     SpArgs a = make_args(c, th);
     const int V = th.d.V;
     const bool bulk = bulk_env && (V % 2 == 0) && (th.first_particle % 2 == 0) && V >= 256;
-    const size_t smem = sizeof(double)*12*(size_t)V + 16;
+    const size_t smem = sizeof(double)*10*(size_t)V + 16;
     const bool chk = c->has_nonfluid;
 #define SP_LAUNCH(T, C, B) do { \
       CUDA_TRY(c, cudaFuncSetAttribute(k_spread_sorted<T, C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
