@@ -3,7 +3,7 @@
 #include "ctx.cuh"
 #include <nccl.h>
 #include <algorithm>
-#include <unordered_map>
+#include "mech_tables.h"
 #include <cstring>
 #include <cstdio>
 #include <cstdlib>
@@ -545,7 +545,6 @@ hcg_status hcg_celltype_add(hcg_ctx* c, const hcg_celltype* t, int32_t* ctype_ou
   if (t->model != HCG_MODEL_RBC_HIGHORDER && t->model != HCG_MODEL_PLT_SIMPLE && t->model != HCG_MODEL_HOST) return hcg_fail(c, HCG_ERR_ARG, "unknown model");
   const int V = t->n_vertices, T = t->n_triangles, E = t->n_edges, I = t->n_inner_edges;
   if (V < 4 || T < 4 || E < 6 || I < 0) return hcg_fail(c, HCG_ERR_ARG, "degenerate mesh");
-  if (V > 65535 || E > 65534 || T > 65534) return hcg_fail(c, HCG_ERR_CAPACITY, "mesh too large for the packed gather tables");
   // ---- per-vertex gather tables
   std::vector<int> vt(6*(size_t)V, -1), vpe(12*(size_t)V, -1), vin(4*(size_t)V, -1);
   std::vector<int> nvt(V, 0), nvpe(V, 0), nvin(V, 0);
@@ -567,40 +566,11 @@ hcg_status hcg_celltype_add(hcg_ctx* c, const hcg_celltype* t, int32_t* ctype_ou
       if (r < 0 || r >= V || r == v) return hcg_fail(c, HCG_ERR_ARG, "ring vertex out of range");
     }
   }
-  // RBC: one packed word per (ring slot j, vertex) - the ring vertex r_j, the edge (v, r_j), the triangle (v, r_j, r_j+1),
-  // the ring size of r_j, which of (v, r_j, r_j+1) is the triangle's third vertex (its centroid sum is rebuilt in the
-  // reference's order) and whether (v, r_j, r_j+1) runs against the triangle's orientation.  Slots past the ring size
-  // repeat r_0 with the null edge E, the null triangle T and ring size 0: they add +0.0.
+  // RBC: the packed ring table of the mechanics kernel (mech_tables.h)
   std::vector<unsigned long long> rg(6*(size_t)V, 0ull);
   if (t->model == HCG_MODEL_RBC_HIGHORDER) {
-    std::unordered_map<unsigned long long, int> emap, tmap;
-    auto ekey = [](int x, int y) { if (x > y) std::swap(x, y); return ((unsigned long long)x << 20) | (unsigned long long)y; };
-    auto tkey = [](int x, int y, int z) { int q[3] = {x, y, z}; std::sort(q, q + 3);
-                                          return ((unsigned long long)q[0] << 40) | ((unsigned long long)q[1] << 20) | (unsigned long long)q[2]; };
-    for (int e = 0; e < E; e++) emap[ekey(t->edges[2*e], t->edges[2*e+1])] = e;
-    for (int k = 0; k < T; k++) tmap[tkey(t->triangles[3*k], t->triangles[3*k+1], t->triangles[3*k+2])] = k;
-    for (int v = 0; v < V; v++) {
-      const int nn = t->vertex_n_vertexes[v];
-      const int* ring = t->vertex_vertexes + 6*v;
-      for (int j = 0; j < 6; j++) {
-        unsigned long long w;
-        if (j < nn) {
-          const int ia = ring[j], ib = ring[(j + 1) % nn];
-          auto ei = emap.find(ekey(v, ia));
-          auto ti = tmap.find(tkey(v, ia, ib));
-          if (ei == emap.end()) return hcg_fail(c, HCG_ERR_ARG, "ring neighbour without an edge");
-          if (ti == tmap.end()) return hcg_fail(c, HCG_ERR_ARG, "consecutive ring neighbours without a triangle");
-          const int* q = t->triangles + 3*ti->second;
-          const int last = q[2] == v ? 0 : (q[2] == ia ? 1 : 2);
-          const bool same = (q[0] == v && q[1] == ia) || (q[0] == ia && q[1] == ib) || (q[0] == ib && q[1] == v);
-          w = (unsigned long long)ia | ((unsigned long long)ei->second << 16) | ((unsigned long long)ti->second << 32) |
-              ((unsigned long long)t->vertex_n_vertexes[ia] << 48) | ((unsigned long long)last << 51) | ((unsigned long long)(same ? 0 : 1) << 53);
-        } else {
-          w = (unsigned long long)ring[0] | ((unsigned long long)E << 16) | ((unsigned long long)T << 32);
-        }
-        rg[(size_t)j*V + v] = w;
-      }
-    }
+    if (const char* why = mech_tables::build_ring_table(V, T, E, t->triangles, t->edges, t->vertex_vertexes, t->vertex_n_vertexes, rg))
+      return hcg_fail(c, HCG_ERR_ARG, why);
   }
   if (t->model == HCG_MODEL_PLT_SIMPLE) {
     for (int e = 0; e < E; e++) {
