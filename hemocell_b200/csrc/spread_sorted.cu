@@ -15,7 +15,7 @@
 #include <climits>
 #include <cstdlib>
 
-#include "spread_node.cuh"   // SpArgs, sp_local_x, sp_wrap, sp_phi2, corner_node (host + device)
+#include "spread_node.cuh"   // SpArgs, sp_local_x, sp_wrap, sp_phi2, sp_stage_vertex, sp_pair_node (host + device)
 
 namespace {
 
@@ -128,9 +128,7 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
   double* CZ = sm + 7*V;                                           // [2][V]  wz[dz]/total
   int2* KV = reinterpret_cast<int2*>(sm + 9*V);                    // [V]  K0 ; corner mask | wrap flags of the x, y, z offsets << 8
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 10*V);
-  // node of corner (dx, dy, dz) = K0 + dx*(DX or WX) + dy*(DY or WY) + dz*(1 or WZ): the offset of the upper corner along an
-  // axis is the plane / row / node stride, or the way back to the start of a periodic axis
-  const int DX = a.ny*a.nz, WX = (1 - a.nxl)*DX, DY = a.nz, WY = -(a.ny - 1)*a.nz, WZ = -(a.nz - 1);
+  const SpStrides st = sp_strides(a);
 
   const uint4* pp = reinterpret_cast<const uint4*>(perm + (int64_t)blockIdx.x*8*V);
   constexpr int NPRE = 3;                                          // chunks of 8 pairs prefetched per thread
@@ -163,48 +161,12 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
       f0 *= s; f1 *= s; f2 *= s;
       fx[p] = f0; fy[p] = f1; fz[p] = f2;
     }
-    bool skip = false;
-    const int bx = (int)floor(px), by = (int)floor(py), bz = (int)floor(pz);
-    double ax[2], ay[2], az[2]; int jx[2], jy[2], jz[2]; bool realx[2];
-#pragma unroll
-    for (int d = 0; d < 2; d++) {
-      ax[d] = sp_phi2(px - (double)(bx + d)); jx[d] = 0; realx[d] = false;
-      if (ax[d] != 0.0) {
-        int lx; bool out;
-        if (sp_local_x(bx + d, a, lx, out)) { jx[d] = lx*a.ny*a.nz; realx[d] = lx >= 1 && lx <= a.nxl; }
-        else { ax[d] = 0.0; if (!out) skip = true; }
-      }
-      ay[d] = sp_phi2(py - (double)(by + d)); int yy = by + d;
-      if (ay[d] != 0.0 && !sp_wrap(yy, a.ny, a.py)) ay[d] = 0.0;
-      jy[d] = yy*a.nz;
-      az[d] = sp_phi2(pz - (double)(bz + d)); int zz = bz + d;
-      if (az[d] != 0.0 && !sp_wrap(zz, a.nz, a.pz)) az[d] = 0.0;
-      jz[d] = zz;
-    }
-    double total = 0.0; unsigned mask = 0;
-#pragma unroll
-    for (int c = 0; c < 8; c++) {               // corner order == the reference's x-outer / z-inner order
-      const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
-      const double w = ax[dx]*ay[dy]*az[dz];
-      if (w == 0.0) continue;
-      if (CHECK_FLAGS && chk && flags[jx[dx] + jy[dy] + jz[dz]] != HCG_FLUID) continue;
-      total += w;
-      if (realx[dx]) mask |= 1u << c;            // ghost planes count in the normalisation only
-    }
-    const double co = 1.0/total;
+    SpVertex sv;
+    sp_stage_vertex<CHECK_FLAGS>(a, st, flags, chk, px, py, pz, sv);
     G[v] = r0 + f0; G[V + v] = r1 + f1; G[2*V + v] = r2 + f2;
 #pragma unroll
-    for (int d = 0; d < 2; d++) {
-      AB[(2*d)*V + v] = ax[d]*ay[0]; AB[(2*d + 1)*V + v] = ax[d]*ay[1];
-      CZ[d*V + v] = az[d]*co;
-    }
-    // lower x corner not addressable (left of a non-periodic domain): its plane is the virtual one below the upper corner's
-    const int kx0 = ax[0] != 0.0 ? jx[0] : jx[1] - DX;
-    unsigned fl = skip ? 0u : mask;               // multi-GPU: a candidate node is not addressable here
-    if (ax[1] != 0.0 && jx[1] - kx0 != DX) { if (jx[1] - kx0 != WX) __trap(); fl |= 1u << 8; }   // (no third plane offset exists)
-    if (jy[1] - jy[0] != DY) fl |= 1u << 9;
-    if (jz[1] - jz[0] != 1) fl |= 1u << 10;
-    KV[v] = make_int2(kx0 + jy[0] + jz[0], (int)fl);
+    for (int d = 0; d < 2; d++) { AB[(2*d)*V + v] = sv.ab[2*d]; AB[(2*d + 1)*V + v] = sv.ab[2*d + 1]; CZ[d*V + v] = sv.cz[d]; }
+    KV[v] = make_int2(sv.k0, (int)sv.fl);
   }
   __syncthreads();
 
@@ -216,10 +178,8 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
       const unsigned e = (e8[k >> 1] >> ((k & 1)*16)) & 0xFFFFu;
       const int v = e >> 3, c = e & 7;
       const int2 kv = KV[v];
-      const unsigned fl = (unsigned)kv.y;
-      if (!((fl >> c) & 1u)) continue;
-      const int key = kv.x + ((c & 4) ? ((fl & 0x100u) ? WX : DX) : 0) + ((c & 2) ? ((fl & 0x200u) ? WY : DY) : 0)
-                           + ((c & 1) ? ((fl & 0x400u) ? WZ : 1) : 0);
+      int key;
+      if (!sp_pair_node(st, kv.x, (unsigned)kv.y, c, key)) continue;
       const double w = AB[(c >> 1)*V + v]*CZ[(c & 1)*V + v];
       const double v0 = G[v]*w, v1 = G[V + v]*w, v2 = G[2*V + v]*w;
       if (key != cur) {

@@ -29,19 +29,21 @@ extern "C" int ibm_kernel_host(int nx, int ny, int nz, const int* periodic, int 
   return ibm_kernel<true>(a, flags, p3[0], p3[1], p3[2], node, w);
 }
 
-// the 8 (vertex, corner) pairs of one particle as the node-sorted spreading kernels rebuild them (spread_sorted.cu: corner_node):
-// valid[c], node[c] (local padded index), weight[c] (raw, not normalised); returns 1 if some corner is not addressable from this slab
-extern "C" int spread_corners_host(int nx, int ny, int nz, const int* periodic, int x0, int nxl, int nranks,
-                                   const uint8_t* flags, const double* p3, uint8_t* valid, int64_t* node, double* weight) {
+// the 8 (vertex, corner) pairs of one particle as k_spread_sorted sees them: phase 1 stages the vertex (sp_stage_vertex), phase 2 reads
+// node and normalised weight of a corner back (sp_pair_node, ab * cz).  valid[c]: the corner adds to a REAL node of this slab
+// (ghost-plane corners count in the normalisation only); returns the staged flag word.
+extern "C" unsigned spread_corners_host(int nx, int ny, int nz, const int* periodic, int x0, int nxl, int nranks,
+                                        const uint8_t* flags, const double* p3, uint8_t* valid, int64_t* node, double* weight) {
   SpArgs a;
   a.nx = nx; a.ny = ny; a.nz = nz; a.px = periodic[0]; a.py = periodic[1]; a.pz = periodic[2];
   a.nxl = nxl; a.x0 = x0; a.nranks = nranks; a.P = (int64_t)ny*nz; a.f_limit = 1e300; a.V = 1; a.first_cell = 0; a.first_particle = 0;
-  int any_unaddressable = 0;
+  const SpStrides st = sp_strides(a);
+  SpVertex sv;
+  sp_stage_vertex<true>(a, st, flags, true, p3[0], p3[1], p3[2], sv);
   for (int c = 0; c < 8; c++) {
-    int nd = -1; double w = 0.0; bool un = false;
-    const bool ok = corner_node(a, flags, p3[0], p3[1], p3[2], c, nd, w, un);
-    valid[c] = ok; node[c] = nd; weight[c] = w;
-    if (un) any_unaddressable = 1;
+    int nd = -1;
+    valid[c] = sp_pair_node(st, sv.k0, sv.fl, c, nd);
+    node[c] = nd; weight[c] = valid[c] ? sv.ab[c >> 1]*sv.cz[c & 1] : 0.0;
   }
-  return any_unaddressable;
+  return sv.fl;
 }
