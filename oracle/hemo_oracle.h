@@ -11,10 +11,11 @@
  * per-operator golden vectors.  This file is a plain-C
  * restatement of the reference algorithm, each function citing the reference
  * file:line it follows.  What *is* pinned (tests/test_oracle_known_answers.py):
- * the reference's stretchCell CI gate run with this oracle, its diameter / volume / surface
- * windows unwidened (scripts/ci/stretchCell_sanity.sh:6-33), the V/T/E counts, and the
- * stretch-cell force-displacement bounds
- * (tests/validation/stretch_cell/test_stretch_cell.cpp:158-162).  The Zou-He velocity / pressure
+ * the reference's two CI gates and two validation tests run with this oracle, their windows
+ * unwidened - stretchCell diameter / volume / surface (scripts/ci/stretchCell_sanity.sh:6-33),
+ * pipeflow cell count / apparent viscosity / particle force (scripts/ci/pipeflow_sanity.sh:6-22,
+ * tests/validation/pipeflow/test_pipeflow.cpp:88-106), the stretch-cell force-displacement bounds
+ * (tests/validation/stretch_cell/test_stretch_cell.cpp:158-162) - and the V/T/E counts.  The Zou-He velocity / pressure
  * nodes (Palabos code, not in the tree) are pinned by physics instead: imposed density and
  * momentum reproduced to 1e-14, plane Poiseuille flow within 2 %, flux continuity through the
  * pre-inlet coupling (tests/test_preinlet_oracle.py).

@@ -255,3 +255,53 @@ def test_stretchCell_ci_windows_hold_for_the_oracle():
         assert 129.34 < surf < 133.04, rows
     # the same run on the GPU through the reference's unmodified stretchCell binary logs 129.343 um^2 and 81.125 um^3 at iteration 100
     assert abs(rows[0][4] - 129.343) < 2e-3 and abs(rows[0][2] - 81.125) < 2e-3, rows[0]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples/pipeflow"), reason="reference tree not present (authoring container only)")
+def test_pipeflow_ci_and_validation_gates_hold_for_the_oracle():
+    """scripts/ci/pipeflow_sanity.sh:6-22 with scripts/ci/config-pipeflow.xml, which is also the setting of the reference's
+    validation test (tests/validation/pipeflow/test_pipeflow.cpp:60-106): examples/pipeflow/tube.stl voxelised at refDirN 50,
+    x periodic, the shipped RBC.pos / PLT.pos, 10 warm-up steps of the bare fluid, body force 8 nu (u_max / 2) / R^2 at Re 0.5
+    (examples/pipeflow/pipeflow.cpp:51-146, mechanics/constantConversion.cpp:61-73), material every 20 and velocity every 5
+    steps, 1000 iterations - run with the CPU oracle.  The reference accepts a build only if 42 cells are present at every
+    measurement, the relative apparent viscosity 0.5 u_max / <|u|> stays inside (1.03, 3.0) and the particle force stays below
+    4 pN (the CI script tests the maximum, the validation test the mean).  The windows are the reference's own.  The lattice
+    comes from the product's host-side STL voxeliser (CPU code); everything per time step is the oracle."""
+    from hemocell_b200 import lib as H
+    ref = "/root/reference/examples/pipeflow"
+    fl, _ = H.voxelize_stl(ref + "/tube.stl", 50, 1)
+    par = M.Parameters(dx=5e-7, dt=1e-7)
+    radius = np.sqrt(int((fl[0] == 0).sum()) / np.pi)
+    u_max = 0.5 * par.nu_lbm / (2 * radius)
+    body = (8 * par.nu_lbm * (u_max * 0.5) / radius / radius, 0.0, 0.0)
+    dom = O.make_domain(*fl.shape, (1, 0, 0), par.tau)
+    flf = np.ascontiguousarray(fl.reshape(-1))
+    O.set_parallel(True)                                   # OpenMP over nodes / particles; the windows do not depend on the order
+    try:
+        sim = O.OracleSim(dom, flf, par.f_limit, body)
+        for _ in range(10):
+            O.collide_and_stream(dom, flf, sim.pop, sim.force, sim.scratch)
+        rbc, plt = O.rbc_celltype(par), O.plt_celltype(par)
+        sim.add_celltype(rbc, 20); sim.add_celltype(plt, 20); sim.vel_timescale = 5
+        rr, pr = H.read_pos(ref + "/RBC.pos"), H.read_pos(ref + "/PLT.pos")
+        # the 0.5 um minimum wall distance of the case file is stored in an unsigned int and therefore 0 (core/hemoCellField.h:64)
+        pos, ids = M.place_cells(rbc.verts, rr, par.dx, fl.shape, flf, 0.0)
+        sim.add_cells(0, pos, ids)
+        pos, ids = M.place_cells(plt.verts, pr, par.dx, fl.shape, flf, 0.0, cell_id0=len(rr))
+        sim.add_cells(1, pos, ids)
+        rows = []
+        for _ in range(1000):
+            sim.iterate()
+            assert len(sim.ctype) == 42
+            if sim.iter % 100 == 0:
+                _, vel = O.moments(dom, flf, sim.pop, sim.force)
+                speed = np.sqrt((vel.reshape(3, -1) ** 2).sum(0))[flf == 0]
+                f_pn = np.sqrt(((sim.pforce + sim.frep) ** 2).sum(1)) * par.df * 1e12
+                rows.append((sim.iter, 0.5 * u_max / speed.mean(), f_pn.max(), f_pn.mean()))
+    finally:
+        O.set_parallel(False)
+    assert len(rows) == 10
+    for it, visc, fmax, fmean in rows:
+        assert 1.03 < visc < 3.0, rows
+        assert fmax < 4.0 and fmean < 4.0, rows
+    assert rows[0][1] > rows[-1][1] and rows[-1][1] < 1.05            # the suspension relaxes towards its steady viscosity
