@@ -161,9 +161,9 @@ k_spread_sorted(SpArgs a, const uint8_t* __restrict__ flags, const uint8_t* __re
       f0 *= s; f1 *= s; f2 *= s;
       fx[p] = f0; fy[p] = f1; fz[p] = f2;
     }
+    G[v] = r0 + f0; G[V + v] = r1 + f1; G[2*V + v] = r2 + f2;     // (stored first: six values less to keep across the staging)
     SpVertex sv;
     sp_stage_vertex<CHECK_FLAGS>(a, st, flags, chk, px, py, pz, sv);
-    G[v] = r0 + f0; G[V + v] = r1 + f1; G[2*V + v] = r2 + f2;
 #pragma unroll
     for (int d = 0; d < 2; d++) { AB[(2*d)*V + v] = sv.ab[2*d]; AB[(2*d + 1)*V + v] = sv.ab[2*d + 1]; CZ[d*V + v] = sv.cz[d]; }
     KV[v] = make_int2(sv.k0, (int)sv.fl);
