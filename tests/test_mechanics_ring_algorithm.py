@@ -49,8 +49,9 @@ def ring_table(L, ct):
     return dict(ring=f(0, 0xffff), edge=f(16, 0xffff), tri=f(32, 0xffff), nn=f(48, 7), last=f(51, 3), neg=f(53, 1))
 
 
-def test_ring_table_names_the_right_elements(lib):
-    ct = O.rbc_celltype(M.Parameters(dx=0.5e-6, dt=1e-7))
+@pytest.mark.parametrize("min_triangles", [600, 200])          # 642 / 1280 / 1920 and the coarser 162 / 320 / 480 mesh
+def test_ring_table_names_the_right_elements(lib, min_triangles):
+    ct = O.rbc_celltype(M.Parameters(dx=0.5e-6, dt=1e-7), dict(M.RBC_MATERIAL, minNumTriangles=min_triangles))
     a = ct._arrs
     tri, edges, vv, nvv = a['triangles'], a['edges'], a['vv'].reshape(-1, 6), a['nvv']
     V, T, E = ct.V, len(tri), len(edges)
